@@ -1,0 +1,254 @@
+/* serac_b200 C ABI -- the drop-in boundary for the serac::Functional evaluation hot path on B200 (sm_100a).
+ *
+ * Every entry point replaces one piece of the reference's Functional machinery (file:line cited per function; paths
+ * are relative to the reference checkout, F/ = src/serac/numerics/functional/).  Plain pointers and sizes only: no
+ * C++ or torch types cross this boundary.  Pointers named *_dev are CUDA device pointers; *_host are host pointers.
+ * All functions return 0 on success and a non-zero code on failure; sb_last_error() describes the last failure on the
+ * calling thread.  (The reference has no return codes -- it aborts through SLIC_ERROR_ROOT, F/functional.hpp:77-98 --
+ * so a C++ wrapper turns non-zero into the same abort.)  `stream` is a cudaStream_t passed as void* (NULL = default
+ * stream).  Work is enqueued asynchronously unless a host buffer is involved.
+ *
+ * There is no CPU fallback: if no CUDA device is usable every compute entry point fails with SB_ERR_CUDA.
+ */
+#ifndef SERAC_B200_H
+#define SERAC_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SB_OK 0
+#define SB_ERR_INVALID 1 /* bad argument / unsupported combination */
+#define SB_ERR_CUDA 2    /* CUDA runtime error (text in sb_last_error) */
+#define SB_ERR_NOT_FOUND 3 /* unknown named integrand */
+
+/* geometry ids = mfem::Geometry::Type values */
+#define SB_GEOM_SEGMENT 1
+#define SB_GEOM_TRIANGLE 2
+#define SB_GEOM_SQUARE 3
+#define SB_GEOM_TETRAHEDRON 4
+#define SB_GEOM_CUBE 5
+
+/* mfem::Ordering::Type values (F/element_restriction.cpp:425-432) */
+#define SB_ORDERING_BYNODES 0
+#define SB_ORDERING_BYVDIM 1
+
+#define SB_MAX_TRIALS 6
+#define SB_NO_DIFFERENTIATION (-1)
+
+typedef struct sb_restriction_s* sb_restriction_t;
+typedef struct sb_integral_s*    sb_integral_t;
+typedef struct sb_csr_s*         sb_csr_t;
+typedef struct sb_functional_s*  sb_functional_t;
+typedef struct sb_halo_s*        sb_halo_t;
+
+int         sb_version(void);
+const char* sb_last_error(void);
+/* number of kernels this library has launched since load / since the last reset (bench.py's gpu_launches) */
+long long sb_launch_count(void);
+void      sb_launch_count_reset(void);
+void      sb_count_launch(void); /* called by kernel-table launchers (serac_b200/kernel_table.cuh) */
+
+/* ---------------------------------------------------------------------------------------------------------------
+ * ElementRestriction  (F/element_restriction.hpp:150-215, F/element_restriction.cpp:392-467)
+ * ------------------------------------------------------------------------------------------------------------- */
+
+/* Build dof_info(e,k) for H1 elements from the host library's native element dofs: applies the native ->
+ * lexicographic permutation of the tensor-product / simplex element, F/element_restriction.cpp:7-65,216-277.
+ * native_dofs_host: [num_elements][ndof] in mfem FiniteElementSpace::GetElementDofs order.
+ * dof_info_host (out): [num_elements][ndof] packed 64-bit DoF words (F/element_restriction.hpp:31-80:
+ * bits 0-47 index, 60-62 orientation, 63 sign). */
+int sb_h1_lexicographic_dof_info(int geom, int p, const int* native_dofs_host, int64_t num_elements,
+                                 uint64_t* dof_info_host);
+/* the permutation itself: lex_perm[k] = native position of lexicographic node k (ndof entries) */
+int sb_h1_lexicographic_permutation(int geom, int p, int* lex_perm_host);
+
+/* ElementRestriction ctor (F/element_restriction.cpp:392-404): takes ownership of a device copy of the table and
+ * builds the transposed (L-dof -> E-slots) CSR used by the deterministic scatter. */
+int sb_restriction_create(const uint64_t* dof_info_host, int64_t num_elements, int nodes_per_elem, int components,
+                          int64_t num_nodes, int ordering, sb_restriction_t* out);
+int sb_restriction_destroy(sb_restriction_t r);
+int64_t sb_restriction_esize(sb_restriction_t r); /* ESize(), F/element_restriction.cpp:421 */
+int64_t sb_restriction_lsize(sb_restriction_t r); /* LSize(), F/element_restriction.cpp:423 */
+/* device int32 table [num_elements][nodes_per_elem] of scalar node ids (what the fused kernels read) */
+int sb_restriction_table_dev(sb_restriction_t r, const int** table_dev);
+/* Gather L -> E (F/element_restriction.cpp:443-454): E[(e*c + comp)*npe + k] = L[vdof(dof_info(e,k), comp)] */
+int sb_restriction_gather(sb_restriction_t r, const double* L_dev, double* E_dev, void* stream);
+/* ScatterAdd E -> L (F/element_restriction.cpp:456-467): L[vdof] += E[...]; deterministic, no atomics: each L entry
+ * sums its E slots in ascending slot order, which is the reference's element-major order, so results are bit-exact. */
+int sb_restriction_scatter_add(sb_restriction_t r, const double* E_dev, double* L_dev, void* stream);
+/* same, but L = sum (overwrites L instead of accumulating; saves the zero-fill of output_L, F/functional.hpp:456) */
+int sb_restriction_scatter(sb_restriction_t r, const double* E_dev, double* L_dev, void* stream);
+
+/* ---------------------------------------------------------------------------------------------------------------
+ * GeometricFactors  (F/geometric_factors.cpp:16-138)
+ * X_q_dev: [ne][sdim][nq]; J_q_dev: [ne][gdim][sdim][nq] with J(j,i,q) = dX_i/dxi_j.
+ * nodes_L_dev: mesh nodes L-vector (vdim = spatial dim) restricted by `mesh_restriction`.
+ * elements_dev: the domain's element ids (NULL = all elements 0..ne-1).
+ * ------------------------------------------------------------------------------------------------------------- */
+int sb_geometric_factors(int geom, int mesh_order, int q, sb_restriction_t mesh_restriction,
+                         const double* nodes_L_dev, const int* elements_dev, int64_t num_elements, double* X_q_dev,
+                         double* J_q_dev, void* stream);
+
+/* ---------------------------------------------------------------------------------------------------------------
+ * Integral  (F/integral.hpp:24-168): one q-function on one domain, with its three kernel families
+ *   evaluation / evaluation_with_AD   F/domain_integral_kernels.hpp:152-220
+ *   jvp                               F/domain_integral_kernels.hpp:277-304
+ *   element_gradient                  F/domain_integral_kernels.hpp:327-361
+ * A q-function is compiled code, so an integral is created from a *kernel table*: either one of the named tables
+ * compiled into this library (sb_integral_create_named; list with sb_named_integrand_*) or a table instantiated in
+ * the caller's own nvcc translation unit from serac_b200/kernel_table.cuh (sb_integral_create_from_table) -- that is
+ * what the C++ serac::Functional wrapper does for user-supplied functors.
+ * ------------------------------------------------------------------------------------------------------------- */
+
+/* device-side description of one trial field for a launch */
+typedef struct {
+  const double* L_dev;     /* L-vector */
+  const int*    table_dev; /* restriction table of this field's space */
+  int64_t       node_stride;
+  int64_t       comp_stride;
+} sb_field_arg;
+
+typedef struct {
+  sb_field_arg  trial[SB_MAX_TRIALS];
+  const double* X_q_dev;
+  const double* J_q_dev;
+  const int*    elements_dev;
+  int           num_elements;
+  double*       r_E_dev;
+  double*       dqf_dev;
+  void*         qdata_dev;
+  int           update_state;
+  double        t;
+} sb_eval_args;
+
+typedef struct {
+  sb_field_arg  trial;
+  const int*    elements_dev;
+  int           num_elements;
+  const double* dqf_dev;
+  double*       r_E_dev;
+} sb_jvp_args;
+
+typedef struct {
+  const int*    elements_dev;
+  int           num_elements;
+  const double* dqf_dev;
+  double*       K_e_dev;
+} sb_elem_grad_args;
+
+typedef int (*sb_eval_launcher)(const sb_eval_args*, const void* qf_blob, void* stream);
+typedef int (*sb_jvp_launcher)(const sb_jvp_args*, void* stream);
+typedef int (*sb_elem_grad_launcher)(const sb_elem_grad_args*, void* stream);
+
+typedef struct {
+  int    geom;       /* SB_GEOM_* */
+  int    dim;        /* geometry dimension */
+  int    q;          /* quadrature points per direction (Q = max order + 1, F/functional.hpp:193) */
+  int    num_trials;
+  int    test_order, test_components;
+  int    trial_order[SB_MAX_TRIALS], trial_components[SB_MAX_TRIALS];
+  size_t qf_bytes;    /* sizeof the q-function functor (copied by value into the kernel parameters) */
+  size_t state_bytes; /* sizeof the quadrature-point state; 0 = no state */
+  int    elements_per_block; /* derivative tiles hold this many elements */
+  sb_eval_launcher      evaluate;                        /* no differentiation */
+  sb_eval_launcher      evaluate_ad[SB_MAX_TRIALS];      /* + derivative store w.r.t. trial i */
+  sb_jvp_launcher       jvp[SB_MAX_TRIALS];
+  sb_elem_grad_launcher element_gradient[SB_MAX_TRIALS];
+  int derivative_mask[SB_MAX_TRIALS];    /* bit b: block b of {d00,d01,d10,d11} present */
+  int derivative_entries[SB_MAX_TRIALS]; /* doubles stored per quadrature point */
+} sb_kernel_table;
+
+int         sb_named_integrand_count(void);
+const char* sb_named_integrand_name(int i);
+/* look up a compiled-in kernel table; params are the functor's constructor arguments (documented per name in
+ * INTEGRATION.md, e.g. "solid_neohookean_hex_p2": {density, K, G, geometric_nonlinearity}) */
+int sb_named_kernel_table(const char* name, const sb_kernel_table** table);
+int sb_named_qf_blob(const char* name, const double* params, int num_params, void* qf_blob, size_t qf_blob_capacity);
+
+/* MakeDomainIntegral (F/integral.hpp:238-260).  elements_host: domain element ids (NULL = EntireDomain).
+ * X_q_dev / J_q_dev: geometric factors for those elements (sb_geometric_factors); the integral keeps the pointers,
+ * the caller keeps ownership.  Derivative buffers are allocated on first use (F/integral.hpp:205-221). */
+int sb_integral_create(const sb_kernel_table* table, const void* qf_blob, const int* elements_host,
+                       int64_t num_elements, const double* X_q_dev, const double* J_q_dev, sb_integral_t* out);
+int sb_integral_destroy(sb_integral_t I);
+/* attach quadrature-point state, [num_elements][nq] AoS of the state struct (F/quadrature_data.hpp:112-142) */
+int sb_integral_set_qdata(sb_integral_t I, void* qdata_dev);
+/* Integral::Mult (F/integral.hpp:65-81): r_E (this geometry's E-vector block of the test space) is overwritten for the
+ * domain's elements.  wrt = SB_NO_DIFFERENTIATION or the trial index whose derivative is stored for later
+ * sb_integral_jvp / sb_integral_element_gradient calls. */
+int sb_integral_evaluate(sb_integral_t I, double t, const sb_field_arg* trials, double* r_E_dev, int wrt,
+                         int update_state, void* stream);
+/* Integral::GradientMult (F/integral.hpp:93-103) */
+int sb_integral_jvp(sb_integral_t I, int wrt, const sb_field_arg* du, double* dr_E_dev, void* stream);
+/* Integral::ComputeElementGradients (F/integral.hpp:112-121): K_e_dev [elements of geometry][trial vdofs][test vdofs]
+ * is accumulated into (+=), as the reference does. */
+int sb_integral_element_gradient(sb_integral_t I, int wrt, double* K_e_dev, void* stream);
+/* stored derivative w.r.t. `wrt`, converted to a dense reference-ordered array for parity checks:
+ * out_dev[e][q][block entries in d00,d01,d10,d11 order, row-major, absent blocks skipped] */
+int sb_integral_export_derivatives(sb_integral_t I, int wrt, double* out_dev, void* stream);
+int sb_integral_derivative_entries(sb_integral_t I, int wrt);
+int sb_integral_derivative_mask(sb_integral_t I, int wrt);
+
+/* ---------------------------------------------------------------------------------------------------------------
+ * Sparsity pattern + assembly  (GradientAssemblyLookupTables, F/dof_numbering.hpp:253-380;
+ *                               Gradient::assemble, F/functional.hpp:569-652)
+ * ------------------------------------------------------------------------------------------------------------- */
+/* lookup_tables.init(test, trial): sorted unique (row, col) pairs of all elements -> row_ptr / col_ind (bit-exact with
+ * the reference), plus the K_e-entry -> nonzero map that replaces nz_LUT's hash lookups. */
+int     sb_csr_create(sb_restriction_t test, sb_restriction_t trial, sb_csr_t* out);
+int     sb_csr_destroy(sb_csr_t A);
+int64_t sb_csr_nnz(sb_csr_t A);
+int64_t sb_csr_num_rows(sb_csr_t A);
+int     sb_csr_pattern_dev(sb_csr_t A, const int** row_ptr_dev, const int** col_ind_dev);
+int     sb_csr_pattern_to_host(sb_csr_t A, int* row_ptr_host, int* col_ind_host);
+/* values[nz] = sum over the contributing K_e entries in ascending (element, i, j) order (deterministic gather;
+ * F/functional.hpp:610-644 does the same sums with one hash lookup per entry). values_dev is overwritten. */
+int sb_csr_assemble(sb_csr_t A, const double* K_e_dev, double* values_dev, void* stream);
+
+/* ---------------------------------------------------------------------------------------------------------------
+ * Functional orchestration  (F/functional.hpp:406-513): P -> gather -> integrals -> scatter-add -> P^T at one rank
+ * (P = identity, mfem/fem/pfespace.cpp:1170-1173) or with a halo exchange object attached.
+ * ------------------------------------------------------------------------------------------------------------- */
+int sb_functional_create(sb_restriction_t test, int num_trials, const sb_restriction_t* trials, sb_functional_t* out);
+int sb_functional_destroy(sb_functional_t F);
+/* AddDomainIntegral (F/functional.hpp:286-317): trial_indices[i] = which Functional argument feeds the integral's
+ * i-th trial (the DependsOn<...> list) */
+int sb_functional_add_integral(sb_functional_t F, sb_integral_t I, const int* trial_indices);
+/* operator()(t, args...) (F/functional.hpp:446-513).  inputs: one L-vector per trial space.  *_on_host != 0 means the
+ * pointers are host buffers: they are copied to / from the device inside the call (synchronous). */
+int sb_functional_evaluate(sb_functional_t F, double t, int wrt, const double* const* inputs, int inputs_on_host,
+                           double* output, int output_on_host, int update_state, void* stream);
+/* Gradient::Mult (F/functional.hpp:406-432,556-559) for the derivative stored by the last evaluate(wrt) */
+int sb_functional_jvp(sb_functional_t F, int wrt, const double* du, int du_on_host, double* dr, int dr_on_host,
+                      void* stream);
+/* assemble(Gradient&) up to the local CSR triple (F/functional.hpp:569-652); values_dev has sb_csr_nnz entries */
+int sb_functional_assemble(sb_functional_t F, int wrt, sb_csr_t* pattern_inout, double* values, int values_on_host,
+                           void* stream);
+
+/* ---------------------------------------------------------------------------------------------------------------
+ * Shared-dof exchange P / P^T  (mfem::ConformingProlongationOperator, mfem/fem/pfespace.cpp:3599-3663; device variant
+ * :3740-3933).  The library packs / unpacks; the transport (NCCL send/recv over NVLink) is driven by the caller with
+ * the buffers returned here so that this library has no MPI / NCCL link dependency.
+ * ------------------------------------------------------------------------------------------------------------- */
+/* ltdof_host: for every local dof, the local true-dof index it copies from, or -1 if it is owned by another rank.
+ * send_idx: true-dof ids packed for neighbours (concatenated, neighbour n owns [send_off[n], send_off[n+1]));
+ * recv_idx: local dof ids filled from neighbours, same layout. */
+int sb_halo_create(int64_t lsize, int64_t tsize, const int* ltdof_host, int num_neighbors, const int64_t* send_off,
+                   const int* send_idx_host, const int64_t* recv_off, const int* recv_idx_host, sb_halo_t* out);
+int sb_halo_destroy(sb_halo_t H);
+int sb_halo_buffers(sb_halo_t H, double** send_buf_dev, double** recv_buf_dev);
+/* P: T -> L.  pack owner values for neighbours / copy owned / (after transport) unpack received values */
+int sb_halo_P_pack(sb_halo_t H, const double* T_dev, void* stream);
+int sb_halo_P_finish(sb_halo_t H, const double* T_dev, double* L_dev, void* stream);
+/* P^T: L -> T.  pack non-owned contributions / copy owned / (after transport) add received, fixed neighbour order */
+int sb_halo_Pt_pack(sb_halo_t H, const double* L_dev, void* stream);
+int sb_halo_Pt_finish(sb_halo_t H, const double* L_dev, double* T_dev, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SERAC_B200_H */

@@ -1,0 +1,38 @@
+// serac_b200: named solid-mechanics integrands -- what SolidMechanics::setMaterial registers with its Functional
+// (src/serac/physics/solid_mechanics.hpp:879-894): ShapeAwareIntegrandWrapperWithState<MaterialStressFunctor<Material>>
+// on H1<p,dim>(H1<1,dim> shape, H1<p,dim> u, H1<p,dim> a).
+#include "registry.hpp"
+
+namespace sb {
+namespace {
+
+using solid_mechanics::LinearIsotropic;
+using solid_mechanics::NeoHookean;
+
+template <typename S, typename Material>
+long make_solid(const double* p, int n, void* out, size_t cap)
+{
+  if (n != 4) return -1;
+  Material m{p[0], p[1], p[2]};
+  auto     gn = (p[3] != 0.0) ? GeometricNonlinearities::On : GeometricNonlinearities::Off;
+  typename S::template qf<Material> qf{MaterialStressFunctor<Material>(m, gn)};
+  return store_blob(qf, out, cap);
+}
+
+#ifndef SB_REG_GEOM
+#error "compile with -DSB_REG_GEOM=CUBE|SQUARE -DSB_REG_P=1|2|3 -DSB_REG_TAG=hex_p2"
+#endif
+#define SB_STR2(x) #x
+#define SB_STR(x) SB_STR2(x)
+
+using S = SolidSig<Geometry::SB_REG_GEOM, SB_REG_P>;
+
+static Registrar r_neo({"solid_neohookean_" SB_STR(SB_REG_TAG),
+                        make_kernel_table<S::type, S::qf<NeoHookean>, NeoHookean::State>(),
+                        &make_solid<S, NeoHookean>, "{density, K, G, geometric_nonlinearity(0|1)}"});
+static Registrar r_lin({"solid_linear_isotropic_" SB_STR(SB_REG_TAG),
+                        make_kernel_table<S::type, S::qf<LinearIsotropic>, LinearIsotropic::State>(),
+                        &make_solid<S, LinearIsotropic>, "{density, K, G, geometric_nonlinearity(0|1)}"});
+
+}  // namespace
+}  // namespace sb

@@ -1,0 +1,1219 @@
+// serac_b200: fused domain-integral kernels for tensor-product H1 elements (quadrilateral / hexahedron).
+//
+// What the reference does per element on the host, one kernel here does per CTA of EPB elements:
+//   * L->E gather            src/serac/numerics/functional/element_restriction.cpp:443-454   (fused: reads L through the
+//                                                                                              restriction table)
+//   * interpolate            src/serac/numerics/functional/detail/hexahedron_H1.inl:169-228  (sum-factorised, smem staged)
+//   * parent_to_physical     src/serac/numerics/functional/finite_element.hpp:246-273
+//   * q-function (+ state)   src/serac/numerics/functional/domain_integral_kernels.hpp:105-150
+//   * physical_to_parent     src/serac/numerics/functional/finite_element.hpp:287-322
+//   * store d(qf)/d(arg)     src/serac/numerics/functional/domain_integral_kernels.hpp:206-213
+//   * integrate              src/serac/numerics/functional/detail/hexahedron_H1.inl:230-280  (sum-factorised, smem staged)
+// and the two derivative consumers
+//   * action_of_gradient     src/serac/numerics/functional/domain_integral_kernels.hpp:277-304
+//   * element_gradient       src/serac/numerics/functional/domain_integral_kernels.hpp:327-361
+//
+// Thread mapping: one thread per quadrature point, EPB elements per CTA (EPB * q^dim ~ 128 threads).  All
+// per-quadrature-point streams (stored derivatives, geometric factors) are laid out [tile][entry][lane] so that a
+// warp reads consecutive doubles.  The element residual is written as an E-vector block; the deterministic E->L
+// scatter is a separate kernel (restriction.cu).
+#pragma once
+
+#include <cuda_runtime.h>
+
+#include "serac_b200/finite_element.hpp"
+#include "serac_b200/tensor.hpp"
+
+namespace serac {
+namespace b200 {
+
+constexpr int MAX_TRIALS = 6;
+
+/// how many elements one CTA processes
+SB_HD int elements_per_block(int dim, int q)
+{
+  if (dim == 3) return (q <= 1) ? 64 : (q == 2) ? 16 : (q == 3) ? 4 : 2;
+  if (dim == 2) return (q <= 1) ? 128 : (q == 2) ? 32 : (q == 3) ? 14 : 8;
+  return 1;
+}
+
+/// one trial / test field as the kernels see it
+struct FieldArg {
+  const double* L;            ///< L-vector (device)
+  const int*    table;        ///< [elements of this geometry][ndof] lexicographic scalar node ids
+  long long     node_stride;  ///< byVDIM: components ; byNODES: 1      (element_restriction.cpp:425-432)
+  long long     comp_stride;  ///< byVDIM: 1          ; byNODES: num_nodes
+};
+
+template <int NT>
+struct EvalParams {
+  FieldArg      trial[NT > 0 ? NT : 1];
+  BasisTable1D  trial_basis[NT > 0 ? NT : 1];
+  BasisTable1D  test_basis;
+  const double* X_q;           ///< [e][i][q]       (geometric_factors.cpp:27,48)
+  const double* J_q;           ///< [e][j][i][q] = dX_i/dxi_j
+  const int*    elements;      ///< domain element ids (index into the restriction tables / E-vector)
+  int           num_elements;  ///< how many entries of `elements`
+  double*       r_E;           ///< [element][comp][node] E-vector block of the test space
+  double*       dqf;           ///< stored q-function derivatives, [tile][entry][lane]
+  void*         qdata;         ///< [e][q] AoS of the state type (quadrature_data.hpp:127-131)
+  int           update_state;
+  double        t;
+};
+
+struct JvpParams {
+  FieldArg      trial;
+  BasisTable1D  trial_basis;
+  BasisTable1D  test_basis;
+  const int*    elements;
+  int           num_elements;
+  const double* dqf;
+  double*       r_E;
+};
+
+struct ElemGradParams {
+  BasisTable1D  trial_basis;
+  BasisTable1D  test_basis;
+  const int*    elements;
+  int           num_elements;
+  const double* dqf;
+  double*       K_e;  ///< [element][trial_comp*ntrial + J][test_comp*ntest + I]   (functional.hpp:599-601,632-636)
+};
+
+// ------------------------------------------------------------------------------------------------
+// component accessors that hide the c == 1 special cases of the q-function argument types
+// (domain_integral_kernels.hpp:33-65)
+// ------------------------------------------------------------------------------------------------
+template <typename Space, int dim, typename T = double>
+struct qf_arg {
+  static constexpr int c = Space::components;
+  using value_t          = std::conditional_t<c == 1, T, tensor<T, c>>;
+  using grad_t           = std::conditional_t<c == 1, tensor<T, dim>, tensor<T, c, dim>>;
+  using type             = tuple<value_t, grad_t>;
+};
+
+template <typename T, typename = std::enable_if_t<is_scalar_v<T>>>
+SB_HD T& vcomp(T& v, int)
+{
+  return v;
+}
+template <typename T, typename = std::enable_if_t<is_scalar_v<T>>>
+SB_HD const T& vcomp(const T& v, int)
+{
+  return v;
+}
+template <typename T, int c>
+SB_HD T& vcomp(tensor<T, c>& v, int a)
+{
+  return v[a];
+}
+template <typename T, int c>
+SB_HD const T& vcomp(const tensor<T, c>& v, int a)
+{
+  return v[a];
+}
+template <typename T, int dim>
+SB_HD T& gcomp(tensor<T, dim>& g, int, int j)
+{
+  return g[j];
+}
+template <typename T, int dim>
+SB_HD const T& gcomp(const tensor<T, dim>& g, int, int j)
+{
+  return g[j];
+}
+template <typename T, int c, int dim>
+SB_HD T& gcomp(tensor<T, c, dim>& g, int a, int j)
+{
+  return g[a][j];
+}
+template <typename T, int c, int dim>
+SB_HD const T& gcomp(const tensor<T, c, dim>& g, int a, int j)
+{
+  return g[a][j];
+}
+
+template <typename T>
+struct scalar_type_of {
+  using type = T;
+};
+template <typename T, int... n>
+struct scalar_type_of<tensor<T, n...>> {
+  using type = T;
+};
+template <typename T>
+inline constexpr bool carries_derivative_v = is_dual_number<typename scalar_type_of<T>::type>::value;
+
+/// partial k of a (possibly plain) scalar
+SB_HD double partial(double, int) { return 0.0; }
+template <int N>
+SB_HD double partial(const dual<N>& x, int k)
+{
+  return x.gradient[k];
+}
+
+// ------------------------------------------------------------------------------------------------
+// sum-factorised interpolation / integration staged through shared memory.
+// All threads of the CTA must call these (they contain __syncthreads()).
+// Thread (qz,qy,qx) of an element owns quadrature point Q = (qz*q + qy)*q + qx   (hexahedron_H1.inl:155,256).
+// ------------------------------------------------------------------------------------------------
+template <int dim, int n, int q, int c>
+struct TensorProduct;
+
+template <int n, int q, int c>
+struct TensorProduct<3, n, q, c> {
+  static constexpr int ndof          = n * n * n;
+  static constexpr int interp_scratch = c * ndof + 2 * c * n * n * q + 3 * c * n * q * q;
+  static constexpr int integ_scratch  = 4 * c * q * q * q + 3 * c * n * q * q + 2 * c * n * n * q;
+
+  /// u: smem [c][n][n][n] already filled; s: this element's scratch (>= interp_scratch doubles, u lives at s[0])
+  template <bool NEED_VALUE, bool NEED_GRAD>
+  static __device__ __forceinline__ void interpolate(const double* __restrict__ B, const double* __restrict__ G,
+                                                     double* s, int qx, int qy, int qz, double (&val)[c],
+                                                     double (&grad)[c][3])
+  {
+    const double* u  = s;
+    double*       A1 = s + c * ndof;               // [2][c][n][n][q]
+    double*       A2 = A1 + 2 * c * n * n * q;     // [3][c][n][q][q]
+    if (qz < n && qy < n) {
+      SB_UNROLL
+      for (int a = 0; a < c; a++) {
+        double sB = 0.0, sG = 0.0;
+        SB_UNROLL
+        for (int dx = 0; dx < n; dx++) {
+          const double uu = u[((a * n + qz) * n + qy) * n + dx];
+          sB += B[qx * n + dx] * uu;
+          if (NEED_GRAD) sG += G[qx * n + dx] * uu;
+        }
+        A1[(((0 * c + a) * n + qz) * n + qy) * q + qx] = sB;
+        if (NEED_GRAD) A1[(((1 * c + a) * n + qz) * n + qy) * q + qx] = sG;
+      }
+    }
+    __syncthreads();
+    if (qz < n) {
+      SB_UNROLL
+      for (int a = 0; a < c; a++) {
+        double sBB = 0.0, sGB = 0.0, sBG = 0.0;
+        SB_UNROLL
+        for (int dy = 0; dy < n; dy++) {
+          const double b  = A1[(((0 * c + a) * n + qz) * n + dy) * q + qx];
+          const double By = B[qy * n + dy];
+          sBB += By * b;
+          if (NEED_GRAD) {
+            const double g = A1[(((1 * c + a) * n + qz) * n + dy) * q + qx];
+            sGB += By * g;
+            sBG += G[qy * n + dy] * b;
+          }
+        }
+        A2[(((0 * c + a) * n + qz) * q + qy) * q + qx] = sBB;
+        if (NEED_GRAD) {
+          A2[(((1 * c + a) * n + qz) * q + qy) * q + qx] = sGB;
+          A2[(((2 * c + a) * n + qz) * q + qy) * q + qx] = sBG;
+        }
+      }
+    }
+    __syncthreads();
+    SB_UNROLL
+    for (int a = 0; a < c; a++) {
+      double v = 0.0, gx = 0.0, gy = 0.0, gz = 0.0;
+      SB_UNROLL
+      for (int dz = 0; dz < n; dz++) {
+        const double bb = A2[(((0 * c + a) * n + dz) * q + qy) * q + qx];
+        const double Bz = B[qz * n + dz];
+        if (NEED_VALUE) v += Bz * bb;
+        if (NEED_GRAD) {
+          const double gb = A2[(((1 * c + a) * n + dz) * q + qy) * q + qx];
+          const double bg = A2[(((2 * c + a) * n + dz) * q + qy) * q + qx];
+          gx += Bz * gb;
+          gy += Bz * bg;
+          gz += G[qz * n + dz] * bb;
+        }
+      }
+      val[a]     = v;
+      grad[a][0] = gx;
+      grad[a][1] = gy;
+      grad[a][2] = gz;
+    }
+  }
+
+  /// integrate weighted source src[c] / parent-space flux[c][3] of this thread's quadrature point against the
+  /// test functions; the thread (dz,dy,dx) = (qz,qy,qx) with all three < n returns the dof value in out[c].
+  template <bool HAS_SOURCE, bool HAS_FLUX>
+  static __device__ __forceinline__ bool integrate(const double* __restrict__ B, const double* __restrict__ G,
+                                                   double* s, int qx, int qy, int qz, const double (&src)[c],
+                                                   const double (&flux)[c][3], double (&out)[c])
+  {
+    double* S  = s;                        // [4][c][q][q][q]
+    double* P  = S + 4 * c * q * q * q;    // [3][c][n][q][q]
+    double* Qs = P + 3 * c * n * q * q;    // [2][c][n][n][q]
+    SB_UNROLL
+    for (int a = 0; a < c; a++) {
+      if (HAS_SOURCE) S[(((0 * c + a) * q + qz) * q + qy) * q + qx] = src[a];
+      if (HAS_FLUX) {
+        S[(((1 * c + a) * q + qz) * q + qy) * q + qx] = flux[a][0];
+        S[(((2 * c + a) * q + qz) * q + qy) * q + qx] = flux[a][1];
+        S[(((3 * c + a) * q + qz) * q + qy) * q + qx] = flux[a][2];
+      }
+    }
+    __syncthreads();
+    if (qz < n) {  // dz = qz
+      SB_UNROLL
+      for (int a = 0; a < c; a++) {
+        double p0 = 0.0, p1 = 0.0, p2 = 0.0;
+        SB_UNROLL
+        for (int k = 0; k < q; k++) {
+          const double Bz = B[k * n + qz];
+          if (HAS_SOURCE) p0 += Bz * S[(((0 * c + a) * q + k) * q + qy) * q + qx];
+          if (HAS_FLUX) {
+            p0 += G[k * n + qz] * S[(((3 * c + a) * q + k) * q + qy) * q + qx];
+            p1 += Bz * S[(((1 * c + a) * q + k) * q + qy) * q + qx];
+            p2 += Bz * S[(((2 * c + a) * q + k) * q + qy) * q + qx];
+          }
+        }
+        P[(((0 * c + a) * n + qz) * q + qy) * q + qx] = p0;
+        if (HAS_FLUX) {
+          P[(((1 * c + a) * n + qz) * q + qy) * q + qx] = p1;
+          P[(((2 * c + a) * n + qz) * q + qy) * q + qx] = p2;
+        }
+      }
+    }
+    __syncthreads();
+    if (qz < n && qy < n) {  // dz = qz, dy = qy
+      SB_UNROLL
+      for (int a = 0; a < c; a++) {
+        double q0 = 0.0, q1 = 0.0;
+        SB_UNROLL
+        for (int k = 0; k < q; k++) {
+          const double By = B[k * n + qy];
+          q0 += By * P[(((0 * c + a) * n + qz) * q + k) * q + qx];
+          if (HAS_FLUX) {
+            q0 += G[k * n + qy] * P[(((2 * c + a) * n + qz) * q + k) * q + qx];
+            q1 += By * P[(((1 * c + a) * n + qz) * q + k) * q + qx];
+          }
+        }
+        Qs[(((0 * c + a) * n + qz) * n + qy) * q + qx] = q0;
+        if (HAS_FLUX) Qs[(((1 * c + a) * n + qz) * n + qy) * q + qx] = q1;
+      }
+    }
+    __syncthreads();
+    const bool owner = (qz < n && qy < n && qx < n);
+    if (owner) {
+      SB_UNROLL
+      for (int a = 0; a < c; a++) {
+        double r = 0.0;
+        SB_UNROLL
+        for (int k = 0; k < q; k++) {
+          r += B[k * n + qx] * Qs[(((0 * c + a) * n + qz) * n + qy) * q + k];
+          if (HAS_FLUX) r += G[k * n + qx] * Qs[(((1 * c + a) * n + qz) * n + qy) * q + k];
+        }
+        out[a] = r;
+      }
+    }
+    return owner;
+  }
+};
+
+template <int n, int q, int c>
+struct TensorProduct<2, n, q, c> {
+  static constexpr int ndof           = n * n;
+  static constexpr int interp_scratch = c * ndof + 2 * c * n * q;
+  static constexpr int integ_scratch  = 3 * c * q * q + 2 * c * n * q;
+
+  template <bool NEED_VALUE, bool NEED_GRAD>
+  static __device__ __forceinline__ void interpolate(const double* __restrict__ B, const double* __restrict__ G,
+                                                     double* s, int qx, int qy, int, double (&val)[c],
+                                                     double (&grad)[c][2])
+  {
+    const double* u  = s;
+    double*       A1 = s + c * ndof;  // [2][c][n][q]
+    if (qy < n) {
+      SB_UNROLL
+      for (int a = 0; a < c; a++) {
+        double sB = 0.0, sG = 0.0;
+        SB_UNROLL
+        for (int dx = 0; dx < n; dx++) {
+          const double uu = u[(a * n + qy) * n + dx];
+          sB += B[qx * n + dx] * uu;
+          if (NEED_GRAD) sG += G[qx * n + dx] * uu;
+        }
+        A1[((0 * c + a) * n + qy) * q + qx] = sB;
+        if (NEED_GRAD) A1[((1 * c + a) * n + qy) * q + qx] = sG;
+      }
+    }
+    __syncthreads();
+    SB_UNROLL
+    for (int a = 0; a < c; a++) {
+      double v = 0.0, gx = 0.0, gy = 0.0;
+      SB_UNROLL
+      for (int dy = 0; dy < n; dy++) {
+        const double b  = A1[((0 * c + a) * n + dy) * q + qx];
+        const double By = B[qy * n + dy];
+        if (NEED_VALUE) v += By * b;
+        if (NEED_GRAD) {
+          gx += By * A1[((1 * c + a) * n + dy) * q + qx];
+          gy += G[qy * n + dy] * b;
+        }
+      }
+      val[a]     = v;
+      grad[a][0] = gx;
+      grad[a][1] = gy;
+    }
+  }
+
+  template <bool HAS_SOURCE, bool HAS_FLUX>
+  static __device__ __forceinline__ bool integrate(const double* __restrict__ B, const double* __restrict__ G,
+                                                   double* s, int qx, int qy, int, const double (&src)[c],
+                                                   const double (&flux)[c][2], double (&out)[c])
+  {
+    double* S = s;                  // [3][c][q][q]
+    double* P = S + 3 * c * q * q;  // [2][c][n][q]
+    SB_UNROLL
+    for (int a = 0; a < c; a++) {
+      if (HAS_SOURCE) S[((0 * c + a) * q + qy) * q + qx] = src[a];
+      if (HAS_FLUX) {
+        S[((1 * c + a) * q + qy) * q + qx] = flux[a][0];
+        S[((2 * c + a) * q + qy) * q + qx] = flux[a][1];
+      }
+    }
+    __syncthreads();
+    if (qy < n) {  // dy = qy
+      SB_UNROLL
+      for (int a = 0; a < c; a++) {
+        double p0 = 0.0, p1 = 0.0;
+        SB_UNROLL
+        for (int k = 0; k < q; k++) {
+          const double By = B[k * n + qy];
+          if (HAS_SOURCE) p0 += By * S[((0 * c + a) * q + k) * q + qx];
+          if (HAS_FLUX) {
+            p0 += G[k * n + qy] * S[((2 * c + a) * q + k) * q + qx];
+            p1 += By * S[((1 * c + a) * q + k) * q + qx];
+          }
+        }
+        P[((0 * c + a) * n + qy) * q + qx] = p0;
+        if (HAS_FLUX) P[((1 * c + a) * n + qy) * q + qx] = p1;
+      }
+    }
+    __syncthreads();
+    const bool owner = (qy < n && qx < n);
+    if (owner) {
+      SB_UNROLL
+      for (int a = 0; a < c; a++) {
+        double r = 0.0;
+        SB_UNROLL
+        for (int k = 0; k < q; k++) {
+          r += B[k * n + qx] * P[((0 * c + a) * n + qy) * q + k];
+          if (HAS_FLUX) r += G[k * n + qx] * P[((1 * c + a) * n + qy) * q + k];
+        }
+        out[a] = r;
+      }
+    }
+    return owner;
+  }
+};
+
+SB_HD int cmax(int a, int b) { return a > b ? a : b; }
+
+// ------------------------------------------------------------------------------------------------
+// compile-time description of one integral: geometry, Q, test space, trial spaces
+// ------------------------------------------------------------------------------------------------
+template <Geometry geom, int Q, typename test, typename... trials>
+struct Signature {
+  static constexpr Geometry geometry = geom;
+  static constexpr int      dim      = dimension_of(geom);
+  static constexpr int      q        = Q;
+  static constexpr int      NT       = int(sizeof...(trials));
+  static constexpr int      QPE      = num_quadrature_points(geom, Q);  ///< quadrature points per element
+  static constexpr int      EPB      = elements_per_block(dim, Q);
+  static constexpr int      threads  = EPB * QPE;
+  using test_space                   = test;
+  template <int i>
+  using trial_space = typename serac::detail::type_at<i, trials...>::type;
+
+  static constexpr int test_n    = test::order + 1;
+  static constexpr int test_c    = test::components;
+  static constexpr int test_ndof = ipow(test_n, dim);
+
+  static_assert(((trials::order + 1 <= Q) && ...), "quadrature rule must have at least p + 1 points per direction");
+  static_assert(test::order + 1 <= Q, "quadrature rule must have at least p + 1 points per direction");
+
+};
+
+template <typename Sig, int... I>
+constexpr int max_interp_scratch(std::integer_sequence<int, I...>)
+{
+  int m = 0;
+  ((m = cmax(m, TensorProduct<Sig::dim, Sig::template trial_space<I>::order + 1, Sig::q,
+                              Sig::template trial_space<I>::components>::interp_scratch)),
+   ...);
+  return m;
+}
+
+template <typename Sig>
+constexpr int eval_scratch_per_element()
+{
+  return cmax(max_interp_scratch<Sig>(std::make_integer_sequence<int, Sig::NT>{}),
+              TensorProduct<Sig::dim, Sig::test_n, Sig::q, Sig::test_c>::integ_scratch);
+}
+
+/// smem layout: [tables: (NT + 1) x 2 x MAX_Q*MAX_Q] [EPB x scratch]
+template <typename Sig>
+constexpr int eval_smem_doubles()
+{
+  return (Sig::NT + 1) * 2 * MAX_Q * MAX_Q + Sig::EPB * eval_scratch_per_element<Sig>();
+}
+
+// ------------------------------------------------------------------------------------------------
+// layout of the stored derivative d(source, flux)/d(value, grad) w.r.t. one trial argument.
+// Blocks follow the reference's nested tuple order (domain_integral_kernels.hpp:223-237):
+//   d00 = d source / d value   [ct][ck]
+//   d01 = d source / d grad    [ct][ck][dim]
+//   d10 = d flux   / d value   [ct][dim][ck]
+//   d11 = d flux   / d grad    [ct][dim][ck][dim]
+// A block is absent when the q-function's output does not carry derivatives in the pass that seeds it -- the same
+// structural pruning the reference gets from `zero` gradient types.
+// ------------------------------------------------------------------------------------------------
+struct DerivativeLayout {
+  int  ct, ck, dim;
+  bool has[4];
+  int  offset[4];
+  int  size[4];
+  int  entries;
+};
+
+SB_HD DerivativeLayout make_layout(int ct, int ck, int dim, bool d00, bool d01, bool d10, bool d11)
+{
+  DerivativeLayout L{};
+  L.ct      = ct;
+  L.ck      = ck;
+  L.dim     = dim;
+  L.has[0]  = d00;
+  L.has[1]  = d01;
+  L.has[2]  = d10;
+  L.has[3]  = d11;
+  L.size[0] = ct * ck;
+  L.size[1] = ct * ck * dim;
+  L.size[2] = ct * dim * ck;
+  L.size[3] = ct * dim * ck * dim;
+  int off   = 0;
+  for (int b = 0; b < 4; b++) {
+    L.offset[b] = off;
+    if (L.has[b]) off += L.size[b];
+  }
+  L.entries = off;
+  return L;
+}
+
+// ---- calling the q-function -------------------------------------------------------------------
+template <typename QF, typename Pos, typename State, typename... Args>
+SERAC_HOST_DEVICE inline auto call_qf(const QF& qf, double t, const Pos& x, State& state, const Args&... args)
+{
+  if constexpr (std::is_same_v<State, Nothing>) {
+    return qf(t, x, args...);
+  } else {
+    return qf(t, x, state, args...);
+  }
+}
+
+template <typename T>
+struct output_traits;  // of tuple<source, flux>
+template <typename S, typename F>
+struct output_traits<tuple<S, F>> {
+  static constexpr bool has_source  = !is_zero<S>::value;
+  static constexpr bool has_flux    = !is_zero<F>::value;
+  static constexpr bool source_dual = carries_derivative_v<S>;
+  static constexpr bool flux_dual   = carries_derivative_v<F>;
+};
+
+/// argument K as seen by the q-function in a derivative pass
+/// PASS == -1: value pass (value components carry dual<ck>, gradient plain)
+/// PASS >= 0 : gradient-row pass (row PASS of the gradient carries dual<dim>, value plain)
+template <typename Space, int dim, int PASS>
+struct seeded_arg {
+  static constexpr int c = Space::components;
+  static constexpr int N = (PASS < 0) ? c : dim;
+  using value_scalar     = std::conditional_t<(PASS < 0), dual<N>, double>;
+  using grad_scalar      = std::conditional_t<(PASS < 0), double, dual<N>>;
+  using value_t          = std::conditional_t<c == 1, value_scalar, tensor<value_scalar, c>>;
+  using grad_t           = std::conditional_t<c == 1, tensor<grad_scalar, dim>, tensor<grad_scalar, c, dim>>;
+  using type             = tuple<value_t, grad_t>;
+};
+
+template <typename Sig, int WRT, int PASS, typename QF, typename State, int... I>
+auto pass_output_type(std::integer_sequence<int, I...>)
+{
+  constexpr int dim = Sig::dim;
+  using pos_t       = tuple<tensor<double, dim>, tensor<double, dim, dim>>;
+  if constexpr (std::is_same_v<State, Nothing>) {
+    return decltype(std::declval<QF>()(
+        double{}, pos_t{},
+        std::declval<std::conditional_t<
+            I == WRT, typename seeded_arg<typename Sig::template trial_space<I>, dim, PASS>::type,
+            typename qf_arg<typename Sig::template trial_space<I>, dim>::type>>()...)){};
+  } else {
+    return decltype(std::declval<QF>()(
+        double{}, pos_t{}, std::declval<State&>(),
+        std::declval<std::conditional_t<
+            I == WRT, typename seeded_arg<typename Sig::template trial_space<I>, dim, PASS>::type,
+            typename qf_arg<typename Sig::template trial_space<I>, dim>::type>>()...)){};
+  }
+}
+
+template <typename Sig, typename QF, typename State, int... I>
+auto plain_output_type(std::integer_sequence<int, I...>)
+{
+  constexpr int dim = Sig::dim;
+  using pos_t       = tuple<tensor<double, dim>, tensor<double, dim, dim>>;
+  if constexpr (std::is_same_v<State, Nothing>) {
+    return decltype(std::declval<QF>()(
+        double{}, pos_t{}, std::declval<typename qf_arg<typename Sig::template trial_space<I>, dim>::type>()...)){};
+  } else {
+    return decltype(std::declval<QF>()(
+        double{}, pos_t{}, std::declval<State&>(),
+        std::declval<typename qf_arg<typename Sig::template trial_space<I>, dim>::type>()...)){};
+  }
+}
+
+template <typename Sig, int WRT, typename QF, typename State>
+struct DerivativeTraits {
+  using seq              = std::make_integer_sequence<int, Sig::NT>;
+  using value_pass_out   = decltype(pass_output_type<Sig, WRT, -1, QF, State>(seq{}));
+  using grad_pass_out    = decltype(pass_output_type<Sig, WRT, 0, QF, State>(seq{}));
+  using trial            = typename Sig::template trial_space<WRT>;
+  static constexpr int  ct  = Sig::test_c;
+  static constexpr int  ck  = trial::components;
+  static constexpr int  dim = Sig::dim;
+  static constexpr bool d00 = output_traits<value_pass_out>::source_dual;
+  static constexpr bool d10 = output_traits<value_pass_out>::flux_dual;
+  static constexpr bool d01 = output_traits<grad_pass_out>::source_dual;
+  static constexpr bool d11 = output_traits<grad_pass_out>::flux_dual;
+  static constexpr bool value_pass_active = d00 || d10;
+  static constexpr bool grad_pass_active  = d01 || d11;
+  static constexpr DerivativeLayout layout() { return make_layout(ct, ck, dim, d00, d01, d10, d11); }
+};
+
+// ---- output component extraction ----------------------------------------------------------------
+template <int ct, typename S>
+SB_HD auto source_component(const S& s, int a)
+{
+  if constexpr (is_zero<S>::value) {
+    return 0.0;
+  } else {
+    return vcomp(s, a);
+  }
+}
+template <int ct, int dim, typename F>
+SB_HD auto flux_component(const F& f, int a, int j)
+{
+  if constexpr (is_zero<F>::value) {
+    return 0.0;
+  } else {
+    return gcomp(f, a, j);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// evaluation kernel.  WRT < 0: plain residual.  WRT >= 0: residual + derivative store w.r.t. trial WRT.
+// ------------------------------------------------------------------------------------------------
+template <typename Sig, int I>
+__device__ __forceinline__ void load_and_interpolate(const EvalParams<Sig::NT>& P, const double* tables, double* scratch,
+                                                     int el, int elem, int qx, int qy, int qz,
+                                                     typename qf_arg<typename Sig::template trial_space<I>, Sig::dim>::type& arg,
+                                                     const tensor<double, Sig::dim, Sig::dim>& invJ)
+{
+  using space       = typename Sig::template trial_space<I>;
+  constexpr int dim = Sig::dim;
+  constexpr int n   = space::order + 1;
+  constexpr int c   = space::components;
+  using TP          = TensorProduct<dim, n, Sig::q, c>;
+  constexpr int per = eval_scratch_per_element<Sig>();
+
+  __syncthreads();  // scratch reuse
+  // cooperative gather: EPB elements x c x ndof values
+  const FieldArg& f = P.trial[I];
+  for (int i = threadIdx.x; i < Sig::EPB * c * TP::ndof; i += Sig::threads) {
+    const int le   = i / (c * TP::ndof);
+    const int rem  = i - le * (c * TP::ndof);
+    const int a    = rem / TP::ndof;
+    const int node = rem - a * TP::ndof;
+    int       e    = blockIdx.x * Sig::EPB + le;
+    if (e >= P.num_elements) e = P.num_elements - 1;
+    const int       ge  = P.elements[e];
+    const long long idx = (long long)f.table[(long long)ge * TP::ndof + node];
+    scratch[le * per + a * TP::ndof + node] = f.L[idx * f.node_stride + a * f.comp_stride];
+  }
+  __syncthreads();
+  const double* B = tables + (I * 2 + 0) * MAX_Q * MAX_Q;
+  const double* G = tables + (I * 2 + 1) * MAX_Q * MAX_Q;
+  double        val[c];
+  double        grad[c][dim];
+  TP::template interpolate<true, true>(B, G, scratch + el * per, qx, qy, qz, val, grad);
+  (void)elem;
+  // parent -> physical: grad <- grad . inv(J)    (finite_element.hpp:262-264)
+  SB_UNROLL
+  for (int a = 0; a < c; a++) {
+    vcomp(get<0>(arg), a) = val[a];
+    SB_UNROLL
+    for (int j = 0; j < dim; j++) {
+      double sum = 0.0;
+      SB_UNROLL
+      for (int k = 0; k < dim; k++) sum += grad[a][k] * invJ(k, j);
+      gcomp(get<1>(arg), a, j) = sum;
+    }
+  }
+}
+
+/// build the seeded version of argument `arg` for a derivative pass
+template <typename Space, int dim, int PASS>
+__device__ __forceinline__ auto seed_argument(const typename qf_arg<Space, dim>::type& arg,
+                                              const tensor<double, dim, dim>& invJ)
+{
+  using S          = seeded_arg<Space, dim, PASS>;
+  constexpr int c  = Space::components;
+  typename S::type out{};
+  if constexpr (PASS < 0) {
+    SB_UNROLL
+    for (int a = 0; a < c; a++) {
+      auto& v              = vcomp(get<0>(out), a);
+      v                    = make_dual_constant<S::N>(vcomp(get<0>(arg), a));
+      v.gradient[a]        = 1.0;
+      SB_UNROLL
+      for (int j = 0; j < dim; j++) gcomp(get<1>(out), a, j) = gcomp(get<1>(arg), a, j);
+    }
+  } else {
+    SB_UNROLL
+    for (int a = 0; a < c; a++) {
+      vcomp(get<0>(out), a) = vcomp(get<0>(arg), a);
+      SB_UNROLL
+      for (int j = 0; j < dim; j++) {
+        auto& g = gcomp(get<1>(out), a, j);
+        g       = make_dual_constant<S::N>(gcomp(get<1>(arg), a, j));
+        // the seed is the PARENT-space gradient (the reference promotes to dual before parent_to_physical,
+        // domain_integral_kernels.hpp:181-186), so d(physical grad[a][j]) / d(parent grad[a][k]) = invJ(k, j)
+        if (a == PASS) {
+          SB_UNROLL
+          for (int k = 0; k < dim; k++) g.gradient[k] = invJ(k, j);
+        }
+      }
+    }
+  }
+  return out;
+}
+
+template <typename Sig, int WRT, int PASS, typename QF, typename State, typename Pos, typename Inputs, int... I>
+__device__ __forceinline__ auto run_pass(const QF& qf, double t, const Pos& pos, State& state, const Inputs& in,
+                                         const tensor<double, Sig::dim, Sig::dim>& invJ,
+                                         std::integer_sequence<int, I...>)
+{
+  auto pick = [&](auto idx) {
+    constexpr int i = decltype(idx)::value;
+    if constexpr (i == WRT) {
+      return seed_argument<typename Sig::template trial_space<i>, Sig::dim, PASS>(get<i>(in), invJ);
+    } else {
+      return get<i>(in);
+    }
+  };
+  return call_qf(qf, t, pos, state, pick(std::integral_constant<int, I>{})...);
+}
+
+template <typename Sig, typename QF, typename Pos, typename State, typename Inputs, int... I>
+__device__ __forceinline__ auto call_qf_tuple(const QF& qf, double t, const Pos& pos, State& st, const Inputs& in,
+                                              std::integer_sequence<int, I...>)
+{
+  return call_qf(qf, t, pos, st, get<I>(in)...);
+}
+
+template <typename Sig, int WRT, typename QF, typename State>
+__global__ void __launch_bounds__(Sig::threads) evaluation_kernel(const __grid_constant__ EvalParams<Sig::NT> P,
+                                                                  const __grid_constant__ QF qf)
+{
+  constexpr int dim = Sig::dim;
+  constexpr int q   = Sig::q;
+  constexpr int NT  = Sig::NT;
+  constexpr int QPE = Sig::QPE;
+  constexpr int EPB = Sig::EPB;
+  constexpr int ct  = Sig::test_c;
+  constexpr int per = eval_scratch_per_element<Sig>();
+  using seq         = std::make_integer_sequence<int, NT>;
+
+  extern __shared__ double smem[];
+  double* tables  = smem;
+  double* scratch = smem + (NT + 1) * 2 * MAX_Q * MAX_Q;
+
+  for (int i = threadIdx.x; i < (NT + 1) * 2 * MAX_Q * MAX_Q; i += Sig::threads) {
+    const int           which = i / (2 * MAX_Q * MAX_Q);
+    const int           rem   = i - which * (2 * MAX_Q * MAX_Q);
+    const BasisTable1D& bt    = (which < NT) ? P.trial_basis[which < NT ? which : 0] : P.test_basis;
+    tables[i]                 = (rem < MAX_Q * MAX_Q) ? bt.B[rem] : bt.G[rem - MAX_Q * MAX_Q];
+  }
+
+  const int el = threadIdx.x / QPE;
+  const int ql = threadIdx.x - el * QPE;
+  const int qx = ql % q;
+  const int qy = (ql / q) % q;
+  const int qz = (dim == 3) ? ql / (q * q) : 0;
+
+  const int  e_raw = blockIdx.x * EPB + el;
+  const bool valid = e_raw < P.num_elements;
+  const int  e     = valid ? e_raw : P.num_elements - 1;
+  const int  elem  = P.elements[e];
+
+  // geometric factors of this quadrature point:  Jm(i,j) = dX_i/dxi_j = J_q[e](j,i,q)
+  tensor<double, dim>      x{};
+  tensor<double, dim, dim> Jm{};
+  SB_UNROLL
+  for (int i = 0; i < dim; i++) {
+    x[i] = P.X_q[((long long)e * dim + i) * QPE + ql];
+    SB_UNROLL
+    for (int j = 0; j < dim; j++) Jm(i, j) = P.J_q[(((long long)e * dim + j) * dim + i) * QPE + ql];
+  }
+  const auto   invJ = inv(Jm);
+  const double dv   = det(Jm);
+
+  auto inputs = [&]<int... I>(std::integer_sequence<int, I...>)
+  {
+    tuple<typename qf_arg<typename Sig::template trial_space<I>, dim>::type...> in{};
+    (load_and_interpolate<Sig, I>(P, tables, scratch, el, elem, qx, qy, qz, get<I>(in), invJ), ...);
+    return in;
+  }
+  (seq{});
+
+  const auto pos = tuple<tensor<double, dim>, tensor<double, dim, dim>>{x, Jm};
+
+  // quadrature weight of this point
+  const BasisTable1D& tb = P.test_basis;
+  double              w  = tb.w[qx] * tb.w[qy];
+  if (dim == 3) w *= tb.w[qz];
+
+  // --- state ---
+  State  state_old{};
+  State* qd = nullptr;
+  if constexpr (!std::is_same_v<State, Nothing> && !std::is_empty_v<State>) {
+    qd        = reinterpret_cast<State*>(P.qdata) + ((long long)e * QPE + ql);
+    state_old = *qd;
+  }
+
+  double src[ct];
+  double flux[ct][dim];
+  bool   have_values = false;
+  (void)have_values;
+
+  // physical -> parent on one output tuple, generic in the scalar type   (finite_element.hpp:301-303)
+  auto pull_back = [&](const auto& out, auto& s_out, auto& f_out) {
+    using out_t = std::decay_t<decltype(out)>;
+    SB_UNROLL
+    for (int a = 0; a < ct; a++) {
+      if constexpr (output_traits<out_t>::has_source) s_out[a] = source_component<ct>(get<0>(out), a) * dv;
+      if constexpr (output_traits<out_t>::has_flux) {
+        SB_UNROLL
+        for (int k = 0; k < dim; k++) {
+          auto sum = flux_component<ct, dim>(get<1>(out), a, 0) * invJ(k, 0);
+          SB_UNROLL
+          for (int j = 1; j < dim; j++) sum = sum + flux_component<ct, dim>(get<1>(out), a, j) * invJ(k, j);
+          f_out[a][k] = sum * dv;
+        }
+      }
+    }
+  };
+
+  using plain_out_t                = decltype(plain_output_type<Sig, QF, State>(seq{}));
+  constexpr bool has_source        = output_traits<plain_out_t>::has_source;
+  constexpr bool has_flux          = output_traits<plain_out_t>::has_flux;
+
+  auto take_values = [&](const auto& s_out, const auto& f_out) {
+    SB_UNROLL
+    for (int a = 0; a < ct; a++) {
+      if constexpr (has_source) src[a] = get_value(s_out[a]) * w;
+      if constexpr (has_flux) {
+        SB_UNROLL
+        for (int k = 0; k < dim; k++) flux[a][k] = get_value(f_out[a][k]) * w;
+      }
+    }
+  };
+
+  if constexpr (WRT < 0) {
+    State st  = state_old;
+    auto  out = call_qf_tuple<Sig>(qf, P.t, pos, st, inputs, seq{});
+    double s_out[ct];
+    double f_out[ct][dim];
+    pull_back(out, s_out, f_out);
+    take_values(s_out, f_out);
+    if constexpr (!std::is_same_v<State, Nothing> && !std::is_empty_v<State>) {
+      if (P.update_state && valid) *qd = st;
+    }
+  } else {
+    using DT                   = DerivativeTraits<Sig, WRT, QF, State>;
+    constexpr DerivativeLayout LY = DT::layout();
+    constexpr int              ck = DT::ck;
+    const long long            tile = blockIdx.x;
+    double* dq = P.dqf + tile * (long long)LY.entries * Sig::threads + threadIdx.x;
+    bool    first = true;
+
+    if constexpr (DT::value_pass_active) {
+      State st  = state_old;
+      auto  out = run_pass<Sig, WRT, -1, QF, State>(qf, P.t, pos, st, inputs, invJ, seq{});
+      using out_t = std::decay_t<decltype(out)>;
+      using S_t   = std::conditional_t<output_traits<out_t>::source_dual, dual<ck>, double>;
+      using F_t   = std::conditional_t<output_traits<out_t>::flux_dual, dual<ck>, double>;
+      S_t s_out[ct];
+      F_t f_out[ct][dim];
+      pull_back(out, s_out, f_out);
+      if (first) {
+        take_values(s_out, f_out);
+        if constexpr (!std::is_same_v<State, Nothing> && !std::is_empty_v<State>) {
+          if (P.update_state && valid) *qd = st;
+        }
+        first = false;
+      }
+      if (valid) {
+        SB_UNROLL
+        for (int a = 0; a < ct; a++) {
+          if constexpr (LY.has[0]) {
+            SB_UNROLL
+            for (int b = 0; b < ck; b++) dq[(long long)(LY.offset[0] + a * ck + b) * Sig::threads] = partial(s_out[a], b);
+          }
+          if constexpr (LY.has[2]) {
+            SB_UNROLL
+            for (int k = 0; k < dim; k++) {
+              SB_UNROLL
+              for (int b = 0; b < ck; b++)
+                dq[(long long)(LY.offset[2] + (a * dim + k) * ck + b) * Sig::threads] = partial(f_out[a][k], b);
+            }
+          }
+        }
+      }
+    }
+    if constexpr (DT::grad_pass_active) {
+      auto grad_pass = [&](auto row_c) {
+        constexpr int              row = decltype(row_c)::value;
+        constexpr DerivativeLayout LY  = DT::layout();  // (re-declared: captured constexpr locals are not constants)
+        State         st  = state_old;
+        auto          out = run_pass<Sig, WRT, row, QF, State>(qf, P.t, pos, st, inputs, invJ, seq{});
+        using out_t       = std::decay_t<decltype(out)>;
+        using S_t         = std::conditional_t<output_traits<out_t>::source_dual, dual<dim>, double>;
+        using F_t         = std::conditional_t<output_traits<out_t>::flux_dual, dual<dim>, double>;
+        S_t s_out[ct];
+        F_t f_out[ct][dim];
+        pull_back(out, s_out, f_out);
+        if (first) {
+          take_values(s_out, f_out);
+          if constexpr (!std::is_same_v<State, Nothing> && !std::is_empty_v<State>) {
+            if (P.update_state && valid) *qd = st;
+          }
+          first = false;
+        }
+        if (valid) {
+          SB_UNROLL
+          for (int a = 0; a < ct; a++) {
+            if constexpr (LY.has[1]) {
+              SB_UNROLL
+              for (int l = 0; l < dim; l++)
+                dq[(long long)(LY.offset[1] + (a * ck + row) * dim + l) * Sig::threads] = partial(s_out[a], l);
+            }
+            if constexpr (LY.has[3]) {
+              SB_UNROLL
+              for (int k = 0; k < dim; k++) {
+                SB_UNROLL
+                for (int l = 0; l < dim; l++)
+                  dq[(long long)(LY.offset[3] + ((a * dim + k) * ck + row) * dim + l) * Sig::threads] =
+                      partial(f_out[a][k], l);
+              }
+            }
+          }
+        }
+      };
+      [&]<int... R>(std::integer_sequence<int, R...>) { (grad_pass(std::integral_constant<int, R>{}), ...); }
+      (std::make_integer_sequence<int, ck>{});
+    }
+    if constexpr (!DT::value_pass_active && !DT::grad_pass_active) {
+      State  st  = state_old;
+      auto   out = call_qf_tuple<Sig>(qf, P.t, pos, st, inputs, seq{});
+      double s_out[ct];
+      double f_out[ct][dim];
+      pull_back(out, s_out, f_out);
+      take_values(s_out, f_out);
+      if constexpr (!std::is_same_v<State, Nothing> && !std::is_empty_v<State>) {
+        if (P.update_state && valid) *qd = st;
+      }
+    }
+  }
+
+  // --- integrate against the test space and write the E-vector block ---
+  if constexpr (has_source || has_flux) {
+    using TP = TensorProduct<dim, Sig::test_n, q, ct>;
+    __syncthreads();
+    const double* B = tables + (NT * 2 + 0) * MAX_Q * MAX_Q;
+    const double* G = tables + (NT * 2 + 1) * MAX_Q * MAX_Q;
+    double        out[ct];
+    if constexpr (!has_source) {
+      SB_UNROLL
+      for (int a = 0; a < ct; a++) src[a] = 0.0;
+    }
+    if constexpr (!has_flux) {
+      SB_UNROLL
+      for (int a = 0; a < ct; a++) {
+        SB_UNROLL
+        for (int k = 0; k < dim; k++) flux[a][k] = 0.0;
+      }
+    }
+    const bool owner = TP::template integrate<has_source, has_flux>(B, G, scratch + el * per, qx, qy, qz, src, flux, out);
+    if (owner && valid) {
+      constexpr int n    = Sig::test_n;
+      const int     node = (dim == 3) ? (qz * n + qy) * n + qx : qy * n + qx;
+      SB_UNROLL
+      for (int a = 0; a < ct; a++) P.r_E[((long long)elem * ct + a) * Sig::test_ndof + node] = out[a];
+    }
+  }
+}
+
+
+// ------------------------------------------------------------------------------------------------
+// Jacobian-vector product with the stored derivatives: dr_E = B^T ( dqf : B du )
+// (domain_integral_kernels.hpp:277-304, chain_rule :223-237).  Pure streaming over dqf: this is the HBM-bound kernel.
+// MASK bit b set <=> derivative block b (d00,d01,d10,d11) is present.
+// ------------------------------------------------------------------------------------------------
+template <int dim, int q, int nk, int ck, int nt, int ct, int MASK>
+struct JvpConfig {
+  static constexpr int  QPE     = ipow(q, dim);
+  static constexpr int  EPB     = elements_per_block(dim, q);
+  static constexpr int  threads = EPB * QPE;
+  static constexpr bool d00 = (MASK & 1) != 0, d01 = (MASK & 2) != 0, d10 = (MASK & 4) != 0, d11 = (MASK & 8) != 0;
+  using TPk = TensorProduct<dim, nk, q, ck>;
+  using TPt = TensorProduct<dim, nt, q, ct>;
+  static constexpr int per     = cmax(TPk::interp_scratch, TPt::integ_scratch);
+  static constexpr int smem_doubles = 4 * MAX_Q * MAX_Q + EPB * per;
+  static constexpr DerivativeLayout layout() { return make_layout(ct, ck, dim, d00, d01, d10, d11); }
+};
+
+template <int dim, int q, int nk, int ck, int nt, int ct, int MASK>
+__global__ void __launch_bounds__(JvpConfig<dim, q, nk, ck, nt, ct, MASK>::threads)
+    jvp_kernel(const __grid_constant__ JvpParams P)
+{
+  using C                       = JvpConfig<dim, q, nk, ck, nt, ct, MASK>;
+  constexpr DerivativeLayout LY = C::layout();
+  constexpr int QPE = C::QPE, EPB = C::EPB, per = C::per;
+  extern __shared__ double smem[];
+  double* tables  = smem;
+  double* scratch = smem + 4 * MAX_Q * MAX_Q;
+  for (int i = threadIdx.x; i < 4 * MAX_Q * MAX_Q; i += C::threads) {
+    const int           which = i / (2 * MAX_Q * MAX_Q);
+    const int           rem   = i - which * (2 * MAX_Q * MAX_Q);
+    const BasisTable1D& bt    = (which == 0) ? P.trial_basis : P.test_basis;
+    tables[i]                 = (rem < MAX_Q * MAX_Q) ? bt.B[rem] : bt.G[rem - MAX_Q * MAX_Q];
+  }
+  const int el = threadIdx.x / QPE;
+  const int ql = threadIdx.x - el * QPE;
+  const int qx = ql % q;
+  const int qy = (ql / q) % q;
+  const int qz = (dim == 3) ? ql / (q * q) : 0;
+
+  const int  e_raw = blockIdx.x * EPB + el;
+  const bool valid = e_raw < P.num_elements;
+  const int  e     = valid ? e_raw : P.num_elements - 1;
+  const int  elem  = P.elements[e];
+
+  // issue the derivative loads early: they are independent of the interpolation
+  const double* dq = P.dqf + (long long)blockIdx.x * LY.entries * C::threads + threadIdx.x;
+
+  // gather du
+  const FieldArg& f = P.trial;
+  for (int i = threadIdx.x; i < EPB * ck * C::TPk::ndof; i += C::threads) {
+    const int le   = i / (ck * C::TPk::ndof);
+    const int rem  = i - le * (ck * C::TPk::ndof);
+    const int a    = rem / C::TPk::ndof;
+    const int node = rem - a * C::TPk::ndof;
+    int       ee   = blockIdx.x * EPB + le;
+    if (ee >= P.num_elements) ee = P.num_elements - 1;
+    const int       ge  = P.elements[ee];
+    const long long idx = (long long)f.table[(long long)ge * C::TPk::ndof + node];
+    scratch[le * per + a * C::TPk::ndof + node] = f.L[idx * f.node_stride + a * f.comp_stride];
+  }
+  __syncthreads();
+  double v[ck];
+  double g[ck][dim];
+  C::TPk::template interpolate<(C::d00 || C::d10), (C::d01 || C::d11)>(tables, tables + MAX_Q * MAX_Q,
+                                                                        scratch + el * per, qx, qy, qz, v, g);
+
+  const BasisTable1D& tb = P.test_basis;
+  double              w  = tb.w[qx] * tb.w[qy];
+  if (dim == 3) w *= tb.w[qz];
+
+  constexpr bool has_source = C::d00 || C::d01;
+  constexpr bool has_flux   = C::d10 || C::d11;
+  double         src[ct];
+  double         flux[ct][dim];
+  const long long stride = C::threads;
+  SB_UNROLL
+  for (int a = 0; a < ct; a++) {
+    double s = 0.0;
+    if constexpr (C::d00) {
+      SB_UNROLL
+      for (int b = 0; b < ck; b++) s += __ldcs(dq + (LY.offset[0] + a * ck + b) * stride) * v[b];
+    }
+    if constexpr (C::d01) {
+      SB_UNROLL
+      for (int b = 0; b < ck; b++) {
+        SB_UNROLL
+        for (int l = 0; l < dim; l++) s += __ldcs(dq + (LY.offset[1] + (a * ck + b) * dim + l) * stride) * g[b][l];
+      }
+    }
+    src[a] = s * w;
+    SB_UNROLL
+    for (int k = 0; k < dim; k++) {
+      double fl = 0.0;
+      if constexpr (C::d10) {
+        SB_UNROLL
+        for (int b = 0; b < ck; b++) fl += __ldcs(dq + (LY.offset[2] + (a * dim + k) * ck + b) * stride) * v[b];
+      }
+      if constexpr (C::d11) {
+        SB_UNROLL
+        for (int b = 0; b < ck; b++) {
+          SB_UNROLL
+          for (int l = 0; l < dim; l++)
+            fl += __ldcs(dq + (LY.offset[3] + ((a * dim + k) * ck + b) * dim + l) * stride) * g[b][l];
+        }
+      }
+      flux[a][k] = fl * w;
+    }
+  }
+
+  __syncthreads();
+  double     out[ct];
+  const bool owner = C::TPt::template integrate<has_source, has_flux>(
+      tables + 2 * MAX_Q * MAX_Q, tables + 3 * MAX_Q * MAX_Q, scratch + el * per, qx, qy, qz, src, flux, out);
+  if (owner && valid) {
+    const int node = (dim == 3) ? (qz * nt + qy) * nt + qx : qy * nt + qx;
+    SB_UNROLL
+    for (int a = 0; a < ct; a++) P.r_E[((long long)elem * ct + a) * C::TPt::ndof + node] = out[a];
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// element stiffness matrices from the stored derivatives (domain_integral_kernels.hpp:327-361,
+// batch_apply_shape_fn hexahedron_H1.inl:132-167).  For every trial node J the ck trial components are
+// integrated together (ct*ck "components"), K_e is written trial-major (functional.hpp:599-601).
+// ------------------------------------------------------------------------------------------------
+template <int dim, int q, int nk, int ck, int nt, int ct, int MASK>
+struct ElemGradConfig {
+  static constexpr int  QPE     = ipow(q, dim);
+  static constexpr int  EPB     = elements_per_block(dim, q);
+  static constexpr int  threads = EPB * QPE;
+  static constexpr bool d00 = (MASK & 1) != 0, d01 = (MASK & 2) != 0, d10 = (MASK & 4) != 0, d11 = (MASK & 8) != 0;
+  using TPt = TensorProduct<dim, nt, q, ct * ck>;
+  static constexpr int ndof_k = ipow(nk, dim);
+  static constexpr int per    = TPt::integ_scratch;
+  static constexpr int smem_doubles = 4 * MAX_Q * MAX_Q + EPB * per;
+  static constexpr DerivativeLayout layout() { return make_layout(ct, ck, dim, d00, d01, d10, d11); }
+};
+
+template <int dim, int q, int nk, int ck, int nt, int ct, int MASK>
+__global__ void __launch_bounds__(ElemGradConfig<dim, q, nk, ck, nt, ct, MASK>::threads)
+    element_gradient_kernel(const __grid_constant__ ElemGradParams P)
+{
+  using C                       = ElemGradConfig<dim, q, nk, ck, nt, ct, MASK>;
+  constexpr DerivativeLayout LY = C::layout();
+  constexpr int QPE = C::QPE, EPB = C::EPB, per = C::per;
+  extern __shared__ double smem[];
+  double* tables  = smem;
+  double* scratch = smem + 4 * MAX_Q * MAX_Q;
+  for (int i = threadIdx.x; i < 4 * MAX_Q * MAX_Q; i += C::threads) {
+    const int           which = i / (2 * MAX_Q * MAX_Q);
+    const int           rem   = i - which * (2 * MAX_Q * MAX_Q);
+    const BasisTable1D& bt    = (which == 0) ? P.trial_basis : P.test_basis;
+    tables[i]                 = (rem < MAX_Q * MAX_Q) ? bt.B[rem] : bt.G[rem - MAX_Q * MAX_Q];
+  }
+  __syncthreads();
+  const double* Bk = tables;
+  const double* Gk = tables + MAX_Q * MAX_Q;
+  const double* Bt = tables + 2 * MAX_Q * MAX_Q;
+  const double* Gt = tables + 3 * MAX_Q * MAX_Q;
+
+  const int el = threadIdx.x / QPE;
+  const int ql = threadIdx.x - el * QPE;
+  const int qx = ql % q;
+  const int qy = (ql / q) % q;
+  const int qz = (dim == 3) ? ql / (q * q) : 0;
+
+  const int  e_raw = blockIdx.x * EPB + el;
+  const bool valid = e_raw < P.num_elements;
+  const int  e     = valid ? e_raw : P.num_elements - 1;
+  const int  elem  = P.elements[e];
+
+  const BasisTable1D& tb = P.test_basis;
+  double              w  = tb.w[qx] * tb.w[qy];
+  if (dim == 3) w *= tb.w[qz];
+
+  // this quadrature point's derivative blocks, pre-multiplied by the quadrature weight
+  const double*   dq     = P.dqf + (long long)blockIdx.x * LY.entries * C::threads + threadIdx.x;
+  const long long stride = C::threads;
+  double          D[LY.entries > 0 ? LY.entries : 1];
+  SB_UNROLL
+  for (int i = 0; i < LY.entries; i++) D[i] = dq[i * stride] * w;
+
+  constexpr bool has_source = C::d00 || C::d01;
+  constexpr bool has_flux   = C::d10 || C::d11;
+  constexpr int  cc         = ct * ck;
+  constexpr int  ndt        = C::TPt::ndof;
+  constexpr int  ndk        = C::ndof_k;
+
+  for (int J = 0; J < ndk; J++) {
+    const int jx = J % nk;
+    const int jy = (J / nk) % nk;
+    const int jz = (dim == 3) ? J / (nk * nk) : 0;
+    double    phi, dphi[dim];
+    if constexpr (dim == 3) {
+      const double bx = Bk[qx * nk + jx], by = Bk[qy * nk + jy], bz = Bk[qz * nk + jz];
+      phi     = bx * by * bz;
+      dphi[0] = Gk[qx * nk + jx] * by * bz;
+      dphi[1] = bx * Gk[qy * nk + jy] * bz;
+      dphi[2] = bx * by * Gk[qz * nk + jz];
+    } else {
+      const double bx = Bk[qx * nk + jx], by = Bk[qy * nk + jy];
+      phi     = bx * by;
+      dphi[0] = Gk[qx * nk + jx] * by;
+      dphi[1] = bx * Gk[qy * nk + jy];
+    }
+    // "component" index of the batched integrate: a * ck + b
+    double src[cc];
+    double flux[cc][dim];
+    SB_UNROLL
+    for (int a = 0; a < ct; a++) {
+      SB_UNROLL
+      for (int b = 0; b < ck; b++) {
+        double s = 0.0;
+        if constexpr (C::d00) s += D[LY.offset[0] + a * ck + b] * phi;
+        if constexpr (C::d01) {
+          SB_UNROLL
+          for (int l = 0; l < dim; l++) s += D[LY.offset[1] + (a * ck + b) * dim + l] * dphi[l];
+        }
+        src[a * ck + b] = s;
+        SB_UNROLL
+        for (int k = 0; k < dim; k++) {
+          double fl = 0.0;
+          if constexpr (C::d10) fl += D[LY.offset[2] + (a * dim + k) * ck + b] * phi;
+          if constexpr (C::d11) {
+            SB_UNROLL
+            for (int l = 0; l < dim; l++) fl += D[LY.offset[3] + ((a * dim + k) * ck + b) * dim + l] * dphi[l];
+          }
+          flux[a * ck + b][k] = fl;
+        }
+      }
+    }
+    __syncthreads();
+    double     out[cc];
+    const bool owner = C::TPt::template integrate<has_source, has_flux>(Bt, Gt, scratch + el * per, qx, qy, qz, src,
+                                                                        flux, out);
+    if (owner && valid) {
+      const int I = (dim == 3) ? (qz * nt + qy) * nt + qx : qy * nt + qx;
+      SB_UNROLL
+      for (int a = 0; a < ct; a++) {
+        SB_UNROLL
+        for (int b = 0; b < ck; b++) {
+          P.K_e[((long long)elem * (ck * ndk) + (b * ndk + J)) * (ct * ndt) + a * ndt + I] += out[a * ck + b];
+        }
+      }
+    }
+  }
+}
+
+}  // namespace b200
+}  // namespace serac

@@ -1,0 +1,167 @@
+// serac_b200: type erasure of the templated kernels into the C ABI's sb_kernel_table.
+//
+// The reference erases (geometry, Q, spaces, q-function) into three std::function tables per Integral
+// (src/serac/numerics/functional/integral.hpp:127-145, generate_kernels :184-222).  A C ABI cannot carry a template or
+// a std::function, so the same erasure is done here with plain function pointers: make_kernel_table<Sig, QF, State>()
+// instantiates, for every trial argument i, evaluation_with_AD_[i], jvp_[i] and element_gradient_[i]
+// (integral.hpp:205-221) and returns their launchers.  Any translation unit compiled by nvcc can do this for its own
+// functors; registry_*.cu does it for the named integrands shipped in the library.
+#pragma once
+
+#include <cstring>
+
+#include "serac_b200.h"
+#include "serac_b200/domain_integral.cuh"
+
+namespace serac {
+namespace b200 {
+
+extern "C" void sb_count_launch(void);  // launch counter lives in the library (capi.cu)
+
+inline FieldArg to_field(const sb_field_arg& f)
+{
+  return FieldArg{f.L_dev, f.table_dev, (long long)f.node_stride, (long long)f.comp_stride};
+}
+
+template <typename K>
+inline int ensure_smem(K kernel, size_t bytes)
+{
+  if (bytes > 48 * 1024) {
+    cudaError_t err = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(bytes));
+    if (err != cudaSuccess) return int(err);
+  }
+  return 0;
+}
+
+template <typename Sig, int WRT, typename QF, typename State>
+int launch_evaluate(const sb_eval_args* a, const void* qf_blob, void* stream)
+{
+  constexpr int NT = Sig::NT;
+  EvalParams<NT> P{};
+  auto           fill = [&]<int... I>(std::integer_sequence<int, I...>)
+  {
+    ((P.trial[I] = to_field(a->trial[I]), P.trial_basis[I] = make_basis_table(Sig::template trial_space<I>::order, Sig::q)),
+     ...);
+  };
+  fill(std::make_integer_sequence<int, NT>{});
+  P.test_basis   = make_basis_table(Sig::test_space::order, Sig::q);
+  P.X_q          = a->X_q_dev;
+  P.J_q          = a->J_q_dev;
+  P.elements     = a->elements_dev;
+  P.num_elements = a->num_elements;
+  P.r_E          = a->r_E_dev;
+  P.dqf          = a->dqf_dev;
+  P.qdata        = a->qdata_dev;
+  P.update_state = a->update_state;
+  P.t            = a->t;
+  if (a->num_elements <= 0) return 0;
+  auto         kernel = &evaluation_kernel<Sig, WRT, QF, State>;
+  const size_t smem   = size_t(eval_smem_doubles<Sig>()) * sizeof(double);
+  if (int e = ensure_smem(kernel, smem)) return e;
+  const int grid = (a->num_elements + Sig::EPB - 1) / Sig::EPB;
+  alignas(16) unsigned char qf_storage[sizeof(QF)];
+  std::memcpy(qf_storage, qf_blob, sizeof(QF));
+  kernel<<<grid, Sig::threads, smem, cudaStream_t(stream)>>>(P, *reinterpret_cast<const QF*>(qf_storage));
+  sb_count_launch();
+  return int(cudaGetLastError());
+}
+
+template <typename Sig, int WRT, int MASK>
+int launch_jvp(const sb_jvp_args* a, void* stream)
+{
+  using trial       = typename Sig::template trial_space<WRT>;
+  constexpr int nk  = trial::order + 1;
+  constexpr int ck  = trial::components;
+  using C           = JvpConfig<Sig::dim, Sig::q, nk, ck, Sig::test_n, Sig::test_c, MASK>;
+  if constexpr (MASK == 0) {
+    return 0;  // structurally zero derivative: dr_E block stays as the caller zeroed it
+  } else {
+    JvpParams P{};
+    P.trial        = to_field(a->trial);
+    P.trial_basis  = make_basis_table(trial::order, Sig::q);
+    P.test_basis   = make_basis_table(Sig::test_space::order, Sig::q);
+    P.elements     = a->elements_dev;
+    P.num_elements = a->num_elements;
+    P.dqf          = a->dqf_dev;
+    P.r_E          = a->r_E_dev;
+    if (a->num_elements <= 0) return 0;
+    auto         kernel = &jvp_kernel<Sig::dim, Sig::q, nk, ck, Sig::test_n, Sig::test_c, MASK>;
+    const size_t smem   = size_t(C::smem_doubles) * sizeof(double);
+    if (int e = ensure_smem(kernel, smem)) return e;
+    const int grid = (a->num_elements + C::EPB - 1) / C::EPB;
+    kernel<<<grid, C::threads, smem, cudaStream_t(stream)>>>(P);
+    sb_count_launch();
+    return int(cudaGetLastError());
+  }
+}
+
+template <typename Sig, int WRT, int MASK>
+int launch_element_gradient(const sb_elem_grad_args* a, void* stream)
+{
+  using trial      = typename Sig::template trial_space<WRT>;
+  constexpr int nk = trial::order + 1;
+  constexpr int ck = trial::components;
+  using C          = ElemGradConfig<Sig::dim, Sig::q, nk, ck, Sig::test_n, Sig::test_c, MASK>;
+  if constexpr (MASK == 0) {
+    return 0;
+  } else {
+    ElemGradParams P{};
+    P.trial_basis  = make_basis_table(trial::order, Sig::q);
+    P.test_basis   = make_basis_table(Sig::test_space::order, Sig::q);
+    P.elements     = a->elements_dev;
+    P.num_elements = a->num_elements;
+    P.dqf          = a->dqf_dev;
+    P.K_e          = a->K_e_dev;
+    if (a->num_elements <= 0) return 0;
+    auto         kernel = &element_gradient_kernel<Sig::dim, Sig::q, nk, ck, Sig::test_n, Sig::test_c, MASK>;
+    const size_t smem   = size_t(C::smem_doubles) * sizeof(double);
+    if (int e = ensure_smem(kernel, smem)) return e;
+    const int grid = (a->num_elements + C::EPB - 1) / C::EPB;
+    kernel<<<grid, C::threads, smem, cudaStream_t(stream)>>>(P);
+    sb_count_launch();
+    return int(cudaGetLastError());
+  }
+}
+
+template <typename Sig, typename QF, typename State, int WRT>
+void fill_wrt(sb_kernel_table& T)
+{
+  using DT                   = DerivativeTraits<Sig, WRT, QF, State>;
+  constexpr DerivativeLayout L = DT::layout();
+  constexpr int mask = (L.has[0] ? 1 : 0) | (L.has[1] ? 2 : 0) | (L.has[2] ? 4 : 0) | (L.has[3] ? 8 : 0);
+  T.evaluate_ad[WRT]        = &launch_evaluate<Sig, WRT, QF, State>;
+  T.jvp[WRT]                = &launch_jvp<Sig, WRT, mask>;
+  T.element_gradient[WRT]   = &launch_element_gradient<Sig, WRT, mask>;
+  T.derivative_mask[WRT]    = mask;
+  T.derivative_entries[WRT] = L.entries;
+}
+
+/// State = serac::Nothing: q-function takes no state argument; serac::Empty: takes an Empty& it never touches;
+/// anything else: trivially copyable per-quadrature-point struct
+template <typename Sig, typename QF, typename State>
+sb_kernel_table make_kernel_table()
+{
+  static_assert(std::is_trivially_copyable_v<QF>, "q-function functors are copied by value into kernel parameters");
+  sb_kernel_table T{};
+  T.geom            = int(Sig::geometry);
+  T.dim             = Sig::dim;
+  T.q               = Sig::q;
+  T.num_trials      = Sig::NT;
+  T.test_order      = Sig::test_space::order;
+  T.test_components = Sig::test_c;
+  auto fill         = [&]<int... I>(std::integer_sequence<int, I...>)
+  {
+    ((T.trial_order[I] = Sig::template trial_space<I>::order,
+      T.trial_components[I] = Sig::template trial_space<I>::components, fill_wrt<Sig, QF, State, I>(T)),
+     ...);
+  };
+  fill(std::make_integer_sequence<int, Sig::NT>{});
+  T.qf_bytes           = sizeof(QF);
+  T.state_bytes        = (std::is_same_v<State, Nothing> || std::is_empty_v<State>) ? 0 : sizeof(State);
+  T.elements_per_block = Sig::EPB;
+  T.evaluate           = &launch_evaluate<Sig, -1, QF, State>;
+  return T;
+}
+
+}  // namespace b200
+}  // namespace serac

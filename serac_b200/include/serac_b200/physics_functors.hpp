@@ -1,0 +1,341 @@
+// serac_b200: device-ready q-function functors of the physics modules that call Functional.
+//
+// These mirror, with the same names, members, argument meaning and maths, the functors the reference's callers build
+// around a material model before handing it to Functional::AddDomainIntegral:
+//   solid_mechanics::LinearIsotropic / NeoHookean / StVenantKirchhoff   src/serac/physics/materials/solid_material.hpp:24-127
+//   solid_mechanics::J2SmallStrain / J2 + hardening laws                src/serac/physics/materials/solid_material.hpp:130-330
+//   SolidMechanics::MaterialStressFunctor                               src/serac/physics/solid_mechanics.hpp:808-853
+//   heat_transfer::LinearIsotropicConductor                             src/serac/physics/materials/thermal_material.hpp:20-65
+//   HeatTransfer::ThermalMaterialIntegrand                              src/serac/physics/heat_transfer.hpp:381-405
+//   detail::ShapeCorrection, ShapeAwareIntegrandWrapper[WithState]      src/serac/numerics/functional/shape_aware_functional.hpp:37-141,364-438
+// Every operator() is SERAC_HOST_DEVICE and free of host-only constructs (no slic, no std::function, no host lambdas)
+// so the evaluation kernels can inline them (SURVEY.md Appendix C lists what the reference still lacks).
+#pragma once
+
+#include "serac_b200/finite_element.hpp"
+#include "serac_b200/tensor.hpp"
+#include "serac_b200/scalar_solver.hpp"
+
+namespace serac {
+
+constexpr int SOURCE     = 0;
+constexpr int FLUX       = 1;
+constexpr int VALUE      = 0;
+constexpr int DERIVATIVE = 1;
+
+enum class GeometricNonlinearities
+{
+  On,
+  Off
+};
+
+namespace solid_mechanics {
+
+/// linear isotropic elasticity (solid_material.hpp:24-50)
+struct LinearIsotropic {
+  using State = Empty;
+  template <typename T, int dim>
+  SERAC_HOST_DEVICE auto operator()(State&, const tensor<T, dim, dim>& du_dX) const
+  {
+    auto I       = Identity<dim>();
+    auto lambda  = K - (2.0 / 3.0) * G;
+    auto epsilon = 0.5 * (transpose(du_dX) + du_dX);
+    return lambda * tr(epsilon) * I + 2.0 * G * epsilon;
+  }
+  double density;
+  double K;
+  double G;
+};
+
+template <typename T, int dim>
+SERAC_HOST_DEVICE auto greenStrain(const tensor<T, dim, dim>& grad_u)
+{
+  return 0.5 * (grad_u + transpose(grad_u) + dot(transpose(grad_u), grad_u));
+}
+
+/// St. Venant-Kirchhoff (solid_material.hpp:61-92)
+struct StVenantKirchhoff {
+  using State = Empty;
+  template <typename T, int dim>
+  SERAC_HOST_DEVICE auto operator()(State&, const tensor<T, dim, dim>& grad_u) const
+  {
+    auto       I     = Identity<dim>();
+    auto       F     = grad_u + I;
+    const auto E     = greenStrain(grad_u);
+    const auto S     = K * tr(E) * I + 2.0 * G * dev(E);
+    const auto P     = dot(F, S);
+    const auto sigma = dot(P, transpose(F)) / det(F);
+    return sigma;
+  }
+  double density;
+  double K;
+  double G;
+};
+
+/// compressible neo-Hookean (solid_material.hpp:98-127)
+struct NeoHookean {
+  using State = Empty;
+  template <typename T, int dim>
+  SERAC_HOST_DEVICE auto operator()(State&, const tensor<T, dim, dim>& du_dX) const
+  {
+    auto I         = Identity<dim>();
+    auto lambda    = K - (2.0 / 3.0) * G;
+    auto B_minus_I = du_dX * transpose(du_dX) + transpose(du_dX) + du_dX;
+    auto J_minus_1 = detApIm1(du_dX);
+    auto J         = J_minus_1 + 1;
+    return (lambda * log1p(J_minus_1) * I + G * B_minus_I) / J;
+  }
+  double density;
+  double K;
+  double G;
+};
+
+/// sigma_y + Hi * eqps (solid_material.hpp:132-149)
+struct LinearHardening {
+  double sigma_y;
+  double Hi;
+  template <typename T>
+  SERAC_HOST_DEVICE auto operator()(const T accumulated_plastic_strain) const
+  {
+    return sigma_y + Hi * accumulated_plastic_strain;
+  }
+};
+
+/// sigma_y (1 + eqps/eps0)^(1/n) (solid_material.hpp:154-173)
+struct PowerLawHardening {
+  double sigma_y;
+  double n;
+  double eps0;
+  template <typename T>
+  SERAC_HOST_DEVICE auto operator()(const T accumulated_plastic_strain) const
+  {
+    return sigma_y * pow(1.0 + accumulated_plastic_strain / eps0, 1.0 / n);
+  }
+};
+
+/// Voce saturation hardening (solid_material.hpp:180-198)
+struct VoceHardening {
+  double sigma_y;
+  double sigma_sat;
+  double strain_constant;
+  template <typename T>
+  SERAC_HOST_DEVICE auto operator()(const T accumulated_plastic_strain) const
+  {
+    return sigma_sat - (sigma_sat - sigma_y) * exp(-1.0 * accumulated_plastic_strain / strain_constant);
+  }
+};
+
+/// small-strain J2 plasticity with isotropic + linear kinematic hardening (solid_material.hpp:201-259)
+template <typename HardeningType>
+struct J2SmallStrain {
+  static constexpr int    dim = 3;
+  static constexpr double tol = 1e-10;
+
+  double        E;
+  double        nu;
+  HardeningType hardening;
+  double        Hk;
+  double        density;
+
+  struct State {
+    tensor<double, dim, dim> plastic_strain;
+    double                   accumulated_plastic_strain;
+  };
+
+  /// return-map residual: trial_q - (3G + Hk) d - flow_stress(eqps_old + d)
+  struct Residual {
+    double        eqps_old, G, Hk;
+    HardeningType hardening;
+    template <typename T1, typename T2>
+    SERAC_HOST_DEVICE auto operator()(const T1& delta_eqps, const T2& trial_q) const
+    {
+      return trial_q - (3.0 * G + Hk) * delta_eqps - hardening(eqps_old + delta_eqps);
+    }
+  };
+
+  template <typename T>
+  SERAC_HOST_DEVICE auto operator()(State& state, const tensor<T, dim, dim>& du_dX) const
+  {
+    auto         I = Identity<dim>();
+    const double K = E / (3.0 * (1.0 - 2.0 * nu));
+    const double G = 0.5 * E / (1.0 + nu);
+
+    // (i) elastic predictor
+    auto el_strain = sym(du_dX) - state.plastic_strain;
+    auto p         = K * tr(el_strain);
+    auto s         = 2.0 * G * dev(el_strain);
+    auto sigma_b   = (2.0 / 3.0 * Hk) * state.plastic_strain;
+    auto eta       = s - sigma_b;
+    auto q         = ::sqrt(1.5) * norm(eta);
+
+    // (ii) admissibility
+    const double eqps_old = state.accumulated_plastic_strain;
+    Residual     residual{eqps_old, G, Hk, hardening};
+    if (residual(0.0, get_value(q)) > tol * hardening.sigma_y) {
+      // (iii) return mapping
+      ScalarSolverOptions opts{0, tol * hardening.sigma_y, 25};
+      double              lower_bound = 0.0;
+      double              upper_bound = (get_value(q) - hardening(eqps_old)) / (3.0 * G + Hk);
+      auto                delta_eqps  = get<0>(solve_scalar_equation(residual, 0.0, lower_bound, upper_bound, opts, q));
+
+      auto Np = 1.5 * eta / q;
+
+      s = s - 2.0 * G * delta_eqps * Np;
+      state.accumulated_plastic_strain += get_value(delta_eqps);
+      state.plastic_strain += get_value(delta_eqps) * get_value(Np);
+    }
+    return s + p * I;
+  }
+};
+
+}  // namespace solid_mechanics
+
+namespace heat_transfer {
+
+/// constant isotropic conductor (thermal_material.hpp:20-65); returns {volumetric heat capacity, heat flux}
+struct LinearIsotropicConductor {
+  LinearIsotropicConductor(double density = 1.0, double specific_heat_capacity = 1.0, double conductivity = 1.0)
+      : density_(density), specific_heat_capacity_(specific_heat_capacity), conductivity_(conductivity)
+  {
+  }
+  template <typename T1, typename T2, typename T3>
+  SERAC_HOST_DEVICE auto operator()(const T1&, const T2&, const T3& temperature_gradient) const
+  {
+    return serac::tuple{density_ * specific_heat_capacity_, -1.0 * conductivity_ * temperature_gradient};
+  }
+  double density_;
+  double specific_heat_capacity_;
+  double conductivity_;
+};
+
+}  // namespace heat_transfer
+
+/// q-function SolidMechanics::setMaterial registers (solid_mechanics.hpp:808-853)
+template <typename Material>
+struct MaterialStressFunctor {
+  SERAC_HOST_DEVICE MaterialStressFunctor(Material material, GeometricNonlinearities gn)
+      : material_(material), geom_nonlin_(gn)
+  {
+  }
+  Material                material_;
+  GeometricNonlinearities geom_nonlin_;
+
+  template <typename X, typename State, typename Displacement, typename Acceleration, typename... Params>
+  SERAC_HOST_DEVICE auto operator()(double, X, State& state, Displacement displacement, Acceleration acceleration,
+                                    Params... params) const
+  {
+    auto du_dX   = get<DERIVATIVE>(displacement);
+    auto d2u_dt2 = get<VALUE>(acceleration);
+
+    auto stress = material_(state, du_dX, params...);
+
+    constexpr int dim = std::decay_t<decltype(du_dX)>::first_dim;
+    auto          dx_dX = 0.0 * du_dX + Identity<dim>();
+    if (geom_nonlin_ == GeometricNonlinearities::On) {
+      dx_dX = dx_dX + du_dX;
+    }
+    auto flux = dot(stress, transpose(inv(dx_dX))) * det(dx_dX);
+    return serac::tuple{material_.density * d2u_dt2, flux};
+  }
+};
+
+/// q-function HeatTransfer::setMaterial registers (heat_transfer.hpp:381-405)
+template <typename MaterialType>
+struct ThermalMaterialIntegrand {
+  SERAC_HOST_DEVICE ThermalMaterialIntegrand(MaterialType material) : material_(material) {}
+  template <typename X, typename T, typename dT_dt, typename... Params>
+  SERAC_HOST_DEVICE auto operator()(double, X x, T temperature, dT_dt dtemp_dt, Params... params) const
+  {
+    auto u     = get<VALUE>(temperature);
+    auto du_dX = get<DERIVATIVE>(temperature);
+    auto du_dt = get<VALUE>(dtemp_dt);
+    auto resp  = material_(x, u, du_dX, params...);
+    return serac::tuple{get<0>(resp) * du_dt, -1.0 * get<1>(resp)};
+  }
+  MaterialType material_;
+};
+
+namespace detail {
+
+/// pull-backs for a shape displacement field p: x = X + p (shape_aware_functional.hpp:37-141)
+template <int dim, typename shape_type>
+struct ShapeCorrection {
+  using jacobian_type = std::decay_t<decltype(get<DERIVATIVE>(std::declval<shape_type>()))>;
+  using scalar_type   = typename jacobian_type::value_type;
+
+  SERAC_HOST_DEVICE ShapeCorrection(Dimension<dim>, const shape_type& p)
+      : J_(Identity<dim>() + get<DERIVATIVE>(p)), detJ_(det(J_)), inv_J_(inv(J_)), inv_JT_(transpose(inv_J_))
+  {
+  }
+
+  /// du/dx' = du/dX (dx'/dX)^-1 for H1 / L2 trial arguments
+  template <typename space_type, typename trial_type>
+  SERAC_HOST_DEVICE auto modify_trial_argument(space_type, const trial_type& u) const
+  {
+    static_assert(space_type::family == Family::H1 || space_type::family == Family::L2,
+                  "shape-aware pull-back implemented for H1 and L2 trial spaces");
+    auto trial_derivative = dot(get<DERIVATIVE>(u), inv_J_);
+    return serac::tuple{get<VALUE>(u), trial_derivative};
+  }
+
+  /// map the q-function's (source, flux) back to the reference configuration
+  template <typename test_space, typename q_func_type>
+  SERAC_HOST_DEVICE auto modify_shape_aware_qf_return(test_space, const q_func_type& v) const
+  {
+    if constexpr (std::is_same_v<test_space, double>) {
+      return detJ_ * v;
+    } else {
+      auto modified_flux   = dot(get<FLUX>(v), inv_JT_) * detJ_;
+      auto modified_source = get<SOURCE>(v) * detJ_;
+      return serac::tuple{modified_source, modified_flux};
+    }
+  }
+
+  tensor<scalar_type, dim, dim> J_;
+  scalar_type                   detJ_;
+  tensor<scalar_type, dim, dim> inv_J_;
+  tensor<scalar_type, dim, dim> inv_JT_;
+};
+
+}  // namespace detail
+
+/// what ShapeAwareFunctional::AddDomainIntegral wraps every integrand in (shape_aware_functional.hpp:364-438,456-468):
+/// argument 0 is the shape displacement, the remaining arguments are the user's trial functions.
+template <typename Integrand, int dim, typename test_space, typename... trial_spaces>
+struct ShapeAwareIntegrandWrapper {
+  SERAC_HOST_DEVICE ShapeAwareIntegrandWrapper(Integrand integrand) : integrand_(integrand) {}
+  Integrand integrand_;
+
+  template <typename PositionType, typename ShapeValueType, typename... QFuncArgs>
+  SERAC_HOST_DEVICE auto operator()(double time, PositionType x, ShapeValueType shape_val,
+                                    QFuncArgs... qfunc_args) const
+  {
+    detail::ShapeCorrection<dim, ShapeValueType> shape_correction(Dimension<dim>{}, shape_val);
+    auto x_mod = serac::tuple{get<VALUE>(x) + get<VALUE>(shape_val),
+                              get<DERIVATIVE>(x) + get<DERIVATIVE>(shape_val) * get<DERIVATIVE>(x)};
+    auto unmodified =
+        integrand_(time, x_mod, shape_correction.modify_trial_argument(trial_spaces{}, qfunc_args)...);
+    return shape_correction.modify_shape_aware_qf_return(test_space{}, unmodified);
+  }
+};
+
+/// same, for integrands with quadrature-point state
+template <typename Integrand, int dim, typename test_space, typename... trial_spaces>
+struct ShapeAwareIntegrandWrapperWithState {
+  SERAC_HOST_DEVICE ShapeAwareIntegrandWrapperWithState(Integrand integrand) : integrand_(integrand) {}
+  Integrand integrand_;
+
+  template <typename PositionType, typename StateType, typename ShapeValueType, typename... QFuncArgs>
+  SERAC_HOST_DEVICE auto operator()(double time, PositionType x, StateType& state, ShapeValueType shape_val,
+                                    QFuncArgs... qfunc_args) const
+  {
+    detail::ShapeCorrection<dim, ShapeValueType> shape_correction(Dimension<dim>{}, shape_val);
+    auto x_mod = serac::tuple{get<VALUE>(x) + get<VALUE>(shape_val),
+                              get<DERIVATIVE>(x) + get<DERIVATIVE>(shape_val) * get<DERIVATIVE>(x)};
+    auto unmodified =
+        integrand_(time, x_mod, state, shape_correction.modify_trial_argument(trial_spaces{}, qfunc_args)...);
+    return shape_correction.modify_shape_aware_qf_return(test_space{}, unmodified);
+  }
+};
+
+}  // namespace serac
