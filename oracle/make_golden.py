@@ -1,0 +1,132 @@
+"""TEST INFRASTRUCTURE ONLY (oracle/): builds parity problems with the REFERENCE oracle (oracle/ref.py) and writes them as
+small golden fixtures under tests/golden/.  Each fixture holds the inputs the product needs (native element dofs, mesh
+nodes, L-vectors) and the reference's outputs for them (dof_info, X_q/J_q, residual, JVP, element matrices, CSR).
+
+    python oracle/make_golden.py            # regenerates every fixture listed in FIXTURES (needs oracle/_ref)
+
+`reference_problem(...)` is also imported by the tests to run live comparisons at other sizes when oracle/_ref exists."""
+import os
+import sys
+
+import numpy as np
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from oracle import ref  # noqa: E402
+
+GOLDEN_DIR = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests", "golden")
+REFERENCE_MESHES = "/root/reference/data/meshes"
+
+
+def make_mesh(spec):
+    """spec: ("file", name, refinements) | ("cart3d", nx, ny, nz, perturb) | ("cart2d", nx, ny, perturb)"""
+    if spec[0] == "file":
+        return ref.Mesh.from_file(os.path.join(REFERENCE_MESHES, spec[1]), spec[2])
+    if spec[0] == "cart3d":
+        m = ref.Mesh.cartesian3d(spec[1], spec[2], spec[3])
+        if spec[4]:
+            m.perturb(spec[4])
+        return m
+    if spec[0] == "cart2d":
+        m = ref.Mesh.cartesian2d(spec[1], spec[2])
+        if spec[3]:
+            m.perturb(spec[3])
+        return m
+    raise ValueError(spec)
+
+
+def reference_problem(mesh_spec, kind, p, params, vdim, seed=42, with_matrix=True, shape_amp=0.0, state_init=None):
+    """Runs the reference path for one Integral on the whole mesh with signature test(shape p=1 vector, u, a)
+    (SolidMechanics: vdim = dim; HeatTransfer: vdim = 1) and returns inputs + outputs as a dict of numpy arrays."""
+    mesh = make_mesh(mesh_spec)
+    dim = mesh.dim
+    tag = f"{dim}d_p{p}"
+    space = ref.Space(mesh, p, vdim)
+    shape_space = ref.Space(mesh, 1, dim)
+    rng = np.random.default_rng(seed)
+    U = 0.01 * rng.uniform(-1.0, 1.0, space.vsize)  # keeps F invertible
+    A = rng.uniform(-1.0, 1.0, space.vsize)
+    S = shape_amp * rng.uniform(-1.0, 1.0, shape_space.vsize)
+    dU = rng.uniform(0.0, 1.0, space.vsize)  # check_gradient.hpp:19,26
+    q = p + 1
+    order, ordering, nodes, nodes_info = mesh.nodes()
+    X_q, J_q = mesh.geometric_factors(q)
+
+    I = ref.Integral(f"{kind}_{tag}", mesh, params)
+    out = dict(
+        kind=kind, geom=mesh.geom, dim=dim, p=p, vdim=vdim, ne=mesh.ne, params=np.asarray(params, dtype=np.float64),
+        native_dofs=space.native_dofs(), dof_info=space.dof_info(), num_nodes=space.num_nodes,
+        shape_native_dofs=shape_space.native_dofs(), shape_dof_info=shape_space.dof_info(),
+        shape_num_nodes=shape_space.num_nodes,
+        mesh_order=order, mesh_ordering=ordering, mesh_nodes=nodes, mesh_dof_info=nodes_info,
+        mesh_num_nodes=len(nodes) // dim,
+        U=U, A=A, S=S, dU=dU, X_q=X_q, J_q=J_q,
+    )
+    ins = [shape_space.gather(S), space.gather(U), space.gather(A)]
+    out["U_E"] = ins[1]
+    state_bytes = I.state_bytes()
+    if state_bytes:
+        if state_init is not None:
+            I.set_qdata(state_init)
+        out["qdata0"] = I.get_qdata()
+    # residual without differentiation (functional.hpp:446-498 with P = identity)
+    r_E = I.mult(0.0, ins, space.esize)
+    out["r_E"] = r_E
+    out["r"] = space.scatter_add(r_E, np.zeros(space.vsize))
+    # residual with derivative store w.r.t. u (argument 1) -- values must equal the plain residual
+    r_E_ad = I.mult(0.0, ins, space.esize, wrt=1)
+    out["r_E_ad"] = r_E_ad
+    # Jacobian action (functional.hpp:406-432)
+    dr_E = I.jvp(1, space.gather(dU), space.esize)
+    out["dr_E"] = dr_E
+    out["dr"] = space.scatter_add(dr_E, np.zeros(space.vsize))
+    # derivative w.r.t. the acceleration (argument 2: the mass matrix) and the shape field (argument 0)
+    I.mult(0.0, ins, space.esize, wrt=2)
+    out["dr_da"] = space.scatter_add(I.jvp(2, space.gather(dU), space.esize), np.zeros(space.vsize))
+    dS = rng.uniform(0.0, 1.0, shape_space.vsize)
+    out["dS"] = dS
+    I.mult(0.0, ins, space.esize, wrt=0)
+    out["dr_dshape"] = space.scatter_add(I.jvp(0, shape_space.gather(dS), space.esize), np.zeros(space.vsize))
+    if state_bytes:
+        # committing the state (domain_integral_kernels.hpp:143-147)
+        I.mult(0.0, ins, space.esize, update_state=True)
+        out["qdata1"] = I.get_qdata()
+        out["r_E_after_commit"] = I.mult(0.0, ins, space.esize)
+        I.set_qdata(out["qdata0"])
+    if with_matrix:
+        I.mult(0.0, ins, space.esize, wrt=1)
+        npe = space.dof_info().shape[1]
+        K_e = I.element_gradient(1, mesh.ne, npe * vdim, npe * vdim)
+        out["K_e"] = K_e
+        csr = ref.Csr(space, space)
+        rp, ci = csr.pattern()
+        out["row_ptr"], out["col_ind"] = rp, ci
+        out["values"] = csr.assemble(K_e)
+    return out
+
+
+# (file name, kwargs of reference_problem)
+FIXTURES = [
+    ("solid_neohookean_hex_p2_patch", dict(mesh_spec=("file", "patch3D_hexes.mesh", 0), kind="solid_neohookean", p=2,
+                                           params=[1.0, 100.0, 50.0, 1.0], vdim=3, shape_amp=0.01)),
+    ("solid_neohookean_hex_p1_beam", dict(mesh_spec=("file", "beam-hex.mesh", 0), kind="solid_neohookean", p=1,
+                                          params=[1.0, 100.0, 50.0, 1.0], vdim=3)),
+    ("solid_neohookean_hex_p3_cart", dict(mesh_spec=("cart3d", 2, 2, 1, 0.02), kind="solid_neohookean", p=3,
+                                          params=[1.0, 100.0, 50.0, 1.0], vdim=3, with_matrix=False)),
+    ("solid_linear_isotropic_hex_p2_cart", dict(mesh_spec=("cart3d", 2, 1, 2, 0.02), kind="solid_linear_isotropic",
+                                                p=2, params=[2.0, 100.0, 50.0, 0.0], vdim=3)),
+    ("solid_neohookean_quad_p2_cart", dict(mesh_spec=("cart2d", 3, 2, 0.02), kind="solid_neohookean", p=2,
+                                           params=[1.0, 100.0, 50.0, 1.0], vdim=2)),
+]
+
+
+def main():
+    os.makedirs(GOLDEN_DIR, exist_ok=True)
+    for name, kw in FIXTURES:
+        data = reference_problem(**kw)
+        path = os.path.join(GOLDEN_DIR, name + ".npz")
+        np.savez_compressed(path, **data)
+        print(f"{name}: ne={data['ne']} vsize={len(data['U'])} -> {os.path.getsize(path) / 1024:.0f} KiB")
+
+
+if __name__ == "__main__":
+    main()

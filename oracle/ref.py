@@ -1,0 +1,226 @@
+"""TEST INFRASTRUCTURE ONLY (oracle/): ctypes binding of oracle/_ref/libserac_ref.so -- the REFERENCE's own Functional
+building blocks compiled from /root/reference (see oracle/ref_driver.hpp).  Used by tests (to validate the numpy
+restatement and to generate golden fixtures) and by bench.py's cpu_baseline / --impl reference legs.  Never imported by
+the product package."""
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB_PATH = os.path.join(_HERE, "_ref", "libserac_ref.so")
+
+GEOM = {"segment": 1, "triangle": 2, "quad": 3, "tet": 4, "hex": 5}
+BYNODES, BYVDIM = 0, 1
+
+
+def available():
+    return os.path.exists(_LIB_PATH)
+
+
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        L = C.CDLL(_LIB_PATH, mode=os.RTLD_NOW | os.RTLD_DEEPBIND)  # python exports symbols that clash with mfem otherwise
+        vp, i, d, l = C.c_void_p, C.c_int, C.c_double, C.c_long
+        sig = {
+            "ref_mesh_from_file": (vp, [C.c_char_p, i]),
+            "ref_mesh_cartesian3d": (vp, [i, i, i, d, d, d]),
+            "ref_mesh_cartesian2d": (vp, [i, i, d, d]),
+            "ref_mesh_destroy": (None, [vp]),
+            "ref_mesh_dim": (i, [vp]),
+            "ref_mesh_num_elements": (i, [vp]),
+            "ref_mesh_perturb": (None, [vp, d]),
+            "ref_mesh_nodes_order": (i, [vp]),
+            "ref_mesh_nodes_ordering": (i, [vp]),
+            "ref_mesh_nodes_size": (l, [vp]),
+            "ref_mesh_nodes": (None, [vp, vp]),
+            "ref_mesh_nodes_dof_info": (l, [vp, i, vp]),
+            "ref_space_create": (vp, [vp, i, i, i]),
+            "ref_space_destroy": (None, [vp]),
+            "ref_space_vsize": (l, [vp]),
+            "ref_space_num_nodes": (l, [vp]),
+            "ref_space_esize": (l, [vp, i]),
+            "ref_space_native_dofs": (l, [vp, i, vp]),
+            "ref_space_dof_info": (l, [vp, i, vp]),
+            "ref_space_gather": (None, [vp, i, vp, vp]),
+            "ref_space_scatter_add": (None, [vp, i, vp, vp]),
+            "ref_lex_perm": (i, [i, i, vp]),
+            "ref_geometric_factors": (None, [vp, i, i, vp, vp]),
+            "ref_csr_create": (vp, [vp, vp]),
+            "ref_csr_destroy": (None, [vp]),
+            "ref_csr_nnz": (l, [vp]),
+            "ref_csr_num_rows": (l, [vp]),
+            "ref_csr_pattern": (None, [vp, vp, vp]),
+            "ref_csr_assemble": (None, [vp, vp, vp, i, vp, vp]),
+            "ref_num_kinds": (i, []),
+            "ref_kind_name": (C.c_char_p, [i]),
+            "ref_integral_create": (vp, [C.c_char_p, vp, vp, i]),
+            "ref_integral_destroy": (None, [vp]),
+            "ref_integral_state_bytes": (C.c_size_t, [vp]),
+            "ref_integral_qdata_count": (C.c_size_t, [vp]),
+            "ref_integral_get_qdata": (None, [vp, vp]),
+            "ref_integral_set_qdata": (None, [vp, vp]),
+            "ref_integral_mult": (i, [vp, i, d, vp, i, vp, i, i]),
+            "ref_integral_jvp": (i, [vp, i, i, vp, vp]),
+            "ref_integral_element_gradient": (i, [vp, i, i, vp, l, l, l]),
+        }
+        for name, (res, args) in sig.items():
+            f = getattr(L, name)
+            f.restype = res
+            f.argtypes = args
+        _lib = L
+    return _lib
+
+
+def _p(a):
+    return a.ctypes.data_as(C.c_void_p)
+
+
+class Mesh:
+    def __init__(self, handle):
+        self.h = handle
+        self.dim = lib().ref_mesh_dim(handle)
+        self.ne = lib().ref_mesh_num_elements(handle)
+        self.geom = GEOM["hex"] if self.dim == 3 else GEOM["quad"]
+
+    @staticmethod
+    def from_file(path, refinements=0):
+        return Mesh(lib().ref_mesh_from_file(path.encode(), refinements))
+
+    @staticmethod
+    def cartesian3d(nx, ny, nz, sx=1.0, sy=1.0, sz=1.0):
+        return Mesh(lib().ref_mesh_cartesian3d(nx, ny, nz, sx, sy, sz))
+
+    @staticmethod
+    def cartesian2d(nx, ny, sx=1.0, sy=1.0):
+        return Mesh(lib().ref_mesh_cartesian2d(nx, ny, sx, sy))
+
+    def perturb(self, amp):
+        lib().ref_mesh_perturb(self.h, amp)
+
+    def nodes(self):
+        """(order, ordering, L-vector of nodal coordinates, dof_info table of the nodes space)"""
+        L = lib()
+        n = L.ref_mesh_nodes_size(self.h)
+        x = np.empty(n)
+        L.ref_mesh_nodes(self.h, _p(x))
+        cnt = L.ref_mesh_nodes_dof_info(self.h, self.geom, None)
+        info = np.empty(cnt, dtype=np.uint64)
+        L.ref_mesh_nodes_dof_info(self.h, self.geom, _p(info))
+        return L.ref_mesh_nodes_order(self.h), L.ref_mesh_nodes_ordering(self.h), x, info.reshape(self.ne, -1)
+
+    def geometric_factors(self, q):
+        nq = q**self.dim
+        X = np.empty((self.ne, self.dim, nq))
+        J = np.empty((self.ne, self.dim, self.dim, nq))
+        lib().ref_geometric_factors(self.h, q, self.geom, _p(X), _p(J))
+        return X, J
+
+
+class Space:
+    def __init__(self, mesh, p, vdim, ordering=BYVDIM):
+        self.mesh, self.p, self.vdim, self.ordering = mesh, p, vdim, ordering
+        self.h = lib().ref_space_create(mesh.h, p, vdim, ordering)
+        self.vsize = lib().ref_space_vsize(self.h)
+        self.num_nodes = lib().ref_space_num_nodes(self.h)
+        self.geom = mesh.geom
+        self.esize = lib().ref_space_esize(self.h, self.geom)
+
+    def native_dofs(self):
+        n = lib().ref_space_native_dofs(self.h, self.geom, None)
+        out = np.empty(n, dtype=np.int32)
+        lib().ref_space_native_dofs(self.h, self.geom, _p(out))
+        return out.reshape(self.mesh.ne, -1)
+
+    def dof_info(self):
+        n = lib().ref_space_dof_info(self.h, self.geom, None)
+        out = np.empty(n, dtype=np.uint64)
+        lib().ref_space_dof_info(self.h, self.geom, _p(out))
+        return out.reshape(self.mesh.ne, -1)
+
+    def gather(self, Lvec):
+        E = np.empty(self.esize)
+        lib().ref_space_gather(self.h, self.geom, _p(np.ascontiguousarray(Lvec)), _p(E))
+        return E
+
+    def scatter_add(self, E, Lvec):
+        lib().ref_space_scatter_add(self.h, self.geom, _p(np.ascontiguousarray(E)), _p(Lvec))
+        return Lvec
+
+
+def lex_perm(geom, p):
+    out = np.empty(64, dtype=np.int32)
+    n = lib().ref_lex_perm(geom, p, _p(out))
+    return out[:n].copy()
+
+
+class Csr:
+    def __init__(self, test, trial):
+        self.test, self.trial = test, trial
+        self.h = lib().ref_csr_create(test.h, trial.h)
+        self.nnz = lib().ref_csr_nnz(self.h)
+        self.num_rows = lib().ref_csr_num_rows(self.h)
+
+    def pattern(self):
+        rp = np.empty(self.num_rows + 1, dtype=np.int32)
+        ci = np.empty(self.nnz, dtype=np.int32)
+        lib().ref_csr_pattern(self.h, _p(rp), _p(ci))
+        return rp, ci
+
+    def assemble(self, K_e):
+        vals = np.zeros(self.nnz)
+        lib().ref_csr_assemble(self.h, self.test.h, self.trial.h, self.test.geom, _p(np.ascontiguousarray(K_e)),
+                               _p(vals))
+        return vals
+
+
+def kinds():
+    return [lib().ref_kind_name(i).decode() for i in range(lib().ref_num_kinds())]
+
+
+class Integral:
+    """One reference Integral (integral.hpp:24) on the entire mesh; E-vector level API."""
+
+    def __init__(self, kind, mesh, params):
+        params = np.ascontiguousarray(params, dtype=np.float64)
+        self.h = lib().ref_integral_create(kind.encode(), mesh.h, _p(params), len(params))
+        if not self.h:
+            raise KeyError(kind)
+        self.mesh = mesh
+        self.geom = mesh.geom
+
+    def mult(self, t, inputs_E, out_size, wrt=-1, update_state=False):
+        ins = [np.ascontiguousarray(a, dtype=np.float64) for a in inputs_E]
+        arr = (C.c_void_p * len(ins))(*[a.ctypes.data for a in ins])
+        out = np.zeros(out_size)
+        rc = lib().ref_integral_mult(self.h, self.geom, float(t), arr, len(ins), _p(out), wrt, int(update_state))
+        assert rc == 0
+        return out
+
+    def jvp(self, wrt, du_E, out_size):
+        out = np.zeros(out_size)
+        rc = lib().ref_integral_jvp(self.h, self.geom, wrt, _p(np.ascontiguousarray(du_E)), _p(out))
+        assert rc == 0
+        return out
+
+    def element_gradient(self, wrt, ne, ncol, nrow):
+        K = np.zeros((ne, ncol, nrow))
+        rc = lib().ref_integral_element_gradient(self.h, self.geom, wrt, _p(K), ne, ncol, nrow)
+        assert rc == 0
+        return K
+
+    def state_bytes(self):
+        return lib().ref_integral_state_bytes(self.h)
+
+    def get_qdata(self):
+        n = lib().ref_integral_state_bytes(self.h) * lib().ref_integral_qdata_count(self.h)
+        out = np.empty(n // 8)
+        lib().ref_integral_get_qdata(self.h, _p(out))
+        return out
+
+    def set_qdata(self, data):
+        lib().ref_integral_set_qdata(self.h, _p(np.ascontiguousarray(data)))

@@ -1,0 +1,155 @@
+// TEST INFRASTRUCTURE ONLY (oracle/): instantiations of the REFERENCE's MakeDomainIntegral for the q-functions the
+// physics modules register.  Compiled once per (REF_DIM, REF_P).  The two functor shells below restate, with the
+// reference's own tensor/tuple/dual types, what lives inside class templates that need MPI to instantiate:
+//   SolidMechanics::MaterialStressFunctor       src/serac/physics/solid_mechanics.hpp:808-853
+//   ShapeAwareFunctional::ShapeAwareIntegrandWrapper[WithState]  shape_aware_functional.hpp:364-438
+// (the shape pull-backs themselves -- detail::ShapeCorrection and apply_shape_aware_qf_helper* -- are the reference's).
+#include "ref_driver.hpp"
+
+#ifndef REF_DIM
+#error "compile with -DREF_DIM=2|3 -DREF_P=1|2|3"
+#endif
+
+namespace {
+using namespace serac;
+constexpr int dim = REF_DIM;
+constexpr int p   = REF_P;
+
+template <typename Material>
+struct MaterialStress {
+  Material material_;
+  bool     geom_nonlin_;
+  template <typename X, typename State, typename Displacement, typename Acceleration>
+  auto operator()(double, X, State& state, Displacement displacement, Acceleration acceleration) const
+  {
+    auto du_dX   = get<1>(displacement);
+    auto d2u_dt2 = get<0>(acceleration);
+    auto stress  = material_(state, du_dX);
+    auto dx_dX   = 0.0 * du_dX + Identity<dim>();
+    if (geom_nonlin_) dx_dX += du_dX;
+    auto flux = dot(stress, transpose(inv(dx_dX))) * det(dx_dX);
+    return serac::tuple{material_.density * d2u_dt2, flux};
+  }
+};
+
+template <typename Material>
+struct ThermalIntegrand {
+  Material material_;
+  template <typename X, typename T, typename dT_dt>
+  auto operator()(double, X x, T temperature, dT_dt dtemp_dt) const
+  {
+    auto [u, du_dX]                 = temperature;
+    auto du_dt                      = get<0>(dtemp_dt);
+    auto [heat_capacity, heat_flux] = material_(x, u, du_dX);
+    return serac::tuple{heat_capacity * du_dt, -1.0 * heat_flux};
+  }
+};
+
+template <typename Integrand, typename test_space, typename... trial_spaces>
+struct ShapeAwareWithState {
+  Integrand integrand_;
+  template <typename Pos, typename State, typename Shape, typename... Args>
+  auto operator()(double time, Pos x, State& state, Shape shape_val, Args... args) const
+  {
+    auto                    qfunc_tuple = make_tuple(args...);
+    auto                    spaces      = make_tuple(trial_spaces{}...);
+    serac::detail::ShapeCorrection shape_correction(Dimension<dim>{}, shape_val);
+    auto unmodified = serac::detail::apply_shape_aware_qf_helper_with_state(
+        integrand_, time, x, state, shape_val, spaces, qfunc_tuple, shape_correction,
+        std::make_integer_sequence<int, sizeof...(args)>{});
+    return shape_correction.modify_shape_aware_qf_return(test_space{}, unmodified);
+  }
+};
+
+template <typename Integrand, typename test_space, typename... trial_spaces>
+struct ShapeAware {
+  Integrand integrand_;
+  template <typename Pos, typename Shape, typename... Args>
+  auto operator()(double time, Pos x, Shape shape_val, Args... args) const
+  {
+    auto                    qfunc_tuple = make_tuple(args...);
+    auto                    spaces      = make_tuple(trial_spaces{}...);
+    serac::detail::ShapeCorrection shape_correction(Dimension<dim>{}, shape_val);
+    auto unmodified = serac::detail::apply_shape_aware_qf_helper(integrand_, time, x, shape_val, spaces, qfunc_tuple,
+                                                          shape_correction,
+                                                          std::make_integer_sequence<int, sizeof...(args)>{});
+    return shape_correction.modify_shape_aware_qf_return(test_space{}, unmodified);
+  }
+};
+
+constexpr mfem::Geometry::Type tp_geom = (dim == 3) ? mfem::Geometry::CUBE : mfem::Geometry::SQUARE;
+
+template <typename State>
+std::shared_ptr<QuadratureData<State>> make_qdata(mfem::Mesh& mesh, ref::IntegralHolder& h, State init)
+{
+  // StateManager::newQuadratureDataBuffer (state_manager.hpp:108-132): elements per geometry x qpts per element
+  typename QuadratureData<State>::geom_array_t elems{}, qpts{};
+  for (int e = 0; e < mesh.GetNE(); e++) elems[size_t(mesh.GetElementGeometry(e))]++;
+  for (int g = 0; g < mfem::Geometry::NUM_GEOMETRIES; g++)
+    qpts[size_t(g)] = uint32_t(std::max(0, num_quadrature_points(mfem::Geometry::Type(g), p + 1)));
+  auto qd        = std::make_shared<QuadratureData<State>>(elems, qpts, init);
+  h.qdata        = qd;
+  h.state_bytes  = sizeof(State);
+  h.qdata_count  = size_t(elems[size_t(tp_geom)]) * size_t(qpts[size_t(tp_geom)]);
+  h.qdata_raw    = (h.qdata_count > 0) ? static_cast<void*>(&(*qd)[tp_geom](0, 0)) : nullptr;
+  return qd;
+}
+
+using solid_test  = H1<p, dim>;
+using solid_sig   = solid_test(H1<1, dim>, H1<p, dim>, H1<p, dim>);
+using thermal_sig = H1<p>(H1<1, dim>, H1<p>, H1<p>);
+
+template <typename Material>
+ref::IntegralHolder make_solid_stateless(mfem::Mesh& mesh, Material m, bool gn)
+{
+  ref::IntegralHolder h;
+  using QF = ShapeAwareWithState<MaterialStress<Material>, solid_test, H1<p, dim>, H1<p, dim>>;
+  QF     qf{MaterialStress<Material>{m, gn}};
+  Domain d     = EntireDomain(mesh);
+  h.integral   = std::make_unique<Integral>(MakeDomainIntegral<solid_sig, p + 1, dim>(d, qf, EmptyQData, {0, 1, 2}));
+  h.num_trials = 3;
+  return h;
+}
+
+#define STR2(x) #x
+#define STR(x) STR2(x)
+#define TAG STR(REF_DIM) "d_p" STR(REF_P)
+
+ref::Registrar r1("solid_neohookean_" TAG, [](mfem::Mesh& mesh, const double* q, int n) {
+  SLIC_ERROR_IF(n != 4, "params: density K G geom_nonlin");
+  return make_solid_stateless(mesh, solid_mechanics::NeoHookean{q[0], q[1], q[2]}, q[3] != 0.0);
+});
+ref::Registrar r2("solid_linear_isotropic_" TAG, [](mfem::Mesh& mesh, const double* q, int n) {
+  SLIC_ERROR_IF(n != 4, "params: density K G geom_nonlin");
+  return make_solid_stateless(mesh, solid_mechanics::LinearIsotropic{q[0], q[1], q[2]}, q[3] != 0.0);
+});
+
+#if REF_DIM == 3
+ref::Registrar r3("solid_j2smallstrain_linear_" TAG, [](mfem::Mesh& mesh, const double* q, int n) {
+  SLIC_ERROR_IF(n != 7, "params: E nu sigma_y Hi Hk density geom_nonlin");
+  using Material = solid_mechanics::J2SmallStrain<solid_mechanics::LinearHardening>;
+  Material m{q[0], q[1], solid_mechanics::LinearHardening{q[2], q[3]}, q[4], q[5]};
+  ref::IntegralHolder h;
+  using QF = ShapeAwareWithState<MaterialStress<Material>, solid_test, H1<p, dim>, H1<p, dim>>;
+  QF     qf{MaterialStress<Material>{m, q[6] != 0.0}};
+  Domain d  = EntireDomain(mesh);
+  auto   qd = make_qdata<Material::State>(mesh, h, Material::State{});
+  h.integral   = std::make_unique<Integral>(MakeDomainIntegral<solid_sig, p + 1, dim>(d, qf, qd, {0, 1, 2}));
+  h.num_trials = 3;
+  return h;
+});
+#endif
+
+ref::Registrar r4("thermal_linear_conductor_" TAG, [](mfem::Mesh& mesh, const double* q, int n) {
+  SLIC_ERROR_IF(n != 3, "params: density specific_heat conductivity");
+  using Material = heat_transfer::LinearIsotropicConductor;
+  ref::IntegralHolder h;
+  using QF = ShapeAware<ThermalIntegrand<Material>, H1<p>, H1<p>, H1<p>>;
+  QF     qf{ThermalIntegrand<Material>{Material(q[0], q[1], q[2])}};
+  Domain d     = EntireDomain(mesh);
+  h.integral   = std::make_unique<Integral>(MakeDomainIntegral<thermal_sig, p + 1, dim>(d, qf, NoQData, {0, 1, 2}));
+  h.num_trials = 3;
+  return h;
+});
+
+}  // namespace

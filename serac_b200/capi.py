@@ -1,0 +1,371 @@
+"""ctypes binding of libserac_b200.so (include/serac_b200.h) plus thin Python mirrors of the reference objects the C ABI
+replaces (ElementRestriction, Integral, Functional).  PyTorch is used only for device memory and streams.
+
+The library is the product: if it is missing or a call fails this module raises -- there is no CPU fallback."""
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libserac_b200.so")
+
+SEGMENT, TRIANGLE, SQUARE, TETRAHEDRON, CUBE = 1, 2, 3, 4, 5
+BYNODES, BYVDIM = 0, 1
+NO_DIFFERENTIATION = -1
+MAX_TRIALS = 6
+
+# every symbol include/serac_b200.h declares: (restype, argtypes)
+_vp, _i, _d, _i64, _sz = C.c_void_p, C.c_int, C.c_double, C.c_int64, C.c_size_t
+_pp = C.POINTER(C.c_void_p)
+
+
+class FieldArg(C.Structure):
+    _fields_ = [("L_dev", _vp), ("table_dev", _vp), ("node_stride", _i64), ("comp_stride", _i64)]
+
+
+class KernelTable(C.Structure):
+    _fields_ = [
+        ("geom", _i), ("dim", _i), ("q", _i), ("num_trials", _i), ("test_order", _i), ("test_components", _i),
+        ("trial_order", _i * MAX_TRIALS), ("trial_components", _i * MAX_TRIALS),
+        ("qf_bytes", _sz), ("state_bytes", _sz), ("elements_per_block", _i),
+        ("evaluate", _vp), ("evaluate_ad", _vp * MAX_TRIALS), ("jvp", _vp * MAX_TRIALS),
+        ("element_gradient", _vp * MAX_TRIALS),
+        ("derivative_mask", _i * MAX_TRIALS), ("derivative_entries", _i * MAX_TRIALS),
+    ]
+
+
+SIGNATURES = {
+    "sb_version": (_i, []),
+    "sb_last_error": (C.c_char_p, []),
+    "sb_launch_count": (C.c_longlong, []),
+    "sb_launch_count_reset": (None, []),
+    "sb_count_launch": (None, []),
+    "sb_h1_lexicographic_dof_info": (_i, [_i, _i, _vp, _i64, _vp]),
+    "sb_h1_lexicographic_permutation": (_i, [_i, _i, _vp]),
+    "sb_restriction_create": (_i, [_vp, _i64, _i, _i, _i64, _i, _pp]),
+    "sb_restriction_destroy": (_i, [_vp]),
+    "sb_restriction_esize": (_i64, [_vp]),
+    "sb_restriction_lsize": (_i64, [_vp]),
+    "sb_restriction_table_dev": (_i, [_vp, _pp]),
+    "sb_restriction_gather": (_i, [_vp, _vp, _vp, _vp]),
+    "sb_restriction_scatter_add": (_i, [_vp, _vp, _vp, _vp]),
+    "sb_restriction_scatter": (_i, [_vp, _vp, _vp, _vp]),
+    "sb_geometric_factors": (_i, [_i, _i, _i, _vp, _vp, _vp, _i64, _vp, _vp, _vp]),
+    "sb_named_integrand_count": (_i, []),
+    "sb_named_integrand_name": (C.c_char_p, [_i]),
+    "sb_named_kernel_table": (_i, [C.c_char_p, C.POINTER(C.POINTER(KernelTable))]),
+    "sb_named_qf_blob": (_i, [C.c_char_p, _vp, _i, _vp, _sz]),
+    "sb_integral_create": (_i, [C.POINTER(KernelTable), _vp, _vp, _i64, _vp, _vp, _pp]),
+    "sb_integral_destroy": (_i, [_vp]),
+    "sb_integral_set_qdata": (_i, [_vp, _vp]),
+    "sb_integral_evaluate": (_i, [_vp, _d, C.POINTER(FieldArg), _vp, _i, _i, _vp]),
+    "sb_integral_jvp": (_i, [_vp, _i, C.POINTER(FieldArg), _vp, _vp]),
+    "sb_integral_element_gradient": (_i, [_vp, _i, _vp, _vp]),
+    "sb_integral_export_derivatives": (_i, [_vp, _i, _vp, _vp]),
+    "sb_integral_derivative_entries": (_i, [_vp, _i]),
+    "sb_integral_derivative_mask": (_i, [_vp, _i]),
+    "sb_csr_create": (_i, [_vp, _vp, _pp]),
+    "sb_csr_destroy": (_i, [_vp]),
+    "sb_csr_nnz": (_i64, [_vp]),
+    "sb_csr_num_rows": (_i64, [_vp]),
+    "sb_csr_pattern_dev": (_i, [_vp, _pp, _pp]),
+    "sb_csr_pattern_to_host": (_i, [_vp, _vp, _vp]),
+    "sb_csr_assemble": (_i, [_vp, _vp, _vp, _vp]),
+    "sb_functional_create": (_i, [_vp, _i, _pp, _pp]),
+    "sb_functional_destroy": (_i, [_vp]),
+    "sb_functional_add_integral": (_i, [_vp, _vp, _vp]),
+    "sb_functional_evaluate": (_i, [_vp, _d, _i, _pp, _i, _vp, _i, _i, _vp]),
+    "sb_functional_jvp": (_i, [_vp, _i, _vp, _i, _vp, _i, _vp]),
+    "sb_functional_assemble": (_i, [_vp, _i, _pp, _vp, _i, _vp]),
+    "sb_halo_create": (_i, [_i64, _i64, _vp, _i, _vp, _vp, _vp, _vp, _pp]),
+    "sb_halo_destroy": (_i, [_vp]),
+    "sb_halo_buffers": (_i, [_vp, _pp, _pp]),
+    "sb_halo_P_pack": (_i, [_vp, _vp, _vp]),
+    "sb_halo_P_finish": (_i, [_vp, _vp, _vp, _vp]),
+    "sb_halo_Pt_pack": (_i, [_vp, _vp, _vp]),
+    "sb_halo_Pt_finish": (_i, [_vp, _vp, _vp, _vp]),
+}
+
+_lib = None
+
+
+class SeracB200Error(RuntimeError):
+    pass
+
+
+def lib():
+    """Load libserac_b200.so; raises if it has not been built (python -c 'import __graft_entry__ as g; g.build()')."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise SeracB200Error(f"{LIB_PATH} is missing: build it with `make -C serac_b200/csrc` "
+                                 "(there is no CPU fallback for the Functional path)")
+        L = C.CDLL(LIB_PATH)
+        for name, (res, args) in SIGNATURES.items():
+            f = getattr(L, name)  # AttributeError if the library does not export a declared symbol
+            f.restype = res
+            f.argtypes = args
+        _lib = L
+    return _lib
+
+
+def check(rc):
+    if rc != 0:
+        raise SeracB200Error(f"serac_b200 error {rc}: {lib().sb_last_error().decode()}")
+
+
+def _np_ptr(a):
+    return a.ctypes.data_as(C.c_void_p)
+
+
+def _dev_ptr(t):
+    return C.c_void_p(t.data_ptr()) if t is not None else C.c_void_p(0)
+
+
+def _stream_ptr():
+    import torch
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def lexicographic_permutation(geom, p):
+    n = {SEGMENT: p + 1, SQUARE: (p + 1)**2, CUBE: (p + 1)**3}[geom]
+    out = np.empty(n, dtype=np.int32)
+    check(lib().sb_h1_lexicographic_permutation(geom, p, _np_ptr(out)))
+    return out
+
+
+def h1_dof_info(geom, p, native_dofs):
+    """GetElementRestriction for H1 (element_restriction.cpp:216-277): native mfem element dofs -> packed DoF words."""
+    native = np.ascontiguousarray(native_dofs, dtype=np.int32)
+    out = np.empty(native.shape, dtype=np.uint64)
+    check(lib().sb_h1_lexicographic_dof_info(geom, p, _np_ptr(native), native.shape[0], _np_ptr(out)))
+    return out
+
+
+class ElementRestriction:
+    """Mirror of serac::ElementRestriction (element_restriction.hpp:150-215) for one geometry."""
+
+    def __init__(self, dof_info, components, num_nodes, ordering=BYVDIM):
+        info = np.ascontiguousarray(dof_info, dtype=np.uint64)
+        self.num_elements, self.nodes_per_elem = info.shape
+        self.components, self.num_nodes, self.ordering = components, int(num_nodes), ordering
+        h = C.c_void_p()
+        check(lib().sb_restriction_create(_np_ptr(info), self.num_elements, self.nodes_per_elem, components,
+                                          self.num_nodes, ordering, C.byref(h)))
+        self.h = h
+        self.node_stride = components if ordering == BYVDIM else 1
+        self.comp_stride = 1 if ordering == BYVDIM else self.num_nodes
+        t = C.c_void_p()
+        check(lib().sb_restriction_table_dev(self.h, C.byref(t)))
+        self.table_dev = t.value
+
+    def __del__(self):
+        try:
+            lib().sb_restriction_destroy(self.h)
+        except Exception:
+            pass
+
+    def ESize(self):
+        return lib().sb_restriction_esize(self.h)
+
+    def LSize(self):
+        return lib().sb_restriction_lsize(self.h)
+
+    def Gather(self, L, E=None):
+        import torch
+        if E is None:
+            E = torch.empty(self.ESize(), dtype=torch.float64, device=L.device)
+        check(lib().sb_restriction_gather(self.h, _dev_ptr(L), _dev_ptr(E), _stream_ptr()))
+        return E
+
+    def ScatterAdd(self, E, L):
+        check(lib().sb_restriction_scatter_add(self.h, _dev_ptr(E), _dev_ptr(L), _stream_ptr()))
+        return L
+
+    def Scatter(self, E, L):
+        check(lib().sb_restriction_scatter(self.h, _dev_ptr(E), _dev_ptr(L), _stream_ptr()))
+        return L
+
+    def field(self, L):
+        return FieldArg(L.data_ptr(), self.table_dev, self.node_stride, self.comp_stride)
+
+
+def geometric_factors(geom, mesh_order, q, mesh_restriction, nodes_L, num_elements=None, elements=None):
+    """GeometricFactors (geometric_factors.cpp:62-138) -> (X_q [ne][dim][nq], J_q [ne][dim][dim][nq]) on device."""
+    import torch
+    dim = 3 if geom == CUBE else 2
+    ne = mesh_restriction.num_elements if num_elements is None else num_elements
+    nq = q**dim
+    X = torch.empty((ne, dim, nq), dtype=torch.float64, device=nodes_L.device)
+    J = torch.empty((ne, dim, dim, nq), dtype=torch.float64, device=nodes_L.device)
+    check(lib().sb_geometric_factors(geom, mesh_order, q, mesh_restriction.h, _dev_ptr(nodes_L),
+                                     _dev_ptr(elements), ne, _dev_ptr(X), _dev_ptr(J), _stream_ptr()))
+    return X, J
+
+
+def named_integrands():
+    L = lib()
+    return [L.sb_named_integrand_name(i).decode() for i in range(L.sb_named_integrand_count())]
+
+
+class Integral:
+    """Mirror of serac::Integral (integral.hpp:24-168) created from a named (compiled-in) integrand."""
+
+    def __init__(self, name, params, X_q, J_q, num_elements, elements=None):
+        L = lib()
+        tp = C.POINTER(KernelTable)()
+        check(L.sb_named_kernel_table(name.encode(), C.byref(tp)))
+        self.table = tp.contents
+        params = np.ascontiguousarray(params, dtype=np.float64)
+        blob = (C.c_ubyte * self.table.qf_bytes)()
+        check(L.sb_named_qf_blob(name.encode(), _np_ptr(params), len(params), blob, self.table.qf_bytes))
+        el = None if elements is None else np.ascontiguousarray(elements, dtype=np.int32)
+        h = C.c_void_p()
+        check(L.sb_integral_create(tp, blob, None if el is None else _np_ptr(el), num_elements, _dev_ptr(X_q),
+                                   _dev_ptr(J_q), C.byref(h)))
+        self.h = h
+        self._keep = (X_q, J_q)
+        self.num_elements = num_elements
+        self.nq = self.table.q**self.table.dim
+        self.qdata = None
+
+    def __del__(self):
+        try:
+            lib().sb_integral_destroy(self.h)
+        except Exception:
+            pass
+
+    def set_qdata(self, qdata):
+        self.qdata = qdata
+        check(lib().sb_integral_set_qdata(self.h, _dev_ptr(qdata)))
+
+    def Mult(self, t, fields, r_E, wrt=NO_DIFFERENTIATION, update_state=False):
+        arr = (FieldArg * len(fields))(*fields)
+        check(lib().sb_integral_evaluate(self.h, float(t), arr, _dev_ptr(r_E), wrt, int(update_state), _stream_ptr()))
+        return r_E
+
+    def GradientMult(self, wrt, du_field, dr_E):
+        check(lib().sb_integral_jvp(self.h, wrt, C.byref(du_field), _dev_ptr(dr_E), _stream_ptr()))
+        return dr_E
+
+    def ComputeElementGradients(self, wrt, K_e):
+        check(lib().sb_integral_element_gradient(self.h, wrt, _dev_ptr(K_e), _stream_ptr()))
+        return K_e
+
+    def derivative_entries(self, wrt):
+        return lib().sb_integral_derivative_entries(self.h, wrt)
+
+    def derivative_mask(self, wrt):
+        return lib().sb_integral_derivative_mask(self.h, wrt)
+
+    def export_derivatives(self, wrt):
+        import torch
+        out = torch.empty((self.num_elements, self.nq, self.derivative_entries(wrt)), dtype=torch.float64,
+                          device="cuda")
+        check(lib().sb_integral_export_derivatives(self.h, wrt, _dev_ptr(out), _stream_ptr()))
+        return out
+
+
+class CsrPattern:
+    """Mirror of GradientAssemblyLookupTables (dof_numbering.hpp:253-380)."""
+
+    def __init__(self, test, trial, handle=None):
+        if handle is None:
+            handle = C.c_void_p()
+            check(lib().sb_csr_create(test.h, trial.h, C.byref(handle)))
+        self.h = handle
+        self.nnz = lib().sb_csr_nnz(self.h)
+        self.num_rows = lib().sb_csr_num_rows(self.h)
+
+    def __del__(self):
+        try:
+            lib().sb_csr_destroy(self.h)
+        except Exception:
+            pass
+
+    def to_host(self):
+        rp = np.empty(self.num_rows + 1, dtype=np.int32)
+        ci = np.empty(self.nnz, dtype=np.int32)
+        check(lib().sb_csr_pattern_to_host(self.h, _np_ptr(rp), _np_ptr(ci)))
+        return rp, ci
+
+    def assemble(self, K_e, values=None):
+        import torch
+        if values is None:
+            values = torch.empty(self.nnz, dtype=torch.float64, device=K_e.device)
+        check(lib().sb_csr_assemble(self.h, _dev_ptr(K_e), _dev_ptr(values), _stream_ptr()))
+        return values
+
+
+class Functional:
+    """Mirror of serac::Functional's evaluation orchestration at one rank (functional.hpp:406-513,569-652)."""
+
+    def __init__(self, test, trials):
+        self.test, self.trials = test, list(trials)
+        arr = (C.c_void_p * len(trials))(*[t.h for t in trials])
+        h = C.c_void_p()
+        check(lib().sb_functional_create(test.h, len(trials), arr, C.byref(h)))
+        self.h = h
+        self.integrals = []
+        self._csr = {}
+
+    def __del__(self):
+        try:
+            lib().sb_functional_destroy(self.h)
+        except Exception:
+            pass
+
+    def AddDomainIntegral(self, integral, depends_on):
+        idx = np.ascontiguousarray(depends_on, dtype=np.int32)
+        check(lib().sb_functional_add_integral(self.h, integral.h, _np_ptr(idx)))
+        self.integrals.append(integral)
+
+    def __call__(self, t, inputs, wrt=NO_DIFFERENTIATION, out=None, update_state=False):
+        """inputs: list of torch CUDA tensors (device path) or numpy arrays (host path, copies inside the call)."""
+        import torch
+        on_host = isinstance(inputs[0], np.ndarray)
+        n = self.test.LSize()
+        if on_host:
+            ins = [np.ascontiguousarray(a, dtype=np.float64) for a in inputs]
+            ptrs = (C.c_void_p * len(ins))(*[a.ctypes.data for a in ins])
+            if out is None:
+                out = np.empty(n)
+            check(lib().sb_functional_evaluate(self.h, float(t), wrt, ptrs, 1, _np_ptr(out), 1, int(update_state),
+                                               _stream_ptr()))
+        else:
+            ptrs = (C.c_void_p * len(inputs))(*[a.data_ptr() for a in inputs])
+            if out is None:
+                out = torch.empty(n, dtype=torch.float64, device=inputs[0].device)
+            check(lib().sb_functional_evaluate(self.h, float(t), wrt, ptrs, 0, _dev_ptr(out), 0, int(update_state),
+                                               _stream_ptr()))
+        return out
+
+    def GradientMult(self, wrt, du, out=None):
+        import torch
+        n = self.test.LSize()
+        if isinstance(du, np.ndarray):
+            du = np.ascontiguousarray(du, dtype=np.float64)
+            if out is None:
+                out = np.empty(n)
+            check(lib().sb_functional_jvp(self.h, wrt, _np_ptr(du), 1, _np_ptr(out), 1, _stream_ptr()))
+        else:
+            if out is None:
+                out = torch.empty(n, dtype=torch.float64, device=du.device)
+            check(lib().sb_functional_jvp(self.h, wrt, _dev_ptr(du), 0, _dev_ptr(out), 0, _stream_ptr()))
+        return out
+
+    def assemble(self, wrt, on_host=False):
+        """-> (CsrPattern, values): the local CSR triple the reference wraps in mfem::SparseMatrix (functional.hpp:649)."""
+        import torch
+        if wrt not in self._csr:
+            self._csr[wrt] = CsrPattern(self.test, self.trials[wrt])
+        pat = self._csr[wrt]
+        hp = C.c_void_p(pat.h.value)
+        if on_host:
+            vals = np.empty(pat.nnz)
+            check(lib().sb_functional_assemble(self.h, wrt, C.byref(hp), _np_ptr(vals), 1, _stream_ptr()))
+        else:
+            vals = torch.empty(pat.nnz, dtype=torch.float64, device="cuda")
+            check(lib().sb_functional_assemble(self.h, wrt, C.byref(hp), _dev_ptr(vals), 0, _stream_ptr()))
+        return pat, vals

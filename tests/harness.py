@@ -1,0 +1,60 @@
+"""Shared test plumbing: load golden fixtures / live reference problems and drive the product (C ABI through
+serac_b200.capi) on them.  The oracle (oracle/) is only ever the checker here."""
+import glob
+import os
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+GOLDEN = os.path.join(ROOT, "tests", "golden")
+
+KIND_TO_NAME = {5: "hex", 3: "quad"}
+
+
+def golden_names():
+    return sorted(os.path.splitext(os.path.basename(f))[0] for f in glob.glob(os.path.join(GOLDEN, "*.npz")))
+
+
+def load_golden(name):
+    d = np.load(os.path.join(GOLDEN, name + ".npz"))
+    return {k: (d[k].item() if d[k].ndim == 0 else d[k]) for k in d.files}
+
+
+def rel_l2(a, b):
+    a = np.asarray(a, dtype=np.float64).ravel()
+    b = np.asarray(b, dtype=np.float64).ravel()
+    nb = np.linalg.norm(b)
+    return np.linalg.norm(a - b) / (nb if nb > 0 else 1.0)
+
+
+class Product:
+    """The product objects for one parity problem (same signature as oracle.make_golden.reference_problem)."""
+
+    def __init__(self, prob, device):
+        import torch
+        from serac_b200 import capi
+        self.capi, self.torch, self.prob, self.dev = capi, torch, prob, device
+        geom, p, dim, vdim = int(prob["geom"]), int(prob["p"]), int(prob["dim"]), int(prob["vdim"])
+        self.geom, self.p, self.dim, self.vdim = geom, p, dim, vdim
+        # restriction tables built by the PRODUCT from the host library's native dofs
+        self.dof_info = capi.h1_dof_info(geom, p, prob["native_dofs"])
+        self.shape_dof_info = capi.h1_dof_info(geom, 1, prob["shape_native_dofs"])
+        self.G = capi.ElementRestriction(self.dof_info, vdim, int(prob["num_nodes"]))
+        self.G_shape = capi.ElementRestriction(self.shape_dof_info, dim, int(prob["shape_num_nodes"]))
+        self.G_mesh = capi.ElementRestriction(prob["mesh_dof_info"], dim, int(prob["mesh_num_nodes"]),
+                                              int(prob["mesh_ordering"]))
+        t = lambda a: torch.as_tensor(np.ascontiguousarray(a), dtype=torch.float64, device=device)
+        self.t = t
+        self.nodes = t(prob["mesh_nodes"])
+        self.X_q, self.J_q = capi.geometric_factors(geom, int(prob["mesh_order"]), p + 1, self.G_mesh, self.nodes)
+        name = f"{prob['kind']}_{KIND_TO_NAME[geom]}_p{p}"
+        self.integral = capi.Integral(name, prob["params"], self.X_q, self.J_q, int(prob["ne"]))
+        self.U, self.A, self.S, self.dU = t(prob["U"]), t(prob["A"]), t(prob["S"]), t(prob["dU"])
+        self.F = capi.Functional(self.G, [self.G_shape, self.G, self.G])
+        self.F.AddDomainIntegral(self.integral, [0, 1, 2])
+        if self.integral.table.state_bytes:
+            self.qdata = t(prob["qdata0"]).clone()
+            self.integral.set_qdata(self.qdata)
+
+    def fields(self):
+        return [self.G_shape.field(self.S), self.G.field(self.U), self.G.field(self.A)]
