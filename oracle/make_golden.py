@@ -34,7 +34,8 @@ def make_mesh(spec):
     raise ValueError(spec)
 
 
-def reference_problem(mesh_spec, kind, p, params, vdim, seed=42, with_matrix=True, shape_amp=0.0, state_init=None):
+def reference_problem(mesh_spec, kind, p, params, vdim, seed=42, with_matrix=True, shape_amp=0.0, state_init=None,
+                      u_amp=0.01):
     """Runs the reference path for one Integral on the whole mesh with signature test(shape p=1 vector, u, a)
     (SolidMechanics: vdim = dim; HeatTransfer: vdim = 1) and returns inputs + outputs as a dict of numpy arrays."""
     mesh = make_mesh(mesh_spec)
@@ -43,7 +44,7 @@ def reference_problem(mesh_spec, kind, p, params, vdim, seed=42, with_matrix=Tru
     space = ref.Space(mesh, p, vdim)
     shape_space = ref.Space(mesh, 1, dim)
     rng = np.random.default_rng(seed)
-    U = 0.01 * rng.uniform(-1.0, 1.0, space.vsize)  # keeps F invertible
+    U = u_amp * rng.uniform(-1.0, 1.0, space.vsize)  # small enough that F = I + du/dX stays invertible on this mesh
     A = rng.uniform(-1.0, 1.0, space.vsize)
     S = shape_amp * rng.uniform(-1.0, 1.0, shape_space.vsize)
     dU = rng.uniform(0.0, 1.0, space.vsize)  # check_gradient.hpp:19,26
@@ -119,8 +120,31 @@ FIXTURES = [
 ]
 
 
+def config_a_fixture():
+    """BASELINE.json configs[1]: beam-hex.mesh refined 4x (32 768 hexes), H1 p=2 vdim 3 (839 619 vdofs).  Stores the
+    host-library inputs (native dofs, mesh nodes) and a strided sample + norms of the reference residual / Jacobian
+    action so the full-size GPU run can be checked without shipping 13 MB of doubles."""
+    kw = dict(mesh_spec=("file", "beam-hex.mesh", 4), kind="solid_neohookean", p=2, params=[1.0, 100.0, 50.0, 1.0],
+              vdim=3, with_matrix=False, u_amp=1e-3)  # h = 1/16: 0.01 would fold elements (det F < 0 -> NaN)
+    d = reference_problem(**kw)
+    assert np.isfinite(d["r"]).all() and np.isfinite(d["dr"]).all()
+    stride = 97
+    keep = dict(kind=d["kind"], geom=d["geom"], dim=d["dim"], p=d["p"], vdim=d["vdim"], ne=d["ne"], params=d["params"],
+                native_dofs=d["native_dofs"].astype(np.int32), num_nodes=d["num_nodes"],
+                shape_native_dofs=d["shape_native_dofs"].astype(np.int32), shape_num_nodes=d["shape_num_nodes"],
+                mesh_order=d["mesh_order"], mesh_ordering=d["mesh_ordering"], mesh_nodes=d["mesh_nodes"],
+                mesh_num_nodes=d["mesh_num_nodes"], seed=42, u_amp=kw["u_amp"], sample_stride=stride,
+                r_sample=d["r"][::stride], dr_sample=d["dr"][::stride], r_norm=np.linalg.norm(d["r"]),
+                dr_norm=np.linalg.norm(d["dr"]), r_sum=d["r"].sum(), dr_sum=d["dr"].sum())
+    return keep
+
+
 def main():
     os.makedirs(GOLDEN_DIR, exist_ok=True)
+    data = config_a_fixture()
+    path = os.path.join(GOLDEN_DIR, "config_a_beam_hex_r4_p2.npz")
+    np.savez_compressed(path, **data)
+    print(f"config A: ne={data['ne']} -> {os.path.getsize(path) / 1024:.0f} KiB")
     for name, kw in FIXTURES:
         data = reference_problem(**kw)
         path = os.path.join(GOLDEN_DIR, name + ".npz")

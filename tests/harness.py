@@ -12,7 +12,9 @@ KIND_TO_NAME = {5: "hex", 3: "quad"}
 
 
 def golden_names():
-    return sorted(os.path.splitext(os.path.basename(f))[0] for f in glob.glob(os.path.join(GOLDEN, "*.npz")))
+    """small fixtures with full reference outputs (the config_* files are full-size inputs + sampled outputs)"""
+    names = sorted(os.path.splitext(os.path.basename(f))[0] for f in glob.glob(os.path.join(GOLDEN, "*.npz")))
+    return [n for n in names if not n.startswith("config_")]
 
 
 def load_golden(name):
@@ -25,6 +27,16 @@ def rel_l2(a, b):
     b = np.asarray(b, dtype=np.float64).ravel()
     nb = np.linalg.norm(b)
     return np.linalg.norm(a - b) / (nb if nb > 0 else 1.0)
+
+
+def make_inputs(seed, vsize, shape_vsize, shape_amp=0.0, u_amp=0.01):
+    """the same draws, in the same order, as oracle.make_golden.reference_problem"""
+    rng = np.random.default_rng(seed)
+    U = u_amp * rng.uniform(-1.0, 1.0, vsize)
+    A = rng.uniform(-1.0, 1.0, vsize)
+    S = shape_amp * rng.uniform(-1.0, 1.0, shape_vsize)
+    dU = rng.uniform(0.0, 1.0, vsize)
+    return dict(U=U, A=A, S=S, dU=dU)
 
 
 class Product:
@@ -41,7 +53,9 @@ class Product:
         self.shape_dof_info = capi.h1_dof_info(geom, 1, prob["shape_native_dofs"])
         self.G = capi.ElementRestriction(self.dof_info, vdim, int(prob["num_nodes"]))
         self.G_shape = capi.ElementRestriction(self.shape_dof_info, dim, int(prob["shape_num_nodes"]))
-        self.G_mesh = capi.ElementRestriction(prob["mesh_dof_info"], dim, int(prob["mesh_num_nodes"]),
+        # the mesh-nodes space is H1 p=1 with the same scalar numbering as the shape space
+        mesh_info = prob["mesh_dof_info"] if "mesh_dof_info" in prob else self.shape_dof_info
+        self.G_mesh = capi.ElementRestriction(mesh_info, dim, int(prob["mesh_num_nodes"]),
                                               int(prob["mesh_ordering"]))
         t = lambda a: torch.as_tensor(np.ascontiguousarray(a), dtype=torch.float64, device=device)
         self.t = t
@@ -49,6 +63,8 @@ class Product:
         self.X_q, self.J_q = capi.geometric_factors(geom, int(prob["mesh_order"]), p + 1, self.G_mesh, self.nodes)
         name = f"{prob['kind']}_{KIND_TO_NAME[geom]}_p{p}"
         self.integral = capi.Integral(name, prob["params"], self.X_q, self.J_q, int(prob["ne"]))
+        if "U" not in prob:  # full-size fixtures regenerate the inputs from the seed (oracle/make_golden.py)
+            prob.update(make_inputs(int(prob["seed"]), self.G.LSize(), self.G_shape.LSize(), u_amp=float(prob["u_amp"])))
         self.U, self.A, self.S, self.dU = t(prob["U"]), t(prob["A"]), t(prob["S"]), t(prob["dU"])
         self.F = capi.Functional(self.G, [self.G_shape, self.G, self.G])
         self.F.AddDomainIntegral(self.integral, [0, 1, 2])

@@ -104,3 +104,27 @@ def test_element_gradient_and_assembly(case):
     import scipy.sparse as sp
     A = sp.csr_matrix((vals.cpu().numpy(), ci, rp), shape=(len(rp) - 1, len(prob["U"])))
     assert rel_l2(A @ prob["dU"], prob["dr"]) < TOL
+
+
+def test_config_a_full_size(cuda):
+    """BASELINE.json configs[1] at full size (32 768 hexes, 839 619 vdofs): sampled reference residual / Jacobian action,
+    plus size-independent properties: linearity of the Jacobian action and JVP == directional finite difference."""
+    prob = load_golden("config_a_beam_hex_r4_p2")
+    P = Product(prob, cuda)
+    stride = int(prob["sample_stride"])
+    r = P.F(0.0, [P.S, P.U, P.A], wrt=1).cpu().numpy()
+    dr = P.F.GradientMult(1, P.dU).cpu().numpy()
+    assert rel_l2(r[::stride], prob["r_sample"]) < TOL
+    assert rel_l2(dr[::stride], prob["dr_sample"]) < TOL
+    assert abs(np.linalg.norm(r) - prob["r_norm"]) < TOL * prob["r_norm"]
+    assert abs(np.linalg.norm(dr) - prob["dr_norm"]) < TOL * prob["dr_norm"]
+    # linearity: J(a x + b y) = a J x + b J y
+    y = P.torch.linspace(-1, 1, P.G.LSize(), dtype=P.torch.float64, device=cuda)
+    lhs = P.F.GradientMult(1, 0.3 * P.dU - 1.7 * y).cpu().numpy()
+    rhs = 0.3 * dr - 1.7 * P.F.GradientMult(1, y).cpu().numpy()
+    assert rel_l2(lhs, rhs) < 1e-13
+    # central finite difference of the residual in direction dU (check_gradient.hpp:60-90)
+    eps = 1e-6
+    rp = P.F(0.0, [P.S, P.U + eps * P.dU, P.A]).cpu().numpy()
+    rm = P.F(0.0, [P.S, P.U - eps * P.dU, P.A]).cpu().numpy()
+    assert rel_l2((rp - rm) / (2 * eps), dr) < 1e-7
