@@ -1,0 +1,50 @@
+// serac_b200: tuning variants of the config-A integrand (not part of the default build: make TUNE=1).
+// name: tune_e<EPB>_r<ROWS>_m<MINB>
+#include "registry.hpp"
+
+namespace sb {
+namespace {
+using solid_mechanics::NeoHookean;
+
+template <int EPB>
+struct TuneSig {
+  static constexpr int dim = 3;
+  using test               = H1<2, 3>;
+  using type               = SignatureT<Geometry::CUBE, 3, EPB, test, H1<1, 3>, H1<2, 3>, H1<2, 3>>;
+  using qf = ShapeAwareIntegrandWrapperWithState<MaterialStressFunctor<NeoHookean>, 3, test, H1<2, 3>, H1<2, 3>>;
+};
+
+template <int EPB>
+long make_blob(const double* p, int n, void* out, size_t cap)
+{
+  if (n != 4) return -1;
+  typename TuneSig<EPB>::qf qf{MaterialStressFunctor<NeoHookean>(
+      NeoHookean{p[0], p[1], p[2]}, (p[3] != 0.0) ? GeometricNonlinearities::On : GeometricNonlinearities::Off)};
+  return store_blob(qf, out, cap);
+}
+
+#define TUNE(E, R, M)                                                                                          \
+  static Registrar tune_##E##_##R##_##M({"tune_e" #E "_r" #R "_m" #M,                                          \
+                                         make_kernel_table<TuneSig<E>::type, TuneSig<E>::qf, Empty, R, M>(), \
+                                         &make_blob<E>, "{density, K, G, gn}"});
+#ifndef TUNE_SET
+#define TUNE_SET 0
+#endif
+#if TUNE_SET == 0
+TUNE(4, 1, 1)
+TUNE(4, 1, 2)
+TUNE(4, 1, 3)
+TUNE(4, 1, 4)
+#elif TUNE_SET == 1
+TUNE(4, 3, 1)
+TUNE(4, 3, 2)
+TUNE(8, 1, 1)
+TUNE(8, 1, 2)
+#elif TUNE_SET == 2
+TUNE(8, 3, 1)
+TUNE(2, 1, 4)
+TUNE(2, 1, 8)
+TUNE(2, 3, 4)
+#endif
+}  // namespace
+}  // namespace sb

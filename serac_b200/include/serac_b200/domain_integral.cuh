@@ -416,14 +416,15 @@ SB_HD int cmax(int a, int b) { return a > b ? a : b; }
 // ------------------------------------------------------------------------------------------------
 // compile-time description of one integral: geometry, Q, test space, trial spaces
 // ------------------------------------------------------------------------------------------------
-template <Geometry geom, int Q, typename test, typename... trials>
-struct Signature {
+/// EPB_ = elements per CTA = elements per stored-derivative tile (0: elements_per_block default)
+template <Geometry geom, int Q, int EPB_, typename test, typename... trials>
+struct SignatureT {
   static constexpr Geometry geometry = geom;
   static constexpr int      dim      = dimension_of(geom);
   static constexpr int      q        = Q;
   static constexpr int      NT       = int(sizeof...(trials));
   static constexpr int      QPE      = num_quadrature_points(geom, Q);  ///< quadrature points per element
-  static constexpr int      EPB      = elements_per_block(dim, Q);
+  static constexpr int      EPB      = (EPB_ > 0) ? EPB_ : elements_per_block(dim, Q);
   static constexpr int      threads  = EPB * QPE;
   using test_space                   = test;
   template <int i>
@@ -437,6 +438,9 @@ struct Signature {
   static_assert(test::order + 1 <= Q, "quadrature rule must have at least p + 1 points per direction");
 
 };
+
+template <Geometry geom, int Q, typename test, typename... trials>
+using Signature = SignatureT<geom, Q, 0, test, trials...>;
 
 template <typename Sig, int... I>
 constexpr int max_interp_scratch(std::integer_sequence<int, I...>)
@@ -526,11 +530,12 @@ struct output_traits<tuple<S, F>> {
 
 /// argument K as seen by the q-function in a derivative pass
 /// PASS == -1: value pass (value components carry dual<ck>, gradient plain)
-/// PASS >= 0 : gradient-row pass (row PASS of the gradient carries dual<dim>, value plain)
-template <typename Space, int dim, int PASS>
+/// PASS >= 0 : gradient pass: rows [PASS*ROWS, (PASS+1)*ROWS) of the gradient are seeded, every gradient entry is a
+///             dual<ROWS*dim> (partial index = local_row*dim + parent direction), value plain
+template <typename Space, int dim, int PASS, int ROWS = 1>
 struct seeded_arg {
   static constexpr int c = Space::components;
-  static constexpr int N = (PASS < 0) ? c : dim;
+  static constexpr int N = (PASS < 0) ? c : ROWS * dim;
   using value_scalar     = std::conditional_t<(PASS < 0), dual<N>, double>;
   using grad_scalar      = std::conditional_t<(PASS < 0), double, dual<N>>;
   using value_t          = std::conditional_t<c == 1, value_scalar, tensor<value_scalar, c>>;
@@ -538,7 +543,7 @@ struct seeded_arg {
   using type             = tuple<value_t, grad_t>;
 };
 
-template <typename Sig, int WRT, int PASS, typename QF, typename State, int... I>
+template <typename Sig, int WRT, int PASS, typename QF, typename State, int ROWS, int... I>
 auto pass_output_type(std::integer_sequence<int, I...>)
 {
   constexpr int dim = Sig::dim;
@@ -547,13 +552,13 @@ auto pass_output_type(std::integer_sequence<int, I...>)
     return decltype(std::declval<QF>()(
         double{}, pos_t{},
         std::declval<std::conditional_t<
-            I == WRT, typename seeded_arg<typename Sig::template trial_space<I>, dim, PASS>::type,
+            I == WRT, typename seeded_arg<typename Sig::template trial_space<I>, dim, PASS, ROWS>::type,
             typename qf_arg<typename Sig::template trial_space<I>, dim>::type>>()...)){};
   } else {
     return decltype(std::declval<QF>()(
         double{}, pos_t{}, std::declval<State&>(),
         std::declval<std::conditional_t<
-            I == WRT, typename seeded_arg<typename Sig::template trial_space<I>, dim, PASS>::type,
+            I == WRT, typename seeded_arg<typename Sig::template trial_space<I>, dim, PASS, ROWS>::type,
             typename qf_arg<typename Sig::template trial_space<I>, dim>::type>>()...)){};
   }
 }
@@ -576,8 +581,8 @@ auto plain_output_type(std::integer_sequence<int, I...>)
 template <typename Sig, int WRT, typename QF, typename State>
 struct DerivativeTraits {
   using seq              = std::make_integer_sequence<int, Sig::NT>;
-  using value_pass_out   = decltype(pass_output_type<Sig, WRT, -1, QF, State>(seq{}));
-  using grad_pass_out    = decltype(pass_output_type<Sig, WRT, 0, QF, State>(seq{}));
+  using value_pass_out   = decltype(pass_output_type<Sig, WRT, -1, QF, State, 1>(seq{}));
+  using grad_pass_out    = decltype(pass_output_type<Sig, WRT, 0, QF, State, 1>(seq{}));
   using trial            = typename Sig::template trial_space<WRT>;
   static constexpr int  ct  = Sig::test_c;
   static constexpr int  ck  = trial::components;
@@ -663,11 +668,11 @@ __device__ __forceinline__ void load_and_interpolate(const EvalParams<Sig::NT>& 
 }
 
 /// build the seeded version of argument `arg` for a derivative pass
-template <typename Space, int dim, int PASS>
+template <typename Space, int dim, int PASS, int ROWS>
 __device__ __forceinline__ auto seed_argument(const typename qf_arg<Space, dim>::type& arg,
                                               const tensor<double, dim, dim>& invJ)
 {
-  using S          = seeded_arg<Space, dim, PASS>;
+  using S          = seeded_arg<Space, dim, PASS, ROWS>;
   constexpr int c  = Space::components;
   typename S::type out{};
   if constexpr (PASS < 0) {
@@ -689,9 +694,9 @@ __device__ __forceinline__ auto seed_argument(const typename qf_arg<Space, dim>:
         g       = make_dual_constant<S::N>(gcomp(get<1>(arg), a, j));
         // the seed is the PARENT-space gradient (the reference promotes to dual before parent_to_physical,
         // domain_integral_kernels.hpp:181-186), so d(physical grad[a][j]) / d(parent grad[a][k]) = invJ(k, j)
-        if (a == PASS) {
+        if (a >= PASS * ROWS && a < (PASS + 1) * ROWS) {
           SB_UNROLL
-          for (int k = 0; k < dim; k++) g.gradient[k] = invJ(k, j);
+          for (int k = 0; k < dim; k++) g.gradient[(a - PASS * ROWS) * dim + k] = invJ(k, j);
         }
       }
     }
@@ -699,7 +704,7 @@ __device__ __forceinline__ auto seed_argument(const typename qf_arg<Space, dim>:
   return out;
 }
 
-template <typename Sig, int WRT, int PASS, typename QF, typename State, typename Pos, typename Inputs, int... I>
+template <typename Sig, int WRT, int PASS, int ROWS, typename QF, typename State, typename Pos, typename Inputs, int... I>
 __device__ __forceinline__ auto run_pass(const QF& qf, double t, const Pos& pos, State& state, const Inputs& in,
                                          const tensor<double, Sig::dim, Sig::dim>& invJ,
                                          std::integer_sequence<int, I...>)
@@ -707,7 +712,7 @@ __device__ __forceinline__ auto run_pass(const QF& qf, double t, const Pos& pos,
   auto pick = [&](auto idx) {
     constexpr int i = decltype(idx)::value;
     if constexpr (i == WRT) {
-      return seed_argument<typename Sig::template trial_space<i>, Sig::dim, PASS>(get<i>(in), invJ);
+      return seed_argument<typename Sig::template trial_space<i>, Sig::dim, PASS, ROWS>(get<i>(in), invJ);
     } else {
       return get<i>(in);
     }
@@ -722,8 +727,9 @@ __device__ __forceinline__ auto call_qf_tuple(const QF& qf, double t, const Pos&
   return call_qf(qf, t, pos, st, get<I>(in)...);
 }
 
-template <typename Sig, int WRT, typename QF, typename State>
-__global__ void __launch_bounds__(Sig::threads) evaluation_kernel(const __grid_constant__ EvalParams<Sig::NT> P,
+/// ROWS: gradient rows seeded per derivative pass (1 .. ck); MINB: __launch_bounds__ minimum resident CTAs per SM
+template <typename Sig, int WRT, typename QF, typename State, int ROWS = 1, int MINB = 1>
+__global__ void __launch_bounds__(Sig::threads, MINB) evaluation_kernel(const __grid_constant__ EvalParams<Sig::NT> P,
                                                                   const __grid_constant__ QF qf)
 {
   constexpr int dim = Sig::dim;
@@ -850,7 +856,7 @@ __global__ void __launch_bounds__(Sig::threads) evaluation_kernel(const __grid_c
 
     if constexpr (DT::value_pass_active) {
       State st  = state_old;
-      auto  out = run_pass<Sig, WRT, -1, QF, State>(qf, P.t, pos, st, inputs, invJ, seq{});
+      auto  out = run_pass<Sig, WRT, -1, 1, QF, State>(qf, P.t, pos, st, inputs, invJ, seq{});
       using out_t = std::decay_t<decltype(out)>;
       using S_t   = std::conditional_t<output_traits<out_t>::source_dual, dual<ck>, double>;
       using F_t   = std::conditional_t<output_traits<out_t>::flux_dual, dual<ck>, double>;
@@ -883,14 +889,16 @@ __global__ void __launch_bounds__(Sig::threads) evaluation_kernel(const __grid_c
       }
     }
     if constexpr (DT::grad_pass_active) {
-      auto grad_pass = [&](auto row_c) {
-        constexpr int              row = decltype(row_c)::value;
-        constexpr DerivativeLayout LY  = DT::layout();  // (re-declared: captured constexpr locals are not constants)
-        State         st  = state_old;
-        auto          out = run_pass<Sig, WRT, row, QF, State>(qf, P.t, pos, st, inputs, invJ, seq{});
-        using out_t       = std::decay_t<decltype(out)>;
-        using S_t         = std::conditional_t<output_traits<out_t>::source_dual, dual<dim>, double>;
-        using F_t         = std::conditional_t<output_traits<out_t>::flux_dual, dual<dim>, double>;
+      static_assert(ck % ROWS == 0, "ROWS must divide the number of trial components");
+      auto grad_pass = [&](auto pass_c) {
+        constexpr int              pass = decltype(pass_c)::value;
+        constexpr int              NP   = ROWS * dim;
+        constexpr DerivativeLayout LY   = DT::layout();  // (re-declared: captured constexpr locals are not constants)
+        State                      st   = state_old;
+        auto out    = run_pass<Sig, WRT, pass, ROWS, QF, State>(qf, P.t, pos, st, inputs, invJ, seq{});
+        using out_t = std::decay_t<decltype(out)>;
+        using S_t   = std::conditional_t<output_traits<out_t>::source_dual, dual<NP>, double>;
+        using F_t   = std::conditional_t<output_traits<out_t>::flux_dual, dual<NP>, double>;
         S_t s_out[ct];
         F_t f_out[ct][dim];
         pull_back(out, s_out, f_out);
@@ -903,26 +911,31 @@ __global__ void __launch_bounds__(Sig::threads) evaluation_kernel(const __grid_c
         }
         if (valid) {
           SB_UNROLL
-          for (int a = 0; a < ct; a++) {
-            if constexpr (LY.has[1]) {
-              SB_UNROLL
-              for (int l = 0; l < dim; l++)
-                dq[(long long)(LY.offset[1] + (a * ck + row) * dim + l) * Sig::threads] = partial(s_out[a], l);
-            }
-            if constexpr (LY.has[3]) {
-              SB_UNROLL
-              for (int k = 0; k < dim; k++) {
+          for (int rl = 0; rl < ROWS; rl++) {
+            const int row = pass * ROWS + rl;
+            SB_UNROLL
+            for (int a = 0; a < ct; a++) {
+              if constexpr (LY.has[1]) {
                 SB_UNROLL
                 for (int l = 0; l < dim; l++)
-                  dq[(long long)(LY.offset[3] + ((a * dim + k) * ck + row) * dim + l) * Sig::threads] =
-                      partial(f_out[a][k], l);
+                  dq[(long long)(LY.offset[1] + (a * ck + row) * dim + l) * Sig::threads] =
+                      partial(s_out[a], rl * dim + l);
+              }
+              if constexpr (LY.has[3]) {
+                SB_UNROLL
+                for (int k = 0; k < dim; k++) {
+                  SB_UNROLL
+                  for (int l = 0; l < dim; l++)
+                    dq[(long long)(LY.offset[3] + ((a * dim + k) * ck + row) * dim + l) * Sig::threads] =
+                        partial(f_out[a][k], rl * dim + l);
+                }
               }
             }
           }
         }
       };
       [&]<int... R>(std::integer_sequence<int, R...>) { (grad_pass(std::integral_constant<int, R>{}), ...); }
-      (std::make_integer_sequence<int, ck>{});
+      (std::make_integer_sequence<int, ck / ROWS>{});
     }
     if constexpr (!DT::value_pass_active && !DT::grad_pass_active) {
       State  st  = state_old;
@@ -971,10 +984,10 @@ __global__ void __launch_bounds__(Sig::threads) evaluation_kernel(const __grid_c
 // (domain_integral_kernels.hpp:277-304, chain_rule :223-237).  Pure streaming over dqf: this is the HBM-bound kernel.
 // MASK bit b set <=> derivative block b (d00,d01,d10,d11) is present.
 // ------------------------------------------------------------------------------------------------
-template <int dim, int q, int nk, int ck, int nt, int ct, int MASK>
+template <int dim, int q, int nk, int ck, int nt, int ct, int MASK, int EPB_ = 0>
 struct JvpConfig {
   static constexpr int  QPE     = ipow(q, dim);
-  static constexpr int  EPB     = elements_per_block(dim, q);
+  static constexpr int  EPB     = (EPB_ > 0) ? EPB_ : elements_per_block(dim, q);
   static constexpr int  threads = EPB * QPE;
   static constexpr bool d00 = (MASK & 1) != 0, d01 = (MASK & 2) != 0, d10 = (MASK & 4) != 0, d11 = (MASK & 8) != 0;
   using TPk = TensorProduct<dim, nk, q, ck>;
@@ -984,11 +997,11 @@ struct JvpConfig {
   static constexpr DerivativeLayout layout() { return make_layout(ct, ck, dim, d00, d01, d10, d11); }
 };
 
-template <int dim, int q, int nk, int ck, int nt, int ct, int MASK>
-__global__ void __launch_bounds__(JvpConfig<dim, q, nk, ck, nt, ct, MASK>::threads)
+template <int dim, int q, int nk, int ck, int nt, int ct, int MASK, int EPB_ = 0>
+__global__ void __launch_bounds__(JvpConfig<dim, q, nk, ck, nt, ct, MASK, EPB_>::threads)
     jvp_kernel(const __grid_constant__ JvpParams P)
 {
-  using C                       = JvpConfig<dim, q, nk, ck, nt, ct, MASK>;
+  using C                       = JvpConfig<dim, q, nk, ck, nt, ct, MASK, EPB_>;
   constexpr DerivativeLayout LY = C::layout();
   constexpr int QPE = C::QPE, EPB = C::EPB, per = C::per;
   extern __shared__ double smem[];
@@ -1092,10 +1105,10 @@ __global__ void __launch_bounds__(JvpConfig<dim, q, nk, ck, nt, ct, MASK>::threa
 // batch_apply_shape_fn hexahedron_H1.inl:132-167).  For every trial node J the ck trial components are
 // integrated together (ct*ck "components"), K_e is written trial-major (functional.hpp:599-601).
 // ------------------------------------------------------------------------------------------------
-template <int dim, int q, int nk, int ck, int nt, int ct, int MASK>
+template <int dim, int q, int nk, int ck, int nt, int ct, int MASK, int EPB_ = 0>
 struct ElemGradConfig {
   static constexpr int  QPE     = ipow(q, dim);
-  static constexpr int  EPB     = elements_per_block(dim, q);
+  static constexpr int  EPB     = (EPB_ > 0) ? EPB_ : elements_per_block(dim, q);
   static constexpr int  threads = EPB * QPE;
   static constexpr bool d00 = (MASK & 1) != 0, d01 = (MASK & 2) != 0, d10 = (MASK & 4) != 0, d11 = (MASK & 8) != 0;
   using TPt = TensorProduct<dim, nt, q, ct * ck>;
@@ -1105,11 +1118,11 @@ struct ElemGradConfig {
   static constexpr DerivativeLayout layout() { return make_layout(ct, ck, dim, d00, d01, d10, d11); }
 };
 
-template <int dim, int q, int nk, int ck, int nt, int ct, int MASK>
-__global__ void __launch_bounds__(ElemGradConfig<dim, q, nk, ck, nt, ct, MASK>::threads)
+template <int dim, int q, int nk, int ck, int nt, int ct, int MASK, int EPB_ = 0>
+__global__ void __launch_bounds__(ElemGradConfig<dim, q, nk, ck, nt, ct, MASK, EPB_>::threads)
     element_gradient_kernel(const __grid_constant__ ElemGradParams P)
 {
-  using C                       = ElemGradConfig<dim, q, nk, ck, nt, ct, MASK>;
+  using C                       = ElemGradConfig<dim, q, nk, ck, nt, ct, MASK, EPB_>;
   constexpr DerivativeLayout LY = C::layout();
   constexpr int QPE = C::QPE, EPB = C::EPB, per = C::per;
   extern __shared__ double smem[];

@@ -33,7 +33,7 @@ inline int ensure_smem(K kernel, size_t bytes)
   return 0;
 }
 
-template <typename Sig, int WRT, typename QF, typename State>
+template <typename Sig, int WRT, typename QF, typename State, int ROWS = 1, int MINB = 1>
 int launch_evaluate(const sb_eval_args* a, const void* qf_blob, void* stream)
 {
   constexpr int NT = Sig::NT;
@@ -55,7 +55,7 @@ int launch_evaluate(const sb_eval_args* a, const void* qf_blob, void* stream)
   P.update_state = a->update_state;
   P.t            = a->t;
   if (a->num_elements <= 0) return 0;
-  auto         kernel = &evaluation_kernel<Sig, WRT, QF, State>;
+  auto         kernel = &evaluation_kernel<Sig, WRT, QF, State, ROWS, MINB>;
   const size_t smem   = size_t(eval_smem_doubles<Sig>()) * sizeof(double);
   if (int e = ensure_smem(kernel, smem)) return e;
   const int grid = (a->num_elements + Sig::EPB - 1) / Sig::EPB;
@@ -72,7 +72,7 @@ int launch_jvp(const sb_jvp_args* a, void* stream)
   using trial       = typename Sig::template trial_space<WRT>;
   constexpr int nk  = trial::order + 1;
   constexpr int ck  = trial::components;
-  using C           = JvpConfig<Sig::dim, Sig::q, nk, ck, Sig::test_n, Sig::test_c, MASK>;
+  using C           = JvpConfig<Sig::dim, Sig::q, nk, ck, Sig::test_n, Sig::test_c, MASK, Sig::EPB>;
   if constexpr (MASK == 0) {
     return 0;  // structurally zero derivative: dr_E block stays as the caller zeroed it
   } else {
@@ -85,7 +85,7 @@ int launch_jvp(const sb_jvp_args* a, void* stream)
     P.dqf          = a->dqf_dev;
     P.r_E          = a->r_E_dev;
     if (a->num_elements <= 0) return 0;
-    auto         kernel = &jvp_kernel<Sig::dim, Sig::q, nk, ck, Sig::test_n, Sig::test_c, MASK>;
+    auto         kernel = &jvp_kernel<Sig::dim, Sig::q, nk, ck, Sig::test_n, Sig::test_c, MASK, Sig::EPB>;
     const size_t smem   = size_t(C::smem_doubles) * sizeof(double);
     if (int e = ensure_smem(kernel, smem)) return e;
     const int grid = (a->num_elements + C::EPB - 1) / C::EPB;
@@ -101,7 +101,7 @@ int launch_element_gradient(const sb_elem_grad_args* a, void* stream)
   using trial      = typename Sig::template trial_space<WRT>;
   constexpr int nk = trial::order + 1;
   constexpr int ck = trial::components;
-  using C          = ElemGradConfig<Sig::dim, Sig::q, nk, ck, Sig::test_n, Sig::test_c, MASK>;
+  using C          = ElemGradConfig<Sig::dim, Sig::q, nk, ck, Sig::test_n, Sig::test_c, MASK, Sig::EPB>;
   if constexpr (MASK == 0) {
     return 0;
   } else {
@@ -113,7 +113,7 @@ int launch_element_gradient(const sb_elem_grad_args* a, void* stream)
     P.dqf          = a->dqf_dev;
     P.K_e          = a->K_e_dev;
     if (a->num_elements <= 0) return 0;
-    auto         kernel = &element_gradient_kernel<Sig::dim, Sig::q, nk, ck, Sig::test_n, Sig::test_c, MASK>;
+    auto         kernel = &element_gradient_kernel<Sig::dim, Sig::q, nk, ck, Sig::test_n, Sig::test_c, MASK, Sig::EPB>;
     const size_t smem   = size_t(C::smem_doubles) * sizeof(double);
     if (int e = ensure_smem(kernel, smem)) return e;
     const int grid = (a->num_elements + C::EPB - 1) / C::EPB;
@@ -123,13 +123,15 @@ int launch_element_gradient(const sb_elem_grad_args* a, void* stream)
   }
 }
 
-template <typename Sig, typename QF, typename State, int WRT>
+template <typename Sig, typename QF, typename State, int WRT, int ROWS_REQ, int MINB>
 void fill_wrt(sb_kernel_table& T)
 {
   using DT                   = DerivativeTraits<Sig, WRT, QF, State>;
   constexpr DerivativeLayout L = DT::layout();
   constexpr int mask = (L.has[0] ? 1 : 0) | (L.has[1] ? 2 : 0) | (L.has[2] ? 4 : 0) | (L.has[3] ? 8 : 0);
-  T.evaluate_ad[WRT]        = &launch_evaluate<Sig, WRT, QF, State>;
+  constexpr int ck   = Sig::template trial_space<WRT>::components;
+  constexpr int ROWS = (ROWS_REQ > 0 && ck % ROWS_REQ == 0) ? ROWS_REQ : 1;
+  T.evaluate_ad[WRT]        = &launch_evaluate<Sig, WRT, QF, State, ROWS, MINB>;
   T.jvp[WRT]                = &launch_jvp<Sig, WRT, mask>;
   T.element_gradient[WRT]   = &launch_element_gradient<Sig, WRT, mask>;
   T.derivative_mask[WRT]    = mask;
@@ -138,7 +140,8 @@ void fill_wrt(sb_kernel_table& T)
 
 /// State = serac::Nothing: q-function takes no state argument; serac::Empty: takes an Empty& it never touches;
 /// anything else: trivially copyable per-quadrature-point struct
-template <typename Sig, typename QF, typename State>
+/// ROWS_REQ: gradient rows per derivative pass (1 = least registers, ck = one pass); MINB: min resident CTAs per SM
+template <typename Sig, typename QF, typename State, int ROWS_REQ = 1, int MINB = 1>
 sb_kernel_table make_kernel_table()
 {
   static_assert(std::is_trivially_copyable_v<QF>, "q-function functors are copied by value into kernel parameters");
@@ -152,7 +155,7 @@ sb_kernel_table make_kernel_table()
   auto fill         = [&]<int... I>(std::integer_sequence<int, I...>)
   {
     ((T.trial_order[I] = Sig::template trial_space<I>::order,
-      T.trial_components[I] = Sig::template trial_space<I>::components, fill_wrt<Sig, QF, State, I>(T)),
+      T.trial_components[I] = Sig::template trial_space<I>::components, fill_wrt<Sig, QF, State, I, ROWS_REQ, MINB>(T)),
      ...);
   };
   fill(std::make_integer_sequence<int, Sig::NT>{});

@@ -1,0 +1,62 @@
+"""CPU: the C-ABI library loads, exports every symbol include/serac_b200.h declares, and its host-side (no GPU needed)
+entry points agree with the oracle.  No compute calls here."""
+import ctypes as C
+import os
+import re
+
+import numpy as np
+import pytest
+
+from harness import ROOT, golden_names, load_golden
+from oracle import functional_oracle as fo
+from serac_b200 import capi
+
+
+def header_symbols():
+    text = open(os.path.join(ROOT, "include", "serac_b200.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(sb_[a-zA-Z0-9_]+)\s*\(", text)))
+
+
+def test_library_exports_every_declared_symbol():
+    lib = C.CDLL(capi.LIB_PATH)
+    syms = header_symbols()
+    assert len(syms) > 40
+    for s in syms:
+        assert hasattr(lib, s), f"libserac_b200.so does not export {s}"
+    assert set(syms) <= set(capi.SIGNATURES)  # and the ctypes binding covers the header
+
+
+def test_version_and_registry():
+    lib = capi.lib()
+    assert lib.sb_version() >= 100
+    names = capi.named_integrands()
+    assert "solid_neohookean_hex_p2" in names and "solid_linear_isotropic_hex_p1" in names
+
+
+@pytest.mark.parametrize("geom", [capi.SEGMENT, capi.SQUARE, capi.CUBE])
+@pytest.mark.parametrize("p", [1, 2, 3])
+def test_lexicographic_permutation_matches_oracle(geom, p):
+    assert np.array_equal(capi.lexicographic_permutation(geom, p), fo.lexicographic_permutation(geom, p))
+
+
+@pytest.mark.parametrize("name", golden_names())
+def test_dof_info_matches_reference(name):
+    prob = load_golden(name)
+    info = capi.h1_dof_info(int(prob["geom"]), int(prob["p"]), prob["native_dofs"])
+    assert np.array_equal(info, prob["dof_info"])
+
+
+def test_unknown_integrand_is_an_error():
+    tp = C.POINTER(capi.KernelTable)()
+    rc = capi.lib().sb_named_kernel_table(b"no_such_integrand", C.byref(tp))
+    assert rc == 3 and b"no_such_integrand" in capi.lib().sb_last_error()
+
+
+def test_no_cpu_fallback_without_gpu():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    info = np.zeros((1, 8), dtype=np.uint64)
+    with pytest.raises(capi.SeracB200Error):
+        capi.ElementRestriction(info, 3, 8)  # needs device memory: must fail loudly, not fall back

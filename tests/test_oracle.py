@@ -1,0 +1,102 @@
+"""CPU: pins the numpy restatement (oracle/functional_oracle.py) against the golden fixtures that the reference's own
+kernels produced (oracle/make_golden.py via oracle/_ref), and -- when oracle/_ref is present -- live against the reference
+for integrands that have no fixture."""
+import numpy as np
+import pytest
+
+from harness import golden_names, load_golden, rel_l2
+from oracle import functional_oracle as fo
+from oracle import ref
+
+MASK = np.uint64(0x0000FFFFFFFFFFFF)
+
+
+def run_oracle(prob, wrt=1, state=None):
+    geom, p, dim, vdim = int(prob["geom"]), int(prob["p"]), int(prob["dim"]), int(prob["vdim"])
+    q = p + 1
+    table = fo.dof_info(geom, p, prob["native_dofs"])
+    shape_table = fo.dof_info(geom, 1, prob["shape_native_dofs"])
+    mesh_table = prob["mesh_dof_info"] & MASK
+    byvdim = int(prob["mesh_ordering"]) == 1
+    X_q, J_q = fo.geometric_factors(fo.gather(mesh_table, prob["mesh_nodes"], dim, byvdim), int(prob["mesh_order"]), q,
+                                    dim)
+    qf = fo.make_qf(str(prob["kind"]), list(prob["params"]))
+    trials = [fo.gather(shape_table, prob["S"], dim), fo.gather(table, prob["U"], vdim),
+              fo.gather(table, prob["A"], vdim)]
+    r_E, blocks = fo.evaluation_kernel(qf, trials, [1, p, p], X_q, J_q, p, q, dim, wrt=wrt, state=state)
+    return dict(table=table, shape_table=shape_table, X_q=X_q, J_q=J_q, r_E=r_E, blocks=blocks, p=p, q=q, dim=dim,
+                vdim=vdim)
+
+
+@pytest.fixture(scope="module", params=golden_names())
+def case(request):
+    prob = load_golden(request.param)
+    return prob, run_oracle(prob)
+
+
+def test_tables_bit_exact(case):
+    prob, o = case
+    assert np.array_equal(o["table"], prob["dof_info"])
+    assert np.array_equal(o["shape_table"], prob["shape_dof_info"])
+
+
+def test_gather_scatter_bit_exact(case):
+    prob, o = case
+    E = fo.gather(o["table"], prob["U"], o["vdim"])
+    assert np.array_equal(E.ravel(), prob["U_E"])
+    L = fo.scatter_add(o["table"], prob["r_E"], np.zeros(len(prob["U"])), o["vdim"])
+    assert np.array_equal(L, prob["r"])
+
+
+def test_geometric_factors(case):
+    prob, o = case
+    assert rel_l2(o["X_q"], prob["X_q"]) < 1e-14 and rel_l2(o["J_q"], prob["J_q"]) < 1e-14
+
+
+def test_residual_and_jvp(case):
+    prob, o = case
+    assert rel_l2(o["r_E"], prob["r_E"]) < 1e-13
+    dU_E = fo.gather(o["table"], prob["dU"], o["vdim"])
+    dr_E = fo.action_of_gradient_kernel(o["blocks"], dU_E, o["p"], o["p"], o["q"], o["dim"])
+    assert rel_l2(dr_E, prob["dr_E"]) < 1e-13
+
+
+def test_other_arguments(case):
+    prob, _ = case
+    o2 = run_oracle(prob, wrt=2)
+    dU_E = fo.gather(o2["table"], prob["dU"], o2["vdim"])
+    dr = fo.scatter_add(o2["table"], fo.action_of_gradient_kernel(o2["blocks"], dU_E, o2["p"], o2["p"], o2["q"],
+                                                                 o2["dim"]), np.zeros(len(prob["U"])), o2["vdim"])
+    assert rel_l2(dr, prob["dr_da"]) < 1e-13
+    o0 = run_oracle(prob, wrt=0)
+    dS_E = fo.gather(o0["shape_table"], prob["dS"], o0["dim"])
+    dr = fo.scatter_add(o0["table"], fo.action_of_gradient_kernel(o0["blocks"], dS_E, 1, o0["p"], o0["q"], o0["dim"]),
+                        np.zeros(len(prob["U"])), o0["vdim"])
+    assert rel_l2(dr, prob["dr_dshape"]) < 1e-13
+
+
+def test_element_matrices_and_csr(case):
+    prob, o = case
+    if "K_e" not in prob:
+        pytest.skip("fixture without matrices")
+    K_e = fo.element_gradient_kernel(o["blocks"], o["p"], o["p"], o["q"], o["dim"])
+    assert rel_l2(K_e, prob["K_e"]) < 1e-13
+    vd = fo.element_vdofs(o["table"], o["vdim"], int(prob["num_nodes"]))
+    row_ptr, col_ind, keys = fo.csr_pattern(vd, vd, len(prob["U"]))
+    assert np.array_equal(row_ptr, prob["row_ptr"]) and np.array_equal(col_ind, prob["col_ind"])
+    vals = fo.csr_assemble(prob["K_e"], vd, vd, keys)
+    assert np.array_equal(vals, prob["values"])  # same additions in the same order
+
+
+@pytest.mark.skipif(not ref.available(), reason="oracle/_ref not built")
+@pytest.mark.parametrize("kind,vdim,params", [("thermal_linear_conductor", 1, [1.3, 0.7, 2.1])])
+def test_live_reference_other_integrands(kind, vdim, params):
+    from oracle.make_golden import reference_problem
+    prob = reference_problem(mesh_spec=("cart3d", 2, 2, 2, 0.03), kind=kind, p=2, params=params, vdim=vdim,
+                             shape_amp=0.01)
+    o = run_oracle(prob)
+    assert rel_l2(o["r_E"], prob["r_E"]) < 1e-13
+    dU_E = fo.gather(o["table"], prob["dU"], vdim)
+    assert rel_l2(fo.action_of_gradient_kernel(o["blocks"], dU_E, 2, 2, 3, 3), prob["dr_E"]) < 1e-13
+    K_e = fo.element_gradient_kernel(o["blocks"], 2, 2, 3, 3)
+    assert rel_l2(K_e, prob["K_e"]) < 1e-13
