@@ -642,7 +642,7 @@ __device__ __forceinline__ void load_and_interpolate(const EvalParams<Sig::NT>& 
     const int node = rem - a * TP::ndof;
     int       e    = blockIdx.x * Sig::EPB + le;
     if (e >= P.num_elements) e = P.num_elements - 1;
-    const int       ge  = P.elements[e];
+    const int       ge  = P.elements ? P.elements[e] : e;
     const long long idx = (long long)f.table[(long long)ge * TP::ndof + node];
     scratch[le * per + a * TP::ndof + node] = f.L[idx * f.node_stride + a * f.comp_stride];
   }
@@ -761,7 +761,7 @@ __global__ void __launch_bounds__(Sig::threads, MINB) evaluation_kernel(const __
   const int  e_raw = blockIdx.x * EPB + el;
   const bool valid = e_raw < P.num_elements;
   const int  e     = valid ? e_raw : P.num_elements - 1;
-  const int  elem  = P.elements[e];
+  const int  elem  = P.elements ? P.elements[e] : e;
 
   // geometric factors of this quadrature point:  Jm(i,j) = dX_i/dxi_j = J_q[e](j,i,q)
   tensor<double, dim>      x{};
@@ -1022,7 +1022,7 @@ __global__ void __launch_bounds__(JvpConfig<dim, q, nk, ck, nt, ct, MASK, EPB_>:
   const int  e_raw = blockIdx.x * EPB + el;
   const bool valid = e_raw < P.num_elements;
   const int  e     = valid ? e_raw : P.num_elements - 1;
-  const int  elem  = P.elements[e];
+  const int  elem  = P.elements ? P.elements[e] : e;
 
   // issue the derivative loads early: they are independent of the interpolation
   const double* dq = P.dqf + (long long)blockIdx.x * LY.entries * C::threads + threadIdx.x;
@@ -1036,7 +1036,7 @@ __global__ void __launch_bounds__(JvpConfig<dim, q, nk, ck, nt, ct, MASK, EPB_>:
     const int node = rem - a * C::TPk::ndof;
     int       ee   = blockIdx.x * EPB + le;
     if (ee >= P.num_elements) ee = P.num_elements - 1;
-    const int       ge  = P.elements[ee];
+    const int       ge  = P.elements ? P.elements[ee] : ee;
     const long long idx = (long long)f.table[(long long)ge * C::TPk::ndof + node];
     scratch[le * per + a * C::TPk::ndof + node] = f.L[idx * f.node_stride + a * f.comp_stride];
   }
@@ -1149,7 +1149,7 @@ __global__ void __launch_bounds__(ElemGradConfig<dim, q, nk, ck, nt, ct, MASK, E
   const int  e_raw = blockIdx.x * EPB + el;
   const bool valid = e_raw < P.num_elements;
   const int  e     = valid ? e_raw : P.num_elements - 1;
-  const int  elem  = P.elements[e];
+  const int  elem  = P.elements ? P.elements[e] : e;
 
   const BasisTable1D& tb = P.test_basis;
   double              w  = tb.w[qx] * tb.w[qy];

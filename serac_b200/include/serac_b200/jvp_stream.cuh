@@ -1,0 +1,490 @@
+// serac_b200: the Jacobian-vector product as a persistent, TMA-fed streaming kernel.
+//
+// Same arithmetic as jvp_kernel (domain_integral.cuh; reference: action_of_gradient_kernel,
+// src/serac/numerics/functional/domain_integral_kernels.hpp:277-304 with chain_rule :223-237), different data movement.
+// The kernel is HBM-bound on the stored derivatives (648 of 666 B per quadrature point for solids), so:
+//   * CTAs are persistent (grid = resident CTAs x SMs) and walk the derivative tiles round-robin;
+//   * each tile -- [entry][lane] doubles, contiguous in HBM -- is brought into shared memory by ONE bulk async copy
+//     (cp.async.bulk / TMA, completion on an mbarrier), issued a whole tile ahead of its use, so the copy engine keeps
+//     tens of KB in flight per SM without costing registers;
+//   * the du gather of tile i+1 (table -> L dependent loads) is issued into registers while tile i is contracted and
+//     integrated, so its latency never sits on the critical path;
+//   * the 1-D basis rows / columns every thread needs live in registers for the whole kernel (the sum-factorised
+//     stages then cost one shared-memory load per FMA instead of two).
+#pragma once
+
+#include <cstdint>
+
+#include "serac_b200/domain_integral.cuh"
+
+namespace serac {
+namespace b200 {
+
+namespace tma {
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return uint32_t(__cvta_generic_to_shared(p)); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, int count)
+{
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes)
+{
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+/// 1-D bulk copy global -> shared (SASS: UBLKCP); dst/src 16-byte aligned, bytes a multiple of 16
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar)
+{
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                   smem_u32(dst)),
+               "l"(src), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity)
+{
+  asm volatile(
+      "{\n"
+      ".reg .pred P1;\n"
+      "LAB_WAIT:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
+      "@P1 bra DONE;\n"
+      "bra LAB_WAIT;\n"
+      "DONE:\n"
+      "}" ::"r"(smem_u32(bar)),
+      "r"(parity)
+      : "memory");
+}
+}  // namespace tma
+
+/// this thread's rows of B and G (interpolation) and columns (integration) in each direction
+template <int dim, int n, int q>
+struct ThreadBasis {
+  double Br[dim][n], Gr[dim][n];  ///< B(q_d, 0..n-1): row of this thread's quadrature index in direction d
+  double Bc[dim][q], Gc[dim][q];  ///< B(0..q-1, min(q_d, n-1)): column of this thread's node index in direction d
+  __device__ __forceinline__ void load(const double* __restrict__ B, const double* __restrict__ G, const int (&qi)[3])
+  {
+    SB_UNROLL
+    for (int d = 0; d < dim; d++) {
+      SB_UNROLL
+      for (int k = 0; k < n; k++) {
+        Br[d][k] = B[qi[d] * n + k];
+        Gr[d][k] = G[qi[d] * n + k];
+      }
+      const int col = qi[d] < n ? qi[d] : n - 1;
+      SB_UNROLL
+      for (int k = 0; k < q; k++) {
+        Bc[d][k] = B[k * n + col];
+        Gc[d][k] = G[k * n + col];
+      }
+    }
+  }
+};
+
+/// sum-factorised interpolation / integration with the 1-D tables in registers (same staging and summation order as
+/// TensorProduct<> in domain_integral.cuh, hence the same bits)
+template <int dim, int n, int q, int c>
+struct TensorProductR;
+
+template <int n, int q, int c>
+struct TensorProductR<3, n, q, c> {
+  using TP = TensorProduct<3, n, q, c>;
+  template <bool NEED_VALUE, bool NEED_GRAD>
+  static __device__ __forceinline__ void interpolate(const ThreadBasis<3, n, q>& tb, double* s, int qx, int qy, int qz,
+                                                     double (&val)[c], double (&grad)[c][3])
+  {
+    constexpr int ndof = n * n * n;
+    const double* u    = s;
+    double*       A1   = s + c * ndof;
+    double*       A2   = A1 + 2 * c * n * n * q;
+    if (qz < n && qy < n) {
+      SB_UNROLL
+      for (int a = 0; a < c; a++) {
+        double sB = 0.0, sG = 0.0;
+        SB_UNROLL
+        for (int dx = 0; dx < n; dx++) {
+          const double uu = u[((a * n + qz) * n + qy) * n + dx];
+          sB += tb.Br[0][dx] * uu;
+          if (NEED_GRAD) sG += tb.Gr[0][dx] * uu;
+        }
+        A1[(((0 * c + a) * n + qz) * n + qy) * q + qx] = sB;
+        if (NEED_GRAD) A1[(((1 * c + a) * n + qz) * n + qy) * q + qx] = sG;
+      }
+    }
+    __syncthreads();
+    if (qz < n) {
+      SB_UNROLL
+      for (int a = 0; a < c; a++) {
+        double sBB = 0.0, sGB = 0.0, sBG = 0.0;
+        SB_UNROLL
+        for (int dy = 0; dy < n; dy++) {
+          const double b = A1[(((0 * c + a) * n + qz) * n + dy) * q + qx];
+          sBB += tb.Br[1][dy] * b;
+          if (NEED_GRAD) {
+            const double g = A1[(((1 * c + a) * n + qz) * n + dy) * q + qx];
+            sGB += tb.Br[1][dy] * g;
+            sBG += tb.Gr[1][dy] * b;
+          }
+        }
+        A2[(((0 * c + a) * n + qz) * q + qy) * q + qx] = sBB;
+        if (NEED_GRAD) {
+          A2[(((1 * c + a) * n + qz) * q + qy) * q + qx] = sGB;
+          A2[(((2 * c + a) * n + qz) * q + qy) * q + qx] = sBG;
+        }
+      }
+    }
+    __syncthreads();
+    SB_UNROLL
+    for (int a = 0; a < c; a++) {
+      double v = 0.0, gx = 0.0, gy = 0.0, gz = 0.0;
+      SB_UNROLL
+      for (int dz = 0; dz < n; dz++) {
+        const double bb = A2[(((0 * c + a) * n + dz) * q + qy) * q + qx];
+        if (NEED_VALUE) v += tb.Br[2][dz] * bb;
+        if (NEED_GRAD) {
+          const double gb = A2[(((1 * c + a) * n + dz) * q + qy) * q + qx];
+          const double bg = A2[(((2 * c + a) * n + dz) * q + qy) * q + qx];
+          gx += tb.Br[2][dz] * gb;
+          gy += tb.Br[2][dz] * bg;
+          gz += tb.Gr[2][dz] * bb;
+        }
+      }
+      val[a]     = v;
+      grad[a][0] = gx;
+      grad[a][1] = gy;
+      grad[a][2] = gz;
+    }
+  }
+
+  template <bool HAS_SOURCE, bool HAS_FLUX>
+  static __device__ __forceinline__ bool integrate(const ThreadBasis<3, n, q>& tb, double* s, int qx, int qy, int qz,
+                                                   const double (&src)[c], const double (&flux)[c][3],
+                                                   double (&out)[c])
+  {
+    double* S  = s;
+    double* P  = S + 4 * c * q * q * q;
+    double* Qs = P + 3 * c * n * q * q;
+    SB_UNROLL
+    for (int a = 0; a < c; a++) {
+      if (HAS_SOURCE) S[(((0 * c + a) * q + qz) * q + qy) * q + qx] = src[a];
+      if (HAS_FLUX) {
+        S[(((1 * c + a) * q + qz) * q + qy) * q + qx] = flux[a][0];
+        S[(((2 * c + a) * q + qz) * q + qy) * q + qx] = flux[a][1];
+        S[(((3 * c + a) * q + qz) * q + qy) * q + qx] = flux[a][2];
+      }
+    }
+    __syncthreads();
+    if (qz < n) {
+      SB_UNROLL
+      for (int a = 0; a < c; a++) {
+        double p0 = 0.0, p1 = 0.0, p2 = 0.0;
+        SB_UNROLL
+        for (int k = 0; k < q; k++) {
+          if (HAS_SOURCE) p0 += tb.Bc[2][k] * S[(((0 * c + a) * q + k) * q + qy) * q + qx];
+          if (HAS_FLUX) {
+            p0 += tb.Gc[2][k] * S[(((3 * c + a) * q + k) * q + qy) * q + qx];
+            p1 += tb.Bc[2][k] * S[(((1 * c + a) * q + k) * q + qy) * q + qx];
+            p2 += tb.Bc[2][k] * S[(((2 * c + a) * q + k) * q + qy) * q + qx];
+          }
+        }
+        P[(((0 * c + a) * n + qz) * q + qy) * q + qx] = p0;
+        if (HAS_FLUX) {
+          P[(((1 * c + a) * n + qz) * q + qy) * q + qx] = p1;
+          P[(((2 * c + a) * n + qz) * q + qy) * q + qx] = p2;
+        }
+      }
+    }
+    __syncthreads();
+    if (qz < n && qy < n) {
+      SB_UNROLL
+      for (int a = 0; a < c; a++) {
+        double q0 = 0.0, q1 = 0.0;
+        SB_UNROLL
+        for (int k = 0; k < q; k++) {
+          q0 += tb.Bc[1][k] * P[(((0 * c + a) * n + qz) * q + k) * q + qx];
+          if (HAS_FLUX) {
+            q0 += tb.Gc[1][k] * P[(((2 * c + a) * n + qz) * q + k) * q + qx];
+            q1 += tb.Bc[1][k] * P[(((1 * c + a) * n + qz) * q + k) * q + qx];
+          }
+        }
+        Qs[(((0 * c + a) * n + qz) * n + qy) * q + qx] = q0;
+        if (HAS_FLUX) Qs[(((1 * c + a) * n + qz) * n + qy) * q + qx] = q1;
+      }
+    }
+    __syncthreads();
+    const bool owner = (qz < n && qy < n && qx < n);
+    if (owner) {
+      SB_UNROLL
+      for (int a = 0; a < c; a++) {
+        double r = 0.0;
+        SB_UNROLL
+        for (int k = 0; k < q; k++) {
+          r += tb.Bc[0][k] * Qs[(((0 * c + a) * n + qz) * n + qy) * q + k];
+          if (HAS_FLUX) r += tb.Gc[0][k] * Qs[(((1 * c + a) * n + qz) * n + qy) * q + k];
+        }
+        out[a] = r;
+      }
+    }
+    return owner;
+  }
+};
+
+template <int n, int q, int c>
+struct TensorProductR<2, n, q, c> {
+  template <bool NEED_VALUE, bool NEED_GRAD>
+  static __device__ __forceinline__ void interpolate(const ThreadBasis<2, n, q>& tb, double* s, int qx, int qy, int,
+                                                     double (&val)[c], double (&grad)[c][2])
+  {
+    constexpr int ndof = n * n;
+    const double* u    = s;
+    double*       A1   = s + c * ndof;
+    if (qy < n) {
+      SB_UNROLL
+      for (int a = 0; a < c; a++) {
+        double sB = 0.0, sG = 0.0;
+        SB_UNROLL
+        for (int dx = 0; dx < n; dx++) {
+          const double uu = u[(a * n + qy) * n + dx];
+          sB += tb.Br[0][dx] * uu;
+          if (NEED_GRAD) sG += tb.Gr[0][dx] * uu;
+        }
+        A1[((0 * c + a) * n + qy) * q + qx] = sB;
+        if (NEED_GRAD) A1[((1 * c + a) * n + qy) * q + qx] = sG;
+      }
+    }
+    __syncthreads();
+    SB_UNROLL
+    for (int a = 0; a < c; a++) {
+      double v = 0.0, gx = 0.0, gy = 0.0;
+      SB_UNROLL
+      for (int dy = 0; dy < n; dy++) {
+        const double b = A1[((0 * c + a) * n + dy) * q + qx];
+        if (NEED_VALUE) v += tb.Br[1][dy] * b;
+        if (NEED_GRAD) {
+          gx += tb.Br[1][dy] * A1[((1 * c + a) * n + dy) * q + qx];
+          gy += tb.Gr[1][dy] * b;
+        }
+      }
+      val[a]     = v;
+      grad[a][0] = gx;
+      grad[a][1] = gy;
+    }
+  }
+
+  template <bool HAS_SOURCE, bool HAS_FLUX>
+  static __device__ __forceinline__ bool integrate(const ThreadBasis<2, n, q>& tb, double* s, int qx, int qy, int,
+                                                   const double (&src)[c], const double (&flux)[c][2],
+                                                   double (&out)[c])
+  {
+    double* S = s;
+    double* P = S + 3 * c * q * q;
+    SB_UNROLL
+    for (int a = 0; a < c; a++) {
+      if (HAS_SOURCE) S[((0 * c + a) * q + qy) * q + qx] = src[a];
+      if (HAS_FLUX) {
+        S[((1 * c + a) * q + qy) * q + qx] = flux[a][0];
+        S[((2 * c + a) * q + qy) * q + qx] = flux[a][1];
+      }
+    }
+    __syncthreads();
+    if (qy < n) {
+      SB_UNROLL
+      for (int a = 0; a < c; a++) {
+        double p0 = 0.0, p1 = 0.0;
+        SB_UNROLL
+        for (int k = 0; k < q; k++) {
+          if (HAS_SOURCE) p0 += tb.Bc[1][k] * S[((0 * c + a) * q + k) * q + qx];
+          if (HAS_FLUX) {
+            p0 += tb.Gc[1][k] * S[((2 * c + a) * q + k) * q + qx];
+            p1 += tb.Bc[1][k] * S[((1 * c + a) * q + k) * q + qx];
+          }
+        }
+        P[((0 * c + a) * n + qy) * q + qx] = p0;
+        if (HAS_FLUX) P[((1 * c + a) * n + qy) * q + qx] = p1;
+      }
+    }
+    __syncthreads();
+    const bool owner = (qy < n && qx < n);
+    if (owner) {
+      SB_UNROLL
+      for (int a = 0; a < c; a++) {
+        double r = 0.0;
+        SB_UNROLL
+        for (int k = 0; k < q; k++) {
+          r += tb.Bc[0][k] * P[((0 * c + a) * n + qy) * q + k];
+          if (HAS_FLUX) r += tb.Gc[0][k] * P[((1 * c + a) * n + qy) * q + k];
+        }
+        out[a] = r;
+      }
+    }
+    return owner;
+  }
+};
+
+template <int dim, int q, int nk, int ck, int nt, int ct, int MASK, int EPB_ = 0>
+struct JvpStreamConfig {
+  using Base                     = JvpConfig<dim, q, nk, ck, nt, ct, MASK, EPB_>;
+  static constexpr int QPE       = Base::QPE;
+  static constexpr int EPB       = Base::EPB;
+  static constexpr int threads   = Base::threads;
+  static constexpr int per       = Base::per;
+  static constexpr int entries   = Base::layout().entries;
+  static constexpr int tile_doubles = entries * threads;
+  /// the bulk copy moves whole 16-byte units
+  static constexpr bool supported = (tile_doubles % 2 == 0) && (tile_doubles * 8 < (1 << 20));
+  static constexpr int  ndof_k    = ipow(nk, dim);
+  static constexpr int  gathers   = EPB * ck * ndof_k;
+  static constexpr int  NG        = (gathers + threads - 1) / threads;  ///< du values each thread prefetches
+  // smem: [tables 4 x MAX_Q^2][scratch EPB x per (+1 pad to keep the tile 16-byte aligned)][tile][mbarrier]
+  static constexpr int scratch_doubles = ((4 * MAX_Q * MAX_Q + EPB * per + 1) / 2) * 2;
+  static constexpr size_t smem_bytes   = size_t(scratch_doubles + tile_doubles) * 8 + 16;
+};
+
+template <int dim, int q, int nk, int ck, int nt, int ct, int MASK, int EPB_ = 0>
+__global__ void __launch_bounds__(JvpStreamConfig<dim, q, nk, ck, nt, ct, MASK, EPB_>::threads, 2)
+    jvp_stream_kernel(const __grid_constant__ JvpParams P, const int num_tiles)
+{
+  using C                       = JvpStreamConfig<dim, q, nk, ck, nt, ct, MASK, EPB_>;
+  using B                       = typename C::Base;
+  constexpr DerivativeLayout LY = B::layout();
+  constexpr int QPE = C::QPE, EPB = C::EPB, per = C::per, T = C::threads, NG = C::NG, ndk = C::ndof_k;
+  extern __shared__ __align__(16) double smem[];
+  double*   tables  = smem;
+  double*   scratch = smem + 4 * MAX_Q * MAX_Q;
+  double*   tile_s  = smem + C::scratch_doubles;
+  uint64_t* bar     = reinterpret_cast<uint64_t*>(tile_s + C::tile_doubles);
+  const int tid     = threadIdx.x;
+
+  for (int i = tid; i < 4 * MAX_Q * MAX_Q; i += T) {
+    const int           which = i / (2 * MAX_Q * MAX_Q);
+    const int           rem   = i - which * (2 * MAX_Q * MAX_Q);
+    const BasisTable1D& bt    = (which == 0) ? P.trial_basis : P.test_basis;
+    tables[i]                 = (rem < MAX_Q * MAX_Q) ? bt.B[rem] : bt.G[rem - MAX_Q * MAX_Q];
+  }
+  if (tid == 0) tma::mbar_init(bar, 1);
+  __syncthreads();
+
+  constexpr uint32_t tile_bytes = uint32_t(C::tile_doubles) * 8u;
+  int                tile       = blockIdx.x;
+  if (tid == 0 && tile < num_tiles) {
+    tma::mbar_expect_tx(bar, tile_bytes);
+    tma::bulk_g2s(tile_s, P.dqf + (long long)tile * C::tile_doubles, tile_bytes, bar);
+  }
+
+  const int el    = tid / QPE;
+  const int ql    = tid - el * QPE;
+  const int qi[3] = {ql % q, (ql / q) % q, (dim == 3) ? ql / (q * q) : 0};
+  const int qx = qi[0], qy = qi[1], qz = qi[2];
+
+  ThreadBasis<dim, nk, q> tbk;
+  ThreadBasis<dim, nt, q> tbt;
+  tbk.load(tables, tables + MAX_Q * MAX_Q, qi);
+  tbt.load(tables + 2 * MAX_Q * MAX_Q, tables + 3 * MAX_Q * MAX_Q, qi);
+  const BasisTable1D& wt = P.test_basis;
+  double              w  = wt.w[qx] * wt.w[qy];
+  if (dim == 3) w *= wt.w[qz];
+
+  // tile-invariant part of this thread's gather slots
+  const FieldArg& f = P.trial;
+  int             g_le[NG], g_node[NG];
+  long long       g_comp[NG];
+  SB_UNROLL
+  for (int j = 0; j < NG; j++) {
+    const int i   = tid + j * T;
+    const int ii  = (i < C::gathers) ? i : 0;
+    g_le[j]       = ii / (ck * ndk);
+    const int rem = ii - g_le[j] * (ck * ndk);
+    const int a   = rem / ndk;
+    g_node[j]     = rem - a * ndk;
+    g_comp[j]     = a * f.comp_stride;
+  }
+  auto gather = [&](int t, double(&v)[NG]) {
+    SB_UNROLL
+    for (int j = 0; j < NG; j++) {
+      int e = t * EPB + g_le[j];
+      if (e >= P.num_elements) e = P.num_elements - 1;
+      const int       ge  = P.elements ? P.elements[e] : e;
+      const long long idx = (long long)f.table[(long long)ge * ndk + g_node[j]];
+      v[j]                = f.L[idx * f.node_stride + g_comp[j]];
+    }
+  };
+
+  double nxt[NG];
+  if (tile < num_tiles) gather(tile, nxt);
+  uint32_t parity = 0;
+
+  using TPk = TensorProductR<dim, nk, q, ck>;
+  using TPt = TensorProductR<dim, nt, q, ct>;
+  constexpr bool has_source = B::d00 || B::d01;
+  constexpr bool has_flux   = B::d10 || B::d11;
+
+  for (; tile < num_tiles; tile += gridDim.x) {
+    __syncthreads();  // previous tile's integrate has finished reading the scratch
+    SB_UNROLL
+    for (int j = 0; j < NG; j++) {
+      const int i = tid + j * T;
+      if (i < C::gathers) scratch[g_le[j] * per + (i - g_le[j] * (ck * ndk))] = nxt[j];
+    }
+    __syncthreads();
+    double v[ck];
+    double g[ck][dim];
+    TPk::template interpolate<(B::d00 || B::d10), (B::d01 || B::d11)>(tbk, scratch + el * per, qx, qy, qz, v, g);
+
+    const int next = tile + gridDim.x;
+    if (next < num_tiles) gather(next, nxt);  // in flight while this tile is contracted and integrated
+
+    tma::mbar_wait(bar, parity);
+    parity ^= 1u;
+
+    const double* dq = tile_s + tid;
+    double        src[ct];
+    double        flux[ct][dim];
+    SB_UNROLL
+    for (int a = 0; a < ct; a++) {
+      double s = 0.0;
+      if constexpr (B::d00) {
+        SB_UNROLL
+        for (int b = 0; b < ck; b++) s += dq[(LY.offset[0] + a * ck + b) * T] * v[b];
+      }
+      if constexpr (B::d01) {
+        SB_UNROLL
+        for (int b = 0; b < ck; b++) {
+          SB_UNROLL
+          for (int l = 0; l < dim; l++) s += dq[(LY.offset[1] + (a * ck + b) * dim + l) * T] * g[b][l];
+        }
+      }
+      src[a] = s * w;
+      SB_UNROLL
+      for (int k = 0; k < dim; k++) {
+        double fl = 0.0;
+        if constexpr (B::d10) {
+          SB_UNROLL
+          for (int b = 0; b < ck; b++) fl += dq[(LY.offset[2] + (a * dim + k) * ck + b) * T] * v[b];
+        }
+        if constexpr (B::d11) {
+          SB_UNROLL
+          for (int b = 0; b < ck; b++) {
+            SB_UNROLL
+            for (int l = 0; l < dim; l++) fl += dq[(LY.offset[3] + ((a * dim + k) * ck + b) * dim + l) * T] * g[b][l];
+          }
+        }
+        flux[a][k] = fl * w;
+      }
+    }
+    __syncthreads();  // every thread is done with the tile buffer (and with the interpolation scratch)
+    if (tid == 0 && next < num_tiles) {
+      tma::mbar_expect_tx(bar, tile_bytes);
+      tma::bulk_g2s(tile_s, P.dqf + (long long)next * C::tile_doubles, tile_bytes, bar);
+    }
+    double     out[ct];
+    const bool owner = TPt::template integrate<has_source, has_flux>(tbt, scratch + el * per, qx, qy, qz, src, flux, out);
+    const int  e_raw = tile * EPB + el;
+    if (owner && e_raw < P.num_elements) {
+      const int elem = P.elements ? P.elements[e_raw] : e_raw;
+      const int node = (dim == 3) ? (qz * nt + qy) * nt + qx : qy * nt + qx;
+      SB_UNROLL
+      for (int a = 0; a < ct; a++) P.r_E[((long long)elem * ct + a) * ipow(nt, dim) + node] = out[a];
+    }
+  }
+}
+
+}  // namespace b200
+}  // namespace serac

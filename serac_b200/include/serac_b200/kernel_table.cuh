@@ -8,10 +8,12 @@
 // functors; registry_*.cu does it for the named integrands shipped in the library.
 #pragma once
 
+#include <cstdlib>
 #include <cstring>
 
 #include "serac_b200.h"
 #include "serac_b200/domain_integral.cuh"
+#include "serac_b200/jvp_stream.cuh"
 
 namespace serac {
 namespace b200 {
@@ -66,6 +68,28 @@ int launch_evaluate(const sb_eval_args* a, const void* qf_blob, void* stream)
   return int(cudaGetLastError());
 }
 
+/// number of SMs of the current device (cached)
+inline int sm_count()
+{
+  static int n = 0;
+  if (n == 0) {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess)
+      n = 148;
+  }
+  return n;
+}
+
+/// SB_JVP_KERNEL=legacy selects the one-tile-per-CTA kernel (for A/B measurements); default is the TMA-fed stream kernel
+inline bool use_stream_jvp()
+{
+  static const bool v = [] {
+    const char* e = std::getenv("SB_JVP_KERNEL");
+    return !(e && std::strcmp(e, "legacy") == 0);
+  }();
+  return v;
+}
+
 template <typename Sig, int WRT, int MASK>
 int launch_jvp(const sb_jvp_args* a, void* stream)
 {
@@ -85,11 +109,28 @@ int launch_jvp(const sb_jvp_args* a, void* stream)
     P.dqf          = a->dqf_dev;
     P.r_E          = a->r_E_dev;
     if (a->num_elements <= 0) return 0;
+    const int tiles = (a->num_elements + C::EPB - 1) / C::EPB;
+    using SC        = JvpStreamConfig<Sig::dim, Sig::q, nk, ck, Sig::test_n, Sig::test_c, MASK, Sig::EPB>;
+    if constexpr (SC::supported && SC::smem_bytes <= 227 * 1024) {
+      if (use_stream_jvp()) {
+        auto       kernel = &jvp_stream_kernel<Sig::dim, Sig::q, nk, ck, Sig::test_n, Sig::test_c, MASK, Sig::EPB>;
+        static int resident = 0;  // CTAs per SM for this instantiation
+        if (resident == 0) {
+          if (int e = ensure_smem(kernel, SC::smem_bytes)) return e;
+          int nb = 0;
+          if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kernel, SC::threads, SC::smem_bytes) != cudaSuccess) nb = 1;
+          resident = nb > 0 ? nb : 1;
+        }
+        const int grid = tiles < resident * sm_count() ? tiles : resident * sm_count();
+        kernel<<<grid, SC::threads, SC::smem_bytes, cudaStream_t(stream)>>>(P, tiles);
+        sb_count_launch();
+        return int(cudaGetLastError());
+      }
+    }
     auto         kernel = &jvp_kernel<Sig::dim, Sig::q, nk, ck, Sig::test_n, Sig::test_c, MASK, Sig::EPB>;
     const size_t smem   = size_t(C::smem_doubles) * sizeof(double);
     if (int e = ensure_smem(kernel, smem)) return e;
-    const int grid = (a->num_elements + C::EPB - 1) / C::EPB;
-    kernel<<<grid, C::threads, smem, cudaStream_t(stream)>>>(P);
+    kernel<<<tiles, C::threads, smem, cudaStream_t(stream)>>>(P);
     sb_count_launch();
     return int(cudaGetLastError());
   }
