@@ -22,6 +22,7 @@
 #include <cuda_runtime.h>
 
 #include "serac_b200/finite_element.hpp"
+#include "serac_b200/physics_functors.hpp"
 #include "serac_b200/tensor.hpp"
 
 namespace serac {
@@ -578,7 +579,8 @@ auto plain_output_type(std::integer_sequence<int, I...>)
   }
 }
 
-template <typename Sig, int WRT, typename QF, typename State>
+/// FAST: use the q-function's own flux tangent (provides_flux_tangent, physics_functors.hpp) instead of dual numbers
+template <typename Sig, int WRT, typename QF, typename State, bool FAST = true>
 struct DerivativeTraits {
   using seq              = std::make_integer_sequence<int, Sig::NT>;
   using value_pass_out   = decltype(pass_output_type<Sig, WRT, -1, QF, State, 1>(seq{}));
@@ -587,10 +589,14 @@ struct DerivativeTraits {
   static constexpr int  ct  = Sig::test_c;
   static constexpr int  ck  = trial::components;
   static constexpr int  dim = Sig::dim;
-  static constexpr bool d00 = output_traits<value_pass_out>::source_dual;
-  static constexpr bool d10 = output_traits<value_pass_out>::flux_dual;
-  static constexpr bool d01 = output_traits<grad_pass_out>::source_dual;
-  static constexpr bool d11 = output_traits<grad_pass_out>::flux_dual;
+  static constexpr bool tangent = FAST && !std::is_same_v<State, Nothing> && provides_flux_tangent<QF, WRT>::value;
+  static constexpr bool d00 = !tangent && output_traits<value_pass_out>::source_dual;
+  static constexpr bool d10 = !tangent && output_traits<value_pass_out>::flux_dual;
+  static constexpr bool d01 = !tangent && output_traits<grad_pass_out>::source_dual;
+  static constexpr bool d11 = tangent || output_traits<grad_pass_out>::flux_dual;
+  static_assert(!tangent || (!output_traits<value_pass_out>::source_dual && !output_traits<value_pass_out>::flux_dual &&
+                             !output_traits<grad_pass_out>::source_dual),
+                "a flux tangent provider may only be declared for an argument whose gradient alone enters the flux");
   static constexpr bool value_pass_active = d00 || d10;
   static constexpr bool grad_pass_active  = d01 || d11;
   static constexpr DerivativeLayout layout() { return make_layout(ct, ck, dim, d00, d01, d10, d11); }
@@ -728,7 +734,7 @@ __device__ __forceinline__ auto call_qf_tuple(const QF& qf, double t, const Pos&
 }
 
 /// ROWS: gradient rows seeded per derivative pass (1 .. ck); MINB: __launch_bounds__ minimum resident CTAs per SM
-template <typename Sig, int WRT, typename QF, typename State, int ROWS = 1, int MINB = 1>
+template <typename Sig, int WRT, typename QF, typename State, int ROWS = 1, int MINB = 1, bool FAST = true>
 __global__ void __launch_bounds__(Sig::threads, MINB) evaluation_kernel(const __grid_constant__ EvalParams<Sig::NT> P,
                                                                   const __grid_constant__ QF qf)
 {
@@ -847,14 +853,40 @@ __global__ void __launch_bounds__(Sig::threads, MINB) evaluation_kernel(const __
       if (P.update_state && valid) *qd = st;
     }
   } else {
-    using DT                   = DerivativeTraits<Sig, WRT, QF, State>;
+    using DT                   = DerivativeTraits<Sig, WRT, QF, State, FAST>;
     constexpr DerivativeLayout LY = DT::layout();
     constexpr int              ck = DT::ck;
     const long long            tile = blockIdx.x;
     double* dq = P.dqf + tile * (long long)LY.entries * Sig::threads + threadIdx.x;
     bool    first = true;
 
-    if constexpr (DT::value_pass_active) {
+    if constexpr (DT::tangent) {
+      // the q-function differentiates itself (closed-form / material-only AD) and applies the parent maps analytically
+      State               st = state_old;
+      ParentMap<dim>      map{invJ, dv};
+      tensor<double, ct>      s_p{};
+      tensor<double, ct, dim> f_p{};
+      auto sink = [&](int a, int k, int b, int l, double v) {
+        if (valid) dq[(long long)(((a * dim + k) * ck + b) * dim + l) * Sig::threads] = v;
+      };
+      [&]<int... I>(std::integer_sequence<int, I...>)
+      {
+        qf.flux_tangent(std::integral_constant<int, WRT>{}, P.t, pos, st, map, s_p, f_p, sink, get<I>(inputs)...);
+      }
+      (seq{});
+      SB_UNROLL
+      for (int a = 0; a < ct; a++) {
+        if constexpr (has_source) src[a] = s_p[a] * w;
+        if constexpr (has_flux) {
+          SB_UNROLL
+          for (int k = 0; k < dim; k++) flux[a][k] = f_p[a][k] * w;
+        }
+      }
+      if constexpr (!std::is_empty_v<State>) {
+        if (P.update_state && valid) *qd = st;
+      }
+      first = false;
+    } else if constexpr (DT::value_pass_active) {
       State st  = state_old;
       auto  out = run_pass<Sig, WRT, -1, 1, QF, State>(qf, P.t, pos, st, inputs, invJ, seq{});
       using out_t = std::decay_t<decltype(out)>;
@@ -888,7 +920,7 @@ __global__ void __launch_bounds__(Sig::threads, MINB) evaluation_kernel(const __
         }
       }
     }
-    if constexpr (DT::grad_pass_active) {
+    if constexpr (!DT::tangent && DT::grad_pass_active) {
       static_assert(ck % ROWS == 0, "ROWS must divide the number of trial components");
       auto grad_pass = [&](auto pass_c) {
         constexpr int              pass = decltype(pass_c)::value;
@@ -937,7 +969,7 @@ __global__ void __launch_bounds__(Sig::threads, MINB) evaluation_kernel(const __
       [&]<int... R>(std::integer_sequence<int, R...>) { (grad_pass(std::integral_constant<int, R>{}), ...); }
       (std::make_integer_sequence<int, ck / ROWS>{});
     }
-    if constexpr (!DT::value_pass_active && !DT::grad_pass_active) {
+    if constexpr (!DT::tangent && !DT::value_pass_active && !DT::grad_pass_active) {
       State  st  = state_old;
       auto   out = call_qf_tuple<Sig>(qf, P.t, pos, st, inputs, seq{});
       double s_out[ct];

@@ -35,7 +35,7 @@ inline int ensure_smem(K kernel, size_t bytes)
   return 0;
 }
 
-template <typename Sig, int WRT, typename QF, typename State, int ROWS = 1, int MINB = 1>
+template <typename Sig, int WRT, typename QF, typename State, int ROWS = 1, int MINB = 1, bool FAST = true>
 int launch_evaluate(const sb_eval_args* a, const void* qf_blob, void* stream)
 {
   constexpr int NT = Sig::NT;
@@ -57,7 +57,7 @@ int launch_evaluate(const sb_eval_args* a, const void* qf_blob, void* stream)
   P.update_state = a->update_state;
   P.t            = a->t;
   if (a->num_elements <= 0) return 0;
-  auto         kernel = &evaluation_kernel<Sig, WRT, QF, State, ROWS, MINB>;
+  auto         kernel = &evaluation_kernel<Sig, WRT, QF, State, ROWS, MINB, FAST>;
   const size_t smem   = size_t(eval_smem_doubles<Sig>()) * sizeof(double);
   if (int e = ensure_smem(kernel, smem)) return e;
   const int grid = (a->num_elements + Sig::EPB - 1) / Sig::EPB;
@@ -164,15 +164,15 @@ int launch_element_gradient(const sb_elem_grad_args* a, void* stream)
   }
 }
 
-template <typename Sig, typename QF, typename State, int WRT, int ROWS_REQ, int MINB>
+template <typename Sig, typename QF, typename State, int WRT, int ROWS_REQ, int MINB, bool FAST>
 void fill_wrt(sb_kernel_table& T)
 {
-  using DT                   = DerivativeTraits<Sig, WRT, QF, State>;
+  using DT                   = DerivativeTraits<Sig, WRT, QF, State, FAST>;
   constexpr DerivativeLayout L = DT::layout();
   constexpr int mask = (L.has[0] ? 1 : 0) | (L.has[1] ? 2 : 0) | (L.has[2] ? 4 : 0) | (L.has[3] ? 8 : 0);
   constexpr int ck   = Sig::template trial_space<WRT>::components;
   constexpr int ROWS = (ROWS_REQ > 0 && ck % ROWS_REQ == 0) ? ROWS_REQ : 1;
-  T.evaluate_ad[WRT]        = &launch_evaluate<Sig, WRT, QF, State, ROWS, MINB>;
+  T.evaluate_ad[WRT]        = &launch_evaluate<Sig, WRT, QF, State, ROWS, MINB, FAST>;
   T.jvp[WRT]                = &launch_jvp<Sig, WRT, mask>;
   T.element_gradient[WRT]   = &launch_element_gradient<Sig, WRT, mask>;
   T.derivative_mask[WRT]    = mask;
@@ -182,7 +182,8 @@ void fill_wrt(sb_kernel_table& T)
 /// State = serac::Nothing: q-function takes no state argument; serac::Empty: takes an Empty& it never touches;
 /// anything else: trivially copyable per-quadrature-point struct
 /// ROWS_REQ: gradient rows per derivative pass (1 = least registers, ck = one pass); MINB: min resident CTAs per SM
-template <typename Sig, typename QF, typename State, int ROWS_REQ = 1, int MINB = 1>
+/// FAST: let q-functions that provide a flux tangent use it (false = dual numbers everywhere, the reference's scheme)
+template <typename Sig, typename QF, typename State, int ROWS_REQ = 1, int MINB = 1, bool FAST = true>
 sb_kernel_table make_kernel_table()
 {
   static_assert(std::is_trivially_copyable_v<QF>, "q-function functors are copied by value into kernel parameters");
@@ -196,7 +197,7 @@ sb_kernel_table make_kernel_table()
   auto fill         = [&]<int... I>(std::integer_sequence<int, I...>)
   {
     ((T.trial_order[I] = Sig::template trial_space<I>::order,
-      T.trial_components[I] = Sig::template trial_space<I>::components, fill_wrt<Sig, QF, State, I, ROWS_REQ, MINB>(T)),
+      T.trial_components[I] = Sig::template trial_space<I>::components, fill_wrt<Sig, QF, State, I, ROWS_REQ, MINB, FAST>(T)),
      ...);
   };
   fill(std::make_integer_sequence<int, Sig::NT>{});

@@ -29,6 +29,41 @@ enum class GeometricNonlinearities
   Off
 };
 
+/// The two linear maps around a q-function at one quadrature point, folded together so that a tangent provider can apply
+/// them in a single pass (an extension of the q-function concept; the reference differentiates *through* these maps
+/// with dual numbers, src/serac/numerics/functional/domain_integral_kernels.hpp:181-213):
+///   physical gradient = parent gradient . M      (M = inv(dX/dxi), times inv(I + grad p) under a shape-aware wrapper)
+///   parent flux       = scale * physical flux . M^T,   parent source = scale * physical source
+template <int dim>
+struct ParentMap {
+  tensor<double, dim, dim> M;
+  double                   scale;
+};
+
+SB_HD double partial_of(double, int) { return 0.0; }
+template <int N>
+SB_HD double partial_of(const dual<N>& x, int k)
+{
+  return x.gradient[k];
+}
+
+/// does material M provide  stress_tangent_row(state, du_dX, sigma, b, Cb):  Cb[a][j][m] = d sigma[a][j] / d du_dX[b][m] ?
+template <typename M, typename = void>
+struct has_closed_form_tangent : std::false_type {
+};
+template <typename M>
+struct has_closed_form_tangent<M, std::void_t<decltype(M::closed_form_tangent)>> : std::bool_constant<M::closed_form_tangent> {
+};
+
+/// does q-function QF provide flux_tangent(integral_constant<WRT>, ...) for its argument WRT ?
+template <typename QF, int WRT, typename = void>
+struct provides_flux_tangent : std::false_type {
+};
+template <typename QF, int WRT>
+struct provides_flux_tangent<QF, WRT, std::void_t<decltype(QF::template has_flux_tangent<WRT>)>>
+    : std::bool_constant<QF::template has_flux_tangent<WRT>> {
+};
+
 namespace solid_mechanics {
 
 /// linear isotropic elasticity (solid_material.hpp:24-50)
@@ -41,6 +76,24 @@ struct LinearIsotropic {
     auto lambda  = K - (2.0 / 3.0) * G;
     auto epsilon = 0.5 * (transpose(du_dX) + du_dX);
     return lambda * tr(epsilon) * I + 2.0 * G * epsilon;
+  }
+  /// closed-form d sigma / d du_dX, row b: lambda d_aj d_bm + G (d_ab d_jm + d_am d_jb)
+  static constexpr bool closed_form_tangent = true;
+  template <int dim>
+  SERAC_HOST_DEVICE void stress_tangent_row(const State&, const tensor<double, dim, dim>&, const tensor<double, dim, dim>&,
+                                            int b, tensor<double, dim, dim, dim>& Cb) const
+  {
+    const double lambda = K - (2.0 / 3.0) * G;
+    SB_UNROLL
+    for (int a = 0; a < dim; a++) {
+      SB_UNROLL
+      for (int j = 0; j < dim; j++) {
+        SB_UNROLL
+        for (int m = 0; m < dim; m++) {
+          Cb[a][j][m] = ((a == j && b == m) ? lambda : 0.0) + ((a == b && j == m) ? G : 0.0) + ((a == m && j == b) ? G : 0.0);
+        }
+      }
+    }
   }
   double density;
   double K;
@@ -84,6 +137,33 @@ struct NeoHookean {
     auto J_minus_1 = detApIm1(du_dX);
     auto J         = J_minus_1 + 1;
     return (lambda * log1p(J_minus_1) * I + G * B_minus_I) / J;
+  }
+  /// closed-form d sigma / d du_dX, row b.  With F = I + H, B = F F^T, J = det F:
+  ///   d sigma[a][j] / d H[b][m] = ( lambda d_aj Finv[m][b] + G (d_ab F[j][m] + F[a][m] d_jb) ) / J - sigma[a][j] Finv[m][b]
+  static constexpr bool closed_form_tangent = true;
+  template <int dim>
+  SERAC_HOST_DEVICE void stress_tangent_row(const State&, const tensor<double, dim, dim>& du_dX,
+                                            const tensor<double, dim, dim>& sigma, int b,
+                                            tensor<double, dim, dim, dim>& Cb) const
+  {
+    const double lambda = K - (2.0 / 3.0) * G;
+    const auto   F      = du_dX + Identity<dim>();
+    const auto   Finv   = inv(F);
+    const double rJ     = 1.0 / (detApIm1(du_dX) + 1);
+    SB_UNROLL
+    for (int a = 0; a < dim; a++) {
+      SB_UNROLL
+      for (int j = 0; j < dim; j++) {
+        SB_UNROLL
+        for (int m = 0; m < dim; m++) {
+          double v = -sigma[a][j] * Finv[m][b];
+          if (a == j) v += lambda * rJ * Finv[m][b];
+          if (a == b) v += G * rJ * F[j][m];
+          if (j == b) v += G * rJ * F[a][m];
+          Cb[a][j][m] = v;
+        }
+      }
+    }
   }
   double density;
   double K;
@@ -237,6 +317,108 @@ struct MaterialStressFunctor {
     auto flux = dot(stress, transpose(inv(dx_dX))) * det(dx_dX);
     return serac::tuple{material_.density * d2u_dt2, flux};
   }
+
+  /// Tangent fast path (extension): the derivative w.r.t. the displacement (argument 0) touches only the flux and only
+  /// through du_dX, so instead of pushing dual numbers through the Cauchy -> Piola transform and the surrounding linear
+  /// maps, differentiate the material alone (closed form when the material has one, else forward-mode AD one gradient
+  /// row at a time) and apply everything else analytically.  With F = I + H, P = J sigma F^-T, A = M F^-1, Pp = P M^T:
+  ///   parent flux                          = scale Pp
+  ///   d(parent flux)[a][k]/d(parent grad)[b][l] = scale ( J sum_jm A[k][j] M[l][m] C[a][j][b][m] - A[k][b] Pp[a][l] + Pp[a][k] A[l][b] )
+  /// (geometric nonlinearity off: P = sigma, A = M and the last two terms vanish).  Same mathematics as the reference's
+  /// dual-number evaluation of operator() above, to rounding.
+  template <int WRT>
+  static constexpr bool has_flux_tangent = (WRT == 0);
+
+  template <typename X, typename State, int dim, typename Sink, typename Displacement, typename Acceleration>
+  SERAC_HOST_DEVICE void flux_tangent(std::integral_constant<int, 0>, double, const X&, State& state,
+                                      const ParentMap<dim>& map, tensor<double, dim>& source,
+                                      tensor<double, dim, dim>& flux, Sink&& sink, const Displacement& displacement,
+                                      const Acceleration& acceleration) const
+  {
+    const tensor<double, dim, dim> H = get<DERIVATIVE>(displacement);
+    source                           = (material_.density * map.scale) * get<VALUE>(acceleration);
+
+    const bool  nonlinear = (geom_nonlin_ == GeometricNonlinearities::On);
+    const State state_old = state;
+    tensor<double, dim, dim> sigma{};
+    if constexpr (has_closed_form_tangent<Material>::value) {
+      sigma = material_(state, H);
+    }
+
+    tensor<double, dim, dim> A = map.M, Pp{};
+    double                   J = 1.0;
+    SB_UNROLL
+    for (int b = 0; b < dim; b++) {
+      // Cb[a][j][m] = d sigma[a][j] / d H[b][m]
+      tensor<double, dim, dim, dim> Cb{};
+      if constexpr (has_closed_form_tangent<Material>::value) {
+        material_.stress_tangent_row(state_old, H, sigma, b, Cb);
+      } else {
+        tensor<dual<dim>, dim, dim> Hd{};
+        SB_UNROLL
+        for (int i = 0; i < dim; i++) {
+          SB_UNROLL
+          for (int m = 0; m < dim; m++) {
+            Hd[i][m] = make_dual_constant<dim>(H[i][m]);
+            if (i == b) Hd[i][m].gradient[m] = 1.0;
+          }
+        }
+        State st = state_old;
+        auto  sd = material_(st, Hd);
+        SB_UNROLL
+        for (int a = 0; a < dim; a++) {
+          SB_UNROLL
+          for (int j = 0; j < dim; j++) {
+            if (b == 0) sigma[a][j] = get_value(sd[a][j]);
+            SB_UNROLL
+            for (int m = 0; m < dim; m++) Cb[a][j][m] = partial_of(sd[a][j], m);
+          }
+        }
+        if (b == 0) state = st;
+      }
+      if (b == 0) {
+        // Piola stress in parent coordinates (needs sigma, which the AD path only has after its first pass)
+        if (nonlinear) {
+          const auto F    = H + Identity<dim>();
+          const auto Finv = inv(F);
+          J               = det(F);
+          A               = dot(map.M, Finv);
+          Pp              = dot(sigma, transpose(A)) * J;   // J sigma Finv^T M^T
+        } else {
+          Pp = dot(sigma, transpose(map.M));
+        }
+        flux = map.scale * Pp;
+      }
+      const double sJ = map.scale * J;
+      SB_UNROLL
+      for (int a = 0; a < dim; a++) {
+        // T[j][l] = sum_m Cb[a][j][m] M[l][m]
+        tensor<double, dim, dim> T{};
+        SB_UNROLL
+        for (int j = 0; j < dim; j++) {
+          SB_UNROLL
+          for (int l = 0; l < dim; l++) {
+            double t = Cb[a][j][0] * map.M[l][0];
+            SB_UNROLL
+            for (int m = 1; m < dim; m++) t += Cb[a][j][m] * map.M[l][m];
+            T[j][l] = t;
+          }
+        }
+        SB_UNROLL
+        for (int k = 0; k < dim; k++) {
+          SB_UNROLL
+          for (int l = 0; l < dim; l++) {
+            double d = A[k][0] * T[0][l];
+            SB_UNROLL
+            for (int j = 1; j < dim; j++) d += A[k][j] * T[j][l];
+            d *= sJ;
+            if (nonlinear) d += map.scale * (Pp[a][k] * A[l][b] - A[k][b] * Pp[a][l]);
+            sink(a, k, b, l, d);
+          }
+        }
+      }
+    }
+  }
 };
 
 /// q-function HeatTransfer::setMaterial registers (heat_transfer.hpp:381-405)
@@ -335,6 +517,25 @@ struct ShapeAwareIntegrandWrapperWithState {
     auto unmodified =
         integrand_(time, x_mod, state, shape_correction.modify_trial_argument(trial_spaces{}, qfunc_args)...);
     return shape_correction.modify_shape_aware_qf_return(test_space{}, unmodified);
+  }
+
+  /// tangent fast path: argument i + 1 of the wrapper is argument i of the integrand; the shape correction only
+  /// post-multiplies the linear maps (du/dx' = du/dX inv(J_p), flux -> flux inv(J_p)^T det J_p)
+  template <int WRT>
+  static constexpr bool has_flux_tangent = (WRT >= 1) && provides_flux_tangent<Integrand, WRT - 1>::value;
+
+  template <int WRT, typename PositionType, typename StateType, typename Source, typename Flux, typename Sink,
+            typename ShapeValueType, typename... QFuncArgs>
+  SERAC_HOST_DEVICE void flux_tangent(std::integral_constant<int, WRT>, double time, const PositionType& x,
+                                      StateType& state, const ParentMap<dim>& map, Source& source, Flux& flux,
+                                      Sink&& sink, const ShapeValueType& shape_val, const QFuncArgs&... qfunc_args) const
+  {
+    detail::ShapeCorrection<dim, ShapeValueType> shape_correction(Dimension<dim>{}, shape_val);
+    ParentMap<dim> inner{dot(map.M, shape_correction.inv_J_), map.scale * shape_correction.detJ_};
+    auto x_mod = serac::tuple{get<VALUE>(x) + get<VALUE>(shape_val),
+                              get<DERIVATIVE>(x) + get<DERIVATIVE>(shape_val) * get<DERIVATIVE>(x)};
+    integrand_.flux_tangent(std::integral_constant<int, WRT - 1>{}, time, x_mod, state, inner, source, flux, sink,
+                            shape_correction.modify_trial_argument(trial_spaces{}, qfunc_args)...);
   }
 };
 

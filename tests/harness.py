@@ -42,7 +42,7 @@ def make_inputs(seed, vsize, shape_vsize, shape_amp=0.0, u_amp=0.01):
 class Product:
     """The product objects for one parity problem (same signature as oracle.make_golden.reference_problem)."""
 
-    def __init__(self, prob, device):
+    def __init__(self, prob, device, name_suffix=""):
         import torch
         from serac_b200 import capi
         self.capi, self.torch, self.prob, self.dev = capi, torch, prob, device
@@ -61,7 +61,7 @@ class Product:
         self.t = t
         self.nodes = t(prob["mesh_nodes"])
         self.X_q, self.J_q = capi.geometric_factors(geom, int(prob["mesh_order"]), p + 1, self.G_mesh, self.nodes)
-        name = f"{prob['kind']}_{KIND_TO_NAME[geom]}_p{p}"
+        name = f"{prob['kind']}_{KIND_TO_NAME[geom]}_p{p}{name_suffix}"
         self.integral = capi.Integral(name, prob["params"], self.X_q, self.J_q, int(prob["ne"]))
         if "U" not in prob:  # full-size fixtures regenerate the inputs from the seed (oracle/make_golden.py)
             prob.update(make_inputs(int(prob["seed"]), self.G.LSize(), self.G_shape.LSize(), u_amp=float(prob["u_amp"])))

@@ -106,6 +106,22 @@ def test_element_gradient_and_assembly(case):
     assert rel_l2(A @ prob["dU"], prob["dr"]) < TOL
 
 
+def test_tangent_fast_path_matches_dual_number_path(cuda):
+    """The closed-form flux tangent (MaterialStressFunctor::flux_tangent) against the same integrand differentiated with
+    dual numbers end to end (the reference's scheme, registered as *_ad): stored derivatives, residual, JVP."""
+    prob = load_golden("solid_neohookean_hex_p2_patch")
+    fast, ad = Product(prob, cuda), Product(prob, cuda, name_suffix="_ad")
+    assert fast.integral.derivative_mask(1) == ad.integral.derivative_mask(1) == 8
+    r_f = fast.F(0.0, [fast.S, fast.U, fast.A], wrt=1).cpu().numpy()
+    r_a = ad.F(0.0, [ad.S, ad.U, ad.A], wrt=1).cpu().numpy()
+    assert rel_l2(r_f, r_a) < 1e-14 and rel_l2(r_a, prob["r"]) < TOL
+    D_f = fast.integral.export_derivatives(1).cpu().numpy()
+    D_a = ad.integral.export_derivatives(1).cpu().numpy()
+    assert rel_l2(D_f, D_a) < 1e-13
+    assert rel_l2(ad.F.GradientMult(1, ad.dU).cpu().numpy(), prob["dr"]) < TOL
+    assert rel_l2(fast.F.GradientMult(1, fast.dU).cpu().numpy(), prob["dr"]) < TOL
+
+
 def test_config_a_full_size(cuda):
     """BASELINE.json configs[1] at full size (32 768 hexes, 839 619 vdofs): sampled reference residual / Jacobian action,
     plus size-independent properties: linearity of the Jacobian action and JVP == directional finite difference."""
