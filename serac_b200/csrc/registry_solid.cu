@@ -38,7 +38,7 @@ static Registrar r_lin({"solid_linear_isotropic_" SB_STR(SB_REG_TAG),
 // the same integrand differentiated with dual numbers end to end (the reference's scheme; what an arbitrary user functor
 // gets): kept to cross-check the tangent fast path
 static Registrar r_neo_ad({"solid_neohookean_" SB_STR(SB_REG_TAG) "_ad",
-                           make_kernel_table<S::type, S::qf<NeoHookean>, NeoHookean::State, 1, 1, false>(),
+                           make_kernel_table<S::type, S::qf<NeoHookean>, NeoHookean::State, 1, 0, false>(),
                            &make_solid<S, NeoHookean>, "{density, K, G, geometric_nonlinearity(0|1)}"});
 #endif
 

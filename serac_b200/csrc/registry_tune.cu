@@ -36,15 +36,10 @@ TUNE(4, 1, 2)
 TUNE(4, 1, 3)
 TUNE(4, 1, 4)
 #elif TUNE_SET == 1
-TUNE(4, 3, 1)
-TUNE(4, 3, 2)
 TUNE(8, 1, 1)
 TUNE(8, 1, 2)
-#elif TUNE_SET == 2
-TUNE(8, 3, 1)
-TUNE(2, 1, 4)
+TUNE(2, 1, 6)
 TUNE(2, 1, 8)
-TUNE(2, 3, 4)
 #endif
 }  // namespace
 }  // namespace sb

@@ -434,6 +434,16 @@ struct SignatureT {
   static constexpr int test_n    = test::order + 1;
   static constexpr int test_c    = test::components;
   static constexpr int test_ndof = ipow(test_n, dim);
+  static constexpr int trial_n(int i)
+  {
+    constexpr int v[] = {(trials::order + 1)..., 0};
+    return v[i];
+  }
+  static constexpr int trial_c(int i)
+  {
+    constexpr int v[] = {trials::components..., 0};
+    return v[i];
+  }
 
   static_assert(((trials::order + 1 <= Q) && ...), "quadrature rule must have at least p + 1 points per direction");
   static_assert(test::order + 1 <= Q, "quadrature rule must have at least p + 1 points per direction");
@@ -443,29 +453,187 @@ struct SignatureT {
 template <Geometry geom, int Q, typename test, typename... trials>
 using Signature = SignatureT<geom, Q, 0, test, trials...>;
 
-template <typename Sig, int... I>
-constexpr int max_interp_scratch(std::integer_sequence<int, I...>)
-{
-  int m = 0;
-  ((m = cmax(m, TensorProduct<Sig::dim, Sig::template trial_space<I>::order + 1, Sig::q,
-                              Sig::template trial_space<I>::components>::interp_scratch)),
-   ...);
-  return m;
-}
-
+/// shared-memory plan of the evaluation kernel (doubles):
+///   [tables: (NT + 1) x 2 x MAX_Q^2][gathered dofs of every trial field: EPB x c x ndof each][work: EPB x W]
+/// The interpolation work areas of the trial fields are disjoint (all fields advance stage by stage together, two
+/// barriers in total); the integration scratch of the test space reuses the same work area afterwards.
 template <typename Sig>
-constexpr int eval_scratch_per_element()
-{
-  return cmax(max_interp_scratch<Sig>(std::make_integer_sequence<int, Sig::NT>{}),
-              TensorProduct<Sig::dim, Sig::test_n, Sig::q, Sig::test_c>::integ_scratch);
-}
+struct EvalLayout {
+  static constexpr int dim = Sig::dim, q = Sig::q, NT = Sig::NT, EPB = Sig::EPB;
+  static constexpr int tables = (NT + 1) * 2 * MAX_Q * MAX_Q;
+  static constexpr int ndof(int i) { return ipow(Sig::trial_n(i), dim); }
+  static constexpr int gather_size(int i) { return EPB * Sig::trial_c(i) * ndof(i); }
+  static constexpr int gather_off(int i)
+  {
+    int o = 0;
+    for (int j = 0; j < i; j++) o += gather_size(j);
+    return o;
+  }
+  /// per-element interpolation work of field i: A1 (+ A2 in 3D)
+  static constexpr int work_size(int i)
+  {
+    const int n = Sig::trial_n(i), c = Sig::trial_c(i);
+    return (dim == 3) ? 2 * c * n * n * q + 3 * c * n * q * q : 2 * c * n * q;
+  }
+  static constexpr int work_off(int i)
+  {
+    int o = 0;
+    for (int j = 0; j < i; j++) o += work_size(j);
+    return o;
+  }
+  static constexpr int W = cmax(work_off(NT), TensorProduct<dim, Sig::test_n, q, Sig::test_c>::integ_scratch);
+  static constexpr int gather_total = gather_off(NT);
+  static constexpr int total        = tables + gather_total + EPB * W;
+};
 
-/// smem layout: [tables: (NT + 1) x 2 x MAX_Q*MAX_Q] [EPB x scratch]
 template <typename Sig>
 constexpr int eval_smem_doubles()
 {
-  return (Sig::NT + 1) * 2 * MAX_Q * MAX_Q + Sig::EPB * eval_scratch_per_element<Sig>();
+  return EvalLayout<Sig>::total;
 }
+
+/// the sum-factorised interpolation of one field split into its stages, 1-D table rows hoisted into registers per
+/// stage (same staging and summation order as TensorProduct<>::interpolate)
+template <int dim, int n, int q, int c>
+struct InterpStages;
+
+template <int n, int q, int c>
+struct InterpStages<3, n, q, c> {
+  static __device__ __forceinline__ void s1(const double* __restrict__ B, const double* __restrict__ G,
+                                            const double* __restrict__ u, double* __restrict__ A1, int qx, int qy, int qz)
+  {
+    if (qz < n && qy < n) {
+      double b[n], g[n];
+      SB_UNROLL
+      for (int d = 0; d < n; d++) {
+        b[d] = B[qx * n + d];
+        g[d] = G[qx * n + d];
+      }
+      SB_UNROLL
+      for (int a = 0; a < c; a++) {
+        double sB = 0.0, sG = 0.0;
+        SB_UNROLL
+        for (int dx = 0; dx < n; dx++) {
+          const double uu = u[((a * n + qz) * n + qy) * n + dx];
+          sB += b[dx] * uu;
+          sG += g[dx] * uu;
+        }
+        A1[(((0 * c + a) * n + qz) * n + qy) * q + qx] = sB;
+        A1[(((1 * c + a) * n + qz) * n + qy) * q + qx] = sG;
+      }
+    }
+  }
+  static __device__ __forceinline__ void s2(const double* __restrict__ B, const double* __restrict__ G,
+                                            const double* __restrict__ A1, double* __restrict__ A2, int qx, int qy, int qz)
+  {
+    if (qz < n) {
+      double b[n], g[n];
+      SB_UNROLL
+      for (int d = 0; d < n; d++) {
+        b[d] = B[qy * n + d];
+        g[d] = G[qy * n + d];
+      }
+      SB_UNROLL
+      for (int a = 0; a < c; a++) {
+        double sBB = 0.0, sGB = 0.0, sBG = 0.0;
+        SB_UNROLL
+        for (int dy = 0; dy < n; dy++) {
+          const double vb = A1[(((0 * c + a) * n + qz) * n + dy) * q + qx];
+          const double vg = A1[(((1 * c + a) * n + qz) * n + dy) * q + qx];
+          sBB += b[dy] * vb;
+          sGB += b[dy] * vg;
+          sBG += g[dy] * vb;
+        }
+        A2[(((0 * c + a) * n + qz) * q + qy) * q + qx] = sBB;
+        A2[(((1 * c + a) * n + qz) * q + qy) * q + qx] = sGB;
+        A2[(((2 * c + a) * n + qz) * q + qy) * q + qx] = sBG;
+      }
+    }
+  }
+  static __device__ __forceinline__ void s3(const double* __restrict__ B, const double* __restrict__ G,
+                                            const double* __restrict__ A2, int qx, int qy, int qz, double (&val)[c],
+                                            double (&grad)[c][3])
+  {
+    double b[n], g[n];
+    SB_UNROLL
+    for (int d = 0; d < n; d++) {
+      b[d] = B[qz * n + d];
+      g[d] = G[qz * n + d];
+    }
+    SB_UNROLL
+    for (int a = 0; a < c; a++) {
+      double v = 0.0, gx = 0.0, gy = 0.0, gz = 0.0;
+      SB_UNROLL
+      for (int dz = 0; dz < n; dz++) {
+        const double bb = A2[(((0 * c + a) * n + dz) * q + qy) * q + qx];
+        const double gb = A2[(((1 * c + a) * n + dz) * q + qy) * q + qx];
+        const double bg = A2[(((2 * c + a) * n + dz) * q + qy) * q + qx];
+        v += b[dz] * bb;
+        gx += b[dz] * gb;
+        gy += b[dz] * bg;
+        gz += g[dz] * bb;
+      }
+      val[a]     = v;
+      grad[a][0] = gx;
+      grad[a][1] = gy;
+      grad[a][2] = gz;
+    }
+  }
+};
+
+template <int n, int q, int c>
+struct InterpStages<2, n, q, c> {
+  static __device__ __forceinline__ void s1(const double* __restrict__ B, const double* __restrict__ G,
+                                            const double* __restrict__ u, double* __restrict__ A1, int qx, int qy, int)
+  {
+    if (qy < n) {
+      double b[n], g[n];
+      SB_UNROLL
+      for (int d = 0; d < n; d++) {
+        b[d] = B[qx * n + d];
+        g[d] = G[qx * n + d];
+      }
+      SB_UNROLL
+      for (int a = 0; a < c; a++) {
+        double sB = 0.0, sG = 0.0;
+        SB_UNROLL
+        for (int dx = 0; dx < n; dx++) {
+          const double uu = u[(a * n + qy) * n + dx];
+          sB += b[dx] * uu;
+          sG += g[dx] * uu;
+        }
+        A1[((0 * c + a) * n + qy) * q + qx] = sB;
+        A1[((1 * c + a) * n + qy) * q + qx] = sG;
+      }
+    }
+  }
+  /// final stage in 2D
+  static __device__ __forceinline__ void s2(const double* __restrict__ B, const double* __restrict__ G,
+                                            const double* __restrict__ A1, int qx, int qy, int, double (&val)[c],
+                                            double (&grad)[c][2])
+  {
+    double b[n], g[n];
+    SB_UNROLL
+    for (int d = 0; d < n; d++) {
+      b[d] = B[qy * n + d];
+      g[d] = G[qy * n + d];
+    }
+    SB_UNROLL
+    for (int a = 0; a < c; a++) {
+      double v = 0.0, gx = 0.0, gy = 0.0;
+      SB_UNROLL
+      for (int dy = 0; dy < n; dy++) {
+        const double vb = A1[((0 * c + a) * n + dy) * q + qx];
+        v += b[dy] * vb;
+        gx += b[dy] * A1[((1 * c + a) * n + dy) * q + qx];
+        gy += g[dy] * vb;
+      }
+      val[a]     = v;
+      grad[a][0] = gx;
+      grad[a][1] = gy;
+    }
+  }
+};
 
 // ------------------------------------------------------------------------------------------------
 // layout of the stored derivative d(source, flux)/d(value, grad) w.r.t. one trial argument.
@@ -625,54 +793,6 @@ SB_HD auto flux_component(const F& f, int a, int j)
 // ------------------------------------------------------------------------------------------------
 // evaluation kernel.  WRT < 0: plain residual.  WRT >= 0: residual + derivative store w.r.t. trial WRT.
 // ------------------------------------------------------------------------------------------------
-template <typename Sig, int I>
-__device__ __forceinline__ void load_and_interpolate(const EvalParams<Sig::NT>& P, const double* tables, double* scratch,
-                                                     int el, int elem, int qx, int qy, int qz,
-                                                     typename qf_arg<typename Sig::template trial_space<I>, Sig::dim>::type& arg,
-                                                     const tensor<double, Sig::dim, Sig::dim>& invJ)
-{
-  using space       = typename Sig::template trial_space<I>;
-  constexpr int dim = Sig::dim;
-  constexpr int n   = space::order + 1;
-  constexpr int c   = space::components;
-  using TP          = TensorProduct<dim, n, Sig::q, c>;
-  constexpr int per = eval_scratch_per_element<Sig>();
-
-  __syncthreads();  // scratch reuse
-  // cooperative gather: EPB elements x c x ndof values
-  const FieldArg& f = P.trial[I];
-  for (int i = threadIdx.x; i < Sig::EPB * c * TP::ndof; i += Sig::threads) {
-    const int le   = i / (c * TP::ndof);
-    const int rem  = i - le * (c * TP::ndof);
-    const int a    = rem / TP::ndof;
-    const int node = rem - a * TP::ndof;
-    int       e    = blockIdx.x * Sig::EPB + le;
-    if (e >= P.num_elements) e = P.num_elements - 1;
-    const int       ge  = P.elements ? P.elements[e] : e;
-    const long long idx = (long long)f.table[(long long)ge * TP::ndof + node];
-    scratch[le * per + a * TP::ndof + node] = f.L[idx * f.node_stride + a * f.comp_stride];
-  }
-  __syncthreads();
-  const double* B = tables + (I * 2 + 0) * MAX_Q * MAX_Q;
-  const double* G = tables + (I * 2 + 1) * MAX_Q * MAX_Q;
-  double        val[c];
-  double        grad[c][dim];
-  TP::template interpolate<true, true>(B, G, scratch + el * per, qx, qy, qz, val, grad);
-  (void)elem;
-  // parent -> physical: grad <- grad . inv(J)    (finite_element.hpp:262-264)
-  SB_UNROLL
-  for (int a = 0; a < c; a++) {
-    vcomp(get<0>(arg), a) = val[a];
-    SB_UNROLL
-    for (int j = 0; j < dim; j++) {
-      double sum = 0.0;
-      SB_UNROLL
-      for (int k = 0; k < dim; k++) sum += grad[a][k] * invJ(k, j);
-      gcomp(get<1>(arg), a, j) = sum;
-    }
-  }
-}
-
 /// build the seeded version of argument `arg` for a derivative pass
 template <typename Space, int dim, int PASS, int ROWS>
 __device__ __forceinline__ auto seed_argument(const typename qf_arg<Space, dim>::type& arg,
@@ -744,14 +864,16 @@ __global__ void __launch_bounds__(Sig::threads, MINB) evaluation_kernel(const __
   constexpr int QPE = Sig::QPE;
   constexpr int EPB = Sig::EPB;
   constexpr int ct  = Sig::test_c;
-  constexpr int per = eval_scratch_per_element<Sig>();
+  using LAY         = EvalLayout<Sig>;
+  constexpr int per = LAY::W;
   using seq         = std::make_integer_sequence<int, NT>;
 
   extern __shared__ double smem[];
   double* tables  = smem;
-  double* scratch = smem + (NT + 1) * 2 * MAX_Q * MAX_Q;
+  double* gathered = smem + LAY::tables;
+  double* scratch = gathered + LAY::gather_total;
 
-  for (int i = threadIdx.x; i < (NT + 1) * 2 * MAX_Q * MAX_Q; i += Sig::threads) {
+  for (int i = threadIdx.x; i < LAY::tables; i += Sig::threads) {
     const int           which = i / (2 * MAX_Q * MAX_Q);
     const int           rem   = i - which * (2 * MAX_Q * MAX_Q);
     const BasisTable1D& bt    = (which < NT) ? P.trial_basis[which < NT ? which : 0] : P.test_basis;
@@ -769,7 +891,7 @@ __global__ void __launch_bounds__(Sig::threads, MINB) evaluation_kernel(const __
   const int  e     = valid ? e_raw : P.num_elements - 1;
   const int  elem  = P.elements ? P.elements[e] : e;
 
-  // geometric factors of this quadrature point:  Jm(i,j) = dX_i/dxi_j = J_q[e](j,i,q)
+  // geometric factors of this quadrature point:  Jm(i,j) = dX_i/dxi_j = J_q[e](j,i,q)   (loads issued first)
   tensor<double, dim>      x{};
   tensor<double, dim, dim> Jm{};
   SB_UNROLL
@@ -778,13 +900,138 @@ __global__ void __launch_bounds__(Sig::threads, MINB) evaluation_kernel(const __
     SB_UNROLL
     for (int j = 0; j < dim; j++) Jm(i, j) = P.J_q[(((long long)e * dim + j) * dim + i) * QPE + ql];
   }
+
+  // --- L -> E gather of every trial field at once (element_restriction.cpp:443-454): all loads are issued before the
+  //     first one is consumed, so the table -> L latency is paid once per CTA, not once per field ---
+  {
+    constexpr int NGMAX = [] {
+      int m = 1;
+      for (int i = 0; i < NT; i++) m = cmax(m, (LAY::gather_size(i) + Sig::threads - 1) / Sig::threads);
+      return m;
+    }();
+    double gv[NT > 0 ? NT : 1][NGMAX];
+    auto   load_field = [&](auto idx) {
+      constexpr int   I    = decltype(idx)::value;
+      constexpr int   c    = Sig::trial_c(I);
+      constexpr int   nd   = LAY::ndof(I);
+      constexpr int   NG   = (LAY::gather_size(I) + Sig::threads - 1) / Sig::threads;
+      const FieldArg& f    = P.trial[I];
+      SB_UNROLL
+      for (int j = 0; j < NG; j++) {
+        const int i = threadIdx.x + j * Sig::threads;
+        constexpr int sz = LAY::gather_size(I);
+        if (i < sz) {
+          const int le   = i / (c * nd);
+          const int rem  = i - le * (c * nd);
+          const int a    = rem / nd;
+          const int node = rem - a * nd;
+          int       ee   = blockIdx.x * EPB + le;
+          if (ee >= P.num_elements) ee = P.num_elements - 1;
+          const int       ge  = P.elements ? P.elements[ee] : ee;
+          const long long idx = (long long)f.table[(long long)ge * nd + node];
+          gv[I][j]            = f.L[idx * f.node_stride + a * f.comp_stride];
+        }
+      }
+    };
+    auto store_field = [&](auto idx) {
+      constexpr int I  = decltype(idx)::value;
+      constexpr int NG = (LAY::gather_size(I) + Sig::threads - 1) / Sig::threads;
+      SB_UNROLL
+      for (int j = 0; j < NG; j++) {
+        const int i = threadIdx.x + j * Sig::threads;
+        constexpr int off = LAY::gather_off(I), sz = LAY::gather_size(I);
+        if (i < sz) gathered[off + i] = gv[I][j];
+      }
+    };
+    [&]<int... I>(std::integer_sequence<int, I...>) { (load_field(std::integral_constant<int, I>{}), ...); }
+    (seq{});
+    [&]<int... I>(std::integer_sequence<int, I...>) { (store_field(std::integral_constant<int, I>{}), ...); }
+    (seq{});
+  }
   const auto   invJ = inv(Jm);
   const double dv   = det(Jm);
+  __syncthreads();
 
+  // --- interpolate every trial field, stage by stage (hexahedron_H1.inl:169-228), then parent -> physical
+  //     (finite_element.hpp:262-264) ---
   auto inputs = [&]<int... I>(std::integer_sequence<int, I...>)
   {
     tuple<typename qf_arg<typename Sig::template trial_space<I>, dim>::type...> in{};
-    (load_and_interpolate<Sig, I>(P, tables, scratch, el, elem, qx, qy, qz, get<I>(in), invJ), ...);
+    auto u_of  = [&](auto idx) {
+      constexpr int J = decltype(idx)::value;
+      constexpr int off = LAY::gather_off(J), sz = Sig::trial_c(J) * LAY::ndof(J);
+      return gathered + off + el * sz;
+    };
+    auto w_of = [&](auto idx) {
+      constexpr int off = LAY::work_off(decltype(idx)::value);
+      return scratch + el * per + off;
+    };
+    auto B_of = [&](auto idx) { return tables + (decltype(idx)::value * 2 + 0) * MAX_Q * MAX_Q; };
+    auto G_of = [&](auto idx) { return tables + (decltype(idx)::value * 2 + 1) * MAX_Q * MAX_Q; };
+    // parent -> physical: grad <- grad . inv(J)
+    auto finish = [&](auto idx, const auto& val, const auto& grad) {
+      constexpr int J = decltype(idx)::value;
+      constexpr int c = Sig::trial_c(J);
+      auto&         arg = get<J>(in);
+      SB_UNROLL
+      for (int a = 0; a < c; a++) {
+        vcomp(get<0>(arg), a) = val[a];
+        SB_UNROLL
+        for (int j = 0; j < dim; j++) {
+          double sum = 0.0;
+          SB_UNROLL
+          for (int k = 0; k < dim; k++) sum += grad[a][k] * invJ(k, j);
+          gcomp(get<1>(arg), a, j) = sum;
+        }
+      }
+    };
+    if constexpr (dim == 3) {
+      auto s1 = [&](auto idx) {
+        constexpr int J = decltype(idx)::value;
+        constexpr int n = Sig::trial_n(J), c = Sig::trial_c(J);
+        using ST        = InterpStages<3, n, q, c>;
+        ST::s1(B_of(idx), G_of(idx), u_of(idx), w_of(idx), qx, qy, qz);
+      };
+      auto s2 = [&](auto idx) {
+        constexpr int J = decltype(idx)::value;
+        constexpr int n = Sig::trial_n(J), c = Sig::trial_c(J);
+        using ST        = InterpStages<3, n, q, c>;
+        ST::s2(B_of(idx), G_of(idx), w_of(idx), w_of(idx) + 2 * c * n * n * q, qx, qy, qz);
+      };
+      auto s3 = [&](auto idx) {
+        constexpr int J = decltype(idx)::value;
+        constexpr int n = Sig::trial_n(J), c = Sig::trial_c(J);
+        using ST        = InterpStages<3, n, q, c>;
+        double val[c];
+        double grad[c][3];
+        ST::s3(B_of(idx), G_of(idx), w_of(idx) + 2 * c * n * n * q, qx, qy, qz, val, grad);
+        finish(idx, val, grad);
+      };
+      (s1(std::integral_constant<int, I>{}), ...);
+      __syncthreads();
+      (s2(std::integral_constant<int, I>{}), ...);
+      __syncthreads();
+      (s3(std::integral_constant<int, I>{}), ...);
+    } else {
+      auto s1 = [&](auto idx) {
+        constexpr int J = decltype(idx)::value;
+        constexpr int n = Sig::trial_n(J), c = Sig::trial_c(J);
+        using ST        = InterpStages<2, n, q, c>;
+        ST::s1(B_of(idx), G_of(idx), u_of(idx), w_of(idx), qx, qy, qz);
+      };
+      auto s2 = [&](auto idx) {
+        constexpr int J = decltype(idx)::value;
+        constexpr int n = Sig::trial_n(J), c = Sig::trial_c(J);
+        using ST        = InterpStages<2, n, q, c>;
+        double val[c];
+        double grad[c][2];
+        ST::s2(B_of(idx), G_of(idx), w_of(idx), qx, qy, qz, val, grad);
+        finish(idx, val, grad);
+      };
+      (s1(std::integral_constant<int, I>{}), ...);
+      __syncthreads();
+      (s2(std::integral_constant<int, I>{}), ...);
+    }
     return in;
   }
   (seq{});

@@ -35,6 +35,29 @@ inline int ensure_smem(K kernel, size_t bytes)
   return 0;
 }
 
+/// q-functions may expose run-time flags as compile-time variants (num_variants, variant<V>, variant_index(),
+/// as_variant<V>(): see MaterialStressFunctor); the launcher then picks the kernel specialised for the flag's value
+template <typename QF, typename = void>
+struct qf_variants {
+  static constexpr int n = 1;
+};
+template <typename QF>
+struct qf_variants<QF, std::void_t<decltype(QF::num_variants)>> {
+  static constexpr int n = QF::num_variants;
+};
+
+template <typename Sig, int WRT, typename QF, typename State, int ROWS, int MINB, bool FAST>
+int launch_evaluation_kernel(const EvalParams<Sig::NT>& P, const QF& qf, int num_elements, void* stream)
+{
+  auto         kernel = &evaluation_kernel<Sig, WRT, QF, State, ROWS, MINB, FAST>;
+  const size_t smem   = size_t(eval_smem_doubles<Sig>()) * sizeof(double);
+  if (int e = ensure_smem(kernel, smem)) return e;
+  const int grid = (num_elements + Sig::EPB - 1) / Sig::EPB;
+  kernel<<<grid, Sig::threads, smem, cudaStream_t(stream)>>>(P, qf);
+  sb_count_launch();
+  return int(cudaGetLastError());
+}
+
 template <typename Sig, int WRT, typename QF, typename State, int ROWS = 1, int MINB = 1, bool FAST = true>
 int launch_evaluate(const sb_eval_args* a, const void* qf_blob, void* stream)
 {
@@ -57,15 +80,24 @@ int launch_evaluate(const sb_eval_args* a, const void* qf_blob, void* stream)
   P.update_state = a->update_state;
   P.t            = a->t;
   if (a->num_elements <= 0) return 0;
-  auto         kernel = &evaluation_kernel<Sig, WRT, QF, State, ROWS, MINB, FAST>;
-  const size_t smem   = size_t(eval_smem_doubles<Sig>()) * sizeof(double);
-  if (int e = ensure_smem(kernel, smem)) return e;
-  const int grid = (a->num_elements + Sig::EPB - 1) / Sig::EPB;
   alignas(16) unsigned char qf_storage[sizeof(QF)];
   std::memcpy(qf_storage, qf_blob, sizeof(QF));
-  kernel<<<grid, Sig::threads, smem, cudaStream_t(stream)>>>(P, *reinterpret_cast<const QF*>(qf_storage));
-  sb_count_launch();
-  return int(cudaGetLastError());
+  const QF& qf = *reinterpret_cast<const QF*>(qf_storage);
+  if constexpr (qf_variants<QF>::n > 1) {
+    int  err      = int(cudaErrorInvalidValue);
+    auto dispatch = [&]<int... V>(std::integer_sequence<int, V...>)
+    {
+      (((qf.variant_index() == V)
+            ? void(err = launch_evaluation_kernel<Sig, WRT, typename QF::template variant<V>, State, ROWS, MINB, FAST>(
+                       P, qf.template as_variant<V>(), a->num_elements, stream))
+            : void()),
+       ...);
+    };
+    dispatch(std::make_integer_sequence<int, qf_variants<QF>::n>{});
+    return err;
+  } else {
+    return launch_evaluation_kernel<Sig, WRT, QF, State, ROWS, MINB, FAST>(P, qf, a->num_elements, stream);
+  }
 }
 
 /// number of SMs of the current device (cached)
@@ -164,6 +196,14 @@ int launch_element_gradient(const sb_elem_grad_args* a, void* stream)
   }
 }
 
+/// 128 registers per thread: 65536 / 128 = 512 threads per SM
+template <typename Sig>
+constexpr int default_min_blocks()
+{
+  constexpr int t32 = ((Sig::threads + 31) / 32) * 32;
+  return (512 / t32) > 0 ? (512 / t32) : 1;
+}
+
 template <typename Sig, typename QF, typename State, int WRT, int ROWS_REQ, int MINB, bool FAST>
 void fill_wrt(sb_kernel_table& T)
 {
@@ -172,7 +212,10 @@ void fill_wrt(sb_kernel_table& T)
   constexpr int mask = (L.has[0] ? 1 : 0) | (L.has[1] ? 2 : 0) | (L.has[2] ? 4 : 0) | (L.has[3] ? 8 : 0);
   constexpr int ck   = Sig::template trial_space<WRT>::components;
   constexpr int ROWS = (ROWS_REQ > 0 && ck % ROWS_REQ == 0) ? ROWS_REQ : 1;
-  T.evaluate_ad[WRT]        = &launch_evaluate<Sig, WRT, QF, State, ROWS, MINB, FAST>;
+  // resident CTAs per SM asked of ptxas: kernels whose q-function differentiates itself fit 128 registers / thread
+  // (measured: 263 -> 178 us on config A); dual-number kernels already spill at 255 and are left alone
+  constexpr int MB = (MINB > 0) ? MINB : (DT::tangent ? default_min_blocks<Sig>() : 1);
+  T.evaluate_ad[WRT]        = &launch_evaluate<Sig, WRT, QF, State, ROWS, MB, FAST>;
   T.jvp[WRT]                = &launch_jvp<Sig, WRT, mask>;
   T.element_gradient[WRT]   = &launch_element_gradient<Sig, WRT, mask>;
   T.derivative_mask[WRT]    = mask;
@@ -183,7 +226,8 @@ void fill_wrt(sb_kernel_table& T)
 /// anything else: trivially copyable per-quadrature-point struct
 /// ROWS_REQ: gradient rows per derivative pass (1 = least registers, ck = one pass); MINB: min resident CTAs per SM
 /// FAST: let q-functions that provide a flux tangent use it (false = dual numbers everywhere, the reference's scheme)
-template <typename Sig, typename QF, typename State, int ROWS_REQ = 1, int MINB = 1, bool FAST = true>
+/// MINB: __launch_bounds__ min resident CTAs per SM (0 = choose: default_min_blocks for plain / tangent kernels)
+template <typename Sig, typename QF, typename State, int ROWS_REQ = 1, int MINB = 0, bool FAST = true>
 sb_kernel_table make_kernel_table()
 {
   static_assert(std::is_trivially_copyable_v<QF>, "q-function functors are copied by value into kernel parameters");
@@ -204,7 +248,7 @@ sb_kernel_table make_kernel_table()
   T.qf_bytes           = sizeof(QF);
   T.state_bytes        = (std::is_same_v<State, Nothing> || std::is_empty_v<State>) ? 0 : sizeof(State);
   T.elements_per_block = Sig::EPB;
-  T.evaluate           = &launch_evaluate<Sig, -1, QF, State>;
+  T.evaluate           = &launch_evaluate<Sig, -1, QF, State, 1, (MINB > 0 ? MINB : default_min_blocks<Sig>()), FAST>;
   return T;
 }
 

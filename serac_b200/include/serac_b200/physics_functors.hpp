@@ -138,6 +138,15 @@ struct NeoHookean {
     auto J         = J_minus_1 + 1;
     return (lambda * log1p(J_minus_1) * I + G * B_minus_I) / J;
   }
+  /// first Piola stress P = lambda log J F^-T + G (F - F^-T):
+  ///   dP[a][i]/dF[b][m] = lambda Finv[i][a] Finv[m][b] + (G - lambda log J) Finv[i][b] Finv[m][a] + G d_ab d_im
+  static constexpr bool closed_form_piola_tangent = true;
+  template <int dim>
+  SERAC_HOST_DEVICE tensor<double, 3> piola_tangent_coefficients(const State&, const tensor<double, dim, dim>& du_dX) const
+  {
+    const double lambda = K - (2.0 / 3.0) * G;
+    return tensor<double, 3>{{lambda, G - lambda * log1p(detApIm1(du_dX)), G}};
+  }
   /// closed-form d sigma / d du_dX, row b.  With F = I + H, B = F F^T, J = det F:
   ///   d sigma[a][j] / d H[b][m] = ( lambda d_aj Finv[m][b] + G (d_ab F[j][m] + F[a][m] d_jb) ) / J - sigma[a][j] Finv[m][b]
   static constexpr bool closed_form_tangent = true;
@@ -290,8 +299,28 @@ struct LinearIsotropicConductor {
 
 }  // namespace heat_transfer
 
+/// does material M provide piola_tangent_coefficients(state, du_dX) -> {c1, c2, c3} with
+///   d P[a][i] / d F[b][m] = c1 Finv[i][a] Finv[m][b] + c2 Finv[i][b] Finv[m][a] + c3 d_ab d_im      (P = J sigma F^-T) ?
+template <typename M, typename = void>
+struct has_piola_tangent_coefficients : std::false_type {
+};
+template <typename M>
+struct has_piola_tangent_coefficients<M, std::void_t<decltype(M::closed_form_piola_tangent)>>
+    : std::bool_constant<M::closed_form_piola_tangent> {
+};
+
+/// how MaterialStressFunctor knows its geometric-nonlinearity flag: at run time (the reference's member), or fixed at
+/// compile time (the kernel launcher converts a Dynamic functor into the matching static variant before the launch, so
+/// the device code carries no dead branch and its register allocation is that of the live one)
+enum class FlagMode
+{
+  Dynamic,
+  StaticOff,
+  StaticOn
+};
+
 /// q-function SolidMechanics::setMaterial registers (solid_mechanics.hpp:808-853)
-template <typename Material>
+template <typename Material, FlagMode MODE = FlagMode::Dynamic>
 struct MaterialStressFunctor {
   SERAC_HOST_DEVICE MaterialStressFunctor(Material material, GeometricNonlinearities gn)
       : material_(material), geom_nonlin_(gn)
@@ -299,6 +328,24 @@ struct MaterialStressFunctor {
   }
   Material                material_;
   GeometricNonlinearities geom_nonlin_;
+
+  // --- run-time flag -> compile-time variant (see FlagMode) ---
+  static constexpr int num_variants = (MODE == FlagMode::Dynamic) ? 2 : 1;
+  template <int V>
+  using variant = MaterialStressFunctor<Material, V == 0 ? FlagMode::StaticOff : FlagMode::StaticOn>;
+  int variant_index() const { return geom_nonlin_ == GeometricNonlinearities::On ? 1 : 0; }
+  template <int V>
+  variant<V> as_variant() const
+  {
+    return variant<V>(material_, geom_nonlin_);
+  }
+
+  SERAC_HOST_DEVICE bool nonlinear() const
+  {
+    if constexpr (MODE == FlagMode::StaticOn) return true;
+    if constexpr (MODE == FlagMode::StaticOff) return false;
+    return geom_nonlin_ == GeometricNonlinearities::On;
+  }
 
   template <typename X, typename State, typename Displacement, typename Acceleration, typename... Params>
   SERAC_HOST_DEVICE auto operator()(double, X, State& state, Displacement displacement, Acceleration acceleration,
@@ -311,7 +358,7 @@ struct MaterialStressFunctor {
 
     constexpr int dim = std::decay_t<decltype(du_dX)>::first_dim;
     auto          dx_dX = 0.0 * du_dX + Identity<dim>();
-    if (geom_nonlin_ == GeometricNonlinearities::On) {
+    if (nonlinear()) {
       dx_dX = dx_dX + du_dX;
     }
     auto flux = dot(stress, transpose(inv(dx_dX))) * det(dx_dX);
@@ -322,10 +369,12 @@ struct MaterialStressFunctor {
   /// through du_dX, so instead of pushing dual numbers through the Cauchy -> Piola transform and the surrounding linear
   /// maps, differentiate the material alone (closed form when the material has one, else forward-mode AD one gradient
   /// row at a time) and apply everything else analytically.  With F = I + H, P = J sigma F^-T, A = M F^-1, Pp = P M^T:
-  ///   parent flux                          = scale Pp
+  ///   parent flux                               = scale Pp
   ///   d(parent flux)[a][k]/d(parent grad)[b][l] = scale ( J sum_jm A[k][j] M[l][m] C[a][j][b][m] - A[k][b] Pp[a][l] + Pp[a][k] A[l][b] )
-  /// (geometric nonlinearity off: P = sigma, A = M and the last two terms vanish).  Same mathematics as the reference's
-  /// dual-number evaluation of operator() above, to rounding.
+  /// (geometric nonlinearity off: P = sigma, A = M and the last two terms vanish).  Materials that know their first
+  /// Piola tangent as c1 F^-T (x) F^-T + c2 F^-T [x] F^-T + c3 I [x] I shortcut further:
+  ///   d(parent flux)[a][k]/d(parent grad)[b][l] = scale ( c1 A[k][a] A[l][b] + c2 A[k][b] A[l][a] + c3 d_ab (M M^T)[k][l] )
+  /// Same mathematics as the reference's dual-number evaluation of operator() above, to rounding.
   template <int WRT>
   static constexpr bool has_flux_tangent = (WRT == 0);
 
@@ -337,16 +386,62 @@ struct MaterialStressFunctor {
   {
     const tensor<double, dim, dim> H = get<DERIVATIVE>(displacement);
     source                           = (material_.density * map.scale) * get<VALUE>(acceleration);
+    const tensor<double, dim, dim>& M = map.M;
 
-    const bool  nonlinear = (geom_nonlin_ == GeometricNonlinearities::On);
+    if constexpr (has_piola_tangent_coefficients<Material>::value) {
+      if (nonlinear()) {
+        const auto   c     = material_.piola_tangent_coefficients(state, H);
+        const auto   sigma = material_(state, H);
+        const auto   F     = H + Identity<dim>();
+        const auto   A     = dot(M, inv(F));
+        flux               = dot(sigma, transpose(A)) * (det(F) * map.scale);
+        const double c1 = c[0] * map.scale, c2 = c[1] * map.scale, c3 = c[2] * map.scale;
+        tensor<double, dim, dim> Q{};  // c3 M M^T (symmetric)
+        SB_UNROLL
+        for (int k = 0; k < dim; k++) {
+          SB_UNROLL
+          for (int l = k; l < dim; l++) {
+            double t = M[k][0] * M[l][0];
+            SB_UNROLL
+            for (int m = 1; m < dim; m++) t += M[k][m] * M[l][m];
+            Q[k][l] = Q[l][k] = c3 * t;
+          }
+        }
+        SB_UNROLL
+        for (int a = 0; a < dim; a++) {
+          SB_UNROLL
+          for (int k = 0; k < dim; k++) {
+            const double c1Aka = c1 * A[k][a];
+            SB_UNROLL
+            for (int b = 0; b < dim; b++) {
+              const double c2Akb = c2 * A[k][b];
+              SB_UNROLL
+              for (int l = 0; l < dim; l++) {
+                double d = c1Aka * A[l][b] + c2Akb * A[l][a];
+                if (a == b) d += Q[k][l];
+                sink(a, k, b, l, d);
+              }
+            }
+          }
+        }
+        return;
+      }
+    }
+
+    const bool  nonlin    = nonlinear();
     const State state_old = state;
     tensor<double, dim, dim> sigma{};
     if constexpr (has_closed_form_tangent<Material>::value) {
       sigma = material_(state, H);
     }
 
-    tensor<double, dim, dim> A = map.M, Pp{};
-    double                   J = 1.0;
+    // A = M Finv, As = scale J A, sPp = scale Pp = sigma As^T
+    tensor<double, dim, dim> A = M, As = map.scale * M, sPp{};
+    if (nonlin) {
+      const auto F = H + Identity<dim>();
+      A            = dot(M, inv(F));
+      As           = (det(F) * map.scale) * A;
+    }
     SB_UNROLL
     for (int b = 0; b < dim; b++) {
       // Cb[a][j][m] = d sigma[a][j] / d H[b][m]
@@ -377,19 +472,9 @@ struct MaterialStressFunctor {
         if (b == 0) state = st;
       }
       if (b == 0) {
-        // Piola stress in parent coordinates (needs sigma, which the AD path only has after its first pass)
-        if (nonlinear) {
-          const auto F    = H + Identity<dim>();
-          const auto Finv = inv(F);
-          J               = det(F);
-          A               = dot(map.M, Finv);
-          Pp              = dot(sigma, transpose(A)) * J;   // J sigma Finv^T M^T
-        } else {
-          Pp = dot(sigma, transpose(map.M));
-        }
-        flux = map.scale * Pp;
+        sPp  = dot(sigma, transpose(As));  // (the AD path only has sigma after its first pass)
+        flux = sPp;
       }
-      const double sJ = map.scale * J;
       SB_UNROLL
       for (int a = 0; a < dim; a++) {
         // T[j][l] = sum_m Cb[a][j][m] M[l][m]
@@ -398,9 +483,9 @@ struct MaterialStressFunctor {
         for (int j = 0; j < dim; j++) {
           SB_UNROLL
           for (int l = 0; l < dim; l++) {
-            double t = Cb[a][j][0] * map.M[l][0];
+            double t = Cb[a][j][0] * M[l][0];
             SB_UNROLL
-            for (int m = 1; m < dim; m++) t += Cb[a][j][m] * map.M[l][m];
+            for (int m = 1; m < dim; m++) t += Cb[a][j][m] * M[l][m];
             T[j][l] = t;
           }
         }
@@ -408,11 +493,10 @@ struct MaterialStressFunctor {
         for (int k = 0; k < dim; k++) {
           SB_UNROLL
           for (int l = 0; l < dim; l++) {
-            double d = A[k][0] * T[0][l];
+            double d = As[k][0] * T[0][l];
             SB_UNROLL
-            for (int j = 1; j < dim; j++) d += A[k][j] * T[j][l];
-            d *= sJ;
-            if (nonlinear) d += map.scale * (Pp[a][k] * A[l][b] - A[k][b] * Pp[a][l]);
+            for (int j = 1; j < dim; j++) d += As[k][j] * T[j][l];
+            if (nonlin) d += sPp[a][k] * A[l][b] - A[k][b] * sPp[a][l];
             sink(a, k, b, l, d);
           }
         }
@@ -517,6 +601,26 @@ struct ShapeAwareIntegrandWrapperWithState {
     auto unmodified =
         integrand_(time, x_mod, state, shape_correction.modify_trial_argument(trial_spaces{}, qfunc_args)...);
     return shape_correction.modify_shape_aware_qf_return(test_space{}, unmodified);
+  }
+
+  // run-time flag -> compile-time variant forwarding (see FlagMode)
+  template <typename I, typename = void>
+  struct variants_of {
+    static constexpr int n = 1;
+  };
+  template <typename I>
+  struct variants_of<I, std::void_t<decltype(I::num_variants)>> {
+    static constexpr int n = I::num_variants;
+  };
+  static constexpr int num_variants = variants_of<Integrand>::n;
+  template <int V>
+  using variant =
+      ShapeAwareIntegrandWrapperWithState<typename Integrand::template variant<V>, dim, test_space, trial_spaces...>;
+  int variant_index() const { return integrand_.variant_index(); }
+  template <int V>
+  variant<V> as_variant() const
+  {
+    return variant<V>(integrand_.template as_variant<V>());
   }
 
   /// tangent fast path: argument i + 1 of the wrapper is argument i of the integrand; the shape correction only
