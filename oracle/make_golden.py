@@ -117,6 +117,16 @@ FIXTURES = [
                                                 p=2, params=[2.0, 100.0, 50.0, 0.0], vdim=3)),
     ("solid_neohookean_quad_p2_cart", dict(mesh_spec=("cart2d", 3, 2, 0.02), kind="solid_neohookean", p=2,
                                            params=[1.0, 100.0, 50.0, 1.0], vdim=2)),
+    # BASELINE.json configs[0]: HeatTransfer linear conduction, H1 p=1 on star.mesh (20 quads)
+    ("thermal_linear_conductor_quad_p1_star", dict(mesh_spec=("file", "star.mesh", 1), kind="thermal_linear_conductor",
+                                                   p=1, params=[1.5, 2.0, 0.7], vdim=1, shape_amp=0.01)),
+    ("thermal_linear_conductor_hex_p2_cart", dict(mesh_spec=("cart3d", 2, 2, 1, 0.02), kind="thermal_linear_conductor",
+                                                  p=2, params=[1.0, 1.0, 3.0], vdim=1)),
+    # BASELINE.json configs[2] material family: J2 plasticity with QuadratureData state (plastic loading: the return map
+    # runs at most points with these parameters), E nu sigma_y Hi Hk density geom_nonlin
+    ("solid_j2smallstrain_linear_hex_p2_cart", dict(mesh_spec=("cart3d", 2, 1, 2, 0.02),
+                                                    kind="solid_j2smallstrain_linear", p=2,
+                                                    params=[100.0, 0.25, 0.5, 5.0, 2.0, 1.0, 0.0], vdim=3, u_amp=0.02)),
 ]
 
 
@@ -141,11 +151,15 @@ def config_a_fixture():
 
 def main():
     os.makedirs(GOLDEN_DIR, exist_ok=True)
-    data = config_a_fixture()
-    path = os.path.join(GOLDEN_DIR, "config_a_beam_hex_r4_p2.npz")
-    np.savez_compressed(path, **data)
-    print(f"config A: ne={data['ne']} -> {os.path.getsize(path) / 1024:.0f} KiB")
+    only = sys.argv[1:]
+    if not only or "config_a" in only:
+        data = config_a_fixture()
+        path = os.path.join(GOLDEN_DIR, "config_a_beam_hex_r4_p2.npz")
+        np.savez_compressed(path, **data)
+        print(f"config A: ne={data['ne']} -> {os.path.getsize(path) / 1024:.0f} KiB")
     for name, kw in FIXTURES:
+        if only and name not in only:
+            continue
         data = reference_problem(**kw)
         path = os.path.join(GOLDEN_DIR, name + ".npz")
         np.savez_compressed(path, **data)

@@ -34,6 +34,23 @@ static Registrar r_lin({"solid_linear_isotropic_" SB_STR(SB_REG_TAG),
                         make_kernel_table<S::type, S::qf<LinearIsotropic>, LinearIsotropic::State>(),
                         &make_solid<S, LinearIsotropic>, "{density, K, G, geometric_nonlinearity(0|1)}"});
 
+#ifdef SB_REG_J2
+// small-strain J2 plasticity with quadrature-point state (solid_material.hpp:201-259; State = plastic strain + eqps)
+using J2Lin = solid_mechanics::J2SmallStrain<solid_mechanics::LinearHardening>;
+template <typename SS>
+long make_j2(const double* p, int n, void* out, size_t cap)
+{
+  if (n != 7) return -1;
+  J2Lin m{p[0], p[1], solid_mechanics::LinearHardening{p[2], p[3]}, p[4], p[5]};
+  auto  gn = (p[6] != 0.0) ? GeometricNonlinearities::On : GeometricNonlinearities::Off;
+  typename SS::template qf<J2Lin> qf{MaterialStressFunctor<J2Lin>(m, gn)};
+  return store_blob(qf, out, cap);
+}
+static Registrar r_j2({"solid_j2smallstrain_linear_" SB_STR(SB_REG_TAG),
+                       make_kernel_table<S::type, S::qf<J2Lin>, J2Lin::State>(), &make_j2<S>,
+                       "{E, nu, sigma_y, Hi, Hk, density, geometric_nonlinearity(0|1)}"});
+#endif
+
 #ifdef SB_REG_AD
 // the same integrand differentiated with dual numbers end to end (the reference's scheme; what an arbitrary user functor
 // gets): kept to cross-check the tangent fast path

@@ -79,6 +79,27 @@ def test_jvp_wrt_acceleration_and_shape(case):
     assert rel_l2(dr.cpu().numpy(), prob["dr_dshape"]) < TOL
 
 
+def test_state_commit(case):
+    """QuadratureData semantics (domain_integral_kernels.hpp:143-147): state is read every evaluation, written back only
+    when update_state is set; the next evaluation then starts from the committed state."""
+    prob, P = case
+    if "qdata1" not in prob:
+        pytest.skip("stateless integrand")
+    r_E = P.torch.zeros(P.G.ESize(), dtype=P.torch.float64, device=P.dev)
+    P.integral.Mult(0.0, P.fields(), r_E)  # no commit: state untouched
+    assert np.array_equal(P.qdata.cpu().numpy().ravel(), np.asarray(prob["qdata0"]).ravel())
+    P.integral.Mult(0.0, P.fields(), r_E, update_state=True)
+    assert rel_l2(r_E.cpu().numpy(), prob["r_E"]) < TOL
+    assert rel_l2(P.qdata.cpu().numpy(), prob["qdata1"]) < TOL
+    P.integral.Mult(0.0, P.fields(), r_E)
+    assert rel_l2(r_E.cpu().numpy(), prob["r_E_after_commit"]) < TOL
+    # committing through the derivative-storing kernel gives the same state
+    P.qdata.copy_(P.t(prob["qdata0"]).reshape(P.qdata.shape))
+    P.integral.Mult(0.0, P.fields(), r_E, wrt=1, update_state=True)
+    assert rel_l2(P.qdata.cpu().numpy(), prob["qdata1"]) < TOL
+    P.qdata.copy_(P.t(prob["qdata0"]).reshape(P.qdata.shape))
+
+
 def test_host_buffer_path_matches_device_path(case):
     prob, P = case
     r = P.F(0.0, [prob["S"], prob["U"], prob["A"]], wrt=1)

@@ -23,9 +23,17 @@ def run_oracle(prob, wrt=1, state=None):
     qf = fo.make_qf(str(prob["kind"]), list(prob["params"]))
     trials = [fo.gather(shape_table, prob["S"], dim), fo.gather(table, prob["U"], vdim),
               fo.gather(table, prob["A"], vdim)]
+    if state is None and "qdata0" in prob:
+        state = j2_state(prob["qdata0"], int(prob["ne"]), q**dim)
     r_E, blocks = fo.evaluation_kernel(qf, trials, [1, p, p], X_q, J_q, p, q, dim, wrt=wrt, state=state)
     return dict(table=table, shape_table=shape_table, X_q=X_q, J_q=J_q, r_E=r_E, blocks=blocks, p=p, q=q, dim=dim,
                 vdim=vdim)
+
+
+def j2_state(qdata, ne, nq):
+    """[ne][nq] AoS of J2SmallStrain::State {plastic_strain[3][3], eqps} (solid_material.hpp:212-215) -> oracle dict"""
+    s = np.asarray(qdata).reshape(ne, nq, 10)
+    return dict(plastic_strain=[[s[:, :, 3 * i + j].copy() for j in range(3)] for i in range(3)], eqps=s[:, :, 9].copy())
 
 
 @pytest.fixture(scope="module", params=golden_names())
@@ -59,6 +67,22 @@ def test_residual_and_jvp(case):
     dU_E = fo.gather(o["table"], prob["dU"], o["vdim"])
     dr_E = fo.action_of_gradient_kernel(o["blocks"], dU_E, o["p"], o["p"], o["q"], o["dim"])
     assert rel_l2(dr_E, prob["dr_E"]) < 1e-13
+
+
+def test_state_update(case):
+    """domain_integral_kernels.hpp:143-147: the state the q-function computed is what a committing evaluation stores"""
+    prob, _ = case
+    if "qdata1" not in prob:
+        pytest.skip("stateless integrand")
+    ne, nq = int(prob["ne"]), (int(prob["p"]) + 1)**int(prob["dim"])
+    st = j2_state(prob["qdata0"], ne, nq)
+    run_oracle(prob, wrt=-1, state=st)
+    new = st["_updated"]
+    want = np.asarray(prob["qdata1"]).reshape(ne, nq, 10)
+    assert rel_l2(new["eqps"], want[:, :, 9]) < 1e-13
+    for i in range(3):
+        for j in range(3):
+            assert np.abs(new["plastic_strain"][i][j] - want[:, :, 3 * i + j]).max() < 1e-14
 
 
 def test_other_arguments(case):
