@@ -241,6 +241,10 @@ int sb_halo_create(int64_t lsize, int64_t tsize, const int* ltdof_host, int num_
                    const int* send_idx_host, const int64_t* recv_off, const int* recv_idx_host, sb_halo_t* out);
 int sb_halo_destroy(sb_halo_t H);
 int sb_halo_buffers(sb_halo_t H, double** send_buf_dev, double** recv_buf_dev);
+/* use caller-owned staging buffers instead (each at least max(total send, total recv) doubles), e.g. buffers registered
+ * with the transport or peer-mapped symmetric memory; the library stops using (and later frees) its own */
+int sb_halo_set_buffers(sb_halo_t H, double* send_buf_dev, double* recv_buf_dev);
+int64_t sb_halo_buffer_doubles(sb_halo_t H);
 /* P: T -> L.  pack owner values for neighbours / copy owned / (after transport) unpack received values */
 int sb_halo_P_pack(sb_halo_t H, const double* T_dev, void* stream);
 int sb_halo_P_finish(sb_halo_t H, const double* T_dev, double* L_dev, void* stream);

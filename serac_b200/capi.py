@@ -81,6 +81,8 @@ SIGNATURES = {
     "sb_halo_create": (_i, [_i64, _i64, _vp, _i, _vp, _vp, _vp, _vp, _pp]),
     "sb_halo_destroy": (_i, [_vp]),
     "sb_halo_buffers": (_i, [_vp, _pp, _pp]),
+    "sb_halo_set_buffers": (_i, [_vp, _vp, _vp]),
+    "sb_halo_buffer_doubles": (_i64, [_vp]),
     "sb_halo_P_pack": (_i, [_vp, _vp, _vp]),
     "sb_halo_P_finish": (_i, [_vp, _vp, _vp, _vp]),
     "sb_halo_Pt_pack": (_i, [_vp, _vp, _vp]),

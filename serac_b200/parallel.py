@@ -1,0 +1,140 @@
+"""Shared-dof exchange P / P^T across ranks and the rank-parallel Functional built on it.
+
+Reference: mfem::ConformingProlongationOperator::Mult / MultTranspose (mfem/fem/pfespace.cpp:3599-3663), which
+serac::Functional applies around every evaluation (src/serac/numerics/functional/functional.hpp:446-498, 406-432).
+One process per GPU; the pack / ordered-unpack kernels are the C ABI's sb_halo_* (no atomics: P^T adds the received
+partial sums in a fixed neighbour order); the transport is torch.distributed point-to-point (NCCL over NVLink on GPUs).
+
+`HostHalo` is the same index logic in numpy over any torch.distributed backend (gloo): it exists so the partition /
+ownership / list construction can be tested on CPU; it is never used on the GPU path."""
+import ctypes as C
+
+import numpy as np
+
+from . import capi
+
+
+def _p2p(dist, sends, recvs, group=None):
+    """sends / recvs: lists of (tensor view, peer rank); one batched round"""
+    ops = [dist.P2POp(dist.irecv, t, peer, group) for t, peer in recvs if t.numel()]
+    ops += [dist.P2POp(dist.isend, t, peer, group) for t, peer in sends if t.numel()]
+    if not ops:
+        return
+    for req in dist.batch_isend_irecv(ops):
+        req.wait()
+
+
+class HaloExchange:
+    """P: T -> L and P^T: L -> T for one space on one rank (device buffers)."""
+
+    def __init__(self, lists, device, group=None):
+        import torch
+        import torch.distributed as dist
+        self.torch, self.dist, self.group, self.device = torch, dist, group, device
+        self.lists = lists
+        self.lsize, self.tsize = int(lists["lsize"]), int(lists["tsize"])
+        self.neighbors = list(lists["neighbors"])
+        self.send_off = np.asarray(lists["send_off"], dtype=np.int64)
+        self.recv_off = np.asarray(lists["recv_off"], dtype=np.int64)
+        h = C.c_void_p()
+        L = capi.lib()
+        capi.check(L.sb_halo_create(self.lsize, self.tsize, capi._np_ptr(lists["ltdof"]), len(self.neighbors),
+                                    capi._np_ptr(self.send_off), capi._np_ptr(lists["send_idx"]),
+                                    capi._np_ptr(self.recv_off), capi._np_ptr(lists["recv_idx"]), C.byref(h)))
+        self.h = h
+        n = max(int(L.sb_halo_buffer_doubles(h)), 1)
+        self.send_buf = torch.zeros(n, dtype=torch.float64, device=device)
+        self.recv_buf = torch.zeros(n, dtype=torch.float64, device=device)
+        capi.check(L.sb_halo_set_buffers(h, capi._dev_ptr(self.send_buf), capi._dev_ptr(self.recv_buf)))
+
+    def __del__(self):
+        try:
+            capi.lib().sb_halo_destroy(self.h)
+        except Exception:
+            pass
+
+    def _round(self, out_off, in_off):
+        sends = [(self.send_buf[out_off[i]:out_off[i + 1]], r) for i, r in enumerate(self.neighbors)]
+        recvs = [(self.recv_buf[in_off[i]:in_off[i + 1]], r) for i, r in enumerate(self.neighbors)]
+        _p2p(self.dist, sends, recvs, self.group)
+
+    def P(self, T, L=None):
+        """T-vector -> L-vector: owned entries copied, entries owned elsewhere received from their owner"""
+        lib = capi.lib()
+        if L is None:
+            L = self.torch.empty(self.lsize, dtype=self.torch.float64, device=self.device)
+        s = capi._stream_ptr()
+        capi.check(lib.sb_halo_P_pack(self.h, capi._dev_ptr(T), s))
+        self._round(self.send_off, self.recv_off)
+        capi.check(lib.sb_halo_P_finish(self.h, capi._dev_ptr(T), capi._dev_ptr(L), s))
+        return L
+
+    def Pt(self, L, T=None):
+        """L-vector -> T-vector: owned entries plus the partial sums every sharer computed, in fixed neighbour order"""
+        lib = capi.lib()
+        if T is None:
+            T = self.torch.empty(self.tsize, dtype=self.torch.float64, device=self.device)
+        s = capi._stream_ptr()
+        capi.check(lib.sb_halo_Pt_pack(self.h, capi._dev_ptr(L), s))
+        self._round(self.recv_off, self.send_off)  # P^T sends what P received and vice versa
+        capi.check(lib.sb_halo_Pt_finish(self.h, capi._dev_ptr(L), capi._dev_ptr(T), s))
+        return T
+
+
+class HostHalo:
+    """numpy restatement of HaloExchange's semantics (CPU tests of the partition logic only)."""
+
+    def __init__(self, lists, group=None):
+        import torch
+        import torch.distributed as dist
+        self.torch, self.dist, self.group, self.l = torch, dist, group, lists
+        self.neighbors = list(lists["neighbors"])
+
+    def _round(self, send, out_off, in_off):
+        t = self.torch
+        sbuf = t.as_tensor(np.ascontiguousarray(send))
+        rbuf = t.zeros(int(in_off[-1]), dtype=t.float64)
+        sends = [(sbuf[out_off[i]:out_off[i + 1]], r) for i, r in enumerate(self.neighbors)]
+        recvs = [(rbuf[in_off[i]:in_off[i + 1]], r) for i, r in enumerate(self.neighbors)]
+        _p2p(self.dist, sends, recvs, self.group)
+        return rbuf.numpy()
+
+    def P(self, T):
+        l = self.l
+        recv = self._round(T[l["send_idx"]], l["send_off"], l["recv_off"])
+        L = np.zeros(l["lsize"])
+        own = l["ltdof"] >= 0
+        L[own] = T[l["ltdof"][own]]
+        L[l["recv_idx"]] = recv
+        return L
+
+    def Pt(self, L):
+        l = self.l
+        recv = self._round(L[l["recv_idx"]], l["recv_off"], l["send_off"])
+        T = np.zeros(l["tsize"])
+        own = l["ltdof"] >= 0
+        T[l["ltdof"][own]] = L[own]
+        for k in range(len(recv)):  # ascending slot order = neighbour order, then list order
+            T[l["send_idx"][k]] += recv[k]
+        return T
+
+
+class ParFunctional:
+    """serac::Functional on a partitioned mesh (functional.hpp:446-498): T-vectors in, T-vector out."""
+
+    def __init__(self, functional, trial_halos, test_halo):
+        self.F, self.trial_halos, self.test_halo = functional, list(trial_halos), test_halo
+        self._L = [None] * len(self.trial_halos)
+        self._rL = None
+        self._duL = {}
+
+    def __call__(self, t, T_inputs, wrt=capi.NO_DIFFERENTIATION, out=None, update_state=False):
+        for i, (h, T) in enumerate(zip(self.trial_halos, T_inputs)):
+            self._L[i] = h.P(T, self._L[i])
+        self._rL = self.F(t, self._L, wrt=wrt, out=self._rL, update_state=update_state)
+        return self.test_halo.Pt(self._rL, out)
+
+    def GradientMult(self, wrt, dT, out=None):
+        self._duL[wrt] = self.trial_halos[wrt].P(dT, self._duL.get(wrt))
+        self._rL = self.F.GradientMult(wrt, self._duL[wrt], out=self._rL)
+        return self.test_halo.Pt(self._rL, out)

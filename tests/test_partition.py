@@ -1,0 +1,112 @@
+"""CPU: the structured-mesh partitioner and the shared-dof exchange logic (serac_b200/structured.py, parallel.py), incl.
+world_size-2 and -4 runs over the gloo backend.  The distributed residual is checked against the numpy oracle evaluated
+on the global mesh (oracle as checker only)."""
+import os
+import socket
+
+import numpy as np
+import pytest
+
+from harness import rel_l2
+from serac_b200.structured import Partition, StructuredHexMesh, factor_ranks
+
+
+def test_factor_ranks():
+    assert factor_ranks(1) == (1, 1, 1)
+    assert sorted(factor_ranks(2)) == [1, 1, 2] and sorted(factor_ranks(4)) == [1, 2, 2] and factor_ranks(8) == (2, 2, 2)
+    assert factor_ranks(4, (128, 16, 16)) == (4, 1, 1)  # beams are cut along their length
+
+
+def test_element_table_matches_lexicographic_convention():
+    m = StructuredHexMesh(2, 1, 1)
+    t = m.element_table(1)
+    # nodes of a 3 x 2 x 2 grid; element 0: x fastest, then y, then z
+    assert t.tolist() == [[0, 1, 3, 4, 6, 7, 9, 10], [1, 2, 4, 5, 7, 8, 10, 11]]
+    assert m.element_table(2).shape == (2, 27) and m.num_nodes(2) == 5 * 3 * 3
+
+
+@pytest.mark.parametrize("ranks", [(2, 1, 1), (2, 2, 1), (2, 2, 2), (3, 1, 2)])
+@pytest.mark.parametrize("p", [1, 2])
+def test_ownership_and_lists_are_consistent(ranks, p):
+    mesh = StructuredHexMesh(5, 4, 3)
+    world = int(np.prod(ranks))
+    parts = [Partition(mesh, ranks, r, p, components=3) for r in range(world)]
+    # every global vdof is owned exactly once
+    owned = np.concatenate([pt.global_true_vdofs() for pt in parts])
+    assert len(owned) == mesh.num_nodes(p) * 3 and len(np.unique(owned)) == len(owned)
+    assert sum(pt.num_elements for pt in parts) == mesh.ne
+    lists = [pt.halo_lists() for pt in parts]
+    for r, (pt, l) in enumerate(zip(parts, lists)):
+        gl, gt = pt.global_local_vdofs(), pt.global_true_vdofs()
+        for i, s in enumerate(l["neighbors"]):
+            j = lists[s]["neighbors"].index(r)
+            mine = gt[l["send_idx"][l["send_off"][i]:l["send_off"][i + 1]]]
+            theirs = parts[s].global_local_vdofs()[lists[s]["recv_idx"][lists[s]["recv_off"][j]:lists[s]["recv_off"][j + 1]]]
+            assert np.array_equal(mine, theirs)  # same dofs in the same order on both sides
+        # the owner of a shared node is the lowest rank that holds it
+        for s in l["neighbors"]:
+            shared = pt.shared_with[s]
+            assert (pt.owner[shared] <= min(r, s)).all()
+        assert (l["ltdof"] >= 0).sum() == l["tsize"] and len(gl) == l["lsize"]
+
+
+def _free_port():
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        return s.getsockname()[1]
+
+
+def _worker(rank, world, port, ranks, p, out):
+    import torch.distributed as dist
+    from oracle import functional_oracle as fo
+    from serac_b200.parallel import HostHalo
+    os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        mesh = StructuredHexMesh(4, 3, 2, 2.0, 1.5, 1.0)
+        c = 3
+        pt = Partition(mesh, ranks, rank, p, components=c)
+        halo = HostHalo(pt.halo_lists())
+        f = lambda g: np.sin(0.37 * g) + 0.01 * g  # a globally consistent vector
+        # --- P: T -> L reproduces the global vector on every local dof ---
+        L = halo.P(f(pt.global_true_vdofs().astype(np.float64)))
+        assert np.array_equal(L, f(pt.global_local_vdofs().astype(np.float64)))
+        # --- local residual with the numpy oracle, then P^T; compare with the oracle on the global mesh ---
+        U_glob = 0.01 * f(np.arange(mesh.num_nodes(p) * c, dtype=np.float64))
+        qf = fo.make_qf("solid_neohookean", [1.0, 100.0, 50.0, 1.0])
+
+        def residual(table, shape_table, coords, U, nnodes):
+            q = p + 1
+            X_q, J_q = fo.geometric_factors(fo.gather(shape_table, coords, 3), 1, q, 3)
+            trials = [fo.gather(shape_table, np.zeros_like(coords), 3), fo.gather(table, U, c),
+                      fo.gather(table, np.zeros_like(U), c)]
+            r_E, _ = fo.evaluation_kernel(qf, trials, [1, p, p], X_q, J_q, p, q, 3, wrt=-1)
+            return fo.scatter_add(table, r_E, np.zeros(nnodes * c), c)
+
+        r_loc = residual(pt.element_table(p), pt.element_table(1), pt.vertex_coordinates(),
+                         U_glob[pt.global_local_vdofs()], pt.num_local_nodes)
+        r_T = halo.Pt(r_loc)
+        r_glob = residual(mesh.element_table(p), mesh.element_table(1), mesh.vertex_coordinates(), U_glob,
+                          mesh.num_nodes(p))
+        err = rel_l2(r_T, r_glob[pt.global_true_vdofs()])
+        assert err < 1e-13, err
+        out.put((rank, "ok"))
+    except Exception as e:  # noqa: BLE001
+        out.put((rank, repr(e)))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world,ranks", [(2, (2, 1, 1)), (4, (2, 2, 1))])
+def test_distributed_residual_over_gloo(world, ranks):
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    out = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, world, port, ranks, 2, out)) for r in range(world)]
+    for pr in procs:
+        pr.start()
+    res = [out.get(timeout=240) for _ in procs]
+    for pr in procs:
+        pr.join(timeout=60)
+    assert all(msg == "ok" for _, msg in res), res
