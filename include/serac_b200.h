@@ -252,6 +252,27 @@ int sb_halo_P_finish(sb_halo_t H, const double* T_dev, double* L_dev, void* stre
 int sb_halo_Pt_pack(sb_halo_t H, const double* L_dev, void* stream);
 int sb_halo_Pt_finish(sb_halo_t H, const double* L_dev, double* T_dev, void* stream);
 
+
+/* Peer-memory transport: the whole exchange as two kernels over NVLink-mapped peer buffers -- no NCCL call on the path,
+ * so a step can be captured in a CUDA graph and an exchange costs two launches (~5 us) instead of a p2p group.
+ * Every rank owns a receive RING in memory its neighbours can map (CUDA IPC / symmetric memory; mapping is the caller's
+ * job): 2 slots of `slot_doubles` doubles followed by 2 x SB_HALO_MAX_NEIGHBORS int64 arrival flags, i.e.
+ * (2 * slot_doubles + 2 * SB_HALO_MAX_NEIGHBORS) 8-byte words, zero-initialised.  Round k uses slot k % 2: a sender can
+ * be at most one round ahead of a receiver (it needs that receiver's round k - 1 data first), so two slots suffice.
+ *   peer_ring[n]        neighbour n's ring as mapped in this process
+ *   peer_P_off[n]       where this rank's P segment starts inside neighbour n's slot (= its recv_off for this rank)
+ *   peer_Pt_off[n]      same for P^T (= its send_off for this rank)
+ *   my_index_at_peer[n] this rank's position in neighbour n's neighbour list (selects the flag it raises there)
+ * The put kernel writes straight into the neighbours' slots and raises their flags (release, system scope); the finish
+ * kernel waits for its own flags (acquire) and unpacks.  A wait that exceeds ~2 s gives up and records an error that
+ * sb_halo_peer_status reports (non-zero), instead of hanging the device. */
+#define SB_HALO_MAX_NEIGHBORS 32
+int sb_halo_enable_peer(sb_halo_t H, double* my_ring_dev, int64_t slot_doubles, double* const* peer_ring,
+                        const int64_t* peer_P_off, const int64_t* peer_Pt_off, const int* my_index_at_peer);
+int sb_halo_P_peer(sb_halo_t H, const double* T_dev, double* L_dev, void* stream);
+int sb_halo_Pt_peer(sb_halo_t H, const double* L_dev, double* T_dev, void* stream);
+int sb_halo_peer_status(sb_halo_t H, int* status_host);
+
 #ifdef __cplusplus
 }
 #endif

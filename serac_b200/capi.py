@@ -83,6 +83,10 @@ SIGNATURES = {
     "sb_halo_buffers": (_i, [_vp, _pp, _pp]),
     "sb_halo_set_buffers": (_i, [_vp, _vp, _vp]),
     "sb_halo_buffer_doubles": (_i64, [_vp]),
+    "sb_halo_enable_peer": (_i, [_vp, _vp, _i64, _vp, _vp, _vp, _vp]),
+    "sb_halo_P_peer": (_i, [_vp, _vp, _vp, _vp]),
+    "sb_halo_Pt_peer": (_i, [_vp, _vp, _vp, _vp]),
+    "sb_halo_peer_status": (_i, [_vp, _vp]),
     "sb_halo_P_pack": (_i, [_vp, _vp, _vp]),
     "sb_halo_P_finish": (_i, [_vp, _vp, _vp, _vp]),
     "sb_halo_Pt_pack": (_i, [_vp, _vp, _vp]),

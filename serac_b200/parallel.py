@@ -47,11 +47,59 @@ class HaloExchange:
         self.recv_buf = torch.zeros(n, dtype=torch.float64, device=device)
         capi.check(L.sb_halo_set_buffers(h, capi._dev_ptr(self.send_buf), capi._dev_ptr(self.recv_buf)))
 
+        self.peer = False
+
     def __del__(self):
         try:
             capi.lib().sb_halo_destroy(self.h)
         except Exception:
             pass
+
+    def enable_peer(self):
+        """Switch the transport to the peer-memory kernels (sb_halo_*_peer): every rank's receive ring lives in
+        torch symmetric memory (CUDA IPC-mapped over NVLink), neighbours write into it directly.  Collective: every
+        rank of the group must call it.  Returns False (and keeps the NCCL transport) if symmetric memory is
+        unavailable."""
+        torch, dist = self.torch, self.dist
+        import torch.distributed._symmetric_memory as symm_mem
+        lib = capi.lib()
+        MAXN = 32
+        rank, world = dist.get_rank(self.group), dist.get_world_size(self.group)
+        slot = torch.tensor([max(int(lib.sb_halo_buffer_doubles(self.h)), 1)], dtype=torch.int64, device=self.device)
+        dist.all_reduce(slot, op=dist.ReduceOp.MAX, group=self.group)
+        slot = int(slot.item())
+        meta = [None] * world
+        dist.all_gather_object(meta, dict(neighbors=self.neighbors, send_off=self.send_off.tolist(),
+                                          recv_off=self.recv_off.tolist()), group=self.group)
+        try:
+            grp = self.group if self.group is not None else dist.group.WORLD
+            ring = symm_mem.empty(2 * slot + 2 * MAXN, dtype=torch.float64, device=self.device)
+            ring.zero_()
+            hdl = symm_mem.rendezvous(ring, grp.group_name if hasattr(grp, "group_name") else grp)
+            ptrs = [int(p) for p in hdl.buffer_ptrs]
+        except Exception as e:  # noqa: BLE001
+            if rank == 0:
+                print(f"[serac_b200] symmetric memory unavailable ({e!r}); keeping the NCCL transport", flush=True)
+            return False
+        torch.cuda.synchronize()
+        dist.barrier(group=self.group)  # every ring is zeroed before anyone writes
+        nn = len(self.neighbors)
+        peer_ring = (C.c_void_p * max(nn, 1))()
+        P_off, Pt_off = np.zeros(max(nn, 1), dtype=np.int64), np.zeros(max(nn, 1), dtype=np.int64)
+        my_idx = np.zeros(max(nn, 1), dtype=np.int32)
+        for i, s in enumerate(self.neighbors):
+            j = meta[s]["neighbors"].index(rank)
+            peer_ring[i] = ptrs[s]
+            P_off[i], Pt_off[i], my_idx[i] = meta[s]["recv_off"][j], meta[s]["send_off"][j], j
+        capi.check(lib.sb_halo_enable_peer(self.h, capi._dev_ptr(ring), slot, peer_ring, capi._np_ptr(P_off),
+                                           capi._np_ptr(Pt_off), capi._np_ptr(my_idx)))
+        self._ring, self._hdl, self.peer = ring, hdl, True
+        return True
+
+    def peer_status(self):
+        st = C.c_int(0)
+        capi.check(capi.lib().sb_halo_peer_status(self.h, C.byref(st)))
+        return st.value
 
     def _round(self, out_off, in_off):
         sends = [(self.send_buf[out_off[i]:out_off[i + 1]], r) for i, r in enumerate(self.neighbors)]
@@ -64,6 +112,9 @@ class HaloExchange:
         if L is None:
             L = self.torch.empty(self.lsize, dtype=self.torch.float64, device=self.device)
         s = capi._stream_ptr()
+        if self.peer:
+            capi.check(lib.sb_halo_P_peer(self.h, capi._dev_ptr(T), capi._dev_ptr(L), s))
+            return L
         capi.check(lib.sb_halo_P_pack(self.h, capi._dev_ptr(T), s))
         self._round(self.send_off, self.recv_off)
         capi.check(lib.sb_halo_P_finish(self.h, capi._dev_ptr(T), capi._dev_ptr(L), s))
@@ -75,6 +126,9 @@ class HaloExchange:
         if T is None:
             T = self.torch.empty(self.tsize, dtype=self.torch.float64, device=self.device)
         s = capi._stream_ptr()
+        if self.peer:
+            capi.check(lib.sb_halo_Pt_peer(self.h, capi._dev_ptr(L), capi._dev_ptr(T), s))
+            return T
         capi.check(lib.sb_halo_Pt_pack(self.h, capi._dev_ptr(L), s))
         self._round(self.recv_off, self.send_off)  # P^T sends what P received and vice versa
         capi.check(lib.sb_halo_Pt_finish(self.h, capi._dev_ptr(L), capi._dev_ptr(T), s))

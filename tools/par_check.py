@@ -47,6 +47,10 @@ def main():
     part, part1 = Partition(mesh, ranks, rank, p, 3), Partition(mesh, ranks, rank, 1, 3)
     loc = build(dev, mesh, part, p)
     halo, halo1 = HaloExchange(part.halo_lists(), dev), HaloExchange(part1.halo_lists(), dev)
+    transport = "nccl"
+    if os.environ.get("SB_HALO_TRANSPORT", "peer") == "peer":
+        ok1, ok2 = halo.enable_peer(), halo1.enable_peer()
+        transport = "peer" if (ok1 and ok2) else "nccl"
     PF = ParFunctional(loc["F"], [halo1, halo, halo], halo)
     # globally consistent inputs
     rng = np.random.default_rng(7)
@@ -56,6 +60,12 @@ def main():
     gt, gt1 = part.global_true_vdofs(), part1.global_true_vdofs()
     r_T = PF(0.0, [t(S[gt1]), t(U[gt]), t(A[gt])], wrt=1)
     dr_T = PF.GradientMult(1, t(dU[gt]))
+    for _ in range(5):  # repeated rounds exercise the two-slot ring
+        r_T = PF(0.0, [t(S[gt1]), t(U[gt]), t(A[gt])], wrt=1)
+        dr_T = PF.GradientMult(1, t(dU[gt]))
+    torch.cuda.synchronize()
+    if transport == "peer":
+        assert halo.peer_status() == 0 and halo1.peer_status() == 0, "a peer flag wait timed out"
     # the same on the whole mesh, one GPU
     glob = build(dev, mesh, None, p)
     r = glob["F"](0.0, [t(S), t(U), t(A)], wrt=1).cpu().numpy()
@@ -66,7 +76,7 @@ def main():
     dist.all_reduce(errs, op=dist.ReduceOp.MAX)
     ok = bool((errs < 1e-13).all())
     if rank == 0:
-        print(f"par_check {'ok' if ok else 'FAILED'}: world={world} ranks={ranks} mesh={nx}x{ny}x{nz} p={p} "
+        print(f"par_check {'ok' if ok else 'FAILED'}: world={world} ranks={ranks} mesh={nx}x{ny}x{nz} p={p} transport={transport} "
               f"residual {errs[0].item():.2e} jvp {errs[1].item():.2e}", flush=True)
     dist.destroy_process_group()
     sys.exit(0 if ok else 1)
