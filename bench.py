@@ -31,6 +31,10 @@ sys.path.insert(0, ROOT)
 METRIC = "GDOF/s Functional residual + Jacobian action (p=2 hex)"
 CONFIG_A = os.path.join(ROOT, "tests", "golden", "config_a_beam_hex_r4_p2.npz")
 NEOHOOKEAN = [1.0, 100.0, 50.0, 1.0]  # density, K, G, geometric nonlinearity on (BASELINE.md §2 probe values)
+# dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed `ncu --set full` capture of this command
+# (profiles/r1_ncu_full_summary.md); None until captured
+JVP_NCU_TRAFFIC_BYTES = None
+EVAL_NCU_TRAFFIC_BYTES = None
 
 
 # ---------------------------------------------------------------------------------------------------------------------
@@ -108,7 +112,48 @@ def build_problem(device):
     vs, ss = G.LSize(), G_shape.LSize()
     host = dict(U=1e-3 * rng.uniform(-1, 1, vs), A=np.zeros(vs), S=np.zeros(ss), dU=rng.uniform(0, 1, vs))
     return dict(capi=capi, G=G, G_shape=G_shape, G_mesh=G_mesh, integral=integral, F=F, host=host, ne=int(d["ne"]),
-                nq=int(d["ne"]) * (p + 1)**dim, vdofs=vs, p=p, keep=(nodes, X_q, J_q))
+                nq=int(d["ne"]) * (p + 1)**dim, vdofs=vs, tdofs=vs, tdofs_shape=ss, p=p, keep=(nodes, X_q, J_q),
+                mesh="beam-hex.mesh refined 4x (mfem numbering; fixture tests/golden/config_a_beam_hex_r4_p2.npz)")
+
+
+PER_GPU_BOX = (128, 16, 16)  # hexes per GPU = config A's 32 768 (the beam refined 4x), element size 1/16
+
+
+def build_partitioned_problem(device, rank, world):
+    """N > 1: the config-A box per GPU (weak scaling), boxes laid out 2x1x1 / 2x2x1 / 2x2x2, one
+    partition per rank with the shared-dof exchange P / P^T (mfem/fem/pfespace.cpp:3599-3663) on the box faces."""
+    import torch
+    from serac_b200 import capi
+    from serac_b200.parallel import HaloExchange, ParFunctional
+    from serac_b200.structured import Partition, StructuredHexMesh, factor_ranks
+    p = 2
+    ranks = factor_ranks(world)
+    n = tuple(PER_GPU_BOX[d] * ranks[d] for d in range(3))
+    mesh = StructuredHexMesh(*n, n[0] / 16.0, n[1] / 16.0, n[2] / 16.0)
+    part, part1 = Partition(mesh, ranks, rank, p, 3), Partition(mesh, ranks, rank, 1, 3)
+    tab, tab1 = part.element_table(p), part.element_table(1)
+    G = capi.ElementRestriction(tab, 3, part.num_local_nodes)
+    G_shape = capi.ElementRestriction(tab1, 3, part1.num_local_nodes)
+    nodes = torch.as_tensor(part.vertex_coordinates(), dtype=torch.float64, device=device)
+    X_q, J_q = capi.geometric_factors(capi.CUBE, 1, p + 1, G_shape, nodes)
+    integral = capi.Integral("solid_neohookean_hex_p2", NEOHOOKEAN, X_q, J_q, tab.shape[0])
+    F = capi.Functional(G, [G_shape, G, G])
+    F.AddDomainIntegral(integral, [0, 1, 2])
+    halo, halo1 = HaloExchange(part.halo_lists(), device), HaloExchange(part1.halo_lists(), device)
+    transport = "nccl"
+    if os.environ.get("SB_HALO_TRANSPORT", "peer") == "peer":
+        ok = [halo.enable_peer(), halo1.enable_peer()]
+        transport = "peer" if all(ok) else "nccl"
+    PF = ParFunctional(F, [halo1, halo, halo], halo)
+    # globally consistent synthetic inputs: a function of the global vdof id, so shared dofs agree across ranks
+    gt, gt1 = part.global_true_vdofs().astype(np.float64), part1.global_true_vdofs().astype(np.float64)
+    host = dict(U=1e-3 * np.sin(0.37 * gt + 1.0), A=np.zeros(len(gt)), S=np.zeros(len(gt1)),
+                dU=0.5 + 0.5 * np.sin(0.11 * gt))
+    return dict(capi=capi, G=G, G_shape=G_shape, integral=integral, F=F, PF=PF, halo=halo, halo1=halo1, host=host,
+                ne=tab.shape[0], nq=tab.shape[0] * (p + 1)**3, vdofs=G.LSize(), tdofs=halo.tsize, tdofs_shape=halo1.tsize,
+                global_vdofs=mesh.num_nodes(p) * 3, p=p, transport=transport, ranks=ranks, keep=(nodes, X_q, J_q),
+                mesh=f"structured {n[0]}x{n[1]}x{n[2]} hexes, {ranks[0]}x{ranks[1]}x{ranks[2]} boxes of "
+                     f"{PER_GPU_BOX[0]}x{PER_GPU_BOX[1]}x{PER_GPU_BOX[2]}")
 
 
 def run_product(args):
@@ -121,17 +166,21 @@ def run_product(args):
     dev = torch.device("cuda", local)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
-    P = build_problem(dev)
+        P = build_partitioned_problem(dev, rank, world)
+        call = P["PF"]
+    else:
+        P = build_problem(dev)
+        call = P["F"]
     capi, F, G, integral = P["capi"], P["F"], P["G"], P["integral"]
     t64 = lambda a: torch.as_tensor(a, dtype=torch.float64, device=dev)
-    U, A, S, dU = (t64(P["host"][k]) for k in ("U", "A", "S", "dU"))
-    r = torch.empty(P["vdofs"], dtype=torch.float64, device=dev)
+    U, A, S, dU = (t64(P["host"][k]) for k in ("U", "A", "S", "dU"))  # T-vectors (= L-vectors at one rank)
+    r = torch.empty(P["tdofs"], dtype=torch.float64, device=dev)
     dr = torch.empty_like(r)
     r_E = torch.empty(G.ESize(), dtype=torch.float64, device=dev)
 
     def step_device():
-        F(0.0, [S, U, A], wrt=1, out=r)
-        F.GradientMult(1, dU, out=dr)
+        call(0.0, [S, U, A], wrt=1, out=r)
+        call.GradientMult(1, dU, out=dr)
 
     # --- warm-up (also allocates the derivative buffer), then capture the step in a CUDA graph ---
     for _ in range(max(args.warmup, 3)):
@@ -141,17 +190,24 @@ def run_product(args):
     step_device()
     torch.cuda.synchronize()
     launches_per_step = capi.lib().sb_launch_count()
-    graph = torch.cuda.CUDAGraph()
-    side = torch.cuda.Stream()
-    with torch.cuda.stream(side):
-        step_device()
-        torch.cuda.synchronize()
-        with torch.cuda.graph(graph, stream=side):
+    # the NCCL point-to-point transport is driven from the host, so only the peer-memory transport is graph-captured
+    use_graph = not args.no_graph and (world == 1 or P["transport"] == "peer")
+    if use_graph:
+        graph = torch.cuda.CUDAGraph()
+        side = torch.cuda.Stream()
+        with torch.cuda.stream(side):
             step_device()
-    torch.cuda.synchronize()
-    for _ in range(3):
-        graph.replay()
-    torch.cuda.synchronize()
+            torch.cuda.synchronize()
+            if world > 1:
+                dist.barrier()
+            with torch.cuda.graph(graph, stream=side):
+                step_device()
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        for _ in range(3):
+            graph.replay()
+        torch.cuda.synchronize()
 
     sampler = ClockSampler(local)
     if rank == 0:
@@ -162,10 +218,10 @@ def run_product(args):
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for _ in range(args.steps):
-        if args.no_graph:
-            step_device()
-        else:
+        if use_graph:
             graph.replay()
+        else:
+            step_device()
     e1.record()
     torch.cuda.synchronize()
     if world > 1:
@@ -176,33 +232,72 @@ def run_product(args):
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
         ms_total = float(tt.item())
     ms_per_step = ms_total / args.steps
+    if world > 1 and P["transport"] == "peer":
+        assert P["halo"].peer_status() == 0 and P["halo1"].peer_status() == 0, "a peer-memory flag wait timed out"
 
-    # --- per-kernel durations inside a second timed loop (events on the launching stream) ---
-    fields = [P["G_shape"].field(S), G.field(U), G.field(A)]
-    du_field = G.field(dU)
+    # --- per-kernel durations inside a second timed loop (events on the launching stream; rank-local kernels only) ---
+    UL, AL, SL, dUL = (U, A, S, dU) if world == 1 else (P["PF"]._L[1], P["PF"]._L[2], P["PF"]._L[0], P["PF"]._duL[1])
+    rL = torch.empty(P["vdofs"], dtype=torch.float64, device=dev)
+    fields = [P["G_shape"].field(SL), G.field(UL), G.field(AL)]
+    du_field = G.field(dUL)
     ev = [[torch.cuda.Event(enable_timing=True) for _ in range(5)] for _ in range(args.steps)]
     for k in range(args.steps):
         ev[k][0].record()
         integral.Mult(0.0, fields, r_E, wrt=1)
         ev[k][1].record()
-        G.Scatter(r_E, r)
+        G.Scatter(r_E, rL)
         ev[k][2].record()
         integral.GradientMult(1, du_field, r_E)
         ev[k][3].record()
-        G.Scatter(r_E, dr)
+        G.Scatter(r_E, rL)
         ev[k][4].record()
     torch.cuda.synchronize()
     phase_ms = [float(np.mean([ev[k][i].elapsed_time(ev[k][i + 1]) for k in range(args.steps)])) for i in range(4)]
+    halo_ms = None
+    if world > 1:  # the exchange alone: P of the three inputs + P^T of the output, as in one evaluation
+        dist.barrier()
+        h0, h1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        h0.record()
+        for _ in range(args.steps):
+            P["halo1"].P(S, SL)
+            P["halo"].P(U, UL)
+            P["halo"].P(A, AL)
+            P["halo"].Pt(rL, r)
+        h1.record()
+        torch.cuda.synchronize()
+        halo_ms = h0.elapsed_time(h1) / args.steps
+        dist.barrier()
+        # restore the outputs the sanity check below compares against
+        step_device()
+        torch.cuda.synchronize()
 
-    # --- end to end through the host-buffer C ABI (pinned host memory in, host memory out) ---
-    pin = lambda a: torch.as_tensor(a, dtype=torch.float64).pin_memory().numpy()
+    # --- end to end through the host-buffer API (pinned host memory in, host memory out) ---
+    pin = lambda a: torch.as_tensor(a, dtype=torch.float64).pin_memory()
     hU, hA, hS, hdU = (pin(P["host"][k]) for k in ("U", "A", "S", "dU"))
-    hr = torch.empty(P["vdofs"], dtype=torch.float64).pin_memory().numpy()
-    hdr = torch.empty(P["vdofs"], dtype=torch.float64).pin_memory().numpy()
+    hr = torch.empty(P["tdofs"], dtype=torch.float64).pin_memory()
+    hdr = torch.empty(P["tdofs"], dtype=torch.float64).pin_memory()
 
-    def step_host():
-        F(0.0, [hS, hU, hA], wrt=1, out=hr)
-        F.GradientMult(1, hdU, out=hdr)
+    if world == 1:
+        # sb_functional_evaluate / sb_functional_jvp with host pointers: the copies happen inside the C ABI call
+        nU, nA, nS, ndU, nr, ndr = (x.numpy() for x in (hU, hA, hS, hdU, hr, hdr))
+
+        def step_host():
+            F(0.0, [nS, nU, nA], wrt=1, out=nr)
+            F.GradientMult(1, ndU, out=ndr)
+    else:
+        dS, dUd, dA, ddU = (torch.empty_like(x, device=dev) for x in (hS, hU, hA, hdU))
+        d_r, d_dr = torch.empty_like(r), torch.empty_like(dr)
+
+        def step_host():
+            dS.copy_(hS, non_blocking=True)
+            dUd.copy_(hU, non_blocking=True)
+            dA.copy_(hA, non_blocking=True)
+            call(0.0, [dS, dUd, dA], wrt=1, out=d_r)
+            hr.copy_(d_r, non_blocking=True)
+            ddU.copy_(hdU, non_blocking=True)
+            call.GradientMult(1, ddU, out=d_dr)
+            hdr.copy_(d_dr, non_blocking=True)
+            torch.cuda.current_stream().synchronize()
 
     for _ in range(3):
         step_host()
@@ -222,12 +317,20 @@ def run_product(args):
     clocks = sampler.stop() if rank == 0 else None
 
     # sanity: host path and device path agree bit for bit (same kernels, same data)
-    assert np.array_equal(hr, r.cpu().numpy()) and np.array_equal(hdr, dr.cpu().numpy())
+    assert np.array_equal(hr.numpy(), r.cpu().numpy()) and np.array_equal(hdr.numpy(), dr.cpu().numpy())
+    assert np.isfinite(hr.numpy()).all() and np.abs(hdr.numpy()).max() > 0
 
+    sums = torch.tensor([P["tdofs"], P["tdofs_shape"]], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(sums)
+    vdofs_total, shape_total = int(sums[0].item()), int(sums[1].item())
+    if world > 1:
+        assert vdofs_total == P["global_vdofs"], "true dofs of the partitions do not add up to the global space"
+        dist.barrier()
+        dist.destroy_process_group()
     if rank != 0:
         return
     peak, peak_src = measured_peaks()
-    vdofs_total = P["vdofs"] * world
     # algorithmic bytes of the Jacobian action per quadrature point: du + dr L-vectors (8*3*p^3/(p+1)^3
     # each), 81 stored derivatives (648 B), int32 restriction table (4 B)  = 666 B/qpt at p=2
     p = P["p"]
@@ -235,27 +338,38 @@ def run_product(args):
     jvp_bytes = (2 * V + 648.0 + 4.0) * P["nq"]
     jvp_ms = phase_ms[2]
     achieved = jvp_bytes / (jvp_ms * 1e-3) / 1e9
+    eval_bytes = (3 * V + 0.9 + 96.0 + 648.0 + 4.0) * P["nq"]  # residual + derivative store, ~770 B/qpt (§8d)
     out = {
         "metric": METRIC, "value": vdofs_total / (ms_per_step * 1e-3) / 1e9, "unit": "GDOF/s", "n_gpus": world,
         "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": "configs[1]: SolidMechanics NeoHookean H1 p=2 hex, beam-hex.mesh refined 4x "
-                               "(32768 hexes, 839619 vdofs, 884736 qpts) per GPU; step = residual with derivative store "
-                               "+ one Jacobian action", "vdofs_per_gpu": P["vdofs"], "qpts_per_gpu": P["nq"],
+        "config": {"workload": "configs[1]: SolidMechanics NeoHookean H1 p=2 hex, 32768 hexes / ~840k vdofs / 884736 "
+                               "qpts per GPU; step = residual with derivative store + one Jacobian action",
+                   "mesh": P["mesh"], "vdofs_total": vdofs_total, "vdofs_per_gpu": P["vdofs"],
+                   "qpts_per_gpu": P["nq"],
                    "l2_policy": "inputs larger than L2 (573 MB stored derivatives streamed each step)",
-                   "step_launch": "kernel by kernel" if args.no_graph else "CUDA graph replay", "parallelism": f"1 partition per GPU x{world}"},
+                   "step_launch": "CUDA graph replay" if use_graph else "kernel by kernel",
+                   "parallelism": f"1 mesh partition per GPU x{world}"
+                                  + (f", shared-dof exchange over {P['transport']}" if world > 1 else "")},
         "e2e": {"value": vdofs_total / e2e_s / 1e9, "unit": "GDOF/s",
-                "h2d_bytes_per_step": int(8 * (3 * P["vdofs"] + P["G_shape"].LSize())),
-                "d2h_bytes_per_step": int(8 * 2 * P["vdofs"]), "ms_per_step": e2e_s * 1e3},
+                "h2d_bytes_per_step": int(8 * (3 * vdofs_total + shape_total)),
+                "d2h_bytes_per_step": int(8 * 2 * vdofs_total), "ms_per_step": e2e_s * 1e3},
         "gpu_launches": int(launches_per_step * args.steps),
         "phases_ms": {"evaluate_with_derivative_store": phase_ms[0], "scatter_r": phase_ms[1], "jvp": phase_ms[2],
                       "scatter_dr": phase_ms[3]},
-        "roofline": {"kernel": "jvp_kernel<3,3,3,3,3,3,8>", "bound": "hbm", "achieved": achieved, "peak": peak,
-                     "unit": "GB/s", "frac": achieved / peak, "peak_source": peak_src,
-                     "algorithmic_bytes_per_launch": jvp_bytes, "traffic": None},
+        "qpts_per_s": P["nq"] * world / (ms_per_step * 1e-3),
+        "roofline": {"kernel": "jvp_stream_kernel<3,3,3,3,3,3,8,*>", "bound": "hbm", "achieved": achieved,
+                     "peak": peak, "unit": "GB/s", "frac": achieved / peak, "peak_source": peak_src,
+                     "algorithmic_bytes_per_launch": jvp_bytes, "traffic": JVP_NCU_TRAFFIC_BYTES},
+        "roofline_evaluate": {"kernel": "evaluation_kernel<wrt=1>", "bound": "hbm",
+                              "achieved": eval_bytes / (phase_ms[0] * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
+                              "frac": eval_bytes / (phase_ms[0] * 1e-3) / 1e9 / peak,
+                              "algorithmic_bytes_per_launch": eval_bytes, "traffic": EVAL_NCU_TRAFFIC_BYTES},
         "clocks": clocks,
     }
-    if args.gpus == 1 and not args.no_cpu_baseline:
+    if halo_ms is not None:
+        out["phases_ms"]["halo_exchange_3P_1Pt"] = halo_ms
+    if args.gpus == 1 and world == 1 and not args.no_cpu_baseline:
         out["cpu_baseline"] = cpu_baseline_sample()
     print(json.dumps(out))
 
