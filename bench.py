@@ -32,9 +32,9 @@ METRIC = "GDOF/s Functional residual + Jacobian action (p=2 hex)"
 CONFIG_A = os.path.join(ROOT, "tests", "golden", "config_a_beam_hex_r4_p2.npz")
 NEOHOOKEAN = [1.0, 100.0, 50.0, 1.0]  # density, K, G, geometric nonlinearity on (BASELINE.md §2 probe values)
 # dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed `ncu --set full` capture of this command
-# (profiles/r1_ncu_full_summary.md); None until captured
-JVP_NCU_TRAFFIC_BYTES = None
-EVAL_NCU_TRAFFIC_BYTES = None
+# (profiles/r1_ncu_full_summary.md)
+JVP_NCU_TRAFFIC_BYTES = 606.6e6   # 583.8 MB read + 22.8 MB written
+EVAL_NCU_TRAFFIC_BYTES = 621.7e6  # 83.3 MB read + 538.4 MB written (rest of the 573 MB store still in L2)
 
 
 # ---------------------------------------------------------------------------------------------------------------------
@@ -240,8 +240,9 @@ def run_product(args):
     rL = torch.empty(P["vdofs"], dtype=torch.float64, device=dev)
     fields = [P["G_shape"].field(SL), G.field(UL), G.field(AL)]
     du_field = G.field(dUL)
-    ev = [[torch.cuda.Event(enable_timing=True) for _ in range(5)] for _ in range(args.steps)]
-    for k in range(args.steps):
+    psteps = min(args.steps, 200)
+    ev = [[torch.cuda.Event(enable_timing=True) for _ in range(5)] for _ in range(psteps)]
+    for k in range(psteps):
         ev[k][0].record()
         integral.Mult(0.0, fields, r_E, wrt=1)
         ev[k][1].record()
@@ -252,20 +253,20 @@ def run_product(args):
         G.Scatter(r_E, rL)
         ev[k][4].record()
     torch.cuda.synchronize()
-    phase_ms = [float(np.mean([ev[k][i].elapsed_time(ev[k][i + 1]) for k in range(args.steps)])) for i in range(4)]
+    phase_ms = [float(np.mean([ev[k][i].elapsed_time(ev[k][i + 1]) for k in range(psteps)])) for i in range(4)]
     halo_ms = None
     if world > 1:  # the exchange alone: P of the three inputs + P^T of the output, as in one evaluation
         dist.barrier()
         h0, h1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         h0.record()
-        for _ in range(args.steps):
+        for _ in range(psteps):
             P["halo1"].P(S, SL)
             P["halo"].P(U, UL)
             P["halo"].P(A, AL)
             P["halo"].Pt(rL, r)
         h1.record()
         torch.cuda.synchronize()
-        halo_ms = h0.elapsed_time(h1) / args.steps
+        halo_ms = h0.elapsed_time(h1) / psteps
         dist.barrier()
         # restore the outputs the sanity check below compares against
         step_device()
@@ -452,8 +453,8 @@ def run_reference(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=50)
-    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=1000)
+    ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="launch the step kernel by kernel (for ncu captures)")

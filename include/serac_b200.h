@@ -86,6 +86,9 @@ int sb_restriction_scatter(sb_restriction_t r, const double* E_dev, double* L_de
 /* ---------------------------------------------------------------------------------------------------------------
  * GeometricFactors  (F/geometric_factors.cpp:16-138)
  * X_q_dev: [ne][sdim][nq]; J_q_dev: [ne][gdim][sdim][nq] with J(j,i,q) = dX_i/dxi_j.
+ * sdim = the restriction's component count: gdim for domain elements, gdim + 1 for the boundary faces of a boundary
+ * integral (the FaceType::BOUNDARY constructor, F/geometric_factors.cpp:140-220; pass the face restriction of the mesh
+ * nodes space, built from fes->GetFaceDofs with geom = the face geometry).
  * nodes_L_dev: mesh nodes L-vector (vdim = spatial dim) restricted by `mesh_restriction`.
  * elements_dev: the domain's element ids (NULL = all elements 0..ne-1).
  * ------------------------------------------------------------------------------------------------------------- */
@@ -160,6 +163,7 @@ typedef struct {
   sb_elem_grad_launcher element_gradient[SB_MAX_TRIALS];
   int derivative_mask[SB_MAX_TRIALS];    /* bit b: block b of {d00,d01,d10,d11} present */
   int derivative_entries[SB_MAX_TRIALS]; /* doubles stored per quadrature point */
+  int spatial_dim; /* == dim for domain integrals; dim + 1 for boundary integrals (geom = the face geometry) */
 } sb_kernel_table;
 
 int         sb_named_integrand_count(void);
@@ -208,6 +212,12 @@ int     sb_csr_pattern_to_host(sb_csr_t A, int* row_ptr_host, int* col_ind_host)
 /* values[nz] = sum over the contributing K_e entries in ascending (element, i, j) order (deterministic gather;
  * F/functional.hpp:610-644 does the same sums with one hash lookup per entry). values_dev is overwritten. */
 int sb_csr_assemble(sb_csr_t A, const double* K_e_dev, double* values_dev, void* stream);
+/* values[nz] += element matrices living on another pair of restrictions of the same spaces -- the boundary faces
+ * (F/functional.hpp:610-644 loops over Domain::Type::BoundaryElements after Elements with the same lookup table).
+ * K_e_dev: [faces][trial vdofs][test vdofs]; ordered (ascending face, i, j) per nonzero, no atomics.  Fails if a face
+ * dof pair is not in the pattern (the reference's nz_LUT lookup would throw). */
+int sb_csr_accumulate(sb_csr_t A, sb_restriction_t test_faces, sb_restriction_t trial_faces, const double* K_e_dev,
+                      double* values_dev, void* stream);
 
 /* ---------------------------------------------------------------------------------------------------------------
  * Functional orchestration  (F/functional.hpp:406-513): P -> gather -> integrals -> scatter-add -> P^T at one rank
@@ -218,6 +228,12 @@ int sb_functional_destroy(sb_functional_t F);
 /* AddDomainIntegral (F/functional.hpp:286-317): trial_indices[i] = which Functional argument feeds the integral's
  * i-th trial (the DependsOn<...> list) */
 int sb_functional_add_integral(sb_functional_t F, sb_integral_t I, const int* trial_indices);
+/* AddBoundaryIntegral (F/functional.hpp:328-354).  The integral was created from a boundary kernel table
+ * (spatial_dim == dim + 1) with the geometric factors of the boundary faces.  test_faces / trial_faces[i]: the
+ * FaceType::BOUNDARY element restrictions (F/element_restriction.cpp:279-388,406-419) of the test space and of the space
+ * feeding the integral's i-th trial: dof_info from sb_h1_lexicographic_dof_info(face geometry, p, fes->GetFaceDofs ...). */
+int sb_functional_add_boundary_integral(sb_functional_t F, sb_integral_t I, const int* trial_indices,
+                                        sb_restriction_t test_faces, const sb_restriction_t* trial_faces);
 /* operator()(t, args...) (F/functional.hpp:446-513).  inputs: one L-vector per trial space.  *_on_host != 0 means the
  * pointers are host buffers: they are copied to / from the device inside the call (synchronous). */
 int sb_functional_evaluate(sb_functional_t F, double t, int wrt, const double* const* inputs, int inputs_on_host,

@@ -105,6 +105,67 @@ def reference_problem(mesh_spec, kind, p, params, vdim, seed=42, with_matrix=Tru
     return out
 
 
+def reference_boundary_problem(mesh_spec, kind, p, params, seed=42, shape_amp=0.0, u_amp=0.01):
+    """One reference BOUNDARY Integral (MakeBoundaryIntegral, integral.hpp:322-350) on EntireBoundary(mesh) with the
+    SolidMechanics signature H1<p,dim>(shape H1<1,dim>, u, a): inputs (native face dofs of every space, mesh nodes) and
+    the reference's outputs (face dof_info, face geometric factors, residual, JVPs, face element matrices and their
+    contribution to the CSR values of the domain pattern)."""
+    mesh = make_mesh(mesh_spec)
+    dim = mesh.dim
+    tag = f"{dim}d_p{p}"
+    space, shape_space = ref.Space(mesh, p, dim), ref.Space(mesh, 1, dim)
+    fspace, fshape = ref.FaceSpace(space), ref.FaceSpace(shape_space)
+    rng = np.random.default_rng(seed)
+    U = u_amp * rng.uniform(-1.0, 1.0, space.vsize)
+    A = rng.uniform(-1.0, 1.0, space.vsize)
+    S = shape_amp * rng.uniform(-1.0, 1.0, shape_space.vsize)
+    dU = rng.uniform(0.0, 1.0, space.vsize)
+    dS = rng.uniform(0.0, 1.0, shape_space.vsize)
+    q = p + 1
+    order, ordering, nodes, nodes_info = mesh.nodes()
+    mesh_face_native, mesh_face_info = mesh.nodes_face_tables()
+    X_q, J_q = mesh.boundary_geometric_factors(q)
+    I = ref.Integral(f"{kind}_{tag}", mesh, params, boundary=True)
+    out = dict(
+        kind=kind, geom=mesh.geom, face_geom=mesh.face_geom, dim=dim, p=p, vdim=dim, ne=mesh.ne, nf=fspace.nf,
+        params=np.asarray(params, dtype=np.float64),
+        native_dofs=space.native_dofs(), num_nodes=space.num_nodes, shape_num_nodes=shape_space.num_nodes,
+        face_native_dofs=fspace.native_dofs(), face_dof_info=fspace.dof_info(),
+        shape_face_native_dofs=fshape.native_dofs(), shape_face_dof_info=fshape.dof_info(),
+        mesh_order=order, mesh_ordering=ordering, mesh_nodes=nodes, mesh_num_nodes=len(nodes) // dim,
+        mesh_face_native_dofs=mesh_face_native, mesh_face_dof_info=mesh_face_info,
+        U=U, A=A, S=S, dU=dU, dS=dS, X_q=X_q, J_q=J_q,
+    )
+    ins = [fshape.gather(S), fspace.gather(U), fspace.gather(A)]
+    r_E = I.mult(0.0, ins, fspace.esize)
+    out["r_E"] = r_E
+    out["r"] = fspace.scatter_add(r_E, np.zeros(space.vsize))
+    out["r_E_ad"] = I.mult(0.0, ins, fspace.esize, wrt=1)
+    out["dr"] = fspace.scatter_add(I.jvp(1, fspace.gather(dU), fspace.esize), np.zeros(space.vsize))
+    I.mult(0.0, ins, fspace.esize, wrt=0)
+    out["dr_dshape"] = fspace.scatter_add(I.jvp(0, fshape.gather(dS), fspace.esize), np.zeros(space.vsize))
+    I.mult(0.0, ins, fspace.esize, wrt=1)
+    npe = fspace.dof_info().shape[1]
+    K_e = I.element_gradient(1, fspace.nf, npe * dim, npe * dim)
+    out["K_e"] = K_e
+    csr = ref.Csr(space, space)
+    rp, ci = csr.pattern()
+    out["row_ptr"], out["col_ind"] = rp, ci
+    out["values"] = csr.assemble_faces(K_e, np.zeros(csr.nnz))
+    return out
+
+
+BOUNDARY_FIXTURES = [
+    # follower pressure on the current configuration: depends on u, so d/du is non-zero (setPressure)
+    ("solid_pressure_hex_p2_cart", dict(mesh_spec=("cart3d", 2, 1, 2, 0.02), kind="solid_pressure", p=2,
+                                        params=[3.0, 1.0], shape_amp=0.01)),
+    ("solid_pressure_hex_p1_patch", dict(mesh_spec=("file", "patch3D_hexes.mesh", 0), kind="solid_pressure", p=1,
+                                         params=[-1.5, 1.0], shape_amp=0.01)),
+    # dead traction: only the shape derivative is non-zero (setTraction)
+    ("solid_traction_hex_p2_cart", dict(mesh_spec=("cart3d", 2, 2, 1, 0.02), kind="solid_traction", p=2,
+                                        params=[0.3, -1.0, 2.0], shape_amp=0.01)),
+]
+
 # (file name, kwargs of reference_problem)
 FIXTURES = [
     ("solid_neohookean_hex_p2_patch", dict(mesh_spec=("file", "patch3D_hexes.mesh", 0), kind="solid_neohookean", p=2,
@@ -164,6 +225,15 @@ def main():
         path = os.path.join(GOLDEN_DIR, name + ".npz")
         np.savez_compressed(path, **data)
         print(f"{name}: ne={data['ne']} vsize={len(data['U'])} -> {os.path.getsize(path) / 1024:.0f} KiB")
+    for name, kw in BOUNDARY_FIXTURES:
+        if only and name not in only:
+            continue
+        data = reference_boundary_problem(**kw)
+        path = os.path.join(GOLDEN_DIR, "bdr_" + name + ".npz")
+        np.savez_compressed(path, **data)
+        print(f"{name}: faces={data['nf']} vsize={len(data['U'])} |r|={np.linalg.norm(data['r']):.3e} "
+              f"|dr|={np.linalg.norm(data['dr']):.3e} |dr_dshape|={np.linalg.norm(data['dr_dshape']):.3e} -> "
+              f"{os.path.getsize(path) / 1024:.0f} KiB")
 
 
 if __name__ == "__main__":

@@ -49,6 +49,15 @@ def lib():
             "ref_space_gather": (None, [vp, i, vp, vp]),
             "ref_space_scatter_add": (None, [vp, i, vp, vp]),
             "ref_lex_perm": (i, [i, i, vp]),
+            "ref_space_face_native_dofs": (l, [vp, i, vp]),
+            "ref_space_face_dof_info": (l, [vp, i, vp]),
+            "ref_space_face_esize": (l, [vp, i]),
+            "ref_space_face_gather": (None, [vp, i, vp, vp]),
+            "ref_space_face_scatter_add": (None, [vp, i, vp, vp]),
+            "ref_mesh_nodes_face_dof_info": (l, [vp, i, vp]),
+            "ref_mesh_nodes_face_native_dofs": (l, [vp, i, vp]),
+            "ref_boundary_geometric_factors": (l, [vp, i, i, vp, vp]),
+            "ref_csr_assemble_faces": (None, [vp, vp, vp, i, vp, vp]),
             "ref_geometric_factors": (None, [vp, i, i, vp, vp]),
             "ref_csr_create": (vp, [vp, vp]),
             "ref_csr_destroy": (None, [vp]),
@@ -113,6 +122,33 @@ class Mesh:
         L.ref_mesh_nodes_dof_info(self.h, self.geom, _p(info))
         return L.ref_mesh_nodes_order(self.h), L.ref_mesh_nodes_ordering(self.h), x, info.reshape(self.ne, -1)
 
+    @property
+    def face_geom(self):
+        return GEOM["quad"] if self.dim == 3 else GEOM["segment"]
+
+    def num_boundary_faces(self):
+        return lib().ref_boundary_geometric_factors(self.h, 1, self.face_geom, None, None)
+
+    def boundary_geometric_factors(self, q):
+        """GeometricFactors(EntireBoundary, q, face_geom, FaceType::BOUNDARY): X [nf][sdim][nq], J [nf][gdim][sdim][nq]"""
+        nf, gd = self.num_boundary_faces(), self.dim - 1
+        nq = q**gd
+        X = np.empty((nf, self.dim, nq))
+        J = np.empty((nf, gd, self.dim, nq))
+        lib().ref_boundary_geometric_factors(self.h, q, self.face_geom, _p(X), _p(J))
+        return X, J
+
+    def nodes_face_tables(self):
+        """(native face dofs, dof_info) of the mesh-nodes space on the boundary faces"""
+        L, g = lib(), self.face_geom
+        n = L.ref_mesh_nodes_face_native_dofs(self.h, g, None)
+        nat = np.empty(n, dtype=np.int32)
+        L.ref_mesh_nodes_face_native_dofs(self.h, g, _p(nat))
+        info = np.empty(L.ref_mesh_nodes_face_dof_info(self.h, g, None), dtype=np.uint64)
+        L.ref_mesh_nodes_face_dof_info(self.h, g, _p(info))
+        nf = self.num_boundary_faces()
+        return nat.reshape(nf, -1), info.reshape(nf, -1)
+
     def geometric_factors(self, q):
         nq = q**self.dim
         X = np.empty((self.ne, self.dim, nq))
@@ -152,6 +188,36 @@ class Space:
         return Lvec
 
 
+class FaceSpace:
+    """the FaceType::BOUNDARY ElementRestriction of a Space (element_restriction.cpp:406-419)"""
+
+    def __init__(self, space):
+        self.space, self.geom = space, space.mesh.face_geom
+        self.nf = space.mesh.num_boundary_faces()
+        self.esize = lib().ref_space_face_esize(space.h, self.geom)
+
+    def native_dofs(self):
+        n = lib().ref_space_face_native_dofs(self.space.h, self.geom, None)
+        out = np.empty(n, dtype=np.int32)
+        lib().ref_space_face_native_dofs(self.space.h, self.geom, _p(out))
+        return out.reshape(self.nf, -1)
+
+    def dof_info(self):
+        n = lib().ref_space_face_dof_info(self.space.h, self.geom, None)
+        out = np.empty(n, dtype=np.uint64)
+        lib().ref_space_face_dof_info(self.space.h, self.geom, _p(out))
+        return out.reshape(self.nf, -1)
+
+    def gather(self, Lvec):
+        E = np.empty(self.esize)
+        lib().ref_space_face_gather(self.space.h, self.geom, _p(np.ascontiguousarray(Lvec)), _p(E))
+        return E
+
+    def scatter_add(self, E, Lvec):
+        lib().ref_space_face_scatter_add(self.space.h, self.geom, _p(np.ascontiguousarray(E)), _p(Lvec))
+        return Lvec
+
+
 def lex_perm(geom, p):
     out = np.empty(64, dtype=np.int32)
     n = lib().ref_lex_perm(geom, p, _p(out))
@@ -178,6 +244,13 @@ class Csr:
         return vals
 
 
+    def assemble_faces(self, K_e, values):
+        """+= boundary-face element matrices (functional.hpp:610-644, Domain::Type::BoundaryElements)"""
+        lib().ref_csr_assemble_faces(self.h, self.test.h, self.trial.h, self.test.mesh.face_geom,
+                                     _p(np.ascontiguousarray(K_e)), _p(values))
+        return values
+
+
 def kinds():
     return [lib().ref_kind_name(i).decode() for i in range(lib().ref_num_kinds())]
 
@@ -185,13 +258,13 @@ def kinds():
 class Integral:
     """One reference Integral (integral.hpp:24) on the entire mesh; E-vector level API."""
 
-    def __init__(self, kind, mesh, params):
+    def __init__(self, kind, mesh, params, boundary=False):
         params = np.ascontiguousarray(params, dtype=np.float64)
         self.h = lib().ref_integral_create(kind.encode(), mesh.h, _p(params), len(params))
         if not self.h:
             raise KeyError(kind)
         self.mesh = mesh
-        self.geom = mesh.geom
+        self.geom = mesh.face_geom if boundary else mesh.geom
 
     def mult(self, t, inputs_E, out_size, wrt=-1, update_state=False):
         ins = [np.ascontiguousarray(a, dtype=np.float64) for a in inputs_E]

@@ -150,6 +150,120 @@ int ref_lex_perm(int geom, int p, int* out)
   return int(v.size());
 }
 
+struct Csr {
+  serac::GradientAssemblyLookupTables lut;
+};
+
+// ---- boundary faces: ElementRestriction(fes, face_geom, FaceType::BOUNDARY) (element_restriction.cpp:279-388,406-419)
+/// raw mfem face dofs (fes->GetFaceDofs) of the boundary faces of one geometry, in face order: the INPUT the product's
+/// lexicographic permutation is applied to
+long ref_space_face_native_dofs(void* s, int face_geom, int* out)
+{
+  auto* fes  = static_cast<Space*>(s)->fes.get();
+  auto* mesh = fes->GetMesh();
+  long  n    = 0;
+  for (int f = 0; f < fes->GetNF(); f++) {
+    if (mesh->GetFaceGeometry(f) != mfem::Geometry::Type(face_geom)) continue;
+    if (mesh->GetFaceInformation(f).IsInterior()) continue;
+    mfem::Array<int> dofs;
+    fes->GetFaceDofs(f, dofs);
+    for (int k = 0; k < dofs.Size(); k++) {
+      if (out) out[n] = dofs[k];
+      n++;
+    }
+  }
+  return n;
+}
+long ref_space_face_dof_info(void* s, int face_geom, uint64_t* out)
+{
+  serac::ElementRestriction r(static_cast<Space*>(s)->fes.get(), mfem::Geometry::Type(face_geom),
+                              FaceType::BOUNDARY);
+  const long n = long(r.num_elements * r.nodes_per_elem);
+  if (out) std::memcpy(out, r.dof_info.data(), sizeof(uint64_t) * size_t(n));
+  return n;
+}
+long ref_space_face_esize(void* s, int face_geom)
+{
+  serac::ElementRestriction r(static_cast<Space*>(s)->fes.get(), mfem::Geometry::Type(face_geom),
+                              FaceType::BOUNDARY);
+  return long(r.ESize());
+}
+void ref_space_face_gather(void* s, int face_geom, const double* L, double* E)
+{
+  serac::ElementRestriction r(static_cast<Space*>(s)->fes.get(), mfem::Geometry::Type(face_geom),
+                              FaceType::BOUNDARY);
+  mfem::Vector Lv(const_cast<double*>(L), int(r.LSize())), Ev(E, int(r.ESize()));
+  r.Gather(Lv, Ev);
+}
+void ref_space_face_scatter_add(void* s, int face_geom, const double* E, double* L)
+{
+  serac::ElementRestriction r(static_cast<Space*>(s)->fes.get(), mfem::Geometry::Type(face_geom),
+                              FaceType::BOUNDARY);
+  mfem::Vector Lv(L, int(r.LSize())), Ev(const_cast<double*>(E), int(r.ESize()));
+  r.ScatterAdd(Ev, Lv);
+}
+long ref_mesh_nodes_face_dof_info(void* m, int face_geom, uint64_t* out)
+{
+  auto* fes = static_cast<mfem::Mesh*>(m)->GetNodes()->FESpace();
+  serac::ElementRestriction r(fes, mfem::Geometry::Type(face_geom), FaceType::BOUNDARY);
+  const long n = long(r.num_elements * r.nodes_per_elem);
+  if (out) std::memcpy(out, r.dof_info.data(), sizeof(uint64_t) * size_t(n));
+  return n;
+}
+long ref_mesh_nodes_face_native_dofs(void* m, int face_geom, int* out)
+{
+  auto* mesh = static_cast<mfem::Mesh*>(m);
+  auto* fes  = mesh->GetNodes()->FESpace();
+  long  n    = 0;
+  for (int f = 0; f < fes->GetNF(); f++) {
+    if (mesh->GetFaceGeometry(f) != mfem::Geometry::Type(face_geom)) continue;
+    if (mesh->GetFaceInformation(f).IsInterior()) continue;
+    mfem::Array<int> dofs;
+    fes->GetFaceDofs(f, dofs);
+    for (int k = 0; k < dofs.Size(); k++) {
+      if (out) out[n] = dofs[k];
+      n++;
+    }
+  }
+  return n;
+}
+/// GeometricFactors(domain, q, face_geom, FaceType::BOUNDARY) on EntireBoundary(mesh) (geometric_factors.cpp:140-220)
+long ref_boundary_geometric_factors(void* m, int q, int face_geom, double* X, double* J)
+{
+  auto*                   mesh = static_cast<mfem::Mesh*>(m);
+  serac::Domain           d    = serac::EntireBoundary(*mesh);
+  serac::GeometricFactors gf(d, q, mfem::Geometry::Type(face_geom), FaceType::BOUNDARY);
+  if (X) std::memcpy(X, gf.X.GetData(), sizeof(double) * size_t(gf.X.Size()));
+  if (J) std::memcpy(J, gf.J.GetData(), sizeof(double) * size_t(gf.J.Size()));
+  return long(gf.num_elements);
+}
+/// scatter of boundary-face element matrices into CSR values as Gradient::assemble does for
+/// Domain::Type::BoundaryElements (functional.hpp:610-644); accumulates into `values`
+void ref_csr_assemble_faces(void* c, void* test_space, void* trial_space, int face_geom, const double* K_e,
+                            double* values)
+{
+  auto& lut = static_cast<Csr*>(c)->lut;
+  serac::ElementRestriction test(static_cast<Space*>(test_space)->fes.get(), mfem::Geometry::Type(face_geom),
+                                 FaceType::BOUNDARY);
+  serac::ElementRestriction trial(static_cast<Space*>(trial_space)->fes.get(), mfem::Geometry::Type(face_geom),
+                                  FaceType::BOUNDARY);
+  std::vector<DoF> test_vdofs(test.nodes_per_elem * test.components);
+  std::vector<DoF> trial_vdofs(trial.nodes_per_elem * trial.components);
+  const size_t nrow = test_vdofs.size(), ncol = trial_vdofs.size();
+  for (uint64_t e = 0; e < test.num_elements; e++) {
+    test.GetElementVDofs(int(e), test_vdofs);
+    trial.GetElementVDofs(int(e), trial_vdofs);
+    for (size_t i = 0; i < ncol; i++) {
+      int col = int(trial_vdofs[i].index());
+      for (size_t j = 0; j < nrow; j++) {
+        int row  = int(test_vdofs[j].index());
+        int sign = test_vdofs[j].sign() * trial_vdofs[i].sign();
+        values[lut(row, col)] += sign * K_e[(e * ncol + i) * nrow + j];
+      }
+    }
+  }
+}
+
 // ---- GeometricFactors (geometric_factors.cpp:62-138) ----
 void ref_geometric_factors(void* m, int q, int geom, double* X, double* J)
 {
@@ -161,9 +275,6 @@ void ref_geometric_factors(void* m, int q, int geom, double* X, double* J)
 }
 
 // ---- sparsity pattern (dof_numbering.hpp:290-351) ----
-struct Csr {
-  serac::GradientAssemblyLookupTables lut;
-};
 void* ref_csr_create(void* test_space, void* trial_space)
 {
   auto* c = new Csr;

@@ -152,4 +152,66 @@ ref::Registrar r4("thermal_linear_conductor_" TAG, [](mfem::Mesh& mesh, const do
   return h;
 });
 
+#if REF_DIM == 3
+// ---- boundary integrands (faces of the 3D mesh) -------------------------------------------------------------------
+// functor shells restating ShapeAwareFunctional::ShapeAwareBoundaryIntegrandWrapper (shape_aware_functional.hpp:474-499)
+// and the lambdas of SolidMechanics::setTraction / setPressure (solid_mechanics.hpp:1030-1036, 1075-1101) with a
+// constant traction vector / pressure; compute_boundary_area_correction is the reference's.
+template <typename Integrand>
+struct ShapeAwareBoundary {
+  Integrand integrand_;
+  template <typename Pos, typename Shape, typename... Args>
+  auto operator()(double time, Pos x, Shape shape_val, Args... args) const
+  {
+    auto unmodified_qf_return = integrand_(time, x + shape_val, args...);
+    return unmodified_qf_return * serac::detail::compute_boundary_area_correction(x, shape_val);
+  }
+};
+
+struct UniformTractionIntegrand {
+  tensor<double, dim> traction_;
+  template <typename X, typename U, typename A>
+  auto operator()(double, X x, U, A) const
+  {
+    auto n = cross(get<DERIVATIVE>(x));
+    (void)normalize(n);  // the reference hands normalize(n) to the traction function, which ignores it here
+    return -1.0 * traction_;
+  }
+};
+
+struct UniformPressureIntegrand {
+  double pressure_;
+  bool   geom_nonlin_;
+  template <typename X, typename U, typename A>
+  auto operator()(double, X Xref, U displacement, A) const
+  {
+    auto x = Xref + 0.0 * displacement;
+    if (geom_nonlin_) {
+      x = x + displacement;
+    }
+    auto n = cross(get<DERIVATIVE>(x));
+    return pressure_ * (n / norm(cross(get<DERIVATIVE>(Xref))));
+  }
+};
+
+template <typename QF>
+ref::IntegralHolder make_boundary(mfem::Mesh& mesh, QF qf)
+{
+  ref::IntegralHolder h;
+  Domain d     = EntireBoundary(mesh);
+  h.integral   = std::make_unique<Integral>(MakeBoundaryIntegral<solid_sig, p + 1, dim - 1>(d, qf, {0, 1, 2}));
+  h.num_trials = 3;
+  return h;
+}
+
+ref::Registrar r5("solid_traction_" TAG, [](mfem::Mesh& mesh, const double* q, int n) {
+  SLIC_ERROR_IF(n != 3, "params: tx ty tz");
+  return make_boundary(mesh, ShapeAwareBoundary<UniformTractionIntegrand>{UniformTractionIntegrand{{{q[0], q[1], q[2]}}}});
+});
+ref::Registrar r6("solid_pressure_" TAG, [](mfem::Mesh& mesh, const double* q, int n) {
+  SLIC_ERROR_IF(n != 2, "params: pressure geom_nonlin");
+  return make_boundary(mesh, ShapeAwareBoundary<UniformPressureIntegrand>{UniformPressureIntegrand{q[0], q[1] != 0.0}});
+});
+#endif
+
 }  // namespace

@@ -31,7 +31,7 @@ class KernelTable(C.Structure):
         ("qf_bytes", _sz), ("state_bytes", _sz), ("elements_per_block", _i),
         ("evaluate", _vp), ("evaluate_ad", _vp * MAX_TRIALS), ("jvp", _vp * MAX_TRIALS),
         ("element_gradient", _vp * MAX_TRIALS),
-        ("derivative_mask", _i * MAX_TRIALS), ("derivative_entries", _i * MAX_TRIALS),
+        ("derivative_mask", _i * MAX_TRIALS), ("derivative_entries", _i * MAX_TRIALS), ("spatial_dim", _i),
     ]
 
 
@@ -72,7 +72,9 @@ SIGNATURES = {
     "sb_csr_pattern_dev": (_i, [_vp, _pp, _pp]),
     "sb_csr_pattern_to_host": (_i, [_vp, _vp, _vp]),
     "sb_csr_assemble": (_i, [_vp, _vp, _vp, _vp]),
+    "sb_csr_accumulate": (_i, [_vp, _vp, _vp, _vp, _vp, _vp]),
     "sb_functional_create": (_i, [_vp, _i, _pp, _pp]),
+    "sb_functional_add_boundary_integral": (_i, [_vp, _vp, _vp, _vp, _pp]),
     "sb_functional_destroy": (_i, [_vp]),
     "sb_functional_add_integral": (_i, [_vp, _vp, _vp]),
     "sb_functional_evaluate": (_i, [_vp, _d, _i, _pp, _i, _vp, _i, _i, _vp]),
@@ -201,10 +203,11 @@ def geometric_factors(geom, mesh_order, q, mesh_restriction, nodes_L, num_elemen
     """GeometricFactors (geometric_factors.cpp:62-138) -> (X_q [ne][dim][nq], J_q [ne][dim][dim][nq]) on device."""
     import torch
     dim = 3 if geom == CUBE else 2
+    sdim = mesh_restriction.components  # == dim for domain elements, dim + 1 for the faces of a boundary integral
     ne = mesh_restriction.num_elements if num_elements is None else num_elements
     nq = q**dim
-    X = torch.empty((ne, dim, nq), dtype=torch.float64, device=nodes_L.device)
-    J = torch.empty((ne, dim, dim, nq), dtype=torch.float64, device=nodes_L.device)
+    X = torch.empty((ne, sdim, nq), dtype=torch.float64, device=nodes_L.device)
+    J = torch.empty((ne, dim, sdim, nq), dtype=torch.float64, device=nodes_L.device)
     check(lib().sb_geometric_factors(geom, mesh_order, q, mesh_restriction.h, _dev_ptr(nodes_L),
                                      _dev_ptr(elements), ne, _dev_ptr(X), _dev_ptr(J), _stream_ptr()))
     return X, J
@@ -326,6 +329,15 @@ class Functional:
         idx = np.ascontiguousarray(depends_on, dtype=np.int32)
         check(lib().sb_functional_add_integral(self.h, integral.h, _np_ptr(idx)))
         self.integrals.append(integral)
+
+    def AddBoundaryIntegral(self, integral, depends_on, test_faces, trial_faces):
+        """functional.hpp:328-354: test_faces / trial_faces[i] are the boundary-face ElementRestrictions of the test space
+        and of the space feeding the integral's i-th trial"""
+        idx = np.ascontiguousarray(depends_on, dtype=np.int32)
+        arr = (C.c_void_p * len(trial_faces))(*[r.h for r in trial_faces])
+        check(lib().sb_functional_add_boundary_integral(self.h, integral.h, _np_ptr(idx), test_faces.h, arr))
+        self.integrals.append(integral)
+        self._keep = getattr(self, "_keep", []) + [test_faces, list(trial_faces)]
 
     def __call__(self, t, inputs, wrt=NO_DIFFERENTIATION, out=None, update_state=False):
         """inputs: list of torch CUDA tensors (device path) or numpy arrays (host path, copies inside the call)."""

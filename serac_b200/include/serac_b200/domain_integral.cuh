@@ -448,10 +448,40 @@ struct SignatureT {
   static_assert(((trials::order + 1 <= Q) && ...), "quadrature rule must have at least p + 1 points per direction");
   static_assert(test::order + 1 <= Q, "quadrature rule must have at least p + 1 points per direction");
 
+  /// domain integral: the element lives in a space of its own dimension
+  static constexpr bool boundary = false;
+  static constexpr int  sdim     = dim;
 };
 
 template <Geometry geom, int Q, typename test, typename... trials>
 using Signature = SignatureT<geom, Q, 0, test, trials...>;
+
+/// boundary integral (boundary_integral_kernels.hpp:159-205): `geom` is the FACE geometry, embedded in sdim = dim + 1
+/// space dimensions.  X_q is [e][sdim][q], J_q is [e][dim][sdim][q]; the q-function sees tuple{x, dX/dxi (sdim x dim)},
+/// trial gradients stay in parent (xi) coordinates and its result is a source only, weighted by |dX/dxi_1 x dX/dxi_2|.
+template <Geometry geom, int Q, int EPB_, typename test, typename... trials>
+struct BoundarySignatureT : SignatureT<geom, Q, EPB_, test, trials...> {
+  static constexpr bool boundary = true;
+  static constexpr int  sdim     = dimension_of(geom) + 1;
+};
+template <Geometry geom, int Q, typename test, typename... trials>
+using BoundarySignature = BoundarySignatureT<geom, Q, 0, test, trials...>;
+
+/// first q-function argument after t: tuple{position, dX/dxi}
+template <typename Sig>
+using position_t = tuple<tensor<double, Sig::sdim>, tensor<double, Sig::sdim, Sig::dim>>;
+
+/// adapts a boundary q-function (returns the source term alone, boundary_integral_kernels.hpp:111-156) to the
+/// tuple{source, flux} convention of the evaluation kernel
+template <typename QF>
+struct BoundaryIntegrand {
+  QF qf;
+  template <typename... Args>
+  SERAC_HOST_DEVICE auto operator()(double t, const Args&... args) const
+  {
+    return serac::tuple{qf(t, args...), zero{}};
+  }
+};
 
 /// shared-memory plan of the evaluation kernel (doubles):
 ///   [tables: (NT + 1) x 2 x MAX_Q^2][gathered dofs of every trial field: EPB x c x ndof each][work: EPB x W]
@@ -716,7 +746,7 @@ template <typename Sig, int WRT, int PASS, typename QF, typename State, int ROWS
 auto pass_output_type(std::integer_sequence<int, I...>)
 {
   constexpr int dim = Sig::dim;
-  using pos_t       = tuple<tensor<double, dim>, tensor<double, dim, dim>>;
+  using pos_t       = position_t<Sig>;
   if constexpr (std::is_same_v<State, Nothing>) {
     return decltype(std::declval<QF>()(
         double{}, pos_t{},
@@ -736,7 +766,7 @@ template <typename Sig, typename QF, typename State, int... I>
 auto plain_output_type(std::integer_sequence<int, I...>)
 {
   constexpr int dim = Sig::dim;
-  using pos_t       = tuple<tensor<double, dim>, tensor<double, dim, dim>>;
+  using pos_t       = position_t<Sig>;
   if constexpr (std::is_same_v<State, Nothing>) {
     return decltype(std::declval<QF>()(
         double{}, pos_t{}, std::declval<typename qf_arg<typename Sig::template trial_space<I>, dim>::type>()...)){};
@@ -892,13 +922,14 @@ __global__ void __launch_bounds__(Sig::threads, MINB) evaluation_kernel(const __
   const int  elem  = P.elements ? P.elements[e] : e;
 
   // geometric factors of this quadrature point:  Jm(i,j) = dX_i/dxi_j = J_q[e](j,i,q)   (loads issued first)
-  tensor<double, dim>      x{};
-  tensor<double, dim, dim> Jm{};
+  constexpr int sdim = Sig::sdim;
+  tensor<double, sdim>      x{};
+  tensor<double, sdim, dim> Jm{};
   SB_UNROLL
-  for (int i = 0; i < dim; i++) {
-    x[i] = P.X_q[((long long)e * dim + i) * QPE + ql];
+  for (int i = 0; i < sdim; i++) {
+    x[i] = P.X_q[((long long)e * sdim + i) * QPE + ql];
     SB_UNROLL
-    for (int j = 0; j < dim; j++) Jm(i, j) = P.J_q[(((long long)e * dim + j) * dim + i) * QPE + ql];
+    for (int j = 0; j < dim; j++) Jm(i, j) = P.J_q[(((long long)e * dim + j) * sdim + i) * QPE + ql];
   }
 
   // --- L -> E gather of every trial field at once (element_restriction.cpp:443-454): all loads are issued before the
@@ -948,8 +979,17 @@ __global__ void __launch_bounds__(Sig::threads, MINB) evaluation_kernel(const __
     [&]<int... I>(std::integer_sequence<int, I...>) { (store_field(std::integral_constant<int, I>{}), ...); }
     (seq{});
   }
-  const auto   invJ = inv(Jm);
-  const double dv   = det(Jm);
+  // domain: parent <-> physical maps.  boundary: trial gradients stay in xi coordinates and the measure is the
+  // surface element |dX/dxi_1 x dX/dxi_2| (boundary_integral_kernels.hpp:148-152)
+  tensor<double, dim, dim> invJ;
+  double                   dv;
+  if constexpr (Sig::boundary) {
+    invJ = Identity<dim>();
+    dv   = norm(cross(Jm));
+  } else {
+    invJ = inv(Jm);
+    dv   = det(Jm);
+  }
   __syncthreads();
 
   // --- interpolate every trial field, stage by stage (hexahedron_H1.inl:169-228), then parent -> physical
@@ -1036,7 +1076,7 @@ __global__ void __launch_bounds__(Sig::threads, MINB) evaluation_kernel(const __
   }
   (seq{});
 
-  const auto pos = tuple<tensor<double, dim>, tensor<double, dim, dim>>{x, Jm};
+  const auto pos = position_t<Sig>{x, Jm};
 
   // quadrature weight of this point
   const BasisTable1D& tb = P.test_basis;

@@ -234,6 +234,7 @@ sb_kernel_table make_kernel_table()
   sb_kernel_table T{};
   T.geom            = int(Sig::geometry);
   T.dim             = Sig::dim;
+  T.spatial_dim     = Sig::sdim;
   T.q               = Sig::q;
   T.num_trials      = Sig::NT;
   T.test_order      = Sig::test_space::order;
@@ -250,6 +251,17 @@ sb_kernel_table make_kernel_table()
   T.elements_per_block = Sig::EPB;
   T.evaluate           = &launch_evaluate<Sig, -1, QF, State, 1, (MINB > 0 ? MINB : default_min_blocks<Sig>()), FAST>;
   return T;
+}
+
+/// kernel table of a boundary integral (MakeBoundaryIntegral, integral.hpp:322-350): QF is the user's boundary
+/// q-function `(t, tuple{x, dX/dxi}, tuple{value, d/dxi}...) -> source`; Sig is a BoundarySignature on the face geometry.
+/// The functor blob handed to sb_integral_create is the QF itself (BoundaryIntegrand<QF> has the same layout).
+template <typename Sig, typename QF, int ROWS_REQ = 1, int MINB = 0>
+sb_kernel_table make_boundary_kernel_table()
+{
+  static_assert(Sig::boundary, "make_boundary_kernel_table needs a BoundarySignature");
+  static_assert(sizeof(BoundaryIntegrand<QF>) == sizeof(QF), "adapter must not change the functor layout");
+  return make_kernel_table<Sig, BoundaryIntegrand<QF>, Nothing, ROWS_REQ, MINB, false>();
 }
 
 }  // namespace b200

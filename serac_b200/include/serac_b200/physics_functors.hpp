@@ -643,4 +643,92 @@ struct ShapeAwareIntegrandWrapperWithState {
   }
 };
 
+// ------------------------------------------------------------------------------------------------
+// boundary integrands (q-functions of AddBoundaryIntegral: `(t, tuple{x, dX/dxi}, tuple{value, d/dxi}...) -> source`)
+// ------------------------------------------------------------------------------------------------
+namespace detail {
+/// ratio of the shape-displaced surface element to the reference one (shape_aware_functional.hpp:155-174)
+template <typename position_type, typename shape_type>
+SERAC_HOST_DEVICE auto compute_boundary_area_correction(const position_type& X, const shape_type& shape)
+{
+  auto x_prime = X + shape;
+  auto n       = cross(get<DERIVATIVE>(x_prime));
+  return norm(n) / norm(cross(get<DERIVATIVE>(X)));
+}
+}  // namespace detail
+
+/// what ShapeAwareFunctional::AddBoundaryIntegral wraps every boundary integrand in
+/// (shape_aware_functional.hpp:474-499,515-520): argument 0 is the shape displacement
+template <typename Integrand>
+struct ShapeAwareBoundaryIntegrandWrapper {
+  SERAC_HOST_DEVICE ShapeAwareBoundaryIntegrandWrapper(Integrand integrand) : integrand_(integrand) {}
+  Integrand integrand_;
+
+  template <typename PositionType, typename ShapeValueType, typename... QFuncArgs>
+  SERAC_HOST_DEVICE auto operator()(double time, PositionType x, ShapeValueType shape_val,
+                                    QFuncArgs... qfunc_args) const
+  {
+    auto unmodified_qf_return = integrand_(time, x + shape_val, qfunc_args...);
+    return unmodified_qf_return * detail::compute_boundary_area_correction(x, shape_val);
+  }
+};
+
+/// the boundary q-function SolidMechanics::setTraction registers (solid_mechanics.hpp:1030-1036);
+/// traction_function(x, n, t) -> traction vector
+template <typename TractionType>
+struct TractionIntegrand {
+  SERAC_HOST_DEVICE TractionIntegrand(TractionType f) : traction_function(f) {}
+  TractionType traction_function;
+
+  template <typename X, typename Displacement, typename Acceleration, typename... Params>
+  SERAC_HOST_DEVICE auto operator()(double t, X x, Displacement /*displacement*/, Acceleration /*acceleration*/,
+                                    Params... params) const
+  {
+    auto n = cross(get<DERIVATIVE>(x));
+    return -1.0 * traction_function(get<VALUE>(x), normalize(n), t, params...);
+  }
+};
+
+/// the boundary q-function SolidMechanics::setPressure registers (solid_mechanics.hpp:1075-1101): follower load applied
+/// on the current configuration when geometric nonlinearities are on; pressure_function(x, t) -> scalar
+template <typename PressureType>
+struct PressureIntegrand {
+  SERAC_HOST_DEVICE PressureIntegrand(PressureType f, GeometricNonlinearities gn) : pressure_function(f), geom_nonlin(gn)
+  {
+  }
+  PressureType            pressure_function;
+  GeometricNonlinearities geom_nonlin;
+
+  template <typename X, typename Displacement, typename Acceleration, typename... Params>
+  SERAC_HOST_DEVICE auto operator()(double t, X Xref, Displacement displacement, Acceleration /*acceleration*/,
+                                    Params... params) const
+  {
+    auto x = Xref + 0.0 * displacement;
+    if (geom_nonlin == GeometricNonlinearities::On) {
+      x = x + displacement;
+    }
+    auto n = cross(get<DERIVATIVE>(x));
+    return pressure_function(get<VALUE>(Xref), t, params...) * (n / norm(cross(get<DERIVATIVE>(Xref))));
+  }
+};
+
+/// load functions for the named integrands: constant traction vector / constant pressure
+template <int dim>
+struct UniformTraction {
+  tensor<double, dim> traction;
+  template <typename X, typename N>
+  SERAC_HOST_DEVICE tensor<double, dim> operator()(const X&, const N&, double) const
+  {
+    return traction;
+  }
+};
+struct UniformPressure {
+  double pressure;
+  template <typename X>
+  SERAC_HOST_DEVICE double operator()(const X&, double) const
+  {
+    return pressure;
+  }
+};
+
 }  // namespace serac

@@ -14,7 +14,12 @@ KIND_TO_NAME = {5: "hex", 3: "quad"}
 def golden_names():
     """small fixtures with full reference outputs (the config_* files are full-size inputs + sampled outputs)"""
     names = sorted(os.path.splitext(os.path.basename(f))[0] for f in glob.glob(os.path.join(GOLDEN, "*.npz")))
-    return [n for n in names if not n.startswith("config_")]
+    return [n for n in names if not n.startswith("config_") and not n.startswith("bdr_")]
+
+
+def boundary_golden_names():
+    """boundary-integral fixtures (oracle/make_golden.py BOUNDARY_FIXTURES)"""
+    return sorted(os.path.splitext(os.path.basename(f))[0] for f in glob.glob(os.path.join(GOLDEN, "bdr_*.npz")))
 
 
 def load_golden(name):
@@ -74,3 +79,38 @@ class Product:
 
     def fields(self):
         return [self.G_shape.field(self.S), self.G.field(self.U), self.G.field(self.A)]
+
+
+class BoundaryProduct:
+    """The product objects for one boundary-integral parity problem (oracle.make_golden.reference_boundary_problem):
+    Functional H1<p,dim>(shape, u, a) with ONE boundary integral on EntireBoundary (functional.hpp:328-354)."""
+
+    def __init__(self, prob, device):
+        import torch
+        from serac_b200 import capi
+        self.capi, self.torch, self.prob, self.dev = capi, torch, prob, device
+        geom, fgeom, p, dim = int(prob["geom"]), int(prob["face_geom"]), int(prob["p"]), int(prob["dim"])
+        self.p, self.dim = p, dim
+        # domain restrictions: the Functional's spaces and the sparsity pattern (functional.hpp:582-583)
+        self.G = capi.ElementRestriction(capi.h1_dof_info(geom, p, prob["native_dofs"]), dim, int(prob["num_nodes"]))
+        # boundary-face restrictions built by the PRODUCT from mfem's native face dofs (fes->GetFaceDofs)
+        self.face_dof_info = capi.h1_dof_info(fgeom, p, prob["face_native_dofs"])
+        self.shape_face_dof_info = capi.h1_dof_info(fgeom, 1, prob["shape_face_native_dofs"])
+        self.Gf = capi.ElementRestriction(self.face_dof_info, dim, int(prob["num_nodes"]))
+        self.Gf_shape = capi.ElementRestriction(self.shape_face_dof_info, dim, int(prob["shape_num_nodes"]))
+        mesh_face_info = capi.h1_dof_info(fgeom, int(prob["mesh_order"]), prob["mesh_face_native_dofs"])
+        self.Gf_mesh = capi.ElementRestriction(mesh_face_info, dim, int(prob["mesh_num_nodes"]),
+                                               int(prob["mesh_ordering"]))
+        t = lambda a: torch.as_tensor(np.ascontiguousarray(a), dtype=torch.float64, device=device)
+        self.t = t
+        self.nodes = t(prob["mesh_nodes"])
+        self.X_q, self.J_q = capi.geometric_factors(fgeom, int(prob["mesh_order"]), p + 1, self.Gf_mesh, self.nodes)
+        name = f"{prob['kind']}_{KIND_TO_NAME[geom]}_p{p}"
+        self.integral = capi.Integral(name, prob["params"], self.X_q, self.J_q, int(prob["nf"]))
+        self.U, self.A, self.S, self.dU, self.dS = (t(prob[k]) for k in ("U", "A", "S", "dU", "dS"))
+        # shape space domain restriction is not needed by a boundary-only Functional: pass the face one
+        self.F = capi.Functional(self.G, [self.Gf_shape, self.G, self.G])
+        self.F.AddBoundaryIntegral(self.integral, [0, 1, 2], self.Gf, [self.Gf_shape, self.Gf, self.Gf])
+
+    def fields(self):
+        return [self.Gf_shape.field(self.S), self.Gf.field(self.U), self.Gf.field(self.A)]

@@ -7,7 +7,7 @@ import re
 import numpy as np
 import pytest
 
-from harness import ROOT, golden_names, load_golden
+from harness import ROOT, boundary_golden_names, golden_names, load_golden
 from oracle import functional_oracle as fo
 from serac_b200 import capi
 
@@ -45,6 +45,18 @@ def test_dof_info_matches_reference(name):
     prob = load_golden(name)
     info = capi.h1_dof_info(int(prob["geom"]), int(prob["p"]), prob["native_dofs"])
     assert np.array_equal(info, prob["dof_info"])
+
+
+@pytest.mark.parametrize("name", boundary_golden_names())
+def test_boundary_face_dof_info_matches_reference(name):
+    """GetFaceDofs for H1 (element_restriction.cpp:366-371): native face dofs through the face geometry's permutation"""
+    prob = load_golden(name)
+    fg, p = int(prob["face_geom"]), int(prob["p"])
+    assert np.array_equal(capi.h1_dof_info(fg, p, prob["face_native_dofs"]), prob["face_dof_info"])
+    assert np.array_equal(capi.h1_dof_info(fg, 1, prob["shape_face_native_dofs"]), prob["shape_face_dof_info"])
+    assert np.array_equal(capi.h1_dof_info(fg, int(prob["mesh_order"]), prob["mesh_face_native_dofs"]),
+                          prob["mesh_face_dof_info"])
+    assert "solid_pressure_hex_p2" in capi.named_integrands() and "solid_traction_hex_p1" in capi.named_integrands()
 
 
 def test_unknown_integrand_is_an_error():
