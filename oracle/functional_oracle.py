@@ -69,6 +69,144 @@ def basis_tables(p, q):
 
 
 # ----------------------------------------------------------------------------------------------------------------------
+# simplex rules and nodal bases (F/polynomials.hpp:57-260, 285-365; F/detail/triangle_H1.inl, tetrahedron_H1.inl)
+# ----------------------------------------------------------------------------------------------------------------------
+def _tet_rule(q):
+    if q == 1:
+        return [[0.25, 0.25, 0.25]], [0.166666666666666656]
+    if q == 2:
+        a, b = 0.585410196624967936, 0.138196601125011008
+        return [[a, b, b], [b, a, b], [b, b, a], [b, b, b]], [0.0416666666666666624] * 4
+    if q == 3:
+        a, b, c, d = 0.77849529482132992, 0.0738349017262233984, 0.406244343884051008, 0.0937556561159491072
+        pts = [[a, b, b], [b, a, b], [b, b, a], [b, b, b], [c, c, d], [c, d, c], [c, d, d], [d, c, c], [d, c, d],
+               [d, d, c]]
+        return pts, [0.00793885580720148224] * 4 + [0.022485207239643504] * 6
+    if q == 4:
+        a, b = 0.902942215818267904, 0.0323525947272438976
+        c, d, e = 0.262682583887778976, 0.616596533061936896, 0.0603604415251420928
+        f, g = 0.309769304272861952, 0.0706920871814129024
+        pts = [[a, b, b], [b, a, b], [b, b, a], [b, b, b], [c, d, e], [d, c, e], [c, e, d], [d, e, c], [c, e, e],
+               [d, e, e], [e, c, d], [e, d, c], [e, c, e], [e, d, e], [e, e, c], [e, e, d], [f, f, f], [f, f, g],
+               [f, g, f], [g, f, f]]
+        return pts, [0.00117784579907825008] * 4 + [0.0078331114953146176] * 12 + [0.0169894863816446688] * 4
+    raise ValueError(q)
+
+
+def _tri_rule(q):
+    if q == 1:
+        return [[0.333333333333333, 0.333333333333333]], [0.5]
+    if q == 2:
+        a, b = 0.166666666666667, 0.666666666666667
+        return [[a, a], [a, b], [b, a]], [0.166666666666667] * 3
+    if q == 3:
+        a, b, c, d = 0.09157621350978, 0.81684757298044, 0.108103018168071, 0.445948490915964
+        return [[a, a], [a, b], [b, a], [c, d], [d, c], [d, d]], [0.0549758718276665] * 3 + [0.111690794839] * 3
+    if q == 4:
+        a, b = 0.055564052669793, 0.888871894660413
+        c, d, e = 0.070255540518384, 0.634210747745723, 0.295533711735893
+        t = 0.333333333333333
+        pts = [[a, a], [a, b], [b, a], [c, d], [d, c], [d, e], [c, e], [e, c], [e, d], [t, t]]
+        return pts, [0.0209777564983245] * 3 + [0.0560492060354435] * 6 + [0.100771494292365]
+    raise ValueError(q)
+
+
+def is_simplex(geom):
+    return geom in (TRIANGLE, TETRAHEDRON)
+
+
+def num_quadrature_points(geom, q):
+    """F/geometry.hpp:25-43"""
+    return {SEGMENT: q, TRIANGLE: q * (q + 1) // 2, SQUARE: q * q, TETRAHEDRON: q * (q + 1) * (q + 2) // 6,
+            CUBE: q**3}[geom]
+
+
+def simplex_quadrature(geom, q):
+    pts, w = _tet_rule(q) if geom == TETRAHEDRON else _tri_rule(q)
+    return np.array(pts), np.array(w)
+
+
+def simplex_lattice(geom, p):
+    """integer lattice coordinates of the nodes in the reference's (lexicographic, x fastest) numbering"""
+    if geom == TRIANGLE:
+        return [(i, j) for j in range(p + 1) for i in range(p + 1 - j)]
+    return [(i, j, k) for k in range(p + 1) for j in range(p + 1 - k) for i in range(p + 1 - k - j)]
+
+
+def simplex_nodes(geom, p):
+    """node positions: Gauss-Lobatto points along edges, centroids inside faces (p = 3), as the nodal polynomials of
+    triangle_H1.inl / tetrahedron_H1.inl imply (each is 1 at its own node and 0 at the others)"""
+    gl = {1: [0.0, 1.0], 2: [0.0, 0.5, 1.0], 3: [0.0, 0.5 - 0.1 * _SQRT5, 0.5 + 0.1 * _SQRT5, 1.0]}[p]
+    out = []
+    for c in simplex_lattice(geom, p):
+        last = p - sum(c)
+        bary = list(c) + [last]
+        nz = sum(1 for b in bary if b > 0)
+        if nz == 3:
+            x = [1.0 / 3.0 if b > 0 else 0.0 for b in c]
+        else:
+            x = [gl[b] for b in c]
+            if nz == 2 and last == 0:  # edge opposite to the origin: coordinates sum to one
+                i0, i1 = [d for d, b in enumerate(c) if b > 0]
+                x[i1] = 1.0 - x[i0]
+        out.append(x)
+    return np.array(out)
+
+
+def simplex_shape_tables(geom, p, pts):
+    """phi [npts][ndof], dphi [npts][ndof][dim] of the nodal basis of P_p.  p = 1, 2: the closed forms of
+    triangle_H1.inl:50-80 / tetrahedron_H1.inl:47-84; p = 3: the unique Lagrange basis through simplex_nodes (the
+    reference spells the same polynomials out), from the monomial Vandermonde system."""
+    pts = np.asarray(pts, dtype=np.float64)
+    dim = pts.shape[1]
+    x = [pts[:, d] for d in range(dim)]
+    one, zero = np.ones(len(pts)), np.zeros(len(pts))
+    if p == 1:
+        lam0 = 1.0 - sum(x)
+        phi = [lam0] + x
+        dphi = [[-one] * dim] + [[one if d == e else zero for e in range(dim)] for d in range(dim)]
+        return np.stack(phi, 1), np.stack([np.stack(g, 1) for g in dphi], 1)
+    if p == 2:
+        lam = [1.0 - sum(x)] + x  # barycentric coordinates; node (i,j,k) <-> pair of vertices
+        dlam = [[-1.0] * dim] + [[1.0 if d == e else 0.0 for e in range(dim)] for d in range(dim)]
+        phi, dphi = [], []
+        for c in simplex_lattice(geom, 2):
+            bary = [2 - sum(c)] + list(c)
+            idx = [v for v, b in enumerate(bary) for _ in range(b)]  # the two (possibly equal) vertices
+            a, b = idx
+            if a == b:  # vertex function lam (2 lam - 1)
+                phi.append(lam[a] * (2.0 * lam[a] - 1.0))
+                dphi.append(np.stack([(4.0 * lam[a] - 1.0) * dlam[a][e] for e in range(dim)], 1))
+            else:  # edge function 4 lam_a lam_b
+                phi.append(4.0 * lam[a] * lam[b])
+                dphi.append(np.stack([4.0 * (lam[a] * dlam[b][e] + lam[b] * dlam[a][e]) for e in range(dim)], 1))
+        return np.stack(phi, 1), np.stack(dphi, 1)
+    nodes = simplex_nodes(geom, p)
+    expo = simplex_lattice(geom, p)  # monomial exponents: same index set
+
+    def monomials(P, deriv=None):
+        cols = []
+        for ex in expo:
+            v = np.ones(len(P))
+            for d in range(dim):
+                e = ex[d]
+                if d == deriv:
+                    if e == 0:
+                        v = np.zeros(len(P))
+                        break
+                    v = v * e
+                    e -= 1
+                v = v * P[:, d]**e
+            cols.append(v)
+        return np.stack(cols, 1)
+
+    C = np.linalg.inv(monomials(nodes))  # phi_k = sum_m C[m, k] mono_m
+    phi = monomials(pts) @ C
+    dphi = np.stack([monomials(pts, d) @ C for d in range(dim)], 2)
+    return phi, dphi
+
+
+# ----------------------------------------------------------------------------------------------------------------------
 # ElementRestriction (F/element_restriction.cpp)
 # ----------------------------------------------------------------------------------------------------------------------
 def lexicographic_permutation(geom, p):
@@ -98,6 +236,26 @@ def lexicographic_permutation(geom, p):
         native += [(0, p - i, j) for j in interior for i in interior]  # face 4: x = 0
         native += [(i, j, p) for j in interior for i in interior]      # face 5: z = p
         native += [(i, j, k) for k in interior for j in interior for i in interior]
+    elif geom in (TRIANGLE, TETRAHEDRON):
+        # mfem H1_TriangleElement / H1_TetrahedronElement native order: vertices, edges, faces, interior
+        if geom == TRIANGLE:
+            native = [(0, 0), (p, 0), (0, p)]
+            native += [(i, 0) for i in interior] + [(p - i, i) for i in interior] + [(0, p - i) for i in interior]
+            native += [(i, j) for j in interior for i in range(1, p - j)]
+        else:
+            native = [(0, 0, 0), (p, 0, 0), (0, p, 0), (0, 0, p)]
+            native += [(i, 0, 0) for i in interior] + [(0, i, 0) for i in interior] + [(0, 0, i) for i in interior]
+            native += [(p - i, i, 0) for i in interior] + [(p - i, 0, i) for i in interior]
+            native += [(0, p - i, i) for i in interior]
+            face_ij = [(i, j) for j in interior for i in range(1, p - j)]
+            native += [(p - i - j, i, j) for (i, j) in face_ij] + [(0, j, i) for (i, j) in face_ij]
+            native += [(i, 0, j) for (i, j) in face_ij] + [(j, i, 0) for (i, j) in face_ij]
+            native += [(i, j, k) for k in interior for j in range(1, p - k) for i in range(1, p - k - j)]
+        lattice = simplex_lattice(geom, p)
+        lex = np.empty(len(native), dtype=np.int64)
+        for nat, c in enumerate(native):
+            lex[lattice.index(c)] = nat
+        return lex
     else:
         raise ValueError("unsupported geometry")
     lex = np.empty(len(native), dtype=np.int64)
@@ -142,9 +300,14 @@ def scatter_add(table, E, L, components, byvdim=True):
 # ----------------------------------------------------------------------------------------------------------------------
 # tensor-product H1 element: interpolate / integrate (F/detail/hexahedron_H1.inl:169-280, quadrilateral_H1.inl)
 # ----------------------------------------------------------------------------------------------------------------------
-def interpolate(u_E, p, q, dim):
+def interpolate(u_E, p, q, dim, geom=None):
     """u_E [ne][c][n^dim] (lexicographic, x fastest) -> value [ne][c][nq], parent gradient [ne][c][dim][nq] with the
-    quadrature index Q = (qz*q + qy)*q + qx."""
+    quadrature index Q = (qz*q + qy)*q + qx.  Simplex geometries: dense sums over the nodal basis
+    (triangle_H1.inl:269-292, tetrahedron_H1.inl:369-390)."""
+    if geom is not None and is_simplex(geom):
+        xi, _ = simplex_quadrature(geom, q)
+        phi, dphi = simplex_shape_tables(geom, p, xi)
+        return np.einsum("qk,eck->ecq", phi, u_E), np.einsum("qkj,eck->ecjq", dphi, u_E)
     B, G, _ = basis_tables(p, q)
     ne, c = u_E.shape[:2]
     n = p + 1
@@ -165,9 +328,19 @@ def interpolate(u_E, p, q, dim):
     return val.reshape(ne, c, nq), grad.reshape(ne, c, dim, nq)
 
 
-def integrate(source, flux, p, q, dim):
+def integrate(source, flux, p, q, dim, geom=None):
     """source [ne][c][nq] or None, flux [ne][c][dim][nq] or None (parent space) -> r_E [ne][c][n^dim];
-    weights folded in as in hexahedron_H1.inl:244-246."""
+    weights folded in as in hexahedron_H1.inl:244-246.  Simplex geometries: tetrahedron_H1.inl:392-429."""
+    if geom is not None and is_simplex(geom):
+        xi, w = simplex_quadrature(geom, q)
+        phi, dphi = simplex_shape_tables(geom, p, xi)
+        ref = source if source is not None else flux
+        out = np.zeros(ref.shape[:2] + (phi.shape[1],))
+        if source is not None:
+            out += np.einsum("ecq,qk,q->eck", source, phi, w)
+        if flux is not None:
+            out += np.einsum("ecjq,qkj,q->eck", flux, dphi, w)
+        return out
     B, G, w = basis_tables(p, q)
     Bw, Gw = B * w[:, None], G * w[:, None]
     n = p + 1
@@ -192,9 +365,9 @@ def integrate(source, flux, p, q, dim):
     return out.reshape(ne, c, n**dim)
 
 
-def geometric_factors(nodes_E, mesh_order, q, dim):
+def geometric_factors(nodes_E, mesh_order, q, dim, geom=None):
     """compute_geometric_factors (F/geometric_factors.cpp:16-60): X_q [ne][dim][nq], J_q [ne][j][i][nq] = dX_i/dxi_j"""
-    val, grad = interpolate(nodes_E, mesh_order, q, dim)
+    val, grad = interpolate(nodes_E, mesh_order, q, dim, geom)
     return val, np.transpose(grad, (0, 2, 1, 3))
 
 
@@ -471,7 +644,7 @@ def _tensor_lists(val, grad):
     return [val[:, a] for a in range(c)], [[grad[:, a, j] for j in range(dim)] for a in range(c)]
 
 
-def evaluation_kernel(qf, trials_E, orders, X_q, J_q, test_order, q, dim, wrt=-1, state=None):
+def evaluation_kernel(qf, trials_E, orders, X_q, J_q, test_order, q, dim, wrt=-1, state=None, geom=None):
     """evaluation_kernel_impl (F/domain_integral_kernels.hpp:152-220).  trials_E: list of [ne][c][ndof] E-vectors.
     Returns r_E [ne][ct][ndof] and, when wrt >= 0, the derivative blocks after physical_to_parent:
       d00 [ne][nq][ct][ck], d01 [ne][nq][ct][ck][dim], d10 [ne][nq][ct][dim][ck], d11 [ne][nq][ct][dim][ck][dim]."""
@@ -482,7 +655,7 @@ def evaluation_kernel(qf, trials_E, orders, X_q, J_q, test_order, q, dim, wrt=-1
     dv = mdet(Jm)
     args = []
     for k, (uE, p) in enumerate(zip(trials_E, orders)):
-        val, grad = interpolate(uE, p, q, dim)  # parent space
+        val, grad = interpolate(uE, p, q, dim, geom)  # parent space
         c = val.shape[1]
         vals, grads = _tensor_lists(val, grad)
         if k == wrt:
@@ -509,7 +682,7 @@ def evaluation_kernel(qf, trials_E, orders, X_q, J_q, test_order, q, dim, wrt=-1
     src_v = np.stack([np.broadcast_to(value_of(s), (ne, nq)) for s in source], axis=1)
     flux_v = np.stack([np.stack([np.broadcast_to(value_of(flux[a][j]), (ne, nq)) for j in range(dim)], axis=1)
                        for a in range(ct)], axis=1)
-    r_E = integrate(src_v, flux_v, test_order, q, dim)
+    r_E = integrate(src_v, flux_v, test_order, q, dim, geom)
     if wrt < 0:
         return r_E, None
     ck = trials_E[wrt].shape[1]
@@ -524,32 +697,34 @@ def evaluation_kernel(qf, trials_E, orders, X_q, J_q, test_order, q, dim, wrt=-1
     return r_E, blocks
 
 
-def action_of_gradient_kernel(blocks, du_E, trial_order, test_order, q, dim):
+def action_of_gradient_kernel(blocks, du_E, trial_order, test_order, q, dim, geom=None):
     """action_of_gradient_kernel (F/domain_integral_kernels.hpp:277-304) with chain_rule (:223-237)"""
-    val, grad = interpolate(du_E, trial_order, q, dim)  # parent space, no J needed
+    val, grad = interpolate(du_E, trial_order, q, dim, geom)  # parent space, no J needed
     v = np.transpose(val, (0, 2, 1))  # [ne][nq][ck]
     g = np.transpose(grad, (0, 3, 1, 2))  # [ne][nq][ck][dim]
     src = np.einsum("eqab,eqb->eqa", blocks["d00"], v) + np.einsum("eqabl,eqbl->eqa", blocks["d01"], g)
     flx = np.einsum("eqakb,eqb->eqak", blocks["d10"], v) + np.einsum("eqakbl,eqbl->eqak", blocks["d11"], g)
-    return integrate(np.transpose(src, (0, 2, 1)), np.transpose(flx, (0, 2, 3, 1)), test_order, q, dim)
+    return integrate(np.transpose(src, (0, 2, 1)), np.transpose(flx, (0, 2, 3, 1)), test_order, q, dim, geom)
 
 
-def element_gradient_kernel(blocks, trial_order, test_order, q, dim):
+def element_gradient_kernel(blocks, trial_order, test_order, q, dim, geom=None):
     """element_gradient_kernel (F/domain_integral_kernels.hpp:327-361) with batch_apply_shape_fn
     (F/detail/hexahedron_H1.inl:132-167): K_e [ne][ck*ndk + J][ct*ndt + I] (trial-major, F/functional.hpp:599-601)"""
     d00, d01, d10, d11 = blocks["d00"], blocks["d01"], blocks["d10"], blocks["d11"]
     ne, nq, ct, ck = d00.shape
     nk = trial_order + 1
     ndk, ndt = nk**dim, (test_order + 1)**dim
+    if geom is not None and is_simplex(geom):
+        ndk, ndt = len(simplex_lattice(geom, trial_order)), len(simplex_lattice(geom, test_order))
     # shape function J and its parent gradient at every quadrature point = interpolation of the unit E-vector e_J
-    phi, dphi = interpolate(np.eye(ndk)[None], trial_order, q, dim)
+    phi, dphi = interpolate(np.eye(ndk)[None], trial_order, q, dim, geom)
     phi, dphi = phi[0], dphi[0]  # [J][nq], [J][dim][nq]
     K = np.zeros((ne, ck * ndk, ct * ndt))
     for b in range(ck):
         src = np.einsum("eqa,Jq->eJaq", d00[:, :, :, b], phi) + np.einsum("eqal,Jlq->eJaq", d01[:, :, :, b, :], dphi)
         flx = (np.einsum("eqak,Jq->eJakq", d10[:, :, :, :, b], phi) +
                np.einsum("eqakl,Jlq->eJakq", d11[:, :, :, :, b, :], dphi))
-        rr = integrate(src.reshape(ne * ndk, ct, nq), flx.reshape(ne * ndk, ct, dim, nq), test_order, q, dim)
+        rr = integrate(src.reshape(ne * ndk, ct, nq), flx.reshape(ne * ndk, ct, dim, nq), test_order, q, dim, geom)
         K[:, b * ndk:(b + 1) * ndk, :] = rr.reshape(ne, ndk, ct * ndt)
     return K
 

@@ -18,7 +18,8 @@ REFERENCE_MESHES = "/root/reference/data/meshes"
 
 
 def make_mesh(spec):
-    """spec: ("file", name, refinements) | ("cart3d", nx, ny, nz, perturb) | ("cart2d", nx, ny, perturb)"""
+    """spec: ("file", name, refinements) | ("cart3d", nx, ny, nz, perturb) | ("cart2d", nx, ny, perturb)
+    | ("cart3d_tet", nx, ny, nz, perturb) | ("cart2d_tri", nx, ny, perturb)"""
     if spec[0] == "file":
         return ref.Mesh.from_file(os.path.join(REFERENCE_MESHES, spec[1]), spec[2])
     if spec[0] == "cart3d":
@@ -28,6 +29,16 @@ def make_mesh(spec):
         return m
     if spec[0] == "cart2d":
         m = ref.Mesh.cartesian2d(spec[1], spec[2])
+        if spec[3]:
+            m.perturb(spec[3])
+        return m
+    if spec[0] == "cart3d_tet":
+        m = ref.Mesh.cartesian3d_tet(spec[1], spec[2], spec[3])
+        if spec[4]:
+            m.perturb(spec[4])
+        return m
+    if spec[0] == "cart2d_tri":
+        m = ref.Mesh.cartesian2d_tri(spec[1], spec[2])
         if spec[3]:
             m.perturb(spec[3])
         return m
@@ -178,6 +189,22 @@ FIXTURES = [
                                                 p=2, params=[2.0, 100.0, 50.0, 0.0], vdim=3)),
     ("solid_neohookean_quad_p2_cart", dict(mesh_spec=("cart2d", 3, 2, 0.02), kind="solid_neohookean", p=2,
                                            params=[1.0, 100.0, 50.0, 1.0], vdim=2)),
+    # simplex elements (BASELINE.json configs[3] runs on a tet mesh, H1 p=1)
+    ("solid_neohookean_tet_p1_beam", dict(mesh_spec=("file", "beam-tet.mesh", 0), kind="solid_neohookean", p=1,
+                                          params=[1.0, 100.0, 50.0, 1.0], vdim=3, shape_amp=0.01)),
+    ("solid_neohookean_tet_p2_cart", dict(mesh_spec=("cart3d_tet", 2, 1, 1, 0.02), kind="solid_neohookean", p=2,
+                                          params=[1.0, 100.0, 50.0, 1.0], vdim=3, shape_amp=0.01)),
+    ("solid_linear_isotropic_tet_p3_patch", dict(mesh_spec=("file", "patch3D_tets.mesh", 0),
+                                                 kind="solid_linear_isotropic", p=3, params=[2.0, 100.0, 50.0, 0.0],
+                                                 vdim=3, with_matrix=False)),
+    ("solid_neohookean_tri_p2_cart", dict(mesh_spec=("cart2d_tri", 3, 2, 0.02), kind="solid_neohookean", p=2,
+                                          params=[1.0, 100.0, 50.0, 1.0], vdim=2, shape_amp=0.01)),
+    ("thermal_linear_conductor_tet_p1_patch", dict(mesh_spec=("file", "patch3D_tets.mesh", 0),
+                                                   kind="thermal_linear_conductor", p=1, params=[1.5, 2.0, 0.7],
+                                                   vdim=1, shape_amp=0.01)),
+    ("thermal_linear_conductor_tri_p1_patch", dict(mesh_spec=("file", "patch2D_tris.mesh", 1),
+                                                   kind="thermal_linear_conductor", p=1, params=[1.5, 2.0, 0.7],
+                                                   vdim=1)),
     # BASELINE.json configs[0]: HeatTransfer linear conduction, H1 p=1 on star.mesh (20 quads)
     ("thermal_linear_conductor_quad_p1_star", dict(mesh_spec=("file", "star.mesh", 1), kind="thermal_linear_conductor",
                                                    p=1, params=[1.5, 2.0, 0.7], vdim=1, shape_amp=0.01)),

@@ -30,6 +30,9 @@ def lib():
             "ref_mesh_from_file": (vp, [C.c_char_p, i]),
             "ref_mesh_cartesian3d": (vp, [i, i, i, d, d, d]),
             "ref_mesh_cartesian2d": (vp, [i, i, d, d]),
+            "ref_mesh_cartesian3d_tet": (vp, [i, i, i, d, d, d]),
+            "ref_mesh_cartesian2d_tri": (vp, [i, i, d, d]),
+            "ref_mesh_geom": (i, [vp]),
             "ref_mesh_destroy": (None, [vp]),
             "ref_mesh_dim": (i, [vp]),
             "ref_mesh_num_elements": (i, [vp]),
@@ -85,6 +88,11 @@ def lib():
     return _lib
 
 
+def num_quadrature_points(geom, q):
+    """F/geometry.hpp:25-43"""
+    return {1: q, 2: q * (q + 1) // 2, 3: q * q, 4: q * (q + 1) * (q + 2) // 6, 5: q**3}[geom]
+
+
 def _p(a):
     return a.ctypes.data_as(C.c_void_p)
 
@@ -94,7 +102,9 @@ class Mesh:
         self.h = handle
         self.dim = lib().ref_mesh_dim(handle)
         self.ne = lib().ref_mesh_num_elements(handle)
-        self.geom = GEOM["hex"] if self.dim == 3 else GEOM["quad"]
+        self.geom = lib().ref_mesh_geom(handle)  # mfem::Geometry::Type of the (single-geometry) mesh
+        if self.geom < 0:
+            raise ValueError("mixed-geometry meshes are not supported by this driver")
 
     @staticmethod
     def from_file(path, refinements=0):
@@ -107,6 +117,14 @@ class Mesh:
     @staticmethod
     def cartesian2d(nx, ny, sx=1.0, sy=1.0):
         return Mesh(lib().ref_mesh_cartesian2d(nx, ny, sx, sy))
+
+    @staticmethod
+    def cartesian3d_tet(nx, ny, nz, sx=1.0, sy=1.0, sz=1.0):
+        return Mesh(lib().ref_mesh_cartesian3d_tet(nx, ny, nz, sx, sy, sz))
+
+    @staticmethod
+    def cartesian2d_tri(nx, ny, sx=1.0, sy=1.0):
+        return Mesh(lib().ref_mesh_cartesian2d_tri(nx, ny, sx, sy))
 
     def perturb(self, amp):
         lib().ref_mesh_perturb(self.h, amp)
@@ -124,7 +142,7 @@ class Mesh:
 
     @property
     def face_geom(self):
-        return GEOM["quad"] if self.dim == 3 else GEOM["segment"]
+        return {GEOM["hex"]: GEOM["quad"], GEOM["tet"]: GEOM["triangle"]}.get(self.geom, GEOM["segment"])
 
     def num_boundary_faces(self):
         return lib().ref_boundary_geometric_factors(self.h, 1, self.face_geom, None, None)
@@ -132,7 +150,7 @@ class Mesh:
     def boundary_geometric_factors(self, q):
         """GeometricFactors(EntireBoundary, q, face_geom, FaceType::BOUNDARY): X [nf][sdim][nq], J [nf][gdim][sdim][nq]"""
         nf, gd = self.num_boundary_faces(), self.dim - 1
-        nq = q**gd
+        nq = num_quadrature_points(self.face_geom, q)
         X = np.empty((nf, self.dim, nq))
         J = np.empty((nf, gd, self.dim, nq))
         lib().ref_boundary_geometric_factors(self.h, q, self.face_geom, _p(X), _p(J))
@@ -150,7 +168,7 @@ class Mesh:
         return nat.reshape(nf, -1), info.reshape(nf, -1)
 
     def geometric_factors(self, q):
-        nq = q**self.dim
+        nq = num_quadrature_points(self.geom, q)
         X = np.empty((self.ne, self.dim, nq))
         J = np.empty((self.ne, self.dim, self.dim, nq))
         lib().ref_geometric_factors(self.h, q, self.geom, _p(X), _p(J))

@@ -45,6 +45,29 @@ void* ref_mesh_cartesian2d(int nx, int ny, double sx, double sy)
   mesh->EnsureNodes();
   return mesh;
 }
+/// simplex meshes: element type TETRAHEDRON / TRIANGLE instead of the tensor-product one
+void* ref_mesh_cartesian3d_tet(int nx, int ny, int nz, double sx, double sy, double sz)
+{
+  auto* mesh = new mfem::Mesh(mfem::Mesh::MakeCartesian3D(nx, ny, nz, mfem::Element::TETRAHEDRON, sx, sy, sz));
+  mesh->EnsureNodes();
+  return mesh;
+}
+void* ref_mesh_cartesian2d_tri(int nx, int ny, double sx, double sy)
+{
+  auto* mesh = new mfem::Mesh(mfem::Mesh::MakeCartesian2D(nx, ny, mfem::Element::TRIANGLE, true, sx, sy));
+  mesh->EnsureNodes();
+  return mesh;
+}
+/// geometry of the mesh's elements (single-geometry meshes only: returns -1 when mixed)
+int ref_mesh_geom(void* m)
+{
+  auto* mesh = static_cast<mfem::Mesh*>(m);
+  if (mesh->GetNE() == 0) return -1;
+  const auto g = mesh->GetElementGeometry(0);
+  for (int e = 1; e < mesh->GetNE(); e++)
+    if (mesh->GetElementGeometry(e) != g) return -1;
+  return int(g);
+}
 void ref_mesh_destroy(void* m) { delete static_cast<mfem::Mesh*>(m); }
 int  ref_mesh_dim(void* m) { return static_cast<mfem::Mesh*>(m)->Dimension(); }
 int  ref_mesh_num_elements(void* m) { return static_cast<mfem::Mesh*>(m)->GetNE(); }

@@ -90,8 +90,10 @@ std::shared_ptr<QuadratureData<State>> make_qdata(mfem::Mesh& mesh, ref::Integra
   auto qd        = std::make_shared<QuadratureData<State>>(elems, qpts, init);
   h.qdata        = qd;
   h.state_bytes  = sizeof(State);
-  h.qdata_count  = size_t(elems[size_t(tp_geom)]) * size_t(qpts[size_t(tp_geom)]);
-  h.qdata_raw    = (h.qdata_count > 0) ? static_cast<void*>(&(*qd)[tp_geom](0, 0)) : nullptr;
+  // single-geometry meshes: the buffer of the geometry the mesh is made of (hex / quad / tet / tri)
+  const auto g   = (mesh.GetNE() > 0) ? mesh.GetElementGeometry(0) : tp_geom;
+  h.qdata_count  = size_t(elems[size_t(g)]) * size_t(qpts[size_t(g)]);
+  h.qdata_raw    = (h.qdata_count > 0) ? static_cast<void*>(&(*qd)[g](0, 0)) : nullptr;
   return qd;
 }
 

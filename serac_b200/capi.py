@@ -136,8 +136,24 @@ def _stream_ptr():
     return C.c_void_p(torch.cuda.current_stream().cuda_stream)
 
 
+def geometry_dimension(geom):
+    return {SEGMENT: 1, TRIANGLE: 2, SQUARE: 2, TETRAHEDRON: 3, CUBE: 3}[geom]
+
+
+def num_nodes(geom, p):
+    """H1 nodes per element"""
+    return {SEGMENT: p + 1, TRIANGLE: (p + 1) * (p + 2) // 2, SQUARE: (p + 1)**2,
+            TETRAHEDRON: (p + 1) * (p + 2) * (p + 3) // 6, CUBE: (p + 1)**3}[geom]
+
+
+def num_quadrature_points(geom, q):
+    """geometry.hpp:25-43"""
+    return {SEGMENT: q, TRIANGLE: q * (q + 1) // 2, SQUARE: q * q, TETRAHEDRON: q * (q + 1) * (q + 2) // 6,
+            CUBE: q**3}[geom]
+
+
 def lexicographic_permutation(geom, p):
-    n = {SEGMENT: p + 1, SQUARE: (p + 1)**2, CUBE: (p + 1)**3}[geom]
+    n = num_nodes(geom, p)
     out = np.empty(n, dtype=np.int32)
     check(lib().sb_h1_lexicographic_permutation(geom, p, _np_ptr(out)))
     return out
@@ -202,10 +218,10 @@ class ElementRestriction:
 def geometric_factors(geom, mesh_order, q, mesh_restriction, nodes_L, num_elements=None, elements=None):
     """GeometricFactors (geometric_factors.cpp:62-138) -> (X_q [ne][dim][nq], J_q [ne][dim][dim][nq]) on device."""
     import torch
-    dim = 3 if geom == CUBE else 2
+    dim = geometry_dimension(geom)
     sdim = mesh_restriction.components  # == dim for domain elements, dim + 1 for the faces of a boundary integral
     ne = mesh_restriction.num_elements if num_elements is None else num_elements
-    nq = q**dim
+    nq = num_quadrature_points(geom, q)
     X = torch.empty((ne, sdim, nq), dtype=torch.float64, device=nodes_L.device)
     J = torch.empty((ne, dim, sdim, nq), dtype=torch.float64, device=nodes_L.device)
     check(lib().sb_geometric_factors(geom, mesh_order, q, mesh_restriction.h, _dev_ptr(nodes_L),
@@ -236,7 +252,7 @@ class Integral:
         self.h = h
         self._keep = (X_q, J_q)
         self.num_elements = num_elements
-        self.nq = self.table.q**self.table.dim
+        self.nq = num_quadrature_points(self.table.geom, self.table.q)
         self.qdata = None
 
     def __del__(self):

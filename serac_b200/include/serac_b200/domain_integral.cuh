@@ -38,6 +38,15 @@ SB_HD int elements_per_block(int dim, int q)
   return 1;
 }
 
+/// geometry-aware version: simplices have no tensor structure, one thread per quadrature point, ~128 threads per CTA
+SB_HD int elements_per_block(Geometry g, int q)
+{
+  if (!is_simplex(g)) return elements_per_block(dimension_of(g), q);
+  const int nq  = num_quadrature_points(g, q);
+  const int epb = 128 / nq;
+  return epb > 32 ? 32 : (epb < 1 ? 1 : epb);
+}
+
 /// one trial / test field as the kernels see it
 struct FieldArg {
   const double* L;            ///< L-vector (device)
@@ -51,6 +60,7 @@ struct EvalParams {
   FieldArg      trial[NT > 0 ? NT : 1];
   BasisTable1D  trial_basis[NT > 0 ? NT : 1];
   BasisTable1D  test_basis;
+  const double* simplex_tab[NT + 1];  ///< simplex geometries: device SimplexTable::tab of every trial space, then test
   const double* X_q;           ///< [e][i][q]       (geometric_factors.cpp:27,48)
   const double* J_q;           ///< [e][j][i][q] = dX_i/dxi_j
   const int*    elements;      ///< domain element ids (index into the restriction tables / E-vector)
@@ -66,6 +76,8 @@ struct JvpParams {
   FieldArg      trial;
   BasisTable1D  trial_basis;
   BasisTable1D  test_basis;
+  const double* simplex_trial_tab;  ///< simplex geometries only
+  const double* simplex_test_tab;
   const int*    elements;
   int           num_elements;
   const double* dqf;
@@ -75,6 +87,8 @@ struct JvpParams {
 struct ElemGradParams {
   BasisTable1D  trial_basis;
   BasisTable1D  test_basis;
+  const double* simplex_trial_tab;  ///< simplex geometries only
+  const double* simplex_test_tab;
   const int*    elements;
   int           num_elements;
   const double* dqf;
@@ -412,6 +426,76 @@ struct TensorProduct<2, n, q, c> {
   }
 };
 
+// ------------------------------------------------------------------------------------------------
+// simplex elements: dense interpolation / integration (triangle_H1.inl:269-336, tetrahedron_H1.inl:369-429).
+// tab = SimplexTable::tab in shared memory: [qpt][node][1 + dim] = {phi, dphi/dxi}.
+// ------------------------------------------------------------------------------------------------
+template <int dim, int ndof, int nq, int c>
+struct SimplexOps {
+  static constexpr int integ_scratch = c * (1 + dim) * nq;
+
+  /// u: smem [c][ndof] of this element
+  static __device__ __forceinline__ void interpolate(const double* __restrict__ tab, const double* __restrict__ u, int ql,
+                                                     double (&val)[c], double (&grad)[c][dim])
+  {
+    SB_UNROLL
+    for (int a = 0; a < c; a++) {
+      val[a] = 0.0;
+      SB_UNROLL
+      for (int j = 0; j < dim; j++) grad[a][j] = 0.0;
+    }
+    const double* t = tab + ql * ndof * (1 + dim);
+    SB_UNROLL
+    for (int k = 0; k < ndof; k++) {
+      double f[1 + dim];
+      SB_UNROLL
+      for (int j = 0; j <= dim; j++) f[j] = t[k * (1 + dim) + j];
+      SB_UNROLL
+      for (int a = 0; a < c; a++) {
+        const double uu = u[a * ndof + k];
+        val[a] += uu * f[0];
+        SB_UNROLL
+        for (int j = 0; j < dim; j++) grad[a][j] += uu * f[1 + j];
+      }
+    }
+  }
+
+  /// every thread of the CTA must call this; thread ql < ndof returns the value of node ql in out[c]
+  template <bool HAS_SOURCE, bool HAS_FLUX>
+  static __device__ __forceinline__ bool integrate(const double* __restrict__ tab, double* S, int ql,
+                                                   const double (&src)[c], const double (&flux)[c][dim], double (&out)[c])
+  {
+    SB_UNROLL
+    for (int a = 0; a < c; a++) {
+      if (HAS_SOURCE) S[(a * (1 + dim) + 0) * nq + ql] = src[a];
+      if (HAS_FLUX) {
+        SB_UNROLL
+        for (int j = 0; j < dim; j++) S[(a * (1 + dim) + 1 + j) * nq + ql] = flux[a][j];
+      }
+    }
+    __syncthreads();
+    const bool owner = ql < ndof;
+    if (owner) {
+      SB_UNROLL
+      for (int a = 0; a < c; a++) out[a] = 0.0;
+      for (int Q = 0; Q < nq; Q++) {
+        const double* t = tab + (Q * ndof + ql) * (1 + dim);
+        SB_UNROLL
+        for (int a = 0; a < c; a++) {
+          double r = out[a];
+          if (HAS_SOURCE) r += S[(a * (1 + dim) + 0) * nq + Q] * t[0];
+          if (HAS_FLUX) {
+            SB_UNROLL
+            for (int j = 0; j < dim; j++) r += S[(a * (1 + dim) + 1 + j) * nq + Q] * t[1 + j];
+          }
+          out[a] = r;
+        }
+      }
+    }
+    return owner;
+  }
+};
+
 SB_HD int cmax(int a, int b) { return a > b ? a : b; }
 
 // ------------------------------------------------------------------------------------------------
@@ -425,7 +509,8 @@ struct SignatureT {
   static constexpr int      q        = Q;
   static constexpr int      NT       = int(sizeof...(trials));
   static constexpr int      QPE      = num_quadrature_points(geom, Q);  ///< quadrature points per element
-  static constexpr int      EPB      = (EPB_ > 0) ? EPB_ : elements_per_block(dim, Q);
+  static constexpr bool     simplex  = is_simplex(geom);
+  static constexpr int      EPB      = (EPB_ > 0) ? EPB_ : elements_per_block(geom, Q);
   static constexpr int      threads  = EPB * QPE;
   using test_space                   = test;
   template <int i>
@@ -433,7 +518,12 @@ struct SignatureT {
 
   static constexpr int test_n    = test::order + 1;
   static constexpr int test_c    = test::components;
-  static constexpr int test_ndof = ipow(test_n, dim);
+  static constexpr int test_ndof = num_nodes(geom, test::order);
+  static constexpr int trial_ndof(int i)
+  {
+    constexpr int v[] = {num_nodes(geom, trials::order)..., 0};
+    return v[i];
+  }
   static constexpr int trial_n(int i)
   {
     constexpr int v[] = {(trials::order + 1)..., 0};
@@ -490,8 +580,17 @@ struct BoundaryIntegrand {
 template <typename Sig>
 struct EvalLayout {
   static constexpr int dim = Sig::dim, q = Sig::q, NT = Sig::NT, EPB = Sig::EPB;
-  static constexpr int tables = (NT + 1) * 2 * MAX_Q * MAX_Q;
-  static constexpr int ndof(int i) { return ipow(Sig::trial_n(i), dim); }
+  static constexpr int QPE = Sig::QPE;
+  static constexpr int ndof(int i) { return Sig::trial_ndof(i); }
+  /// simplex: offset of space i's {phi, dphi} table (i == NT: test space); the nq weights follow the last table
+  static constexpr int simplex_tab_size(int i) { return QPE * (i < NT ? ndof(i) : Sig::test_ndof) * (1 + dim); }
+  static constexpr int simplex_tab_off(int i)
+  {
+    int o = 0;
+    for (int j = 0; j < i; j++) o += simplex_tab_size(j);
+    return o;
+  }
+  static constexpr int tables = Sig::simplex ? simplex_tab_off(NT + 1) + QPE : (NT + 1) * 2 * MAX_Q * MAX_Q;
   static constexpr int gather_size(int i) { return EPB * Sig::trial_c(i) * ndof(i); }
   static constexpr int gather_off(int i)
   {
@@ -503,7 +602,16 @@ struct EvalLayout {
   static constexpr int work_size(int i)
   {
     const int n = Sig::trial_n(i), c = Sig::trial_c(i);
+    if (Sig::simplex) return 0;  // dense interpolation reads the gathered dofs directly
     return (dim == 3) ? 2 * c * n * n * q + 3 * c * n * q * q : 2 * c * n * q;
+  }
+  static constexpr int integ_scratch()
+  {
+    if constexpr (Sig::simplex) {
+      return Sig::test_c * (1 + dim) * QPE;
+    } else {
+      return TensorProduct<dim, Sig::test_n, q, Sig::test_c>::integ_scratch;
+    }
   }
   static constexpr int work_off(int i)
   {
@@ -511,7 +619,7 @@ struct EvalLayout {
     for (int j = 0; j < i; j++) o += work_size(j);
     return o;
   }
-  static constexpr int W = cmax(work_off(NT), TensorProduct<dim, Sig::test_n, q, Sig::test_c>::integ_scratch);
+  static constexpr int W = cmax(work_off(NT), integ_scratch());
   static constexpr int gather_total = gather_off(NT);
   static constexpr int total        = tables + gather_total + EPB * W;
 };
@@ -903,11 +1011,27 @@ __global__ void __launch_bounds__(Sig::threads, MINB) evaluation_kernel(const __
   double* gathered = smem + LAY::tables;
   double* scratch = gathered + LAY::gather_total;
 
-  for (int i = threadIdx.x; i < LAY::tables; i += Sig::threads) {
-    const int           which = i / (2 * MAX_Q * MAX_Q);
-    const int           rem   = i - which * (2 * MAX_Q * MAX_Q);
-    const BasisTable1D& bt    = (which < NT) ? P.trial_basis[which < NT ? which : 0] : P.test_basis;
-    tables[i]                 = (rem < MAX_Q * MAX_Q) ? bt.B[rem] : bt.G[rem - MAX_Q * MAX_Q];
+  if constexpr (Sig::simplex) {
+    // {phi, dphi} tables of every space, then the quadrature weights (which trail the test space's table in global memory)
+    [&]<int... I>(std::integer_sequence<int, I...>)
+    {
+      auto copy = [&](auto idx) {
+        constexpr int J   = decltype(idx)::value;
+        constexpr int off = LAY::simplex_tab_off(J);
+        constexpr int sz  = LAY::simplex_tab_size(J) + (J == NT ? QPE : 0);
+        const double* src = P.simplex_tab[J];
+        for (int i = threadIdx.x; i < sz; i += Sig::threads) tables[off + i] = src[i];
+      };
+      (copy(std::integral_constant<int, I>{}), ...);
+    }
+    (std::make_integer_sequence<int, NT + 1>{});
+  } else {
+    for (int i = threadIdx.x; i < LAY::tables; i += Sig::threads) {
+      const int           which = i / (2 * MAX_Q * MAX_Q);
+      const int           rem   = i - which * (2 * MAX_Q * MAX_Q);
+      const BasisTable1D& bt    = (which < NT) ? P.trial_basis[which < NT ? which : 0] : P.test_basis;
+      tables[i]                 = (rem < MAX_Q * MAX_Q) ? bt.B[rem] : bt.G[rem - MAX_Q * MAX_Q];
+    }
   }
 
   const int el = threadIdx.x / QPE;
@@ -1025,7 +1149,17 @@ __global__ void __launch_bounds__(Sig::threads, MINB) evaluation_kernel(const __
         }
       }
     };
-    if constexpr (dim == 3) {
+    if constexpr (Sig::simplex) {
+      auto dense = [&](auto idx) {
+        constexpr int J = decltype(idx)::value;
+        constexpr int c = Sig::trial_c(J);
+        double        val[c];
+        double        grad[c][dim];
+        SimplexOps<dim, LAY::ndof(J), QPE, c>::interpolate(tables + LAY::simplex_tab_off(J), u_of(idx), ql, val, grad);
+        finish(idx, val, grad);
+      };
+      (dense(std::integral_constant<int, I>{}), ...);
+    } else if constexpr (dim == 3) {
       auto s1 = [&](auto idx) {
         constexpr int J = decltype(idx)::value;
         constexpr int n = Sig::trial_n(J), c = Sig::trial_c(J);
@@ -1079,9 +1213,14 @@ __global__ void __launch_bounds__(Sig::threads, MINB) evaluation_kernel(const __
   const auto pos = position_t<Sig>{x, Jm};
 
   // quadrature weight of this point
-  const BasisTable1D& tb = P.test_basis;
-  double              w  = tb.w[qx] * tb.w[qy];
-  if (dim == 3) w *= tb.w[qz];
+  double w;
+  if constexpr (Sig::simplex) {
+    w = tables[LAY::simplex_tab_off(NT + 1) + ql];
+  } else {
+    const BasisTable1D& tb = P.test_basis;
+    w                      = tb.w[qx] * tb.w[qy];
+    if (dim == 3) w *= tb.w[qz];
+  }
 
   // --- state ---
   State  state_old{};
@@ -1271,10 +1410,7 @@ __global__ void __launch_bounds__(Sig::threads, MINB) evaluation_kernel(const __
 
   // --- integrate against the test space and write the E-vector block ---
   if constexpr (has_source || has_flux) {
-    using TP = TensorProduct<dim, Sig::test_n, q, ct>;
     __syncthreads();
-    const double* B = tables + (NT * 2 + 0) * MAX_Q * MAX_Q;
-    const double* G = tables + (NT * 2 + 1) * MAX_Q * MAX_Q;
     double        out[ct];
     if constexpr (!has_source) {
       SB_UNROLL
@@ -1287,10 +1423,19 @@ __global__ void __launch_bounds__(Sig::threads, MINB) evaluation_kernel(const __
         for (int k = 0; k < dim; k++) flux[a][k] = 0.0;
       }
     }
-    const bool owner = TP::template integrate<has_source, has_flux>(B, G, scratch + el * per, qx, qy, qz, src, flux, out);
+    bool owner;
+    if constexpr (Sig::simplex) {
+      owner = SimplexOps<dim, Sig::test_ndof, QPE, ct>::template integrate<has_source, has_flux>(
+          tables + LAY::simplex_tab_off(NT), scratch + el * per, ql, src, flux, out);
+    } else {
+      using TP        = TensorProduct<dim, Sig::test_n, q, ct>;
+      const double* B = tables + (NT * 2 + 0) * MAX_Q * MAX_Q;
+      const double* G = tables + (NT * 2 + 1) * MAX_Q * MAX_Q;
+      owner = TP::template integrate<has_source, has_flux>(B, G, scratch + el * per, qx, qy, qz, src, flux, out);
+    }
     if (owner && valid) {
       constexpr int n    = Sig::test_n;
-      const int     node = (dim == 3) ? (qz * n + qy) * n + qx : qy * n + qx;
+      const int     node = Sig::simplex ? ql : (dim == 3) ? (qz * n + qy) * n + qx : qy * n + qx;
       SB_UNROLL
       for (int a = 0; a < ct; a++) P.r_E[((long long)elem * ct + a) * Sig::test_ndof + node] = out[a];
     }

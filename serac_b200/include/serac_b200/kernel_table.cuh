@@ -14,6 +14,7 @@
 #include "serac_b200.h"
 #include "serac_b200/domain_integral.cuh"
 #include "serac_b200/jvp_stream.cuh"
+#include "serac_b200/simplex_integral.cuh"
 
 namespace serac {
 namespace b200 {
@@ -70,6 +71,16 @@ int launch_evaluate(const sb_eval_args* a, const void* qf_blob, void* stream)
   };
   fill(std::make_integer_sequence<int, NT>{});
   P.test_basis   = make_basis_table(Sig::test_space::order, Sig::q);
+  if constexpr (Sig::simplex) {
+    auto tabs = [&]<int... I>(std::integer_sequence<int, I...>)
+    {
+      ((P.simplex_tab[I] = simplex_table_dev(Sig::geometry, Sig::template trial_space<I>::order, Sig::q)), ...);
+    };
+    tabs(std::make_integer_sequence<int, NT>{});
+    P.simplex_tab[NT] = simplex_table_dev(Sig::geometry, Sig::test_space::order, Sig::q);
+    for (int i = 0; i <= NT; i++)
+      if (!P.simplex_tab[i]) return int(cudaErrorMemoryAllocation);
+  }
   P.X_q          = a->X_q_dev;
   P.J_q          = a->J_q_dev;
   P.elements     = a->elements_dev;
@@ -141,6 +152,18 @@ int launch_jvp(const sb_jvp_args* a, void* stream)
     P.dqf          = a->dqf_dev;
     P.r_E          = a->r_E_dev;
     if (a->num_elements <= 0) return 0;
+    if constexpr (Sig::simplex) {
+      using SX            = SimplexConfig<Sig::geometry, Sig::q, trial::order, ck, Sig::test_space::order, Sig::test_c, MASK, Sig::EPB>;
+      P.simplex_trial_tab = simplex_table_dev(Sig::geometry, trial::order, Sig::q);
+      P.simplex_test_tab  = simplex_table_dev(Sig::geometry, Sig::test_space::order, Sig::q);
+      if (!P.simplex_trial_tab || !P.simplex_test_tab) return int(cudaErrorMemoryAllocation);
+      auto         kernel = &simplex_jvp_kernel<Sig::geometry, Sig::q, trial::order, ck, Sig::test_space::order, Sig::test_c, MASK, Sig::EPB>;
+      const size_t smem   = size_t(SX::jvp_smem_doubles) * sizeof(double);
+      if (int e = ensure_smem(kernel, smem)) return e;
+      kernel<<<(a->num_elements + SX::EPB - 1) / SX::EPB, SX::threads, smem, cudaStream_t(stream)>>>(P);
+      sb_count_launch();
+      return int(cudaGetLastError());
+    } else {
     const int tiles = (a->num_elements + C::EPB - 1) / C::EPB;
     using SC        = JvpStreamConfig<Sig::dim, Sig::q, nk, ck, Sig::test_n, Sig::test_c, MASK, Sig::EPB>;
     if constexpr (SC::supported && SC::smem_bytes <= 227 * 1024) {
@@ -165,6 +188,7 @@ int launch_jvp(const sb_jvp_args* a, void* stream)
     kernel<<<tiles, C::threads, smem, cudaStream_t(stream)>>>(P);
     sb_count_launch();
     return int(cudaGetLastError());
+    }
   }
 }
 
@@ -186,13 +210,26 @@ int launch_element_gradient(const sb_elem_grad_args* a, void* stream)
     P.dqf          = a->dqf_dev;
     P.K_e          = a->K_e_dev;
     if (a->num_elements <= 0) return 0;
-    auto         kernel = &element_gradient_kernel<Sig::dim, Sig::q, nk, ck, Sig::test_n, Sig::test_c, MASK, Sig::EPB>;
-    const size_t smem   = size_t(C::smem_doubles) * sizeof(double);
-    if (int e = ensure_smem(kernel, smem)) return e;
-    const int grid = (a->num_elements + C::EPB - 1) / C::EPB;
-    kernel<<<grid, C::threads, smem, cudaStream_t(stream)>>>(P);
-    sb_count_launch();
-    return int(cudaGetLastError());
+    if constexpr (Sig::simplex) {
+      using SX            = SimplexConfig<Sig::geometry, Sig::q, trial::order, ck, Sig::test_space::order, Sig::test_c, MASK, Sig::EPB>;
+      P.simplex_trial_tab = simplex_table_dev(Sig::geometry, trial::order, Sig::q);
+      P.simplex_test_tab  = simplex_table_dev(Sig::geometry, Sig::test_space::order, Sig::q);
+      if (!P.simplex_trial_tab || !P.simplex_test_tab) return int(cudaErrorMemoryAllocation);
+      auto kernel = &simplex_element_gradient_kernel<Sig::geometry, Sig::q, trial::order, ck, Sig::test_space::order, Sig::test_c, MASK, Sig::EPB>;
+      const size_t smem = size_t(SX::grad_smem_doubles) * sizeof(double);
+      if (int e = ensure_smem(kernel, smem)) return e;
+      kernel<<<(a->num_elements + SX::EPB - 1) / SX::EPB, SX::threads, smem, cudaStream_t(stream)>>>(P);
+      sb_count_launch();
+      return int(cudaGetLastError());
+    } else {
+      auto         kernel = &element_gradient_kernel<Sig::dim, Sig::q, nk, ck, Sig::test_n, Sig::test_c, MASK, Sig::EPB>;
+      const size_t smem   = size_t(C::smem_doubles) * sizeof(double);
+      if (int e = ensure_smem(kernel, smem)) return e;
+      const int grid = (a->num_elements + C::EPB - 1) / C::EPB;
+      kernel<<<grid, C::threads, smem, cudaStream_t(stream)>>>(P);
+      sb_count_launch();
+      return int(cudaGetLastError());
+    }
   }
 }
 

@@ -8,7 +8,7 @@ import numpy as np
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 GOLDEN = os.path.join(ROOT, "tests", "golden")
 
-KIND_TO_NAME = {5: "hex", 3: "quad"}
+KIND_TO_NAME = {5: "hex", 3: "quad", 4: "tet", 2: "tri"}
 
 
 def golden_names():

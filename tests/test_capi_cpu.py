@@ -34,7 +34,7 @@ def test_version_and_registry():
     assert "solid_neohookean_hex_p2" in names and "solid_linear_isotropic_hex_p1" in names
 
 
-@pytest.mark.parametrize("geom", [capi.SEGMENT, capi.SQUARE, capi.CUBE])
+@pytest.mark.parametrize("geom", [capi.SEGMENT, capi.TRIANGLE, capi.SQUARE, capi.TETRAHEDRON, capi.CUBE])
 @pytest.mark.parametrize("p", [1, 2, 3])
 def test_lexicographic_permutation_matches_oracle(geom, p):
     assert np.array_equal(capi.lexicographic_permutation(geom, p), fo.lexicographic_permutation(geom, p))

@@ -19,15 +19,15 @@ def run_oracle(prob, wrt=1, state=None):
     mesh_table = prob["mesh_dof_info"] & MASK
     byvdim = int(prob["mesh_ordering"]) == 1
     X_q, J_q = fo.geometric_factors(fo.gather(mesh_table, prob["mesh_nodes"], dim, byvdim), int(prob["mesh_order"]), q,
-                                    dim)
+                                    dim, geom)
     qf = fo.make_qf(str(prob["kind"]), list(prob["params"]))
     trials = [fo.gather(shape_table, prob["S"], dim), fo.gather(table, prob["U"], vdim),
               fo.gather(table, prob["A"], vdim)]
     if state is None and "qdata0" in prob:
-        state = j2_state(prob["qdata0"], int(prob["ne"]), q**dim)
-    r_E, blocks = fo.evaluation_kernel(qf, trials, [1, p, p], X_q, J_q, p, q, dim, wrt=wrt, state=state)
+        state = j2_state(prob["qdata0"], int(prob["ne"]), fo.num_quadrature_points(geom, q))
+    r_E, blocks = fo.evaluation_kernel(qf, trials, [1, p, p], X_q, J_q, p, q, dim, wrt=wrt, state=state, geom=geom)
     return dict(table=table, shape_table=shape_table, X_q=X_q, J_q=J_q, r_E=r_E, blocks=blocks, p=p, q=q, dim=dim,
-                vdim=vdim)
+                vdim=vdim, geom=geom)
 
 
 def j2_state(qdata, ne, nq):
@@ -65,7 +65,7 @@ def test_residual_and_jvp(case):
     prob, o = case
     assert rel_l2(o["r_E"], prob["r_E"]) < 1e-13
     dU_E = fo.gather(o["table"], prob["dU"], o["vdim"])
-    dr_E = fo.action_of_gradient_kernel(o["blocks"], dU_E, o["p"], o["p"], o["q"], o["dim"])
+    dr_E = fo.action_of_gradient_kernel(o["blocks"], dU_E, o["p"], o["p"], o["q"], o["dim"], o["geom"])
     assert rel_l2(dr_E, prob["dr_E"]) < 1e-13
 
 
@@ -74,7 +74,7 @@ def test_state_update(case):
     prob, _ = case
     if "qdata1" not in prob:
         pytest.skip("stateless integrand")
-    ne, nq = int(prob["ne"]), (int(prob["p"]) + 1)**int(prob["dim"])
+    ne, nq = int(prob["ne"]), fo.num_quadrature_points(int(prob["geom"]), int(prob["p"]) + 1)
     st = j2_state(prob["qdata0"], ne, nq)
     run_oracle(prob, wrt=-1, state=st)
     new = st["_updated"]
@@ -90,12 +90,13 @@ def test_other_arguments(case):
     o2 = run_oracle(prob, wrt=2)
     dU_E = fo.gather(o2["table"], prob["dU"], o2["vdim"])
     dr = fo.scatter_add(o2["table"], fo.action_of_gradient_kernel(o2["blocks"], dU_E, o2["p"], o2["p"], o2["q"],
-                                                                 o2["dim"]), np.zeros(len(prob["U"])), o2["vdim"])
+                                                                 o2["dim"], o2["geom"]), np.zeros(len(prob["U"])),
+                        o2["vdim"])
     assert rel_l2(dr, prob["dr_da"]) < 1e-13
     o0 = run_oracle(prob, wrt=0)
     dS_E = fo.gather(o0["shape_table"], prob["dS"], o0["dim"])
-    dr = fo.scatter_add(o0["table"], fo.action_of_gradient_kernel(o0["blocks"], dS_E, 1, o0["p"], o0["q"], o0["dim"]),
-                        np.zeros(len(prob["U"])), o0["vdim"])
+    dr = fo.scatter_add(o0["table"], fo.action_of_gradient_kernel(o0["blocks"], dS_E, 1, o0["p"], o0["q"], o0["dim"],
+                                                                 o0["geom"]), np.zeros(len(prob["U"])), o0["vdim"])
     assert rel_l2(dr, prob["dr_dshape"]) < 1e-13
 
 
@@ -103,7 +104,7 @@ def test_element_matrices_and_csr(case):
     prob, o = case
     if "K_e" not in prob:
         pytest.skip("fixture without matrices")
-    K_e = fo.element_gradient_kernel(o["blocks"], o["p"], o["p"], o["q"], o["dim"])
+    K_e = fo.element_gradient_kernel(o["blocks"], o["p"], o["p"], o["q"], o["dim"], o["geom"])
     assert rel_l2(K_e, prob["K_e"]) < 1e-13
     vd = fo.element_vdofs(o["table"], o["vdim"], int(prob["num_nodes"]))
     row_ptr, col_ind, keys = fo.csr_pattern(vd, vd, len(prob["U"]))
