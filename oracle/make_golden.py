@@ -116,6 +116,82 @@ def reference_problem(mesh_spec, kind, p, params, vdim, seed=42, with_matrix=Tru
     return out
 
 
+def reference_multifield_problem(mesh_spec, kind, p, params, test_vdim, trial_vdims, amps, seed=42, u_amp=0.01):
+    """One reference domain Integral with an arbitrary list of trial fields after the shape displacement: signature
+    H1<p,test_vdim>(shape H1<1,dim>, H1<p,trial_vdims[0]>, ...) -- the parameterized physics modules (thermomechanics:
+    SolidMechanics<..., Parameters<H1<p>>> and HeatTransfer<..., Parameters<H1<p,dim>>>, thermomechanics.hpp:534-537).
+    amps[i] scales the uniform(-1,1) draw of trial field i + 1 (offsets: see `offsets`).  Outputs: residual, the Jacobian
+    action and the assembled (possibly rectangular) matrix w.r.t. EVERY argument, and the committed state."""
+    mesh = make_mesh(mesh_spec)
+    dim = mesh.dim
+    tag = f"{dim}d_p{p}"
+    test = ref.Space(mesh, p, test_vdim)
+    shape_space = ref.Space(mesh, 1, dim)
+    spaces, by_vdim = [shape_space], {}
+    for v in trial_vdims:
+        if v not in by_vdim:
+            by_vdim[v] = test if v == test_vdim else ref.Space(mesh, p, v)
+        spaces.append(by_vdim[v])
+    rng = np.random.default_rng(seed)
+    fields = [0.01 * rng.uniform(-1.0, 1.0, shape_space.vsize)]
+    for sp, (amp, offset) in zip(spaces[1:], amps):
+        fields.append(offset + amp * rng.uniform(-1.0, 1.0, sp.vsize))
+    dfields = [rng.uniform(0.0, 1.0, sp.vsize) for sp in spaces]
+    q = p + 1
+    order, ordering, nodes, nodes_info = mesh.nodes()
+    X_q, J_q = mesh.geometric_factors(q)
+    I = ref.Integral(f"{kind}_{tag}", mesh, params)
+    out = dict(kind=kind, geom=mesh.geom, dim=dim, p=p, ne=mesh.ne, params=np.asarray(params, dtype=np.float64),
+               test_vdim=test_vdim, trial_vdims=np.asarray([dim] + list(trial_vdims)), num_nodes=test.num_nodes,
+               native_dofs=test.native_dofs(), dof_info=test.dof_info(),
+               shape_native_dofs=shape_space.native_dofs(), shape_num_nodes=shape_space.num_nodes,
+               mesh_order=order, mesh_ordering=ordering, mesh_nodes=nodes, mesh_dof_info=nodes_info,
+               mesh_num_nodes=len(nodes) // dim, X_q=X_q, J_q=J_q)
+    for i, (f, df) in enumerate(zip(fields, dfields)):
+        out[f"field{i}"], out[f"dfield{i}"] = f, df
+    ins = [sp.gather(f) for sp, f in zip(spaces, fields)]
+    if I.state_bytes():
+        out["qdata0"] = I.get_qdata()
+    r_E = I.mult(0.0, ins, test.esize)
+    out["r_E"] = r_E
+    out["r"] = test.scatter_add(r_E, np.zeros(test.vsize))
+    npe = test.dof_info().shape[1]
+    for i, sp in enumerate(spaces):
+        r_E_ad = I.mult(0.0, ins, test.esize, wrt=i)
+        assert np.array_equal(r_E_ad, r_E) or np.allclose(r_E_ad, r_E, rtol=1e-13, atol=1e-300)
+        out[f"dr{i}"] = test.scatter_add(I.jvp(i, sp.gather(dfields[i]), test.esize), np.zeros(test.vsize))
+        npe_k = sp.dof_info().shape[1]
+        vk = dim if i == 0 else trial_vdims[i - 1]
+        K_e = I.element_gradient(i, mesh.ne, npe_k * vk, npe * test_vdim)
+        csr = ref.Csr(test, sp)
+        rp, ci = csr.pattern()
+        out[f"row_ptr{i}"], out[f"col_ind{i}"], out[f"values{i}"] = rp, ci, csr.assemble(K_e)
+    if I.state_bytes():
+        I.mult(0.0, ins, test.esize, update_state=True)
+        out["qdata1"] = I.get_qdata()
+        out["r_E_after_commit"] = I.mult(0.0, ins, test.esize)
+    return out
+
+
+# thermomechanics (BASELINE.json configs[3]: coupled HeatTransfer + SolidMechanics, thermoelastic material, tet mesh, p=1)
+# params: density E nu C_v alpha theta_ref k [geom_nonlin]; amps = (amplitude, offset) per trial field after the shape
+_GSV = [1.0, 100.0, 0.25, 1.0, 1.0e-3, 1.0, 1.0]
+MULTIFIELD_FIXTURES = [
+    ("thermoelastic_solid_tet_p1_beam", dict(mesh_spec=("file", "beam-tet.mesh", 0), kind="thermoelastic_solid", p=1,
+                                             params=_GSV + [1.0], test_vdim=3, trial_vdims=[3, 3, 1],
+                                             amps=[(0.01, 0.0), (1.0, 0.0), (0.5, 2.0)])),
+    ("thermoelastic_thermal_tet_p1_beam", dict(mesh_spec=("file", "beam-tet.mesh", 0), kind="thermoelastic_thermal",
+                                               p=1, params=_GSV, test_vdim=1, trial_vdims=[1, 1, 3],
+                                               amps=[(0.5, 2.0), (1.0, 0.0), (0.01, 0.0)])),
+    ("thermoelastic_solid_hex_p2_cart", dict(mesh_spec=("cart3d", 2, 1, 1, 0.02), kind="thermoelastic_solid", p=2,
+                                             params=_GSV + [1.0], test_vdim=3, trial_vdims=[3, 3, 1],
+                                             amps=[(0.01, 0.0), (1.0, 0.0), (0.5, 2.0)])),
+    ("thermoelastic_thermal_tet_p2_cart", dict(mesh_spec=("cart3d_tet", 1, 1, 1, 0.02), kind="thermoelastic_thermal",
+                                               p=2, params=_GSV, test_vdim=1, trial_vdims=[1, 1, 3],
+                                               amps=[(0.5, 2.0), (1.0, 0.0), (0.01, 0.0)])),
+]
+
+
 def reference_boundary_problem(mesh_spec, kind, p, params, seed=42, shape_amp=0.0, u_amp=0.01):
     """One reference BOUNDARY Integral (MakeBoundaryIntegral, integral.hpp:322-350) on EntireBoundary(mesh) with the
     SolidMechanics signature H1<p,dim>(shape H1<1,dim>, u, a): inputs (native face dofs of every space, mesh nodes) and
@@ -252,6 +328,15 @@ def main():
         path = os.path.join(GOLDEN_DIR, name + ".npz")
         np.savez_compressed(path, **data)
         print(f"{name}: ne={data['ne']} vsize={len(data['U'])} -> {os.path.getsize(path) / 1024:.0f} KiB")
+    for name, kw in MULTIFIELD_FIXTURES:
+        if only and name not in only:
+            continue
+        data = reference_multifield_problem(**kw)
+        path = os.path.join(GOLDEN_DIR, "multi_" + name + ".npz")
+        np.savez_compressed(path, **data)
+        print(f"{name}: ne={data['ne']} |r|={np.linalg.norm(data['r']):.3e} " +
+              " ".join(f"|dr{i}|={np.linalg.norm(data[f'dr{i}']):.3e}" for i in range(4)) +
+              f" -> {os.path.getsize(path) / 1024:.0f} KiB")
     for name, kw in BOUNDARY_FIXTURES:
         if only and name not in only:
             continue

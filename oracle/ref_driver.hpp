@@ -14,6 +14,7 @@
 #include "serac/numerics/functional/shape_aware_functional.hpp"
 #include "serac/physics/materials/solid_material.hpp"
 #include "serac/physics/materials/thermal_material.hpp"
+#include "serac/physics/materials/green_saint_venant_thermoelastic.hpp"
 
 namespace ref {
 

@@ -155,6 +155,101 @@ ref::Registrar r4("thermal_linear_conductor_" TAG, [](mfem::Mesh& mesh, const do
 });
 
 #if REF_DIM == 3
+// ---- thermomechanics (BASELINE.json configs[3]) ---------------------------------------------------------------------
+// functor shells restating Thermomechanics::ThermalMaterialInterface / MechanicalMaterialInterface
+// (src/serac/physics/thermomechanics.hpp:272-352), which live inside a class template that needs MPI to instantiate;
+// the material itself (materials/green_saint_venant_thermoelastic.hpp) and the integrand functors above are the
+// reference's, with the parameter pack forwarded as SolidMechanics / HeatTransfer do (solid_mechanics.hpp:834-852,
+// heat_transfer.hpp:392-402).
+template <typename Material>
+struct MechanicalInterface {
+  using State = typename Material::State;
+  Material mat;
+  double   density;
+  template <typename T1, typename T2>
+  auto operator()(State& state, const T1& displacement_gradient, const T2& temperature) const
+  {
+    auto [theta, dtheta_dX]         = temperature;
+    auto [T, heat_capacity, s0, q0] = mat(state, displacement_gradient, theta, dtheta_dX);
+    return T;
+  }
+};
+
+template <typename Material>
+struct ThermalInterface {
+  using State = typename Material::State;
+  Material mat;
+  template <typename T1, typename T2, typename T3, typename T4>
+  auto operator()(const T1&, const T2& temperature, const T3& temperature_gradient, const T4& displacement) const
+  {
+    State state{};
+    auto [u, du_dX]                 = displacement;
+    auto [T, heat_capacity, s0, q0] = mat(state, du_dX, temperature, temperature_gradient);
+    return serac::tuple{heat_capacity, q0};
+  }
+};
+
+template <typename Material>
+struct MaterialStressWithParam {
+  Material material_;
+  bool     geom_nonlin_;
+  template <typename X, typename State, typename Displacement, typename Acceleration, typename Param>
+  auto operator()(double, X, State& state, Displacement displacement, Acceleration acceleration, Param param) const
+  {
+    auto du_dX   = get<1>(displacement);
+    auto d2u_dt2 = get<0>(acceleration);
+    auto stress  = material_(state, du_dX, param);
+    auto dx_dX   = 0.0 * du_dX + Identity<dim>();
+    if (geom_nonlin_) dx_dX += du_dX;
+    auto flux = dot(stress, transpose(inv(dx_dX))) * det(dx_dX);
+    return serac::tuple{material_.density * d2u_dt2, flux};
+  }
+};
+
+template <typename Material>
+struct ThermalIntegrandWithParam {
+  Material material_;
+  template <typename X, typename T, typename dT_dt, typename Param>
+  auto operator()(double, X x, T temperature, dT_dt dtemp_dt, Param param) const
+  {
+    auto [u, du_dX]                 = temperature;
+    auto du_dt                      = get<0>(dtemp_dt);
+    auto [heat_capacity, heat_flux] = material_(x, u, du_dX, param);
+    return serac::tuple{heat_capacity * du_dt, -1.0 * heat_flux};
+  }
+};
+
+using GSV = GreenSaintVenantThermoelasticMaterial;
+
+ref::Registrar r7("thermoelastic_solid_" TAG, [](mfem::Mesh& mesh, const double* q, int n) {
+  SLIC_ERROR_IF(n != 8, "params: density E nu C_v alpha theta_ref k geom_nonlin");
+  GSV mat{q[0], q[1], q[2], q[3], q[4], q[5], q[6]};
+  using Mech = MechanicalInterface<GSV>;
+  using sig  = solid_test(H1<1, dim>, H1<p, dim>, H1<p, dim>, H1<p>);
+  using QF   = ShapeAwareWithState<MaterialStressWithParam<Mech>, solid_test, H1<p, dim>, H1<p, dim>, H1<p>>;
+  QF     qf{MaterialStressWithParam<Mech>{Mech{mat, mat.density}, q[7] != 0.0}};
+  ref::IntegralHolder h;
+  Domain d  = EntireDomain(mesh);
+  auto   qd = make_qdata<GSV::State>(mesh, h, GSV::State{});
+  h.integral   = std::make_unique<Integral>(MakeDomainIntegral<sig, p + 1, dim>(d, qf, qd, {0, 1, 2, 3}));
+  h.num_trials = 4;
+  return h;
+});
+
+ref::Registrar r8("thermoelastic_thermal_" TAG, [](mfem::Mesh& mesh, const double* q, int n) {
+  SLIC_ERROR_IF(n != 7, "params: density E nu C_v alpha theta_ref k");
+  GSV mat{q[0], q[1], q[2], q[3], q[4], q[5], q[6]};
+  using Therm = ThermalInterface<GSV>;
+  using sig   = H1<p>(H1<1, dim>, H1<p>, H1<p>, H1<p, dim>);
+  using QF    = ShapeAware<ThermalIntegrandWithParam<Therm>, H1<p>, H1<p>, H1<p>, H1<p, dim>>;
+  QF     qf{ThermalIntegrandWithParam<Therm>{Therm{mat}}};
+  ref::IntegralHolder h;
+  Domain d     = EntireDomain(mesh);
+  h.integral   = std::make_unique<Integral>(MakeDomainIntegral<sig, p + 1, dim>(d, qf, NoQData, {0, 1, 2, 3}));
+  h.num_trials = 4;
+  return h;
+});
+
 // ---- boundary integrands (faces of the 3D mesh) -------------------------------------------------------------------
 // functor shells restating ShapeAwareFunctional::ShapeAwareBoundaryIntegrandWrapper (shape_aware_functional.hpp:474-499)
 // and the lambdas of SolidMechanics::setTraction / setPressure (solid_mechanics.hpp:1030-1036, 1075-1101) with a

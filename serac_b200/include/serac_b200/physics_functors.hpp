@@ -299,6 +299,90 @@ struct LinearIsotropicConductor {
 
 }  // namespace heat_transfer
 
+// ------------------------------------------------------------------------------------------------
+// thermomechanics (BASELINE.json configs[3]): one material evaluated by both physics modules
+// ------------------------------------------------------------------------------------------------
+/// Green-Saint Venant thermoelastic model (materials/green_saint_venant_thermoelastic.hpp:26-92): returns
+/// tuple{Cauchy stress, volumetric heat capacity, internal heat source, heat flux}
+struct GreenSaintVenantThermoelasticMaterial {
+  double density;    ///< density
+  double E;          ///< Young's modulus
+  double nu;         ///< Poisson's ratio
+  double C_v;        ///< volumetric heat capacity
+  double alpha;      ///< thermal expansion coefficient
+  double theta_ref;  ///< datum temperature for thermal expansion
+  double k;          ///< thermal conductivity
+
+  struct State {
+    double strain_trace;  ///< trace of the Green-Saint Venant strain tensor
+  };
+
+  template <typename T1, typename T2, typename T3>
+  SERAC_HOST_DEVICE auto operator()(State& state, const tensor<T1, 3, 3>& grad_u, T2 theta,
+                                    const tensor<T3, 3>& grad_theta) const
+  {
+    const double K    = E / (3.0 * (1.0 - 2.0 * nu));
+    const double G    = 0.5 * E / (1.0 + nu);
+    const auto   I    = Identity<3>();
+    auto         F    = grad_u + I;
+    const auto   Eg   = solid_mechanics::greenStrain(grad_u);
+    const auto   trEg = tr(Eg);
+
+    const auto S     = 2.0 * G * dev(Eg) + K * (trEg - 3.0 * alpha * (theta - theta_ref)) * I;
+    const auto P     = dot(F, S);
+    const auto sigma = dot(P, transpose(F)) / det(F);
+
+    const auto s0 = -3 * K * alpha * theta * (trEg - state.strain_trace);  // internal heat source
+    const auto q0 = -k * grad_theta;                                       // heat flux
+
+    state.strain_trace = get_value(trEg);
+    return serac::tuple{sigma, C_v, s0, q0};
+  }
+};
+
+namespace thermomechanics {
+
+/// makes a thermomechanical material usable by HeatTransfer (thermomechanics.hpp:272-310); the State is a throw-away
+/// local, as in the reference
+template <typename ThermalMechanicalMaterial>
+struct ThermalMaterialInterface {
+  using State = typename ThermalMechanicalMaterial::State;
+  ThermalMechanicalMaterial mat;
+  SERAC_HOST_DEVICE ThermalMaterialInterface(const ThermalMechanicalMaterial& m) : mat(m) {}
+
+  template <typename T1, typename T2, typename T3, typename T4, typename... param_types>
+  SERAC_HOST_DEVICE auto operator()(const T1& /* x */, const T2& temperature, const T3& temperature_gradient,
+                                    const T4& displacement, param_types... parameters) const
+  {
+    State state{};
+    auto  du_dX = get<DERIVATIVE>(displacement);
+    auto  resp  = mat(state, du_dX, temperature, temperature_gradient, parameters...);
+    return serac::tuple{get<1>(resp), get<3>(resp)};
+  }
+};
+
+/// makes a thermomechanical material usable by SolidMechanics (thermomechanics.hpp:318-352)
+template <typename ThermalMechanicalMaterial>
+struct MechanicalMaterialInterface {
+  using State = typename ThermalMechanicalMaterial::State;
+  static constexpr bool     parameterized = true;
+  ThermalMechanicalMaterial mat;
+  double                    density;
+  SERAC_HOST_DEVICE MechanicalMaterialInterface(ThermalMechanicalMaterial m) : mat(m), density(m.density) {}
+
+  template <typename T1, typename T2, typename... param_types>
+  SERAC_HOST_DEVICE auto operator()(State& state, const T1& displacement_gradient, const T2& temperature,
+                                    param_types... parameters) const
+  {
+    auto theta     = get<VALUE>(temperature);
+    auto dtheta_dX = get<DERIVATIVE>(temperature);
+    auto resp      = mat(state, displacement_gradient, theta, dtheta_dX, parameters...);
+    return get<0>(resp);
+  }
+};
+
+}  // namespace thermomechanics
+
 /// does material M provide piola_tangent_coefficients(state, du_dX) -> {c1, c2, c3} with
 ///   d P[a][i] / d F[b][m] = c1 Finv[i][a] Finv[m][b] + c2 Finv[i][b] Finv[m][a] + c3 d_ab d_im      (P = J sigma F^-T) ?
 template <typename M, typename = void>
@@ -307,6 +391,15 @@ struct has_piola_tangent_coefficients : std::false_type {
 template <typename M>
 struct has_piola_tangent_coefficients<M, std::void_t<decltype(M::closed_form_piola_tangent)>>
     : std::bool_constant<M::closed_form_piola_tangent> {
+};
+
+/// materials that take parameter fields after du_dX (e.g. MechanicalMaterialInterface: the temperature) are
+/// differentiated with dual numbers end to end: the tangent fast path below is written for (displacement, acceleration)
+template <typename M, typename = void>
+struct is_parameterized_material : std::false_type {
+};
+template <typename M>
+struct is_parameterized_material<M, std::void_t<decltype(M::parameterized)>> : std::bool_constant<M::parameterized> {
 };
 
 /// how MaterialStressFunctor knows its geometric-nonlinearity flag: at run time (the reference's member), or fixed at
@@ -376,7 +469,7 @@ struct MaterialStressFunctor {
   ///   d(parent flux)[a][k]/d(parent grad)[b][l] = scale ( c1 A[k][a] A[l][b] + c2 A[k][b] A[l][a] + c3 d_ab (M M^T)[k][l] )
   /// Same mathematics as the reference's dual-number evaluation of operator() above, to rounding.
   template <int WRT>
-  static constexpr bool has_flux_tangent = (WRT == 0);
+  static constexpr bool has_flux_tangent = (WRT == 0) && !is_parameterized_material<Material>::value;
 
   template <typename X, typename State, int dim, typename Sink, typename Displacement, typename Acceleration>
   SERAC_HOST_DEVICE void flux_tangent(std::integral_constant<int, 0>, double, const X&, State& state,

@@ -14,7 +14,12 @@ KIND_TO_NAME = {5: "hex", 3: "quad", 4: "tet", 2: "tri"}
 def golden_names():
     """small fixtures with full reference outputs (the config_* files are full-size inputs + sampled outputs)"""
     names = sorted(os.path.splitext(os.path.basename(f))[0] for f in glob.glob(os.path.join(GOLDEN, "*.npz")))
-    return [n for n in names if not n.startswith("config_") and not n.startswith("bdr_")]
+    return [n for n in names if not n.startswith(("config_", "bdr_", "multi_"))]
+
+
+def multifield_golden_names():
+    """parameterized-physics fixtures (oracle/make_golden.py MULTIFIELD_FIXTURES)"""
+    return sorted(os.path.splitext(os.path.basename(f))[0] for f in glob.glob(os.path.join(GOLDEN, "multi_*.npz")))
 
 
 def boundary_golden_names():
@@ -114,3 +119,41 @@ class BoundaryProduct:
 
     def fields(self):
         return [self.Gf_shape.field(self.S), self.Gf.field(self.U), self.Gf.field(self.A)]
+
+
+class MultiFieldProduct:
+    """The product objects for one multi-field parity problem (oracle.make_golden.reference_multifield_problem):
+    Functional H1<p,test_vdim>(shape H1<1,dim>, H1<p,v1>, H1<p,v2>, H1<p,v3>) with one domain integral -- the
+    signatures of the parameterized physics modules (thermomechanics.hpp:534-537)."""
+
+    def __init__(self, prob, device):
+        import torch
+        from serac_b200 import capi
+        self.capi, self.torch, self.prob, self.dev = capi, torch, prob, device
+        geom, p, dim = int(prob["geom"]), int(prob["p"]), int(prob["dim"])
+        self.geom, self.p, self.dim = geom, p, dim
+        self.dof_info = capi.h1_dof_info(geom, p, prob["native_dofs"])
+        self.shape_dof_info = capi.h1_dof_info(geom, 1, prob["shape_native_dofs"])
+        nn = int(prob["num_nodes"])
+        vdims = [int(v) for v in prob["trial_vdims"]]
+        self.G_shape = capi.ElementRestriction(self.shape_dof_info, dim, int(prob["shape_num_nodes"]))
+        by_vdim = {}
+        for v in set(vdims[1:]) | {int(prob["test_vdim"])}:
+            by_vdim[v] = capi.ElementRestriction(self.dof_info, v, nn)
+        self.G_test = by_vdim[int(prob["test_vdim"])]
+        self.G_trials = [self.G_shape] + [by_vdim[v] for v in vdims[1:]]
+        self.G_mesh = capi.ElementRestriction(prob["mesh_dof_info"], dim, int(prob["mesh_num_nodes"]),
+                                              int(prob["mesh_ordering"]))
+        t = lambda a: torch.as_tensor(np.ascontiguousarray(a), dtype=torch.float64, device=device)
+        self.t = t
+        self.nodes = t(prob["mesh_nodes"])
+        self.X_q, self.J_q = capi.geometric_factors(geom, int(prob["mesh_order"]), p + 1, self.G_mesh, self.nodes)
+        name = f"{prob['kind']}_{KIND_TO_NAME[geom]}_p{p}"
+        self.integral = capi.Integral(name, prob["params"], self.X_q, self.J_q, int(prob["ne"]))
+        self.fields = [t(prob[f"field{i}"]) for i in range(len(vdims))]
+        self.dfields = [t(prob[f"dfield{i}"]) for i in range(len(vdims))]
+        self.F = capi.Functional(self.G_test, self.G_trials)
+        self.F.AddDomainIntegral(self.integral, list(range(len(vdims))))
+        if self.integral.table.state_bytes:
+            self.qdata = t(prob["qdata0"]).clone()
+            self.integral.set_qdata(self.qdata)
