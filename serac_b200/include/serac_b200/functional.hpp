@@ -1,0 +1,494 @@
+// serac_b200: the C++ host side -- `serac::Functional<test(trials...)>` with the reference's public API, driving the
+// C ABI (include/serac_b200.h) and nothing else.
+//
+// Mirrors (names, argument meaning, ownership and error behaviour; not code) of
+//   src/serac/numerics/functional/functional.hpp:189-745   Functional, Gradient, assemble, differentiate_wrt, updateQdata
+//   src/serac/numerics/functional/domain.hpp               Domain, EntireDomain
+//   src/serac/numerics/functional/quadrature_data.hpp      QuadratureData<T>, NoQData, EmptyQData
+// The mesh / finite-element-space layer is mfem's in the reference and stays out of scope: the three
+// small host structs below (FiniteElementSpace, Mesh, Vector) carry exactly what Functional reads from
+// mfem::ParFiniteElementSpace / mfem::Mesh / mfem::Vector -- native element dofs, node coordinates, sizes -- so an
+// mfem build fills them with GetElementDofs / GetNodes and everything downstream is unchanged.
+//
+// q-functions are device code: translation units that instantiate Functional are compiled by nvcc
+// (-std=c++20 --expt-relaxed-constexpr).  nvcc does not allow generic (auto-parameter) extended lambdas, so a
+// q-function is a functor struct with a templated operator() -- the form serac's own physics modules use.
+//
+// Errors: the reference aborts through SLIC_ERROR_ROOT (functional.hpp:77-98); here a non-zero C-ABI status prints
+// sb_last_error() and aborts.  There is no CPU fallback.
+#pragma once
+
+#include <algorithm>
+#include <array>
+#include <cstdio>
+#include <cstdlib>
+#include <memory>
+#include <numeric>
+#include <tuple>
+#include <vector>
+
+#include "serac_b200.h"
+#include "serac_b200/kernel_table.cuh"
+
+namespace serac {
+
+#define SERAC_B200_CHECK(expr)                                                                      \
+  do {                                                                                              \
+    int _rc = (expr);                                                                               \
+    if (_rc != SB_OK) {                                                                             \
+      std::fprintf(stderr, "serac::Functional: %s failed (%d): %s\n", #expr, _rc, sb_last_error()); \
+      std::abort();                                                                                 \
+    }                                                                                               \
+  } while (0)
+
+#define SERAC_B200_CUDA(expr)                                                                                 \
+  do {                                                                                                        \
+    cudaError_t _e = (expr);                                                                                  \
+    if (_e != cudaSuccess) {                                                                                  \
+      std::fprintf(stderr, "serac::Functional: %s failed: %s\n", #expr, cudaGetErrorString(_e));              \
+      std::abort();                                                                                           \
+    }                                                                                                         \
+  } while (0)
+
+enum class Ordering : int
+{
+  byNODES = SB_ORDERING_BYNODES,
+  byVDIM  = SB_ORDERING_BYVDIM
+};
+
+/// device-resident vector (stand-in for mfem::Vector with device memory)
+class Vector {
+ public:
+  Vector() = default;
+  explicit Vector(int64_t n) { SetSize(n); }
+  explicit Vector(const std::vector<double>& host) { SetSize(int64_t(host.size())); set(host.data()); }
+  Vector(const Vector& o) { *this = o; }
+  Vector& operator=(const Vector& o)
+  {
+    if (this != &o) {
+      SetSize(o.n_);
+      if (n_) SERAC_B200_CUDA(cudaMemcpy(d_, o.d_, sizeof(double) * size_t(n_), cudaMemcpyDeviceToDevice));
+    }
+    return *this;
+  }
+  ~Vector() { cudaFree(d_); }
+  void SetSize(int64_t n)
+  {
+    if (n == n_) return;
+    cudaFree(d_);
+    d_ = nullptr;
+    n_ = n;
+    if (n) SERAC_B200_CUDA(cudaMalloc(&d_, sizeof(double) * size_t(n)));
+  }
+  int64_t       Size() const { return n_; }
+  const double* Read() const { return d_; }  ///< device pointer
+  double*       Write() { return d_; }
+  void set(const double* host) { SERAC_B200_CUDA(cudaMemcpy(d_, host, sizeof(double) * size_t(n_), cudaMemcpyHostToDevice)); }
+  void get(double* host) const { SERAC_B200_CUDA(cudaMemcpy(host, d_, sizeof(double) * size_t(n_), cudaMemcpyDeviceToHost)); }
+  std::vector<double> to_host() const
+  {
+    std::vector<double> h(static_cast<size_t>(n_));
+    if (n_) get(h.data());
+    return h;
+  }
+  Vector& operator=(double v)
+  {
+    std::vector<double> h(size_t(n_), v);
+    if (n_) set(h.data());
+    return *this;
+  }
+
+ private:
+  int64_t n_ = 0;
+  double* d_ = nullptr;
+};
+
+/// what Functional reads from an mfem::ParFiniteElementSpace: H1 order, vdim, ordering, GetNDofs() and, per element,
+/// fes->GetElementDofs(e) in mfem's native order (single-geometry meshes)
+struct FiniteElementSpace {
+  Geometry         geometry;
+  int              order;
+  int              vdim;
+  Ordering         ordering = Ordering::byVDIM;  // serac's default (serac_config.hpp.in:61-66)
+  int64_t          num_nodes;
+  int64_t          num_elements;
+  std::vector<int> native_element_dofs;  ///< [num_elements][nodes per element]
+  /// fes->GetFaceDofs of the mesh's boundary faces in mfem's native order (only needed by AddBoundaryIntegral)
+  int64_t          num_boundary_faces = 0;
+  std::vector<int> native_boundary_face_dofs;  ///< [num_boundary_faces][nodes per face]
+  int64_t          GetVSize() const { return num_nodes * vdim; }
+};
+
+/// what Functional reads from an mfem::Mesh: the nodal grid function (Functional demands nodes, functional.hpp:74-89)
+struct Mesh {
+  FiniteElementSpace  nodes_space;  ///< vdim == space dimension
+  std::vector<double> nodes;        ///< L-vector of node coordinates in nodes_space's ordering
+  int                 Dimension() const { return dimension_of(nodes_space.geometry); }
+  int64_t             GetNE() const { return nodes_space.num_elements; }
+};
+
+/// a set of elements of one mesh (domain.hpp); EntireDomain(mesh) = all of them
+struct Domain {
+  const Mesh*      mesh;
+  bool             entire;
+  std::vector<int> elements;  ///< element ids when !entire
+};
+inline Domain EntireDomain(const Mesh& mesh) { return Domain{&mesh, true, {}}; }
+
+/// per-quadrature-point state buffer [elements][qpts] (quadrature_data.hpp:112-142), device resident
+template <typename T>
+struct QuadratureData {
+  QuadratureData(int64_t num_elements, int qpts_per_element, T init = T{}) : count(num_elements * qpts_per_element)
+  {
+    std::vector<T> h(size_t(count), init);
+    SERAC_B200_CUDA(cudaMalloc(&data, sizeof(T) * size_t(count)));
+    SERAC_B200_CUDA(cudaMemcpy(data, h.data(), sizeof(T) * size_t(count), cudaMemcpyHostToDevice));
+  }
+  ~QuadratureData() { cudaFree(data); }
+  QuadratureData(const QuadratureData&)            = delete;
+  QuadratureData& operator=(const QuadratureData&) = delete;
+  std::vector<T> to_host() const
+  {
+    std::vector<T> h(static_cast<size_t>(count));
+    SERAC_B200_CUDA(cudaMemcpy(h.data(), data, sizeof(T) * size_t(count), cudaMemcpyDeviceToHost));
+    return h;
+  }
+  int64_t count;
+  T*      data = nullptr;
+};
+/// sentinels (quadrature_data.hpp:20-37)
+inline const std::shared_ptr<QuadratureData<Nothing>> NoQData{};
+inline const std::shared_ptr<QuadratureData<Empty>>   EmptyQData{};
+
+/// tag returned by differentiate_wrt (functional.hpp:47-66)
+struct differentiate_wrt_this {
+  const Vector& ref;
+  operator const Vector&() const { return ref; }
+};
+inline differentiate_wrt_this differentiate_wrt(const Vector& v) { return differentiate_wrt_this{v}; }
+
+/// the local CSR triple assemble() hands back (what the reference wraps as mfem::SparseMatrix -> HypreParMatrix,
+/// functional.hpp:649-662; at one rank RAP with P = identity leaves it unchanged)
+struct CsrMatrix {
+  int64_t             num_rows = 0, num_cols = 0;
+  std::vector<int>    row_ptr, col_ind;
+  std::vector<double> values;
+};
+
+template <typename T>
+class Functional;
+
+template <typename test, typename... trials>
+class Functional<test(trials...)> {
+  static constexpr int num_trial_spaces = int(sizeof...(trials));
+  static constexpr int Q                = std::max({test::order, trials::order...}) + 1;  // functional.hpp:193
+
+  template <int i>
+  using trial_at = typename serac::detail::type_at<i, trials...>::type;
+
+ public:
+  class Gradient;
+
+  /// functional.hpp:219-281: one element restriction per space, built from the space's native element dofs
+  Functional(const FiniteElementSpace* test_fes, std::array<const FiniteElementSpace*, num_trial_spaces> trial_fes)
+      : test_space_(test_fes), trial_space_(trial_fes)
+  {
+    constexpr int orders[] = {trials::order..., 0};
+    constexpr int comps[]  = {trials::components..., 0};
+    check_space(*test_fes, test::order, test::components, "test");
+    G_test_ = make_restriction(*test_fes);
+    for (int i = 0; i < num_trial_spaces; i++) {
+      check_space(*trial_fes[size_t(i)], orders[i], comps[i], "trial");
+      // spaces that are the same object share one restriction
+      G_trial_[size_t(i)] = nullptr;
+      if (trial_fes[size_t(i)] == test_fes) G_trial_[size_t(i)] = G_test_;
+      for (int j = 0; j < i; j++)
+        if (trial_fes[size_t(j)] == trial_fes[size_t(i)]) G_trial_[size_t(i)] = G_trial_[size_t(j)];
+      if (!G_trial_[size_t(i)]) G_trial_[size_t(i)] = make_restriction(*trial_fes[size_t(i)]);
+    }
+    SERAC_B200_CHECK(sb_functional_create(G_test_, num_trial_spaces, G_trial_.data(), &F_));
+    output_L_.SetSize(test_fes->GetVSize());
+    grad_.reserve(size_t(num_trial_spaces));
+    for (int i = 0; i < num_trial_spaces; i++) grad_.emplace_back(*this, i);
+  }
+
+  ~Functional()
+  {
+    sb_functional_destroy(F_);
+    for (auto I : integrals_) sb_integral_destroy(I);
+    for (auto A : csr_) sb_csr_destroy(A);
+    std::vector<sb_restriction_t> freed;
+    auto release = [&](sb_restriction_t r) {
+      if (r && std::find(freed.begin(), freed.end(), r) == freed.end()) {
+        freed.push_back(r);
+        sb_restriction_destroy(r);
+      }
+    };
+    release(G_test_);
+    for (auto r : G_trial_) release(r);
+    for (auto r : mesh_restrictions_) release(r);
+    for (auto p : device_buffers_) cudaFree(p);
+  }
+  Functional(const Functional&)            = delete;
+  Functional& operator=(const Functional&) = delete;
+
+  /// functional.hpp:286-317.  integrand: callable `(double t, tuple{x, dx_dxi}, [State&,] tuple{value, grad}...)
+  /// -> tuple{source, flux}`; args...: which Functional arguments it depends on, in the order it takes them.
+  template <int dim, int... args, typename Integrand, typename StateType = Nothing>
+  void AddDomainIntegral(Dimension<dim>, DependsOn<args...>, const Integrand& integrand, Domain& domain,
+                         std::shared_ptr<QuadratureData<StateType>> qdata = NoQData)
+  {
+    static_assert(((args >= 0 && args < num_trial_spaces) && ...), "DependsOn<> index out of range");
+    const Mesh& mesh = *domain.mesh;
+    if (mesh.Dimension() != dim) fail("AddDomainIntegral: Dimension<dim> does not match the mesh");
+    const Geometry g = mesh.nodes_space.geometry;
+    if (g != test_space_->geometry) fail("AddDomainIntegral: mesh and test space geometries differ");
+    const sb_kernel_table* table = nullptr;
+    // the reference instantiates the kernels of every geometry of this dimension (functional.hpp:296-317)
+    if constexpr (dim == 3) {
+      if (g == Geometry::CUBE) table = table_for<Geometry::CUBE, Integrand, StateType, args...>();
+      if (g == Geometry::TETRAHEDRON) table = table_for<Geometry::TETRAHEDRON, Integrand, StateType, args...>();
+    } else if constexpr (dim == 2) {
+      if (g == Geometry::SQUARE) table = table_for<Geometry::SQUARE, Integrand, StateType, args...>();
+      if (g == Geometry::TRIANGLE) table = table_for<Geometry::TRIANGLE, Integrand, StateType, args...>();
+    }
+    if (!table) fail("AddDomainIntegral: unsupported element geometry");
+
+    // GeometricFactors (geometric_factors.cpp:62-138) on the domain's elements
+    sb_restriction_t G_mesh = make_restriction(mesh.nodes_space);
+    mesh_restrictions_.push_back(G_mesh);
+    const int64_t ne  = domain.entire ? mesh.GetNE() : int64_t(domain.elements.size());
+    const int     nq  = num_quadrature_points(g, Q);
+    double*       nodes_dev = device_copy(mesh.nodes.data(), mesh.nodes.size());
+    int*          elems_dev = domain.entire ? nullptr : device_copy(domain.elements.data(), domain.elements.size());
+    double*       X_q = device_alloc<double>(size_t(ne) * size_t(dim) * size_t(nq));
+    double*       J_q = device_alloc<double>(size_t(ne) * size_t(dim) * size_t(dim) * size_t(nq));
+    SERAC_B200_CHECK(sb_geometric_factors(int(g), mesh.nodes_space.order, Q, G_mesh, nodes_dev, elems_dev, ne, X_q, J_q,
+                                          nullptr));
+    sb_integral_t I = nullptr;
+    SERAC_B200_CHECK(sb_integral_create(table, &integrand, domain.entire ? nullptr : domain.elements.data(), ne, X_q, J_q,
+                                        &I));
+    if constexpr (!std::is_same_v<StateType, Nothing> && !std::is_empty_v<StateType>) {
+      if (!qdata) fail("AddDomainIntegral: integrand with state needs a QuadratureData buffer");
+      if (qdata->count != ne * nq) fail("AddDomainIntegral: QuadratureData size does not match elements x qpts");
+      SERAC_B200_CHECK(sb_integral_set_qdata(I, qdata->data));
+      qdata_keepalive_.push_back(qdata);
+    }
+    const int which[] = {args..., 0};
+    SERAC_B200_CHECK(sb_functional_add_integral(F_, I, which));
+    integrals_.push_back(I);
+  }
+
+  /// functional.hpp:328-354.  dim = dimension of the boundary faces; integrand: `(t, tuple{x, dx_dxi},
+  /// tuple{value, d/dxi}...) -> source` (trial derivatives stay in parent coordinates on a boundary).  Every space and
+  /// the mesh must carry its native boundary-face dofs.  Faces of 3D meshes (quadrilaterals / triangles).
+  template <int dim, int... args, typename Integrand>
+  void AddBoundaryIntegral(Dimension<dim>, DependsOn<args...>, const Integrand& integrand, const Mesh& mesh)
+  {
+    static_assert(dim == 2, "boundary integrals are implemented on the faces of 3D meshes");
+    static_assert(((args >= 0 && args < num_trial_spaces) && ...), "DependsOn<> index out of range");
+    if (mesh.Dimension() != dim + 1) fail("AddBoundaryIntegral: Dimension<dim> must be the mesh dimension - 1");
+    const Geometry g  = mesh.nodes_space.geometry;
+    const Geometry fg = (g == Geometry::CUBE) ? Geometry::SQUARE : Geometry::TRIANGLE;
+    const sb_kernel_table* table = nullptr;
+    if (fg == Geometry::SQUARE) table = boundary_table_for<Geometry::SQUARE, Integrand, args...>();
+    if (fg == Geometry::TRIANGLE) table = boundary_table_for<Geometry::TRIANGLE, Integrand, args...>();
+    const int64_t    nf     = mesh.nodes_space.num_boundary_faces;
+    sb_restriction_t G_mesh = make_face_restriction(mesh.nodes_space, fg);
+    mesh_restrictions_.push_back(G_mesh);
+    const int nq        = num_quadrature_points(fg, Q);
+    double*   nodes_dev = device_copy(mesh.nodes.data(), mesh.nodes.size());
+    double*   X_q       = device_alloc<double>(size_t(nf) * size_t(dim + 1) * size_t(nq));
+    double*   J_q       = device_alloc<double>(size_t(nf) * size_t(dim) * size_t(dim + 1) * size_t(nq));
+    SERAC_B200_CHECK(sb_geometric_factors(int(fg), mesh.nodes_space.order, Q, G_mesh, nodes_dev, nullptr, nf, X_q, J_q,
+                                          nullptr));
+    sb_integral_t I = nullptr;
+    SERAC_B200_CHECK(sb_integral_create(table, &integrand, nullptr, nf, X_q, J_q, &I));
+    sb_restriction_t test_faces = make_face_restriction(*test_space_, fg);
+    mesh_restrictions_.push_back(test_faces);
+    const int        which[] = {args..., 0};
+    sb_restriction_t trial_faces[sizeof...(args) + 1];
+    for (size_t i = 0; i < sizeof...(args); i++) {
+      trial_faces[i] = make_face_restriction(*trial_space_[size_t(which[i])], fg);
+      mesh_restrictions_.push_back(trial_faces[i]);
+    }
+    SERAC_B200_CHECK(sb_functional_add_boundary_integral(F_, I, which, test_faces, trial_faces));
+    integrals_.push_back(I);
+  }
+
+  /// functional.hpp:446-513: at most one argument may be wrapped in differentiate_wrt(); then the return value is
+  /// tuple{residual, Gradient&}, else the residual alone.  The references stay valid until the next call.
+  template <typename... T>
+  decltype(auto) operator()(double t, const T&... args)
+  {
+    static_assert(sizeof...(T) == sizeof...(trials), "one argument per trial space");
+    constexpr int num_differentiated = (int(std::is_same_v<T, differentiate_wrt_this>) + ...);
+    static_assert(num_differentiated <= 1, "at most one argument can be differentiated (functional.hpp:504)");
+    constexpr int wrt             = index_of_differentiation<T...>();
+    const Vector* in[]            = {&static_cast<const Vector&>(args)...};
+    const double* ptrs[sizeof...(T)];
+    for (size_t i = 0; i < sizeof...(T); i++) {
+      if (in[i]->Size() != trial_space_[i]->GetVSize()) fail("operator(): argument size does not match its space");
+      ptrs[i] = in[i]->Read();
+    }
+    SERAC_B200_CHECK(sb_functional_evaluate(F_, t, wrt, ptrs, 0, output_L_.Write(), 0, update_qdata_ ? 1 : 0, nullptr));
+    if constexpr (wrt >= 0) {
+      return std::tuple<Vector&, Gradient&>(output_L_, grad_[size_t(wrt)]);
+    } else {
+      return static_cast<Vector&>(output_L_);
+    }
+  }
+
+  /// functional.hpp:523: whether the next evaluations commit the quadrature-point state
+  void updateQdata(bool update_flag) { update_qdata_ = update_flag; }
+
+  /// functional.hpp:532-709: mfem::Operator whose Mult is the Jacobian action with the derivatives stored by the last
+  /// operator() that differentiated w.r.t. this argument
+  class Gradient {
+   public:
+    Gradient(Functional& f, int which) : form_(f), which_argument_(which), df_(f.test_space_->GetVSize()) {}
+    int64_t Height() const { return form_.test_space_->GetVSize(); }
+    int64_t Width() const { return form_.trial_space_[size_t(which_argument_)]->GetVSize(); }
+    /// Gradient::Mult (functional.hpp:556-559)
+    void Mult(const Vector& dx, Vector& df) const
+    {
+      if (dx.Size() != Width() || df.Size() != Height()) form_.fail("Gradient::Mult: size mismatch");
+      SERAC_B200_CHECK(sb_functional_jvp(form_.F_, which_argument_, dx.Read(), 0, df.Write(), 0, nullptr));
+    }
+    /// functional.hpp:562
+    Vector& operator()(const Vector& dx)
+    {
+      Mult(dx, df_);
+      return df_;
+    }
+    /// assemble(Gradient&) (functional.hpp:569-667) up to the local CSR triple
+    friend std::unique_ptr<CsrMatrix> assemble(Gradient& g) { return g.assemble_local(); }
+
+    std::unique_ptr<CsrMatrix> assemble_local()
+    {
+      Gradient&   g = *this;
+      Functional& f = g.form_;
+      const int   w = g.which_argument_;
+      if (f.csr_.size() < size_t(num_trial_spaces)) f.csr_.resize(size_t(num_trial_spaces), nullptr);
+      if (!f.csr_[size_t(w)]) SERAC_B200_CHECK(sb_csr_create(f.G_test_, f.G_trial_[size_t(w)], &f.csr_[size_t(w)]));
+      sb_csr_t A   = f.csr_[size_t(w)];
+      auto     out = std::make_unique<CsrMatrix>();
+      out->num_rows = sb_csr_num_rows(A);
+      out->num_cols = g.Width();
+      out->row_ptr.resize(size_t(out->num_rows) + 1);
+      out->col_ind.resize(size_t(sb_csr_nnz(A)));
+      out->values.resize(size_t(sb_csr_nnz(A)));
+      SERAC_B200_CHECK(sb_functional_assemble(f.F_, w, &A, out->values.data(), 1, nullptr));
+      SERAC_B200_CHECK(sb_csr_pattern_to_host(A, out->row_ptr.data(), out->col_ind.data()));
+      return out;
+    }
+
+   private:
+    Functional& form_;
+    int         which_argument_;
+    Vector      df_;
+  };
+
+ private:
+  template <typename... T>
+  static constexpr int index_of_differentiation()
+  {
+    constexpr bool d[] = {std::is_same_v<T, differentiate_wrt_this>...};
+    for (int i = 0; i < int(sizeof...(T)); i++)
+      if (d[i]) return i;
+    return SB_NO_DIFFERENTIATION;
+  }
+
+  template <Geometry g, typename Integrand, typename StateType, int... args>
+  static const sb_kernel_table* table_for()
+  {
+    using Sig = b200::Signature<g, Q, test, trial_at<args>...>;
+    // FAST = false: arbitrary user functors are differentiated with dual numbers, the reference's scheme; functors that
+    // provide their own tangent (physics_functors.hpp) opt in through provides_flux_tangent
+    static const sb_kernel_table table = b200::make_kernel_table<Sig, Integrand, StateType>();
+    return &table;
+  }
+
+  template <Geometry fg, typename Integrand, int... args>
+  static const sb_kernel_table* boundary_table_for()
+  {
+    using Sig = b200::BoundarySignature<fg, Q, test, trial_at<args>...>;
+    static const sb_kernel_table table = b200::make_boundary_kernel_table<Sig, Integrand>();
+    return &table;
+  }
+
+  /// FaceType::BOUNDARY ElementRestriction (element_restriction.cpp:279-388) from the native boundary-face dofs
+  sb_restriction_t make_face_restriction(const FiniteElementSpace& fes, Geometry fg) const
+  {
+    const int npf = b200::num_nodes(fg, fes.order);
+    if (fes.native_boundary_face_dofs.size() != size_t(fes.num_boundary_faces) * size_t(npf))
+      fail("AddBoundaryIntegral: a space does not carry its native boundary-face dofs");
+    std::vector<uint64_t> dof_info(size_t(fes.num_boundary_faces) * size_t(npf));
+    SERAC_B200_CHECK(sb_h1_lexicographic_dof_info(int(fg), fes.order, fes.native_boundary_face_dofs.data(),
+                                                  fes.num_boundary_faces, dof_info.data()));
+    sb_restriction_t r = nullptr;
+    SERAC_B200_CHECK(sb_restriction_create(dof_info.data(), fes.num_boundary_faces, npf, fes.vdim, fes.num_nodes,
+                                           int(fes.ordering), &r));
+    return r;
+  }
+
+  [[noreturn]] void fail(const char* msg) const
+  {
+    std::fprintf(stderr, "serac::Functional: %s\n", msg);
+    std::abort();
+  }
+
+  void check_space(const FiniteElementSpace& fes, int order, int components, const char* what) const
+  {
+    if (fes.order != order || fes.vdim != components) {
+      std::fprintf(stderr, "serac::Functional: %s space is H1<%d,%d> but the template signature says H1<%d,%d>\n", what,
+                   fes.order, fes.vdim, order, components);
+      std::abort();
+    }
+  }
+
+  /// ElementRestriction ctor (element_restriction.cpp:392-404) from the native element dofs
+  static sb_restriction_t make_restriction(const FiniteElementSpace& fes)
+  {
+    const int             npe = b200::num_nodes(fes.geometry, fes.order);
+    std::vector<uint64_t> dof_info(size_t(fes.num_elements) * size_t(npe));
+    SERAC_B200_CHECK(sb_h1_lexicographic_dof_info(int(fes.geometry), fes.order, fes.native_element_dofs.data(),
+                                                  fes.num_elements, dof_info.data()));
+    sb_restriction_t r = nullptr;
+    SERAC_B200_CHECK(sb_restriction_create(dof_info.data(), fes.num_elements, npe, fes.vdim, fes.num_nodes,
+                                           int(fes.ordering), &r));
+    return r;
+  }
+
+  template <typename T>
+  T* device_alloc(size_t n)
+  {
+    T* p = nullptr;
+    SERAC_B200_CUDA(cudaMalloc(&p, sizeof(T) * (n ? n : 1)));
+    device_buffers_.push_back(p);
+    return p;
+  }
+  template <typename T>
+  T* device_copy(const T* host, size_t n)
+  {
+    T* p = device_alloc<T>(n);
+    if (n) SERAC_B200_CUDA(cudaMemcpy(p, host, sizeof(T) * n, cudaMemcpyHostToDevice));
+    return p;
+  }
+
+  const FiniteElementSpace*                                test_space_;
+  std::array<const FiniteElementSpace*, num_trial_spaces> trial_space_;
+  sb_restriction_t                                         G_test_ = nullptr;
+  std::array<sb_restriction_t, num_trial_spaces>           G_trial_{};
+  sb_functional_t                                          F_ = nullptr;
+  std::vector<sb_integral_t>                               integrals_;
+  std::vector<sb_restriction_t>                            mesh_restrictions_;
+  std::vector<sb_csr_t>                                    csr_;
+  std::vector<void*>                                       device_buffers_;
+  std::vector<std::shared_ptr<void>>                       qdata_keepalive_;
+  Vector                                                   output_L_;
+  std::vector<Gradient>                                    grad_;
+  bool                                                     update_qdata_ = false;
+};
+
+}  // namespace serac

@@ -1,0 +1,268 @@
+// Test driver for the C++ host side (serac_b200/functional.hpp): builds serac::Functional objects the way the
+// reference's physics modules and unit tests do (src/serac/physics/solid_mechanics.hpp:879-894, :1075-1101;
+// src/serac/numerics/functional/tests/functional_basic_h1_scalar.cpp, check_gradient.hpp) on problems exported by
+// pytest from the golden fixtures, and writes its results back for pytest to compare with the reference's outputs.
+//
+//   functional_test <case> <directory>
+//     solid     H1<2,3>(H1<1,3>, H1<2,3>, H1<2,3>), shape-aware NeoHookean stress integrand (hex or tet mesh)
+//     j2        same signature, J2SmallStrain<LinearHardening> with QuadratureData state, updateQdata(true)
+//     pressure  same signature, ONE boundary integral: follower pressure (hex mesh, quadrilateral faces)
+//     user      H1<2>(H1<2>) with a q-function defined in THIS file: checked here against finite differences and the
+//               assembled matrix (check_gradient.hpp:16-90)
+// Directory layout: <name>.bin raw little-endian arrays (int32 / float64), meta.txt "key value" lines.
+#include <cmath>
+#include <cstdio>
+#include <fstream>
+#include <map>
+#include <string>
+
+#include "serac_b200/functional.hpp"
+
+using namespace serac;
+
+static std::string g_dir;
+
+template <typename T>
+std::vector<T> read_bin(const std::string& name)
+{
+  std::ifstream f(g_dir + "/" + name + ".bin", std::ios::binary | std::ios::ate);
+  if (!f) {
+    std::fprintf(stderr, "missing input %s\n", name.c_str());
+    std::exit(2);
+  }
+  const std::streamsize n = f.tellg();
+  f.seekg(0);
+  std::vector<T> v(size_t(n) / sizeof(T));
+  f.read(reinterpret_cast<char*>(v.data()), n);
+  return v;
+}
+
+template <typename T>
+void write_bin(const std::string& name, const std::vector<T>& v)
+{
+  std::ofstream f(g_dir + "/out_" + name + ".bin", std::ios::binary);
+  f.write(reinterpret_cast<const char*>(v.data()), std::streamsize(v.size() * sizeof(T)));
+}
+
+std::map<std::string, double> read_meta()
+{
+  std::map<std::string, double> m;
+  std::ifstream                 f(g_dir + "/meta.txt");
+  std::string                   k;
+  double                        v;
+  while (f >> k >> v) m[k] = v;
+  return m;
+}
+
+struct Problem {
+  Mesh               mesh;
+  FiniteElementSpace space, shape_space, scalar_space;
+};
+
+/// spaces of one exported fixture: H1<p,dim> (u, a), H1<1,dim> (shape, and the mesh nodes), H1<p> (scalar)
+Problem load_problem(const std::map<std::string, double>& meta, bool with_faces)
+{
+  Problem        P;
+  const Geometry g   = Geometry(int(meta.at("geom")));
+  const int      p   = int(meta.at("p"));
+  const int      dim = int(meta.at("dim"));
+  const int64_t  ne  = int64_t(meta.at("ne"));
+  P.space            = FiniteElementSpace{g, p, dim, Ordering::byVDIM, int64_t(meta.at("num_nodes")), ne,
+                               read_bin<int>("native_dofs")};
+  P.scalar_space      = P.space;
+  P.scalar_space.vdim = 1;
+  P.shape_space = FiniteElementSpace{g, 1, dim, Ordering::byVDIM, int64_t(meta.at("shape_num_nodes")), ne,
+                                     read_bin<int>("shape_native_dofs")};
+  P.mesh.nodes_space = FiniteElementSpace{g, int(meta.at("mesh_order")), dim, Ordering(int(meta.at("mesh_ordering"))),
+                                          int64_t(meta.at("mesh_num_nodes")), ne, read_bin<int>("mesh_native_dofs")};
+  P.mesh.nodes       = read_bin<double>("mesh_nodes");
+  if (with_faces) {
+    const int64_t nf = int64_t(meta.at("nf"));
+    P.space.num_boundary_faces = P.shape_space.num_boundary_faces = P.mesh.nodes_space.num_boundary_faces = nf;
+    P.space.native_boundary_face_dofs            = read_bin<int>("face_native_dofs");
+    P.shape_space.native_boundary_face_dofs      = read_bin<int>("shape_face_native_dofs");
+    P.mesh.nodes_space.native_boundary_face_dofs = read_bin<int>("mesh_face_native_dofs");
+  }
+  return P;
+}
+
+constexpr int p   = 2;
+constexpr int dim = 3;
+using solid_test  = H1<p, dim>;
+using SolidFunctional = Functional<solid_test(H1<1, dim>, H1<p, dim>, H1<p, dim>)>;
+
+template <typename Material>
+using SolidIntegrand = ShapeAwareIntegrandWrapperWithState<MaterialStressFunctor<Material>, dim, solid_test, H1<p, dim>, H1<p, dim>>;
+
+int run_solid(const std::map<std::string, double>& meta)
+{
+  Problem P = load_problem(meta, false);
+  auto    params = read_bin<double>("params");
+  SolidFunctional residual(&P.space, {&P.shape_space, &P.space, &P.space});
+  using Material = solid_mechanics::NeoHookean;
+  Material m{params[0], params[1], params[2]};
+  auto     gn = params[3] != 0.0 ? GeometricNonlinearities::On : GeometricNonlinearities::Off;
+  Domain   whole = EntireDomain(P.mesh);
+  // SolidMechanics::setMaterial (solid_mechanics.hpp:879-894)
+  residual.AddDomainIntegral(Dimension<dim>{}, DependsOn<0, 1, 2>{}, SolidIntegrand<Material>(MaterialStressFunctor<Material>(m, gn)),
+                             whole, EmptyQData);
+  Vector S(read_bin<double>("S")), U(read_bin<double>("U")), A(read_bin<double>("A")), dU(read_bin<double>("dU"));
+  // plain residual, then residual + Jacobian (functional.hpp:446-513)
+  Vector& r0 = residual(0.0, S, U, A);
+  write_bin("r_plain", r0.to_host());
+  auto [r, drdu] = residual(0.0, S, differentiate_wrt(U), A);
+  write_bin("r", r.to_host());
+  write_bin("dr", drdu(dU).to_host());
+  auto K = assemble(drdu);
+  write_bin("row_ptr", K->row_ptr);
+  write_bin("col_ind", K->col_ind);
+  write_bin("values", K->values);
+  // mass matrix action: derivative w.r.t. the acceleration
+  auto [r2, drda] = residual(0.0, S, U, differentiate_wrt(A));
+  write_bin("dr_da", drda(dU).to_host());
+  return 0;
+}
+
+int run_j2(const std::map<std::string, double>& meta)
+{
+  Problem P = load_problem(meta, false);
+  auto    q = read_bin<double>("params");  // E nu sigma_y Hi Hk density geom_nonlin
+  using Material = solid_mechanics::J2SmallStrain<solid_mechanics::LinearHardening>;
+  Material m{q[0], q[1], solid_mechanics::LinearHardening{q[2], q[3]}, q[4], q[5]};
+  auto     gn = q[6] != 0.0 ? GeometricNonlinearities::On : GeometricNonlinearities::Off;
+  SolidFunctional residual(&P.space, {&P.shape_space, &P.space, &P.space});
+  const int nq    = num_quadrature_points(P.space.geometry, p + 1);
+  auto      qdata = std::make_shared<QuadratureData<Material::State>>(P.mesh.GetNE(), nq, Material::State{});
+  Domain    whole = EntireDomain(P.mesh);
+  residual.AddDomainIntegral(Dimension<dim>{}, DependsOn<0, 1, 2>{}, SolidIntegrand<Material>(MaterialStressFunctor<Material>(m, gn)),
+                             whole, qdata);
+  Vector S(read_bin<double>("S")), U(read_bin<double>("U")), A(read_bin<double>("A")), dU(read_bin<double>("dU"));
+  auto [r, drdu] = residual(0.0, S, differentiate_wrt(U), A);
+  write_bin("r", r.to_host());
+  write_bin("dr", drdu(dU).to_host());
+  // the post-convergence pass of SolidMechanics (solid_mechanics.hpp:1282-1287): commit the state
+  residual.updateQdata(true);
+  residual(0.0, S, U, A);
+  residual.updateQdata(false);
+  auto                states = qdata->to_host();
+  std::vector<double> flat(states.size() * sizeof(Material::State) / sizeof(double));
+  std::memcpy(flat.data(), states.data(), flat.size() * sizeof(double));
+  write_bin("qdata1", flat);
+  write_bin("r_after_commit", residual(0.0, S, U, A).to_host());
+  return 0;
+}
+
+int run_pressure(const std::map<std::string, double>& meta)
+{
+  Problem P = load_problem(meta, true);
+  auto    q = read_bin<double>("params");  // pressure geom_nonlin
+  SolidFunctional residual(&P.space, {&P.shape_space, &P.space, &P.space});
+  auto gn = q[1] != 0.0 ? GeometricNonlinearities::On : GeometricNonlinearities::Off;
+  // SolidMechanics::setPressure (solid_mechanics.hpp:1075-1101) inside ShapeAwareFunctional::AddBoundaryIntegral
+  using Integrand = ShapeAwareBoundaryIntegrandWrapper<PressureIntegrand<UniformPressure>>;
+  residual.AddBoundaryIntegral(Dimension<dim - 1>{}, DependsOn<0, 1, 2>{},
+                               Integrand(PressureIntegrand<UniformPressure>(UniformPressure{q[0]}, gn)), P.mesh);
+  Vector S(read_bin<double>("S")), U(read_bin<double>("U")), A(read_bin<double>("A")), dU(read_bin<double>("dU")),
+      dS(read_bin<double>("dS"));
+  auto [r, drdu] = residual(0.0, S, differentiate_wrt(U), A);
+  write_bin("r", r.to_host());
+  write_bin("dr", drdu(dU).to_host());
+  auto [r2, drds] = residual(0.0, differentiate_wrt(S), U, A);
+  write_bin("dr_dshape", drds(dS).to_host());
+  return 0;
+}
+
+/// a q-function that exists nowhere in the library: nonlinear reaction-diffusion with a position-dependent source
+struct UserQFunction {
+  double a, b;
+  template <typename X, typename T>
+  SERAC_HOST_DEVICE auto operator()(double t, X x, T temperature) const
+  {
+    auto u      = get<0>(temperature);
+    auto du_dx  = get<1>(temperature);
+    auto X0     = get<0>(x);
+    auto source = a * u * u * u + (X0[0] + 2.0 * X0[1] - X0[2]) * (1.0 + t);
+    auto flux   = (b + u * u) * du_dx;
+    return serac::tuple{source, flux};
+  }
+};
+
+int run_user(const std::map<std::string, double>& meta)
+{
+  Problem P = load_problem(meta, false);
+  Functional<H1<p>(H1<p>)> residual(&P.scalar_space, {&P.scalar_space});
+  Domain whole = EntireDomain(P.mesh);
+  residual.AddDomainIntegral(Dimension<dim>{}, DependsOn<0>{}, UserQFunction{0.7, 1.3}, whole);
+  const int64_t       n = P.scalar_space.GetVSize();
+  std::vector<double> u(static_cast<size_t>(n)), du(static_cast<size_t>(n));
+  for (int64_t i = 0; i < n; i++) {
+    u[size_t(i)]  = 0.5 * std::sin(0.37 * double(i) + 0.1);
+    du[size_t(i)] = std::cos(0.11 * double(i)) * (0.3 + double(i % 7) / 7.0);
+  }
+  Vector U(u), dU(du);
+  auto [r, drdu]          = residual(0.5, differentiate_wrt(U));
+  std::vector<double> r0  = r.to_host();
+  std::vector<double> jvp = drdu(dU).to_host();
+  auto                K   = assemble(drdu);
+  // (1) J du from the assembled matrix
+  double err_mat = 0.0, norm = 0.0;
+  for (int64_t i = 0; i < n; i++) {
+    double s = 0.0;
+    for (int k = K->row_ptr[size_t(i)]; k < K->row_ptr[size_t(i) + 1]; k++) s += K->values[size_t(k)] * du[size_t(K->col_ind[size_t(k)])];
+    err_mat += (s - jvp[size_t(i)]) * (s - jvp[size_t(i)]);
+    norm += jvp[size_t(i)] * jvp[size_t(i)];
+  }
+  err_mat = std::sqrt(err_mat / norm);
+  // (2) central finite difference of the residual
+  const double        eps = 1e-5;
+  std::vector<double> up(u), um(u);
+  for (int64_t i = 0; i < n; i++) {
+    up[size_t(i)] += eps * du[size_t(i)];
+    um[size_t(i)] -= eps * du[size_t(i)];
+  }
+  std::vector<double> rp = residual(0.5, Vector(up)).to_host();
+  std::vector<double> rm = residual(0.5, Vector(um)).to_host();
+  double              err_fd = 0.0;
+  for (int64_t i = 0; i < n; i++) {
+    const double fd = (rp[size_t(i)] - rm[size_t(i)]) / (2.0 * eps);
+    err_fd += (fd - jvp[size_t(i)]) * (fd - jvp[size_t(i)]);
+  }
+  err_fd = std::sqrt(err_fd / norm);
+  // (3) the plain evaluation returns the same residual as the differentiated one
+  std::vector<double> rplain = residual(0.5, U).to_host();
+  double              err_r  = 0.0, rn = 0.0;
+  for (int64_t i = 0; i < n; i++) {
+    err_r += (rplain[size_t(i)] - r0[size_t(i)]) * (rplain[size_t(i)] - r0[size_t(i)]);
+    rn += r0[size_t(i)] * r0[size_t(i)];
+  }
+  err_r = std::sqrt(err_r / rn);
+  std::printf("user q-function: |J du|=%.6e  matrix-vs-action %.2e  finite-difference %.2e  plain-vs-AD residual %.2e\n",
+              std::sqrt(norm), err_mat, err_fd, err_r);
+  write_bin("r", r0);
+  write_bin("dr", jvp);
+  const bool ok = err_mat < 1e-12 && err_fd < 5e-8 && err_r < 1e-14 && norm > 0.0;
+  std::printf(ok ? "PASS\n" : "FAIL\n");
+  return ok ? 0 : 1;
+}
+
+int main(int argc, char** argv)
+{
+  if (argc != 3) {
+    std::fprintf(stderr, "usage: functional_test <solid|j2|pressure|user> <directory>\n");
+    return 2;
+  }
+  const std::string which = argv[1];
+  g_dir                   = argv[2];
+  auto meta               = read_meta();
+  if (int(meta.at("p")) != p || int(meta.at("dim")) != dim) {
+    std::fprintf(stderr, "this driver is compiled for p = %d, dim = %d\n", p, dim);
+    return 2;
+  }
+  int rc = 2;
+  if (which == "solid") rc = run_solid(meta);
+  if (which == "j2") rc = run_j2(meta);
+  if (which == "pressure") rc = run_pressure(meta);
+  if (which == "user") rc = run_user(meta);
+  std::printf("launches: %lld\n", sb_launch_count());
+  return rc;
+}
