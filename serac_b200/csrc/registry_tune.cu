@@ -31,10 +31,9 @@ long make_blob(const double* p, int n, void* out, size_t cap)
 #define TUNE_SET 0
 #endif
 #if TUNE_SET == 0
-TUNE(4, 1, 1)
-TUNE(4, 1, 2)
-TUNE(4, 1, 3)
 TUNE(4, 1, 4)
+TUNE(4, 1, 5)
+TUNE(4, 1, 6)
 #elif TUNE_SET == 1
 TUNE(8, 1, 1)
 TUNE(8, 1, 2)

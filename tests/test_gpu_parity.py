@@ -165,3 +165,17 @@ def test_config_a_full_size(cuda):
     rp = P.F(0.0, [P.S, P.U + eps * P.dU, P.A]).cpu().numpy()
     rm = P.F(0.0, [P.S, P.U - eps * P.dU, P.A]).cpu().numpy()
     assert rel_l2((rp - rm) / (2 * eps), dr) < 1e-7
+
+
+def test_config_b_properties_p3_cube(cuda):
+    """BASELINE.json configs[4] (structured hex cube, H1 p=3, NeoHookean) at a size the GPU suite can afford (32^3 hexes,
+    2.7 M vdofs): the size-independent properties tools/config_b.py checks at full size."""
+    import sys
+    sys.path.insert(0, str(__import__("pathlib").Path(__file__).resolve().parents[1] / "tools"))
+    import config_b
+    P = config_b.build(32, cuda)
+    props = config_b.check_properties(P, cuda)
+    assert props["sum_of_internal_forces_rel"] < 1e-9, props  # a sum over every node: roundoff grows with the mesh
+    assert props["linearity_rel"] < 1e-12, props
+    assert props["symmetry_rel"] < 1e-10, props
+    assert props["finite_difference_rel"] < 1e-6, props
