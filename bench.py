@@ -244,13 +244,14 @@ def run_product(args):
     ev = [[torch.cuda.Event(enable_timing=True) for _ in range(5)] for _ in range(psteps)]
     for k in range(psteps):
         ev[k][0].record()
-        integral.Mult(0.0, fields, r_E, wrt=1)
+        # the same kernels, in the same E-vector layout ([element][node][comp]), as sb_functional_* launches in the step
+        integral.Mult(0.0, fields, r_E, wrt=1, node_major=True)
         ev[k][1].record()
-        G.Scatter(r_E, rL)
+        G.Scatter(r_E, rL, node_major=True)
         ev[k][2].record()
-        integral.GradientMult(1, du_field, r_E)
+        integral.GradientMult(1, du_field, r_E, node_major=True)
         ev[k][3].record()
-        G.Scatter(r_E, rL)
+        G.Scatter(r_E, rL, node_major=True)
         ev[k][4].record()
     torch.cuda.synchronize()
     phase_ms = [float(np.mean([ev[k][i].elapsed_time(ev[k][i + 1]) for k in range(psteps)])) for i in range(4)]

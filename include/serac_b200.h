@@ -126,6 +126,9 @@ typedef struct {
   void*         qdata_dev;
   int           update_state;
   double        t;
+  int           r_E_node_major; /* 0: r_E is [element][comp][node] (the reference's E-vector, F/element_restriction.cpp:443);
+                                   1: [element][node][comp] -- internal to sb_functional_*: the components of a node are
+                                   contiguous, so the deterministic scatter reads whole 32-byte sectors */
 } sb_eval_args;
 
 typedef struct {
@@ -134,6 +137,7 @@ typedef struct {
   int           num_elements;
   const double* dqf_dev;
   double*       r_E_dev;
+  int           r_E_node_major; /* see sb_eval_args */
 } sb_jvp_args;
 
 typedef struct {
@@ -188,6 +192,15 @@ int sb_integral_evaluate(sb_integral_t I, double t, const sb_field_arg* trials, 
                          int update_state, void* stream);
 /* Integral::GradientMult (F/integral.hpp:93-103) */
 int sb_integral_jvp(sb_integral_t I, int wrt, const sb_field_arg* du, double* dr_E_dev, void* stream);
+/* The same three operations with the E-vector block laid out [element][node][comp] (node_major != 0) instead of the
+ * reference's [element][comp][node]: the layout sb_functional_* uses internally, exposed so that the kernels it runs can
+ * be timed and tested one by one.  node_major == 0 is identical to the plain calls. */
+int sb_integral_evaluate_layout(sb_integral_t I, double t, const sb_field_arg* trials, double* r_E_dev, int wrt,
+                                int update_state, int node_major, void* stream);
+int sb_integral_jvp_layout(sb_integral_t I, int wrt, const sb_field_arg* du, double* dr_E_dev, int node_major,
+                           void* stream);
+int sb_restriction_scatter_layout(sb_restriction_t r, const double* E_dev, double* L_dev, int accumulate,
+                                  int node_major, void* stream);
 /* Integral::ComputeElementGradients (F/integral.hpp:112-121): K_e_dev [elements of geometry][trial vdofs][test vdofs]
  * is accumulated into (+=), as the reference does. */
 int sb_integral_element_gradient(sb_integral_t I, int wrt, double* K_e_dev, void* stream);

@@ -61,6 +61,9 @@ SIGNATURES = {
     "sb_integral_set_qdata": (_i, [_vp, _vp]),
     "sb_integral_evaluate": (_i, [_vp, _d, C.POINTER(FieldArg), _vp, _i, _i, _vp]),
     "sb_integral_jvp": (_i, [_vp, _i, C.POINTER(FieldArg), _vp, _vp]),
+    "sb_integral_evaluate_layout": (_i, [_vp, _d, C.POINTER(FieldArg), _vp, _i, _i, _i, _vp]),
+    "sb_integral_jvp_layout": (_i, [_vp, _i, C.POINTER(FieldArg), _vp, _i, _vp]),
+    "sb_restriction_scatter_layout": (_i, [_vp, _vp, _vp, _i, _i, _vp]),
     "sb_integral_element_gradient": (_i, [_vp, _i, _vp, _vp]),
     "sb_integral_export_derivatives": (_i, [_vp, _i, _vp, _vp]),
     "sb_integral_derivative_entries": (_i, [_vp, _i]),
@@ -203,12 +206,19 @@ class ElementRestriction:
         check(lib().sb_restriction_gather(self.h, _dev_ptr(L), _dev_ptr(E), _stream_ptr()))
         return E
 
-    def ScatterAdd(self, E, L):
-        check(lib().sb_restriction_scatter_add(self.h, _dev_ptr(E), _dev_ptr(L), _stream_ptr()))
+    def ScatterAdd(self, E, L, node_major=False):
+        """node_major: E is [element][node][comp] (the Functional's internal layout) instead of [element][comp][node]"""
+        if node_major:
+            check(lib().sb_restriction_scatter_layout(self.h, _dev_ptr(E), _dev_ptr(L), 1, 1, _stream_ptr()))
+        else:
+            check(lib().sb_restriction_scatter_add(self.h, _dev_ptr(E), _dev_ptr(L), _stream_ptr()))
         return L
 
-    def Scatter(self, E, L):
-        check(lib().sb_restriction_scatter(self.h, _dev_ptr(E), _dev_ptr(L), _stream_ptr()))
+    def Scatter(self, E, L, node_major=False):
+        if node_major:
+            check(lib().sb_restriction_scatter_layout(self.h, _dev_ptr(E), _dev_ptr(L), 0, 1, _stream_ptr()))
+        else:
+            check(lib().sb_restriction_scatter(self.h, _dev_ptr(E), _dev_ptr(L), _stream_ptr()))
         return L
 
     def field(self, L):
@@ -265,13 +275,15 @@ class Integral:
         self.qdata = qdata
         check(lib().sb_integral_set_qdata(self.h, _dev_ptr(qdata)))
 
-    def Mult(self, t, fields, r_E, wrt=NO_DIFFERENTIATION, update_state=False):
+    def Mult(self, t, fields, r_E, wrt=NO_DIFFERENTIATION, update_state=False, node_major=False):
         arr = (FieldArg * len(fields))(*fields)
-        check(lib().sb_integral_evaluate(self.h, float(t), arr, _dev_ptr(r_E), wrt, int(update_state), _stream_ptr()))
+        check(lib().sb_integral_evaluate_layout(self.h, float(t), arr, _dev_ptr(r_E), wrt, int(update_state),
+                                                int(node_major), _stream_ptr()))
         return r_E
 
-    def GradientMult(self, wrt, du_field, dr_E):
-        check(lib().sb_integral_jvp(self.h, wrt, C.byref(du_field), _dev_ptr(dr_E), _stream_ptr()))
+    def GradientMult(self, wrt, du_field, dr_E, node_major=False):
+        check(lib().sb_integral_jvp_layout(self.h, wrt, C.byref(du_field), _dev_ptr(dr_E), int(node_major),
+                                           _stream_ptr()))
         return dr_E
 
     def ComputeElementGradients(self, wrt, K_e):

@@ -70,7 +70,26 @@ struct EvalParams {
   void*         qdata;         ///< [e][q] AoS of the state type (quadrature_data.hpp:127-131)
   int           update_state;
   double        t;
+  int           prefetch_distance;  ///< CTAs resident on the device: tile blockIdx + distance is prefetched into L2 (0: off)
+  int           node_major;         ///< r_E layout: 0 = [element][comp][node] (reference), 1 = [element][node][comp]
 };
+
+/// position of (element, component a, node) in an E-vector block of ct components and ndof nodes per element
+__device__ __forceinline__ long long e_index(int node_major, long long elem, int a, int node, int ct, int ndof)
+{
+  return node_major ? (elem * ndof + node) * ct + a : (elem * ct + a) * ndof + node;
+}
+
+/// one 128-byte line into L2 (no register, no scoreboard: the CTA that runs `prefetch_distance` tiles later finds its
+/// streaming inputs -- restriction-table rows, X_q, J_q -- in L2 instead of paying the HBM latency twice in a row)
+__device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+
+template <int THREADS>
+__device__ __forceinline__ void prefetch_range_l2(const void* base, long long bytes)
+{
+  const char* b = static_cast<const char*>(base);
+  for (long long off = (long long)threadIdx.x * 128; off < bytes; off += (long long)THREADS * 128) prefetch_l2(b + off);
+}
 
 struct JvpParams {
   FieldArg      trial;
@@ -82,6 +101,7 @@ struct JvpParams {
   int           num_elements;
   const double* dqf;
   double*       r_E;
+  int           node_major;  ///< r_E layout (see EvalParams)
 };
 
 struct ElemGradParams {
@@ -1045,8 +1065,22 @@ __global__ void __launch_bounds__(Sig::threads, MINB) evaluation_kernel(const __
   const int  e     = valid ? e_raw : P.num_elements - 1;
   const int  elem  = P.elements ? P.elements[e] : e;
 
-  // geometric factors of this quadrature point:  Jm(i,j) = dX_i/dxi_j = J_q[e](j,i,q)   (loads issued first)
   constexpr int sdim = Sig::sdim;
+  // L2 prefetch of a later tile's streaming inputs (identity element list: the tile's rows are contiguous)
+  if (P.prefetch_distance > 0 && !P.elements) {
+    const long long pe = ((long long)blockIdx.x + P.prefetch_distance) * EPB;
+    if (pe + EPB <= P.num_elements) {
+      prefetch_range_l2<Sig::threads>(P.J_q + pe * (dim * sdim * QPE), (long long)EPB * dim * sdim * QPE * 8);
+      prefetch_range_l2<Sig::threads>(P.X_q + pe * (sdim * QPE), (long long)EPB * sdim * QPE * 8);
+      [&]<int... I>(std::integer_sequence<int, I...>)
+      {
+        (prefetch_range_l2<Sig::threads>(P.trial[I].table + pe * LAY::ndof(I), (long long)EPB * LAY::ndof(I) * 4), ...);
+      }
+      (seq{});
+    }
+  }
+
+  // geometric factors of this quadrature point:  Jm(i,j) = dX_i/dxi_j = J_q[e](j,i,q)   (loads issued first)
   tensor<double, sdim>      x{};
   tensor<double, sdim, dim> Jm{};
   SB_UNROLL
@@ -1437,7 +1471,7 @@ __global__ void __launch_bounds__(Sig::threads, MINB) evaluation_kernel(const __
       constexpr int n    = Sig::test_n;
       const int     node = Sig::simplex ? ql : (dim == 3) ? (qz * n + qy) * n + qx : qy * n + qx;
       SB_UNROLL
-      for (int a = 0; a < ct; a++) P.r_E[((long long)elem * ct + a) * Sig::test_ndof + node] = out[a];
+      for (int a = 0; a < ct; a++) P.r_E[e_index(P.node_major, elem, a, node, ct, Sig::test_ndof)] = out[a];
     }
   }
 }
@@ -1560,7 +1594,7 @@ __global__ void __launch_bounds__(JvpConfig<dim, q, nk, ck, nt, ct, MASK, EPB_>:
   if (owner && valid) {
     const int node = (dim == 3) ? (qz * nt + qy) * nt + qx : qy * nt + qx;
     SB_UNROLL
-    for (int a = 0; a < ct; a++) P.r_E[((long long)elem * ct + a) * C::TPt::ndof + node] = out[a];
+    for (int a = 0; a < ct; a++) P.r_E[e_index(P.node_major, elem, a, node, ct, C::TPt::ndof)] = out[a];
   }
 }
 

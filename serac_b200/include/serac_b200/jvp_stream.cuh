@@ -481,7 +481,7 @@ __global__ void __launch_bounds__(JvpStreamConfig<dim, q, nk, ck, nt, ct, MASK, 
       const int elem = P.elements ? P.elements[e_raw] : e_raw;
       const int node = (dim == 3) ? (qz * nt + qy) * nt + qx : qy * nt + qx;
       SB_UNROLL
-      for (int a = 0; a < ct; a++) P.r_E[((long long)elem * ct + a) * ipow(nt, dim) + node] = out[a];
+      for (int a = 0; a < ct; a++) P.r_E[e_index(P.node_major, elem, a, node, ct, ipow(nt, dim))] = out[a];
     }
   }
 }

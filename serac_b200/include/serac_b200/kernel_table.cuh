@@ -47,13 +47,43 @@ struct qf_variants<QF, std::void_t<decltype(QF::num_variants)>> {
   static constexpr int n = QF::num_variants;
 };
 
+/// number of SMs of the current device (cached)
+inline int sm_count()
+{
+  static int n = 0;
+  if (n == 0) {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess)
+      n = 148;
+  }
+  return n;
+}
+
+/// SB_EVAL_PREFETCH=0 switches the L2 prefetch of later tiles off (for A/B measurements)
+inline bool use_eval_prefetch()
+{
+  static const bool v = [] {
+    const char* e = std::getenv("SB_EVAL_PREFETCH");
+    return !(e && std::strcmp(e, "0") == 0);
+  }();
+  return v;
+}
+
 template <typename Sig, int WRT, typename QF, typename State, int ROWS, int MINB, bool FAST>
-int launch_evaluation_kernel(const EvalParams<Sig::NT>& P, const QF& qf, int num_elements, void* stream)
+int launch_evaluation_kernel(const EvalParams<Sig::NT>& P_in, const QF& qf, int num_elements, void* stream)
 {
   auto         kernel = &evaluation_kernel<Sig, WRT, QF, State, ROWS, MINB, FAST>;
   const size_t smem   = size_t(eval_smem_doubles<Sig>()) * sizeof(double);
   if (int e = ensure_smem(kernel, smem)) return e;
   const int grid = (num_elements + Sig::EPB - 1) / Sig::EPB;
+  static int resident = 0;  // CTAs per SM of this instantiation
+  if (resident == 0) {
+    int nb = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kernel, Sig::threads, smem) != cudaSuccess) nb = 1;
+    resident = nb > 0 ? nb : 1;
+  }
+  EvalParams<Sig::NT> P = P_in;
+  P.prefetch_distance   = use_eval_prefetch() ? resident * sm_count() : 0;
   kernel<<<grid, Sig::threads, smem, cudaStream_t(stream)>>>(P, qf);
   sb_count_launch();
   return int(cudaGetLastError());
@@ -86,6 +116,7 @@ int launch_evaluate(const sb_eval_args* a, const void* qf_blob, void* stream)
   P.elements     = a->elements_dev;
   P.num_elements = a->num_elements;
   P.r_E          = a->r_E_dev;
+  P.node_major   = a->r_E_node_major;
   P.dqf          = a->dqf_dev;
   P.qdata        = a->qdata_dev;
   P.update_state = a->update_state;
@@ -109,18 +140,6 @@ int launch_evaluate(const sb_eval_args* a, const void* qf_blob, void* stream)
   } else {
     return launch_evaluation_kernel<Sig, WRT, QF, State, ROWS, MINB, FAST>(P, qf, a->num_elements, stream);
   }
-}
-
-/// number of SMs of the current device (cached)
-inline int sm_count()
-{
-  static int n = 0;
-  if (n == 0) {
-    int dev = 0;
-    if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess)
-      n = 148;
-  }
-  return n;
 }
 
 /// SB_JVP_KERNEL=legacy selects the one-tile-per-CTA kernel (for A/B measurements); default is the TMA-fed stream kernel
@@ -151,6 +170,7 @@ int launch_jvp(const sb_jvp_args* a, void* stream)
     P.num_elements = a->num_elements;
     P.dqf          = a->dqf_dev;
     P.r_E          = a->r_E_dev;
+    P.node_major   = a->r_E_node_major;
     if (a->num_elements <= 0) return 0;
     if constexpr (Sig::simplex) {
       using SX            = SimplexConfig<Sig::geometry, Sig::q, trial::order, ck, Sig::test_space::order, Sig::test_c, MASK, Sig::EPB>;

@@ -129,7 +129,7 @@ __global__ void __launch_bounds__(SimplexConfig<geom, Q, pk, ck, pt, ct, MASK, E
       tables + C::tab_k, scratch + el * per, ql, src, flux, out);
   if (owner && valid) {
     SB_UNROLL
-    for (int a = 0; a < ct; a++) P.r_E[((long long)elem * ct + a) * C::ndt + ql] = out[a];
+    for (int a = 0; a < ct; a++) P.r_E[e_index(P.node_major, elem, a, ql, ct, C::ndt)] = out[a];
   }
 }
 

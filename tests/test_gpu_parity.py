@@ -179,3 +179,24 @@ def test_config_b_properties_p3_cube(cuda):
     assert props["linearity_rel"] < 1e-12, props
     assert props["symmetry_rel"] < 1e-10, props
     assert props["finite_difference_rel"] < 1e-6, props
+
+
+def test_node_major_e_vector_layout_is_bit_identical(case):
+    """sb_functional_* keeps its E-vector [element][node][comp]; the sums and their order are the reference's, so the
+    scattered L-vector is bit-identical to the [element][comp][node] route"""
+    prob, P = case
+    nE, ct, nd = int(prob["ne"]), P.vdim, P.dof_info.shape[1]
+    r_ref = P.torch.zeros(P.G.ESize(), dtype=P.torch.float64, device=P.dev)
+    r_nm = P.torch.zeros_like(r_ref)
+    P.integral.Mult(0.0, P.fields(), r_ref, wrt=1)
+    P.integral.Mult(0.0, P.fields(), r_nm, wrt=1, node_major=True)
+    assert P.torch.equal(r_nm.view(nE, nd, ct).permute(0, 2, 1).contiguous().view(-1), r_ref)
+    L_ref = P.G.Scatter(r_ref, P.torch.empty(P.G.LSize(), dtype=P.torch.float64, device=P.dev))
+    L_nm = P.G.Scatter(r_nm, P.torch.empty(P.G.LSize(), dtype=P.torch.float64, device=P.dev), node_major=True)
+    assert P.torch.equal(L_ref, L_nm)
+    d_ref = P.integral.GradientMult(1, P.G.field(P.dU), P.torch.zeros_like(r_ref))
+    d_nm = P.integral.GradientMult(1, P.G.field(P.dU), P.torch.zeros_like(r_ref), node_major=True)
+    assert P.torch.equal(d_nm.view(nE, nd, ct).permute(0, 2, 1).contiguous().view(-1), d_ref)
+    acc = P.torch.full((P.G.LSize(),), 0.5, dtype=P.torch.float64, device=P.dev)
+    acc2 = acc.clone()
+    assert P.torch.equal(P.G.ScatterAdd(d_ref, acc), P.G.ScatterAdd(d_nm, acc2, node_major=True))

@@ -95,16 +95,18 @@ def time_phases(P, device, reps=5):
                 residual_with_derivative_store_ms=timed(lambda: I.Mult(0.0, fl, r_E, wrt=1)),
                 jvp_ms=timed(lambda: I.GradientMult(1, G.field(dU), r_E)),
                 scatter_ms=timed(lambda: G.Scatter(r_E, L)),
+                scatter_node_major_ms=timed(lambda: G.Scatter(r_E, L, node_major=True)),
                 step_ms=timed(lambda: (F(0.0, [S, U, A], wrt=1), F.GradientMult(1, dU))))
 
 
 def main():
     args = [a for a in sys.argv[1:] if not a.startswith("--")]
     N = int(args[0]) if args else 96
+    p = int(sys.argv[sys.argv.index("--p") + 1]) if "--p" in sys.argv else 3
     out_path = sys.argv[sys.argv.index("--json") + 1] if "--json" in sys.argv else None
     device = torch.device("cuda:0")
     t0 = time.time()
-    P = build(N, device)
+    P = build(N, device, p)
     torch.cuda.synchronize()
     setup_s = time.time() - t0
     nq, vdofs = P["nq"], P["G"].LSize()
@@ -113,9 +115,12 @@ def main():
     peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))) if os.path.exists(
         os.path.join(ROOT, "MEASURED_PEAKS.json")) else {}
     peak = float(peaks.get("hbm_gbs", 6450.0))
-    jvp_gbs = 672.0 * nq / (ph["jvp_ms"] * 1e-3) / 1e9
-    ev_gbs = 776.0 * nq / (ph["residual_with_derivative_store_ms"] * 1e-3) / 1e9
-    res = dict(config=f"structured {N}^3 hexes, H1 p=3 vdim 3, NeoHookean, 1 GPU", hexes=P["ne"], vdofs=vdofs, qpts=nq,
+    # V = 8 * 3 p^3 / (p+1)^3 B/qpt per L-vector pass, 4 B/qpt of indices, 648 B/qpt of derivatives
+    V = 24.0 * p**3 / (p + 1)**3
+    jvp_B, ev_B = 2 * V + 648 + 4, 3 * V + 0.9 + 96 + 648 + 4
+    jvp_gbs = jvp_B * nq / (ph["jvp_ms"] * 1e-3) / 1e9
+    ev_gbs = ev_B * nq / (ph["residual_with_derivative_store_ms"] * 1e-3) / 1e9
+    res = dict(config=f"structured {N}^3 hexes, H1 p={p} vdim 3, NeoHookean, 1 GPU", hexes=P["ne"], vdofs=vdofs, qpts=nq,
                stored_derivative_GB=648.0 * nq / 1e9, setup_s=setup_s, properties=props, phases=ph,
                gdofs_per_s_step=vdofs / (ph["step_ms"] * 1e-3) / 1e9, jvp_GBps=jvp_gbs, jvp_frac_of_peak=jvp_gbs / peak,
                evaluate_GBps=ev_gbs, evaluate_frac_of_peak=ev_gbs / peak, hbm_peak_GBps=peak,
