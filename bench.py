@@ -130,30 +130,50 @@ def build_partitioned_problem(device, rank, world):
     ranks = factor_ranks(world)
     n = tuple(PER_GPU_BOX[d] * ranks[d] for d in range(3))
     mesh = StructuredHexMesh(*n, n[0] / 16.0, n[1] / 16.0, n[2] / 16.0)
-    part, part1 = Partition(mesh, ranks, rank, p, 3), Partition(mesh, ranks, rank, 1, 3)
-    tab, tab1 = part.element_table(p), part.element_table(1)
+    # owned-first local numbering: the T-vector is the prefix of the L-vector, so P / P^T run in place
+    inplace = (os.environ.get("SB_HALO_TRANSPORT", "peer") == "peer" and os.environ.get("SB_HALO_OVERLAP", "1") != "0"
+               and os.environ.get("SB_HALO_INPLACE", "1") != "0")
+    part = Partition(mesh, ranks, rank, p, 3, owned_first=inplace)
+    part1 = Partition(mesh, ranks, rank, 1, 3, owned_first=inplace)
+    tab, tab1 = part.element_table(p), part1.element_table(1)
     G = capi.ElementRestriction(tab, 3, part.num_local_nodes)
     G_shape = capi.ElementRestriction(tab1, 3, part1.num_local_nodes)
-    nodes = torch.as_tensor(part.vertex_coordinates(), dtype=torch.float64, device=device)
+    nodes = torch.as_tensor(part1.vertex_coordinates(), dtype=torch.float64, device=device)
     X_q, J_q = capi.geometric_factors(capi.CUBE, 1, p + 1, G_shape, nodes)
     integral = capi.Integral("solid_neohookean_hex_p2", NEOHOOKEAN, X_q, J_q, tab.shape[0])
     F = capi.Functional(G, [G_shape, G, G])
     F.AddDomainIntegral(integral, [0, 1, 2])
-    halo, halo1 = HaloExchange(part.halo_lists(), device), HaloExchange(part1.halo_lists(), device)
+    # one halo object per field whose exchange can be in flight at the same time (u, a, the JVP direction, r, dr)
+    lists, lists1 = part.halo_lists(), part1.halo_lists()
+    halo1 = HaloExchange(lists1, device)
+    halo, halo_a, halo_du, halo_r = (HaloExchange(lists, device) for _ in range(4))
+    halos = [halo1, halo, halo_a, halo_du, halo_r]
     transport = "nccl"
     if os.environ.get("SB_HALO_TRANSPORT", "peer") == "peer":
-        ok = [halo.enable_peer(), halo1.enable_peer()]
+        ok = [h.enable_peer() for h in halos]
         transport = "peer" if all(ok) else "nccl"
-    PF = ParFunctional(F, [halo1, halo, halo], halo)
+    overlap = transport == "peer" and os.environ.get("SB_HALO_OVERLAP", "1") != "0"
+    if inplace and transport != "peer":
+        raise RuntimeError("owned-first partitions were built for the peer transport, which is unavailable: rerun with "
+                           "SB_HALO_INPLACE=0")
+    if overlap:
+        # puts before waits for the three inputs; P(dU) prefetched and P^T(r) on a side stream
+        PF = ParFunctional(F, [halo1, halo, halo_a], halo, du_halos={1: halo_du}, out_halo=halo_r, inplace=inplace)
+    else:
+        PF = ParFunctional(F, [halo1, halo, halo], halo)
     # globally consistent synthetic inputs: a function of the global vdof id, so shared dofs agree across ranks
     gt, gt1 = part.global_true_vdofs().astype(np.float64), part1.global_true_vdofs().astype(np.float64)
     host = dict(U=1e-3 * np.sin(0.37 * gt + 1.0), A=np.zeros(len(gt)), S=np.zeros(len(gt1)),
                 dU=0.5 + 0.5 * np.sin(0.11 * gt))
-    return dict(capi=capi, G=G, G_shape=G_shape, integral=integral, F=F, PF=PF, halo=halo, halo1=halo1, host=host,
+    return dict(capi=capi, G=G, G_shape=G_shape, integral=integral, F=F, PF=PF, halo=halo, halo1=halo1, halos=halos,
+                overlap=overlap, inplace=inplace, host=host,
                 ne=tab.shape[0], nq=tab.shape[0] * (p + 1)**3, vdofs=G.LSize(), tdofs=halo.tsize, tdofs_shape=halo1.tsize,
                 global_vdofs=mesh.num_nodes(p) * 3, p=p, transport=transport, ranks=ranks, keep=(nodes, X_q, J_q),
                 mesh=f"structured {n[0]}x{n[1]}x{n[2]} hexes, {ranks[0]}x{ranks[1]}x{ranks[2]} boxes of "
                      f"{PER_GPU_BOX[0]}x{PER_GPU_BOX[1]}x{PER_GPU_BOX[2]}")
+
+
+ASYNC_E2E = os.environ.get("SB_BENCH_E2E", "async") != "sync"
 
 
 def run_product(args):
@@ -173,14 +193,36 @@ def run_product(args):
         call = P["F"]
     capi, F, G, integral = P["capi"], P["F"], P["G"], P["integral"]
     t64 = lambda a: torch.as_tensor(a, dtype=torch.float64, device=dev)
-    U, A, S, dU = (t64(P["host"][k]) for k in ("U", "A", "S", "dU"))  # T-vectors (= L-vectors at one rank)
+    overlap = world > 1 and P.get("overlap", False)
+    inplace = world > 1 and P.get("inplace", False)
+
+    def tl(host, lsize):
+        """in-place exchanges: an L-sized device buffer whose first tsize entries are the T-vector"""
+        buf = torch.zeros(lsize, dtype=torch.float64, device=dev)
+        buf[:len(host)] = t64(host)
+        return buf
+
+    if inplace:
+        U, A, dU = (tl(P["host"][k], P["vdofs"]) for k in ("U", "A", "dU"))
+        S = tl(P["host"]["S"], P["G_shape"].LSize())
+    else:
+        U, A, S, dU = (t64(P["host"][k]) for k in ("U", "A", "S", "dU"))  # T-vectors (= L-vectors at one rank)
     r = torch.empty(P["tdofs"], dtype=torch.float64, device=dev)
     dr = torch.empty_like(r)
     r_E = torch.empty(G.ESize(), dtype=torch.float64, device=dev)
+    views = {}
 
     def step_device():
-        call(0.0, [S, U, A], wrt=1, out=r)
-        call.GradientMult(1, dU, out=dr)
+        if overlap:
+            call.prefetch_direction(1, dU)  # side stream: the exchange of the JVP direction runs next to the evaluation
+        if inplace:  # results are the prefixes of the Functional's own L-vectors
+            views["r"] = call(0.0, [S, U, A], wrt=1)
+            views["dr"] = call.GradientMult(1, dU)
+        else:
+            call(0.0, [S, U, A], wrt=1, out=r)
+            call.GradientMult(1, dU, out=dr)
+        if overlap:
+            call.join()
 
     # --- warm-up (also allocates the derivative buffer), then capture the step in a CUDA graph ---
     for _ in range(max(args.warmup, 3)):
@@ -233,7 +275,7 @@ def run_product(args):
         ms_total = float(tt.item())
     ms_per_step = ms_total / args.steps
     if world > 1 and P["transport"] == "peer":
-        assert P["halo"].peer_status() == 0 and P["halo1"].peer_status() == 0, "a peer-memory flag wait timed out"
+        assert all(h.peer_status() == 0 for h in P["halos"]), "a peer-memory flag wait timed out"
 
     # --- per-kernel durations inside a second timed loop (events on the launching stream; rank-local kernels only) ---
     UL, AL, SL, dUL = (U, A, S, dU) if world == 1 else (P["PF"]._L[1], P["PF"]._L[2], P["PF"]._L[0], P["PF"]._duL[1])
@@ -261,10 +303,16 @@ def run_product(args):
         h0, h1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         h0.record()
         for _ in range(psteps):
-            P["halo1"].P(S, SL)
-            P["halo"].P(U, UL)
-            P["halo"].P(A, AL)
-            P["halo"].Pt(rL, r)
+            if inplace:
+                P["halo1"].P_inplace(S)
+                P["halo"].P_inplace(U)
+                P["halo"].P_inplace(A)
+                P["halo"].Pt_inplace(rL)
+            else:
+                P["halo1"].P(S, SL)
+                P["halo"].P(U, UL)
+                P["halo"].P(A, AL)
+                P["halo"].Pt(rL, r)
         h1.record()
         torch.cuda.synchronize()
         halo_ms = h0.elapsed_time(h1) / psteps
@@ -272,6 +320,8 @@ def run_product(args):
         # restore the outputs the sanity check below compares against
         step_device()
         torch.cuda.synchronize()
+    if inplace:
+        r, dr = views["r"].clone(), views["dr"].clone()
 
     # --- end to end through the host-buffer API (pinned host memory in, host memory out) ---
     pin = lambda a: torch.as_tensor(a, dtype=torch.float64).pin_memory()
@@ -284,22 +334,42 @@ def run_product(args):
         nU, nA, nS, ndU, nr, ndr = (x.numpy() for x in (hU, hA, hS, hdU, hr, hdr))
 
         def step_host():
-            F(0.0, [nS, nU, nA], wrt=1, out=nr)
-            F.GradientMult(1, ndU, out=ndr)
+            # SB_HOST_ASYNC: r's device -> host copy overlaps the Jacobian action's host -> device copy and kernels
+            F(0.0, [nS, nU, nA], wrt=1, out=nr, async_host=ASYNC_E2E)
+            F.GradientMult(1, ndU, out=ndr, async_host=ASYNC_E2E)
+            F.wait()
     else:
-        dS, dUd, dA, ddU = (torch.empty_like(x, device=dev) for x in (hS, hU, hA, hdU))
-        d_r, d_dr = torch.empty_like(r), torch.empty_like(dr)
+        if inplace:
+            dS, dUd, dA, ddU = (torch.zeros_like(x) for x in (S, U, A, dU))  # L-sized, T-vector in the prefix
+            ts, ts1 = P["tdofs"], P["tdofs_shape"]
 
-        def step_host():
-            dS.copy_(hS, non_blocking=True)
-            dUd.copy_(hU, non_blocking=True)
-            dA.copy_(hA, non_blocking=True)
-            call(0.0, [dS, dUd, dA], wrt=1, out=d_r)
-            hr.copy_(d_r, non_blocking=True)
-            ddU.copy_(hdU, non_blocking=True)
-            call.GradientMult(1, ddU, out=d_dr)
-            hdr.copy_(d_dr, non_blocking=True)
-            torch.cuda.current_stream().synchronize()
+            def step_host():
+                dS[:ts1].copy_(hS, non_blocking=True)
+                dUd[:ts].copy_(hU, non_blocking=True)
+                dA[:ts].copy_(hA, non_blocking=True)
+                rv = call(0.0, [dS, dUd, dA], wrt=1)
+                ddU[:ts].copy_(hdU, non_blocking=True)
+                drv = call.GradientMult(1, ddU)
+                call.join()
+                hr.copy_(rv, non_blocking=True)
+                hdr.copy_(drv, non_blocking=True)
+                torch.cuda.current_stream().synchronize()
+        else:
+            dS, dUd, dA, ddU = (torch.empty_like(x, device=dev) for x in (hS, hU, hA, hdU))
+            d_r, d_dr = torch.empty_like(r), torch.empty_like(dr)
+
+            def step_host():
+                dS.copy_(hS, non_blocking=True)
+                dUd.copy_(hU, non_blocking=True)
+                dA.copy_(hA, non_blocking=True)
+                call(0.0, [dS, dUd, dA], wrt=1, out=d_r)
+                hr.copy_(d_r, non_blocking=True)
+                ddU.copy_(hdU, non_blocking=True)
+                call.GradientMult(1, ddU, out=d_dr)
+                if overlap:
+                    call.join()
+                hdr.copy_(d_dr, non_blocking=True)
+                torch.cuda.current_stream().synchronize()
 
     for _ in range(3):
         step_host()
@@ -352,7 +422,9 @@ def run_product(args):
                    "l2_policy": "inputs larger than L2 (573 MB stored derivatives streamed each step)",
                    "step_launch": "CUDA graph replay" if use_graph else "kernel by kernel",
                    "parallelism": f"1 mesh partition per GPU x{world}"
-                                  + (f", shared-dof exchange over {P['transport']}" if world > 1 else "")},
+                                  + (f", shared-dof exchange over {P['transport']}"
+                                     + (", in place (owned-first numbering), overlapped on a side stream"
+                                        if P.get("inplace") else "") if world > 1 else "")},
         "e2e": {"value": vdofs_total / e2e_s / 1e9, "unit": "GDOF/s",
                 "h2d_bytes_per_step": int(8 * (3 * vdofs_total + shape_total)),
                 "d2h_bytes_per_step": int(8 * 2 * vdofs_total), "ms_per_step": e2e_s * 1e3},

@@ -247,8 +247,16 @@ int sb_functional_add_integral(sb_functional_t F, sb_integral_t I, const int* tr
  * feeding the integral's i-th trial: dof_info from sb_h1_lexicographic_dof_info(face geometry, p, fes->GetFaceDofs ...). */
 int sb_functional_add_boundary_integral(sb_functional_t F, sb_integral_t I, const int* trial_indices,
                                         sb_restriction_t test_faces, const sb_restriction_t* trial_faces);
-/* operator()(t, args...) (F/functional.hpp:446-513).  inputs: one L-vector per trial space.  *_on_host != 0 means the
- * pointers are host buffers: they are copied to / from the device inside the call (synchronous). */
+/* operator()(t, args...) (F/functional.hpp:446-513).  inputs: one L-vector per trial space.  *_on_host:
+ *   SB_DEVICE (0)      device pointers, work is enqueued on `stream`
+ *   SB_HOST_SYNC (1)   host buffers, copied to / from the device inside the call; the result is valid on return
+ *   SB_HOST_ASYNC (2)  outputs only: the device -> host copy is enqueued on the Functional's own copy stream and the call
+ *                      returns at once, so it overlaps the next call's host -> device copies and kernels; the result (and
+ *                      the right to reuse the input buffers) is valid after sb_functional_wait().  Use pinned memory. */
+#define SB_DEVICE 0
+#define SB_HOST_SYNC 1
+#define SB_HOST_ASYNC 2
+int sb_functional_wait(sb_functional_t F);
 int sb_functional_evaluate(sb_functional_t F, double t, int wrt, const double* const* inputs, int inputs_on_host,
                            double* output, int output_on_host, int update_state, void* stream);
 /* Gradient::Mult (F/functional.hpp:406-432,556-559) for the derivative stored by the last evaluate(wrt) */
@@ -300,6 +308,22 @@ int sb_halo_enable_peer(sb_halo_t H, double* my_ring_dev, int64_t slot_doubles, 
                         const int64_t* peer_P_off, const int64_t* peer_Pt_off, const int* my_index_at_peer);
 int sb_halo_P_peer(sb_halo_t H, const double* T_dev, double* L_dev, void* stream);
 int sb_halo_Pt_peer(sb_halo_t H, const double* L_dev, double* T_dev, void* stream);
+/* the two halves of each peer exchange: issue the puts of several fields (one halo object per field in flight) before
+ * the first finish so that the flag waits overlap, or run an exchange on a side stream next to compute kernels */
+int sb_halo_P_peer_put(sb_halo_t H, const double* T_dev, void* stream);
+int sb_halo_P_peer_finish(sb_halo_t H, const double* T_dev, double* L_dev, void* stream);
+int sb_halo_Pt_peer_put(sb_halo_t H, const double* L_dev, void* stream);
+int sb_halo_Pt_peer_finish(sb_halo_t H, const double* L_dev, double* T_dev, void* stream);
+/* In-place exchanges for partitions numbered owned-first (ltdof[i] == i below tsize, -1 above; sb_halo_owned_first
+ * tells): the T-vector is the first tsize entries of the L-vector, so P only fills the entries owned elsewhere and P^T
+ * only adds into the shared owned entries -- nothing else of the vector is read or written.  Pair them with
+ * sb_halo_P_peer_put(H, TL) / sb_halo_Pt_peer_put(H, TL) on the same buffer. */
+int sb_halo_owned_first(sb_halo_t H);
+int sb_halo_P_peer_finish_inplace(sb_halo_t H, double* TL_dev, void* stream);
+int sb_halo_Pt_peer_finish_inplace(sb_halo_t H, double* TL_dev, void* stream);
+/* P in place for up to 4 fields (one halo object each) with ONE put launch and ONE wait + unpack launch: what
+ * Functional::operator() needs before its gathers (F/functional.hpp:460-470 applies P to every argument) */
+int sb_halo_P_peer_inplace_multi(int num_fields, const sb_halo_t* H, double* const* TL_dev, void* stream);
 int sb_halo_peer_status(sb_halo_t H, int* status_host);
 
 #ifdef __cplusplus

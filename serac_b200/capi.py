@@ -82,6 +82,7 @@ SIGNATURES = {
     "sb_functional_add_integral": (_i, [_vp, _vp, _vp]),
     "sb_functional_evaluate": (_i, [_vp, _d, _i, _pp, _i, _vp, _i, _i, _vp]),
     "sb_functional_jvp": (_i, [_vp, _i, _vp, _i, _vp, _i, _vp]),
+    "sb_functional_wait": (_i, [_vp]),
     "sb_functional_assemble": (_i, [_vp, _i, _pp, _vp, _i, _vp]),
     "sb_halo_create": (_i, [_i64, _i64, _vp, _i, _vp, _vp, _vp, _vp, _pp]),
     "sb_halo_destroy": (_i, [_vp]),
@@ -91,6 +92,14 @@ SIGNATURES = {
     "sb_halo_enable_peer": (_i, [_vp, _vp, _i64, _vp, _vp, _vp, _vp]),
     "sb_halo_P_peer": (_i, [_vp, _vp, _vp, _vp]),
     "sb_halo_Pt_peer": (_i, [_vp, _vp, _vp, _vp]),
+    "sb_halo_P_peer_put": (_i, [_vp, _vp, _vp]),
+    "sb_halo_P_peer_finish": (_i, [_vp, _vp, _vp, _vp]),
+    "sb_halo_Pt_peer_put": (_i, [_vp, _vp, _vp]),
+    "sb_halo_Pt_peer_finish": (_i, [_vp, _vp, _vp, _vp]),
+    "sb_halo_owned_first": (_i, [_vp]),
+    "sb_halo_P_peer_finish_inplace": (_i, [_vp, _vp, _vp]),
+    "sb_halo_P_peer_inplace_multi": (_i, [_i, _vp, _vp, _vp]),
+    "sb_halo_Pt_peer_finish_inplace": (_i, [_vp, _vp, _vp]),
     "sb_halo_peer_status": (_i, [_vp, _vp]),
     "sb_halo_P_pack": (_i, [_vp, _vp, _vp]),
     "sb_halo_P_finish": (_i, [_vp, _vp, _vp, _vp]),
@@ -367,8 +376,13 @@ class Functional:
         self.integrals.append(integral)
         self._keep = getattr(self, "_keep", []) + [test_faces, list(trial_faces)]
 
-    def __call__(self, t, inputs, wrt=NO_DIFFERENTIATION, out=None, update_state=False):
-        """inputs: list of torch CUDA tensors (device path) or numpy arrays (host path, copies inside the call)."""
+    def wait(self):
+        """results of asynchronous host-buffer calls are valid after this"""
+        check(lib().sb_functional_wait(self.h))
+
+    def __call__(self, t, inputs, wrt=NO_DIFFERENTIATION, out=None, update_state=False, async_host=False):
+        """inputs: list of torch CUDA tensors (device path) or numpy arrays (host path, copies inside the call).
+        async_host: the result's device -> host copy overlaps later calls; call wait() before reading `out`."""
         import torch
         on_host = isinstance(inputs[0], np.ndarray)
         n = self.test.LSize()
@@ -377,8 +391,8 @@ class Functional:
             ptrs = (C.c_void_p * len(ins))(*[a.ctypes.data for a in ins])
             if out is None:
                 out = np.empty(n)
-            check(lib().sb_functional_evaluate(self.h, float(t), wrt, ptrs, 1, _np_ptr(out), 1, int(update_state),
-                                               _stream_ptr()))
+            check(lib().sb_functional_evaluate(self.h, float(t), wrt, ptrs, 1, _np_ptr(out), 2 if async_host else 1,
+                                               int(update_state), _stream_ptr()))
         else:
             ptrs = (C.c_void_p * len(inputs))(*[a.data_ptr() for a in inputs])
             if out is None:
@@ -387,14 +401,15 @@ class Functional:
                                                _stream_ptr()))
         return out
 
-    def GradientMult(self, wrt, du, out=None):
+    def GradientMult(self, wrt, du, out=None, async_host=False):
         import torch
         n = self.test.LSize()
         if isinstance(du, np.ndarray):
             du = np.ascontiguousarray(du, dtype=np.float64)
             if out is None:
                 out = np.empty(n)
-            check(lib().sb_functional_jvp(self.h, wrt, _np_ptr(du), 1, _np_ptr(out), 1, _stream_ptr()))
+            check(lib().sb_functional_jvp(self.h, wrt, _np_ptr(du), 1, _np_ptr(out), 2 if async_host else 1,
+                                          _stream_ptr()))
         else:
             if out is None:
                 out = torch.empty(n, dtype=torch.float64, device=du.device)

@@ -120,6 +120,36 @@ class HaloExchange:
         capi.check(lib.sb_halo_P_finish(self.h, capi._dev_ptr(T), capi._dev_ptr(L), s))
         return L
 
+    # --- the two halves of the peer exchanges (put now, wait + unpack later) ---
+    def P_put(self, T):
+        assert self.peer, "split exchanges need the peer-memory transport"
+        capi.check(capi.lib().sb_halo_P_peer_put(self.h, capi._dev_ptr(T), capi._stream_ptr()))
+
+    def P_finish(self, T, L=None):
+        if L is None:
+            L = self.torch.empty(self.lsize, dtype=self.torch.float64, device=self.device)
+        capi.check(capi.lib().sb_halo_P_peer_finish(self.h, capi._dev_ptr(T), capi._dev_ptr(L), capi._stream_ptr()))
+        return L
+
+    # --- in-place exchanges (owned-first numbering: the T-vector is the first tsize entries of the L-vector TL) ---
+    def owned_first(self):
+        return bool(capi.lib().sb_halo_owned_first(self.h))
+
+    def P_finish_inplace(self, TL):
+        capi.check(capi.lib().sb_halo_P_peer_finish_inplace(self.h, capi._dev_ptr(TL), capi._stream_ptr()))
+        return TL
+
+    def P_inplace(self, TL):
+        """fill the entries of TL owned by other ranks from their owners; the owned prefix is the T-vector, untouched"""
+        self.P_put(TL)
+        return self.P_finish_inplace(TL)
+
+    def Pt_inplace(self, TL):
+        """add every sharer's partial sums into the owned shared entries of TL; TL[:tsize] is then the T-vector"""
+        capi.check(capi.lib().sb_halo_Pt_peer_put(self.h, capi._dev_ptr(TL), capi._stream_ptr()))
+        capi.check(capi.lib().sb_halo_Pt_peer_finish_inplace(self.h, capi._dev_ptr(TL), capi._stream_ptr()))
+        return TL[:self.tsize]
+
     def Pt(self, L, T=None):
         """L-vector -> T-vector: owned entries plus the partial sums every sharer computed, in fixed neighbour order"""
         lib = capi.lib()
@@ -174,21 +204,105 @@ class HostHalo:
 
 
 class ParFunctional:
-    """serac::Functional on a partitioned mesh (functional.hpp:446-498): T-vectors in, T-vector out."""
+    """serac::Functional on a partitioned mesh (functional.hpp:446-498): T-vectors in, T-vector out.
 
-    def __init__(self, functional, trial_halos, test_halo):
+    Exchange scheduling (peer transport; every field in flight has its own halo object):
+      * the puts of all inputs are issued before the first flag wait, so the waits overlap;
+      * with `overlap_halos` (one more halo object per space: du_halos[wrt] for Jacobian-action directions, out_halo for
+        the residual's P^T) the exchange of the direction can be started early with prefetch_direction() and the
+        residual's P^T runs on a side stream next to the following kernels; join() makes the calling stream wait for
+        everything the side stream still owes."""
+
+    def __init__(self, functional, trial_halos, test_halo, du_halos=None, out_halo=None, inplace=False):
+        """inplace: the partitions are numbered owned-first and every vector handed in is an L-sized buffer whose first
+        tsize entries are the T-vector; results are returned as views of the Functional's L-vectors.  P / P^T then touch
+        only the shared entries (no full-vector copies)."""
         self.F, self.trial_halos, self.test_halo = functional, list(trial_halos), test_halo
+        self.du_halos, self.out_halo = dict(du_halos or {}), out_halo
+        self.inplace = bool(inplace)
+        if self.inplace:
+            hs = list(trial_halos) + [test_halo] + list(self.du_halos.values()) + ([out_halo] if out_halo else [])
+            assert all(h.peer and h.owned_first() for h in hs), "in-place exchanges need owned-first peer halos"
         self._L = [None] * len(self.trial_halos)
         self._rL = None
+        self._drL = None
         self._duL = {}
+        self._side = None
+        self._du_ready = {}
+        # distinct objects are needed for fields whose exchanges are in flight together
+        ids = [id(h) for h in self.trial_halos]
+        self._split = all(h.peer for h in self.trial_halos) and len(set(ids)) == len(ids)
+
+    def _side_stream(self):
+        if self._side is None:
+            self._side = capi_torch().cuda.Stream()
+        return self._side
+
+    def prefetch_direction(self, wrt, dT):
+        """start P(dT) for a later GradientMult(wrt, dT) on the side stream (needs du_halos[wrt])"""
+        torch = capi_torch()
+        h = self.du_halos[wrt]
+        side, main = self._side_stream(), torch.cuda.current_stream()
+        side.wait_stream(main)
+        with torch.cuda.stream(side):
+            self._duL[wrt] = h.P_inplace(dT) if self.inplace else h.P(dT, self._duL.get(wrt))
+            ev = torch.cuda.Event()
+            ev.record(side)
+        self._du_ready[wrt] = (ev, dT.data_ptr())
 
     def __call__(self, t, T_inputs, wrt=capi.NO_DIFFERENTIATION, out=None, update_state=False):
-        for i, (h, T) in enumerate(zip(self.trial_halos, T_inputs)):
-            self._L[i] = h.P(T, self._L[i])
+        torch = capi_torch()
+        if self.inplace:
+            assert out is None, "in-place mode returns a view of the Functional's own L-vector"
+            if self._split and len(self.trial_halos) <= 4:  # one put launch + one wait/unpack launch for every input
+                hs = (C.c_void_p * len(self.trial_halos))(*[h.h for h in self.trial_halos])
+                vs = (C.c_void_p * len(T_inputs))(*[TL.data_ptr() for TL in T_inputs])
+                capi.check(capi.lib().sb_halo_P_peer_inplace_multi(len(self.trial_halos), hs, vs, capi._stream_ptr()))
+                self._L = list(T_inputs)
+            else:
+                for h, TL in zip(self.trial_halos, T_inputs):
+                    h.P_put(TL)
+                for i, (h, TL) in enumerate(zip(self.trial_halos, T_inputs)):
+                    self._L[i] = h.P_finish_inplace(TL)
+        elif self._split:
+            for h, T in zip(self.trial_halos, T_inputs):
+                h.P_put(T)
+            for i, (h, T) in enumerate(zip(self.trial_halos, T_inputs)):
+                self._L[i] = h.P_finish(T, self._L[i])
+        else:
+            for i, (h, T) in enumerate(zip(self.trial_halos, T_inputs)):
+                self._L[i] = h.P(T, self._L[i])
         self._rL = self.F(t, self._L, wrt=wrt, out=self._rL, update_state=update_state)
-        return self.test_halo.Pt(self._rL, out)
+        if self.out_halo is not None:
+            side, main = self._side_stream(), torch.cuda.current_stream()
+            side.wait_stream(main)
+            with torch.cuda.stream(side):
+                out = self.out_halo.Pt_inplace(self._rL) if self.inplace else self.out_halo.Pt(self._rL, out)
+            return out  # valid on the calling stream after join()
+        return self.test_halo.Pt_inplace(self._rL) if self.inplace else self.test_halo.Pt(self._rL, out)
 
     def GradientMult(self, wrt, dT, out=None):
-        self._duL[wrt] = self.trial_halos[wrt].P(dT, self._duL.get(wrt))
-        self._rL = self.F.GradientMult(wrt, self._duL[wrt], out=self._rL)
-        return self.test_halo.Pt(self._rL, out)
+        torch = capi_torch()
+        pre = self._du_ready.pop(wrt, None)
+        if pre is not None and pre[1] == dT.data_ptr():
+            torch.cuda.current_stream().wait_event(pre[0])
+        elif self.inplace:
+            self._duL[wrt] = self.trial_halos[wrt].P_inplace(dT)
+        else:
+            self._duL[wrt] = self.trial_halos[wrt].P(dT, self._duL.get(wrt))
+        # its own L-vector: the residual's may still be read by the side stream's P^T
+        self._drL = self.F.GradientMult(wrt, self._duL[wrt], out=self._drL)
+        if self.inplace:
+            assert out is None
+            return self.test_halo.Pt_inplace(self._drL)
+        return self.test_halo.Pt(self._drL, out)
+
+    def join(self):
+        """the calling stream waits for the side stream (results of __call__ with out_halo become valid)"""
+        if self._side is not None:
+            capi_torch().cuda.current_stream().wait_stream(self._side)
+
+
+def capi_torch():
+    import torch
+    return torch

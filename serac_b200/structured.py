@@ -98,8 +98,13 @@ def factor_ranks(world, n=None):
 class Partition:
     """One rank's view of a box partition of a StructuredHexMesh for an H1 space of order p with `components` per node."""
 
-    def __init__(self, mesh, ranks, rank, p, components=1):
+    def __init__(self, mesh, ranks, rank, p, components=1, owned_first=False):
+        """owned_first: number the nodes this rank owns first (in their lexicographic order), the nodes owned by other
+        ranks after them.  The T-vector is then the prefix of the L-vector and P / P^T can run in place
+        (sb_halo_*_inplace).  Default: lexicographic local numbering."""
         self.mesh, self.ranks, self.rank, self.p, self.components = mesh, tuple(ranks), int(rank), int(p), int(components)
+        self.owned_first = bool(owned_first)
+        self.new_of_lex = None  # lexicographic local id -> local id
         px, py, pz = self.ranks
         self.world = px * py * pz
         self.splits = [_split(mesh.n[d], self.ranks[d]) for d in range(3)]
@@ -122,17 +127,35 @@ class Partition:
     def element_table(self, p=None):
         p = self.p if p is None else p
         nb = tuple((p * b[0], p * b[1]) for b in self.box)
-        return self.mesh.element_table(p, self.box, nb)
+        tab = self.mesh.element_table(p, self.box, nb)
+        if self.new_of_lex is not None:
+            assert p == self.p, "an owned-first partition numbers the nodes of its own order only"
+            tab = self.new_of_lex[tab.astype(np.int64)].astype(np.uint64)
+        return tab
 
     def vertex_coordinates(self):
-        return self.mesh.vertex_coordinates(tuple((b[0], b[1]) for b in self.box))
+        xyz = self.mesh.vertex_coordinates(tuple((b[0], b[1]) for b in self.box))
+        if self.new_of_lex is not None:
+            assert self.p == 1, "vertex coordinates in owned-first numbering come from the p = 1 partition"
+            out = np.empty_like(xyz.reshape(-1, 3))
+            out[self.new_of_lex] = xyz.reshape(-1, 3)
+            xyz = out.ravel()
+        return xyz
 
-    def global_node_ids(self):
-        """global lexicographic id of every local node (local order)"""
+    def _lex_global_node_ids(self):
         G = self.mesh.node_grid(self.p)
         (i0, i1), (j0, j1), (k0, k1) = self.node_box
         K, J, I = np.meshgrid(np.arange(k0, k1 + 1), np.arange(j0, j1 + 1), np.arange(i0, i1 + 1), indexing="ij")
         return ((K * G[1] + J) * G[0] + I).ravel().astype(np.int64)
+
+    def global_node_ids(self):
+        """global lexicographic id of every local node (local order)"""
+        gid = self._lex_global_node_ids()
+        if self.new_of_lex is not None:
+            out = np.empty_like(gid)
+            out[self.new_of_lex] = gid
+            gid = out
+        return gid
 
     def _build_sharing(self):
         """which ranks hold each local node; owner = lowest (pfespace.cpp:3527-3545)"""
@@ -164,6 +187,13 @@ class Partition:
                     owner = np.where(mask & (r < owner), r, owner)
         self.owner = owner.ravel()
         self.neighbors = sorted(self.shared_with)
+        if self.owned_first:
+            mine = self.owner == self.rank
+            order = np.concatenate([np.nonzero(mine)[0], np.nonzero(~mine)[0]])  # new id -> lexicographic id
+            self.new_of_lex = np.empty(self.num_local_nodes, dtype=np.int64)
+            self.new_of_lex[order] = np.arange(self.num_local_nodes)
+            self.owner = self.owner[order]
+            self.shared_with = {r: m[order] for r, m in self.shared_with.items()}
         owned = self.owner == self.rank
         self.num_true_nodes = int(owned.sum())
         self.true_of_local = np.full(self.num_local_nodes, -1, dtype=np.int64)

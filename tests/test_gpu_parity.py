@@ -200,3 +200,20 @@ def test_node_major_e_vector_layout_is_bit_identical(case):
     acc = P.torch.full((P.G.LSize(),), 0.5, dtype=P.torch.float64, device=P.dev)
     acc2 = acc.clone()
     assert P.torch.equal(P.G.ScatterAdd(d_ref, acc), P.G.ScatterAdd(d_nm, acc2, node_major=True))
+
+
+def test_async_host_outputs_match(case):
+    """SB_HOST_ASYNC: results copied on the Functional's copy stream are, after wait(), bit-identical to the device path,
+    also when calls are queued back to back on pinned buffers"""
+    prob, P = case
+    torch = P.torch
+    pin = lambda a: torch.as_tensor(np.ascontiguousarray(a), dtype=torch.float64).pin_memory()
+    hS, hU, hA, hdU = (pin(prob[k]) for k in ("S", "U", "A", "dU"))
+    hr, hdr = (torch.empty(P.G.LSize(), dtype=torch.float64).pin_memory() for _ in range(2))
+    r = P.F(0.0, [P.S, P.U, P.A], wrt=1).cpu().numpy()
+    dr = P.F.GradientMult(1, P.dU).cpu().numpy()
+    for _ in range(3):  # queued back to back: the staging buffers are guarded by events
+        P.F(0.0, [hS.numpy(), hU.numpy(), hA.numpy()], wrt=1, out=hr.numpy(), async_host=True)
+        P.F.GradientMult(1, hdU.numpy(), out=hdr.numpy(), async_host=True)
+    P.F.wait()
+    assert np.array_equal(hr.numpy(), r) and np.array_equal(hdr.numpy(), dr)

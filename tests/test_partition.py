@@ -25,12 +25,35 @@ def test_element_table_matches_lexicographic_convention():
     assert m.element_table(2).shape == (2, 27) and m.num_nodes(2) == 5 * 3 * 3
 
 
-@pytest.mark.parametrize("ranks", [(2, 1, 1), (2, 2, 1), (2, 2, 2), (3, 1, 2)])
+@pytest.mark.parametrize("ranks", [(2, 2, 1), (2, 2, 2), (3, 1, 2)])
 @pytest.mark.parametrize("p", [1, 2])
-def test_ownership_and_lists_are_consistent(ranks, p):
+def test_owned_first_numbering(ranks, p):
+    """owned_first=True: the same partition, renumbered so that the T-vector is the prefix of the L-vector (what the
+    in-place exchanges sb_halo_*_inplace require); element tables and node ids follow the renumbering"""
     mesh = StructuredHexMesh(5, 4, 3)
     world = int(np.prod(ranks))
-    parts = [Partition(mesh, ranks, r, p, components=3) for r in range(world)]
+    for r in range(world):
+        a, b = Partition(mesh, ranks, r, p, components=3), Partition(mesh, ranks, r, p, components=3, owned_first=True)
+        l = b.halo_lists()
+        assert np.array_equal(l["ltdof"][:l["tsize"]], np.arange(l["tsize"])) and (l["ltdof"][l["tsize"]:] == -1).all()
+        assert np.array_equal(a.global_true_vdofs(), b.global_true_vdofs())  # owned nodes keep their relative order
+        # same elements, same global nodes
+        assert np.array_equal(a.global_node_ids()[a.element_table().astype(np.int64)],
+                              b.global_node_ids()[b.element_table().astype(np.int64)])
+        assert sorted(a.global_node_ids()) == sorted(b.global_node_ids())
+    if p == 1:
+        a, b = Partition(mesh, ranks, world - 1, 1, 3), Partition(mesh, ranks, world - 1, 1, 3, owned_first=True)
+        xa, xb = a.vertex_coordinates().reshape(-1, 3), b.vertex_coordinates().reshape(-1, 3)
+        assert np.array_equal(xa[np.argsort(a.global_node_ids())], xb[np.argsort(b.global_node_ids())])
+
+
+@pytest.mark.parametrize("owned_first", [False, True])
+@pytest.mark.parametrize("ranks", [(2, 1, 1), (2, 2, 1), (2, 2, 2), (3, 1, 2)])
+@pytest.mark.parametrize("p", [1, 2])
+def test_ownership_and_lists_are_consistent(ranks, p, owned_first):
+    mesh = StructuredHexMesh(5, 4, 3)
+    world = int(np.prod(ranks))
+    parts = [Partition(mesh, ranks, r, p, components=3, owned_first=owned_first) for r in range(world)]
     # every global vdof is owned exactly once
     owned = np.concatenate([pt.global_true_vdofs() for pt in parts])
     assert len(owned) == mesh.num_nodes(p) * 3 and len(np.unique(owned)) == len(owned)

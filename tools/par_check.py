@@ -19,15 +19,17 @@ from serac_b200.structured import Partition, StructuredHexMesh, factor_ranks
 PARAMS = [1.0, 100.0, 50.0, 1.0]
 
 
-def build(dev, mesh, part, p):
-    """Functional for SolidMechanics NeoHookean on `part` (or the whole mesh when part is None)"""
-    src = part if part is not None else mesh
-    tab, tab1 = src.element_table(p), src.element_table(1)
-    nn = part.num_local_nodes if part is not None else mesh.num_nodes(p)
-    nn1 = (Partition(mesh, part.ranks, part.rank, 1).num_local_nodes if part is not None else mesh.num_nodes(1))
+def build(dev, mesh, part, p, part1=None):
+    """Functional for SolidMechanics NeoHookean on `part` (+ its p = 1 partition part1), or the whole mesh when None"""
+    if part is not None:
+        tab, tab1 = part.element_table(p), part1.element_table(1)
+        nn, nn1, xyz = part.num_local_nodes, part1.num_local_nodes, part1.vertex_coordinates()
+    else:
+        tab, tab1 = mesh.element_table(p), mesh.element_table(1)
+        nn, nn1, xyz = mesh.num_nodes(p), mesh.num_nodes(1), mesh.vertex_coordinates()
     G = capi.ElementRestriction(tab, 3, nn)
     G1 = capi.ElementRestriction(tab1, 3, nn1)
-    nodes = torch.as_tensor(src.vertex_coordinates(), dtype=torch.float64, device=dev)
+    nodes = torch.as_tensor(xyz, dtype=torch.float64, device=dev)
     X_q, J_q = capi.geometric_factors(capi.CUBE, 1, p + 1, G1, nodes)
     I = capi.Integral(f"solid_neohookean_hex_p{p}", PARAMS, X_q, J_q, tab.shape[0])
     F = capi.Functional(G, [G1, G, G])
@@ -44,28 +46,51 @@ def main():
     nx, ny, nz, p = (int(a) for a in (sys.argv[1:5] if len(sys.argv) >= 5 else (8, 6, 4, 2)))
     mesh = StructuredHexMesh(nx, ny, nz, 2.0, 1.5, 1.0)
     ranks = factor_ranks(world)
-    part, part1 = Partition(mesh, ranks, rank, p, 3), Partition(mesh, ranks, rank, 1, 3)
-    loc = build(dev, mesh, part, p)
-    halo, halo1 = HaloExchange(part.halo_lists(), dev), HaloExchange(part1.halo_lists(), dev)
+    inplace = (os.environ.get("SB_HALO_TRANSPORT", "peer") == "peer" and os.environ.get("SB_HALO_OVERLAP", "1") != "0"
+               and os.environ.get("SB_HALO_INPLACE", "1") != "0")
+    part = Partition(mesh, ranks, rank, p, 3, owned_first=inplace)
+    part1 = Partition(mesh, ranks, rank, 1, 3, owned_first=inplace)
+    loc = build(dev, mesh, part, p, part1)
+    halo1 = HaloExchange(part1.halo_lists(), dev)
+    halo, halo_a, halo_du, halo_r = (HaloExchange(part.halo_lists(), dev) for _ in range(4))
+    halos = [halo1, halo, halo_a, halo_du, halo_r]
     transport = "nccl"
     if os.environ.get("SB_HALO_TRANSPORT", "peer") == "peer":
-        ok1, ok2 = halo.enable_peer(), halo1.enable_peer()
-        transport = "peer" if (ok1 and ok2) else "nccl"
-    PF = ParFunctional(loc["F"], [halo1, halo, halo], halo)
+        ok = [h.enable_peer() for h in halos]
+        transport = "peer" if all(ok) else "nccl"
+    overlap = transport == "peer" and os.environ.get("SB_HALO_OVERLAP", "1") != "0"
+    if overlap:  # puts before waits, P(dU) prefetched and P^T(r) on a side stream (one halo object per field in flight)
+        PF = ParFunctional(loc["F"], [halo1, halo, halo_a], halo, du_halos={1: halo_du}, out_halo=halo_r,
+                           inplace=inplace)
+    else:
+        PF = ParFunctional(loc["F"], [halo1, halo, halo], halo)
     # globally consistent inputs
     rng = np.random.default_rng(7)
     n, n1 = mesh.num_nodes(p) * 3, mesh.num_nodes(1) * 3
     U, A, S, dU = 0.01 * rng.uniform(-1, 1, n), rng.uniform(-1, 1, n), 0.01 * rng.uniform(-1, 1, n1), rng.uniform(0, 1, n)
     t = lambda a: torch.as_tensor(np.ascontiguousarray(a), dtype=torch.float64, device=dev)
     gt, gt1 = part.global_true_vdofs(), part1.global_true_vdofs()
-    r_T = PF(0.0, [t(S[gt1]), t(U[gt]), t(A[gt])], wrt=1)
-    dr_T = PF.GradientMult(1, t(dU[gt]))
-    for _ in range(5):  # repeated rounds exercise the two-slot ring
-        r_T = PF(0.0, [t(S[gt1]), t(U[gt]), t(A[gt])], wrt=1)
-        dr_T = PF.GradientMult(1, t(dU[gt]))
+    def tvec(values, lsize):
+        """T-vector; in-place mode: an L-sized buffer with the T-vector in its prefix (the rest is filled by P)"""
+        v = t(values)
+        if not inplace:
+            return v
+        buf = torch.full((lsize,), float("nan"), dtype=torch.float64, device=dev)
+        buf[:len(values)] = v
+        return buf
+
+    Ts, Tu, Ta, Tdu = (tvec(S[gt1], loc["G1"].LSize()), tvec(U[gt], loc["G"].LSize()), tvec(A[gt], loc["G"].LSize()),
+                       tvec(dU[gt], loc["G"].LSize()))
+    for _ in range(6):  # repeated rounds exercise the two-slot ring
+        if overlap:
+            PF.prefetch_direction(1, Tdu)
+        r_T = PF(0.0, [Ts, Tu, Ta], wrt=1)
+        dr_T = PF.GradientMult(1, Tdu)
+        PF.join()
     torch.cuda.synchronize()
     if transport == "peer":
-        assert halo.peer_status() == 0 and halo1.peer_status() == 0, "a peer flag wait timed out"
+        assert all(h.peer_status() == 0 for h in halos), "a peer flag wait timed out"
+        transport += ("+overlap" if overlap else "") + ("+inplace" if inplace else "")
     # the same on the whole mesh, one GPU
     glob = build(dev, mesh, None, p)
     r = glob["F"](0.0, [t(S), t(U), t(A)], wrt=1).cpu().numpy()
