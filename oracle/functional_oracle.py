@@ -579,6 +579,90 @@ class J2SmallStrainLinear:
         return [[s[i][j] + (pr if i == j else 0.0) for j in range(3)] for i in range(3)]
 
 
+def _stack_values(A):
+    return np.stack([np.stack([np.broadcast_arrays(value_of(A[i][j]), value_of(A[0][0]))[0] for j in range(3)], -1)
+                     for i in range(3)], -2)
+
+
+def symmetric_mat3_function(A, f, g):
+    """f(A) = Q diag(f(lambda)) Q^T for a symmetric 3x3 tensor given as a list of lists of arrays / Duals; with Dual
+    entries the derivative is sum_ab g(l_a, l_b) Q_ka Q_lb Q_ia Q_jb dA_kl  (F/tuple_tensor_dual_functions.hpp:963-1000).
+    The eigen-decomposition is numpy's (the reference uses the closed form of :802-912; f(A) and its derivative do not
+    depend on which orthonormal eigenbasis is picked)."""
+    Av = _stack_values(A)
+    lam, Q = np.linalg.eigh(Av)
+    fA = np.einsum("...ia,...a,...ja->...ij", Q, f(lam), Q)
+    duals = [A[i][j] for i in range(3) for j in range(3) if isinstance(A[i][j], Dual)]
+    if not duals:
+        return [[fA[..., i, j] for j in range(3)] for i in range(3)]
+    N = duals[0].g.shape[-1]
+    zero = np.zeros(Av.shape[:-2] + (N,))
+    Ag = np.stack([np.stack([A[i][j].g if isinstance(A[i][j], Dual) else zero for j in range(3)], -2)
+                   for i in range(3)], -3)  # [...][k][l][N]
+    G = g(lam[..., :, None], lam[..., None, :])
+    B = np.einsum("...ka,...kln,...lb->...abn", Q, Ag, Q) * G[..., None]
+    out_g = np.einsum("...ia,...abn,...jb->...ijn", Q, B, Q)
+    return [[Dual(fA[..., i, j], out_g[..., i, j, :]) for j in range(3)] for i in range(3)]
+
+
+def log_symm(A):
+    """F/tuple_tensor_dual_functions.hpp:1007-1020"""
+    def g(l1, l2):
+        same = l1 == l2
+        y = np.where(same, 2.0, l1 / l2)
+        return np.where(same, 1.0 / l1, (np.log(y) / (y - 1.0)) / l2)
+    return symmetric_mat3_function(A, np.log, g)
+
+
+def exp_symm(A):
+    """F/tuple_tensor_dual_functions.hpp:1028-1041"""
+    def g(l1, l2):
+        same = l1 == l2
+        arg = np.where(same, 1.0, l1 - l2)
+        return np.where(same, np.exp(l1), np.exp(l2) * np.expm1(arg) / arg)
+    return symmetric_mat3_function(A, np.exp, g)
+
+
+class J2FiniteLinear:
+    """J2<LinearHardening> (src/serac/physics/materials/solid_material.hpp:261-330): finite-deformation J2 in logarithmic
+    strain; state = {"Fpinv": 3x3, "eqps"}.  Linear hardening makes the return-map equation linear, so its root is
+    written in closed form (the reference's scalar solver converges to the same root)."""
+    tol = 1e-10
+
+    def __init__(self, E, nu, sigma_y, Hi, density):
+        self.E, self.nu, self.sigma_y, self.Hi, self.density = E, nu, sigma_y, Hi, density
+
+    def __call__(self, state, du_dX):
+        K = self.E / (3.0 * (1.0 - 2.0 * self.nu))
+        G = 0.5 * self.E / (1.0 + self.nu)
+        Fpinv, eqps_old = state["Fpinv"], state["eqps"]
+        F = madd(du_dX, eye(3))
+        Fe = mdot(F, Fpinv)
+        Ee = mscale(0.5, log_symm(mdot(mT(Fe), Fe)))
+        pr = K * mtr(Ee)
+        s = mscale(2.0 * G, mdev(Ee))
+        q = np.sqrt(1.5) * mnorm(s)
+        qv = value_of(q)
+        yielding = (qv - (self.sigma_y + self.Hi * eqps_old)) > self.tol * self.sigma_y
+        delta = (q - (self.sigma_y + self.Hi * eqps_old)) / (3.0 * G + self.Hi)
+        mask = yielding.astype(float)
+        if isinstance(q, Dual):
+            qsafe = Dual(np.where(yielding, q.v, 1.0), q.g)
+        else:
+            qsafe = np.where(yielding, q, 1.0)
+        Np = [[1.5 * s[i][j] / qsafe for j in range(3)] for i in range(3)]
+        dm = delta * mask  # zero (value and partials) where the step is elastic
+        s = [[s[i][j] - 2.0 * G * dm * Np[i][j] for j in range(3)] for i in range(3)]
+        A = exp_symm([[-1.0 * (dm * Np[i][j]) for j in range(3)] for i in range(3)])  # identity where elastic
+        Fe = mdot(Fe, A)
+        Av = [[value_of(A[i][j]) for j in range(3)] for i in range(3)]
+        state["_updated"] = dict(eqps=eqps_old + value_of(dm), Fpinv=mdot(Fpinv, Av))
+        M = [[s[i][j] + (pr if i == j else 0.0) for j in range(3)] for i in range(3)]
+        FeT = mT(Fe)
+        sig = mdot(mdot(minv(FeT), M), FeT)
+        return mscale(1.0 / mdet(F), sig)
+
+
 class LinearIsotropicConductor:
     """src/serac/physics/materials/thermal_material.hpp:20-65"""
 
@@ -770,6 +854,8 @@ def make_qf(kind, params):
         return shape_aware(material_stress_qf(LinearIsotropic(*params[:3]), params[3] != 0.0))
     if kind == "solid_j2smallstrain_linear":
         return shape_aware(material_stress_qf(J2SmallStrainLinear(*params[:6]), params[6] != 0.0))
+    if kind == "solid_j2_linear":
+        return shape_aware(material_stress_qf(J2FiniteLinear(*params[:5]), params[5] != 0.0))
     if kind == "thermal_linear_conductor":
         return shape_aware(thermal_qf(LinearIsotropicConductor(*params[:3])))
     raise KeyError(kind)

@@ -265,6 +265,10 @@ FIXTURES = [
                                                 p=2, params=[2.0, 100.0, 50.0, 0.0], vdim=3)),
     ("solid_neohookean_quad_p2_cart", dict(mesh_spec=("cart2d", 3, 2, 0.02), kind="solid_neohookean", p=2,
                                            params=[1.0, 100.0, 50.0, 1.0], vdim=2)),
+    # BASELINE.json configs[2]: finite-deformation J2 (logarithmic strain, exponential return map) with the inverse
+    # plastic distortion + eqps as QuadratureData state; E nu sigma_y Hi density geom_nonlin; plastic at most points
+    ("solid_j2_linear_hex_p2_cart", dict(mesh_spec=("cart3d", 2, 1, 2, 0.02), kind="solid_j2_linear", p=2,
+                                         params=[100.0, 0.25, 0.5, 5.0, 1.0, 1.0], vdim=3, u_amp=0.02)),
     # simplex elements (BASELINE.json configs[3] runs on a tet mesh, H1 p=1)
     ("solid_neohookean_tet_p1_beam", dict(mesh_spec=("file", "beam-tet.mesh", 0), kind="solid_neohookean", p=1,
                                           params=[1.0, 100.0, 50.0, 1.0], vdim=3, shape_amp=0.01)),

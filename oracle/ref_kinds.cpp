@@ -142,6 +142,22 @@ ref::Registrar r3("solid_j2smallstrain_linear_" TAG, [](mfem::Mesh& mesh, const 
 });
 #endif
 
+#if REF_DIM == 3
+ref::Registrar r3f("solid_j2_linear_" TAG, [](mfem::Mesh& mesh, const double* q, int n) {
+  SLIC_ERROR_IF(n != 6, "params: E nu sigma_y Hi density geom_nonlin");
+  using Material = solid_mechanics::J2<solid_mechanics::LinearHardening>;
+  Material m{q[0], q[1], solid_mechanics::LinearHardening{q[2], q[3]}, q[4]};
+  ref::IntegralHolder h;
+  using QF = ShapeAwareWithState<MaterialStress<Material>, solid_test, H1<p, dim>, H1<p, dim>>;
+  QF     qf{MaterialStress<Material>{m, q[5] != 0.0}};
+  Domain d  = EntireDomain(mesh);
+  auto   qd = make_qdata<Material::State>(mesh, h, Material::State{});  // Fpinv = I, eqps = 0 (solid_material.hpp:272-275)
+  h.integral   = std::make_unique<Integral>(MakeDomainIntegral<solid_sig, p + 1, dim>(d, qf, qd, {0, 1, 2}));
+  h.num_trials = 3;
+  return h;
+});
+#endif
+
 ref::Registrar r4("thermal_linear_conductor_" TAG, [](mfem::Mesh& mesh, const double* q, int n) {
   SLIC_ERROR_IF(n != 3, "params: density specific_heat conductivity");
   using Material = heat_transfer::LinearIsotropicConductor;

@@ -51,6 +51,23 @@ static Registrar r_j2({"solid_j2smallstrain_linear_" SB_STR(SB_REG_TAG),
                        "{E, nu, sigma_y, Hi, Hk, density, geometric_nonlinearity(0|1)}"});
 #endif
 
+#ifdef SB_REG_J2
+// finite-deformation J2 (solid_material.hpp:261-330; State = inverse plastic distortion + eqps): BASELINE.json configs[2]
+using J2FiniteLin = solid_mechanics::J2<solid_mechanics::LinearHardening>;
+template <typename SS>
+long make_j2_finite(const double* p, int n, void* out, size_t cap)
+{
+  if (n != 6) return -1;
+  J2FiniteLin m{p[0], p[1], solid_mechanics::LinearHardening{p[2], p[3]}, p[4]};
+  auto        gn = (p[5] != 0.0) ? GeometricNonlinearities::On : GeometricNonlinearities::Off;
+  typename SS::template qf<J2FiniteLin> qf{MaterialStressFunctor<J2FiniteLin>(m, gn)};
+  return store_blob(qf, out, cap);
+}
+static Registrar r_j2f({"solid_j2_linear_" SB_STR(SB_REG_TAG),
+                        make_kernel_table<S::type, S::qf<J2FiniteLin>, J2FiniteLin::State>(), &make_j2_finite<S>,
+                        "{E, nu, sigma_y, Hi, density, geometric_nonlinearity(0|1)}"});
+#endif
+
 #ifdef SB_REG_AD
 // the same integrand differentiated with dual numbers end to end (the reference's scheme; what an arbitrary user functor
 // gets): kept to cross-check the tangent fast path

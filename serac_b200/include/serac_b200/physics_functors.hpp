@@ -277,6 +277,72 @@ struct J2SmallStrain {
   }
 };
 
+/// finite-deformation J2 plasticity, logarithmic strain, isotropic hardening (solid_material.hpp:261-330):
+/// multiplicative split F = Fe Fp with the inverse plastic distortion and the equivalent plastic strain as state
+template <typename HardeningType>
+struct J2 {
+  static constexpr int    dim = 3;
+  static constexpr double tol = 1e-10;
+
+  double        E;
+  double        nu;
+  HardeningType hardening;
+  double        density;
+
+  struct State {
+    tensor<double, dim, dim> Fpinv;                       ///< inverse of the plastic distortion (identity initially)
+    double                   accumulated_plastic_strain;  ///< uniaxial equivalent plastic strain
+  };
+
+  struct Residual {
+    double        eqps_old, G;
+    HardeningType hardening;
+    template <typename T1, typename T2>
+    SERAC_HOST_DEVICE auto operator()(const T1& delta_eqps, const T2& trial_mises) const
+    {
+      return trial_mises - 3.0 * G * delta_eqps - hardening(eqps_old + delta_eqps);
+    }
+  };
+
+  template <typename T>
+  SERAC_HOST_DEVICE auto operator()(State& state, const tensor<T, dim, dim>& du_dX) const
+  {
+    auto         I = Identity<dim>();
+    const double K = E / (3.0 * (1.0 - 2.0 * nu));
+    const double G = 0.5 * E / (1.0 + nu);
+
+    // (i) elastic predictor in logarithmic strain
+    auto F  = du_dX + I;
+    auto Fe = dot(F, state.Fpinv);
+    auto Ee = 0.5 * log_symm(dot(transpose(Fe), Fe));
+    auto p  = K * tr(Ee);
+    auto s  = 2.0 * G * dev(Ee);
+    auto q  = ::sqrt(1.5) * norm(s);
+
+    // (ii) admissibility
+    const double eqps_old = state.accumulated_plastic_strain;
+    Residual     residual{eqps_old, G, hardening};
+    if (residual(0.0, get_value(q)) > tol * hardening.sigma_y) {
+      // (iii) return mapping: radial in the Mandel stress, exponential update of the plastic distortion
+      ScalarSolverOptions opts{0, tol * hardening.sigma_y, 25};
+      double              lower_bound = 0.0;
+      double              upper_bound = (get_value(q) - hardening(eqps_old)) / (3.0 * G);
+      auto                delta_eqps  = get<0>(solve_scalar_equation(residual, 0.0, lower_bound, upper_bound, opts, q));
+
+      auto Np = 1.5 * s / q;
+
+      s      = s - 2.0 * G * delta_eqps * Np;
+      auto A = exp_symm(-1.0 * delta_eqps * Np);
+      Fe     = dot(Fe, A);
+      state.accumulated_plastic_strain += get_value(delta_eqps);
+      state.Fpinv = dot(state.Fpinv, get_value(A));
+    }
+    auto M   = s + p * I;  // Mandel stress -> Cauchy
+    auto FeT = transpose(Fe);
+    return dot(dot(inv(FeT), M), FeT) / det(F);
+  }
+};
+
 }  // namespace solid_mechanics
 
 namespace heat_transfer {

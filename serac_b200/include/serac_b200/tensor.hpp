@@ -1226,6 +1226,170 @@ SB_HD auto get_value(const tuple<T...>& t)
   return detail::tuple_map(detail::value_op_any{}, t, std::make_integer_sequence<int, int(sizeof...(T))>{});
 }
 
+// ------------------------------------------------------------------------------------------------
+// isotropic tensor functions of a symmetric 3x3 tensor (tuple_tensor_dual_functions.hpp:791-1045)
+// ------------------------------------------------------------------------------------------------
+/// eigenvalues (ascending) and eigenvectors (columns of Q) of a symmetric 3x3 matrix; closed form after Scherzinger &
+/// Dohrmann, "A robust algorithm for finding the eigenvalues and eigenvectors of 3x3 symmetric matrices" -- the
+/// algorithm the reference uses (tuple_tensor_dual_functions.hpp:802-912): most distinct eigenvalue of the deviator
+/// from the trigonometric solution, its eigenvector from the best-conditioned pair of rows, the other two from the
+/// 2x2 problem in the orthogonal complement.
+SB_HDF void eig_symm(const tensor<double, 3, 3>& A, tensor<double, 3>& eigvals, tensor<double, 3, 3>& eigvecs)
+{
+  const double          pi = 3.14159265358979323846;
+  tensor<double, 3>     eta{};
+  tensor<double, 3, 3>  Q = DenseIdentity<3>();
+  const auto            Ad = dev(A);
+  const double          J2 = 0.5 * inner(Ad, Ad);
+  const double          J3 = det(Ad);
+  if (J2 > 0.0) {
+    double       c     = (0.5 * J3) * pow(3.0 / J2, 1.5);
+    c                  = fmin(fmax(c, -1.0), 1.0);
+    const double alpha = acos(c) / 3.0;
+    const double amp   = 2.0 * sqrt(J2 / 3.0);
+    eta[0]             = (6.0 * alpha < pi) ? amp * cos(alpha) : amp * cos(alpha + 2.0 * pi / 3.0);
+
+    // rows of (A_dev - eta0 I)^T; the two that span its range best give the eigenvector of eta0 as their normal
+    tensor<double, 3, 3> r{};
+    int                  imax = 0;
+    double               nmax = -1.0;
+    for (int i = 0; i < 3; i++) {
+      for (int j = 0; j < 3; j++) r[i][j] = Ad[j][i] - (i == j ? eta[0] : 0.0);
+      const double nr = norm(r[i]);
+      if (nmax < nr) {
+        imax = i;
+        nmax = nr;
+      }
+    }
+    const tensor<double, 3> s0 = normalize(r[imax]);
+    const tensor<double, 3> ra = r[(imax + 1) % 3], rb = r[(imax + 2) % 3];
+    const tensor<double, 3> t1 = ra - dot(ra, s0) * s0;
+    const tensor<double, 3> t2 = rb - dot(rb, s0) * s0;
+    const tensor<double, 3> s1 = normalize((norm(t1) > norm(t2)) ? t1 : t2);
+    const tensor<double, 3> v0 = cross(s0, s1);
+    for (int i = 0; i < 3; i++) Q[i][0] = v0[i];
+
+    // the remaining two eigenvalues: the 2x2 problem in span{s0, s1}
+    const tensor<double, 3> As0 = dot(Ad, s0), As1 = dot(Ad, s1);
+    const double            A11 = dot(s0, As0), A12 = dot(s0, As1), A21 = dot(s1, As0), A22 = dot(s1, As1);
+    const double            d   = A11 - A22;
+    const double            sg  = double((0.0 < d) - (d < 0.0));
+    const double            delta = 0.5 * sg * sqrt(d * d + 4.0 * A12 * A21);
+    eta[1]                        = 0.5 * (A11 + A22) - delta;
+    eta[2]                        = 0.5 * (A11 + A22) + delta;
+    if (fabs(delta) <= 1.0e-15) {  // repeated pair: any basis of the complement
+      for (int i = 0; i < 3; i++) {
+        Q[i][1] = s0[i];
+        Q[i][2] = s1[i];
+      }
+    } else {
+      const tensor<double, 3> u1 = As0 - eta[1] * s0;
+      const tensor<double, 3> u2 = As1 - eta[1] * s1;
+      const tensor<double, 3> w  = normalize((norm(u1) > norm(u2)) ? u1 : u2);
+      const tensor<double, 3> v1 = normalize(cross(w, v0));
+      const tensor<double, 3> v2 = normalize(cross(v0, v1));
+      for (int i = 0; i < 3; i++) {
+        Q[i][1] = v1[i];
+        Q[i][2] = v2[i];
+      }
+    }
+  }
+  const double shift = tr(A) / 3.0;
+  for (int i = 0; i < 3; i++) eta[i] += shift;
+  // ascending order
+  int o[3] = {0, 1, 2};
+  auto swp = [](int& a, int& b) {
+    const int t = a;
+    a           = b;
+    b           = t;
+  };
+  if (eta[o[0]] > eta[o[1]]) swp(o[0], o[1]);
+  if (eta[o[1]] > eta[o[2]]) swp(o[1], o[2]);
+  if (eta[o[0]] > eta[o[1]]) swp(o[0], o[1]);
+  for (int a = 0; a < 3; a++) {
+    eigvals[a] = eta[o[a]];
+    for (int i = 0; i < 3; i++) eigvecs[i][a] = Q[i][o[a]];
+  }
+}
+
+/// f(A) = Q diag(f(lambda)) Q^T; with a dual input the derivative uses the eigenvalue secant function
+/// g(l1, l2) = (f(l1) - f(l2)) / (l1 - l2) (-> f'(l1) when equal), written stably by the caller
+/// (tuple_tensor_dual_functions.hpp:963-1000)
+template <typename T, typename Function, typename EigvalSecantFunction>
+SB_HDF auto symmetric_mat3_function(const tensor<T, 3, 3>& A, const Function& f, const EigvalSecantFunction& g)
+{
+  tensor<double, 3>    lambda{};
+  tensor<double, 3, 3> Q{};
+  eig_symm(get_value(A), lambda, Q);
+  tensor<double, 3, 3> fA{};
+  for (int i = 0; i < 3; i++) {
+    for (int j = 0; j < 3; j++) {
+      double v = 0.0;
+      for (int a = 0; a < 3; a++) v += Q[i][a] * f(lambda[a]) * Q[j][a];
+      fA[i][j] = v;
+    }
+  }
+  if constexpr (!is_dual_number<T>::value) {
+    return fA;
+  } else {
+    constexpr int N = num_partials<T>::value;
+    // rotate the input's partials into the eigenbasis, scale by the secant table, rotate back
+    double G[3][3];
+    for (int a = 0; a < 3; a++)
+      for (int b = 0; b < 3; b++) G[a][b] = g(lambda[a], lambda[b]);
+    tensor<T, 3, 3> out{};
+    for (int i = 0; i < 3; i++)
+      for (int j = 0; j < 3; j++) {
+        out[i][j].value = fA[i][j];
+        for (int n = 0; n < N; n++) out[i][j].gradient[n] = 0.0;
+      }
+    for (int n = 0; n < N; n++) {
+      double B[3][3];  // Q^T dA Q
+      for (int a = 0; a < 3; a++) {
+        for (int b = 0; b < 3; b++) {
+          double v = 0.0;
+          for (int k = 0; k < 3; k++)
+            for (int l = 0; l < 3; l++) v += Q[k][a] * A[k][l].gradient[n] * Q[l][b];
+          B[a][b] = G[a][b] * v;
+        }
+      }
+      for (int i = 0; i < 3; i++) {
+        for (int j = 0; j < 3; j++) {
+          double v = 0.0;
+          for (int a = 0; a < 3; a++)
+            for (int b = 0; b < 3; b++) v += Q[i][a] * B[a][b] * Q[j][b];
+          out[i][j].gradient[n] = v;
+        }
+      }
+    }
+    return out;
+  }
+}
+
+/// logarithm of a symmetric positive definite matrix (tuple_tensor_dual_functions.hpp:1007-1020)
+template <typename T>
+SB_HDF auto log_symm(const tensor<T, 3, 3>& A)
+{
+  auto g = [](double l1, double l2) {
+    if (l1 == l2) return 1.0 / l1;
+    const double y = l1 / l2;
+    return (log(y) / (y - 1.0)) / l2;
+  };
+  return symmetric_mat3_function(A, [](double x) { return log(x); }, g);
+}
+
+/// exponential of a symmetric matrix (tuple_tensor_dual_functions.hpp:1028-1041)
+template <typename T>
+SB_HDF auto exp_symm(const tensor<T, 3, 3>& A)
+{
+  auto g = [](double l1, double l2) {
+    if (l1 == l2) return exp(l1);
+    const double arg = l1 - l2;
+    return exp(l2) * expm1(arg) / arg;
+  };
+  return symmetric_mat3_function(A, [](double x) { return exp(x); }, g);
+}
+
 /// compile-time spatial dimension tag and DependsOn<> (reference: functional.hpp / geometry.hpp)
 template <int d>
 struct Dimension {

@@ -24,16 +24,22 @@ def run_oracle(prob, wrt=1, state=None):
     trials = [fo.gather(shape_table, prob["S"], dim), fo.gather(table, prob["U"], vdim),
               fo.gather(table, prob["A"], vdim)]
     if state is None and "qdata0" in prob:
-        state = j2_state(prob["qdata0"], int(prob["ne"]), fo.num_quadrature_points(geom, q))
+        state = j2_state(prob["qdata0"], int(prob["ne"]), fo.num_quadrature_points(geom, q), tensor_key(prob))
     r_E, blocks = fo.evaluation_kernel(qf, trials, [1, p, p], X_q, J_q, p, q, dim, wrt=wrt, state=state, geom=geom)
     return dict(table=table, shape_table=shape_table, X_q=X_q, J_q=J_q, r_E=r_E, blocks=blocks, p=p, q=q, dim=dim,
                 vdim=vdim, geom=geom)
 
 
-def j2_state(qdata, ne, nq):
-    """[ne][nq] AoS of J2SmallStrain::State {plastic_strain[3][3], eqps} (solid_material.hpp:212-215) -> oracle dict"""
+def tensor_key(prob):
+    """name of the 3x3 state tensor: J2SmallStrain::State::plastic_strain (solid_material.hpp:212-215) or
+    J2::State::Fpinv (:272-275); both are followed by the accumulated plastic strain"""
+    return "Fpinv" if str(prob["kind"]) == "solid_j2_linear" else "plastic_strain"
+
+
+def j2_state(qdata, ne, nq, key="plastic_strain"):
+    """[ne][nq] AoS of {tensor[3][3], eqps} -> oracle dict"""
     s = np.asarray(qdata).reshape(ne, nq, 10)
-    return dict(plastic_strain=[[s[:, :, 3 * i + j].copy() for j in range(3)] for i in range(3)], eqps=s[:, :, 9].copy())
+    return {key: [[s[:, :, 3 * i + j].copy() for j in range(3)] for i in range(3)], "eqps": s[:, :, 9].copy()}
 
 
 @pytest.fixture(scope="module", params=golden_names())
@@ -75,14 +81,15 @@ def test_state_update(case):
     if "qdata1" not in prob:
         pytest.skip("stateless integrand")
     ne, nq = int(prob["ne"]), fo.num_quadrature_points(int(prob["geom"]), int(prob["p"]) + 1)
-    st = j2_state(prob["qdata0"], ne, nq)
+    key = tensor_key(prob)
+    st = j2_state(prob["qdata0"], ne, nq, key)
     run_oracle(prob, wrt=-1, state=st)
     new = st["_updated"]
     want = np.asarray(prob["qdata1"]).reshape(ne, nq, 10)
     assert rel_l2(new["eqps"], want[:, :, 9]) < 1e-13
     for i in range(3):
         for j in range(3):
-            assert np.abs(new["plastic_strain"][i][j] - want[:, :, 3 * i + j]).max() < 1e-14
+            assert np.abs(new[key][i][j] - want[:, :, 3 * i + j]).max() < 1e-13
 
 
 def test_other_arguments(case):
