@@ -145,6 +145,11 @@ typedef struct {
   int           num_elements;
   const double* dqf_dev;
   double*       K_e_dev;
+  int           K_e_node_major; /* 0: K_e is [element][trial vdof][test vdof] with vdof = comp * nodes + node (the
+                                   reference's, F/functional.hpp:599-601); 1: [element][test node][test comp][trial node]
+                                   [trial comp] -- internal to sb_functional_assemble: the entries one CSR row gathers
+                                   from one element are contiguous */
+  int           overwrite;      /* 1: K_e = ... instead of K_e += ... (first integral of an assembly: no memset, no read) */
 } sb_elem_grad_args;
 
 typedef int (*sb_eval_launcher)(const sb_eval_args*, const void* qf_blob, void* stream);
@@ -217,6 +222,10 @@ int sb_integral_derivative_mask(sb_integral_t I, int wrt);
 /* lookup_tables.init(test, trial): sorted unique (row, col) pairs of all elements -> row_ptr / col_ind (bit-exact with
  * the reference), plus the K_e-entry -> nonzero map that replaces nz_LUT's hash lookups. */
 int     sb_csr_create(sb_restriction_t test, sb_restriction_t trial, sb_csr_t* out);
+/* same pattern; K_e_node_major != 0: the object's gather lists address element matrices in the internal node-major
+ * layout (see sb_elem_grad_args), which only sb_functional_assemble produces -- it checks the flag and computes K_e
+ * accordingly.  sb_csr_assemble on such an object expects K_e in that layout. */
+int     sb_csr_create_layout(sb_restriction_t test, sb_restriction_t trial, int K_e_node_major, sb_csr_t* out);
 int     sb_csr_destroy(sb_csr_t A);
 int64_t sb_csr_nnz(sb_csr_t A);
 int64_t sb_csr_num_rows(sb_csr_t A);

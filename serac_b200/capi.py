@@ -69,6 +69,7 @@ SIGNATURES = {
     "sb_integral_derivative_entries": (_i, [_vp, _i]),
     "sb_integral_derivative_mask": (_i, [_vp, _i]),
     "sb_csr_create": (_i, [_vp, _vp, _pp]),
+    "sb_csr_create_layout": (_i, [_vp, _vp, _i, _pp]),
     "sb_csr_destroy": (_i, [_vp]),
     "sb_csr_nnz": (_i64, [_vp]),
     "sb_csr_num_rows": (_i64, [_vp]),
@@ -316,10 +317,11 @@ class Integral:
 class CsrPattern:
     """Mirror of GradientAssemblyLookupTables (dof_numbering.hpp:253-380)."""
 
-    def __init__(self, test, trial, handle=None):
+    def __init__(self, test, trial, handle=None, node_major=False):
+        """node_major: gather lists for element matrices in the Functional's internal layout (sb_csr_create_layout)"""
         if handle is None:
             handle = C.c_void_p()
-            check(lib().sb_csr_create(test.h, trial.h, C.byref(handle)))
+            check(lib().sb_csr_create_layout(test.h, trial.h, int(node_major), C.byref(handle)))
         self.h = handle
         self.nnz = lib().sb_csr_nnz(self.h)
         self.num_rows = lib().sb_csr_num_rows(self.h)
@@ -420,7 +422,7 @@ class Functional:
         """-> (CsrPattern, values): the local CSR triple the reference wraps in mfem::SparseMatrix (functional.hpp:649)."""
         import torch
         if wrt not in self._csr:
-            self._csr[wrt] = CsrPattern(self.test, self.trials[wrt])
+            self._csr[wrt] = CsrPattern(self.test, self.trials[wrt], node_major=True)
         pat = self._csr[wrt]
         hp = C.c_void_p(pat.h.value)
         if on_host:

@@ -113,7 +113,17 @@ struct ElemGradParams {
   int           num_elements;
   const double* dqf;
   double*       K_e;  ///< [element][trial_comp*ntrial + J][test_comp*ntest + I]   (functional.hpp:599-601,632-636)
+  int           node_major;  ///< 1: [element][I][test_comp][J][trial_comp] instead
+  int           overwrite;   ///< 1: store instead of accumulate
 };
+
+/// position of K_e(element; trial comp b, trial node J; test comp a, test node I)
+__device__ __forceinline__ long long k_index(int node_major, long long elem, int b, int J, int a, int I, int ck, int ndk,
+                                             int ct, int ndt)
+{
+  return node_major ? (((elem * ndt + I) * ct + a) * ndk + J) * ck + b
+                    : (elem * (ck * ndk) + (b * ndk + J)) * (long long)(ct * ndt) + a * ndt + I;
+}
 
 // ------------------------------------------------------------------------------------------------
 // component accessors that hide the c == 1 special cases of the q-function argument types
@@ -1616,8 +1626,11 @@ struct ElemGradConfig {
   static constexpr DerivativeLayout layout() { return make_layout(ct, ck, dim, d00, d01, d10, d11); }
 };
 
+#ifndef SB_EG_MINB
+#define SB_EG_MINB 1
+#endif
 template <int dim, int q, int nk, int ck, int nt, int ct, int MASK, int EPB_ = 0>
-__global__ void __launch_bounds__(ElemGradConfig<dim, q, nk, ck, nt, ct, MASK, EPB_>::threads)
+__global__ void __launch_bounds__(ElemGradConfig<dim, q, nk, ck, nt, ct, MASK, EPB_>::threads, SB_EG_MINB)
     element_gradient_kernel(const __grid_constant__ ElemGradParams P)
 {
   using C                       = ElemGradConfig<dim, q, nk, ck, nt, ct, MASK, EPB_>;
@@ -1719,7 +1732,8 @@ __global__ void __launch_bounds__(ElemGradConfig<dim, q, nk, ck, nt, ct, MASK, E
       for (int a = 0; a < ct; a++) {
         SB_UNROLL
         for (int b = 0; b < ck; b++) {
-          P.K_e[((long long)elem * (ck * ndk) + (b * ndk + J)) * (ct * ndt) + a * ndt + I] += out[a * ck + b];
+          const long long at = k_index(P.node_major, elem, b, J, a, I, ck, ndk, ct, ndt);
+          P.K_e[at]          = P.overwrite ? out[a * ck + b] : P.K_e[at] + out[a * ck + b];
         }
       }
     }

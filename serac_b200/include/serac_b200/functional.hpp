@@ -370,7 +370,8 @@ class Functional<test(trials...)> {
       Functional& f = g.form_;
       const int   w = g.which_argument_;
       if (f.csr_.size() < size_t(num_trial_spaces)) f.csr_.resize(size_t(num_trial_spaces), nullptr);
-      if (!f.csr_[size_t(w)]) SERAC_B200_CHECK(sb_csr_create(f.G_test_, f.G_trial_[size_t(w)], &f.csr_[size_t(w)]));
+      if (!f.csr_[size_t(w)])
+        SERAC_B200_CHECK(sb_csr_create_layout(f.G_test_, f.G_trial_[size_t(w)], 1, &f.csr_[size_t(w)]));
       sb_csr_t A   = f.csr_[size_t(w)];
       auto     out = std::make_unique<CsrMatrix>();
       out->num_rows = sb_csr_num_rows(A);

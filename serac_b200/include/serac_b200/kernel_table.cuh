@@ -229,6 +229,8 @@ int launch_element_gradient(const sb_elem_grad_args* a, void* stream)
     P.num_elements = a->num_elements;
     P.dqf          = a->dqf_dev;
     P.K_e          = a->K_e_dev;
+    P.node_major   = a->K_e_node_major;
+    P.overwrite    = a->overwrite;
     if (a->num_elements <= 0) return 0;
     if constexpr (Sig::simplex) {
       using SX            = SimplexConfig<Sig::geometry, Sig::q, trial::order, ck, Sig::test_space::order, Sig::test_c, MASK, Sig::EPB>;

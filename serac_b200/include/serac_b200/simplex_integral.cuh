@@ -206,7 +206,8 @@ __global__ void __launch_bounds__(SimplexConfig<geom, Q, pk, ck, pt, ct, MASK, E
       for (int a = 0; a < ct; a++) {
         SB_UNROLL
         for (int b = 0; b < ck; b++) {
-          P.K_e[((long long)elem * (ck * ndk) + (b * ndk + J)) * (ct * ndt) + a * ndt + ql] += out[a * ck + b];
+          const long long at = k_index(P.node_major, elem, b, J, a, ql, ck, ndk, ct, ndt);
+          P.K_e[at]          = P.overwrite ? out[a * ck + b] : P.K_e[at] + out[a * ck + b];
         }
       }
     }
