@@ -46,7 +46,7 @@ def make_mesh(spec):
 
 
 def reference_problem(mesh_spec, kind, p, params, vdim, seed=42, with_matrix=True, shape_amp=0.0, state_init=None,
-                      u_amp=0.01):
+                      u_amp=0.01, subset=None):
     """Runs the reference path for one Integral on the whole mesh with signature test(shape p=1 vector, u, a)
     (SolidMechanics: vdim = dim; HeatTransfer: vdim = 1) and returns inputs + outputs as a dict of numpy arrays."""
     mesh = make_mesh(mesh_spec)
@@ -63,7 +63,10 @@ def reference_problem(mesh_spec, kind, p, params, vdim, seed=42, with_matrix=Tru
     order, ordering, nodes, nodes_info = mesh.nodes()
     X_q, J_q = mesh.geometric_factors(q)
 
-    I = ref.Integral(f"{kind}_{tag}", mesh, params)
+    # subset: callable ne -> bool mask; the integral then lives on Domain::ofElements of the selected elements
+    # (F/tests/functional_with_domain.cpp): E-vectors stay full size, derivatives are indexed by position in the domain
+    mask = None if subset is None else np.asarray(subset(mesh.ne), dtype=bool)
+    I = ref.Integral(f"{kind}_{tag}", mesh, params, element_mask=mask)
     out = dict(
         kind=kind, geom=mesh.geom, dim=dim, p=p, vdim=vdim, ne=mesh.ne, params=np.asarray(params, dtype=np.float64),
         native_dofs=space.native_dofs(), dof_info=space.dof_info(), num_nodes=space.num_nodes,
@@ -73,6 +76,8 @@ def reference_problem(mesh_spec, kind, p, params, vdim, seed=42, with_matrix=Tru
         mesh_num_nodes=len(nodes) // dim,
         U=U, A=A, S=S, dU=dU, X_q=X_q, J_q=J_q,
     )
+    if mask is not None:
+        out["domain_elements"] = np.nonzero(mask)[0].astype(np.int32)
     ins = [shape_space.gather(S), space.gather(U), space.gather(A)]
     out["U_E"] = ins[1]
     state_bytes = I.state_bytes()
@@ -269,6 +274,13 @@ FIXTURES = [
     # plastic distortion + eqps as QuadratureData state; E nu sigma_y Hi density geom_nonlin; plastic at most points
     ("solid_j2_linear_hex_p2_cart", dict(mesh_spec=("cart3d", 2, 1, 2, 0.02), kind="solid_j2_linear", p=2,
                                          params=[100.0, 0.25, 0.5, 5.0, 1.0, 1.0], vdim=3, u_amp=0.02)),
+    # integrals on part of the mesh (Domain::ofElements; F/tests/functional_with_domain.cpp)
+    ("solid_neohookean_hex_p2_subdomain", dict(mesh_spec=("cart3d", 3, 2, 2, 0.02), kind="solid_neohookean", p=2,
+                                               params=[1.0, 100.0, 50.0, 1.0], vdim=3, shape_amp=0.01,
+                                               subset=lambda ne: np.arange(ne) % 3 != 1)),
+    ("thermal_linear_conductor_tet_p2_subdomain", dict(mesh_spec=("cart3d_tet", 2, 1, 1, 0.02),
+                                                       kind="thermal_linear_conductor", p=2, params=[1.5, 2.0, 0.7],
+                                                       vdim=1, subset=lambda ne: np.arange(ne) % 4 != 2)),
     # simplex elements (BASELINE.json configs[3] runs on a tet mesh, H1 p=1)
     ("solid_neohookean_tet_p1_beam", dict(mesh_spec=("file", "beam-tet.mesh", 0), kind="solid_neohookean", p=1,
                                           params=[1.0, 100.0, 50.0, 1.0], vdim=3, shape_amp=0.01)),

@@ -71,6 +71,7 @@ def lib():
             "ref_num_kinds": (i, []),
             "ref_kind_name": (C.c_char_p, [i]),
             "ref_integral_create": (vp, [C.c_char_p, vp, vp, i]),
+            "ref_integral_create_subset": (vp, [C.c_char_p, vp, vp, i, vp, i]),
             "ref_integral_destroy": (None, [vp]),
             "ref_integral_state_bytes": (C.c_size_t, [vp]),
             "ref_integral_qdata_count": (C.c_size_t, [vp]),
@@ -276,9 +277,15 @@ def kinds():
 class Integral:
     """One reference Integral (integral.hpp:24) on the entire mesh; E-vector level API."""
 
-    def __init__(self, kind, mesh, params, boundary=False):
+    def __init__(self, kind, mesh, params, boundary=False, element_mask=None):
+        """element_mask: bool per mesh element -> the integral's domain is Domain::ofElements of the selected ones"""
         params = np.ascontiguousarray(params, dtype=np.float64)
-        self.h = lib().ref_integral_create(kind.encode(), mesh.h, _p(params), len(params))
+        if element_mask is None:
+            self.h = lib().ref_integral_create(kind.encode(), mesh.h, _p(params), len(params))
+        else:
+            m = np.ascontiguousarray(element_mask, dtype=np.uint8)
+            assert len(m) == mesh.ne and not boundary
+            self.h = lib().ref_integral_create_subset(kind.encode(), mesh.h, _p(params), len(params), _p(m), len(m))
         if not self.h:
             raise KeyError(kind)
         self.mesh = mesh

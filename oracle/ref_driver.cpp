@@ -21,6 +21,23 @@ struct Space {
 using namespace ref;
 std::vector<std::vector<int> > lexicographic_permutations(int p);  // element_restriction.cpp:7
 
+namespace ref {
+static const std::vector<char>* g_domain_mask = nullptr;
+
+serac::Domain domain_for(mfem::Mesh& mesh)
+{
+  if (!g_domain_mask) return serac::EntireDomain(mesh);
+  const std::vector<char>& mask = *g_domain_mask;
+  size_t                   i    = 0;  // the predicate is called once per element, in element order (domain.cpp:249-256)
+  if (mesh.SpaceDimension() == 2)
+    return serac::Domain::ofElements(mesh, std::function<bool(std::vector<serac::vec2>, int)>(
+                                               [&mask, i](std::vector<serac::vec2>, int) mutable { return mask[i++] != 0; }));
+  return serac::Domain::ofElements(mesh, std::function<bool(std::vector<serac::vec3>, int)>(
+                                             [&mask, i](std::vector<serac::vec3>, int) mutable { return mask[i++] != 0; }));
+}
+}  // namespace ref
+using ref::g_domain_mask;
+
 extern "C" {
 
 // ---- mesh ----
@@ -344,6 +361,18 @@ const char* ref_kind_name(int i)
   auto it = factories().begin();
   std::advance(it, i);
   return it->first.c_str();
+}
+/// same, on the sub-domain of the elements with mask[e] != 0 (element order of the mesh)
+void* ref_integral_create_subset(const char* kind, void* mesh, const double* params, int nparams,
+                                 const unsigned char* mask, int nmask)
+{
+  auto it = factories().find(kind);
+  if (it == factories().end()) return nullptr;
+  std::vector<char> m(mask, mask + nmask);
+  g_domain_mask = &m;
+  auto* h       = new IntegralHolder(it->second(*static_cast<mfem::Mesh*>(mesh), params, nparams));
+  g_domain_mask = nullptr;
+  return h;
 }
 void* ref_integral_create(const char* kind, void* mesh, const double* params, int nparams)
 {

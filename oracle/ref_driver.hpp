@@ -30,6 +30,10 @@ struct IntegralHolder {
 using Factory = std::function<IntegralHolder(mfem::Mesh& mesh, const double* params, int nparams)>;
 std::map<std::string, Factory>& factories();
 
+/// the domain the next factory call integrates over: EntireDomain(mesh), or the elements selected by the mask installed
+/// through ref_integral_create_subset (Domain::ofElements, F/domain.cpp:231-306)
+serac::Domain domain_for(mfem::Mesh& mesh);
+
 struct Registrar {
   Registrar(const std::string& name, Factory f) { factories()[name] = f; }
 };

@@ -107,7 +107,7 @@ ref::IntegralHolder make_solid_stateless(mfem::Mesh& mesh, Material m, bool gn)
   ref::IntegralHolder h;
   using QF = ShapeAwareWithState<MaterialStress<Material>, solid_test, H1<p, dim>, H1<p, dim>>;
   QF     qf{MaterialStress<Material>{m, gn}};
-  Domain d     = EntireDomain(mesh);
+  Domain d     = ref::domain_for(mesh);
   h.integral   = std::make_unique<Integral>(MakeDomainIntegral<solid_sig, p + 1, dim>(d, qf, EmptyQData, {0, 1, 2}));
   h.num_trials = 3;
   return h;
@@ -134,7 +134,7 @@ ref::Registrar r3("solid_j2smallstrain_linear_" TAG, [](mfem::Mesh& mesh, const 
   ref::IntegralHolder h;
   using QF = ShapeAwareWithState<MaterialStress<Material>, solid_test, H1<p, dim>, H1<p, dim>>;
   QF     qf{MaterialStress<Material>{m, q[6] != 0.0}};
-  Domain d  = EntireDomain(mesh);
+  Domain d  = ref::domain_for(mesh);
   auto   qd = make_qdata<Material::State>(mesh, h, Material::State{});
   h.integral   = std::make_unique<Integral>(MakeDomainIntegral<solid_sig, p + 1, dim>(d, qf, qd, {0, 1, 2}));
   h.num_trials = 3;
@@ -150,7 +150,7 @@ ref::Registrar r3f("solid_j2_linear_" TAG, [](mfem::Mesh& mesh, const double* q,
   ref::IntegralHolder h;
   using QF = ShapeAwareWithState<MaterialStress<Material>, solid_test, H1<p, dim>, H1<p, dim>>;
   QF     qf{MaterialStress<Material>{m, q[5] != 0.0}};
-  Domain d  = EntireDomain(mesh);
+  Domain d  = ref::domain_for(mesh);
   auto   qd = make_qdata<Material::State>(mesh, h, Material::State{});  // Fpinv = I, eqps = 0 (solid_material.hpp:272-275)
   h.integral   = std::make_unique<Integral>(MakeDomainIntegral<solid_sig, p + 1, dim>(d, qf, qd, {0, 1, 2}));
   h.num_trials = 3;
@@ -164,7 +164,7 @@ ref::Registrar r4("thermal_linear_conductor_" TAG, [](mfem::Mesh& mesh, const do
   ref::IntegralHolder h;
   using QF = ShapeAware<ThermalIntegrand<Material>, H1<p>, H1<p>, H1<p>>;
   QF     qf{ThermalIntegrand<Material>{Material(q[0], q[1], q[2])}};
-  Domain d     = EntireDomain(mesh);
+  Domain d     = ref::domain_for(mesh);
   h.integral   = std::make_unique<Integral>(MakeDomainIntegral<thermal_sig, p + 1, dim>(d, qf, NoQData, {0, 1, 2}));
   h.num_trials = 3;
   return h;
@@ -245,7 +245,7 @@ ref::Registrar r7("thermoelastic_solid_" TAG, [](mfem::Mesh& mesh, const double*
   using QF   = ShapeAwareWithState<MaterialStressWithParam<Mech>, solid_test, H1<p, dim>, H1<p, dim>, H1<p>>;
   QF     qf{MaterialStressWithParam<Mech>{Mech{mat, mat.density}, q[7] != 0.0}};
   ref::IntegralHolder h;
-  Domain d  = EntireDomain(mesh);
+  Domain d  = ref::domain_for(mesh);
   auto   qd = make_qdata<GSV::State>(mesh, h, GSV::State{});
   h.integral   = std::make_unique<Integral>(MakeDomainIntegral<sig, p + 1, dim>(d, qf, qd, {0, 1, 2, 3}));
   h.num_trials = 4;
@@ -260,7 +260,7 @@ ref::Registrar r8("thermoelastic_thermal_" TAG, [](mfem::Mesh& mesh, const doubl
   using QF    = ShapeAware<ThermalIntegrandWithParam<Therm>, H1<p>, H1<p>, H1<p>, H1<p, dim>>;
   QF     qf{ThermalIntegrandWithParam<Therm>{Therm{mat}}};
   ref::IntegralHolder h;
-  Domain d     = EntireDomain(mesh);
+  Domain d     = ref::domain_for(mesh);
   h.integral   = std::make_unique<Integral>(MakeDomainIntegral<sig, p + 1, dim>(d, qf, NoQData, {0, 1, 2, 3}));
   h.num_trials = 4;
   return h;

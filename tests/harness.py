@@ -70,9 +70,19 @@ class Product:
         t = lambda a: torch.as_tensor(np.ascontiguousarray(a), dtype=torch.float64, device=device)
         self.t = t
         self.nodes = t(prob["mesh_nodes"])
-        self.X_q, self.J_q = capi.geometric_factors(geom, int(prob["mesh_order"]), p + 1, self.G_mesh, self.nodes)
+        # integrals on part of the mesh (Domain::ofElements): geometric factors, stored derivatives and state are indexed
+        # by position in the domain, E-vectors by element id (domain_integral_kernels.hpp:183-216)
+        self.domain = prob["domain_elements"].astype(np.int32) if "domain_elements" in prob else None
+        if self.domain is None:
+            self.X_q, self.J_q = capi.geometric_factors(geom, int(prob["mesh_order"]), p + 1, self.G_mesh, self.nodes)
+            ne_dom = int(prob["ne"])
+        else:
+            self._domain_dev = torch.as_tensor(self.domain, dtype=torch.int32, device=device)
+            ne_dom = len(self.domain)
+            self.X_q, self.J_q = capi.geometric_factors(geom, int(prob["mesh_order"]), p + 1, self.G_mesh, self.nodes,
+                                                        num_elements=ne_dom, elements=self._domain_dev)
         name = f"{prob['kind']}_{KIND_TO_NAME[geom]}_p{p}{name_suffix}"
-        self.integral = capi.Integral(name, prob["params"], self.X_q, self.J_q, int(prob["ne"]))
+        self.integral = capi.Integral(name, prob["params"], self.X_q, self.J_q, ne_dom, elements=self.domain)
         if "U" not in prob:  # full-size fixtures regenerate the inputs from the seed (oracle/make_golden.py)
             prob.update(make_inputs(int(prob["seed"]), self.G.LSize(), self.G_shape.LSize(), u_amp=float(prob["u_amp"])))
         self.U, self.A, self.S, self.dU = t(prob["U"]), t(prob["A"]), t(prob["S"]), t(prob["dU"])

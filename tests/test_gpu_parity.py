@@ -41,8 +41,9 @@ def test_scatter_add_bit_exact(case):
 
 def test_geometric_factors(case):
     prob, P = case
-    assert rel_l2(P.X_q.cpu().numpy(), prob["X_q"]) < 1e-14
-    assert rel_l2(P.J_q.cpu().numpy(), prob["J_q"]) < 1e-14
+    sel = slice(None) if P.domain is None else P.domain  # the fixture holds the factors of every element
+    assert rel_l2(P.X_q.cpu().numpy(), prob["X_q"][sel]) < 1e-14
+    assert rel_l2(P.J_q.cpu().numpy(), prob["J_q"][sel]) < 1e-14
 
 
 def test_residual(case):
@@ -217,3 +218,42 @@ def test_async_host_outputs_match(case):
         P.F.GradientMult(1, hdU.numpy(), out=hdr.numpy(), async_host=True)
     P.F.wait()
     assert np.array_equal(hr.numpy(), r) and np.array_equal(hdr.numpy(), dr)
+
+
+def test_complementary_subdomains_sum_to_the_whole(cuda):
+    """Two integrals of one Functional on complementary parts of the mesh (functional.hpp:446-498 sums every integral's
+    E-vector into the same output) equal the integral on the entire mesh; an empty domain contributes exactly zero."""
+    import torch
+    from serac_b200 import capi
+    prob = load_golden("solid_neohookean_hex_p2_subdomain")
+    part = Product(prob, cuda)  # integral on the fixture's sub-domain
+    whole_prob = dict(prob)
+    del whole_prob["domain_elements"]
+    whole = Product(whole_prob, cuda)
+    ne = int(prob["ne"])
+    rest = np.setdiff1d(np.arange(ne, dtype=np.int32), part.domain).astype(np.int32)
+    rest_dev = torch.as_tensor(rest, dtype=torch.int32, device=cuda)
+    name = "solid_neohookean_hex_p2"
+    X2, J2 = capi.geometric_factors(part.geom, int(prob["mesh_order"]), 3, part.G_mesh, part.nodes, num_elements=len(rest),
+                                    elements=rest_dev)
+    I_rest = capi.Integral(name, prob["params"], X2, J2, len(rest), elements=rest)
+    X0, J0 = capi.geometric_factors(part.geom, int(prob["mesh_order"]), 3, part.G_mesh, part.nodes, num_elements=0,
+                                    elements=torch.zeros(0, dtype=torch.int32, device=cuda))
+    I_empty = capi.Integral(name, prob["params"], X0, J0, 0, elements=np.zeros(0, dtype=np.int32))
+    F2 = capi.Functional(part.G, [part.G_shape, part.G, part.G])
+    F2.AddDomainIntegral(part.integral, [0, 1, 2])
+    F2.AddDomainIntegral(I_rest, [0, 1, 2])
+    F2.AddDomainIntegral(I_empty, [0, 1, 2])
+    r2 = F2(0.0, [part.S, part.U, part.A], wrt=1).cpu().numpy()
+    rw = whole.F(0.0, [whole.S, whole.U, whole.A], wrt=1).cpu().numpy()
+    assert rel_l2(r2, rw) < 1e-14
+    d2 = F2.GradientMult(1, part.dU).cpu().numpy()
+    dw = whole.F.GradientMult(1, whole.dU).cpu().numpy()
+    assert rel_l2(d2, dw) < 1e-14
+    _, v2 = F2.assemble(1)
+    _, vw = whole.F.assemble(1)
+    assert rel_l2(v2.cpu().numpy(), vw.cpu().numpy()) < 1e-14
+    # the empty domain alone: exactly zero residual
+    F0 = capi.Functional(part.G, [part.G_shape, part.G, part.G])
+    F0.AddDomainIntegral(I_empty, [0, 1, 2])
+    assert float(F0(0.0, [part.S, part.U, part.A]).abs().max()) == 0.0

@@ -26,6 +26,13 @@ def run_oracle(prob, wrt=1, state=None):
     if state is None and "qdata0" in prob:
         state = j2_state(prob["qdata0"], int(prob["ne"]), fo.num_quadrature_points(geom, q), tensor_key(prob))
     r_E, blocks = fo.evaluation_kernel(qf, trials, [1, p, p], X_q, J_q, p, q, dim, wrt=wrt, state=state, geom=geom)
+    outside = np.ones(int(prob["ne"]), dtype=bool)
+    if "domain_elements" in prob:  # Domain::ofElements: elements outside the domain contribute nothing
+        outside[prob["domain_elements"]] = False
+        r_E[outside] = 0.0
+        if blocks is not None:
+            for b in blocks.values():
+                b[outside] = 0.0
     return dict(table=table, shape_table=shape_table, X_q=X_q, J_q=J_q, r_E=r_E, blocks=blocks, p=p, q=q, dim=dim,
                 vdim=vdim, geom=geom)
 
