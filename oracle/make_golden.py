@@ -253,6 +253,11 @@ BOUNDARY_FIXTURES = [
                                         params=[3.0, 1.0], shape_amp=0.01)),
     ("solid_pressure_hex_p1_patch", dict(mesh_spec=("file", "patch3D_hexes.mesh", 0), kind="solid_pressure", p=1,
                                          params=[-1.5, 1.0], shape_amp=0.01)),
+    # triangular faces of tet meshes (BASELINE.json configs[3] runs on a tet mesh)
+    ("solid_pressure_tet_p2_cart", dict(mesh_spec=("cart3d_tet", 1, 1, 2, 0.02), kind="solid_pressure", p=2,
+                                        params=[3.0, 1.0], shape_amp=0.01)),
+    ("solid_traction_tet_p1_beam", dict(mesh_spec=("file", "beam-tet.mesh", 0), kind="solid_traction", p=1,
+                                        params=[0.3, -1.0, 2.0], shape_amp=0.01)),
     # dead traction: only the shape derivative is non-zero (setTraction)
     ("solid_traction_hex_p2_cart", dict(mesh_spec=("cart3d", 2, 2, 1, 0.02), kind="solid_traction", p=2,
                                         params=[0.3, -1.0, 2.0], shape_amp=0.01)),
