@@ -32,13 +32,12 @@ long make_blob(const double* p, int n, void* out, size_t cap)
 #endif
 #if TUNE_SET == 0
 TUNE(4, 1, 4)
-TUNE(4, 1, 5)
-TUNE(4, 1, 6)
-#elif TUNE_SET == 1
-TUNE(8, 1, 1)
-TUNE(8, 1, 2)
-TUNE(2, 1, 6)
 TUNE(2, 1, 8)
+TUNE(2, 1, 7)
+#elif TUNE_SET == 1
+TUNE(3, 1, 5)
+TUNE(3, 1, 6)
+TUNE(1, 1, 16)
 #endif
 }  // namespace
 }  // namespace sb

@@ -603,13 +603,39 @@ struct BoundaryIntegrand {
   }
 };
 
+/// elements per CTA of the EVALUATION kernel.  The stored-derivative tiles (and the JVP / element-gradient kernels that
+/// stream them) keep Sig::EPB elements per tile; the evaluation kernel may use fewer elements per CTA and then writes
+/// its derivatives into the right lanes of the tile its elements belong to.  p = 2 hexes: ONE element = one warp per
+/// CTA, 16 CTAs/SM -- block barriers cost nothing and CTAs retire independently (measured: 175 -> 161 us on config A;
+/// the JVP stream kernel wants the 4-element tiles: 107 us vs 163 us with 1-element tiles).
+#ifndef SB_EVAL_CTA_E_HEX_Q3
+#define SB_EVAL_CTA_E_HEX_Q3 1
+#endif
+#ifndef SB_EVAL_CTA_E_HEX_Q4
+#define SB_EVAL_CTA_E_HEX_Q4 1
+#endif
+template <typename Sig>
+constexpr int eval_cta_elements()
+{
+  if (Sig::geometry == Geometry::CUBE && Sig::q == 3 && !Sig::boundary) {
+    return (Sig::EPB % SB_EVAL_CTA_E_HEX_Q3 == 0) ? SB_EVAL_CTA_E_HEX_Q3 : Sig::EPB;
+  }
+  if (Sig::geometry == Geometry::CUBE && Sig::q == 4 && !Sig::boundary) {  // p = 3: 64 points = two full warps
+    return (Sig::EPB % SB_EVAL_CTA_E_HEX_Q4 == 0) ? SB_EVAL_CTA_E_HEX_Q4 : Sig::EPB;
+  }
+  return Sig::EPB;
+}
+
 /// shared-memory plan of the evaluation kernel (doubles):
 ///   [tables: (NT + 1) x 2 x MAX_Q^2][gathered dofs of every trial field: EPB x c x ndof each][work: EPB x W]
 /// The interpolation work areas of the trial fields are disjoint (all fields advance stage by stage together, two
 /// barriers in total); the integration scratch of the test space reuses the same work area afterwards.
 template <typename Sig>
 struct EvalLayout {
-  static constexpr int dim = Sig::dim, q = Sig::q, NT = Sig::NT, EPB = Sig::EPB;
+  static constexpr int dim = Sig::dim, q = Sig::q, NT = Sig::NT, EPB = eval_cta_elements<Sig>();
+  static constexpr int CE      = EPB;                ///< elements per CTA
+  static constexpr int threads = CE * Sig::QPE;      ///< threads per CTA
+  static constexpr int TILE    = Sig::EPB * Sig::QPE;  ///< lanes of a stored-derivative tile
   static constexpr int QPE = Sig::QPE;
   static constexpr int ndof(int i) { return Sig::trial_ndof(i); }
   /// simplex: offset of space i's {phi, dphi} table (i == NT: test space); the nq weights follow the last table
@@ -1023,14 +1049,14 @@ __device__ __forceinline__ auto call_qf_tuple(const QF& qf, double t, const Pos&
 
 /// ROWS: gradient rows seeded per derivative pass (1 .. ck); MINB: __launch_bounds__ minimum resident CTAs per SM
 template <typename Sig, int WRT, typename QF, typename State, int ROWS = 1, int MINB = 1, bool FAST = true>
-__global__ void __launch_bounds__(Sig::threads, MINB) evaluation_kernel(const __grid_constant__ EvalParams<Sig::NT> P,
+__global__ void __launch_bounds__(EvalLayout<Sig>::threads, MINB) evaluation_kernel(const __grid_constant__ EvalParams<Sig::NT> P,
                                                                   const __grid_constant__ QF qf)
 {
   constexpr int dim = Sig::dim;
   constexpr int q   = Sig::q;
   constexpr int NT  = Sig::NT;
   constexpr int QPE = Sig::QPE;
-  constexpr int EPB = Sig::EPB;
+  constexpr int EPB = EvalLayout<Sig>::CE;  // elements of THIS CTA (the derivative tile has Sig::EPB)
   constexpr int ct  = Sig::test_c;
   using LAY         = EvalLayout<Sig>;
   constexpr int per = LAY::W;
@@ -1050,13 +1076,13 @@ __global__ void __launch_bounds__(Sig::threads, MINB) evaluation_kernel(const __
         constexpr int off = LAY::simplex_tab_off(J);
         constexpr int sz  = LAY::simplex_tab_size(J) + (J == NT ? QPE : 0);
         const double* src = P.simplex_tab[J];
-        for (int i = threadIdx.x; i < sz; i += Sig::threads) tables[off + i] = src[i];
+        for (int i = threadIdx.x; i < sz; i += LAY::threads) tables[off + i] = src[i];
       };
       (copy(std::integral_constant<int, I>{}), ...);
     }
     (std::make_integer_sequence<int, NT + 1>{});
   } else {
-    for (int i = threadIdx.x; i < LAY::tables; i += Sig::threads) {
+    for (int i = threadIdx.x; i < LAY::tables; i += LAY::threads) {
       const int           which = i / (2 * MAX_Q * MAX_Q);
       const int           rem   = i - which * (2 * MAX_Q * MAX_Q);
       const BasisTable1D& bt    = (which < NT) ? P.trial_basis[which < NT ? which : 0] : P.test_basis;
@@ -1080,11 +1106,11 @@ __global__ void __launch_bounds__(Sig::threads, MINB) evaluation_kernel(const __
   if (P.prefetch_distance > 0 && !P.elements) {
     const long long pe = ((long long)blockIdx.x + P.prefetch_distance) * EPB;
     if (pe + EPB <= P.num_elements) {
-      prefetch_range_l2<Sig::threads>(P.J_q + pe * (dim * sdim * QPE), (long long)EPB * dim * sdim * QPE * 8);
-      prefetch_range_l2<Sig::threads>(P.X_q + pe * (sdim * QPE), (long long)EPB * sdim * QPE * 8);
+      prefetch_range_l2<LAY::threads>(P.J_q + pe * (dim * sdim * QPE), (long long)EPB * dim * sdim * QPE * 8);
+      prefetch_range_l2<LAY::threads>(P.X_q + pe * (sdim * QPE), (long long)EPB * sdim * QPE * 8);
       [&]<int... I>(std::integer_sequence<int, I...>)
       {
-        (prefetch_range_l2<Sig::threads>(P.trial[I].table + pe * LAY::ndof(I), (long long)EPB * LAY::ndof(I) * 4), ...);
+        (prefetch_range_l2<LAY::threads>(P.trial[I].table + pe * LAY::ndof(I), (long long)EPB * LAY::ndof(I) * 4), ...);
       }
       (seq{});
     }
@@ -1105,7 +1131,7 @@ __global__ void __launch_bounds__(Sig::threads, MINB) evaluation_kernel(const __
   {
     constexpr int NGMAX = [] {
       int m = 1;
-      for (int i = 0; i < NT; i++) m = cmax(m, (LAY::gather_size(i) + Sig::threads - 1) / Sig::threads);
+      for (int i = 0; i < NT; i++) m = cmax(m, (LAY::gather_size(i) + LAY::threads - 1) / LAY::threads);
       return m;
     }();
     double gv[NT > 0 ? NT : 1][NGMAX];
@@ -1113,11 +1139,11 @@ __global__ void __launch_bounds__(Sig::threads, MINB) evaluation_kernel(const __
       constexpr int   I    = decltype(idx)::value;
       constexpr int   c    = Sig::trial_c(I);
       constexpr int   nd   = LAY::ndof(I);
-      constexpr int   NG   = (LAY::gather_size(I) + Sig::threads - 1) / Sig::threads;
+      constexpr int   NG   = (LAY::gather_size(I) + LAY::threads - 1) / LAY::threads;
       const FieldArg& f    = P.trial[I];
       SB_UNROLL
       for (int j = 0; j < NG; j++) {
-        const int i = threadIdx.x + j * Sig::threads;
+        const int i = threadIdx.x + j * LAY::threads;
         constexpr int sz = LAY::gather_size(I);
         if (i < sz) {
           const int le   = i / (c * nd);
@@ -1134,10 +1160,10 @@ __global__ void __launch_bounds__(Sig::threads, MINB) evaluation_kernel(const __
     };
     auto store_field = [&](auto idx) {
       constexpr int I  = decltype(idx)::value;
-      constexpr int NG = (LAY::gather_size(I) + Sig::threads - 1) / Sig::threads;
+      constexpr int NG = (LAY::gather_size(I) + LAY::threads - 1) / LAY::threads;
       SB_UNROLL
       for (int j = 0; j < NG; j++) {
-        const int i = threadIdx.x + j * Sig::threads;
+        const int i = threadIdx.x + j * LAY::threads;
         constexpr int off = LAY::gather_off(I), sz = LAY::gather_size(I);
         if (i < sz) gathered[off + i] = gv[I][j];
       }
@@ -1326,8 +1352,10 @@ __global__ void __launch_bounds__(Sig::threads, MINB) evaluation_kernel(const __
     using DT                   = DerivativeTraits<Sig, WRT, QF, State, FAST>;
     constexpr DerivativeLayout LY = DT::layout();
     constexpr int              ck = DT::ck;
-    const long long            tile = blockIdx.x;
-    double* dq = P.dqf + tile * (long long)LY.entries * Sig::threads + threadIdx.x;
+    // derivative tile of this element and this quadrature point's lane in it
+    const long long tile = e_raw / Sig::EPB;
+    const int       lane = int(e_raw - tile * Sig::EPB) * QPE + ql;
+    double*         dq   = P.dqf + tile * (long long)LY.entries * LAY::TILE + lane;
     bool    first = true;
 
     if constexpr (DT::tangent) {
@@ -1337,7 +1365,7 @@ __global__ void __launch_bounds__(Sig::threads, MINB) evaluation_kernel(const __
       tensor<double, ct>      s_p{};
       tensor<double, ct, dim> f_p{};
       auto sink = [&](int a, int k, int b, int l, double v) {
-        if (valid) dq[(long long)(((a * dim + k) * ck + b) * dim + l) * Sig::threads] = v;
+        if (valid) dq[(long long)(((a * dim + k) * ck + b) * dim + l) * LAY::TILE] = v;
       };
       [&]<int... I>(std::integer_sequence<int, I...>)
       {
@@ -1377,14 +1405,14 @@ __global__ void __launch_bounds__(Sig::threads, MINB) evaluation_kernel(const __
         for (int a = 0; a < ct; a++) {
           if constexpr (LY.has[0]) {
             SB_UNROLL
-            for (int b = 0; b < ck; b++) dq[(long long)(LY.offset[0] + a * ck + b) * Sig::threads] = partial(s_out[a], b);
+            for (int b = 0; b < ck; b++) dq[(long long)(LY.offset[0] + a * ck + b) * LAY::TILE] = partial(s_out[a], b);
           }
           if constexpr (LY.has[2]) {
             SB_UNROLL
             for (int k = 0; k < dim; k++) {
               SB_UNROLL
               for (int b = 0; b < ck; b++)
-                dq[(long long)(LY.offset[2] + (a * dim + k) * ck + b) * Sig::threads] = partial(f_out[a][k], b);
+                dq[(long long)(LY.offset[2] + (a * dim + k) * ck + b) * LAY::TILE] = partial(f_out[a][k], b);
             }
           }
         }
@@ -1420,7 +1448,7 @@ __global__ void __launch_bounds__(Sig::threads, MINB) evaluation_kernel(const __
               if constexpr (LY.has[1]) {
                 SB_UNROLL
                 for (int l = 0; l < dim; l++)
-                  dq[(long long)(LY.offset[1] + (a * ck + row) * dim + l) * Sig::threads] =
+                  dq[(long long)(LY.offset[1] + (a * ck + row) * dim + l) * LAY::TILE] =
                       partial(s_out[a], rl * dim + l);
               }
               if constexpr (LY.has[3]) {
@@ -1428,7 +1456,7 @@ __global__ void __launch_bounds__(Sig::threads, MINB) evaluation_kernel(const __
                 for (int k = 0; k < dim; k++) {
                   SB_UNROLL
                   for (int l = 0; l < dim; l++)
-                    dq[(long long)(LY.offset[3] + ((a * dim + k) * ck + row) * dim + l) * Sig::threads] =
+                    dq[(long long)(LY.offset[3] + ((a * dim + k) * ck + row) * dim + l) * LAY::TILE] =
                         partial(f_out[a][k], rl * dim + l);
                 }
               }

@@ -75,16 +75,17 @@ int launch_evaluation_kernel(const EvalParams<Sig::NT>& P_in, const QF& qf, int 
   auto         kernel = &evaluation_kernel<Sig, WRT, QF, State, ROWS, MINB, FAST>;
   const size_t smem   = size_t(eval_smem_doubles<Sig>()) * sizeof(double);
   if (int e = ensure_smem(kernel, smem)) return e;
-  const int grid = (num_elements + Sig::EPB - 1) / Sig::EPB;
+  using LAY      = EvalLayout<Sig>;
+  const int grid = (num_elements + LAY::CE - 1) / LAY::CE;
   static int resident = 0;  // CTAs per SM of this instantiation
   if (resident == 0) {
     int nb = 0;
-    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kernel, Sig::threads, smem) != cudaSuccess) nb = 1;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kernel, LAY::threads, smem) != cudaSuccess) nb = 1;
     resident = nb > 0 ? nb : 1;
   }
   EvalParams<Sig::NT> P = P_in;
   P.prefetch_distance   = use_eval_prefetch() ? resident * sm_count() : 0;
-  kernel<<<grid, Sig::threads, smem, cudaStream_t(stream)>>>(P, qf);
+  kernel<<<grid, LAY::threads, smem, cudaStream_t(stream)>>>(P, qf);
   sb_count_launch();
   return int(cudaGetLastError());
 }
@@ -259,7 +260,7 @@ int launch_element_gradient(const sb_elem_grad_args* a, void* stream)
 template <typename Sig>
 constexpr int default_min_blocks()
 {
-  constexpr int t32 = ((Sig::threads + 31) / 32) * 32;
+  constexpr int t32 = ((EvalLayout<Sig>::threads + 31) / 32) * 32;
   return (512 / t32) > 0 ? (512 / t32) : 1;
 }
 
