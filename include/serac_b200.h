@@ -259,9 +259,11 @@ int sb_functional_add_boundary_integral(sb_functional_t F, sb_integral_t I, cons
 /* operator()(t, args...) (F/functional.hpp:446-513).  inputs: one L-vector per trial space.  *_on_host:
  *   SB_DEVICE (0)      device pointers, work is enqueued on `stream`
  *   SB_HOST_SYNC (1)   host buffers, copied to / from the device inside the call; the result is valid on return
- *   SB_HOST_ASYNC (2)  outputs only: the device -> host copy is enqueued on the Functional's own copy stream and the call
- *                      returns at once, so it overlaps the next call's host -> device copies and kernels; the result (and
- *                      the right to reuse the input buffers) is valid after sb_functional_wait().  Use pinned memory. */
+ *   SB_HOST_ASYNC (2)  host buffers (pinned), copied on the Functional's own upload / download streams: the call returns
+ *                      at once; an input copy overlaps whatever the caller's stream is still running (the direction of
+ *                      the Jacobian action goes up during the evaluation), an output copy overlaps the next call's
+ *                      copies and kernels.  Results -- and the right to modify the input buffers -- are valid after
+ *                      sb_functional_wait(). */
 #define SB_DEVICE 0
 #define SB_HOST_SYNC 1
 #define SB_HOST_ASYNC 2

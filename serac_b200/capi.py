@@ -393,8 +393,9 @@ class Functional:
             ptrs = (C.c_void_p * len(ins))(*[a.ctypes.data for a in ins])
             if out is None:
                 out = np.empty(n)
-            check(lib().sb_functional_evaluate(self.h, float(t), wrt, ptrs, 1, _np_ptr(out), 2 if async_host else 1,
-                                               int(update_state), _stream_ptr()))
+            mode = 2 if async_host else 1
+            check(lib().sb_functional_evaluate(self.h, float(t), wrt, ptrs, mode, _np_ptr(out), mode, int(update_state),
+                                               _stream_ptr()))
         else:
             ptrs = (C.c_void_p * len(inputs))(*[a.data_ptr() for a in inputs])
             if out is None:
@@ -410,8 +411,8 @@ class Functional:
             du = np.ascontiguousarray(du, dtype=np.float64)
             if out is None:
                 out = np.empty(n)
-            check(lib().sb_functional_jvp(self.h, wrt, _np_ptr(du), 1, _np_ptr(out), 2 if async_host else 1,
-                                          _stream_ptr()))
+            mode = 2 if async_host else 1
+            check(lib().sb_functional_jvp(self.h, wrt, _np_ptr(du), mode, _np_ptr(out), mode, _stream_ptr()))
         else:
             if out is None:
                 out = torch.empty(n, dtype=torch.float64, device=du.device)
