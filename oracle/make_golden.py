@@ -197,6 +197,44 @@ MULTIFIELD_FIXTURES = [
 ]
 
 
+def reference_qoi_problem(mesh_spec, kind, p, params, seed=42):
+    """One reference QOI Integral (Functional<double(H1<p,dim>)>, functional_qoi.inl): the per-element totals, the
+    scalar, its directional derivative and its gradient vector (assemble(grad) of a QOI is a vector:
+    functional_qoi.inl:411-455)."""
+    mesh = make_mesh(mesh_spec)
+    dim = mesh.dim
+    space = ref.Space(mesh, p, dim)
+    rng = np.random.default_rng(seed)
+    U = rng.uniform(-1.0, 1.0, space.vsize)
+    dU = rng.uniform(0.0, 1.0, space.vsize)
+    order, ordering, nodes, nodes_info = mesh.nodes()
+    X_q, J_q = mesh.geometric_factors(p + 1)
+    I = ref.Integral(f"{kind}_{dim}d_p{p}", mesh, params)
+    out = dict(kind=kind, geom=mesh.geom, dim=dim, p=p, ne=mesh.ne, params=np.asarray(params, dtype=np.float64),
+               native_dofs=space.native_dofs(), dof_info=space.dof_info(), num_nodes=space.num_nodes,
+               mesh_order=order, mesh_ordering=ordering, mesh_nodes=nodes, mesh_dof_info=nodes_info,
+               mesh_num_nodes=len(nodes) // dim, U=U, dU=dU, X_q=X_q, J_q=J_q)
+    ins = [space.gather(U)]
+    q_E = I.mult(0.0, ins, mesh.ne)  # one total per element (QoIElementRestriction: ESize = number of elements)
+    out["q_E"] = q_E
+    out["value"] = float(np.sum(q_E))
+    I.mult(0.0, ins, mesh.ne, wrt=0)
+    out["dq_E"] = I.jvp(0, space.gather(dU), mesh.ne)
+    out["dvalue"] = float(np.sum(out["dq_E"]))
+    npe = space.dof_info().shape[1]
+    K_e = I.element_gradient(0, mesh.ne, npe * dim, 1)  # [element][trial vdof][1]
+    out["K_e"] = K_e
+    out["gradient"] = space.scatter_add(K_e.reshape(mesh.ne, dim, npe), np.zeros(space.vsize))
+    return out
+
+
+QOI_FIXTURES = [
+    ("qoi_quadratic_hex_p2_cart", dict(mesh_spec=("cart3d", 2, 2, 1, 0.02), kind="qoi_quadratic", p=2, params=[0.7, 1.3])),
+    ("qoi_quadratic_tet_p1_beam", dict(mesh_spec=("file", "beam-tet.mesh", 0), kind="qoi_quadratic", p=1,
+                                       params=[0.7, 1.3])),
+]
+
+
 def reference_boundary_problem(mesh_spec, kind, p, params, seed=42, shape_amp=0.0, u_amp=0.01):
     """One reference BOUNDARY Integral (MakeBoundaryIntegral, integral.hpp:322-350) on EntireBoundary(mesh) with the
     SolidMechanics signature H1<p,dim>(shape H1<1,dim>, u, a): inputs (native face dofs of every space, mesh nodes) and
@@ -358,6 +396,14 @@ def main():
         print(f"{name}: ne={data['ne']} |r|={np.linalg.norm(data['r']):.3e} " +
               " ".join(f"|dr{i}|={np.linalg.norm(data[f'dr{i}']):.3e}" for i in range(4)) +
               f" -> {os.path.getsize(path) / 1024:.0f} KiB")
+    for name, kw in QOI_FIXTURES:
+        if only and name not in only:
+            continue
+        data = reference_qoi_problem(**kw)
+        path = os.path.join(GOLDEN_DIR, name + ".npz")
+        np.savez_compressed(path, **data)
+        print(f"{name}: ne={data['ne']} value={data['value']:.12e} dvalue={data['dvalue']:.6e} "
+              f"|gradient|={np.linalg.norm(data['gradient']):.6e} -> {os.path.getsize(path) / 1024:.0f} KiB")
     for name, kw in BOUNDARY_FIXTURES:
         if only and name not in only:
             continue

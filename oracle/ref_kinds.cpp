@@ -170,6 +170,29 @@ ref::Registrar r4("thermal_linear_conductor_" TAG, [](mfem::Mesh& mesh, const do
   return h;
 });
 
+// ---- quantity of interest: Functional<double(H1<p,dim>)> (functional_qoi.inl:160-190 builds signature QOI(trials...)) ----
+struct QuadraticQoi {
+  double a, b;
+  template <typename X, typename U>
+  auto operator()(double, X x, U u) const
+  {
+    using std::sin;
+    auto [uv, du] = u;
+    auto X0       = get<0>(x);
+    return a * (1.0 + X0[0]) * dot(uv, uv) + (0.5 * b) * inner(du, du) + sin(X0[1]);
+  }
+};
+
+ref::Registrar rq("qoi_quadratic_" TAG, [](mfem::Mesh& mesh, const double* q, int n) {
+  SLIC_ERROR_IF(n != 2, "params: a b");
+  ref::IntegralHolder h;
+  using sig    = QOI(H1<p, dim>);
+  Domain d     = ref::domain_for(mesh);
+  h.integral   = std::make_unique<Integral>(MakeDomainIntegral<sig, p + 1, dim>(d, QuadraticQoi{q[0], q[1]}, NoQData, {0}));
+  h.num_trials = 1;
+  return h;
+});
+
 #if REF_DIM == 3
 // ---- thermomechanics (BASELINE.json configs[3]) ---------------------------------------------------------------------
 // functor shells restating Thermomechanics::ThermalMaterialInterface / MechanicalMaterialInterface

@@ -626,6 +626,20 @@ constexpr int eval_cta_elements()
   return Sig::EPB;
 }
 
+/// adapts the q-function of a quantity of interest (`Functional<double(trials...)>`, F/functional_qoi.inl: returns the
+/// scalar integrand alone) to the tuple{source, flux} convention.  The "test space" is QOI: one node per element whose
+/// shape function is 1 (F/detail/qoi.inl), i.e. an order-0 space -- integrate() then is the weighted sum over the
+/// element's quadrature points, the E-vector holds one total per element and the scatter adds them up.
+template <typename QF>
+struct QoiIntegrand {
+  QF qf;
+  template <typename... Args>
+  SERAC_HOST_DEVICE auto operator()(double t, const Args&... args) const
+  {
+    return serac::tuple{qf(t, args...), zero{}};
+  }
+};
+
 /// shared-memory plan of the evaluation kernel (doubles):
 ///   [tables: (NT + 1) x 2 x MAX_Q^2][gathered dofs of every trial field: EPB x c x ndof each][work: EPB x W]
 /// The interpolation work areas of the trial fields are disjoint (all fields advance stage by stage together, two

@@ -219,7 +219,7 @@ SB_HD int num_nodes(Geometry g, int p)
     case Geometry::SEGMENT:
       return p + 1;
     case Geometry::TRIANGLE:
-      return (p + 1) * (p + 2) / 2;
+      return (p + 1) * (p + 2) / 2;  // p = 0 -> 1: the per-element total of a quantity of interest
     case Geometry::SQUARE:
       return (p + 1) * (p + 1);
     case Geometry::TETRAHEDRON:
@@ -421,7 +421,15 @@ inline SimplexTable make_simplex_table(Geometry g, int p, int Q)
   t.dim = dimension_of(g);
   double xi[MAX_SIMPLEX_QPTS * 3], w[MAX_SIMPLEX_QPTS];
   t.nq   = simplex_quadrature(g, Q, xi, w);
-  t.ndof = simplex_shape_functions(g, p, t.nq, xi, t.tab);
+  if (p == 0) {  // quantity of interest: one "shape function" = 1 (F/detail/qoi.inl:24)
+    t.ndof = 1;
+    for (int i = 0; i < t.nq; i++) {
+      t.tab[i * (1 + t.dim)] = 1.0;
+      for (int d = 0; d < t.dim; d++) t.tab[i * (1 + t.dim) + 1 + d] = 0.0;
+    }
+  } else {
+    t.ndof = simplex_shape_functions(g, p, t.nq, xi, t.tab);
+  }
   for (int i = 0; i < t.nq; i++) t.tab[t.nq * t.ndof * (1 + t.dim) + i] = w[i];
   return t;
 }

@@ -404,10 +404,15 @@ class Functional<test(trials...)> {
   static const sb_kernel_table* table_for()
   {
     using Sig = b200::Signature<g, Q, test, trial_at<args>...>;
-    // FAST = false: arbitrary user functors are differentiated with dual numbers, the reference's scheme; functors that
-    // provide their own tangent (physics_functors.hpp) opt in through provides_flux_tangent
-    static const sb_kernel_table table = b200::make_kernel_table<Sig, Integrand, StateType>();
-    return &table;
+    // arbitrary user functors are differentiated with dual numbers, the reference's scheme; functors that provide their
+    // own tangent (physics_functors.hpp) opt in through provides_flux_tangent
+    if constexpr (test::family == Family::QOI) {  // quantity of interest: the q-function returns the scalar integrand
+      static const sb_kernel_table table = b200::make_qoi_kernel_table<Sig, Integrand, StateType>();
+      return &table;
+    } else {
+      static const sb_kernel_table table = b200::make_kernel_table<Sig, Integrand, StateType>();
+      return &table;
+    }
   }
 
   template <Geometry fg, typename Integrand, int... args>
@@ -491,5 +496,64 @@ class Functional<test(trials...)> {
   std::vector<Gradient>                                    grad_;
   bool                                                     update_qdata_ = false;
 };
+
+/// Quantity of interest, `Functional<double(trials...)>` (functional_qoi.inl:1-470): the same machinery with the QOI
+/// "test space" (one total per element, summed by the scatter).  operator() returns the scalar (or tuple{scalar,
+/// Gradient&}); Gradient::operator()(dx) is the directional derivative (a length-1 Vector), assemble(Gradient&) the
+/// gradient as a 1 x n CsrMatrix and gradient_vector(Gradient&) as a dense vector (the reference returns a
+/// HypreParVector, functional_qoi.inl:411-455).
+template <typename... trials>
+class Functional<double(trials...)> {
+  using Impl                            = Functional<QOI(trials...)>;
+  static constexpr int num_trial_spaces = int(sizeof...(trials));
+
+ public:
+  using Gradient = typename Impl::Gradient;
+
+  explicit Functional(std::array<const FiniteElementSpace*, num_trial_spaces> trial_fes)
+  {
+    const FiniteElementSpace& first = *trial_fes[0];
+    qoi_space_ = FiniteElementSpace{first.geometry, 0, 1, Ordering::byVDIM, 1, first.num_elements,
+                                    std::vector<int>(size_t(first.num_elements), 0)};
+    qoi_space_.num_boundary_faces = first.num_boundary_faces;
+    qoi_space_.native_boundary_face_dofs.assign(size_t(first.num_boundary_faces), 0);
+    impl_ = std::make_unique<Impl>(&qoi_space_, trial_fes);
+  }
+
+  template <int dim, int... args, typename Integrand, typename StateType = Nothing>
+  void AddDomainIntegral(Dimension<dim> d, DependsOn<args...> a, const Integrand& integrand, Domain& domain,
+                         std::shared_ptr<QuadratureData<StateType>> qdata = NoQData)
+  {
+    impl_->AddDomainIntegral(d, a, integrand, domain, qdata);
+  }
+
+  template <typename... T>
+  auto operator()(double t, const T&... args)
+  {
+    constexpr bool differentiated = (std::is_same_v<T, differentiate_wrt_this> || ...);
+    if constexpr (differentiated) {
+      auto r = (*impl_)(t, args...);
+      return std::tuple<double, Gradient&>(std::get<0>(r).to_host()[0], std::get<1>(r));
+    } else {
+      return (*impl_)(t, args...).to_host()[0];
+    }
+  }
+
+  void updateQdata(bool update_flag) { impl_->updateQdata(update_flag); }
+
+ private:
+  FiniteElementSpace    qoi_space_;
+  std::unique_ptr<Impl> impl_;
+};
+
+/// dense gradient of a quantity of interest from its 1 x n matrix
+template <typename G>
+std::vector<double> gradient_vector(G& g)
+{
+  auto                K = assemble(g);
+  std::vector<double> v(size_t(K->num_cols), 0.0);
+  for (size_t k = 0; k < K->col_ind.size(); k++) v[size_t(K->col_ind[k])] = K->values[k];
+  return v;
+}
 
 }  // namespace serac

@@ -324,5 +324,15 @@ sb_kernel_table make_boundary_kernel_table()
   return make_kernel_table<Sig, BoundaryIntegrand<QF>, Nothing, ROWS_REQ, MINB, false>();
 }
 
+/// kernel table of a quantity of interest: Sig's test space is serac::QOI, QF returns the scalar integrand.  The functor
+/// blob handed to sb_integral_create is the QF itself.  State as for make_kernel_table.
+template <typename Sig, typename QF, typename State = Nothing, int ROWS_REQ = 1, int MINB = 0>
+sb_kernel_table make_qoi_kernel_table()
+{
+  static_assert(Sig::test_space::family == Family::QOI, "make_qoi_kernel_table needs a Signature whose test space is QOI");
+  static_assert(sizeof(QoiIntegrand<QF>) == sizeof(QF), "adapter must not change the functor layout");
+  return make_kernel_table<Sig, QoiIntegrand<QF>, State, ROWS_REQ, MINB, false>();
+}
+
 }  // namespace b200
 }  // namespace serac

@@ -15,7 +15,7 @@ inline const double* simplex_table_dev(Geometry g, int p, int Q)
 {
   static std::mutex    mtx;
   static const double* cache[2][4][MAX_Q + 1] = {};
-  if (!is_simplex(g) || p < 1 || p > 3 || Q < 1 || Q > MAX_Q) return nullptr;
+  if (!is_simplex(g) || p < 0 || p > 3 || Q < 1 || Q > MAX_Q) return nullptr;
   const int                   gi = (g == Geometry::TRIANGLE) ? 0 : 1;
   std::lock_guard<std::mutex> lock(mtx);
   if (!cache[gi][p][Q]) {

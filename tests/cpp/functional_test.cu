@@ -9,6 +9,7 @@
 //     pressure  same signature, ONE boundary integral: follower pressure (hex mesh, quadrilateral faces)
 //     user      H1<2>(H1<2>) with a q-function defined in THIS file: checked here against finite differences and the
 //               assembled matrix (check_gradient.hpp:16-90)
+//     qoi       Functional<double(H1<2,3>)> with a q-function defined in this file: value, directional derivative, gradient
 // Directory layout: <name>.bin raw little-endian arrays (int32 / float64), meta.txt "key value" lines.
 #include <cmath>
 #include <cstdio>
@@ -245,6 +246,35 @@ int run_user(const std::map<std::string, double>& meta)
   return ok ? 0 : 1;
 }
 
+/// quantity of interest defined in this file: the integrand of the library's `qoi_quadratic_*` (and of the oracle kind)
+struct QuadraticQoi {
+  double a, b;
+  template <typename X, typename U>
+  SERAC_HOST_DEVICE auto operator()(double, X x, U u) const
+  {
+    auto uv = get<0>(u);
+    auto du = get<1>(u);
+    auto X0 = get<0>(x);
+    return a * (1.0 + X0[0]) * dot(uv, uv) + (0.5 * b) * inner(du, du) + ::sin(X0[1]);
+  }
+};
+
+int run_qoi(const std::map<std::string, double>& meta)
+{
+  Problem P = load_problem(meta, false);
+  auto    q = read_bin<double>("params");
+  Functional<double(H1<p, dim>)> qoi({&P.space});
+  Domain whole = EntireDomain(P.mesh);
+  qoi.AddDomainIntegral(Dimension<dim>{}, DependsOn<0>{}, QuadraticQoi{q[0], q[1]}, whole);
+  Vector U(read_bin<double>("U")), dU(read_bin<double>("dU"));
+  const double plain = qoi(0.0, U);
+  auto [value, dqdu] = qoi(0.0, differentiate_wrt(U));
+  write_bin("value", std::vector<double>{plain, value});
+  write_bin("dvalue", dqdu(dU).to_host());
+  write_bin("gradient", gradient_vector(dqdu));
+  return 0;
+}
+
 int main(int argc, char** argv)
 {
   if (argc != 3) {
@@ -263,6 +293,7 @@ int main(int argc, char** argv)
   if (which == "j2") rc = run_j2(meta);
   if (which == "pressure") rc = run_pressure(meta);
   if (which == "user") rc = run_user(meta);
+  if (which == "qoi") rc = run_qoi(meta);
   std::printf("launches: %lld\n", sb_launch_count());
   return rc;
 }

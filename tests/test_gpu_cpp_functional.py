@@ -111,3 +111,21 @@ def test_user_defined_qfunction(tmp_path, cuda):
     export(prob, d)
     stdout = run("user", d)
     assert "PASS" in stdout
+
+
+def test_qoi_functional(tmp_path, cuda):
+    """Functional<double(H1<2,3>)> (functional_qoi.inl) with a q-function defined in the C++ driver"""
+    prob = load_golden("qoi_quadratic_hex_p2_cart")
+    d = str(tmp_path)
+    fake = dict(prob)
+    # the QOI fixture has one trial field; the driver's loader also wants the shape space and the other inputs
+    lex = fo.lexicographic_permutation(int(prob["geom"]), int(prob["mesh_order"]))
+    native = np.empty(prob["mesh_dof_info"].shape, dtype=np.int32)
+    native[:, lex] = (prob["mesh_dof_info"] & MASK).astype(np.int32)
+    fake.update(shape_native_dofs=native, shape_num_nodes=prob["mesh_num_nodes"], A=prob["U"], S=np.zeros(1))
+    export(fake, d)
+    run("qoi", d)
+    v = out(d, "value")
+    assert abs(v[0] - prob["value"]) < TOL * abs(prob["value"]) and v[0] == v[1]
+    assert abs(out(d, "dvalue")[0] - prob["dvalue"]) < TOL * abs(prob["dvalue"])
+    assert rel_l2(out(d, "gradient"), prob["gradient"]) < TOL
