@@ -32,9 +32,9 @@ METRIC = "GDOF/s Functional residual + Jacobian action (p=2 hex)"
 CONFIG_A = os.path.join(ROOT, "tests", "golden", "config_a_beam_hex_r4_p2.npz")
 NEOHOOKEAN = [1.0, 100.0, 50.0, 1.0]  # density, K, G, geometric nonlinearity on (BASELINE.md §2 probe values)
 # dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed `ncu --set full` capture of this command
-# (profiles/r1c_summary.md, raw extract profiles/r1c_ncu_full_raw_extract.txt)
-JVP_NCU_TRAFFIC_BYTES = 604.8e6   # 583.8 MB read + 21.0 MB written
-EVAL_NCU_TRAFFIC_BYTES = 640.0e6  # 103.7 MB read + 536.2 MB written (rest of the 573 MB store still in L2)
+# (profiles/r1c_summary.md, raw extract profiles/r1e_ncu_full_raw_extract.txt)
+JVP_NCU_TRAFFIC_BYTES = 604.8e6   # 583.7 MB read + 21.1 MB written
+EVAL_NCU_TRAFFIC_BYTES = 638.8e6  # 103.3 MB read + 535.5 MB written (rest of the 573 MB store still in L2)
 
 
 # ---------------------------------------------------------------------------------------------------------------------

@@ -338,8 +338,11 @@ struct JvpStreamConfig {
   static constexpr size_t smem_bytes   = size_t(scratch_doubles + tile_doubles) * 8 + 16;
 };
 
+#ifndef SB_JVP_MINB
+#define SB_JVP_MINB 2
+#endif
 template <int dim, int q, int nk, int ck, int nt, int ct, int MASK, int EPB_ = 0>
-__global__ void __launch_bounds__(JvpStreamConfig<dim, q, nk, ck, nt, ct, MASK, EPB_>::threads, 2)
+__global__ void __launch_bounds__(JvpStreamConfig<dim, q, nk, ck, nt, ct, MASK, EPB_>::threads, SB_JVP_MINB)
     jvp_stream_kernel(const __grid_constant__ JvpParams P, const int num_tiles)
 {
   using C                       = JvpStreamConfig<dim, q, nk, ck, nt, ct, MASK, EPB_>;
