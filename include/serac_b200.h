@@ -126,6 +126,9 @@ typedef struct {
   void*         qdata_dev;
   int           update_state;
   double        t;
+  int           first_element;  /* evaluate only positions [first_element, num_elements) of the domain's element list
+                                   (0 = from the start): lets a caller evaluate the elements that need no halo data while
+                                   the exchange is in flight, the rest afterwards (sb_functional_evaluate_begin / _end) */
   int           r_E_node_major; /* 0: r_E is [element][comp][node] (the reference's E-vector, F/element_restriction.cpp:443);
                                    1: [element][node][comp] -- internal to sb_functional_*: the components of a node are
                                    contiguous, so the deterministic scatter reads whole 32-byte sectors */
@@ -268,6 +271,13 @@ int sb_functional_add_boundary_integral(sb_functional_t F, sb_integral_t I, cons
 #define SB_HOST_SYNC 1
 #define SB_HOST_ASYNC 2
 int sb_functional_wait(sb_functional_t F);
+/* operator() in two halves, device buffers only: _begin evaluates, for every domain integral that covers the whole mesh,
+ * the elements [0, split_element) -- with partitions whose halo-dependent elements are numbered last these need no data
+ * from other ranks, so the caller issues the halo puts, calls _begin, waits for / unpacks the halo, and calls _end, which
+ * evaluates the remaining elements (and every other integral) and scatters.  Same result as sb_functional_evaluate. */
+int sb_functional_evaluate_begin(sb_functional_t F, double t, int wrt, const double* const* inputs_dev, int update_state,
+                                 int64_t split_element, void* stream);
+int sb_functional_evaluate_end(sb_functional_t F, double* output_dev, void* stream);
 int sb_functional_evaluate(sb_functional_t F, double t, int wrt, const double* const* inputs, int inputs_on_host,
                            double* output, int output_on_host, int update_state, void* stream);
 /* Gradient::Mult (F/functional.hpp:406-432,556-559) for the derivative stored by the last evaluate(wrt) */
@@ -335,6 +345,9 @@ int sb_halo_Pt_peer_finish_inplace(sb_halo_t H, double* TL_dev, void* stream);
 /* P in place for up to 4 fields (one halo object each) with ONE put launch and ONE wait + unpack launch: what
  * Functional::operator() needs before its gathers (F/functional.hpp:460-470 applies P to every argument) */
 int sb_halo_P_peer_inplace_multi(int num_fields, const sb_halo_t* H, double* const* TL_dev, void* stream);
+/* its two halves: launch kernels that need no halo data (sb_functional_evaluate_begin) in between */
+int sb_halo_P_peer_put_multi(int num_fields, const sb_halo_t* H, double* const* TL_dev, void* stream);
+int sb_halo_P_peer_finish_inplace_multi(int num_fields, const sb_halo_t* H, double* const* TL_dev, void* stream);
 int sb_halo_peer_status(sb_halo_t H, int* status_host);
 
 #ifdef __cplusplus

@@ -100,6 +100,10 @@ SIGNATURES = {
     "sb_halo_owned_first": (_i, [_vp]),
     "sb_halo_P_peer_finish_inplace": (_i, [_vp, _vp, _vp]),
     "sb_halo_P_peer_inplace_multi": (_i, [_i, _vp, _vp, _vp]),
+    "sb_halo_P_peer_put_multi": (_i, [_i, _vp, _vp, _vp]),
+    "sb_halo_P_peer_finish_inplace_multi": (_i, [_i, _vp, _vp, _vp]),
+    "sb_functional_evaluate_begin": (_i, [_vp, _d, _i, _vp, _i, _i64, _vp]),
+    "sb_functional_evaluate_end": (_i, [_vp, _vp, _vp]),
     "sb_halo_Pt_peer_finish_inplace": (_i, [_vp, _vp, _vp]),
     "sb_halo_peer_status": (_i, [_vp, _vp]),
     "sb_halo_P_pack": (_i, [_vp, _vp, _vp]),
@@ -402,6 +406,21 @@ class Functional:
                 out = torch.empty(n, dtype=torch.float64, device=inputs[0].device)
             check(lib().sb_functional_evaluate(self.h, float(t), wrt, ptrs, 0, _dev_ptr(out), 0, int(update_state),
                                                _stream_ptr()))
+        return out
+
+    def evaluate_begin(self, t, inputs, wrt=NO_DIFFERENTIATION, update_state=False, split_element=0):
+        """first half of __call__ (device tensors): the elements [0, split_element) of the whole-mesh domain integral"""
+        ptrs = (C.c_void_p * len(inputs))(*[a.data_ptr() for a in inputs])
+        self._pending_inputs = list(inputs)  # keep alive until evaluate_end
+        check(lib().sb_functional_evaluate_begin(self.h, float(t), wrt, ptrs, int(update_state), int(split_element),
+                                                 _stream_ptr()))
+
+    def evaluate_end(self, out=None):
+        import torch
+        if out is None:
+            out = torch.empty(self.test.LSize(), dtype=torch.float64, device=self._pending_inputs[0].device)
+        check(lib().sb_functional_evaluate_end(self.h, _dev_ptr(out), _stream_ptr()))
+        self._pending_inputs = None
         return out
 
     def GradientMult(self, wrt, du, out=None, async_host=False):

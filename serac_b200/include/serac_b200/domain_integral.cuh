@@ -64,7 +64,8 @@ struct EvalParams {
   const double* X_q;           ///< [e][i][q]       (geometric_factors.cpp:27,48)
   const double* J_q;           ///< [e][j][i][q] = dX_i/dxi_j
   const int*    elements;      ///< domain element ids (index into the restriction tables / E-vector)
-  int           num_elements;  ///< how many entries of `elements`
+  int           num_elements;  ///< END of the element range of this launch (exclusive): positions in the domain's list
+  int           first_element; ///< start of the range (0 for a whole-domain launch); the grid covers [first, num_elements)
   double*       r_E;           ///< [element][comp][node] E-vector block of the test space
   double*       dqf;           ///< stored q-function derivatives, [tile][entry][lane]
   void*         qdata;         ///< [e][q] AoS of the state type (quadrature_data.hpp:127-131)
@@ -1110,7 +1111,7 @@ __global__ void __launch_bounds__(EvalLayout<Sig>::threads, MINB) evaluation_ker
   const int qy = (ql / q) % q;
   const int qz = (dim == 3) ? ql / (q * q) : 0;
 
-  const int  e_raw = blockIdx.x * EPB + el;
+  const int  e_raw = P.first_element + blockIdx.x * EPB + el;
   const bool valid = e_raw < P.num_elements;
   const int  e     = valid ? e_raw : P.num_elements - 1;
   const int  elem  = P.elements ? P.elements[e] : e;
@@ -1118,7 +1119,7 @@ __global__ void __launch_bounds__(EvalLayout<Sig>::threads, MINB) evaluation_ker
   constexpr int sdim = Sig::sdim;
   // L2 prefetch of a later tile's streaming inputs (identity element list: the tile's rows are contiguous)
   if (P.prefetch_distance > 0 && !P.elements) {
-    const long long pe = ((long long)blockIdx.x + P.prefetch_distance) * EPB;
+    const long long pe = P.first_element + ((long long)blockIdx.x + P.prefetch_distance) * EPB;
     if (pe + EPB <= P.num_elements) {
       prefetch_range_l2<LAY::threads>(P.J_q + pe * (dim * sdim * QPE), (long long)EPB * dim * sdim * QPE * 8);
       prefetch_range_l2<LAY::threads>(P.X_q + pe * (sdim * QPE), (long long)EPB * sdim * QPE * 8);
@@ -1164,7 +1165,7 @@ __global__ void __launch_bounds__(EvalLayout<Sig>::threads, MINB) evaluation_ker
           const int rem  = i - le * (c * nd);
           const int a    = rem / nd;
           const int node = rem - a * nd;
-          int       ee   = blockIdx.x * EPB + le;
+          int       ee   = P.first_element + blockIdx.x * EPB + le;
           if (ee >= P.num_elements) ee = P.num_elements - 1;
           const int       ge  = P.elements ? P.elements[ee] : ee;
           const long long idx = (long long)f.table[(long long)ge * nd + node];

@@ -115,14 +115,15 @@ int launch_evaluate(const sb_eval_args* a, const void* qf_blob, void* stream)
   P.X_q          = a->X_q_dev;
   P.J_q          = a->J_q_dev;
   P.elements     = a->elements_dev;
-  P.num_elements = a->num_elements;
+  P.num_elements  = a->num_elements;
+  P.first_element = a->first_element;
   P.r_E          = a->r_E_dev;
   P.node_major   = a->r_E_node_major;
   P.dqf          = a->dqf_dev;
   P.qdata        = a->qdata_dev;
   P.update_state = a->update_state;
   P.t            = a->t;
-  if (a->num_elements <= 0) return 0;
+  if (a->num_elements - a->first_element <= 0) return 0;
   alignas(16) unsigned char qf_storage[sizeof(QF)];
   std::memcpy(qf_storage, qf_blob, sizeof(QF));
   const QF& qf = *reinterpret_cast<const QF*>(qf_storage);
@@ -132,14 +133,14 @@ int launch_evaluate(const sb_eval_args* a, const void* qf_blob, void* stream)
     {
       (((qf.variant_index() == V)
             ? void(err = launch_evaluation_kernel<Sig, WRT, typename QF::template variant<V>, State, ROWS, MINB, FAST>(
-                       P, qf.template as_variant<V>(), a->num_elements, stream))
+                       P, qf.template as_variant<V>(), a->num_elements - a->first_element, stream))
             : void()),
        ...);
     };
     dispatch(std::make_integer_sequence<int, qf_variants<QF>::n>{});
     return err;
   } else {
-    return launch_evaluation_kernel<Sig, WRT, QF, State, ROWS, MINB, FAST>(P, qf, a->num_elements, stream);
+    return launch_evaluation_kernel<Sig, WRT, QF, State, ROWS, MINB, FAST>(P, qf, a->num_elements - a->first_element, stream);
   }
 }
 

@@ -213,12 +213,16 @@ class ParFunctional:
         residual's P^T runs on a side stream next to the following kernels; join() makes the calling stream wait for
         everything the side stream still owes."""
 
-    def __init__(self, functional, trial_halos, test_halo, du_halos=None, out_halo=None, inplace=False):
+    def __init__(self, functional, trial_halos, test_halo, du_halos=None, out_halo=None, inplace=False,
+                 independent_elements=0):
         """inplace: the partitions are numbered owned-first and every vector handed in is an L-sized buffer whose first
         tsize entries are the T-vector; results are returned as views of the Functional's L-vectors.  P / P^T then touch
         only the shared entries (no full-vector copies)."""
         self.F, self.trial_halos, self.test_halo = functional, list(trial_halos), test_halo
         self.du_halos, self.out_halo = dict(du_halos or {}), out_halo
+        # elements [0, independent_elements) of the (single, whole-mesh) domain integral touch no node owned elsewhere
+        # (Partition.halo_independent_first): they are evaluated while the input exchange is in flight
+        self.independent_elements = int(independent_elements)
         self.inplace = bool(inplace)
         if self.inplace:
             hs = list(trial_halos) + [test_halo] + list(self.du_halos.values()) + ([out_halo] if out_halo else [])
@@ -257,8 +261,17 @@ class ParFunctional:
             if self._split and len(self.trial_halos) <= 4:  # one put launch + one wait/unpack launch for every input
                 hs = (C.c_void_p * len(self.trial_halos))(*[h.h for h in self.trial_halos])
                 vs = (C.c_void_p * len(T_inputs))(*[TL.data_ptr() for TL in T_inputs])
-                capi.check(capi.lib().sb_halo_P_peer_inplace_multi(len(self.trial_halos), hs, vs, capi._stream_ptr()))
+                n, lib = len(self.trial_halos), capi.lib()
                 self._L = list(T_inputs)
+                if self.independent_elements > 0:
+                    # puts -> elements that need no halo data -> wait + unpack -> the halo-dependent elements + scatter
+                    capi.check(lib.sb_halo_P_peer_put_multi(n, hs, vs, capi._stream_ptr()))
+                    self.F.evaluate_begin(t, self._L, wrt=wrt, update_state=update_state,
+                                          split_element=self.independent_elements)
+                    capi.check(lib.sb_halo_P_peer_finish_inplace_multi(n, hs, vs, capi._stream_ptr()))
+                    self._rL = self.F.evaluate_end(out=self._rL)
+                    return self._finish_output(out)
+                capi.check(lib.sb_halo_P_peer_inplace_multi(n, hs, vs, capi._stream_ptr()))
             else:
                 for h, TL in zip(self.trial_halos, T_inputs):
                     h.P_put(TL)
@@ -273,6 +286,11 @@ class ParFunctional:
             for i, (h, T) in enumerate(zip(self.trial_halos, T_inputs)):
                 self._L[i] = h.P(T, self._L[i])
         self._rL = self.F(t, self._L, wrt=wrt, out=self._rL, update_state=update_state)
+        return self._finish_output(out)
+
+    def _finish_output(self, out):
+        """P^T of the residual L-vector (on the side stream when an out_halo was given)"""
+        torch = capi_torch()
         if self.out_halo is not None:
             side, main = self._side_stream(), torch.cuda.current_stream()
             side.wait_stream(main)

@@ -124,14 +124,27 @@ class Partition:
         px, py, _ = self.ranks
         return (c[2] * py + c[1]) * px + c[0]
 
-    def element_table(self, p=None):
+    def element_table(self, p=None, element_order=None):
+        """element_order: permutation of the local elements (see halo_independent_first)"""
         p = self.p if p is None else p
         nb = tuple((p * b[0], p * b[1]) for b in self.box)
         tab = self.mesh.element_table(p, self.box, nb)
         if self.new_of_lex is not None:
             assert p == self.p, "an owned-first partition numbers the nodes of its own order only"
             tab = self.new_of_lex[tab.astype(np.int64)].astype(np.uint64)
+        if element_order is not None:
+            tab = tab[np.asarray(element_order)]
         return tab
+
+    def halo_independent_first(self):
+        """-> (element_order, n_independent): a permutation of the local elements that puts first the elements all of
+        whose nodes this rank owns -- they can be evaluated before P has delivered the values owned elsewhere -- and the
+        halo-dependent ones last.  Use the permutation of the highest-order space for every space of the mesh (a vertex
+        owned elsewhere is also a node of the higher-order space, so its mask contains the lower-order ones)."""
+        tab = self.element_table().astype(np.int64)
+        dependent = (self.owner[tab] != self.rank).any(axis=1)
+        order = np.concatenate([np.nonzero(~dependent)[0], np.nonzero(dependent)[0]])
+        return order, int((~dependent).sum())
 
     def vertex_coordinates(self):
         xyz = self.mesh.vertex_coordinates(tuple((b[0], b[1]) for b in self.box))

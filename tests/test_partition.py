@@ -47,6 +47,35 @@ def test_owned_first_numbering(ranks, p):
         assert np.array_equal(xa[np.argsort(a.global_node_ids())], xb[np.argsort(b.global_node_ids())])
 
 
+@pytest.mark.parametrize("ranks", [(2, 1, 1), (2, 2, 2)])
+def test_halo_independent_elements_first(ranks):
+    """the first n_independent elements of the reordered table touch only nodes this rank owns, the rest at least one
+    node owned elsewhere; the permutation carries over to the lower-order space of the same mesh"""
+    mesh = StructuredHexMesh(5, 4, 3)
+    world = int(np.prod(ranks))
+    for r in range(world):
+        part = Partition(mesh, ranks, r, 2, 3, owned_first=True)
+        part1 = Partition(mesh, ranks, r, 1, 3, owned_first=True)
+        order, n_ind = part.halo_independent_first()
+        assert sorted(order.tolist()) == list(range(part.num_elements))
+        tab = part.element_table(element_order=order).astype(np.int64)
+        owned = part.owner[tab] == r
+        assert owned[:n_ind].all() and (~owned[n_ind:]).any(axis=1).all()
+        tab1 = part1.element_table(element_order=order).astype(np.int64)
+        assert (part1.owner[tab1[:n_ind]] == r).all()
+        # same elements in the same order in both spaces: the vertices of an element are among its p = 2 nodes
+        g2, g1 = part.global_node_ids()[tab], part1.global_node_ids()[tab1]
+        G2, G1 = mesh.node_grid(2), mesh.node_grid(1)
+        corner2 = g2[:, 0]
+        corner1 = g1[:, 0]
+        i2, j2, k2 = corner2 % G2[0], (corner2 // G2[0]) % G2[1], corner2 // (G2[0] * G2[1])
+        i1, j1, k1 = corner1 % G1[0], (corner1 // G1[0]) % G1[1], corner1 // (G1[0] * G1[1])
+        assert np.array_equal(i2, 2 * i1) and np.array_equal(j2, 2 * j1) and np.array_equal(k2, 2 * k1)
+    if world > 1:
+        assert Partition(mesh, ranks, 0, 2, 3, owned_first=True).halo_independent_first()[1] == \
+            Partition(mesh, ranks, 0, 2, 3, owned_first=True).num_elements  # the lowest rank owns all its nodes
+
+
 @pytest.mark.parametrize("owned_first", [False, True])
 @pytest.mark.parametrize("ranks", [(2, 1, 1), (2, 2, 1), (2, 2, 2), (3, 1, 2)])
 @pytest.mark.parametrize("p", [1, 2])
