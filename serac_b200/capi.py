@@ -100,6 +100,7 @@ SIGNATURES = {
     "sb_halo_owned_first": (_i, [_vp]),
     "sb_halo_P_peer_finish_inplace": (_i, [_vp, _vp, _vp]),
     "sb_halo_P_peer_inplace_multi": (_i, [_i, _vp, _vp, _vp]),
+    "sb_halo_Pt_peer_inplace": (_i, [_vp, _vp, _vp]),
     "sb_halo_P_peer_put_multi": (_i, [_i, _vp, _vp, _vp]),
     "sb_halo_P_peer_finish_inplace_multi": (_i, [_i, _vp, _vp, _vp]),
     "sb_functional_evaluate_begin": (_i, [_vp, _d, _i, _vp, _i, _i64, _vp]),

@@ -140,14 +140,15 @@ class HaloExchange:
         return TL
 
     def P_inplace(self, TL):
-        """fill the entries of TL owned by other ranks from their owners; the owned prefix is the T-vector, untouched"""
-        self.P_put(TL)
-        return self.P_finish_inplace(TL)
+        """fill the entries of TL owned by other ranks from their owners; the owned prefix is the T-vector, untouched
+        (one fused put + wait + unpack kernel)"""
+        hs, vs = (C.c_void_p * 1)(self.h), (C.c_void_p * 1)(TL.data_ptr())
+        capi.check(capi.lib().sb_halo_P_peer_inplace_multi(1, hs, vs, capi._stream_ptr()))
+        return TL
 
     def Pt_inplace(self, TL):
         """add every sharer's partial sums into the owned shared entries of TL; TL[:tsize] is then the T-vector"""
-        capi.check(capi.lib().sb_halo_Pt_peer_put(self.h, capi._dev_ptr(TL), capi._stream_ptr()))
-        capi.check(capi.lib().sb_halo_Pt_peer_finish_inplace(self.h, capi._dev_ptr(TL), capi._stream_ptr()))
+        capi.check(capi.lib().sb_halo_Pt_peer_inplace(self.h, capi._dev_ptr(TL), capi._stream_ptr()))
         return TL[:self.tsize]
 
     def Pt(self, L, T=None):
