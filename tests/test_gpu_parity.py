@@ -257,3 +257,21 @@ def test_complementary_subdomains_sum_to_the_whole(cuda):
     F0 = capi.Functional(part.G, [part.G_shape, part.G, part.G])
     F0.AddDomainIntegral(I_empty, [0, 1, 2])
     assert float(F0(0.0, [part.S, part.U, part.A]).abs().max()) == 0.0
+
+
+def test_evaluation_in_two_halves_is_bit_identical(case):
+    """sb_functional_evaluate_begin / _end (elements [0, split) first, the rest later -- what a partitioned run does
+    around its input exchange) returns exactly what the one-call evaluation returns, for any split point"""
+    prob, P = case
+    if P.domain is not None:
+        pytest.skip("the split applies to whole-mesh domain integrals")
+    ne = int(prob["ne"])
+    ref = P.F(0.0, [P.S, P.U, P.A], wrt=1).clone()
+    ref_d = P.integral.export_derivatives(1).clone()
+    for split in sorted({0, 1, ne // 2, ne - 1, ne, ne + 5}):
+        P.F.evaluate_begin(0.0, [P.S, P.U, P.A], wrt=1, split_element=split)
+        got = P.F.evaluate_end()
+        assert P.torch.equal(got, ref), f"split at {split}"
+        assert P.torch.equal(P.integral.export_derivatives(1), ref_d)
+    dr = P.F.GradientMult(1, P.dU).cpu().numpy()
+    assert rel_l2(dr, prob["dr"]) < TOL
