@@ -136,7 +136,8 @@ def build_partitioned_problem(device, rank, world):
     part = Partition(mesh, ranks, rank, p, 3, owned_first=inplace)
     part1 = Partition(mesh, ranks, rank, 1, 3, owned_first=inplace)
     # elements all of whose nodes this rank owns come first: they are evaluated while the input exchange is in flight
-    split = inplace and os.environ.get("SB_HALO_SPLIT", "0") != "0"  # measured: no gain at 2 GPUs, -2.5% at 8
+    # measured: no gain at 2 GPUs, -2.5% at 8; its half-exchanges need the flag protocol (SB_HALO_LL=0)
+    split = inplace and os.environ.get("SB_HALO_SPLIT", "0") != "0" and os.environ.get("SB_HALO_LL", "1") == "0"
     order, n_independent = part.halo_independent_first() if split else (None, 0)
     tab, tab1 = part.element_table(p, element_order=order), part1.element_table(1, element_order=order)
     G = capi.ElementRestriction(tab, 3, part.num_local_nodes)

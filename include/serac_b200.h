@@ -345,8 +345,10 @@ int sb_halo_Pt_peer_finish_inplace(sb_halo_t H, double* TL_dev, void* stream);
 /* P in place for up to 4 fields (one halo object each) with ONE put launch and ONE wait + unpack launch: what
  * Functional::operator() needs before its gathers (F/functional.hpp:460-470 applies P to every argument) */
 int sb_halo_P_peer_inplace_multi(int num_fields, const sb_halo_t* H, double* const* TL_dev, void* stream);
-/* P^T in place in one call.  With SB_HALO_FUSED=1 in the environment both in-place exchanges run as ONE fused kernel
- * per round (put, raise flags, wait, unpack); default: a put launch and a wait + unpack launch */
+/* P^T in place in one call.  sb_halo_P_peer_inplace_multi and sb_halo_Pt_peer_inplace run, by default, the LL protocol:
+ * one kernel per round in which every double travels as two 8-byte {half, round tag} words that the receiver polls -- no
+ * fence, no flag, one NVLink trip.  SB_HALO_LL=0 in the environment selects the flag protocol (put launch + wait/unpack
+ * launch, or one fused launch with SB_HALO_FUSED=1); a halo object must stay with one protocol. */
 int sb_halo_Pt_peer_inplace(sb_halo_t H, double* TL_dev, void* stream);
 /* the two halves of the multi-field P: launch kernels that need no halo data (sb_functional_evaluate_begin) in between */
 int sb_halo_P_peer_put_multi(int num_fields, const sb_halo_t* H, double* const* TL_dev, void* stream);

@@ -73,7 +73,8 @@ class HaloExchange:
                                           recv_off=self.recv_off.tolist()), group=self.group)
         try:
             grp = self.group if self.group is not None else dist.group.WORLD
-            ring = symm_mem.empty(2 * slot + 2 * MAXN, dtype=torch.float64, device=self.device)
+            # two slots of (2 * slot + MAXN) 8-byte words: enough for the flag protocol and for the LL one (SB_HALO_LL=1)
+            ring = symm_mem.empty(4 * slot + 2 * MAXN, dtype=torch.float64, device=self.device)
             ring.zero_()
             hdl = symm_mem.rendezvous(ring, grp.group_name if hasattr(grp, "group_name") else grp)
             ptrs = [int(p) for p in hdl.buffer_ptrs]

@@ -50,7 +50,8 @@ def main():
                and os.environ.get("SB_HALO_INPLACE", "1") != "0")
     part = Partition(mesh, ranks, rank, p, 3, owned_first=inplace)
     part1 = Partition(mesh, ranks, rank, 1, 3, owned_first=inplace)
-    split = inplace and os.environ.get("SB_HALO_SPLIT", "0") != "0"  # measured: no gain at 2 GPUs, -2.5% at 8
+    # measured: no gain at 2 GPUs, -2.5% at 8; its half-exchanges need the flag protocol (SB_HALO_LL=0)
+    split = inplace and os.environ.get("SB_HALO_SPLIT", "0") != "0" and os.environ.get("SB_HALO_LL", "1") == "0"
     order, n_independent = part.halo_independent_first() if split else (None, 0)
     loc = build(dev, mesh, part, p, part1, order)
     halo1 = HaloExchange(part1.halo_lists(), dev)
@@ -93,6 +94,7 @@ def main():
     if transport == "peer":
         assert all(h.peer_status() == 0 for h in halos), "a peer flag wait timed out"
         transport += (("+overlap" if overlap else "") + ("+inplace" if inplace else "") +
+                      ("+LL" if inplace and os.environ.get("SB_HALO_LL", "1") != "0" else "") +
                       (f"+split({n_independent}/{part.num_elements})" if split else ""))
     # the same on the whole mesh, one GPU
     glob = build(dev, mesh, None, p)
