@@ -128,6 +128,9 @@ def build_partitioned_problem(device, rank, world):
     from serac_b200.structured import Partition, StructuredHexMesh, factor_ranks
     p = 2
     ranks = factor_ranks(world)
+    if os.environ.get("SB_BENCH_RANKS"):  # experiments: e.g. "1,2,1" cuts the two boxes across their large face
+        ranks = tuple(int(x) for x in os.environ["SB_BENCH_RANKS"].split(","))
+        assert int(np.prod(ranks)) == world
     n = tuple(PER_GPU_BOX[d] * ranks[d] for d in range(3))
     mesh = StructuredHexMesh(*n, n[0] / 16.0, n[1] / 16.0, n[2] / 16.0)
     # owned-first local numbering: the T-vector is the prefix of the L-vector, so P / P^T run in place
