@@ -673,6 +673,59 @@ class LinearIsotropicConductor:
         return self.rho * self.cp, [-1.0 * self.k * g for g in du_dX]
 
 
+class GreenSaintVenantThermoelastic:
+    """src/serac/physics/materials/green_saint_venant_thermoelastic.hpp:26-92: (state, grad_u, theta, grad_theta) ->
+    (Cauchy stress, C_v, internal heat source, heat flux); state = {"strain_trace"}"""
+
+    def __init__(self, density, E, nu, C_v, alpha, theta_ref, k):
+        self.density, self.E, self.nu, self.C_v, self.alpha, self.theta_ref, self.k = density, E, nu, C_v, alpha, theta_ref, k
+
+    def __call__(self, state, grad_u, theta, grad_theta):
+        K = self.E / (3.0 * (1.0 - 2.0 * self.nu))
+        G = 0.5 * self.E / (1.0 + self.nu)
+        F = madd(grad_u, eye(3))
+        Eg = mscale(0.5, madd(madd(grad_u, mT(grad_u)), mdot(mT(grad_u), grad_u)))
+        trEg = mtr(Eg)
+        vol = K * (trEg - 3.0 * self.alpha * (theta - self.theta_ref))
+        devE = mdev(Eg)
+        S = [[2.0 * G * devE[i][j] + (vol if i == j else 0.0) for j in range(3)] for i in range(3)]
+        P = mdot(F, S)
+        sigma = mscale(1.0 / mdet(F), mdot(P, mT(F)))
+        s0 = -3.0 * K * self.alpha * theta * (trEg - state["strain_trace"])
+        q0 = [-1.0 * self.k * g for g in grad_theta]
+        state["_updated"] = dict(strain_trace=value_of(trEg))
+        return sigma, self.C_v, s0, q0
+
+
+def thermoelastic_solid_qf(material, geom_nonlin):
+    """MaterialStressFunctor<MechanicalMaterialInterface<Material>> (solid_mechanics.hpp:834-852 with the parameter pack,
+    thermomechanics.hpp:318-352): arguments (displacement, acceleration, temperature)"""
+
+    def qf(t, x, state, displacement, acceleration, temperature):
+        du_dX = displacement[1]
+        stress = material(state, du_dX, temperature[0][0], temperature[1][0])[0]
+        dx_dX = madd(mscale(0.0, du_dX), eye(3))
+        if geom_nonlin:
+            dx_dX = madd(dx_dX, du_dX)
+        flux = mscale(mdet(dx_dX), mdot(stress, mT(minv(dx_dX))))
+        return [material.density * a for a in acceleration[0]], flux
+
+    return qf
+
+
+def thermoelastic_thermal_qf(material):
+    """ThermalMaterialIntegrand<ThermalMaterialInterface<Material>> (heat_transfer.hpp:392-402, thermomechanics.hpp:272-310):
+    arguments (temperature, dT/dt, displacement); the material's state is a throw-away local, as in the reference"""
+
+    def qf(t, x, state, temperature, dtemp_dt, displacement):
+        zero = 0.0 * value_of(temperature[0][0])
+        local = dict(strain_trace=zero)
+        _, cap, _, q0 = material(local, displacement[1], temperature[0][0], temperature[1][0])
+        return [cap * dtemp_dt[0][0]], [[-1.0 * h for h in q0]]
+
+    return qf
+
+
 def material_stress_qf(material, geom_nonlin):
     """SolidMechanics::MaterialStressFunctor (src/serac/physics/solid_mechanics.hpp:808-853):
     (state, displacement=(u, du_dX), acceleration=(a, da_dX)) -> (source [c], flux [c][dim])"""
@@ -858,4 +911,8 @@ def make_qf(kind, params):
         return shape_aware(material_stress_qf(J2FiniteLinear(*params[:5]), params[5] != 0.0))
     if kind == "thermal_linear_conductor":
         return shape_aware(thermal_qf(LinearIsotropicConductor(*params[:3])))
+    if kind == "thermoelastic_solid":
+        return shape_aware(thermoelastic_solid_qf(GreenSaintVenantThermoelastic(*params[:7]), params[7] != 0.0))
+    if kind == "thermoelastic_thermal":
+        return shape_aware(thermoelastic_thermal_qf(GreenSaintVenantThermoelastic(*params[:7])))
     raise KeyError(kind)

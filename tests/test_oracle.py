@@ -139,3 +139,109 @@ def test_live_reference_other_integrands(kind, vdim, params):
     assert rel_l2(fo.action_of_gradient_kernel(o["blocks"], dU_E, 2, 2, 3, 3), prob["dr_E"]) < 1e-13
     K_e = fo.element_gradient_kernel(o["blocks"], 2, 2, 3, 3)
     assert rel_l2(K_e, prob["K_e"]) < 1e-13
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# quantities of interest (F/functional_qoi.inl, F/detail/qoi.inl): numpy restatement against the reference's QOI kernels
+# ----------------------------------------------------------------------------------------------------------------------
+def _qoi_names():
+    import glob
+    import os
+    from harness import GOLDEN
+    return sorted(os.path.splitext(os.path.basename(f))[0] for f in glob.glob(os.path.join(GOLDEN, "qoi_*.npz")))
+
+
+def _quadrature_weights(geom, q, dim):
+    if fo.is_simplex(geom):
+        return fo.simplex_quadrature(geom, q)[1]
+    w1 = fo.basis_tables(1, q)[2]
+    w = w1
+    for _ in range(dim - 1):
+        w = np.multiply.outer(w1, w)  # Q = (qz*q + qy)*q + qx
+    return w.ravel()
+
+
+@pytest.mark.parametrize("name", _qoi_names())
+def test_qoi_value_and_gradient(name):
+    """element totals = sum_q f(x_q, u_q, grad u_q) det(J_q) w_q (qoi.inl:33-75); the gradient vector by the chain rule
+    through the interpolation (functional_qoi.inl:411-455)"""
+    prob = load_golden(name)
+    geom, p, dim = int(prob["geom"]), int(prob["p"]), int(prob["dim"])
+    q = p + 1
+    a, b = (float(x) for x in prob["params"])
+    table = fo.dof_info(geom, p, prob["native_dofs"])
+    assert np.array_equal(table, prob["dof_info"])
+    mesh_table = prob["mesh_dof_info"] & MASK
+    byvdim = int(prob["mesh_ordering"]) == 1
+    X_q, J_q = fo.geometric_factors(fo.gather(mesh_table, prob["mesh_nodes"], dim, byvdim), int(prob["mesh_order"]), q,
+                                    dim, geom)
+    assert rel_l2(X_q, prob["X_q"]) < 1e-14 and rel_l2(J_q, prob["J_q"]) < 1e-14
+    U_E = fo.gather(table, prob["U"], dim)
+    val, grad = fo.interpolate(U_E, p, q, dim, geom)  # [ne][c][nq], parent gradient [ne][c][dim][nq]
+    Jm = np.transpose(J_q, (0, 3, 2, 1))  # [ne][nq][i][j] = dX_i/dxi_j
+    invJ = np.linalg.inv(Jm)
+    dv = np.linalg.det(Jm)
+    du = np.einsum("ecjq,eqjk->eqck", grad, invJ)  # physical gradient
+    u = np.transpose(val, (0, 2, 1))  # [ne][nq][c]
+    w = _quadrature_weights(geom, q, dim)
+    x0, x1 = X_q[:, 0, :], X_q[:, 1, :]
+    f = a * (1.0 + x0) * np.einsum("eqc,eqc->eq", u, u) + 0.5 * b * np.einsum("eqck,eqck->eq", du, du) + np.sin(x1)
+    q_E = np.einsum("eq,eq,q->e", f, dv, w)
+    assert rel_l2(q_E, prob["q_E"]) < 1e-13
+    assert abs(q_E.sum() - prob["value"]) < 1e-13 * abs(prob["value"])
+    # d f / d u = 2 a (1 + x0) u ; d f / d (grad u) = b grad u  ->  gradient w.r.t. the dofs through B and G
+    phi, dphi = fo.interpolate(np.eye(U_E.shape[2])[None], p, q, dim, geom)
+    phi, dphi = phi[0], dphi[0]  # [k][nq], [k][dim][nq]
+    dphi_phys = np.einsum("kjq,eqjl->ekql", dphi, invJ)
+    gE = (np.einsum("eq,eqc,kq,eq,q->eck", 2.0 * a * (1.0 + x0), u, phi, dv, w) +
+          b * np.einsum("eqcl,ekql,eq,q->eck", du, dphi_phys, dv, w))
+    g = fo.scatter_add(table, gE, np.zeros(len(prob["U"])), dim)
+    assert rel_l2(g, prob["gradient"]) < 1e-13
+    assert abs(g @ prob["dU"] - prob["dvalue"]) < 1e-12 * abs(prob["dvalue"])
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# thermomechanics (parameterized signatures, BASELINE.json configs[3]): numpy restatement against the reference's kernels
+# ----------------------------------------------------------------------------------------------------------------------
+from harness import multifield_golden_names  # noqa: E402
+
+
+@pytest.mark.parametrize("name", multifield_golden_names())
+def test_thermomechanics_residual_jvp_and_state(name):
+    prob = load_golden(name)
+    geom, p, dim = int(prob["geom"]), int(prob["p"]), int(prob["dim"])
+    q = p + 1
+    vdims = [int(v) for v in prob["trial_vdims"]]
+    test_vdim = int(prob["test_vdim"])
+    table = fo.dof_info(geom, p, prob["native_dofs"])
+    shape_table = fo.dof_info(geom, 1, prob["shape_native_dofs"])
+    mesh_table = prob["mesh_dof_info"] & MASK
+    byvdim = int(prob["mesh_ordering"]) == 1
+    X_q, J_q = fo.geometric_factors(fo.gather(mesh_table, prob["mesh_nodes"], dim, byvdim), int(prob["mesh_order"]), q,
+                                    dim, geom)
+    tables = [shape_table] + [table] * (len(vdims) - 1)
+    orders = [1] + [p] * (len(vdims) - 1)
+    trials = [fo.gather(t, prob[f"field{i}"], v) for i, (t, v) in enumerate(zip(tables, vdims))]
+    qf = fo.make_qf(str(prob["kind"]), list(prob["params"]))
+    ne, nq = int(prob["ne"]), fo.num_quadrature_points(geom, q)
+
+    def state0():
+        if "qdata0" not in prob:
+            return None
+        return dict(strain_trace=np.asarray(prob["qdata0"]).reshape(ne, nq).copy())
+
+    st = state0()
+    r_E, _ = fo.evaluation_kernel(qf, trials, orders, X_q, J_q, p, q, dim, wrt=-1, state=st, geom=geom)
+    assert rel_l2(r_E, prob["r_E"]) < 1e-13
+    if st is not None:  # the committed state: trace of the Green strain (green_saint_venant_thermoelastic.hpp:64)
+        assert rel_l2(st["_updated"]["strain_trace"], np.asarray(prob["qdata1"]).reshape(ne, nq)) < 1e-13
+    for wrt in range(len(vdims)):
+        _, blocks = fo.evaluation_kernel(qf, trials, orders, X_q, J_q, p, q, dim, wrt=wrt, state=state0(), geom=geom)
+        du_E = fo.gather(tables[wrt], prob[f"dfield{wrt}"], vdims[wrt])
+        dr_E = fo.action_of_gradient_kernel(blocks, du_E, orders[wrt], p, q, dim, geom)
+        dr = fo.scatter_add(table, dr_E, np.zeros(int(prob["num_nodes"]) * test_vdim), test_vdim)
+        want = prob[f"dr{wrt}"]
+        if np.linalg.norm(want) == 0.0:
+            assert np.abs(dr).max() < 1e-13
+        else:
+            assert rel_l2(dr, want) < 1e-13
