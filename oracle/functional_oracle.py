@@ -834,6 +834,116 @@ def evaluation_kernel(qf, trials_E, orders, X_q, J_q, test_order, q, dim, wrt=-1
     return r_E, blocks
 
 
+# ----------------------------------------------------------------------------------------------------------------------
+# boundary integrals (F/boundary_integral_kernels.hpp:111-205): faces of a 3D mesh, trial gradients stay in xi coordinates
+# ----------------------------------------------------------------------------------------------------------------------
+def vcross(A):
+    """cross product of the two columns of a 3 x 2 matrix given as a list of rows"""
+    a, b = [A[i][0] for i in range(3)], [A[i][1] for i in range(3)]
+    return [a[1] * b[2] - a[2] * b[1], a[2] * b[0] - a[0] * b[2], a[0] * b[1] - a[1] * b[0]]
+
+
+def vnorm(v):
+    return d_sqrt(v[0] * v[0] + v[1] * v[1] + v[2] * v[2])
+
+
+def shape_aware_boundary(qf):
+    """ShapeAwareBoundaryIntegrandWrapper (F/shape_aware_functional.hpp:474-499): integrand(t, x + p, args...) times the
+    area correction |d(X+p)/dxi_1 x d(X+p)/dxi_2| / |dX/dxi_1 x dX/dxi_2| (:155-174)"""
+
+    def wrapped(t, x, shape, *args):
+        X, dX = x
+        xp = ([X[i] + shape[0][i] for i in range(3)], madd(dX, shape[1]))
+        corr = vnorm(vcross(xp[1])) / vnorm(vcross(dX))
+        return [s * corr for s in qf(t, xp, *args)]
+
+    return wrapped
+
+
+def pressure_qf(pressure, geom_nonlin):
+    """SolidMechanics::setPressure (src/serac/physics/solid_mechanics.hpp:1075-1101) with a constant pressure"""
+
+    def qf(t, x, displacement, acceleration):
+        X, dX = x
+        dx = madd(dX, displacement[1]) if geom_nonlin else madd(dX, mscale(0.0, displacement[1]))
+        n = vcross(dx)
+        ref_area = vnorm(vcross(dX))
+        return [pressure * (c / ref_area) for c in n]
+
+    return qf
+
+
+def traction_qf(traction):
+    """SolidMechanics::setTraction (solid_mechanics.hpp:1030-1036) with a constant traction vector"""
+
+    def qf(t, x, displacement, acceleration):
+        return [-1.0 * tc + 0.0 * x[0][0] for tc in traction]
+
+    return qf
+
+
+def make_boundary_qf(kind, params):
+    if kind == "solid_pressure":
+        return shape_aware_boundary(pressure_qf(params[0], params[1] != 0.0))
+    if kind == "solid_traction":
+        return shape_aware_boundary(traction_qf(list(params[:3])))
+    raise KeyError(kind)
+
+
+def _face_weights(geom, q):
+    if is_simplex(geom):
+        return simplex_quadrature(geom, q)[1]
+    w = basis_tables(1, q)[2]
+    return np.multiply.outer(w, w).ravel()
+
+
+def boundary_evaluation_kernel(qf, trials_E, orders, X_q, J_q, test_order, q, face_geom, wrt=-1):
+    """boundary_integral::evaluation_kernel_impl (F/boundary_integral_kernels.hpp:159-205) with batch_apply_qf (:134-156):
+    X_q [nf][3][nq], J_q [nf][j][i][nq] = dX_i/dxi_j.  Returns r_E [nf][ct][ndof] and, when wrt >= 0, the derivative blocks
+    d00 [nf][nq][ct][ck] and d01 [nf][nq][ct][ck][2] of the weighted source w.r.t. the value and the xi-gradient."""
+    nf, nq = X_q.shape[0], X_q.shape[2]
+    dX = [[J_q[:, j, i, :] for j in range(2)] for i in range(3)]  # 3 x 2
+    args = []
+    for k, (uE, p) in enumerate(zip(trials_E, orders)):
+        val, grad = interpolate(uE, p, q, 2, face_geom)
+        c = val.shape[1]
+        vals, grads = _tensor_lists(val, grad)
+        if k == wrt:
+            N = c + c * 2
+            z = np.zeros((nf, nq, N))
+            for a in range(c):
+                g = z.copy()
+                g[..., a] = 1.0
+                vals[a] = Dual(vals[a], g)
+                for j in range(2):
+                    g = z.copy()
+                    g[..., c + a * 2 + j] = 1.0
+                    grads[a][j] = Dual(grads[a][j], g)
+        args.append((vals, grads))
+    x = ([X_q[:, i, :] for i in range(3)], dX)
+    source = qf(0.0, x, *args)
+    measure = vnorm(vcross(dX))  # |dX/dxi_1 x dX/dxi_2| (:148-152)
+    source = [s * measure for s in source]
+    ct = len(source)
+    src_v = np.stack([np.broadcast_to(value_of(s), (nf, nq)) for s in source], axis=1)
+    r_E = integrate(src_v, None, test_order, q, 2, face_geom)
+    if wrt < 0:
+        return r_E, None
+    ck = trials_E[wrt].shape[1]
+    ds = np.stack([s.g if isinstance(s, Dual) else np.zeros((nf, nq, ck + ck * 2)) for s in source], axis=2)
+    blocks = dict(d00=ds[..., :ck], d01=ds[..., ck:].reshape(nf, nq, ct, ck, 2))
+    return r_E, blocks
+
+
+def boundary_action_of_gradient_kernel(blocks, du_E, trial_order, test_order, q, face_geom):
+    """boundary action_of_gradient_kernel (F/boundary_integral_kernels.hpp:252-277)"""
+    val, grad = interpolate(du_E, trial_order, q, 2, face_geom)
+    v = np.transpose(val, (0, 2, 1))
+    g = np.transpose(grad, (0, 3, 1, 2))
+    src = np.einsum("eqab,eqb->eqa", blocks["d00"], v) + np.einsum("eqabl,eqbl->eqa", blocks["d01"], g)
+    return integrate(np.transpose(src, (0, 2, 1)), None, test_order, q, 2, face_geom)
+
+
 def action_of_gradient_kernel(blocks, du_E, trial_order, test_order, q, dim, geom=None):
     """action_of_gradient_kernel (F/domain_integral_kernels.hpp:277-304) with chain_rule (:223-237)"""
     val, grad = interpolate(du_E, trial_order, q, dim, geom)  # parent space, no J needed

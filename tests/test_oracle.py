@@ -245,3 +245,42 @@ def test_thermomechanics_residual_jvp_and_state(name):
             assert np.abs(dr).max() < 1e-13
         else:
             assert rel_l2(dr, want) < 1e-13
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# boundary integrals (traction / follower pressure on quadrilateral and triangular faces)
+# ----------------------------------------------------------------------------------------------------------------------
+from harness import boundary_golden_names  # noqa: E402
+
+
+@pytest.mark.parametrize("name", boundary_golden_names())
+def test_boundary_residual_and_jvps(name):
+    prob = load_golden(name)
+    fg, p, dim = int(prob["face_geom"]), int(prob["p"]), int(prob["dim"])
+    q = p + 1
+    face_table = fo.dof_info(fg, p, prob["face_native_dofs"])
+    shape_face_table = fo.dof_info(fg, 1, prob["shape_face_native_dofs"])
+    assert np.array_equal(face_table, prob["face_dof_info"])
+    assert np.array_equal(shape_face_table, prob["shape_face_dof_info"])
+    mesh_face_table = fo.dof_info(fg, int(prob["mesh_order"]), prob["mesh_face_native_dofs"])
+    byvdim = int(prob["mesh_ordering"]) == 1
+    nodes_E = fo.gather(mesh_face_table, prob["mesh_nodes"], dim, byvdim)
+    Xv, Xg = fo.interpolate(nodes_E, int(prob["mesh_order"]), q, 2, fg)  # geometric_factors.cpp:140-220
+    X_q, J_q = Xv, np.transpose(Xg, (0, 2, 1, 3))
+    assert rel_l2(X_q, prob["X_q"]) < 1e-14 and rel_l2(J_q, prob["J_q"]) < 1e-14
+    qf = fo.make_boundary_qf(str(prob["kind"]), list(prob["params"]))
+    trials = [fo.gather(shape_face_table, prob["S"], dim), fo.gather(face_table, prob["U"], dim),
+              fo.gather(face_table, prob["A"], dim)]
+    orders = [1, p, p]
+    r_E, _ = fo.boundary_evaluation_kernel(qf, trials, orders, X_q, J_q, p, q, fg)
+    assert rel_l2(r_E.ravel(), prob["r_E"]) < 1e-13
+    r = fo.scatter_add(face_table, r_E, np.zeros(len(prob["U"])), dim)
+    assert rel_l2(r, prob["r"]) < 1e-13
+    for wrt, table, key, dkey, order in ((1, face_table, "dr", "dU", p), (0, shape_face_table, "dr_dshape", "dS", 1)):
+        _, blocks = fo.boundary_evaluation_kernel(qf, trials, orders, X_q, J_q, p, q, fg, wrt=wrt)
+        d_E = fo.boundary_action_of_gradient_kernel(blocks, fo.gather(table, prob[dkey], dim), order, p, q, fg)
+        dr = fo.scatter_add(face_table, d_E, np.zeros(len(prob["U"])), dim)
+        if np.linalg.norm(prob[key]) == 0.0:
+            assert np.abs(dr).max() < 1e-13
+        else:
+            assert rel_l2(dr, prob[key]) < 1e-13
