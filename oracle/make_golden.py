@@ -228,6 +228,45 @@ def reference_qoi_problem(mesh_spec, kind, p, params, seed=42):
     return out
 
 
+def reference_boundary_qoi_problem(mesh_spec, kind, p, params, seed=42):
+    """One reference BOUNDARY QOI Integral on EntireBoundary(mesh): per-face totals, the scalar, its directional
+    derivative and its gradient vector."""
+    mesh = make_mesh(mesh_spec)
+    dim = mesh.dim
+    space = ref.Space(mesh, p, dim)
+    fspace = ref.FaceSpace(space)
+    rng = np.random.default_rng(seed)
+    U = rng.uniform(-1.0, 1.0, space.vsize)
+    dU = rng.uniform(0.0, 1.0, space.vsize)
+    order, ordering, nodes, _ = mesh.nodes()
+    mesh_face_native, mesh_face_info = mesh.nodes_face_tables()
+    X_q, J_q = mesh.boundary_geometric_factors(p + 1)
+    I = ref.Integral(f"{kind}_{dim}d_p{p}", mesh, params, boundary=True)
+    nf = fspace.nf
+    out = dict(kind=kind, geom=mesh.geom, face_geom=mesh.face_geom, dim=dim, p=p, ne=mesh.ne, nf=nf,
+               params=np.asarray(params, dtype=np.float64), native_dofs=space.native_dofs(), num_nodes=space.num_nodes,
+               face_native_dofs=fspace.native_dofs(), face_dof_info=fspace.dof_info(),
+               mesh_order=order, mesh_ordering=ordering, mesh_nodes=nodes, mesh_num_nodes=len(nodes) // dim,
+               mesh_face_native_dofs=mesh_face_native, mesh_face_dof_info=mesh_face_info, U=U, dU=dU, X_q=X_q, J_q=J_q)
+    ins = [fspace.gather(U)]
+    q_E = I.mult(0.0, ins, nf)
+    out["q_E"] = q_E
+    out["value"] = float(np.sum(q_E))
+    I.mult(0.0, ins, nf, wrt=0)
+    out["dvalue"] = float(np.sum(I.jvp(0, fspace.gather(dU), nf)))
+    npf = fspace.dof_info().shape[1]
+    K_e = I.element_gradient(0, nf, npf * dim, 1)
+    out["gradient"] = fspace.scatter_add(K_e.reshape(nf, dim, npf), np.zeros(space.vsize))
+    return out
+
+
+BOUNDARY_QOI_FIXTURES = [
+    ("qoi_boundary_quadratic_hex_p2_cart", dict(mesh_spec=("cart3d", 2, 1, 2, 0.02), kind="qoi_boundary_quadratic", p=2,
+                                                params=[0.7, 1.3])),
+    ("qoi_boundary_quadratic_tet_p1_beam", dict(mesh_spec=("file", "beam-tet.mesh", 0), kind="qoi_boundary_quadratic",
+                                                p=1, params=[0.7, 1.3])),
+]
+
 QOI_FIXTURES = [
     ("qoi_quadratic_hex_p2_cart", dict(mesh_spec=("cart3d", 2, 2, 1, 0.02), kind="qoi_quadratic", p=2, params=[0.7, 1.3])),
     ("qoi_quadratic_tet_p1_beam", dict(mesh_spec=("file", "beam-tet.mesh", 0), kind="qoi_quadratic", p=1,
@@ -403,6 +442,14 @@ def main():
         path = os.path.join(GOLDEN_DIR, name + ".npz")
         np.savez_compressed(path, **data)
         print(f"{name}: ne={data['ne']} value={data['value']:.12e} dvalue={data['dvalue']:.6e} "
+              f"|gradient|={np.linalg.norm(data['gradient']):.6e} -> {os.path.getsize(path) / 1024:.0f} KiB")
+    for name, kw in BOUNDARY_QOI_FIXTURES:
+        if only and name not in only:
+            continue
+        data = reference_boundary_qoi_problem(**kw)
+        path = os.path.join(GOLDEN_DIR, "bqoi_" + name[len("qoi_boundary_"):] + ".npz")
+        np.savez_compressed(path, **data)
+        print(f"{name}: faces={data['nf']} value={data['value']:.12e} dvalue={data['dvalue']:.6e} "
               f"|gradient|={np.linalg.norm(data['gradient']):.6e} -> {os.path.getsize(path) / 1024:.0f} KiB")
     for name, kw in BOUNDARY_FIXTURES:
         if only and name not in only:

@@ -340,6 +340,27 @@ ref::IntegralHolder make_boundary(mfem::Mesh& mesh, QF qf)
   return h;
 }
 
+// boundary quantity of interest (functional_qoi.inl:196-215: MakeBoundaryIntegral<QOI(trials...)>)
+struct QuadraticBoundaryQoi {
+  double a, b;
+  template <typename X, typename U>
+  auto operator()(double, X x, U u) const
+  {
+    auto [uv, du] = u;
+    auto X0       = get<0>(x);
+    return a * (1.0 + X0[0]) * dot(uv, uv) + (0.5 * b) * inner(du, du);
+  }
+};
+ref::Registrar rqb("qoi_boundary_quadratic_" TAG, [](mfem::Mesh& mesh, const double* q, int n) {
+  SLIC_ERROR_IF(n != 2, "params: a b");
+  ref::IntegralHolder h;
+  using sig    = QOI(H1<p, dim>);
+  Domain d     = EntireBoundary(mesh);
+  h.integral   = std::make_unique<Integral>(MakeBoundaryIntegral<sig, p + 1, dim - 1>(d, QuadraticBoundaryQoi{q[0], q[1]}, {0}));
+  h.num_trials = 1;
+  return h;
+});
+
 ref::Registrar r5("solid_traction_" TAG, [](mfem::Mesh& mesh, const double* q, int n) {
   SLIC_ERROR_IF(n != 3, "params: tx ty tz");
   return make_boundary(mesh, ShapeAwareBoundary<UniformTractionIntegrand>{UniformTractionIntegrand{{{q[0], q[1], q[2]}}}});

@@ -19,6 +19,7 @@ constexpr Geometry g   = Geometry::SB_REG_GEOM;
 constexpr int      p   = SB_REG_P;
 constexpr int      dim = dimension_of(g);
 
+#ifndef SB_REG_BOUNDARY
 struct QuadraticQoi {
   double a, b;
   template <typename X, typename U>
@@ -31,6 +32,31 @@ struct QuadraticQoi {
   }
 };
 
+#endif
+#ifdef SB_REG_BOUNDARY
+// boundary variant: g is the FACE geometry; f(x, u) = a (1 + x_0) u.u + b/2 |du/dxi|^2 (trial gradients stay in the
+// face's parent coordinates on a boundary, boundary_integral_kernels.hpp:134-156), weighted by the surface element
+constexpr int sdim = dim + 1;
+struct QuadraticBoundaryQoi {
+  double a, b;
+  template <typename X, typename U>
+  SERAC_HOST_DEVICE auto operator()(double, X x, U u) const
+  {
+    auto uv = get<0>(u);
+    auto du = get<1>(u);
+    auto X0 = get<0>(x);
+    return a * (1.0 + X0[0]) * dot(uv, uv) + (0.5 * b) * inner(du, du);
+  }
+};
+using BSig = BoundarySignature<g, p + 1, QOI, H1<p, sdim>>;
+long make_bqoi(const double* q, int n, void* out, size_t cap)
+{
+  if (n != 2) return -1;
+  return store_blob(QuadraticBoundaryQoi{q[0], q[1]}, out, cap);
+}
+static Registrar r_bqoi({"qoi_boundary_quadratic_" SB_STR(SB_REG_TAG), make_boundary_kernel_table<BSig, QuadraticBoundaryQoi>(),
+                         &make_bqoi, "{a, b}: boundary integrand a (1 + x_0) u.u + b/2 |du/dxi|^2"});
+#else
 using Sig = Signature<g, p + 1, QOI, H1<p, dim>>;
 
 long make_qoi(const double* q, int n, void* out, size_t cap)
@@ -41,6 +67,7 @@ long make_qoi(const double* q, int n, void* out, size_t cap)
 
 static Registrar r_qoi({"qoi_quadratic_" SB_STR(SB_REG_TAG), make_qoi_kernel_table<Sig, QuadraticQoi>(), &make_qoi,
                         "{a, b}: integrand a (1 + x_0) u.u + b/2 |grad u|^2 + sin(x_1)"});
+#endif
 
 }  // namespace
 }  // namespace sb

@@ -527,6 +527,13 @@ class Functional<double(trials...)> {
     impl_->AddDomainIntegral(d, a, integrand, domain, qdata);
   }
 
+  /// functional_qoi.inl:196-215; the q-function returns the scalar integrand per unit area of the boundary
+  template <int dim, int... args, typename Integrand>
+  void AddBoundaryIntegral(Dimension<dim> d, DependsOn<args...> a, const Integrand& integrand, const Mesh& mesh)
+  {
+    impl_->AddBoundaryIntegral(d, a, integrand, mesh);
+  }
+
   template <typename... T>
   auto operator()(double t, const T&... args)
   {

@@ -275,6 +275,32 @@ int run_qoi(const std::map<std::string, double>& meta)
   return 0;
 }
 
+struct QuadraticBoundaryQoi {
+  double a, b;
+  template <typename X, typename U>
+  SERAC_HOST_DEVICE auto operator()(double, X x, U u) const
+  {
+    auto uv = get<0>(u);
+    auto du = get<1>(u);
+    auto X0 = get<0>(x);
+    return a * (1.0 + X0[0]) * dot(uv, uv) + (0.5 * b) * inner(du, du);
+  }
+};
+
+int run_boundary_qoi(const std::map<std::string, double>& meta)
+{
+  Problem P = load_problem(meta, true);
+  auto    q = read_bin<double>("params");
+  Functional<double(H1<p, dim>)> qoi({&P.space});
+  qoi.AddBoundaryIntegral(Dimension<dim - 1>{}, DependsOn<0>{}, QuadraticBoundaryQoi{q[0], q[1]}, P.mesh);
+  Vector U(read_bin<double>("U")), dU(read_bin<double>("dU"));
+  auto [value, dqdu] = qoi(0.0, differentiate_wrt(U));
+  write_bin("value", std::vector<double>{value});
+  write_bin("dvalue", dqdu(dU).to_host());
+  write_bin("gradient", gradient_vector(dqdu));
+  return 0;
+}
+
 int main(int argc, char** argv)
 {
   if (argc != 3) {
@@ -294,6 +320,7 @@ int main(int argc, char** argv)
   if (which == "pressure") rc = run_pressure(meta);
   if (which == "user") rc = run_user(meta);
   if (which == "qoi") rc = run_qoi(meta);
+  if (which == "boundary_qoi") rc = run_boundary_qoi(meta);
   std::printf("launches: %lld\n", sb_launch_count());
   return rc;
 }

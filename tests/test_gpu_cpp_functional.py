@@ -129,3 +129,18 @@ def test_qoi_functional(tmp_path, cuda):
     assert abs(v[0] - prob["value"]) < TOL * abs(prob["value"]) and v[0] == v[1]
     assert abs(out(d, "dvalue")[0] - prob["dvalue"]) < TOL * abs(prob["dvalue"])
     assert rel_l2(out(d, "gradient"), prob["gradient"]) < TOL
+
+
+def test_boundary_qoi_functional(tmp_path, cuda):
+    """Functional<double(H1<2,3>)>::AddBoundaryIntegral with a q-function defined in the C++ driver"""
+    prob = load_golden("bqoi_quadratic_hex_p2_cart")
+    d = str(tmp_path)
+    fake = dict(prob)
+    nv = recover_native(prob, int(prob["geom"]))
+    fake.update(shape_num_nodes=prob["mesh_num_nodes"], A=prob["U"], S=np.zeros(1), dS=np.zeros(1),
+                shape_face_native_dofs=prob["mesh_face_native_dofs"])
+    export(fake, d, boundary=True)
+    run("boundary_qoi", d)
+    assert abs(out(d, "value")[0] - prob["value"]) < TOL * abs(prob["value"])
+    assert abs(out(d, "dvalue")[0] - prob["dvalue"]) < TOL * abs(prob["dvalue"])
+    assert rel_l2(out(d, "gradient"), prob["gradient"]) < TOL

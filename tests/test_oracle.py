@@ -284,3 +284,29 @@ def test_boundary_residual_and_jvps(name):
             assert np.abs(dr).max() < 1e-13
         else:
             assert rel_l2(dr, prob[key]) < 1e-13
+
+
+def _bqoi_names():
+    import glob
+    import os
+    from harness import GOLDEN
+    return sorted(os.path.splitext(os.path.basename(f))[0] for f in glob.glob(os.path.join(GOLDEN, "bqoi_*.npz")))
+
+
+@pytest.mark.parametrize("name", _bqoi_names())
+def test_boundary_qoi_value(name):
+    """boundary quantity of interest: sum over faces and points of f(x, u, du/dxi) |dX/dxi_1 x dX/dxi_2| w"""
+    prob = load_golden(name)
+    fg, p, dim = int(prob["face_geom"]), int(prob["p"]), int(prob["dim"])
+    q = p + 1
+    a, b = (float(x) for x in prob["params"])
+    face_table = fo.dof_info(fg, p, prob["face_native_dofs"])
+    mesh_face_table = fo.dof_info(fg, int(prob["mesh_order"]), prob["mesh_face_native_dofs"])
+    nodes_E = fo.gather(mesh_face_table, prob["mesh_nodes"], dim, int(prob["mesh_ordering"]) == 1)
+    Xv, Xg = fo.interpolate(nodes_E, int(prob["mesh_order"]), q, 2, fg)
+    val, grad = fo.interpolate(fo.gather(face_table, prob["U"], dim), p, q, 2, fg)
+    n = np.cross(Xg[:, :, 0, :], Xg[:, :, 1, :], axis=1)  # [nf][3][nq]
+    measure = np.linalg.norm(n, axis=1)
+    f = a * (1.0 + Xv[:, 0, :]) * np.einsum("ecq,ecq->eq", val, val) + 0.5 * b * np.einsum("ecjq,ecjq->eq", grad, grad)
+    q_E = np.einsum("eq,eq,q->e", f, measure, fo._face_weights(fg, q))
+    assert rel_l2(q_E, prob["q_E"]) < 1e-13 and abs(q_E.sum() - prob["value"]) < 1e-13 * abs(prob["value"])
