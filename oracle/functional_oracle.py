@@ -161,6 +161,8 @@ def simplex_shape_tables(geom, p, pts):
     dim = pts.shape[1]
     x = [pts[:, d] for d in range(dim)]
     one, zero = np.ones(len(pts)), np.zeros(len(pts))
+    if p == 0:  # L2<0> / QOI: one shape function, identically 1
+        return np.ones((len(pts), 1)), np.zeros((len(pts), 1, dim))
     if p == 1:
         lam0 = 1.0 - sum(x)
         phi = [lam0] + x
@@ -1010,7 +1012,19 @@ def csr_assemble(K_e, test_vdofs, trial_vdofs, keys):
 # ----------------------------------------------------------------------------------------------------------------------
 # named integrands (same names / parameters as the product's registry and the reference-oracle kinds)
 # ----------------------------------------------------------------------------------------------------------------------
+def parameterized_diffusion_qf(c0):
+    """the test integrand of the L2-parameter path: H1<p>(H1<p> u, L2<0> k) -> source (c0 + k) u, flux k^2 grad u"""
+
+    def qf(t, x, state, u, k):
+        kv = k[0][0]
+        return [(c0 + kv) * u[0][0]], [[(kv * kv) * g for g in u[1][0]]]
+
+    return qf
+
+
 def make_qf(kind, params):
+    if kind == "param_diffusion":
+        return parameterized_diffusion_qf(params[0])
     if kind == "solid_neohookean":
         return shape_aware(material_stress_qf(NeoHookean(*params[:3]), params[3] != 0.0))
     if kind == "solid_linear_isotropic":

@@ -228,6 +228,45 @@ def reference_qoi_problem(mesh_spec, kind, p, params, seed=42):
     return out
 
 
+def reference_l2_parameter_problem(mesh_spec, p, params, seed=42):
+    """H1<p>(H1<p> u, L2<0> k): a domain integral with a discontinuous piecewise-constant parameter field (the L2 dofs mfem
+    returns are lexicographic already: no permutation, element_restriction.cpp:262-268): residual, the Jacobian action
+    and the assembled matrix w.r.t. both arguments (the second one is rectangular: H1 rows x L2 columns)."""
+    mesh = make_mesh(mesh_spec)
+    dim = mesh.dim
+    space = ref.Space(mesh, p, 1)
+    pspace = ref.Space(mesh, 0, 1, family="L2")
+    rng = np.random.default_rng(seed)
+    U, K = rng.uniform(-1.0, 1.0, space.vsize), rng.uniform(0.5, 1.5, pspace.vsize)
+    dU, dK = rng.uniform(0.0, 1.0, space.vsize), rng.uniform(0.0, 1.0, pspace.vsize)
+    order, ordering, nodes, nodes_info = mesh.nodes()
+    X_q, J_q = mesh.geometric_factors(p + 1)
+    I = ref.Integral(f"param_diffusion_{dim}d_p{p}", mesh, params)
+    out = dict(kind="param_diffusion", geom=mesh.geom, dim=dim, p=p, ne=mesh.ne, params=np.asarray(params, dtype=np.float64),
+               native_dofs=space.native_dofs(), dof_info=space.dof_info(), num_nodes=space.num_nodes,
+               l2_native_dofs=pspace.native_dofs(), l2_dof_info=pspace.dof_info(), l2_num_nodes=pspace.num_nodes,
+               mesh_order=order, mesh_ordering=ordering, mesh_nodes=nodes, mesh_dof_info=nodes_info,
+               mesh_num_nodes=len(nodes) // dim, U=U, K=K, dU=dU, dK=dK, X_q=X_q, J_q=J_q)
+    ins = [space.gather(U), pspace.gather(K)]
+    r_E = I.mult(0.0, ins, space.esize)
+    out["r_E"] = r_E
+    out["r"] = space.scatter_add(r_E, np.zeros(space.vsize))
+    npe = space.dof_info().shape[1]
+    for i, (sp, d) in enumerate(((space, dU), (pspace, dK))):
+        I.mult(0.0, ins, space.esize, wrt=i)
+        out[f"dr{i}"] = space.scatter_add(I.jvp(i, sp.gather(d), space.esize), np.zeros(space.vsize))
+        K_e = I.element_gradient(i, mesh.ne, sp.dof_info().shape[1], npe)
+        csr = ref.Csr(space, sp)
+        rp, ci = csr.pattern()
+        out[f"row_ptr{i}"], out[f"col_ind{i}"], out[f"values{i}"] = rp, ci, csr.assemble(K_e)
+    return out
+
+
+L2_FIXTURES = [
+    ("l2param_diffusion_hex_p2_cart", dict(mesh_spec=("cart3d", 2, 2, 1, 0.02), p=2, params=[0.3])),
+    ("l2param_diffusion_tet_p1_patch", dict(mesh_spec=("file", "patch3D_tets.mesh", 0), p=1, params=[0.3])),
+]
+
 def reference_boundary_qoi_problem(mesh_spec, kind, p, params, seed=42):
     """One reference BOUNDARY QOI Integral on EntireBoundary(mesh): per-face totals, the scalar, its directional
     derivative and its gradient vector."""
@@ -443,6 +482,14 @@ def main():
         np.savez_compressed(path, **data)
         print(f"{name}: ne={data['ne']} value={data['value']:.12e} dvalue={data['dvalue']:.6e} "
               f"|gradient|={np.linalg.norm(data['gradient']):.6e} -> {os.path.getsize(path) / 1024:.0f} KiB")
+    for name, kw in L2_FIXTURES:
+        if only and name not in only:
+            continue
+        data = reference_l2_parameter_problem(**kw)
+        path = os.path.join(GOLDEN_DIR, name + ".npz")
+        np.savez_compressed(path, **data)
+        print(f"{name}: ne={data['ne']} |r|={np.linalg.norm(data['r']):.6e} |dr0|={np.linalg.norm(data['dr0']):.6e} "
+              f"|dr1|={np.linalg.norm(data['dr1']):.6e} -> {os.path.getsize(path) / 1024:.0f} KiB")
     for name, kw in BOUNDARY_QOI_FIXTURES:
         if only and name not in only:
             continue

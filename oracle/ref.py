@@ -43,6 +43,7 @@ def lib():
             "ref_mesh_nodes": (None, [vp, vp]),
             "ref_mesh_nodes_dof_info": (l, [vp, i, vp]),
             "ref_space_create": (vp, [vp, i, i, i]),
+            "ref_space_create_l2": (vp, [vp, i, i, i]),
             "ref_space_destroy": (None, [vp]),
             "ref_space_vsize": (l, [vp]),
             "ref_space_num_nodes": (l, [vp]),
@@ -177,9 +178,10 @@ class Mesh:
 
 
 class Space:
-    def __init__(self, mesh, p, vdim, ordering=BYVDIM):
-        self.mesh, self.p, self.vdim, self.ordering = mesh, p, vdim, ordering
-        self.h = lib().ref_space_create(mesh.h, p, vdim, ordering)
+    def __init__(self, mesh, p, vdim, ordering=BYVDIM, family="H1"):
+        self.mesh, self.p, self.vdim, self.ordering, self.family = mesh, p, vdim, ordering, family
+        create = lib().ref_space_create if family == "H1" else lib().ref_space_create_l2
+        self.h = create(mesh.h, p, vdim, ordering)
         self.vsize = lib().ref_space_vsize(self.h)
         self.num_nodes = lib().ref_space_num_nodes(self.h)
         self.geom = mesh.geom

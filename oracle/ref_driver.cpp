@@ -12,7 +12,7 @@ std::map<std::string, Factory>& factories()
 }
 
 struct Space {
-  std::unique_ptr<mfem::H1_FECollection>     fec;
+  std::unique_ptr<mfem::FiniteElementCollection> fec;
   std::unique_ptr<mfem::FiniteElementSpace>  fes;
   std::unique_ptr<serac::BlockElementRestriction> G;
 };
@@ -131,6 +131,17 @@ void* ref_space_create(void* m, int p, int vdim, int ordering)
   auto* mesh = static_cast<mfem::Mesh*>(m);
   auto* s    = new Space;
   s->fec     = std::make_unique<mfem::H1_FECollection>(p, mesh->Dimension());
+  s->fes = std::make_unique<mfem::FiniteElementSpace>(mesh, s->fec.get(), vdim, mfem::Ordering::Type(ordering));
+  s->G   = std::make_unique<serac::BlockElementRestriction>(s->fes.get());
+  return s;
+}
+/// discontinuous space: L2 with the Gauss-Lobatto nodal basis (what serac's L2<p,c> elements interpolate,
+/// F/detail/hexahedron_L2.inl:90-130); mfem returns its dofs in lexicographic order already (element_restriction.cpp:262-268)
+void* ref_space_create_l2(void* m, int p, int vdim, int ordering)
+{
+  auto* mesh = static_cast<mfem::Mesh*>(m);
+  auto* s    = new Space;
+  s->fec     = std::make_unique<mfem::L2_FECollection>(p, mesh->Dimension(), mfem::BasisType::GaussLobatto);
   s->fes = std::make_unique<mfem::FiniteElementSpace>(mesh, s->fec.get(), vdim, mfem::Ordering::Type(ordering));
   s->G   = std::make_unique<serac::BlockElementRestriction>(s->fes.get());
   return s;

@@ -170,6 +170,28 @@ ref::Registrar r4("thermal_linear_conductor_" TAG, [](mfem::Mesh& mesh, const do
   return h;
 });
 
+// ---- a discontinuous (L2) parameter field: H1<p>(H1<p>, L2<0>), reaction-diffusion with a piecewise-constant coefficient
+// (how the physics modules take material parameters, e.g. Parameters<L2<0>> in solid_mechanics.hpp)
+struct ParameterizedDiffusion {
+  double c0;
+  template <typename X, typename U, typename K>
+  auto operator()(double, X, U u, K k) const
+  {
+    auto [uv, du] = u;
+    auto kv       = get<0>(k);
+    return serac::tuple{(c0 + kv) * uv, (kv * kv) * du};
+  }
+};
+ref::Registrar rp("param_diffusion_" TAG, [](mfem::Mesh& mesh, const double* q, int n) {
+  SLIC_ERROR_IF(n != 1, "params: c0");
+  ref::IntegralHolder h;
+  using sig    = H1<p>(H1<p>, L2<0>);
+  Domain d     = ref::domain_for(mesh);
+  h.integral   = std::make_unique<Integral>(MakeDomainIntegral<sig, p + 1, dim>(d, ParameterizedDiffusion{q[0]}, NoQData, {0, 1}));
+  h.num_trials = 2;
+  return h;
+});
+
 // ---- quantity of interest: Functional<double(H1<p,dim>)> (functional_qoi.inl:160-190 builds signature QOI(trials...)) ----
 struct QuadraticQoi {
   double a, b;

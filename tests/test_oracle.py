@@ -310,3 +310,37 @@ def test_boundary_qoi_value(name):
     f = a * (1.0 + Xv[:, 0, :]) * np.einsum("ecq,ecq->eq", val, val) + 0.5 * b * np.einsum("ecjq,ecjq->eq", grad, grad)
     q_E = np.einsum("eq,eq,q->e", f, measure, fo._face_weights(fg, q))
     assert rel_l2(q_E, prob["q_E"]) < 1e-13 and abs(q_E.sum() - prob["value"]) < 1e-13 * abs(prob["value"])
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# discontinuous (L2) parameter fields
+# ----------------------------------------------------------------------------------------------------------------------
+def _l2_names():
+    import glob
+    import os
+    from harness import GOLDEN
+    return sorted(os.path.splitext(os.path.basename(f))[0] for f in glob.glob(os.path.join(GOLDEN, "l2param_*.npz")))
+
+
+@pytest.mark.parametrize("name", _l2_names())
+def test_l2_parameter_field(name):
+    """H1<p>(H1<p>, L2<0>): L2 dofs are lexicographic already (element_restriction.cpp:262-268), order 0 has one node per
+    element; residual and Jacobian actions w.r.t. both arguments"""
+    prob = load_golden(name)
+    geom, p, dim = int(prob["geom"]), int(prob["p"]), int(prob["dim"])
+    q = p + 1
+    table = fo.dof_info(geom, p, prob["native_dofs"])
+    l2_table = np.asarray(prob["l2_native_dofs"]).astype(np.uint64)  # no permutation
+    assert np.array_equal(l2_table, prob["l2_dof_info"] & MASK)
+    mesh_table = prob["mesh_dof_info"] & MASK
+    X_q, J_q = fo.geometric_factors(fo.gather(mesh_table, prob["mesh_nodes"], dim, int(prob["mesh_ordering"]) == 1),
+                                    int(prob["mesh_order"]), q, dim, geom)
+    trials = [fo.gather(table, prob["U"], 1), fo.gather(l2_table, prob["K"], 1)]
+    qf = fo.make_qf("param_diffusion", list(prob["params"]))
+    r_E, _ = fo.evaluation_kernel(qf, trials, [p, 0], X_q, J_q, p, q, dim, geom=geom)
+    assert rel_l2(r_E.ravel(), prob["r_E"]) < 1e-13
+    for wrt, (tab, order, d) in enumerate(((table, p, prob["dU"]), (l2_table, 0, prob["dK"]))):
+        _, blocks = fo.evaluation_kernel(qf, trials, [p, 0], X_q, J_q, p, q, dim, wrt=wrt, geom=geom)
+        dr_E = fo.action_of_gradient_kernel(blocks, fo.gather(tab, d, 1), order, p, q, dim, geom)
+        dr = fo.scatter_add(table, dr_E, np.zeros(len(prob["U"])), 1)
+        assert rel_l2(dr, prob[f"dr{wrt}"]) < 1e-13
