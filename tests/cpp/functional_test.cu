@@ -104,6 +104,10 @@ int run_solid(const std::map<std::string, double>& meta)
   Material m{params[0], params[1], params[2]};
   auto     gn = params[3] != 0.0 ? GeometricNonlinearities::On : GeometricNonlinearities::Off;
   Domain   whole = EntireDomain(P.mesh);
+  if (meta.count("domain_elements")) {  // integral on part of the mesh (Domain::ofElements, functional_with_domain.cpp)
+    whole.entire   = false;
+    whole.elements = read_bin<int>("domain_elements");
+  }
   // SolidMechanics::setMaterial (solid_mechanics.hpp:879-894)
   residual.AddDomainIntegral(Dimension<dim>{}, DependsOn<0, 1, 2>{}, SolidIntegrand<Material>(MaterialStressFunctor<Material>(m, gn)),
                              whole, EmptyQData);

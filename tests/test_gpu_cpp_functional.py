@@ -45,6 +45,10 @@ def export(prob, d, boundary=False):
         native = np.empty(prob["mesh_dof_info"].shape, dtype=np.int32)
         native[:, lex] = (prob["mesh_dof_info"] & MASK).astype(np.int32)
         arrays["mesh_native_dofs"] = native
+    if "domain_elements" in prob:
+        arrays["domain_elements"] = prob["domain_elements"].astype(np.int32)
+        with open(os.path.join(d, "meta.txt"), "a") as f:
+            f.write(f"domain_elements {len(prob['domain_elements'])}\n")
     for k, a in arrays.items():
         np.ascontiguousarray(a).tofile(os.path.join(d, k + ".bin"))
 
@@ -68,7 +72,8 @@ def out(d, name, dtype=np.float64):
     return np.fromfile(os.path.join(d, f"out_{name}.bin"), dtype=dtype)
 
 
-@pytest.mark.parametrize("name", ["solid_neohookean_hex_p2_patch", "solid_neohookean_tet_p2_cart"])
+@pytest.mark.parametrize("name", ["solid_neohookean_hex_p2_patch", "solid_neohookean_tet_p2_cart",
+                                  "solid_neohookean_hex_p2_subdomain"])
 def test_solid_functional(name, tmp_path, cuda):
     prob = load_golden(name)
     d = str(tmp_path)
