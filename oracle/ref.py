@@ -69,6 +69,10 @@ def lib():
             "ref_csr_num_rows": (l, [vp]),
             "ref_csr_pattern": (None, [vp, vp, vp]),
             "ref_csr_assemble": (None, [vp, vp, vp, i, vp, vp]),
+            "ref_eliminate_rows_cols": (None, [i, vp, vp, vp, vp, i, vp]),
+            "ref_eliminate_bc": (None, [i, vp, vp, vp, vp, vp, i, vp, vp]),
+            "ref_cg": (None, [i, vp, vp, vp, vp, vp, i, d, d, i, i, vp, vp, vp, vp]),
+            "ref_spmv": (None, [i, vp, vp, vp, vp, vp]),
             "ref_num_kinds": (i, []),
             "ref_kind_name": (C.c_char_p, [i]),
             "ref_integral_create": (vp, [C.c_char_p, vp, vp, i]),
@@ -324,3 +328,53 @@ class Integral:
 
     def set_qdata(self, data):
         lib().ref_integral_set_qdata(self.h, _p(np.ascontiguousarray(data)))
+
+
+# ---- the reference stack's linear algebra for a Newton step (oracle/ref_solvers.cpp: the reference's own mfem) ----
+def _csr_args(row_ptr, col_ind):
+    rp = np.ascontiguousarray(row_ptr, dtype=np.int32)
+    ci = np.ascontiguousarray(col_ind, dtype=np.int32)
+    return len(rp) - 1, rp, ci
+
+
+def eliminate_rows_cols(row_ptr, col_ind, values, ess):
+    """SparseMatrix::EliminateRowCol(rc, Ae, DIAG_ONE) for every rc in ess -> (A values, Ae values) in A's pattern"""
+    n, rp, ci = _csr_args(row_ptr, col_ind)
+    A = np.array(values, dtype=np.float64)
+    Ae = np.zeros_like(A)
+    e = np.ascontiguousarray(ess, dtype=np.int32)
+    lib().ref_eliminate_rows_cols(n, _p(rp), _p(ci), _p(A), _p(e), len(e), _p(Ae))
+    return A, Ae
+
+
+def eliminate_bc(row_ptr, col_ind, values, values_e, ess, X, B):
+    n, rp, ci = _csr_args(row_ptr, col_ind)
+    A = np.ascontiguousarray(values, dtype=np.float64)
+    Ae = np.ascontiguousarray(values_e, dtype=np.float64)
+    e = np.ascontiguousarray(ess, dtype=np.int32)
+    x = np.ascontiguousarray(X, dtype=np.float64)
+    b = np.array(B, dtype=np.float64)
+    lib().ref_eliminate_bc(n, _p(rp), _p(ci), _p(A), _p(Ae), _p(e), len(e), _p(x), _p(b))
+    return b
+
+
+def cg(row_ptr, col_ind, values, b, jacobi=True, rel_tol=1e-12, abs_tol=0.0, max_iter=1000, x0=None):
+    """mfem::CGSolver (+ OperatorJacobiSmoother) on an mfem::SparseMatrix -> x, info dict"""
+    n, rp, ci = _csr_args(row_ptr, col_ind)
+    A = np.ascontiguousarray(values, dtype=np.float64)
+    bb = np.ascontiguousarray(b, dtype=np.float64)
+    x = np.zeros(n) if x0 is None else np.array(x0, dtype=np.float64)
+    conv, it = C.c_int(0), C.c_int(0)
+    n0, n1 = C.c_double(0), C.c_double(0)
+    lib().ref_cg(n, _p(rp), _p(ci), _p(A), _p(bb), _p(x), int(jacobi), rel_tol, abs_tol, int(max_iter),
+                 int(x0 is not None), C.byref(conv), C.byref(it), C.byref(n0), C.byref(n1))
+    return x, dict(converged=bool(conv.value), final_iter=it.value, initial_norm=n0.value, final_norm=n1.value)
+
+
+def spmv(row_ptr, col_ind, values, x):
+    n, rp, ci = _csr_args(row_ptr, col_ind)
+    A = np.ascontiguousarray(values, dtype=np.float64)
+    xx = np.ascontiguousarray(x, dtype=np.float64)
+    y = np.zeros(n)
+    lib().ref_spmv(n, _p(rp), _p(ci), _p(A), _p(xx), _p(y))
+    return y

@@ -111,7 +111,30 @@ SIGNATURES = {
     "sb_halo_P_finish": (_i, [_vp, _vp, _vp, _vp]),
     "sb_halo_Pt_pack": (_i, [_vp, _vp, _vp]),
     "sb_halo_Pt_finish": (_i, [_vp, _vp, _vp, _vp]),
+    # include/serac_b200_solvers.h
+    "sb_vector_set_subvector": (_i, [_vp, _vp, _i64, _d, _vp]),
+    "sb_vector_copy_subvector": (_i, [_vp, _vp, _vp, _i64, _vp]),
+    "sb_csr_spmv": (_i, [_vp, _vp, _vp, _vp, _vp]),
+    "sb_csr_diagonal": (_i, [_vp, _vp, _vp, _vp]),
+    "sb_csr_eliminate_rows_cols": (_i, [_vp, _vp, _vp, _i64, _vp, _vp]),
+    "sb_csr_eliminate_bc": (_i, [_vp, _vp, _vp, _vp, _i64, _vp, _vp, _vp]),
+    "sb_functional_gradient_operator_create": (_i, [_vp, _i, _i64, _vp, _i64, _pp]),
+    "sb_functional_gradient_operator_destroy": (_i, [_vp]),
+    "sb_functional_gradient_operator_apply": (_i, [_vp, _vp, _vp, _vp]),
+    "sb_cg_create": (_i, [_i64, _pp]),
+    "sb_cg_destroy": (_i, [_vp]),
+    "sb_cg_solve_csr": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "sb_cg_solve_operator": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "sb_jacobi_setup": (_i, [_vp, _vp, _i64, _vp]),
 }
+
+
+class CgOptions(C.Structure):
+    _fields_ = [("rel_tol", _d), ("abs_tol", _d), ("max_iter", _i), ("iterative_mode", _i), ("check_every", _i)]
+
+
+class CgResult(C.Structure):
+    _fields_ = [("converged", _i), ("final_iter", _i), ("initial_norm", _d), ("final_norm", _d)]
 
 _lib = None
 
@@ -453,3 +476,123 @@ class Functional:
             vals = torch.empty(pat.nnz, dtype=torch.float64, device="cuda")
             check(lib().sb_functional_assemble(self.h, wrt, C.byref(hp), _dev_ptr(vals), 0, _stream_ptr()))
         return pat, vals
+
+
+# ---- the Newton step's linear algebra on the device (include/serac_b200_solvers.h) ------------------------------------
+def _ess_tensor(ess, device="cuda"):
+    import torch
+    if isinstance(ess, torch.Tensor):
+        return ess.to(device=device, dtype=torch.int32).contiguous()
+    return torch.as_tensor(np.ascontiguousarray(ess, dtype=np.int32), device=device)
+
+
+def set_subvector(v, ess, value=0.0):
+    """r.SetSubVector(bcs_.allEssentialTrueDofs(), 0.0)  (solid_mechanics.hpp:1129)"""
+    ess = _ess_tensor(ess, v.device)
+    check(lib().sb_vector_set_subvector(_dev_ptr(v), _dev_ptr(ess), ess.numel(), float(value), _stream_ptr()))
+    return v
+
+
+def csr_spmv(pattern, values, x, out=None):
+    import torch
+    if out is None:
+        out = torch.empty(pattern.num_rows, dtype=torch.float64, device=x.device)
+    check(lib().sb_csr_spmv(pattern.h, _dev_ptr(values), _dev_ptr(x), _dev_ptr(out), _stream_ptr()))
+    return out
+
+
+def csr_diagonal(pattern, values):
+    import torch
+    d = torch.empty(pattern.num_rows, dtype=torch.float64, device=values.device)
+    check(lib().sb_csr_diagonal(pattern.h, _dev_ptr(values), _dev_ptr(d), _stream_ptr()))
+    return d
+
+
+def jacobi_setup(diag):
+    import torch
+    dinv = torch.empty_like(diag)
+    check(lib().sb_jacobi_setup(_dev_ptr(diag), _dev_ptr(dinv), diag.numel(), _stream_ptr()))
+    return dinv
+
+
+def eliminate_rows_cols(pattern, values, ess, want_Ae=True):
+    """bcs_.eliminateAllEssentialDofsFromMatrix(*J_) (boundary_condition_manager.hpp:91-94): values is modified in place;
+    returns Ae's values in the same pattern (or None)"""
+    import torch
+    ess = _ess_tensor(ess, values.device)
+    Ae = torch.empty_like(values) if want_Ae else None
+    check(lib().sb_csr_eliminate_rows_cols(pattern.h, _dev_ptr(values), _dev_ptr(ess), ess.numel(), _dev_ptr(Ae),
+                                           _stream_ptr()))
+    return Ae
+
+
+def eliminate_bc(pattern, values, values_e, ess, X, B):
+    """mfem::EliminateBC(A, Ae, ess, X, B) (solid_mechanics.hpp:1756): B is modified in place"""
+    ess = _ess_tensor(ess, values.device)
+    check(lib().sb_csr_eliminate_bc(pattern.h, _dev_ptr(values), _dev_ptr(values_e), _dev_ptr(ess), ess.numel(),
+                                    _dev_ptr(X), _dev_ptr(B), _stream_ptr()))
+    return B
+
+
+class GradientOperator:
+    """Matrix-free [J_ii 0; 0 I]: Gradient::Mult (functional.hpp:556-559) with essential dofs eliminated."""
+
+    def __init__(self, functional, wrt, ess=()):
+        self.F, self.wrt = functional, wrt
+        self.n = functional.trials[wrt].LSize()
+        self._ess = _ess_tensor(ess)
+        h = C.c_void_p()
+        check(lib().sb_functional_gradient_operator_create(functional.h, wrt, self.n, _dev_ptr(self._ess),
+                                                           self._ess.numel(), C.byref(h)))
+        self.h = h
+
+    def __del__(self):
+        try:
+            lib().sb_functional_gradient_operator_destroy(self.h)
+        except Exception:
+            pass
+
+    def Mult(self, x, out=None):
+        import torch
+        if out is None:
+            out = torch.empty(self.n, dtype=torch.float64, device=x.device)
+        check(lib().sb_functional_gradient_operator_apply(self.h, _dev_ptr(x), _dev_ptr(out), _stream_ptr()))
+        return out
+
+
+class CGSolver:
+    """Mirror of mfem::CGSolver (mfem/linalg/solvers.cpp:719-897) as serac::buildLinearSolver configures it."""
+
+    def __init__(self, n, rel_tol=1e-12, abs_tol=0.0, max_iter=1000, check_every=1):
+        self.n = n
+        self.opt = CgOptions(rel_tol, abs_tol, max_iter, 0, check_every)
+        h = C.c_void_p()
+        check(lib().sb_cg_create(n, C.byref(h)))
+        self.h = h
+        self.result = CgResult()
+
+    def __del__(self):
+        try:
+            lib().sb_cg_destroy(self.h)
+        except Exception:
+            pass
+
+    def _finish(self):
+        r = self.result
+        return dict(converged=bool(r.converged), final_iter=r.final_iter, initial_norm=r.initial_norm,
+                    final_norm=r.final_norm)
+
+    def Mult(self, operator, b, x=None, dinv=None, values=None, iterative_mode=False):
+        """operator: a CsrPattern (with `values`) or a GradientOperator.  -> x, info"""
+        import torch
+        if x is None:
+            x = torch.zeros(self.n, dtype=torch.float64, device=b.device)
+        self.opt.iterative_mode = int(iterative_mode)
+        if isinstance(operator, CsrPattern):
+            check(lib().sb_cg_solve_csr(self.h, operator.h, _dev_ptr(values), _dev_ptr(dinv), _dev_ptr(b), _dev_ptr(x),
+                                        C.byref(self.opt), C.byref(self.result), _stream_ptr()))
+        else:
+            apply = C.cast(lib().sb_functional_gradient_operator_apply, C.c_void_p)
+            check(lib().sb_cg_solve_operator(self.h, apply, operator.h, _dev_ptr(dinv), _dev_ptr(b), _dev_ptr(x),
+                                             C.byref(self.opt), C.byref(self.result), _stream_ptr()))
+        return x, self._finish()

@@ -14,7 +14,7 @@ KIND_TO_NAME = {5: "hex", 3: "quad", 4: "tet", 2: "tri"}
 def golden_names():
     """small fixtures with full reference outputs (the config_* files are full-size inputs + sampled outputs)"""
     names = sorted(os.path.splitext(os.path.basename(f))[0] for f in glob.glob(os.path.join(GOLDEN, "*.npz")))
-    return [n for n in names if not n.startswith(("config_", "bdr_", "multi_", "qoi_", "bqoi_", "l2param_"))]
+    return [n for n in names if not n.startswith(("config_", "bdr_", "multi_", "qoi_", "bqoi_", "l2param_", "krylov_", "newton_"))]
 
 
 def multifield_golden_names():
@@ -25,6 +25,11 @@ def multifield_golden_names():
 def boundary_golden_names():
     """boundary-integral fixtures (oracle/make_golden.py BOUNDARY_FIXTURES)"""
     return sorted(os.path.splitext(os.path.basename(f))[0] for f in glob.glob(os.path.join(GOLDEN, "bdr_*.npz")))
+
+
+def krylov_golden_names():
+    """Newton-step linear-algebra fixtures (oracle/make_golden_krylov.py): the reference's mfem on reference Jacobians"""
+    return sorted(os.path.splitext(os.path.basename(f))[0] for f in glob.glob(os.path.join(GOLDEN, "krylov_*.npz")))
 
 
 def load_golden(name):

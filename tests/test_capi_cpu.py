@@ -1,4 +1,4 @@
-"""CPU: the C-ABI library loads, exports every symbol include/serac_b200.h declares, and its host-side (no GPU needed)
+"""CPU: the C-ABI library loads, exports every symbol include/*.h declares, and its host-side (no GPU needed)
 entry points agree with the oracle.  No compute calls here."""
 import ctypes as C
 import os
@@ -13,9 +13,14 @@ from serac_b200 import capi
 
 
 def header_symbols():
-    text = open(os.path.join(ROOT, "include", "serac_b200.h")).read()
-    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
-    return sorted(set(re.findall(r"\b(sb_[a-zA-Z0-9_]+)\s*\(", text)))
+    import glob
+    syms = set()
+    for path in sorted(glob.glob(os.path.join(ROOT, "include", "*.h"))):
+        text = open(path).read()
+        text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+        text = re.sub(r"typedef[^;{]*\(\*\s*sb_[a-zA-Z0-9_]+\)[^;]*;", "", text)  # function-pointer typedefs are not symbols
+        syms |= set(re.findall(r"\b(sb_[a-zA-Z0-9_]+)\s*\(", text))
+    return sorted(syms)
 
 
 def test_library_exports_every_declared_symbol():

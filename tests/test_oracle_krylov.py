@@ -1,0 +1,77 @@
+"""CPU: the numpy restatement of the Newton-step linear algebra (oracle/krylov_oracle.py) against the reference's own
+mfem (tests/golden/krylov_*.npz, written by oracle/make_golden_krylov.py; live against oracle/_ref when it is built)."""
+import numpy as np
+import pytest
+
+from harness import krylov_golden_names, load_golden, rel_l2
+from oracle import krylov_oracle as ko
+
+
+@pytest.fixture(scope="module", params=krylov_golden_names())
+def case(request):
+    g = load_golden(request.param)
+    src = load_golden(g["source"])
+    g["row_ptr"], g["col_ind"], g["values"] = src["row_ptr"].astype(np.int64), src["col_ind"].astype(np.int64), src["values"]
+    return g
+
+
+def test_fixtures_exist():
+    assert len(krylov_golden_names()) >= 4
+
+
+def test_elimination_is_exact(case):
+    """pure selection / subtraction of 0 or 1: bit-exact"""
+    A, Ae = ko.eliminate_rows_cols(case["row_ptr"], case["col_ind"], case["values"], case["ess"])
+    assert np.array_equal(A, case["values_elim"])
+    assert np.array_equal(Ae, case["values_e"])
+    assert np.array_equal(A + Ae, case["values"])  # A_before = A_after + Ae entry by entry
+
+
+def test_eliminate_bc_and_spmv(case):
+    B = ko.eliminate_bc(case["row_ptr"], case["col_ind"], case["values_elim"], case["values_e"], case["ess"], case["X"],
+                        case["B"])
+    assert rel_l2(B, case["B_bc"]) < 1e-14
+    assert np.array_equal(B[case["ess"]], case["X"][case["ess"]])  # diagonal is exactly 1 there
+    assert rel_l2(ko.spmv(case["row_ptr"], case["col_ind"], case["values_elim"], case["V"]), case["AV"]) < 1e-14
+
+
+def _solve(case, **kw):
+    rp, ci, A = case["row_ptr"], case["col_ind"], case["values_elim"]
+    dinv = ko.jacobi_dinv(ko.diagonal(rp, ci, A)) if case["jacobi"] else None
+    return ko.cg(lambda v: ko.spmv(rp, ci, A, v), case["B_bc"], dinv=dinv, rel_tol=case["rel_tol"],
+                 abs_tol=case["abs_tol"], **kw)
+
+
+def test_cg_matches_mfem(case):
+    x, info = _solve(case, max_iter=case["max_iter"])
+    assert info["converged"] and case["cg_converged"]
+    assert abs(info["final_iter"] - case["cg_final_iter"]) <= 1  # summation order may move the last step
+    assert abs(info["initial_norm"] / case["cg_initial_norm"] - 1) < 1e-12
+    assert rel_l2(x, case["x"]) < 1e-7
+    # the stopping rule itself: (B r, r) <= rel_tol^2 (B r0, r0)
+    assert info["final_norm"] <= case["rel_tol"] * info["initial_norm"] * (1 + 1e-12)
+
+
+def test_cg_max_iter_exit(case):
+    """solvers.cpp:842-845: not converged, final_iter = max_iter, x = the 5th iterate"""
+    x, info = _solve(case, max_iter=5)
+    assert not info["converged"] and info["final_iter"] == 5 == case["cg5_final_iter"] and not case["cg5_converged"]
+    assert rel_l2(x, case["x_maxiter5"]) < 1e-12
+    assert abs(info["final_norm"] / case["cg5_final_norm"] - 1) < 1e-10
+
+
+def test_cg_iterative_mode(case):
+    x, info = _solve(case, max_iter=case["max_iter"], x0=case["X"])
+    assert info["converged"] and abs(info["final_iter"] - case["cgg_final_iter"]) <= 1
+    assert rel_l2(x, case["x_guess"]) < 1e-7
+
+
+def test_live_reference_agrees_with_fixture(case):
+    from oracle import ref
+    if not ref.available():
+        pytest.skip("oracle/_ref not built")
+    A, Ae = ref.eliminate_rows_cols(case["row_ptr"], case["col_ind"], case["values"], case["ess"])
+    assert np.array_equal(A, case["values_elim"]) and np.array_equal(Ae, case["values_e"])
+    x, info = ref.cg(case["row_ptr"], case["col_ind"], A, case["B_bc"], jacobi=bool(case["jacobi"]),
+                     rel_tol=case["rel_tol"], max_iter=case["max_iter"])
+    assert info["final_iter"] == case["cg_final_iter"] and np.array_equal(x, case["x"])
