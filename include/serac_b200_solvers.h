@@ -33,6 +33,12 @@ int sb_vector_set_subvector(double* v_dev, const int* dofs_dev, int64_t num_dofs
 /* v[dofs[i]] = src[dofs[i]]  (the essential entries of the solution vector, solid_mechanics.hpp:1757-1760) */
 int sb_vector_copy_subvector(double* v_dev, const double* src_dev, const int* dofs_dev, int64_t num_dofs, void* stream);
 
+/* y += a x  (mfem::Vector::Add(a, x): the Newton update u -= du, solid_mechanics.hpp / equation_solver.cpp) */
+int sb_vector_axpy(double* y_dev, double a, const double* x_dev, int64_t n, void* stream);
+/* *result_host = (x, y), deterministic (fixed grid, fixed summation order); synchronises `stream` (mfem::Vector::operator*,
+ * Norml2 = sqrt of it: the Newton driver's convergence test) */
+int sb_vector_dot(const double* x_dev, const double* y_dev, int64_t n, double* result_host, void* stream);
+
 /* y = A x for the CSR triple (pattern object + values): one warp per row, lanes stride over the row's nonzeros
  * (coalesced col_ind / values, x gathered through L2), fixed-order shuffle reduction.  HBM-bound: 12 B per nonzero. */
 int sb_csr_spmv(sb_csr_t A, const double* values_dev, const double* x_dev, double* y_dev, void* stream);

@@ -114,6 +114,8 @@ SIGNATURES = {
     # include/serac_b200_solvers.h
     "sb_vector_set_subvector": (_i, [_vp, _vp, _i64, _d, _vp]),
     "sb_vector_copy_subvector": (_i, [_vp, _vp, _vp, _i64, _vp]),
+    "sb_vector_axpy": (_i, [_vp, _d, _vp, _i64, _vp]),
+    "sb_vector_dot": (_i, [_vp, _vp, _i64, C.POINTER(_d), _vp]),
     "sb_csr_spmv": (_i, [_vp, _vp, _vp, _vp, _vp]),
     "sb_csr_diagonal": (_i, [_vp, _vp, _vp, _vp]),
     "sb_csr_eliminate_rows_cols": (_i, [_vp, _vp, _vp, _i64, _vp, _vp]),
@@ -491,6 +493,19 @@ def set_subvector(v, ess, value=0.0):
     ess = _ess_tensor(ess, v.device)
     check(lib().sb_vector_set_subvector(_dev_ptr(v), _dev_ptr(ess), ess.numel(), float(value), _stream_ptr()))
     return v
+
+
+def vector_axpy(y, a, x):
+    """y += a x on the device (the Newton update)"""
+    check(lib().sb_vector_axpy(_dev_ptr(y), float(a), _dev_ptr(x), y.numel(), _stream_ptr()))
+    return y
+
+
+def vector_dot(x, y):
+    """(x, y) with the library's deterministic reduction"""
+    out = C.c_double(0.0)
+    check(lib().sb_vector_dot(_dev_ptr(x), _dev_ptr(y), x.numel(), C.byref(out), _stream_ptr()))
+    return out.value
 
 
 def csr_spmv(pattern, values, x, out=None):

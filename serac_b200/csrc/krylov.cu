@@ -137,6 +137,26 @@ __global__ void reciprocal_kernel(const double* __restrict__ d, double* __restri
     dinv[i] = 1.0 / d[i];
 }
 
+__global__ void axpy_kernel(double* __restrict__ y, double a, const double* __restrict__ x, int64_t n)
+{
+  for (int64_t i = blockIdx.x * int64_t(blockDim.x) + threadIdx.x; i < n; i += int64_t(gridDim.x) * blockDim.x)
+    y[i] = y[i] + a * x[i];
+}
+
+/// out[0] = (x, y); out[1] is the ticket counter (zero before and after)
+__global__ void __launch_bounds__(kThreads) dot_kernel(const double* __restrict__ x, const double* __restrict__ y, int64_t n,
+                                                       double* __restrict__ out, double* __restrict__ partials,
+                                                       unsigned int* __restrict__ ticket)
+{
+  __shared__ double smem[kWarpsPerCta];
+  double            acc = 0.0;
+  for (int64_t i = blockIdx.x * int64_t(blockDim.x) + threadIdx.x; i < n; i += int64_t(gridDim.x) * blockDim.x)
+    acc += x[i] * y[i];
+  const double part  = block_sum(acc, smem);
+  double       total = 0.0;
+  if (grid_sum_last_block(part, partials, ticket, smem, &total) && threadIdx.x == 0) *out = total;
+}
+
 /// y = x with the marked entries zeroed
 __global__ void masked_copy_kernel(const double* __restrict__ x, const unsigned char* __restrict__ mark,
                                    double* __restrict__ y, int64_t n)
@@ -498,6 +518,43 @@ extern "C" int sb_vector_copy_subvector(double* v_dev, const double* src_dev, co
   sb_count_launch();
   SB_CHECK_CUDA(cudaGetLastError());
   return SB_OK;
+}
+
+extern "C" int sb_vector_axpy(double* y_dev, double a, const double* x_dev, int64_t n, void* stream)
+{
+  SB_REQUIRE(n >= 0, "sb_vector_axpy: negative size");
+  if (n == 0) return SB_OK;
+  SB_REQUIRE(y_dev && x_dev, "sb_vector_axpy: null pointer");
+  axpy_kernel<<<reducing_grid(n, kThreads), kThreads, 0, as_stream(stream)>>>(y_dev, a, x_dev, n);
+  sb_count_launch();
+  SB_CHECK_CUDA(cudaGetLastError());
+  return SB_OK;
+}
+
+extern "C" int sb_vector_dot(const double* x_dev, const double* y_dev, int64_t n, double* result_host, void* stream)
+{
+  SB_REQUIRE(n >= 0 && result_host, "sb_vector_dot: bad argument");
+  *result_host = 0.0;
+  if (n == 0) return SB_OK;
+  SB_REQUIRE(x_dev && y_dev, "sb_vector_dot: null pointer");
+  cudaStream_t s = as_stream(stream);
+  // scratch of this call: [0] result, [1] ticket (as 8 bytes), [2 ...] per-block partials
+  double* scratch = nullptr;
+  if (int e = dev_new(&scratch, size_t(kMaxPartials) + 2)) return e;
+  int rc = SB_OK;
+  if (cudaMemsetAsync(scratch, 0, 2 * sizeof(double), s) != cudaSuccess) rc = SB_ERR_CUDA;
+  if (!rc) {
+    dot_kernel<<<reducing_grid(n, kThreads), kThreads, 0, s>>>(x_dev, y_dev, n, scratch, scratch + 2,
+                                                               reinterpret_cast<unsigned int*>(scratch + 1));
+    sb_count_launch();
+    if (cudaGetLastError() != cudaSuccess ||
+        cudaMemcpyAsync(result_host, scratch, sizeof(double), cudaMemcpyDeviceToHost, s) != cudaSuccess ||
+        cudaStreamSynchronize(s) != cudaSuccess)
+      rc = SB_ERR_CUDA;
+  }
+  if (rc) sb::set_error("sb_vector_dot: CUDA failure");
+  cudaFree(scratch);
+  return rc;
 }
 
 extern "C" int sb_jacobi_setup(const double* diag_dev, double* diag_inv_dev, int64_t n, void* stream)

@@ -364,16 +364,32 @@ class Functional<test(trials...)> {
     /// assemble(Gradient&) (functional.hpp:569-667) up to the local CSR triple
     friend std::unique_ptr<CsrMatrix> assemble(Gradient& g) { return g.assemble_local(); }
 
+    /// the sparsity pattern of d(test)/d(this argument), created on first use and owned by the Functional (the
+    /// reference's lookup tables, functional.hpp:571-583)
+    sb_csr_t pattern()
+    {
+      Functional& f = form_;
+      const int   w = which_argument_;
+      if (f.csr_.size() < size_t(num_trial_spaces)) f.csr_.resize(size_t(num_trial_spaces), nullptr);
+      if (!f.csr_[size_t(w)])
+        SERAC_B200_CHECK(sb_csr_create_layout(f.G_test_, f.G_trial_[size_t(w)], 1, &f.csr_[size_t(w)]));
+      return f.csr_[size_t(w)];
+    }
+    /// the values of the assembled matrix into a device array of sb_csr_nnz(pattern) doubles (serac_b200/solvers.hpp)
+    void assemble_values(sb_csr_t A, double* values_dev)
+    {
+      SERAC_B200_CHECK(sb_functional_assemble(form_.F_, which_argument_, &A, values_dev, 0, nullptr));
+    }
+    sb_functional_t functional_handle() const { return form_.F_; }
+    int             argument() const { return which_argument_; }
+
     std::unique_ptr<CsrMatrix> assemble_local()
     {
       Gradient&   g = *this;
       Functional& f = g.form_;
       const int   w = g.which_argument_;
-      if (f.csr_.size() < size_t(num_trial_spaces)) f.csr_.resize(size_t(num_trial_spaces), nullptr);
-      if (!f.csr_[size_t(w)])
-        SERAC_B200_CHECK(sb_csr_create_layout(f.G_test_, f.G_trial_[size_t(w)], 1, &f.csr_[size_t(w)]));
-      sb_csr_t A   = f.csr_[size_t(w)];
-      auto     out = std::make_unique<CsrMatrix>();
+      sb_csr_t    A   = pattern();
+      auto        out = std::make_unique<CsrMatrix>();
       out->num_rows = sb_csr_num_rows(A);
       out->num_cols = g.Width();
       out->row_ptr.resize(size_t(out->num_rows) + 1);

@@ -9,6 +9,9 @@
 //     pressure  same signature, ONE boundary integral: follower pressure (hex mesh, quadrilateral faces)
 //     user      H1<2>(H1<2>) with a q-function defined in THIS file: checked here against finite differences and the
 //               assembled matrix (check_gradient.hpp:16-90)
+//     newton    the solid problem solved the way SolidMechanics::quasiStaticSolve does: Newton on the residual with the
+//               essential rows zeroed, Jacobian = assemble + EliminateRowsCols, CG + Jacobi -- every step on the device;
+//               once with the assembled matrix and once matrix-free over Gradient::Mult
 //     qoi       Functional<double(H1<2,3>)> with a q-function defined in this file: value, directional derivative, gradient
 // Directory layout: <name>.bin raw little-endian arrays (int32 / float64), meta.txt "key value" lines.
 #include <cmath>
@@ -18,6 +21,7 @@
 #include <string>
 
 #include "serac_b200/functional.hpp"
+#include "serac_b200/solvers.hpp"
 
 using namespace serac;
 
@@ -125,6 +129,68 @@ int run_solid(const std::map<std::string, double>& meta)
   // mass matrix action: derivative w.r.t. the acceleration
   auto [r2, drda] = residual(0.0, S, U, differentiate_wrt(A));
   write_bin("dr_da", drda(dU).to_host());
+  return 0;
+}
+
+/// One quasi-static solve (solid_mechanics.hpp:1120-1140 residual / Jacobian lambdas, Newton + CG/Jacobi of
+/// equation_solver.cpp) without leaving the GPU.  Inputs beyond the solid case: ess.bin (essential dofs), meta
+/// force_scale / rel_tol / max_iter / newton_rel / newton_max.  matrix_free: CG over Gradient::Mult instead of the matrix.
+int run_newton(const std::map<std::string, double>& meta, bool matrix_free)
+{
+  Problem P = load_problem(meta, false);
+  auto    params = read_bin<double>("params");
+  SolidFunctional residual(&P.space, {&P.shape_space, &P.space, &P.space});
+  using Material = solid_mechanics::NeoHookean;
+  Material m{params[0], params[1], params[2]};
+  auto     gn = params[3] != 0.0 ? GeometricNonlinearities::On : GeometricNonlinearities::Off;
+  Domain   whole = EntireDomain(P.mesh);
+  residual.AddDomainIntegral(Dimension<dim>{}, DependsOn<0, 1, 2>{}, SolidIntegrand<Material>(MaterialStressFunctor<Material>(m, gn)),
+                             whole, EmptyQData);
+  DofList ess(read_bin<int>("ess"));
+  Vector  S(read_bin<double>("S")), A(read_bin<double>("A"));
+  {
+    auto a = A.to_host();
+    for (auto& v : a) v *= meta.at("force_scale");
+    A.set(a.data());
+  }
+  const int64_t n = P.space.GetVSize();
+  Vector        u(n), du(n), rhs(n);
+  u = 0.0;
+  CGSolver cg;
+  cg.SetRelTol(meta.at("rel_tol"));
+  cg.SetAbsTol(0.0);
+  cg.SetMaxIter(int(meta.at("max_iter")));
+  std::vector<double> norms, cg_iters;
+  for (int it = 0; it < int(meta.at("newton_max")); it++) {
+    auto [r, drdu] = residual(0.0, S, differentiate_wrt(u), A);
+    rhs            = r;
+    SetSubVector(rhs, ess, 0.0);  // r.SetSubVector(bcs_.allEssentialTrueDofs(), 0.0)
+    norms.push_back(Norml2(rhs));
+    if (norms.back() < meta.at("newton_rel") * norms.front()) break;
+    auto J   = assemble_on_device(drdu);  // J_ = assemble(drdu)
+    auto J_e = J->EliminateRowsCols(ess);  // J_e_ = bcs_.eliminateAllEssentialDofsFromMatrix(*J_)
+    JacobiSmoother   prec(*J);
+    GradientOperator op(drdu, ess);
+    if (matrix_free)
+      cg.SetOperator(op);
+    else
+      cg.SetOperator(*J);
+    cg.SetPreconditioner(prec);
+    cg.Mult(rhs, du);
+    if (!cg.GetConverged()) {
+      std::fprintf(stderr, "CG did not converge in Newton step %d\n", it);
+      return 1;
+    }
+    cg_iters.push_back(double(cg.GetNumIterations()));
+    Add(u, -1.0, du);  // u -= du
+  }
+  const std::string tag = matrix_free ? "_mf" : "";
+  write_bin("u" + tag, u.to_host());
+  write_bin("residual_norms" + tag, norms);
+  write_bin("cg_iterations" + tag, cg_iters);
+  std::printf("newton%s: %zu residual evaluations, last |r| = %.3e, CG iterations", tag.c_str(), norms.size(), norms.back());
+  for (double c : cg_iters) std::printf(" %d", int(c));
+  std::printf("\n");
   return 0;
 }
 
@@ -323,6 +389,7 @@ int main(int argc, char** argv)
   if (which == "j2") rc = run_j2(meta);
   if (which == "pressure") rc = run_pressure(meta);
   if (which == "user") rc = run_user(meta);
+  if (which == "newton") rc = run_newton(meta, false) || run_newton(meta, true);
   if (which == "qoi") rc = run_qoi(meta);
   if (which == "boundary_qoi") rc = run_boundary_qoi(meta);
   std::printf("launches: %lld\n", sb_launch_count());

