@@ -100,6 +100,20 @@ int sb_cg_solve_csr(sb_cg_t S, sb_csr_t A, const double* values_dev, const doubl
 int sb_cg_solve_operator(sb_cg_t S, sb_operator_apply apply, void* ctx, const double* diag_inv_dev,
                          const double* b_dev, double* x_dev, const sb_cg_options* opt, sb_cg_result* result,
                          void* stream);
+/* mfem::GMRESSolver (solvers.cpp:981-1165): restarted GMRES(kdim) with modified Gram-Schmidt and a left Jacobi
+ * preconditioner -- serac's default linear solver for SolidMechanics and HeatTransfer (solid_mechanics.hpp:50-57,
+ * heat_transfer.hpp:34-38; kdim 50 = mfem's default).  Same iteration, stopping rule (||M r|| <= max(rel_tol ||M r0||,
+ * abs_tol)), restart and exits.  The Krylov basis ((kdim + 1) n doubles) and the Hessenberg column under construction
+ * live on the device; the host reads one finished column per iteration for the Givens rotations, as the reference does.
+ * Options / result: the sb_cg_* structs (check_every is ignored; initial_norm / final_norm are ||M r||). */
+typedef struct sb_gmres_s* sb_gmres_t;
+int sb_gmres_create(int64_t n, int kdim, sb_gmres_t* out);
+int sb_gmres_destroy(sb_gmres_t G);
+int sb_gmres_solve_csr(sb_gmres_t G, sb_csr_t A, const double* values_dev, const double* diag_inv_dev,
+                       const double* b_dev, double* x_dev, const sb_cg_options* opt, sb_cg_result* result, void* stream);
+int sb_gmres_solve_operator(sb_gmres_t G, sb_operator_apply apply, void* ctx, const double* diag_inv_dev,
+                            const double* b_dev, double* x_dev, const sb_cg_options* opt, sb_cg_result* result,
+                            void* stream);
 /* dinv[i] = 1 / diag[i]  (OperatorJacobiSmoother::Setup with damping 1) */
 int sb_jacobi_setup(const double* diag_dev, double* diag_inv_dev, int64_t n, void* stream);
 

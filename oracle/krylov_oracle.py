@@ -8,6 +8,7 @@ product package.
   eliminate_bc         HypreParMatrix::EliminateBC, mfem/linalg/hypre.cpp:2422-2478
   jacobi_dinv          OperatorJacobiSmoother::Setup (dinv = damping / diag), mfem/linalg/solvers.cpp:262-302
   cg                   CGSolver::Mult, mfem/linalg/solvers.cpp:719-897
+  gmres                GMRESSolver::Mult, mfem/linalg/solvers.cpp:981-1165 (+ plane rotations / Update, :931-980)
 """
 import numpy as np
 
@@ -122,4 +123,87 @@ def cg(apply_A, b, dinv=None, rel_tol=1e-12, abs_tol=0.0, max_iter=1000, x0=None
             break
         nom = betanom  # :872
     info["final_norm"] = np.sqrt(betanom)  # :894
+    return x, info
+
+
+def _generate_rotation(dx, dy):  # solvers.cpp:931-951
+    if dy == 0.0:
+        return 1.0, 0.0
+    if abs(dy) > abs(dx):
+        t = dx / dy
+        sn = 1.0 / np.sqrt(1.0 + t * t)
+        return t * sn, sn
+    t = dy / dx
+    cs = 1.0 / np.sqrt(1.0 + t * t)
+    return cs, t * cs
+
+
+def _apply_rotation(dx, dy, cs, sn):  # :953-958
+    return cs * dx + sn * dy, -sn * dx + cs * dy
+
+
+def _update(x, k, H, s, v):  # :960-980
+    y = s[:k + 1].copy()
+    for i in range(k, -1, -1):
+        y[i] /= H[i, i]
+        for j in range(i - 1, -1, -1):
+            y[j] -= H[j, i] * y[i]
+    for i in range(k + 1):
+        x = x + y[i] * v[i]
+    return x
+
+
+def gmres(apply_A, b, dinv=None, kdim=50, rel_tol=1e-12, abs_tol=0.0, max_iter=1000, x0=None):
+    """GMRESSolver::Mult, statement by statement (solvers.cpp:981-1165): restarted GMRES(kdim), modified Gram-Schmidt,
+    left preconditioner.  Returns x, dict(converged, final_iter, initial_norm, final_norm)."""
+    b = np.asarray(b, dtype=np.float64)
+    m = kdim
+    M = (lambda v: dinv * v) if dinv is not None else (lambda v: v)
+    if x0 is not None:  # :995-1026
+        x = np.array(x0, dtype=np.float64)
+        r = M(b - apply_A(x))
+    else:
+        x = np.zeros_like(b)
+        r = M(b.copy())
+    beta = float(np.sqrt(r @ r))  # :1027
+    info = dict(converged=False, final_iter=0, initial_norm=beta, final_norm=0.0)
+    final_norm = max(rel_tol * beta, abs_tol)  # :1030
+    if beta <= final_norm:  # :1032-1039
+        info.update(converged=True, final_norm=beta)
+        return x, info
+    H = np.zeros((m + 1, m))
+    cs, sn = np.zeros(m + 1), np.zeros(m + 1)
+    v = [None] * (m + 1)
+    j = 1
+    while j <= max_iter:  # :1053
+        v[0] = r / beta  # :1056
+        s = np.zeros(m + 1)
+        s[0] = beta
+        i = 0
+        while i < m and j <= max_iter:  # :1059
+            w = M(apply_A(v[i]))  # :1061-1069
+            for k in range(i + 1):  # :1071-1075
+                H[k, i] = float(w @ v[k])
+                w = w - H[k, i] * v[k]
+            H[i + 1, i] = float(np.sqrt(w @ w))  # :1077
+            v[i + 1] = w / H[i + 1, i]  # :1080
+            for k in range(i):  # :1082-1085
+                H[k, i], H[k + 1, i] = _apply_rotation(H[k, i], H[k + 1, i], cs[k], sn[k])
+            cs[i], sn[i] = _generate_rotation(H[i, i], H[i + 1, i])
+            H[i, i], H[i + 1, i] = _apply_rotation(H[i, i], H[i + 1, i], cs[i], sn[i])
+            s[i], s[i + 1] = _apply_rotation(s[i], s[i + 1], cs[i], sn[i])
+            resid = abs(s[i + 1])  # :1091
+            if resid <= final_norm:  # :1094-1101
+                x = _update(x, i, H, s, v)
+                info.update(converged=True, final_iter=j, final_norm=resid)
+                return x, info
+            i += 1
+            j += 1
+        x = _update(x, i - 1, H, s, v)  # :1117
+        r = M(b - apply_A(x))  # :1119-1128
+        beta = float(np.sqrt(r @ r))
+        if beta <= final_norm:  # :1131-1137
+            info.update(converged=True, final_iter=j, final_norm=beta)
+            return x, info
+    info.update(converged=False, final_iter=max_iter, final_norm=beta)  # :1140-1142
     return x, info

@@ -73,6 +73,7 @@ def lib():
             "ref_eliminate_bc": (None, [i, vp, vp, vp, vp, vp, i, vp, vp]),
             "ref_cg": (None, [i, vp, vp, vp, vp, vp, i, d, d, i, i, vp, vp, vp, vp]),
             "ref_spmv": (None, [i, vp, vp, vp, vp, vp]),
+            "ref_gmres": (None, [i, vp, vp, vp, vp, vp, i, i, d, d, i, i, vp, vp, vp, vp]),
             "ref_num_kinds": (i, []),
             "ref_kind_name": (C.c_char_p, [i]),
             "ref_integral_create": (vp, [C.c_char_p, vp, vp, i]),
@@ -378,3 +379,16 @@ def spmv(row_ptr, col_ind, values, x):
     y = np.zeros(n)
     lib().ref_spmv(n, _p(rp), _p(ci), _p(A), _p(xx), _p(y))
     return y
+
+
+def gmres(row_ptr, col_ind, values, b, jacobi=True, kdim=50, rel_tol=1e-12, abs_tol=0.0, max_iter=1000, x0=None):
+    """mfem::GMRESSolver (+ OperatorJacobiSmoother) on an mfem::SparseMatrix -> x, info dict"""
+    n, rp, ci = _csr_args(row_ptr, col_ind)
+    A = np.ascontiguousarray(values, dtype=np.float64)
+    bb = np.ascontiguousarray(b, dtype=np.float64)
+    x = np.zeros(n) if x0 is None else np.array(x0, dtype=np.float64)
+    conv, it = C.c_int(0), C.c_int(0)
+    n0, n1 = C.c_double(0), C.c_double(0)
+    lib().ref_gmres(n, _p(rp), _p(ci), _p(A), _p(bb), _p(x), int(jacobi), int(kdim), rel_tol, abs_tol, int(max_iter),
+                    int(x0 is not None), C.byref(conv), C.byref(it), C.byref(n0), C.byref(n1))
+    return x, dict(converged=bool(conv.value), final_iter=it.value, initial_norm=n0.value, final_norm=n1.value)

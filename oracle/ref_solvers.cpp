@@ -88,6 +88,32 @@ void ref_cg(int n, const int* row_ptr, const int* col_ind, const double* values,
   *final_norm   = cg.GetFinalNorm();
 }
 
+/// mfem::GMRESSolver::Mult (solvers.cpp:981-1165), restart length kdim, optional OperatorJacobiSmoother
+void ref_gmres(int n, const int* row_ptr, const int* col_ind, const double* values, const double* b, double* x, int jacobi,
+               int kdim, double rel_tol, double abs_tol, int max_iter, int iterative_mode, int* converged, int* final_iter,
+               double* initial_norm, double* final_norm)
+{
+  std::unique_ptr<mfem::SparseMatrix> A(make_matrix(n, row_ptr, col_ind, values));
+  mfem::Vector                        B(const_cast<double*>(b), n), X(x, n), diag(n);
+  A->GetDiag(diag);
+  mfem::Array<int>             no_ess;
+  mfem::OperatorJacobiSmoother prec(diag, no_ess, 1.0);
+  mfem::GMRESSolver            gmres;
+  gmres.SetOperator(*A);
+  if (jacobi) gmres.SetPreconditioner(prec);
+  gmres.SetKDim(kdim);
+  gmres.SetRelTol(rel_tol);
+  gmres.SetAbsTol(abs_tol);
+  gmres.SetMaxIter(max_iter);
+  gmres.SetPrintLevel(-1);
+  gmres.iterative_mode = iterative_mode != 0;
+  gmres.Mult(B, X);
+  *converged    = gmres.GetConverged() ? 1 : 0;
+  *final_iter   = gmres.GetNumIterations();
+  *initial_norm = gmres.GetInitialNorm();
+  *final_norm   = gmres.GetFinalNorm();
+}
+
 /// y = A x with mfem::SparseMatrix::Mult
 void ref_spmv(int n, const int* row_ptr, const int* col_ind, const double* values, const double* x, double* y)
 {

@@ -128,6 +128,10 @@ SIGNATURES = {
     "sb_cg_solve_csr": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "sb_cg_solve_operator": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "sb_jacobi_setup": (_i, [_vp, _vp, _i64, _vp]),
+    "sb_gmres_create": (_i, [_i64, _i, _pp]),
+    "sb_gmres_destroy": (_i, [_vp]),
+    "sb_gmres_solve_csr": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "sb_gmres_solve_operator": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
 }
 
 
@@ -611,3 +615,39 @@ class CGSolver:
             check(lib().sb_cg_solve_operator(self.h, apply, operator.h, _dev_ptr(dinv), _dev_ptr(b), _dev_ptr(x),
                                              C.byref(self.opt), C.byref(self.result), _stream_ptr()))
         return x, self._finish()
+
+
+class GMRESSolver:
+    """Mirror of mfem::GMRESSolver (mfem/linalg/solvers.cpp:981-1165): serac's default linear solver
+    (solid_mechanics.hpp:50-57, heat_transfer.hpp:34-38), restart length kdim (mfem default 50)."""
+
+    def __init__(self, n, kdim=50, rel_tol=1e-12, abs_tol=0.0, max_iter=1000):
+        self.n = n
+        self.opt = CgOptions(rel_tol, abs_tol, max_iter, 0, 1)
+        h = C.c_void_p()
+        check(lib().sb_gmres_create(n, kdim, C.byref(h)))
+        self.h = h
+        self.result = CgResult()
+
+    def __del__(self):
+        try:
+            lib().sb_gmres_destroy(self.h)
+        except Exception:
+            pass
+
+    def Mult(self, operator, b, x=None, dinv=None, values=None, iterative_mode=False):
+        """operator: a CsrPattern (with `values`) or a GradientOperator.  -> x, info"""
+        import torch
+        if x is None:
+            x = torch.zeros(self.n, dtype=torch.float64, device=b.device)
+        self.opt.iterative_mode = int(iterative_mode)
+        if isinstance(operator, CsrPattern):
+            check(lib().sb_gmres_solve_csr(self.h, operator.h, _dev_ptr(values), _dev_ptr(dinv), _dev_ptr(b), _dev_ptr(x),
+                                           C.byref(self.opt), C.byref(self.result), _stream_ptr()))
+        else:
+            apply = C.cast(lib().sb_functional_gradient_operator_apply, C.c_void_p)
+            check(lib().sb_gmres_solve_operator(self.h, apply, operator.h, _dev_ptr(dinv), _dev_ptr(b), _dev_ptr(x),
+                                                C.byref(self.opt), C.byref(self.result), _stream_ptr()))
+        r = self.result
+        return x, dict(converged=bool(r.converged), final_iter=r.final_iter, initial_norm=r.initial_norm,
+                       final_norm=r.final_norm)

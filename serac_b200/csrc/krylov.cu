@@ -11,7 +11,9 @@
 #include <cuda_runtime.h>
 
 #include <algorithm>
+#include <cmath>
 #include <memory>
+#include <vector>
 
 #include "common.hpp"
 #include "serac_b200_solvers.h"
@@ -882,4 +884,359 @@ extern "C" int sb_cg_solve_operator(sb_cg_t S, sb_operator_apply apply, void* ct
   op.apply = apply;
   op.ctx   = ctx;
   return cg_solve(S, op, diag_inv_dev, b_dev, x_dev, opt, result, as_stream(stream));
+}
+
+// ---- GMRES(m) ---------------------------------------------------------------------------------------------------------
+// mfem::GMRESSolver::Mult (mfem/linalg/solvers.cpp:981-1165; line numbers below refer to that file): restarted GMRES with
+// modified Gram-Schmidt.  The Krylov basis, the work vectors and the Hessenberg column being built stay on the device: the
+// chain  H(k,i) = (w, v_k);  w -= H(k,i) v_k  runs as one kernel per k that applies the previous projection and reduces
+// the next inner product (finished by the last block to arrive), with no host round trip inside a column; the host reads
+// the finished column once per iteration for the (m+1) x m Givens / back-substitution arithmetic, as the reference does.
+namespace {
+
+/// w -= hcol[k-1] v_prev (when k > 0), then hcol[k] = (w, v_k)
+__global__ void __launch_bounds__(kThreads) gmres_project_kernel(double* __restrict__ w, const double* __restrict__ v_prev,
+                                                                 const double* __restrict__ v_k, double* __restrict__ hcol,
+                                                                 int k, int64_t n, double* __restrict__ partials,
+                                                                 unsigned int* __restrict__ ticket)
+{
+  __shared__ double smem[kWarpsPerCta];
+  const double      h_prev = (k > 0) ? hcol[k - 1] : 0.0;
+  double            acc    = 0.0;
+  for (int64_t i = blockIdx.x * int64_t(blockDim.x) + threadIdx.x; i < n; i += int64_t(gridDim.x) * blockDim.x) {
+    double wi = w[i];
+    if (k > 0) {
+      wi   = wi + (-h_prev) * v_prev[i];  // w.Add(-H(k,i), *v[k])  (:1074)
+      w[i] = wi;
+    }
+    acc += wi * v_k[i];  // Dot(w, *v[k])  (:1073)
+  }
+  const double part  = block_sum(acc, smem);
+  double       total = 0.0;
+  if (grid_sum_last_block(part, partials, ticket, smem, &total) && threadIdx.x == 0) {
+    hcol[k] = total;
+    __threadfence();
+  }
+}
+
+/// w -= hcol[i] v_i, then hcol[i+1] = ||w||  (:1074, :1077)
+__global__ void __launch_bounds__(kThreads) gmres_norm_kernel(double* __restrict__ w, const double* __restrict__ v_i,
+                                                              double* __restrict__ hcol, int i, int64_t n,
+                                                              double* __restrict__ partials,
+                                                              unsigned int* __restrict__ ticket)
+{
+  __shared__ double smem[kWarpsPerCta];
+  const double      h   = hcol[i];
+  double            acc = 0.0;
+  for (int64_t j = blockIdx.x * int64_t(blockDim.x) + threadIdx.x; j < n; j += int64_t(gridDim.x) * blockDim.x) {
+    const double wj = w[j] + (-h) * v_i[j];
+    w[j]            = wj;
+    acc += wj * wj;
+  }
+  const double part  = block_sum(acc, smem);
+  double       total = 0.0;
+  if (grid_sum_last_block(part, partials, ticket, smem, &total) && threadIdx.x == 0) {
+    hcol[i + 1] = sqrt(total);
+    __threadfence();
+  }
+}
+
+/// v_next = w / hcol[i+1]  (:1080)
+__global__ void gmres_normalize_kernel(const double* __restrict__ w, double* __restrict__ v_next,
+                                       const double* __restrict__ hcol, int i, int64_t n)
+{
+  const double s = 1.0 / hcol[i + 1];
+  for (int64_t j = blockIdx.x * int64_t(blockDim.x) + threadIdx.x; j < n; j += int64_t(gridDim.x) * blockDim.x)
+    v_next[j] = s * w[j];
+}
+
+/// r = M (b - r) or r = b - r (or M b / b when `have_Ax` is 0), out[0] = ||r||  (:1004-1027, :1119-1129)
+__global__ void __launch_bounds__(kThreads) gmres_residual_kernel(const double* __restrict__ b, double* __restrict__ r,
+                                                                  const double* __restrict__ dinv, int have_Ax, int64_t n,
+                                                                  double* __restrict__ out, double* __restrict__ partials,
+                                                                  unsigned int* __restrict__ ticket)
+{
+  __shared__ double smem[kWarpsPerCta];
+  double            acc = 0.0;
+  for (int64_t i = blockIdx.x * int64_t(blockDim.x) + threadIdx.x; i < n; i += int64_t(gridDim.x) * blockDim.x) {
+    double ri = have_Ax ? b[i] - r[i] : b[i];
+    if (dinv) ri = dinv[i] * ri;
+    r[i] = ri;
+    acc += ri * ri;
+  }
+  const double part  = block_sum(acc, smem);
+  double       total = 0.0;
+  if (grid_sum_last_block(part, partials, ticket, smem, &total) && threadIdx.x == 0) {
+    *out = sqrt(total);
+    __threadfence();
+  }
+}
+
+/// v0 = r / beta  (:1056)
+__global__ void gmres_first_vector_kernel(const double* __restrict__ r, double* __restrict__ v0, double inv_beta, int64_t n)
+{
+  for (int64_t i = blockIdx.x * int64_t(blockDim.x) + threadIdx.x; i < n; i += int64_t(gridDim.x) * blockDim.x)
+    v0[i] = inv_beta * r[i];
+}
+
+/// w = D^-1 r
+__global__ void scale_by_kernel(const double* __restrict__ dinv, const double* __restrict__ r, double* __restrict__ w,
+                                int64_t n)
+{
+  for (int64_t i = blockIdx.x * int64_t(blockDim.x) + threadIdx.x; i < n; i += int64_t(gridDim.x) * blockDim.x)
+    w[i] = dinv[i] * r[i];
+}
+
+/// x += sum_j y[j] v_j, j ascending  (Update, :960-980)
+__global__ void gmres_update_kernel(double* __restrict__ x, const double* __restrict__ V, const double* __restrict__ y,
+                                    int count, int64_t n)
+{
+  for (int64_t i = blockIdx.x * int64_t(blockDim.x) + threadIdx.x; i < n; i += int64_t(gridDim.x) * blockDim.x) {
+    double xi = x[i];
+    for (int j = 0; j < count; j++) xi = xi + y[j] * V[int64_t(j) * n + i];
+    x[i] = xi;
+  }
+}
+
+__global__ void zero_kernel(double* __restrict__ x, int64_t n)
+{
+  for (int64_t i = blockIdx.x * int64_t(blockDim.x) + threadIdx.x; i < n; i += int64_t(gridDim.x) * blockDim.x) x[i] = 0.0;
+}
+
+}  // namespace
+
+struct sb_gmres_s {
+  int64_t       n = 0;
+  int           m = 0;
+  double*       V        = nullptr;  // [m + 1][n]
+  double *      r = nullptr, *w = nullptr;
+  double*       hcol     = nullptr;  // [m + 2] the column being built; [m + 2 ...] y of the update (m entries); then beta
+  double*       partials = nullptr;
+  unsigned int* ticket   = nullptr;
+  double*       host     = nullptr;  // pinned, m + 2 doubles
+};
+
+extern "C" int sb_gmres_destroy(sb_gmres_t G)
+{
+  if (!G) return SB_OK;
+  cudaFree(G->V);
+  cudaFree(G->r);
+  cudaFree(G->w);
+  cudaFree(G->hcol);
+  cudaFree(G->partials);
+  cudaFree(G->ticket);
+  if (G->host) cudaFreeHost(G->host);
+  delete G;
+  return SB_OK;
+}
+
+extern "C" int sb_gmres_create(int64_t n, int kdim, sb_gmres_t* out)
+{
+  SB_REQUIRE(out && n >= 0 && kdim >= 1, "sb_gmres_create: bad argument");
+  auto G = std::make_unique<sb_gmres_s>();
+  G->n   = n;
+  G->m   = kdim;
+  int rc = dev_new(&G->V, size_t(kdim + 1) * size_t(n));
+  if (!rc) rc = dev_new(&G->r, size_t(n));
+  if (!rc) rc = dev_new(&G->w, size_t(n));
+  if (!rc) rc = dev_new(&G->hcol, size_t(2 * kdim + 4));
+  if (!rc) rc = dev_new(&G->partials, size_t(kMaxPartials));
+  if (!rc) rc = dev_new(&G->ticket, 1);
+  if (!rc && cudaMemset(G->ticket, 0, sizeof(unsigned int)) != cudaSuccess) rc = SB_ERR_CUDA;
+  if (!rc && cudaMallocHost(reinterpret_cast<void**>(&G->host), size_t(kdim + 2) * sizeof(double)) != cudaSuccess) {
+    sb::set_error("sb_gmres_create: cudaMallocHost failed");
+    rc = SB_ERR_CUDA;
+  }
+  if (rc) {
+    sb_gmres_destroy(G.release());
+    return rc;
+  }
+  *out = G.release();
+  return SB_OK;
+}
+
+namespace {
+
+int apply_plain(const CgOperator& op, int64_t n, const double* x, double* y, cudaStream_t s)
+{
+  if (op.apply) return op.apply(op.ctx, x, y, s);
+  csr_spmv_kernel<<<reducing_grid(n, kWarpsPerCta), kThreads, 0, s>>>(op.A.row_ptr, op.A.col_ind, op.values, x, y, n);
+  sb_count_launch();
+  SB_CHECK_CUDA(cudaGetLastError());
+  return SB_OK;
+}
+
+// GeneratePlaneRotation / ApplyPlaneRotation (:931-958)
+void generate_rotation(double dx, double dy, double& cs, double& sn)
+{
+  if (dy == 0.0) {
+    cs = 1.0;
+    sn = 0.0;
+  } else if (std::fabs(dy) > std::fabs(dx)) {
+    const double t = dx / dy;
+    sn             = 1.0 / std::sqrt(1.0 + t * t);
+    cs             = t * sn;
+  } else {
+    const double t = dy / dx;
+    cs             = 1.0 / std::sqrt(1.0 + t * t);
+    sn             = t * cs;
+  }
+}
+void apply_rotation(double& dx, double& dy, double cs, double sn)
+{
+  const double t = cs * dx + sn * dy;
+  dy             = -sn * dx + cs * dy;
+  dx             = t;
+}
+
+int gmres_solve(sb_gmres_t G, const CgOperator& op, const double* dinv, const double* b, double* x,
+                const sb_cg_options* opt, sb_cg_result* result, cudaStream_t s)
+{
+  SB_REQUIRE(G && opt && result, "sb_gmres_solve: null solver / options / result");
+  SB_REQUIRE(opt->max_iter >= 0, "sb_gmres_solve: max_iter >= 0 required");
+  const int64_t n = G->n;
+  const int     m = G->m;
+  *result         = sb_cg_result{};
+  if (n == 0) {
+    result->converged = 1;
+    return SB_OK;
+  }
+  SB_REQUIRE(b && x, "sb_gmres_solve: null vector");
+  const int vgrid    = reducing_grid(n, kThreads);
+  double*   beta_dev = G->hcol + 2 * m + 3;
+  double*   y_dev    = G->hcol + m + 2;
+  auto      v        = [&](int i) { return G->V + int64_t(i) * n; };
+
+  // r = M (b - A x), beta = ||r||  (:995-1027)
+  auto residual = [&](bool have_Ax, double* beta) -> int {
+    gmres_residual_kernel<<<vgrid, kThreads, 0, s>>>(b, G->r, dinv, have_Ax ? 1 : 0, n, beta_dev, G->partials, G->ticket);
+    sb_count_launch();
+    SB_CHECK_CUDA(cudaGetLastError());
+    SB_CHECK_CUDA(cudaMemcpyAsync(G->host, beta_dev, sizeof(double), cudaMemcpyDeviceToHost, s));
+    SB_CHECK_CUDA(cudaStreamSynchronize(s));
+    *beta = G->host[0];
+    return SB_OK;
+  };
+  // x += sum_i y_i v_i with H y = s back-substituted on the host  (Update, :960-980)
+  std::vector<double> H(size_t(m + 1) * size_t(m), 0.0), sv(size_t(m + 1)), cs(size_t(m + 1)), sn(size_t(m + 1));
+  auto                Hat    = [&](int r_, int c_) -> double& { return H[size_t(r_) * size_t(m) + size_t(c_)]; };
+  auto                update = [&](int k) -> int {
+    if (k < 0) return SB_OK;
+    std::vector<double> y(sv.begin(), sv.begin() + k + 1);
+    for (int i = k; i >= 0; i--) {
+      y[size_t(i)] /= Hat(i, i);
+      for (int j = i - 1; j >= 0; j--) y[size_t(j)] -= Hat(j, i) * y[size_t(i)];
+    }
+    SB_CHECK_CUDA(cudaMemcpyAsync(y_dev, y.data(), size_t(k + 1) * sizeof(double), cudaMemcpyHostToDevice, s));
+    gmres_update_kernel<<<vgrid, kThreads, 0, s>>>(x, G->V, y_dev, k + 1, n);
+    sb_count_launch();
+    SB_CHECK_CUDA(cudaGetLastError());
+    SB_CHECK_CUDA(cudaStreamSynchronize(s));  // y is a stack vector of this call
+    return SB_OK;
+  };
+
+  double beta = 0.0;
+  if (opt->iterative_mode) {
+    if (int e = apply_plain(op, n, x, G->r, s)) return e;
+  } else {
+    zero_kernel<<<vgrid, kThreads, 0, s>>>(x, n);
+    sb_count_launch();
+    SB_CHECK_CUDA(cudaGetLastError());
+  }
+  if (int e = residual(opt->iterative_mode != 0, &beta)) return e;
+  result->initial_norm = beta;
+  SB_REQUIRE(std::isfinite(beta), "sb_gmres_solve: the initial residual is not finite");
+  double final_norm = std::max(opt->rel_tol * beta, opt->abs_tol);  // :1030
+  if (beta <= final_norm) {                                         // :1032-1039
+    result->final_norm = beta;
+    result->final_iter = 0;
+    result->converged  = 1;
+    return SB_OK;
+  }
+  int j = 1;
+  while (j <= opt->max_iter) {  // :1053
+    gmres_first_vector_kernel<<<vgrid, kThreads, 0, s>>>(G->r, v(0), 1.0 / beta, n);
+    sb_count_launch();
+    SB_CHECK_CUDA(cudaGetLastError());
+    std::fill(sv.begin(), sv.end(), 0.0);
+    sv[0] = beta;
+    int i = 0;
+    for (; i < m && j <= opt->max_iter; i++, j++) {  // :1059
+      if (dinv) {                                     // w = M A v_i  (:1061-1069)
+        if (int e = apply_plain(op, n, v(i), G->r, s)) return e;
+        scale_by_kernel<<<vgrid, kThreads, 0, s>>>(dinv, G->r, G->w, n);
+        sb_count_launch();
+        SB_CHECK_CUDA(cudaGetLastError());
+      } else {
+        if (int e = apply_plain(op, n, v(i), G->w, s)) return e;
+      }
+      for (int k = 0; k <= i; k++) {  // modified Gram-Schmidt  (:1071-1075)
+        gmres_project_kernel<<<vgrid, kThreads, 0, s>>>(G->w, k > 0 ? v(k - 1) : nullptr, v(k), G->hcol, k, n, G->partials,
+                                                        G->ticket);
+        sb_count_launch();
+      }
+      gmres_norm_kernel<<<vgrid, kThreads, 0, s>>>(G->w, v(i), G->hcol, i, n, G->partials, G->ticket);
+      sb_count_launch();
+      gmres_normalize_kernel<<<vgrid, kThreads, 0, s>>>(G->w, v(i + 1), G->hcol, i, n);
+      sb_count_launch();
+      SB_CHECK_CUDA(cudaGetLastError());
+      SB_CHECK_CUDA(cudaMemcpyAsync(G->host, G->hcol, size_t(i + 2) * sizeof(double), cudaMemcpyDeviceToHost, s));
+      SB_CHECK_CUDA(cudaStreamSynchronize(s));
+      for (int k = 0; k <= i + 1; k++) Hat(k, i) = G->host[k];
+      SB_REQUIRE(std::isfinite(Hat(i + 1, i)), "sb_gmres_solve: Norm(w) is not finite");
+      for (int k = 0; k < i; k++) apply_rotation(Hat(k, i), Hat(k + 1, i), cs[size_t(k)], sn[size_t(k)]);  // :1082-1085
+      generate_rotation(Hat(i, i), Hat(i + 1, i), cs[size_t(i)], sn[size_t(i)]);
+      apply_rotation(Hat(i, i), Hat(i + 1, i), cs[size_t(i)], sn[size_t(i)]);
+      apply_rotation(sv[size_t(i)], sv[size_t(i) + 1], cs[size_t(i)], sn[size_t(i)]);
+      const double resid = std::fabs(sv[size_t(i) + 1]);  // :1091
+      SB_REQUIRE(std::isfinite(resid), "sb_gmres_solve: the residual estimate is not finite");
+      if (resid <= final_norm) {  // :1094-1101
+        if (int e = update(i)) return e;
+        result->final_norm = resid;
+        result->final_iter = j;
+        result->converged  = 1;
+        return SB_OK;
+      }
+    }
+    if (int e = update(i - 1)) return e;                     // :1117
+    if (int e = apply_plain(op, n, x, G->r, s)) return e;    // :1119
+    if (int e = residual(true, &beta)) return e;             // :1120-1129
+    SB_REQUIRE(std::isfinite(beta), "sb_gmres_solve: the residual is not finite");
+    if (beta <= final_norm) {  // :1131-1137
+      result->final_norm = beta;
+      result->final_iter = j;
+      result->converged  = 1;
+      return SB_OK;
+    }
+  }
+  result->final_norm = beta;  // :1140-1142
+  result->final_iter = opt->max_iter;
+  result->converged  = 0;
+  return SB_OK;
+}
+
+}  // namespace
+
+extern "C" int sb_gmres_solve_csr(sb_gmres_t G, sb_csr_t A, const double* values_dev, const double* diag_inv_dev,
+                                  const double* b_dev, double* x_dev, const sb_cg_options* opt, sb_cg_result* result,
+                                  void* stream)
+{
+  SB_REQUIRE(G != nullptr, "sb_gmres_solve_csr: null solver");
+  CgOperator op;
+  if (int e = view_of(A, &op.A)) return e;
+  SB_REQUIRE(op.A.num_rows == G->n, "sb_gmres_solve_csr: the solver was created for a different size");
+  SB_REQUIRE(values_dev || op.A.nnz == 0, "sb_gmres_solve_csr: null values");
+  op.values = values_dev;
+  return gmres_solve(G, op, diag_inv_dev, b_dev, x_dev, opt, result, as_stream(stream));
+}
+
+extern "C" int sb_gmres_solve_operator(sb_gmres_t G, sb_operator_apply apply, void* ctx, const double* diag_inv_dev,
+                                       const double* b_dev, double* x_dev, const sb_cg_options* opt, sb_cg_result* result,
+                                       void* stream)
+{
+  SB_REQUIRE(G != nullptr && apply != nullptr, "sb_gmres_solve_operator: null solver / operator");
+  CgOperator op;
+  op.apply = apply;
+  op.ctx   = ctx;
+  return gmres_solve(G, op, diag_inv_dev, b_dev, x_dev, opt, result, as_stream(stream));
 }

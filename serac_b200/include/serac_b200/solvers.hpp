@@ -10,6 +10,7 @@
 //   r.SetSubVector(ess, 0.0)  (solid_mechanics.hpp:1129)        serac::SetSubVector(r, ess, 0.0)
 //   mfem::OperatorJacobiSmoother / HypreSmoother Jacobi         serac::JacobiSmoother
 //   mfem::CGSolver (solvers.cpp:719-897)                        serac::CGSolver (SetOperator / SetPreconditioner / Mult)
+//   mfem::GMRESSolver (solvers.cpp:981-1165)                    serac::GMRESSolver (SetKDim, same calls)
 //   Functional::Gradient as the operator (matrix-free)          serac::GradientOperator
 //
 // Failures abort with the library's message, as the reference does through SLIC_ERROR_ROOT.
@@ -214,6 +215,75 @@ class CGSolver {
   sb_cg_options           opt_{1e-12, 0.0, 10, 0, 1};  // mfem's IterativeSolver defaults: rel_tol 0 -> set explicitly
   mutable sb_cg_result    res_{};
   sb_cg_t                 S_  = nullptr;
+  int64_t                 n_  = -1;
+  const DeviceCsrMatrix*  A_  = nullptr;
+  const GradientOperator* op_ = nullptr;
+  const JacobiSmoother*   prec_ = nullptr;
+};
+
+/// mfem::GMRESSolver: serac's default linear solver (solid_mechanics.hpp:50-57)
+class GMRESSolver {
+ public:
+  GMRESSolver() = default;
+  GMRESSolver(const GMRESSolver&)            = delete;
+  GMRESSolver& operator=(const GMRESSolver&) = delete;
+  ~GMRESSolver() { sb_gmres_destroy(G_); }
+  void SetRelTol(double t) { opt_.rel_tol = t; }
+  void SetAbsTol(double t) { opt_.abs_tol = t; }
+  void SetMaxIter(int n) { opt_.max_iter = n; }
+  void SetKDim(int m)
+  {
+    m_ = m;
+    n_ = -1;  // reallocate the basis at the next SetOperator
+  }
+  void SetOperator(const DeviceCsrMatrix& A)
+  {
+    A_  = &A;
+    op_ = nullptr;
+    resize(A.Height());
+  }
+  void SetOperator(const GradientOperator& op)
+  {
+    op_ = &op;
+    A_  = nullptr;
+    resize(op.Height());
+  }
+  void SetPreconditioner(const JacobiSmoother& prec) { prec_ = &prec; }
+  bool iterative_mode = false;
+
+  void Mult(const Vector& b, Vector& x) const
+  {
+    sb_cg_options opt  = opt_;
+    opt.iterative_mode = iterative_mode ? 1 : 0;
+    const double* dinv = prec_ ? prec_->dinv() : nullptr;
+    if (A_) {
+      SERAC_B200_CHECK(sb_gmres_solve_csr(G_, A_->pattern(), A_->values().Read(), dinv, b.Read(), x.Write(), &opt, &res_, nullptr));
+    } else if (op_) {
+      SERAC_B200_CHECK(sb_gmres_solve_operator(G_, sb_functional_gradient_operator_apply, op_->handle(), dinv, b.Read(),
+                                               x.Write(), &opt, &res_, nullptr));
+    } else {
+      std::fprintf(stderr, "serac::GMRESSolver::Mult: no operator set\n");
+      std::abort();
+    }
+  }
+  bool   GetConverged() const { return res_.converged != 0; }
+  int    GetNumIterations() const { return res_.final_iter; }
+  double GetInitialNorm() const { return res_.initial_norm; }
+  double GetFinalNorm() const { return res_.final_norm; }
+
+ private:
+  void resize(int64_t n)
+  {
+    if (G_ && n == n_) return;
+    sb_gmres_destroy(G_);
+    G_ = nullptr;
+    n_ = n;
+    SERAC_B200_CHECK(sb_gmres_create(n, m_, &G_));
+  }
+  sb_cg_options           opt_{1e-12, 0.0, 10, 0, 1};
+  mutable sb_cg_result    res_{};
+  sb_gmres_t              G_  = nullptr;
+  int                     m_  = 50;  // mfem's default
   int64_t                 n_  = -1;
   const DeviceCsrMatrix*  A_  = nullptr;
   const GradientOperator* op_ = nullptr;

@@ -12,6 +12,7 @@
 //     newton    the solid problem solved the way SolidMechanics::quasiStaticSolve does: Newton on the residual with the
 //               essential rows zeroed, Jacobian = assemble + EliminateRowsCols, CG + Jacobi -- every step on the device;
 //               once with the assembled matrix and once matrix-free over Gradient::Mult
+//     krylov    CGSolver / GMRESSolver (assembled and matrix-free) on the eliminated Jacobian at the fixture's state
 //     qoi       Functional<double(H1<2,3>)> with a q-function defined in this file: value, directional derivative, gradient
 // Directory layout: <name>.bin raw little-endian arrays (int32 / float64), meta.txt "key value" lines.
 #include <cmath>
@@ -135,7 +136,7 @@ int run_solid(const std::map<std::string, double>& meta)
 /// One quasi-static solve (solid_mechanics.hpp:1120-1140 residual / Jacobian lambdas, Newton + CG/Jacobi of
 /// equation_solver.cpp) without leaving the GPU.  Inputs beyond the solid case: ess.bin (essential dofs), meta
 /// force_scale / rel_tol / max_iter / newton_rel / newton_max.  matrix_free: CG over Gradient::Mult instead of the matrix.
-int run_newton(const std::map<std::string, double>& meta, bool matrix_free)
+int run_newton(const std::map<std::string, double>& meta, bool matrix_free, bool use_gmres = false)
 {
   Problem P = load_problem(meta, false);
   auto    params = read_bin<double>("params");
@@ -160,6 +161,10 @@ int run_newton(const std::map<std::string, double>& meta, bool matrix_free)
   cg.SetRelTol(meta.at("rel_tol"));
   cg.SetAbsTol(0.0);
   cg.SetMaxIter(int(meta.at("max_iter")));
+  GMRESSolver gmres;
+  gmres.SetRelTol(meta.at("rel_tol"));
+  gmres.SetAbsTol(0.0);
+  gmres.SetMaxIter(int(meta.at("max_iter")));
   std::vector<double> norms, cg_iters;
   for (int it = 0; it < int(meta.at("newton_max")); it++) {
     auto [r, drdu] = residual(0.0, S, differentiate_wrt(u), A);
@@ -171,26 +176,114 @@ int run_newton(const std::map<std::string, double>& meta, bool matrix_free)
     auto J_e = J->EliminateRowsCols(ess);  // J_e_ = bcs_.eliminateAllEssentialDofsFromMatrix(*J_)
     JacobiSmoother   prec(*J);
     GradientOperator op(drdu, ess);
-    if (matrix_free)
-      cg.SetOperator(op);
-    else
-      cg.SetOperator(*J);
-    cg.SetPreconditioner(prec);
-    cg.Mult(rhs, du);
-    if (!cg.GetConverged()) {
-      std::fprintf(stderr, "CG did not converge in Newton step %d\n", it);
+    bool converged = false;
+    int  iters     = 0;
+    if (use_gmres) {  // serac's default: GMRES (solid_mechanics.hpp:50-57)
+      gmres.SetOperator(*J);
+      gmres.SetPreconditioner(prec);
+      gmres.Mult(rhs, du);
+      converged = gmres.GetConverged();
+      iters     = gmres.GetNumIterations();
+    } else {
+      if (matrix_free)
+        cg.SetOperator(op);
+      else
+        cg.SetOperator(*J);
+      cg.SetPreconditioner(prec);
+      cg.Mult(rhs, du);
+      converged = cg.GetConverged();
+      iters     = cg.GetNumIterations();
+    }
+    if (!converged) {
+      std::fprintf(stderr, "the linear solver did not converge in Newton step %d\n", it);
       return 1;
     }
-    cg_iters.push_back(double(cg.GetNumIterations()));
+    cg_iters.push_back(double(iters));
     Add(u, -1.0, du);  // u -= du
   }
-  const std::string tag = matrix_free ? "_mf" : "";
+  const std::string tag = use_gmres ? "_gmres" : (matrix_free ? "_mf" : "");
   write_bin("u" + tag, u.to_host());
   write_bin("residual_norms" + tag, norms);
   write_bin("cg_iterations" + tag, cg_iters);
-  std::printf("newton%s: %zu residual evaluations, last |r| = %.3e, CG iterations", tag.c_str(), norms.size(), norms.back());
+  std::printf("newton%s: %zu residual evaluations, last |r| = %.3e, linear iterations", tag.c_str(), norms.size(), norms.back());
   for (double c : cg_iters) std::printf(" %d", int(c));
   std::printf("\n");
+  return 0;
+}
+
+/// The linear solvers on the Jacobian at the fixture's state, for comparison with the reference's mfem on the same
+/// system (tests/golden/krylov_*.npz): inputs beyond the solid case: ess.bin, B_bc.bin (right-hand side after
+/// EliminateBC), X.bin (initial guess), meta rel_tol / max_iter / jacobi.
+int run_krylov(const std::map<std::string, double>& meta)
+{
+  Problem P = load_problem(meta, false);
+  auto    params = read_bin<double>("params");
+  SolidFunctional residual(&P.space, {&P.shape_space, &P.space, &P.space});
+  using Material = solid_mechanics::NeoHookean;
+  Material m{params[0], params[1], params[2]};
+  auto     gn    = params[3] != 0.0 ? GeometricNonlinearities::On : GeometricNonlinearities::Off;
+  Domain   whole = EntireDomain(P.mesh);
+  residual.AddDomainIntegral(Dimension<dim>{}, DependsOn<0, 1, 2>{}, SolidIntegrand<Material>(MaterialStressFunctor<Material>(m, gn)),
+                             whole, EmptyQData);
+  DofList ess(read_bin<int>("ess"));
+  Vector  S(read_bin<double>("S")), U(read_bin<double>("U")), A(read_bin<double>("A")), B(read_bin<double>("B_bc")),
+      X(read_bin<double>("X"));
+  auto [r, drdu] = residual(0.0, S, differentiate_wrt(U), A);
+  auto J   = assemble_on_device(drdu);
+  auto J_e = J->EliminateRowsCols(ess);
+  write_bin("values_elim", J->values().to_host());
+  write_bin("values_e", J_e->values().to_host());
+  JacobiSmoother   prec(*J);
+  GradientOperator op(drdu, ess);
+  const bool       jacobi = meta.at("jacobi") != 0.0;
+  const int64_t    n      = P.space.GetVSize();
+  Vector           x(n);
+  auto report = [&](const std::string& name, auto& solver) {
+    write_bin("x_" + name, x.to_host());
+    write_bin("info_" + name, std::vector<double>{double(solver.GetConverged()), double(solver.GetNumIterations()),
+                                                  solver.GetInitialNorm(), solver.GetFinalNorm()});
+    std::printf("%s: converged %d, %d iterations, final norm %.3e\n", name.c_str(), int(solver.GetConverged()),
+                solver.GetNumIterations(), solver.GetFinalNorm());
+  };
+  {
+    CGSolver cg;
+    cg.SetRelTol(meta.at("rel_tol"));
+    cg.SetMaxIter(int(meta.at("max_iter")));
+    cg.SetOperator(*J);
+    if (jacobi) cg.SetPreconditioner(prec);
+    cg.Mult(B, x);
+    report("cg", cg);
+  }
+  for (int kdim : {20, 50}) {
+    GMRESSolver gmres;
+    gmres.SetKDim(kdim);
+    gmres.SetRelTol(meta.at("rel_tol"));
+    gmres.SetMaxIter(int(meta.at("max_iter")));
+    gmres.SetOperator(*J);
+    if (jacobi) gmres.SetPreconditioner(prec);
+    gmres.Mult(B, x);
+    report("gmres" + std::to_string(kdim), gmres);
+    if (kdim == 20) {
+      x                    = X;
+      gmres.iterative_mode = true;
+      gmres.Mult(B, x);
+      report("gmres20_guess", gmres);
+      gmres.iterative_mode = false;
+      gmres.SetOperator(op);  // matrix-free over Gradient::Mult
+      gmres.Mult(B, x);
+      report("gmres20_mf", gmres);
+    }
+  }
+  {
+    GMRESSolver gmres;  // max_iter inside the second cycle
+    gmres.SetKDim(5);
+    gmres.SetRelTol(meta.at("rel_tol"));
+    gmres.SetMaxIter(7);
+    gmres.SetOperator(*J);
+    if (jacobi) gmres.SetPreconditioner(prec);
+    gmres.Mult(B, x);
+    report("gmres5_maxiter7", gmres);
+  }
   return 0;
 }
 
@@ -389,7 +482,8 @@ int main(int argc, char** argv)
   if (which == "j2") rc = run_j2(meta);
   if (which == "pressure") rc = run_pressure(meta);
   if (which == "user") rc = run_user(meta);
-  if (which == "newton") rc = run_newton(meta, false) || run_newton(meta, true);
+  if (which == "newton") rc = run_newton(meta, false) || run_newton(meta, true) || run_newton(meta, false, true);
+  if (which == "krylov") rc = run_krylov(meta);
   if (which == "qoi") rc = run_qoi(meta);
   if (which == "boundary_qoi") rc = run_boundary_qoi(meta);
   std::printf("launches: %lld\n", sb_launch_count());

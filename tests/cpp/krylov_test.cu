@@ -293,6 +293,46 @@ int main(int argc, char** argv)
   e = rel_l2(to_host(x_dev, size_t(n)), x1);
   expect(resg.converged == 1 && e < 1e-6, "iterative_mode from a guess reaches the same solution", e, 1e-6);
 
+  // --- GMRES(m): same system, so the same solution; restarts (m = 10) and mfem's default m = 50 -------------------------
+  for (int kdim : {10, 50}) {
+    sb_gmres_t G = nullptr;
+    CK(sb_gmres_create(n, kdim, &G));
+    sb_cg_options og{rel_tol, 0.0, max_iter, 0, 1};
+    sb_cg_result  rg{}, rg2{};
+    CK(sb_gmres_solve_csr(G, A, vals_dev, dinv_dev, B_dev, x_dev, &og, &rg, nullptr));
+    CU(cudaDeviceSynchronize());
+    auto xg = to_host(x_dev, N);
+    e       = rel_l2(xg, x1);
+    std::printf("GMRES(%d): %d iterations (converged %d), final %.3e / initial %.3e\n", kdim, rg.final_iter, rg.converged,
+                rg.final_norm, rg.initial_norm);
+    expect(rg.converged == 1 && e < 1e-6, "GMRES solution vs CG solution", e, 1e-6);
+    expect(rg.final_norm <= rel_tol * rg.initial_norm * (1 + 1e-12), "GMRES stopping rule", rg.final_norm,
+           rel_tol * rg.initial_norm);
+    {  // the reported residual estimate is honest: ||D^-1 (b - A x)|| within a factor of the estimate
+      auto   Ax = He.mult(xg);
+      double tr = 0;
+      for (size_t i = 0; i < N; i++) tr += std::pow(dinv_ref[i] * (Bbc[i] - Ax[i]), 2);
+      expect(std::sqrt(tr) < 10 * rel_tol * rg.initial_norm, "GMRES true preconditioned residual", std::sqrt(tr),
+             10 * rel_tol * rg.initial_norm);
+    }
+    CK(sb_gmres_solve_csr(G, A, vals_dev, dinv_dev, B_dev, x_dev, &og, &rg2, nullptr));
+    CU(cudaDeviceSynchronize());
+    expect(rg2.final_iter == rg.final_iter && to_host(x_dev, N) == xg, "GMRES is deterministic");
+    SpmvCtx      ctxg{A, vals_dev};
+    sb_cg_result rgo{};
+    CK(sb_gmres_solve_operator(G, spmv_callback, &ctxg, dinv_dev, B_dev, x_dev, &og, &rgo, nullptr));
+    CU(cudaDeviceSynchronize());
+    expect(rgo.final_iter == rg.final_iter && to_host(x_dev, N) == xg, "GMRES operator form = CSR form bit for bit");
+    const int     cap = (kdim == 10) ? 13 : 20;  // inside the second cycle / inside the first
+    sb_cg_options om{rel_tol, 0.0, cap, 0, 1};
+    sb_cg_result  rm{};
+    CK(sb_gmres_solve_csr(G, A, vals_dev, dinv_dev, B_dev, x_dev, &om, &rm, nullptr));
+    CU(cudaDeviceSynchronize());
+    expect(rm.converged == 0 && rm.final_iter == cap && rm.final_norm < rm.initial_norm, "GMRES max_iter exit",
+           rm.final_iter, cap);
+    CK(sb_gmres_destroy(G));
+  }
+
   CK(sb_cg_destroy(S));
   CK(sb_csr_destroy(A));
   CK(sb_restriction_destroy(R));

@@ -75,3 +75,32 @@ def test_live_reference_agrees_with_fixture(case):
     x, info = ref.cg(case["row_ptr"], case["col_ind"], A, case["B_bc"], jacobi=bool(case["jacobi"]),
                      rel_tol=case["rel_tol"], max_iter=case["max_iter"])
     assert info["final_iter"] == case["cg_final_iter"] and np.array_equal(x, case["x"])
+
+
+def _gmres(case, **kw):
+    rp, ci, A = case["row_ptr"], case["col_ind"], case["values_elim"]
+    dinv = ko.jacobi_dinv(ko.diagonal(rp, ci, A)) if case["jacobi"] else None
+    return ko.gmres(lambda v: ko.spmv(rp, ci, A, v), case["B_bc"], dinv=dinv, rel_tol=case["rel_tol"],
+                    abs_tol=case["abs_tol"], **kw)
+
+
+@pytest.mark.parametrize("kdim", [20, 50])
+def test_gmres_matches_mfem(case, kdim):
+    """restarted GMRES (solvers.cpp:981-1165): restarts (kdim 20 < iterations) and mfem's default kdim 50"""
+    x, info = _gmres(case, kdim=kdim, max_iter=case["max_iter"])
+    assert info["converged"] and case[f"gmres{kdim}_converged"]
+    assert abs(info["final_iter"] - case[f"gmres{kdim}_final_iter"]) <= 1
+    assert abs(info["initial_norm"] / case[f"gmres{kdim}_initial_norm"] - 1) < 1e-12
+    assert rel_l2(x, case[f"x_gmres{kdim}"]) < 1e-7
+
+
+def test_gmres_exits_like_mfem(case):
+    """max_iter in the middle of the second cycle (kdim 5, max_iter 7): the true residual norm is reported, not converged
+    (:1117-1142); and iterative_mode"""
+    x, info = _gmres(case, kdim=5, max_iter=7)
+    assert not info["converged"] and info["final_iter"] == 7 == case["gmres5m7_final_iter"]
+    assert rel_l2(x, case["x_gmres5_maxiter7"]) < 1e-11
+    assert abs(info["final_norm"] / case["gmres5m7_final_norm"] - 1) < 1e-10
+    xg, ig = _gmres(case, kdim=20, max_iter=case["max_iter"], x0=case["X"])
+    assert ig["converged"] and abs(ig["final_iter"] - case["gmres20g_final_iter"]) <= 1
+    assert rel_l2(xg, case["x_gmres20_guess"]) < 1e-7

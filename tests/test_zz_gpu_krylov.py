@@ -133,6 +133,45 @@ def test_cg_exits_like_mfem(case):
     assert info0["converged"] and info0["final_iter"] == 0 and not x0.any()
 
 
+@pytest.mark.parametrize("kdim", [20, 50])
+def test_gmres_matches_mfem(case, kdim):
+    """mfem::GMRESSolver with restarts (kdim 20) and with mfem's default restart length"""
+    c, g = case, case["g"]
+    vals, _ = _eliminated(c)
+    dinv = _dinv(c, vals)
+    gm = c["capi"].GMRESSolver(c["pat"].num_rows, kdim=kdim, rel_tol=g["rel_tol"], abs_tol=g["abs_tol"],
+                               max_iter=g["max_iter"])
+    x, info = gm.Mult(c["pat"], c["t"](g["B_bc"]), values=vals, dinv=dinv)
+    assert info["converged"] and g[f"gmres{kdim}_converged"]
+    assert abs(info["final_iter"] - g[f"gmres{kdim}_final_iter"]) <= 2
+    assert abs(info["initial_norm"] / g[f"gmres{kdim}_initial_norm"] - 1) < 1e-12
+    assert rel_l2(x.cpu().numpy(), g[f"x_gmres{kdim}"]) < 1e-7
+    x2, info2 = gm.Mult(c["pat"], c["t"](g["B_bc"]), values=vals, dinv=dinv)
+    assert info2 == info and c["torch"].equal(x, x2)  # deterministic
+
+
+def test_gmres_exits_like_mfem(case):
+    c, g = case, case["g"]
+    vals, _ = _eliminated(c)
+    dinv = _dinv(c, vals)
+    n = c["pat"].num_rows
+    gm5 = c["capi"].GMRESSolver(n, kdim=5, rel_tol=g["rel_tol"], max_iter=7)  # stops inside the second cycle
+    x, info = gm5.Mult(c["pat"], c["t"](g["B_bc"]), values=vals, dinv=dinv)
+    assert not info["converged"] and info["final_iter"] == 7 == g["gmres5m7_final_iter"]
+    assert rel_l2(x.cpu().numpy(), g["x_gmres5_maxiter7"]) < 1e-10
+    assert abs(info["final_norm"] / g["gmres5m7_final_norm"] - 1) < 1e-8
+    gm = c["capi"].GMRESSolver(n, kdim=20, rel_tol=g["rel_tol"], max_iter=g["max_iter"])
+    xg, ig = gm.Mult(c["pat"], c["t"](g["B_bc"]), x=c["t"](g["X"]).clone(), values=vals, dinv=dinv, iterative_mode=True)
+    assert ig["converged"] and abs(ig["final_iter"] - g["gmres20g_final_iter"]) <= 2
+    assert rel_l2(xg.cpu().numpy(), g["x_gmres20_guess"]) < 1e-7
+    # matrix-free operator under GMRES
+    P = c["P"]
+    P.F(0.0, [P.S, P.U, P.A], wrt=1)
+    op = c["capi"].GradientOperator(P.F, 1, g["ess"])
+    xo, io = gm.Mult(op, c["t"](g["B_bc"]), dinv=dinv)
+    assert io["converged"] and rel_l2(xo.cpu().numpy(), g["x_gmres20"]) < 1e-7
+
+
 def test_matrix_free_operator_equals_eliminated_matrix(case):
     """[J_ii 0; 0 I] through Gradient::Mult == the eliminated assembled matrix (check_gradient.hpp:34-44 with BCs)"""
     c, g, P = case, case["g"], case["P"]
@@ -204,14 +243,15 @@ def export_newton_case(d):
 
 def check_newton_outputs(d, g):
     from test_gpu_cpp_functional import out
-    for tag in ("", "_mf"):  # assembled-matrix CG, then matrix-free CG over Gradient::Mult
+    for tag in ("", "_mf", "_gmres"):  # assembled-matrix CG, matrix-free CG over Gradient::Mult, GMRES(50)
         norms, iters, u = out(d, "residual_norms" + tag), out(d, "cg_iterations" + tag), out(d, "u" + tag)
         ref_norms = g["residual_norms"]
         assert len(norms) == len(ref_norms), (tag, norms, ref_norms)
         # each linear solve stops at rel_tol: the iterates agree to ~1e-10, so a residual of 1e-8 agrees to ~1e-3 relative
         assert all(abs(a / b - 1) < 1e-3 for a, b in zip(norms[:-1], ref_norms[:-1])), (tag, norms, ref_norms)
         assert norms[-1] < 1e-11 * norms[0]
-        assert all(abs(int(a) - int(b)) <= 2 for a, b in zip(iters, g["cg_iterations"])), (tag, iters)
+        if tag != "_gmres":  # the fixture's linear solver is CG
+            assert all(abs(int(a) - int(b)) <= 2 for a, b in zip(iters, g["cg_iterations"])), (tag, iters)
         assert rel_l2(u, g["u"]) < 1e-8, tag
         assert not u[g["ess"]].any()
 
@@ -224,3 +264,57 @@ def test_cpp_newton_solve_on_the_device(tmp_path, cuda):
     g = export_newton_case(d)
     run("newton", d)
     check_newton_outputs(d, g)
+
+
+CPP_KRYLOV_CASES = ["krylov_solid_neohookean_hex_p2_patch", "krylov_solid_neohookean_tet_p2_cart"]
+
+
+def export_krylov_case(name, d):
+    """inputs of `functional_test krylov`"""
+    import os
+    from test_gpu_cpp_functional import export
+    g = load_golden(name)
+    export(load_golden(g["source"]), d)
+    g["ess"].astype(np.int32).tofile(os.path.join(d, "ess.bin"))
+    g["B_bc"].tofile(os.path.join(d, "B_bc.bin"))
+    g["X"].tofile(os.path.join(d, "X.bin"))
+    with open(os.path.join(d, "meta.txt"), "a") as f:
+        for k in ("rel_tol", "max_iter", "jacobi"):
+            f.write(f"{k} {float(g[k])!r}\n")
+    return g
+
+
+def check_krylov_outputs(d, g):
+    from test_gpu_cpp_functional import out
+    assert rel_l2(out(d, "values_elim"), g["values_elim"]) < 1e-12 and rel_l2(out(d, "values_e"), g["values_e"]) < 1e-12
+    # the structural part of the elimination is exact
+    assert np.array_equal(out(d, "values_elim") == 0.0, g["values_elim"] == 0.0)
+
+    def check(name, x_key, prefix, exact_iters=False):
+        conv, iters, n0, n1 = out(d, "info_" + name)
+        assert bool(conv) == bool(g[prefix + "_converged"]), name
+        if exact_iters:
+            assert int(iters) == int(g[prefix + "_final_iter"]), name
+        else:
+            assert abs(int(iters) - int(g[prefix + "_final_iter"])) <= 2, (name, iters, g[prefix + "_final_iter"])
+        assert abs(n0 / g[prefix + "_initial_norm"] - 1) < 1e-10, name
+        assert rel_l2(out(d, "x_" + name), g[x_key]) < (1e-10 if exact_iters else 1e-7), name
+
+    check("cg", "x", "cg")
+    check("gmres20", "x_gmres20", "gmres20")
+    check("gmres50", "x_gmres50", "gmres50")
+    check("gmres20_guess", "x_gmres20_guess", "gmres20g")
+    check("gmres5_maxiter7", "x_gmres5_maxiter7", "gmres5m7", exact_iters=True)
+    conv, iters, _, _ = out(d, "info_gmres20_mf")  # matrix-free: same system up to summation order
+    assert conv and abs(int(iters) - int(g["gmres20_final_iter"])) <= 2
+    assert rel_l2(out(d, "x_gmres20_mf"), g["x_gmres20"]) < 1e-7
+
+
+@pytest.mark.parametrize("name", CPP_KRYLOV_CASES)
+def test_cpp_linear_solvers_match_mfem(name, tmp_path, cuda):
+    """serac::CGSolver / serac::GMRESSolver (serac_b200/solvers.hpp) under the C++ Functional against mfem's solvers"""
+    from test_gpu_cpp_functional import run
+    d = str(tmp_path)
+    g = export_krylov_case(name, d)
+    run("krylov", d)
+    check_krylov_outputs(d, g)
