@@ -153,6 +153,16 @@ struct QuadratureData {
     SERAC_B200_CUDA(cudaMemcpy(h.data(), data, sizeof(T) * size_t(count), cudaMemcpyDeviceToHost));
     return h;
   }
+  /// restore the state from a checkpoint written with to_host() (the reference saves / reloads quadrature data through
+  /// sidre next to the fields, src/serac/physics/state/state_manager.cpp:213-224; the storage format stays the host's)
+  void from_host(const std::vector<T>& h)
+  {
+    if (int64_t(h.size()) != count) {
+      std::fprintf(stderr, "QuadratureData::from_host: %zu states given, %lld expected\n", h.size(), (long long)count);
+      std::abort();
+    }
+    SERAC_B200_CUDA(cudaMemcpy(data, h.data(), sizeof(T) * size_t(count), cudaMemcpyHostToDevice));
+  }
   int64_t count;
   T*      data = nullptr;
 };
