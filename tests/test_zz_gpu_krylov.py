@@ -318,3 +318,46 @@ def test_cpp_linear_solvers_match_mfem(name, tmp_path, cuda):
     g = export_krylov_case(name, d)
     run("krylov", d)
     check_krylov_outputs(d, g)
+
+
+def test_solver_layer_at_config_a_size(cuda):
+    """BASELINE.json configs[1] at full size (839 619 rows, ~1.6e8 nonzeros): the solver layer through size-independent
+    properties -- the eliminated assembled matrix and the matrix-free operator agree; the host running ahead of the CG
+    verdict changes nothing; CG's recurrence residual is the true residual; GMRES's preconditioned residual norm never
+    grows and the norm it reports at the max_iter exit is the true one."""
+    import torch
+    from serac_b200 import capi
+    P = Product(load_golden("config_a_beam_hex_r4_p2"), cuda)
+    n = P.G.LSize()
+    ess = np.arange(0, 3 * (n // 3 // 64), dtype=np.int32)
+    P.F(0.0, [P.S, P.U, P.A], wrt=1)
+    pat, vals = P.F.assemble(1)
+    capi.eliminate_rows_cols(pat, vals, ess, want_Ae=False)
+    dinv = capi.jacobi_setup(capi.csr_diagonal(pat, vals))
+    assert bool(torch.isfinite(dinv).all()) and bool((dinv > 0).all())  # positive diagonal
+    op = capi.GradientOperator(P.F, 1, ess)
+    y_csr, y_mf = capi.csr_spmv(pat, vals, P.dU), op.Mult(P.dU)
+    assert rel_l2(y_mf.cpu().numpy(), y_csr.cpu().numpy()) < 1e-11
+    assert torch.equal(y_csr[:len(ess)], P.dU[:len(ess)])  # identity on the essential rows
+    b = y_csr.clone()  # a system with a known solution
+
+    def b_norm(r):  # sqrt((B r, r))
+        return float(np.sqrt(capi.vector_dot(r, dinv * r)))
+
+    x1, i1 = capi.CGSolver(n, rel_tol=1e-12, max_iter=40).Mult(pat, b, values=vals, dinv=dinv)
+    x8, i8 = capi.CGSolver(n, rel_tol=1e-12, max_iter=40, check_every=8).Mult(pat, b, values=vals, dinv=dinv)
+    assert i1 == i8 and torch.equal(x1, x8)
+    assert i1["final_iter"] == 40 or i1["converged"]
+    assert i1["final_norm"] < i1["initial_norm"]
+    r_true = b - capi.csr_spmv(pat, vals, x1)
+    assert abs(b_norm(r_true) / i1["final_norm"] - 1) < 1e-3
+    xm, im = capi.CGSolver(n, rel_tol=1e-12, max_iter=40, check_every=8).Mult(op, b, dinv=dinv)  # matrix-free
+    # same Krylov space up to the operators' summation order; rounding differences grow with the iteration count
+    assert im["final_iter"] == i1["final_iter"] and rel_l2(xm.cpu().numpy(), x1.cpu().numpy()) < 1e-6
+    xg, ig = capi.GMRESSolver(n, kdim=20, rel_tol=1e-12, max_iter=40).Mult(pat, b, values=vals, dinv=dinv)
+    assert not ig["converged"] and ig["final_iter"] == 40 and ig["final_norm"] <= ig["initial_norm"]
+    rg = dinv * (b - capi.csr_spmv(pat, vals, xg))
+    assert abs(float(np.sqrt(capi.vector_dot(rg, rg))) / ig["final_norm"] - 1) < 1e-9
+    # both iterations move towards the known solution
+    e0 = float(torch.linalg.norm(P.dU))
+    assert float(torch.linalg.norm(x1 - P.dU)) < e0 and float(torch.linalg.norm(xg - P.dU)) < e0
