@@ -77,3 +77,40 @@ def test_no_cpu_fallback_without_gpu():
     info = np.zeros((1, 8), dtype=np.uint64)
     with pytest.raises(capi.SeracB200Error):
         capi.ElementRestriction(info, 3, 8)  # needs device memory: must fail loudly, not fall back
+
+
+def test_abi_headers_are_plain_c():
+    """the drop-in boundary is a C ABI: both headers must compile as C99 (no C++ or torch types in the signatures)"""
+    import glob
+    import shutil
+    import subprocess
+    gcc = shutil.which("gcc")
+    if gcc is None:
+        pytest.skip("no gcc")
+    for path in sorted(glob.glob(os.path.join(ROOT, "include", "*.h"))):
+        res = subprocess.run([gcc, "-std=c99", "-pedantic", "-Wall", "-Werror", "-fsyntax-only", "-x", "c", path],
+                             capture_output=True, text=True)
+        assert res.returncode == 0, res.stderr
+
+
+def test_solver_option_structs_match_the_header():
+    """ctypes mirrors of sb_cg_options / sb_cg_result have the C layout (checked against a tiny C program)"""
+    import shutil
+    import subprocess
+    import tempfile
+    gcc = shutil.which("gcc")
+    if gcc is None:
+        pytest.skip("no gcc")
+    src = ('#include <stdio.h>\n#include <stddef.h>\n#include "serac_b200_solvers.h"\n'
+           'int main(void){printf("%zu %zu %zu %zu %zu %zu\\n", sizeof(sb_cg_options), offsetof(sb_cg_options, max_iter),'
+           ' offsetof(sb_cg_options, check_every), sizeof(sb_cg_result), offsetof(sb_cg_result, initial_norm),'
+           ' offsetof(sb_cg_result, final_norm)); return 0;}\n')
+    with tempfile.TemporaryDirectory() as d:
+        c = os.path.join(d, "layout.c")
+        open(c, "w").write(src)
+        exe = os.path.join(d, "layout")
+        subprocess.check_call([gcc, "-I", os.path.join(ROOT, "include"), c, "-o", exe])
+        got = [int(v) for v in subprocess.check_output([exe], text=True).split()]
+    want = [C.sizeof(capi.CgOptions), capi.CgOptions.max_iter.offset, capi.CgOptions.check_every.offset,
+            C.sizeof(capi.CgResult), capi.CgResult.initial_norm.offset, capi.CgResult.final_norm.offset]
+    assert got == want
