@@ -79,7 +79,9 @@ int sb_functional_gradient_operator_apply(void* gradient_operator, const double*
 typedef struct {
   double rel_tol, abs_tol; /* IterativeSolver::SetRelTol / SetAbsTol */
   int    max_iter;         /* SetMaxIter */
-  int    iterative_mode;   /* 0: x = 0 initially (the default of serac's solvers); 1: x holds the initial guess */
+  int    iterative_mode;   /* 1: x holds the initial guess (mfem::IterativeSolver's default, solvers.cpp:29-30);
+                              0: x = 0 initially (what Newton drivers set on their linear solver,
+                              src/serac/numerics/equation_solver.cpp:96) */
   int    check_every;      /* >= 1 */
 } sb_cg_options;
 

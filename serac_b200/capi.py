@@ -512,6 +512,13 @@ def vector_dot(x, y):
     return out.value
 
 
+def copy_subvector(v, src, ess):
+    """v[ess] = src[ess] (the essential rows of the warm-start right-hand side, solid_mechanics.hpp:1757-1760)"""
+    ess = _ess_tensor(ess, v.device)
+    check(lib().sb_vector_copy_subvector(_dev_ptr(v), _dev_ptr(src), _dev_ptr(ess), ess.numel(), _stream_ptr()))
+    return v
+
+
 def csr_spmv(pattern, values, x, out=None):
     import torch
     if out is None:

@@ -180,7 +180,9 @@ class CGSolver {
     resize(op.Height());
   }
   void SetPreconditioner(const JacobiSmoother& prec) { prec_ = &prec; }
-  bool iterative_mode = false;
+  /// mfem::IterativeSolver's default (solvers.cpp:29-30): x holds the initial guess; Newton drivers set it to false on
+  /// their linear solver (src/serac/numerics/equation_solver.cpp:96)
+  bool iterative_mode = true;
 
   /// CGSolver::Mult (solvers.cpp:719-897)
   void Mult(const Vector& b, Vector& x) const
@@ -249,7 +251,9 @@ class GMRESSolver {
     resize(op.Height());
   }
   void SetPreconditioner(const JacobiSmoother& prec) { prec_ = &prec; }
-  bool iterative_mode = false;
+  /// mfem::IterativeSolver's default (solvers.cpp:29-30): x holds the initial guess; Newton drivers set it to false on
+  /// their linear solver (src/serac/numerics/equation_solver.cpp:96)
+  bool iterative_mode = true;
 
   void Mult(const Vector& b, Vector& x) const
   {

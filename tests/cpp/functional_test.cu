@@ -161,10 +161,12 @@ int run_newton(const std::map<std::string, double>& meta, bool matrix_free, bool
   cg.SetRelTol(meta.at("rel_tol"));
   cg.SetAbsTol(0.0);
   cg.SetMaxIter(int(meta.at("max_iter")));
+  cg.iterative_mode = false;  // equation_solver.cpp:96: the Newton driver's linear solver starts from zero
   GMRESSolver gmres;
   gmres.SetRelTol(meta.at("rel_tol"));
   gmres.SetAbsTol(0.0);
   gmres.SetMaxIter(int(meta.at("max_iter")));
+  gmres.iterative_mode = false;
   std::vector<double> norms, cg_iters;
   for (int it = 0; it < int(meta.at("newton_max")); it++) {
     auto [r, drdu] = residual(0.0, S, differentiate_wrt(u), A);
@@ -251,6 +253,7 @@ int run_krylov(const std::map<std::string, double>& meta)
     cg.SetMaxIter(int(meta.at("max_iter")));
     cg.SetOperator(*J);
     if (jacobi) cg.SetPreconditioner(prec);
+    cg.iterative_mode = false;
     cg.Mult(B, x);
     report("cg", cg);
   }
@@ -261,6 +264,7 @@ int run_krylov(const std::map<std::string, double>& meta)
     gmres.SetMaxIter(int(meta.at("max_iter")));
     gmres.SetOperator(*J);
     if (jacobi) gmres.SetPreconditioner(prec);
+    gmres.iterative_mode = false;
     gmres.Mult(B, x);
     report("gmres" + std::to_string(kdim), gmres);
     if (kdim == 20) {
@@ -281,6 +285,7 @@ int run_krylov(const std::map<std::string, double>& meta)
     gmres.SetMaxIter(7);
     gmres.SetOperator(*J);
     if (jacobi) gmres.SetPreconditioner(prec);
+    gmres.iterative_mode = false;
     gmres.Mult(B, x);
     report("gmres5_maxiter7", gmres);
   }

@@ -104,3 +104,25 @@ def test_gmres_exits_like_mfem(case):
     xg, ig = _gmres(case, kdim=20, max_iter=case["max_iter"], x0=case["X"])
     assert ig["converged"] and abs(ig["final_iter"] - case["gmres20g_final_iter"]) <= 1
     assert rel_l2(xg, case["x_gmres20_guess"]) < 1e-7
+
+
+def test_warm_start_fixture_restated():
+    """SolidMechanics::warmStartDisplacement (solid_mechanics.hpp:1727-1771) on the reference's Jacobian: EliminateBC,
+    the essential rows, and the GMRES solve restated in numpy reproduce the fixture"""
+    g = load_golden("warmstart_solid_neohookean_hex_p2_patch")
+    src = load_golden(g["source"])
+    rp, ci = src["row_ptr"].astype(np.int64), src["col_ind"].astype(np.int64)
+    ess, n = g["ess"], len(g["u0"])
+    du0 = np.zeros(n)
+    du0[ess] = g["prescribed"] - g["u0"][ess]
+    rhs = ko.eliminate_bc(rp, ci, g["values_elim"], g["values_e"], ess, du0, -g["r"])
+    rhs[ess] = du0[ess]
+    assert rel_l2(rhs, g["rhs"]) < 1e-14
+    A = g["values_elim"]
+    dinv = ko.jacobi_dinv(ko.diagonal(rp, ci, A))
+    du, info = ko.gmres(lambda v: ko.spmv(rp, ci, A, v), rhs, dinv=dinv, kdim=50, rel_tol=g["rel_tol"],
+                        max_iter=g["max_iter"], x0=du0)
+    assert info["converged"] and abs(info["final_iter"] - g["gmres_iterations"]) <= 1
+    assert rel_l2(du, g["du"]) < 1e-7
+    assert np.array_equal(du[ess], du0[ess]) or rel_l2(du[ess], du0[ess]) < 1e-12  # the prescribed increments
+    assert g["residual_after"] < 1e-3 * g["residual_before"]  # one linearized step: second-order small

@@ -320,6 +320,41 @@ def test_cpp_linear_solvers_match_mfem(name, tmp_path, cuda):
     check_krylov_outputs(d, g)
 
 
+def test_warm_start_displacement(cuda):
+    """SolidMechanics::warmStartDisplacement (solid_mechanics.hpp:1727-1771) on the device: new essential values at an
+    equilibrium state -> du on the essential dofs, r = -residual, assemble + eliminate, mfem::EliminateBC, essential rows
+    = the increments, GMRES(50) + Jacobi from du as the initial guess -- against the same steps done by the reference's
+    kernels and mfem (tests/golden/warmstart_*.npz)."""
+    import torch
+    from serac_b200 import capi
+    g = load_golden("warmstart_solid_neohookean_hex_p2_patch")
+    P = Product(load_golden(g["source"]), cuda)
+    t = lambda a: torch.as_tensor(np.ascontiguousarray(a, dtype=np.float64), device=cuda)
+    n, ess = P.G.LSize(), g["ess"]
+    u0, a = t(g["u0"]), float(g["force_scale"]) * P.A
+    du0 = np.zeros(n)
+    du0[ess] = g["prescribed"] - g["u0"][ess]
+    du = t(du0)
+    r = P.F(0.0, [P.S, u0, a], wrt=1)
+    assert rel_l2(r.cpu().numpy(), g["r"]) < 1e-10  # the residual at equilibrium is reactions only
+    pat, vals = P.F.assemble(1)
+    Ae = capi.eliminate_rows_cols(pat, vals, ess)
+    assert rel_l2(vals.cpu().numpy(), g["values_elim"]) < 1e-12 and rel_l2(Ae.cpu().numpy(), g["values_e"]) < 1e-12
+    rhs = -r
+    capi.eliminate_bc(pat, vals, Ae, ess, du, rhs)
+    capi.copy_subvector(rhs, du, ess)
+    assert rel_l2(rhs.cpu().numpy(), g["rhs"]) < 1e-12
+    dinv = capi.jacobi_setup(capi.csr_diagonal(pat, vals))
+    gm = capi.GMRESSolver(n, kdim=50, rel_tol=float(g["rel_tol"]), max_iter=int(g["max_iter"]))
+    x, info = gm.Mult(pat, rhs, x=du.clone(), values=vals, dinv=dinv, iterative_mode=True)
+    assert info["converged"] and abs(info["final_iter"] - int(g["gmres_iterations"])) <= 2
+    assert rel_l2(x.cpu().numpy(), g["du"]) < 1e-7
+    # one linearized step from equilibrium leaves a second-order residual
+    r1 = P.F(0.0, [P.S, u0 + x, a])
+    capi.set_subvector(r1, ess, 0.0)
+    assert abs(float(torch.linalg.norm(r1)) / float(g["residual_after"]) - 1) < 1e-4
+
+
 def test_solver_layer_at_config_a_size(cuda):
     """BASELINE.json configs[1] at full size (839 619 rows, ~1.6e8 nonzeros): the solver layer through size-independent
     properties -- the eliminated assembled matrix and the matrix-free operator agree; the host running ahead of the CG
