@@ -355,6 +355,38 @@ def test_warm_start_displacement(cuda):
     assert abs(float(torch.linalg.norm(r1)) / float(g["residual_after"]) - 1) < 1e-4
 
 
+@pytest.mark.parametrize("name", ["solid_neohookean_hex_p2_patch", "solid_linear_isotropic_hex_p2_cart",
+                                  "solid_neohookean_tet_p2_cart"])
+def test_implicit_dynamics_jacobian(name, cuda):
+    """The second-order Jacobian of SolidMechanics (solid_mechanics.hpp:1187-1207): K = dR/du and M = dR/da assembled
+    into the same pattern, J = M + c0 K (mfem::Add), essential dofs eliminated -- checked through its action against the
+    reference's Jacobian actions (dr_da + c0 dr of the fixture) and solved with CG (M + c0 K is symmetric positive
+    definite)."""
+    import torch
+    from serac_b200 import capi
+    prob = load_golden(name)
+    P = Product(prob, cuda)
+    c0 = 0.25 * 0.01 ** 2  # Newmark beta dt^2
+    P.F(0.0, [P.S, P.U, P.A], wrt=1)
+    pat_k, K = P.F.assemble(1)
+    P.F(0.0, [P.S, P.U, P.A], wrt=2)
+    pat_m, M = P.F.assemble(2)
+    rp_k, ci_k = pat_k.to_host()
+    rp_m, ci_m = pat_m.to_host()
+    assert np.array_equal(rp_k, rp_m) and np.array_equal(ci_k, ci_m)  # same spaces, same graph
+    J = M.clone()
+    capi.vector_axpy(J, c0, K)  # J = M + c0 K
+    want = prob["dr_da"] + c0 * prob["dr"]
+    assert rel_l2(capi.csr_spmv(pat_k, J, P.dU).cpu().numpy(), want) < 1e-12
+    n = P.G.LSize()
+    ess = np.arange(0, n, 7, dtype=np.int32)
+    capi.eliminate_rows_cols(pat_k, J, ess, want_Ae=False)
+    dinv = capi.jacobi_setup(capi.csr_diagonal(pat_k, J))
+    b = capi.csr_spmv(pat_k, J, P.dU)  # known solution
+    x, info = capi.CGSolver(n, rel_tol=1e-12, max_iter=2000).Mult(pat_k, b, values=J, dinv=dinv)
+    assert info["converged"] and rel_l2(x.cpu().numpy(), P.dU.cpu().numpy()) < 1e-8
+
+
 def test_solver_layer_at_config_a_size(cuda):
     """BASELINE.json configs[1] at full size (839 619 rows, ~1.6e8 nonzeros): the solver layer through size-independent
     properties -- the eliminated assembled matrix and the matrix-free operator agree; the host running ahead of the CG
