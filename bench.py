@@ -453,9 +453,63 @@ def run_product(args):
     }
     if halo_ms is not None:
         out["phases_ms"]["halo_exchange_3P_1Pt"] = halo_ms
+    if args.gpus == 1 and world == 1 and not args.no_solver_layer and not args.no_graph:  # (--no-graph = ncu captures)
+        # outside the timed step: the Newton step's linear algebra on the same problem.  Reported
+        # beside the headline, never part of it; a failure here is recorded, not raised
+        try:
+            out["solver_layer"] = solver_layer_sample(P, dev, peak)
+        except Exception as e:  # noqa: BLE001
+            out["solver_layer"] = {"error": f"{type(e).__name__}: {e}"[:300]}
     if args.gpus == 1 and world == 1 and not args.no_cpu_baseline:
         out["cpu_baseline"] = cpu_baseline_sample()
     print(json.dumps(out))
+
+
+def solver_layer_sample(P, dev, peak):
+    """SpMV / CG / GMRES on the eliminated config-A Jacobian (include/serac_b200_solvers.h): CUDA-event times on the
+    stream the kernels are launched on, algorithmic bytes = 12 B per nonzero + 16 B per row for y = A x."""
+    import torch
+    capi, F, G = P["capi"], P["F"], P["G"]
+    t64 = lambda a: torch.as_tensor(a, dtype=torch.float64, device=dev)
+    U, A, S, dU = (t64(P["host"][k]) for k in ("U", "A", "S", "dU"))
+    n = G.LSize()
+    F(0.0, [S, U, A], wrt=1)
+    pat, vals = F.assemble(1)
+    ess = np.arange(0, 3 * (n // 3 // 64), dtype=np.int32)
+    capi.eliminate_rows_cols(pat, vals, ess, want_Ae=False)
+    dinv = capi.jacobi_setup(capi.csr_diagonal(pat, vals))
+    y = torch.empty(n, dtype=torch.float64, device=dev)
+
+    def timed(fn, reps):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize()
+        e0.record()
+        for _ in range(reps):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / reps
+
+    timed(lambda: capi.csr_spmv(pat, vals, dU, out=y), 3)
+    spmv_ms = timed(lambda: capi.csr_spmv(pat, vals, dU, out=y), 10)
+    nnz = int(pat.nnz)
+    spmv_gbs = (12.0 * nnz + 16.0 * n) / (spmv_ms * 1e-3) / 1e9
+    b = y.clone()
+    res = {"workload": "eliminated NeoHookean Jacobian of config A", "rows": int(n), "nnz": nnz,
+           "spmv_ms": spmv_ms, "spmv_gbs": spmv_gbs, "spmv_frac_of_hbm_peak": spmv_gbs / peak,
+           "note": "outside the timed step; 50 iterations each, tolerances 0 so that exactly 50 run"}
+    iters = 50
+    for name, solver, kw in (("cg_jacobi", capi.CGSolver(n, rel_tol=0.0, abs_tol=0.0, max_iter=iters, check_every=10), {}),
+                             ("gmres50_jacobi", capi.GMRESSolver(n, kdim=50, rel_tol=0.0, abs_tol=0.0, max_iter=iters), {})):
+        solver.Mult(pat, b, values=vals, dinv=dinv)  # warm-up
+        capi.lib().sb_launch_count_reset()
+        box = {}
+        ms = timed(lambda: box.update(info=solver.Mult(pat, b, values=vals, dinv=dinv)[1]), 1)
+        info = box["info"]
+        res[name] = {"iterations": int(info["final_iter"]), "ms_per_iteration": ms / max(int(info["final_iter"]), 1),
+                     "launches": int(capi.lib().sb_launch_count()),
+                     "residual_reduction": float(info["final_norm"] / info["initial_norm"])}
+    return res
 
 
 # ---------------------------------------------------------------------------------------------------------------------
@@ -540,6 +594,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-solver-layer", action="store_true",
+                    help="skip the out-of-step sample of the Newton-step linear algebra (solver_layer key)")
     ap.add_argument("--no-graph", action="store_true", help="launch the step kernel by kernel (for ncu captures)")
     args = ap.parse_args()
     if args.impl == "reference":
