@@ -12,6 +12,8 @@
 //     newton    the solid problem solved the way SolidMechanics::quasiStaticSolve does: Newton on the residual with the
 //               essential rows zeroed, Jacobian = assemble + EliminateRowsCols, CG + Jacobi -- every step on the device;
 //               once with the assembled matrix and once matrix-free over Gradient::Mult
+//     equation_solver  the reference's EquationSolverSuite (numerics/tests/equationsolver.cpp): Newton + CG / GMRES
+//               + Jacobi on sin-reaction-diffusion, known answer
 //     krylov    CGSolver / GMRESSolver (assembled and matrix-free) on the eliminated Jacobian at the fixture's state
 //     qoi       Functional<double(H1<2,3>)> with a q-function defined in this file: value, directional derivative, gradient
 // Directory layout: <name>.bin raw little-endian arrays (int32 / float64), meta.txt "key value" lines.
@@ -414,6 +416,97 @@ int run_user(const std::map<std::string, double>& meta)
   return ok ? 0 : 1;
 }
 
+/// the q-function of the reference's own solver test (src/serac/numerics/tests/equationsolver.cpp:66-73)
+struct SineReactionDiffusion {
+  template <typename X, typename T>
+  SERAC_HOST_DEVICE auto operator()(double /*t*/, X /*x*/, T scalar) const
+  {
+    auto u      = get<0>(scalar);
+    auto du_dx  = get<1>(scalar);
+    auto source = 0.5 * sin(u);
+    auto flux   = du_dx;
+    return serac::tuple{source, flux};
+  }
+};
+
+/// EquationSolverSuite of the reference (src/serac/numerics/tests/equationsolver.cpp:33-121), on this fixture's mesh:
+/// solve r(x) - r(x_exact) = 0 from x = 0 with Newton (mfem::NewtonSolver's loop: stop at ||r|| <= max(rel ||r0||, abs))
+/// and CG / GMRES + Jacobi (tolerances of the reference test), every step on the device; the reference's assertion is
+/// |x_i - x_exact_i| / x_exact_i < 1e-6 for every dof.
+int run_equation_solver(const std::map<std::string, double>& meta)
+{
+  Problem P = load_problem(meta, false);
+  Functional<H1<p>(H1<p>)> residual(&P.scalar_space, {&P.scalar_space});
+  Domain whole = EntireDomain(P.mesh);
+  residual.AddDomainIntegral(Dimension<dim>{}, DependsOn<0>{}, SineReactionDiffusion{}, whole);
+  const int64_t       n = P.scalar_space.GetVSize();
+  std::vector<double> xe(static_cast<size_t>(n));
+  unsigned long long  lcg = 12345;  // x_exact.Randomize(0): uniform values; kept away from 0 for the relative test
+  for (auto& v : xe) {
+    lcg = lcg * 6364136223846793005ULL + 1442695040888963407ULL;
+    v   = 0.1 + 0.9 * double(lcg >> 11) / double(1ULL << 53);
+  }
+  Vector x_exact(xe);
+  Vector r_exact = residual(0.0, x_exact);  // copy: the Functional's output vector is reused by the next call
+  DofList no_ess{std::vector<int>{}};
+  bool    all_ok = true;
+  for (int which = 0; which < 3; which++) {  // CG (assembled), GMRES (assembled), GMRES (matrix-free)
+    Vector x(n), dx(n), r(n);
+    x = 0.0;
+    CGSolver    cg;
+    GMRESSolver gmres;
+    cg.SetRelTol(1.0e-10);
+    cg.SetAbsTol(1.0e-12);
+    cg.SetMaxIter(500);
+    cg.iterative_mode = false;
+    gmres.SetRelTol(1.0e-10);
+    gmres.SetAbsTol(1.0e-12);
+    gmres.SetMaxIter(500);
+    gmres.iterative_mode = false;
+    double norm0 = 0.0, norm = 0.0;
+    int    it = 0, linear_its = 0;
+    for (;; it++) {
+      auto [val, grad] = residual(0.0, differentiate_wrt(x));
+      r                = val;
+      Add(r, -1.0, r_exact);  // r -= residual(x_exact)
+      norm = Norml2(r);
+      if (it == 0) norm0 = norm;
+      if (norm <= std::max(1.0e-10 * norm0, 1.0e-12) || it >= 100) break;
+      auto           J = assemble_on_device(grad);
+      JacobiSmoother prec(*J);
+      if (which == 0) {
+        cg.SetOperator(*J);
+        cg.SetPreconditioner(prec);
+        cg.Mult(r, dx);
+        linear_its += cg.GetNumIterations();
+        all_ok = all_ok && cg.GetConverged();
+      } else {
+        GradientOperator op(grad, no_ess);
+        if (which == 1)
+          gmres.SetOperator(*J);
+        else
+          gmres.SetOperator(op);
+        gmres.SetPreconditioner(prec);
+        gmres.Mult(r, dx);
+        linear_its += gmres.GetNumIterations();
+        all_ok = all_ok && gmres.GetConverged();
+      }
+      Add(x, -1.0, dx);
+    }
+    std::vector<double> xc = x.to_host();
+    double              worst = 0.0;
+    for (size_t i = 0; i < xc.size(); i++) worst = std::max(worst, std::abs(xc[i] - xe[i]) / xe[i]);
+    const bool ok = worst < 1.0e-6 && it < 100;
+    std::printf("equation solver [%s]: %d Newton steps, %d linear iterations, |r| %.3e -> %.3e, worst relative error %.3e %s\n",
+                which == 0 ? "CG + Jacobi" : (which == 1 ? "GMRES + Jacobi" : "GMRES + Jacobi, matrix-free"), it, linear_its,
+                norm0, norm, worst, ok ? "PASS" : "FAIL");
+    all_ok = all_ok && ok;
+    write_bin(std::string("x_") + (which == 0 ? "cg" : (which == 1 ? "gmres" : "gmres_mf")), xc);
+  }
+  write_bin("x_exact", xe);
+  return all_ok ? 0 : 1;
+}
+
 /// quantity of interest defined in this file: the integrand of the library's `qoi_quadratic_*` (and of the oracle kind)
 struct QuadraticQoi {
   double a, b;
@@ -489,6 +582,7 @@ int main(int argc, char** argv)
   if (which == "user") rc = run_user(meta);
   if (which == "newton") rc = run_newton(meta, false) || run_newton(meta, true) || run_newton(meta, false, true);
   if (which == "krylov") rc = run_krylov(meta);
+  if (which == "equation_solver") rc = run_equation_solver(meta);
   if (which == "qoi") rc = run_qoi(meta);
   if (which == "boundary_qoi") rc = run_boundary_qoi(meta);
   std::printf("launches: %lld\n", sb_launch_count());

@@ -428,3 +428,19 @@ def test_solver_layer_at_config_a_size(cuda):
     # both iterations move towards the known solution
     e0 = float(torch.linalg.norm(P.dU))
     assert float(torch.linalg.norm(x1 - P.dU)) < e0 and float(torch.linalg.norm(xg - P.dU)) < e0
+
+
+@pytest.mark.parametrize("name", ["solid_neohookean_hex_p2_patch", "solid_neohookean_tet_p2_cart"])
+def test_cpp_equation_solver_suite(name, tmp_path, cuda):
+    """The reference's own known-answer test of the solver stack (src/serac/numerics/tests/equationsolver.cpp:33-121:
+    Functional H1(H1) with source 0.5 sin(u), flux grad u; solve r(x) - r(x_exact) = 0 with Newton and CG / GMRES +
+    Jacobi; assert |x - x_exact| / x_exact < 1e-6 per dof), ported to the C++ host side on this fixture's mesh at p = 2,
+    every step on the device -- with the assembled Jacobian (CG, GMRES) and matrix-free (GMRES)."""
+    from test_gpu_cpp_functional import export, out, run
+    d = str(tmp_path)
+    export(load_golden(name), d)
+    log = run("equation_solver", d)  # non-zero exit (any FAIL) raises
+    assert log.count("PASS") == 3 and "FAIL" not in log, log
+    xe = out(d, "x_exact")
+    for tag in ("cg", "gmres", "gmres_mf"):
+        assert np.max(np.abs(out(d, "x_" + tag) - xe) / xe) < 1e-6
