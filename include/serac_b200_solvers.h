@@ -45,6 +45,13 @@ int sb_csr_spmv(sb_csr_t A, const double* values_dev, const double* x_dev, doubl
 /* diag[i] = A(i,i) (0 if the pattern has no diagonal entry in row i) */
 int sb_csr_diagonal(sb_csr_t A, const double* values_dev, double* diag_dev, void* stream);
 
+/* l1[i] = sum_j |A(i,j)|: the scaling of hypre's l1-Jacobi smoother (mfem::HypreSmoother::l1Jacobi = serac's
+ * Preconditioner::HypreL1Jacobi, HeatTransfer's default, heat_transfer.hpp:34-38; mfem/linalg/hypre.cpp:3630-3632 calls
+ * hypre_ParCSRComputeL1Norms(A, 1, ...): "option 1: the l1 norm of the rows", hypre 2.26.0 -- a third-party dependency
+ * absent from the reference tree, so this entry restates its published definition: parity unpinned).  One sweep from a
+ * zero guess is z = r / l1: pass the result through sb_jacobi_setup and use it as diag_inv_dev. */
+int sb_csr_row_l1_norms(sb_csr_t A, const double* values_dev, double* l1_dev, void* stream);
+
 /* HypreParMatrix::EliminateRowsCols at one rank (hypre_parcsr.cpp:476-489): rows and columns `ess_dofs` of A are zeroed
  * and their diagonal entries set to 1, in place, keeping the pattern; values_e_dev (may be NULL) receives, in the SAME
  * pattern, the eliminated part Ae with Ae(b,b) = A(b,b) - 1, so that A_before = A_after + Ae entry by entry. */

@@ -118,6 +118,7 @@ SIGNATURES = {
     "sb_vector_dot": (_i, [_vp, _vp, _i64, C.POINTER(_d), _vp]),
     "sb_csr_spmv": (_i, [_vp, _vp, _vp, _vp, _vp]),
     "sb_csr_diagonal": (_i, [_vp, _vp, _vp, _vp]),
+    "sb_csr_row_l1_norms": (_i, [_vp, _vp, _vp, _vp]),
     "sb_csr_eliminate_rows_cols": (_i, [_vp, _vp, _vp, _i64, _vp, _vp]),
     "sb_csr_eliminate_bc": (_i, [_vp, _vp, _vp, _vp, _i64, _vp, _vp, _vp]),
     "sb_functional_gradient_operator_create": (_i, [_vp, _i, _i64, _vp, _i64, _pp]),
@@ -531,6 +532,14 @@ def csr_diagonal(pattern, values):
     import torch
     d = torch.empty(pattern.num_rows, dtype=torch.float64, device=values.device)
     check(lib().sb_csr_diagonal(pattern.h, _dev_ptr(values), _dev_ptr(d), _stream_ptr()))
+    return d
+
+
+def csr_row_l1_norms(pattern, values):
+    """sum_j |A(i,j)|: the scaling of HypreSmoother::l1Jacobi (Preconditioner::HypreL1Jacobi)"""
+    import torch
+    d = torch.empty(pattern.num_rows, dtype=torch.float64, device=values.device)
+    check(lib().sb_csr_row_l1_norms(pattern.h, _dev_ptr(values), _dev_ptr(d), _stream_ptr()))
     return d
 
 

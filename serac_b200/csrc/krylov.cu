@@ -208,6 +208,21 @@ __global__ void __launch_bounds__(kThreads) csr_diagonal_kernel(const int* __res
   }
 }
 
+/// l1[row] = sum_j |A(row, j)|, same lane / tree order as the row products
+__global__ void __launch_bounds__(kThreads) csr_row_l1_kernel(const int* __restrict__ row_ptr,
+                                                              const double* __restrict__ values, double* __restrict__ l1,
+                                                              int64_t num_rows)
+{
+  const int     lane  = threadIdx.x & 31;
+  const int64_t warp0 = blockIdx.x * int64_t(kWarpsPerCta) + (threadIdx.x >> 5);
+  for (int64_t row = warp0; row < num_rows; row += int64_t(gridDim.x) * kWarpsPerCta) {
+    double acc = 0.0;
+    for (int j = row_ptr[row] + lane; j < row_ptr[row + 1]; j += 32) acc += fabs(values[j]);
+    acc = warp_sum(acc);
+    if (lane == 0) l1[row] = acc;
+  }
+}
+
 /// A -> [A_ii 0; 0 I], Ae = [0 A_ib; A_bi A_bb - I]   (hypre_parcsr.cpp:476-489)
 __global__ void __launch_bounds__(kThreads) csr_eliminate_kernel(const int* __restrict__ row_ptr,
                                                                  const int* __restrict__ col_ind,
@@ -591,6 +606,19 @@ extern "C" int sb_csr_diagonal(sb_csr_t A, const double* values_dev, double* dia
   SB_REQUIRE(values_dev && diag_dev, "sb_csr_diagonal: null pointer");
   csr_diagonal_kernel<<<reducing_grid(v.num_rows, kWarpsPerCta), kThreads, 0, as_stream(stream)>>>(
       v.row_ptr, v.col_ind, values_dev, diag_dev, v.num_rows);
+  sb_count_launch();
+  SB_CHECK_CUDA(cudaGetLastError());
+  return SB_OK;
+}
+
+extern "C" int sb_csr_row_l1_norms(sb_csr_t A, const double* values_dev, double* l1_dev, void* stream)
+{
+  CsrView v;
+  if (int e = view_of(A, &v)) return e;
+  if (v.num_rows == 0) return SB_OK;
+  SB_REQUIRE(values_dev && l1_dev, "sb_csr_row_l1_norms: null pointer");
+  csr_row_l1_kernel<<<reducing_grid(v.num_rows, kWarpsPerCta), kThreads, 0, as_stream(stream)>>>(v.row_ptr, values_dev,
+                                                                                                  l1_dev, v.num_rows);
   sb_count_launch();
   SB_CHECK_CUDA(cudaGetLastError());
   return SB_OK;

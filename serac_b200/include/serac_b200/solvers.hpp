@@ -125,10 +125,31 @@ class JacobiSmoother {
     dinv_.SetSize(d.Size());
     SERAC_B200_CHECK(sb_jacobi_setup(d.Read(), dinv_.Write(), d.Size(), nullptr));
   }
+  /// from a given scaling vector d: z = r / d
+  explicit JacobiSmoother(const Vector& d)
+  {
+    dinv_.SetSize(d.Size());
+    SERAC_B200_CHECK(sb_jacobi_setup(d.Read(), dinv_.Write(), d.Size(), nullptr));
+  }
   const double* dinv() const { return dinv_.Read(); }
 
  private:
   Vector dinv_;
+};
+
+/// z = r / (sum_j |a_ij|): one sweep of hypre's l1-scaled Jacobi from a zero guess (mfem::HypreSmoother::l1Jacobi,
+/// serac's Preconditioner::HypreL1Jacobi; include/serac_b200_solvers.h: sb_csr_row_l1_norms)
+class L1JacobiSmoother : public JacobiSmoother {
+ public:
+  explicit L1JacobiSmoother(const DeviceCsrMatrix& A) : JacobiSmoother(l1_of(A)) {}
+
+ private:
+  static Vector l1_of(const DeviceCsrMatrix& A)
+  {
+    Vector l1(A.Height());
+    SERAC_B200_CHECK(sb_csr_row_l1_norms(A.pattern(), A.values().Read(), l1.Write(), nullptr));
+    return l1;
+  }
 };
 
 /// matrix-free [J_ii 0; 0 I] over Functional::Gradient (Gradient::Mult, functional.hpp:556-559)

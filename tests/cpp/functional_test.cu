@@ -450,7 +450,7 @@ int run_equation_solver(const std::map<std::string, double>& meta)
   Vector r_exact = residual(0.0, x_exact);  // copy: the Functional's output vector is reused by the next call
   DofList no_ess{std::vector<int>{}};
   bool    all_ok = true;
-  for (int which = 0; which < 3; which++) {  // CG (assembled), GMRES (assembled), GMRES (matrix-free)
+  for (int which = 0; which < 4; which++) {  // CG, GMRES (assembled), GMRES (matrix-free), GMRES + l1-Jacobi (HeatTransfer's default)
     Vector x(n), dx(n), r(n);
     x = 0.0;
     CGSolver    cg;
@@ -472,8 +472,9 @@ int run_equation_solver(const std::map<std::string, double>& meta)
       norm = Norml2(r);
       if (it == 0) norm0 = norm;
       if (norm <= std::max(1.0e-10 * norm0, 1.0e-12) || it >= 100) break;
-      auto           J = assemble_on_device(grad);
-      JacobiSmoother prec(*J);
+      auto             J = assemble_on_device(grad);
+      JacobiSmoother   prec(*J);
+      L1JacobiSmoother prec_l1(*J);
       if (which == 0) {
         cg.SetOperator(*J);
         cg.SetPreconditioner(prec);
@@ -482,11 +483,14 @@ int run_equation_solver(const std::map<std::string, double>& meta)
         all_ok = all_ok && cg.GetConverged();
       } else {
         GradientOperator op(grad, no_ess);
-        if (which == 1)
-          gmres.SetOperator(*J);
-        else
+        if (which == 2)
           gmres.SetOperator(op);
-        gmres.SetPreconditioner(prec);
+        else
+          gmres.SetOperator(*J);
+        if (which == 3)
+          gmres.SetPreconditioner(prec_l1);
+        else
+          gmres.SetPreconditioner(prec);
         gmres.Mult(r, dx);
         linear_its += gmres.GetNumIterations();
         all_ok = all_ok && gmres.GetConverged();
@@ -498,10 +502,10 @@ int run_equation_solver(const std::map<std::string, double>& meta)
     for (size_t i = 0; i < xc.size(); i++) worst = std::max(worst, std::abs(xc[i] - xe[i]) / xe[i]);
     const bool ok = worst < 1.0e-6 && it < 100;
     std::printf("equation solver [%s]: %d Newton steps, %d linear iterations, |r| %.3e -> %.3e, worst relative error %.3e %s\n",
-                which == 0 ? "CG + Jacobi" : (which == 1 ? "GMRES + Jacobi" : "GMRES + Jacobi, matrix-free"), it, linear_its,
+                which == 0 ? "CG + Jacobi" : (which == 1 ? "GMRES + Jacobi" : (which == 2 ? "GMRES + Jacobi, matrix-free" : "GMRES + l1-Jacobi")), it, linear_its,
                 norm0, norm, worst, ok ? "PASS" : "FAIL");
     all_ok = all_ok && ok;
-    write_bin(std::string("x_") + (which == 0 ? "cg" : (which == 1 ? "gmres" : "gmres_mf")), xc);
+    write_bin(std::string("x_") + (which == 0 ? "cg" : (which == 1 ? "gmres" : (which == 2 ? "gmres_mf" : "gmres_l1"))), xc);
   }
   write_bin("x_exact", xe);
   return all_ok ? 0 : 1;

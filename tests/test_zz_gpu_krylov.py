@@ -133,6 +133,22 @@ def test_cg_exits_like_mfem(case):
     assert info0["converged"] and info0["final_iter"] == 0 and not x0.any()
 
 
+def test_l1_jacobi_scaling(case):
+    """HypreSmoother::l1Jacobi (Preconditioner::HypreL1Jacobi): the row l1 norms hypre_ParCSRComputeL1Norms(A, 1) defines
+    (hypre is not in the reference tree: restated, parity unpinned), and GMRES preconditioned with them reaches the
+    solution mfem's Jacobi-preconditioned solve reached"""
+    c, g = case, case["g"]
+    vals, _ = _eliminated(c)
+    l1 = c["capi"].csr_row_l1_norms(c["pat"], vals)
+    rp = c["prob"]["row_ptr"].astype(np.int64)
+    want = np.add.reduceat(np.abs(g["values_elim"]), rp[:-1])
+    assert rel_l2(l1.cpu().numpy(), want) < 1e-14
+    dinv = c["capi"].jacobi_setup(l1)
+    gm = c["capi"].GMRESSolver(c["pat"].num_rows, kdim=50, rel_tol=g["rel_tol"], max_iter=g["max_iter"])
+    x, info = gm.Mult(c["pat"], c["t"](g["B_bc"]), values=vals, dinv=dinv)
+    assert info["converged"] and rel_l2(x.cpu().numpy(), g["x_gmres50"]) < 1e-5
+
+
 @pytest.mark.parametrize("kdim", [20, 50])
 def test_gmres_matches_mfem(case, kdim):
     """mfem::GMRESSolver with restarts (kdim 20) and with mfem's default restart length"""
@@ -435,12 +451,13 @@ def test_cpp_equation_solver_suite(name, tmp_path, cuda):
     """The reference's own known-answer test of the solver stack (src/serac/numerics/tests/equationsolver.cpp:33-121:
     Functional H1(H1) with source 0.5 sin(u), flux grad u; solve r(x) - r(x_exact) = 0 with Newton and CG / GMRES +
     Jacobi; assert |x - x_exact| / x_exact < 1e-6 per dof), ported to the C++ host side on this fixture's mesh at p = 2,
-    every step on the device -- with the assembled Jacobian (CG, GMRES) and matrix-free (GMRES)."""
+    every step on the device -- with the assembled Jacobian (CG, GMRES), matrix-free (GMRES), and with HeatTransfer's default
+    combination GMRES + l1-Jacobi."""
     from test_gpu_cpp_functional import export, out, run
     d = str(tmp_path)
     export(load_golden(name), d)
     log = run("equation_solver", d)  # non-zero exit (any FAIL) raises
-    assert log.count("PASS") == 3 and "FAIL" not in log, log
+    assert log.count("PASS") == 4 and "FAIL" not in log, log
     xe = out(d, "x_exact")
-    for tag in ("cg", "gmres", "gmres_mf"):
+    for tag in ("cg", "gmres", "gmres_mf", "gmres_l1"):
         assert np.max(np.abs(out(d, "x_" + tag) - xe) / xe) < 1e-6
