@@ -126,3 +126,28 @@ def test_warm_start_fixture_restated():
     assert rel_l2(du, g["du"]) < 1e-7
     assert np.array_equal(du[ess], du0[ess]) or rel_l2(du[ess], du0[ess]) < 1e-12  # the prescribed increments
     assert g["residual_after"] < 1e-3 * g["residual_before"]  # one linearized step: second-order small
+
+
+def test_elimination_edge_cases_against_live_mfem(case):
+    """no essential dofs (nothing changes), every dof essential (A = I, Ae = A - I, CG converges in one step): the numpy
+    restatement against the reference's mfem"""
+    from oracle import ref
+    if not ref.available():
+        pytest.skip("oracle/_ref not built")
+    rp, ci, V = case["row_ptr"], case["col_ind"], case["values"]
+    n = len(rp) - 1
+    for ess in (np.zeros(0, dtype=np.int32), np.arange(n, dtype=np.int32), np.array([n - 1], dtype=np.int32)):
+        A, Ae = ko.eliminate_rows_cols(rp, ci, V, ess)
+        A_ref, Ae_ref = ref.eliminate_rows_cols(rp, ci, V, ess)
+        assert np.array_equal(A, A_ref) and np.array_equal(Ae, Ae_ref)
+    A, _ = ko.eliminate_rows_cols(rp, ci, V, np.arange(n))
+    assert np.array_equal(ko.diagonal(rp, ci, A), np.ones(n)) and np.count_nonzero(A) == n
+    x, info = ko.cg(lambda v: ko.spmv(rp, ci, A, v), case["B"], rel_tol=1e-12, max_iter=10)
+    x_ref, info_ref = ref.cg(rp, ci, A, case["B"], jacobi=False, rel_tol=1e-12, max_iter=10)
+    assert info["converged"] and info["final_iter"] == info_ref["final_iter"] == 1 and np.array_equal(x, x_ref)
+    # zero right-hand side: converged at iteration 0 with x = 0 (solvers.cpp:769-775, :1032-1039)
+    for solve, solve_ref in ((ko.cg, ref.cg), (ko.gmres, ref.gmres)):
+        x, info = solve(lambda v: ko.spmv(rp, ci, A, v), np.zeros(n), rel_tol=1e-12, max_iter=10)
+        x_ref, info_ref = solve_ref(rp, ci, A, np.zeros(n), jacobi=False, rel_tol=1e-12, max_iter=10)
+        assert info["converged"] and info_ref["converged"] and info["final_iter"] == info_ref["final_iter"] == 0
+        assert not x.any() and not x_ref.any()
