@@ -117,6 +117,10 @@ def build_problem(device):
 
 
 PER_GPU_BOX = (128, 16, 16)  # hexes per GPU = config A's 32 768 (the beam refined 4x), element size 1/16
+# optional strong-scaling series (SB_BENCH_SCALING=strong, N > 1 only; the default and the driver's series are weak): one
+# fixed 128 x 32 x 32 mesh (131 072 hexes, 3.3 M vdofs) split over the GPUs
+STRONG_SCALING = os.environ.get("SB_BENCH_SCALING", "weak") == "strong"
+STRONG_BOX = (128, 32, 32)
 
 
 def build_partitioned_problem(device, rank, world):
@@ -132,6 +136,10 @@ def build_partitioned_problem(device, rank, world):
         ranks = tuple(int(x) for x in os.environ["SB_BENCH_RANKS"].split(","))
         assert int(np.prod(ranks)) == world
     n = tuple(PER_GPU_BOX[d] * ranks[d] for d in range(3))
+    per_gpu = PER_GPU_BOX
+    if STRONG_SCALING:  # SURVEY.md section 8d "also report": one fixed mesh split over the GPUs
+        assert all(STRONG_BOX[d] % ranks[d] == 0 for d in range(3)), (STRONG_BOX, ranks)
+        n, per_gpu = STRONG_BOX, tuple(STRONG_BOX[d] // ranks[d] for d in range(3))
     mesh = StructuredHexMesh(*n, n[0] / 16.0, n[1] / 16.0, n[2] / 16.0)
     # owned-first local numbering: the T-vector is the prefix of the L-vector, so P / P^T run in place
     inplace = (os.environ.get("SB_HALO_TRANSPORT", "peer") == "peer" and os.environ.get("SB_HALO_OVERLAP", "1") != "0"
@@ -178,7 +186,7 @@ def build_partitioned_problem(device, rank, world):
                 ne=tab.shape[0], nq=tab.shape[0] * (p + 1)**3, vdofs=G.LSize(), tdofs=halo.tsize, tdofs_shape=halo1.tsize,
                 global_vdofs=mesh.num_nodes(p) * 3, p=p, transport=transport, ranks=ranks, keep=(nodes, X_q, J_q),
                 mesh=f"structured {n[0]}x{n[1]}x{n[2]} hexes, {ranks[0]}x{ranks[1]}x{ranks[2]} boxes of "
-                     f"{PER_GPU_BOX[0]}x{PER_GPU_BOX[1]}x{PER_GPU_BOX[2]}")
+                     f"{per_gpu[0]}x{per_gpu[1]}x{per_gpu[2]}" + (" (strong scaling: fixed mesh)" if STRONG_SCALING else ""))
 
 
 ASYNC_E2E = os.environ.get("SB_BENCH_E2E", "async") != "sync"
@@ -422,8 +430,12 @@ def run_product(args):
     out = {
         "metric": METRIC, "value": vdofs_total / (ms_per_step * 1e-3) / 1e9, "unit": "GDOF/s", "n_gpus": world,
         "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True,
-        "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": "configs[1]: SolidMechanics NeoHookean H1 p=2 hex, 32768 hexes / ~840k vdofs / 884736 "
+        "scaling": "strong" if (STRONG_SCALING and world > 1) else "weak", "vs_baseline": None, "dtype": "f64",
+        "data": "synthetic",
+        "config": {"workload": ("strong-scaling variant (SB_BENCH_SCALING=strong): one fixed 128x32x32-hex mesh split over "
+                                "the GPUs; SolidMechanics NeoHookean H1 p=2 hex; step = residual with derivative store + "
+                                "one Jacobian action") if (STRONG_SCALING and world > 1) else
+                               "configs[1]: SolidMechanics NeoHookean H1 p=2 hex, 32768 hexes / ~840k vdofs / 884736 "
                                "qpts per GPU; step = residual with derivative store + one Jacobian action",
                    "mesh": P["mesh"], "vdofs_total": vdofs_total, "vdofs_per_gpu": P["vdofs"],
                    "qpts_per_gpu": P["nq"],
