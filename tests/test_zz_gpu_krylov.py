@@ -188,6 +188,36 @@ def test_gmres_exits_like_mfem(case):
     assert io["converged"] and rel_l2(xo.cpu().numpy(), g["x_gmres20"]) < 1e-7
 
 
+@pytest.mark.parametrize("max_iter", [0, 1, 3])
+def test_iteration_limits_against_live_mfem(case, max_iter):
+    """the exits at tiny iteration limits (solvers.cpp:798, :842-845, :1053, :1140-1142) against the reference's mfem run
+    on the box (oracle/_ref travels with the repository): same flags, same count, same iterate"""
+    from oracle import ref
+    if not ref.available():
+        pytest.skip("oracle/_ref not built")
+    c, g = case, case["g"]
+    vals, _ = _eliminated(c)
+    dinv = _dinv(c, vals)
+    n = c["pat"].num_rows
+    rp, ci = c["prob"]["row_ptr"], c["prob"]["col_ind"]
+    b = c["t"](g["B_bc"])
+    x, info = c["capi"].CGSolver(n, rel_tol=g["rel_tol"], max_iter=max_iter).Mult(c["pat"], b, values=vals, dinv=dinv)
+    x_ref, info_ref = ref.cg(rp, ci, g["values_elim"], g["B_bc"], jacobi=bool(g["jacobi"]), rel_tol=g["rel_tol"],
+                             max_iter=max_iter)
+    assert (info["converged"], info["final_iter"]) == (info_ref["converged"], info_ref["final_iter"])
+    assert rel_l2(x.cpu().numpy(), x_ref) < 1e-12 and abs(info["final_norm"] / info_ref["final_norm"] - 1) < 1e-10
+    gm = c["capi"].GMRESSolver(n, kdim=2, rel_tol=g["rel_tol"], max_iter=max_iter)
+    x, info = gm.Mult(c["pat"], b, values=vals, dinv=dinv)
+    x_ref, info_ref = ref.gmres(rp, ci, g["values_elim"], g["B_bc"], jacobi=bool(g["jacobi"]), kdim=2,
+                                rel_tol=g["rel_tol"], max_iter=max_iter)
+    assert (info["converged"], info["final_iter"]) == (info_ref["converged"], info_ref["final_iter"])
+    assert abs(info["final_norm"] / info_ref["final_norm"] - 1) < 1e-10
+    if max_iter == 0:
+        assert not x.any() and not x_ref.any()
+    else:
+        assert rel_l2(x.cpu().numpy(), x_ref) < 1e-12
+
+
 def test_matrix_free_operator_equals_eliminated_matrix(case):
     """[J_ii 0; 0 I] through Gradient::Mult == the eliminated assembled matrix (check_gradient.hpp:34-44 with BCs)"""
     c, g, P = case, case["g"], case["P"]
