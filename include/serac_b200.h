@@ -155,9 +155,28 @@ typedef struct {
   int           overwrite;      /* 1: K_e = ... instead of K_e += ... (first integral of an assembly: no memset, no read) */
 } sb_elem_grad_args;
 
+/* Fused element-stiffness -> CSR assembly (serac_b200/assemble_rows.cuh): the rows of the matrix are the unit of work.
+ * The index tables come from the assembly plan sb_functional_assemble builds once per (integral, argument); they are
+ * opaque to the caller (layouts: AsmGroup / AsmUnit / AsmNode in assemble_rows.cuh). */
+typedef struct {
+  const double*         dqf_dev;
+  const void*           groups_dev;
+  const void*           units_dev;
+  const void*           nodes_dev;
+  const unsigned short* pos_dev;
+  const int*            row_ptr_dev;
+  double*               values_dev;
+  int64_t               row_node_stride, row_comp_stride; /* test vdof = node * row_node_stride + comp * row_comp_stride */
+  int                   col_byvdim;                       /* trial space ordering (SB_ORDERING_*) */
+  int                   accumulate;                       /* 0: values = rows, 1: values += rows */
+  int                   num_groups;
+  int                   acc_doubles;                      /* shared-memory accumulator the largest group needs */
+} sb_assemble_rows_args;
+
 typedef int (*sb_eval_launcher)(const sb_eval_args*, const void* qf_blob, void* stream);
 typedef int (*sb_jvp_launcher)(const sb_jvp_args*, void* stream);
 typedef int (*sb_elem_grad_launcher)(const sb_elem_grad_args*, void* stream);
+typedef int (*sb_assemble_rows_launcher)(const sb_assemble_rows_args*, void* stream);
 
 typedef struct {
   int    geom;       /* SB_GEOM_* */
@@ -176,6 +195,11 @@ typedef struct {
   int derivative_mask[SB_MAX_TRIALS];    /* bit b: block b of {d00,d01,d10,d11} present */
   int derivative_entries[SB_MAX_TRIALS]; /* doubles stored per quadrature point */
   int spatial_dim; /* == dim for domain integrals; dim + 1 for boundary integrals (geom = the face geometry) */
+  /* fused assembly w.r.t. trial i; NULL where it is not generated (2-D, simplex and boundary integrals, structurally zero
+   * derivatives): sb_functional_assemble then goes through element matrices (element_gradient + sb_csr_accumulate) */
+  sb_assemble_rows_launcher assemble_rows[SB_MAX_TRIALS];
+  int assemble_rows_fixed_doubles[SB_MAX_TRIALS]; /* shared memory the kernel needs besides the accumulator */
+  int assemble_rows_trial_blocks[SB_MAX_TRIALS];  /* blocks the trial components are cut into (one item per block) */
 } sb_kernel_table;
 
 int         sb_named_integrand_count(void);
@@ -223,19 +247,39 @@ int sb_integral_derivative_mask(sb_integral_t I, int wrt);
  *                               Gradient::assemble, F/functional.hpp:569-652)
  * ------------------------------------------------------------------------------------------------------------- */
 /* lookup_tables.init(test, trial): sorted unique (row, col) pairs of all elements -> row_ptr / col_ind (bit-exact with
- * the reference), plus the K_e-entry -> nonzero map that replaces nz_LUT's hash lookups. */
+ * the reference).  Built at node level -- for every test node the sorted union of the trial nodes of its elements -- and
+ * expanded by components on the device, so its cost is the number of NODE pairs of the element matrices, not of their
+ * entries, and nothing limits the number of element-matrix entries (the reference hashes every entry,
+ * F/dof_numbering.hpp:290-351); nnz < 2^31 as in mfem::SparseMatrix. */
 int     sb_csr_create(sb_restriction_t test, sb_restriction_t trial, sb_csr_t* out);
-/* same pattern; K_e_node_major != 0: the object's gather lists address element matrices in the internal node-major
- * layout (see sb_elem_grad_args), which only sb_functional_assemble produces -- it checks the flag and computes K_e
- * accordingly.  sb_csr_assemble on such an object expects K_e in that layout. */
-int     sb_csr_create_layout(sb_restriction_t test, sb_restriction_t trial, int K_e_node_major, sb_csr_t* out);
+/* The same pattern computed on the host from raw restriction tables ([num_elements][npe] node ids): what
+ * sb_csr_create runs before uploading, callable without a device (parity tests of the pattern on CPU-only machines).
+ * Call with col_ind_host == NULL to get nnz and row_ptr first. */
+int     sb_csr_pattern_host(const int* test_table, int test_npe, int test_components, int64_t test_num_nodes,
+                            int test_ordering, const int* trial_table, int trial_npe, int trial_components,
+                            int64_t trial_num_nodes, int trial_ordering, int64_t num_elements, int* row_ptr_host,
+                            int* col_ind_host, int64_t* nnz_out);
+/* Test hook, host only: walks the index tables of the fused assembly (groups of rows, units in element order, row
+ * positions, accumulator offsets, row write-out -- what assemble_rows_kernel walks on the device) over element matrices
+ * supplied by the caller.  It checks tables, not arithmetic; nothing in the library calls it.
+ * K_e_host: [domain position][trial vdof][test vdof]; elements: the integral's domain (NULL = all), nd entries;
+ * acc_cap: accumulator doubles a group may use (small values force groups to be cut); trial_blocks: as the kernel's
+ * (sb_kernel_table::assemble_rows_trial_blocks). */
+int     sb_debug_assembly_plan_host(const int* test_table, int test_npe, int test_components, int64_t test_num_nodes,
+                                    int test_ordering, const int* trial_table, int trial_npe, int trial_components,
+                                    int64_t trial_num_nodes, int trial_ordering, int64_t num_elements,
+                                    const int* elements, int64_t nd, int acc_cap, int trial_blocks,
+                                    const double* K_e_host,
+                                    const int* row_ptr_host, double* values_host, int* num_groups_out);
 int     sb_csr_destroy(sb_csr_t A);
 int64_t sb_csr_nnz(sb_csr_t A);
 int64_t sb_csr_num_rows(sb_csr_t A);
 int     sb_csr_pattern_dev(sb_csr_t A, const int** row_ptr_dev, const int** col_ind_dev);
 int     sb_csr_pattern_to_host(sb_csr_t A, int* row_ptr_host, int* col_ind_host);
 /* values[nz] = sum over the contributing K_e entries in ascending (element, i, j) order (deterministic gather;
- * F/functional.hpp:610-644 does the same sums with one hash lookup per entry). values_dev is overwritten. */
+ * F/functional.hpp:610-644 does the same sums with one hash lookup per entry). values_dev is overwritten.
+ * K_e_dev: [elements][trial vdofs][test vdofs] (the reference's layout); needs < 2^32 element-matrix entries.  This is
+ * the generic route (any geometry); sb_functional_assemble does not materialise K_e where a fused kernel exists. */
 int sb_csr_assemble(sb_csr_t A, const double* K_e_dev, double* values_dev, void* stream);
 /* values[nz] += element matrices living on another pair of restrictions of the same spaces -- the boundary faces
  * (F/functional.hpp:610-644 loops over Domain::Type::BoundaryElements after Elements with the same lookup table).

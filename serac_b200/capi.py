@@ -32,6 +32,8 @@ class KernelTable(C.Structure):
         ("evaluate", _vp), ("evaluate_ad", _vp * MAX_TRIALS), ("jvp", _vp * MAX_TRIALS),
         ("element_gradient", _vp * MAX_TRIALS),
         ("derivative_mask", _i * MAX_TRIALS), ("derivative_entries", _i * MAX_TRIALS), ("spatial_dim", _i),
+        ("assemble_rows", _vp * MAX_TRIALS), ("assemble_rows_fixed_doubles", _i * MAX_TRIALS),
+        ("assemble_rows_trial_blocks", _i * MAX_TRIALS),
     ]
 
 
@@ -69,7 +71,9 @@ SIGNATURES = {
     "sb_integral_derivative_entries": (_i, [_vp, _i]),
     "sb_integral_derivative_mask": (_i, [_vp, _i]),
     "sb_csr_create": (_i, [_vp, _vp, _pp]),
-    "sb_csr_create_layout": (_i, [_vp, _vp, _i, _pp]),
+    "sb_csr_pattern_host": (_i, [_vp, _i, _i, _i64, _i, _vp, _i, _i, _i64, _i, _i64, _vp, _vp, C.POINTER(_i64)]),
+    "sb_debug_assembly_plan_host": (_i, [_vp, _i, _i, _i64, _i, _vp, _i, _i, _i64, _i, _i64, _vp, _i64, _i, _i, _vp, _vp,
+                                        _vp, C.POINTER(_i)]),
     "sb_csr_destroy": (_i, [_vp]),
     "sb_csr_nnz": (_i64, [_vp]),
     "sb_csr_num_rows": (_i64, [_vp]),
@@ -352,12 +356,12 @@ class Integral:
 class CsrPattern:
     """Mirror of GradientAssemblyLookupTables (dof_numbering.hpp:253-380)."""
 
-    def __init__(self, test, trial, handle=None, node_major=False):
-        """node_major: gather lists for element matrices in the Functional's internal layout (sb_csr_create_layout)"""
+    def __init__(self, test, trial, handle=None):
         if handle is None:
             handle = C.c_void_p()
-            check(lib().sb_csr_create_layout(test.h, trial.h, int(node_major), C.byref(handle)))
+            check(lib().sb_csr_create(test.h, trial.h, C.byref(handle)))
         self.h = handle
+        self._keep = (test, trial)  # the pattern refers to the restrictions it was built from
         self.nnz = lib().sb_csr_nnz(self.h)
         self.num_rows = lib().sb_csr_num_rows(self.h)
 
@@ -379,6 +383,44 @@ class CsrPattern:
             values = torch.empty(self.nnz, dtype=torch.float64, device=K_e.device)
         check(lib().sb_csr_assemble(self.h, _dev_ptr(K_e), _dev_ptr(values), _stream_ptr()))
         return values
+
+
+def csr_pattern_host(test_table, test_components, test_num_nodes, trial_table, trial_components, trial_num_nodes,
+                     test_ordering=BYVDIM, trial_ordering=BYVDIM):
+    """row_ptr / col_ind of GradientAssemblyLookupTables from raw restriction tables, computed on the host by the same
+    code sb_csr_create runs before uploading (no device needed)."""
+    tt = np.ascontiguousarray(test_table, dtype=np.int32)
+    kt = np.ascontiguousarray(trial_table, dtype=np.int32)
+    ne = tt.shape[0]
+    rp = np.zeros(test_num_nodes * test_components + 1, dtype=np.int32)
+    nnz = _i64(0)
+    args = [_np_ptr(tt), tt.shape[1], test_components, test_num_nodes, test_ordering, _np_ptr(kt), kt.shape[1],
+            trial_components, trial_num_nodes, trial_ordering, ne]
+    check(lib().sb_csr_pattern_host(*args, _np_ptr(rp), None, C.byref(nnz)))
+    ci = np.empty(nnz.value, dtype=np.int32)
+    check(lib().sb_csr_pattern_host(*args, _np_ptr(rp), _np_ptr(ci), C.byref(nnz)))
+    return rp, ci
+
+
+def debug_assembly_plan_host(test_table, test_components, test_num_nodes, trial_table, trial_components,
+                             trial_num_nodes, K_e, row_ptr, nnz, elements=None, acc_cap=1600, trial_blocks=1,
+                             test_ordering=BYVDIM, trial_ordering=BYVDIM):
+    """test hook: walk the fused assembly's index tables (groups, units, row positions) over element matrices given by
+    the caller, on the host.  K_e: [domain position][trial vdof][test vdof].  -> (values, number of groups)"""
+    tt = np.ascontiguousarray(test_table, dtype=np.int32)
+    kt = np.ascontiguousarray(trial_table, dtype=np.int32)
+    K_e = np.ascontiguousarray(K_e, dtype=np.float64)
+    rp = np.ascontiguousarray(row_ptr, dtype=np.int32)
+    el = None if elements is None else np.ascontiguousarray(elements, dtype=np.int32)
+    nd = tt.shape[0] if el is None else len(el)
+    values = np.zeros(nnz)
+    ng = _i(0)
+    check(lib().sb_debug_assembly_plan_host(_np_ptr(tt), tt.shape[1], test_components, test_num_nodes, test_ordering,
+                                            _np_ptr(kt), kt.shape[1], trial_components, trial_num_nodes, trial_ordering,
+                                            tt.shape[0], None if el is None else _np_ptr(el), nd, acc_cap, trial_blocks,
+                                            _np_ptr(K_e),
+                                            _np_ptr(rp), _np_ptr(values), C.byref(ng)))
+    return values, ng.value
 
 
 class Functional:
@@ -473,7 +515,7 @@ class Functional:
         """-> (CsrPattern, values): the local CSR triple the reference wraps in mfem::SparseMatrix (functional.hpp:649)."""
         import torch
         if wrt not in self._csr:
-            self._csr[wrt] = CsrPattern(self.test, self.trials[wrt], node_major=True)
+            self._csr[wrt] = CsrPattern(self.test, self.trials[wrt])
         pat = self._csr[wrt]
         hp = C.c_void_p(pat.h.value)
         if on_host:

@@ -382,7 +382,7 @@ class Functional<test(trials...)> {
       const int   w = which_argument_;
       if (f.csr_.size() < size_t(num_trial_spaces)) f.csr_.resize(size_t(num_trial_spaces), nullptr);
       if (!f.csr_[size_t(w)])
-        SERAC_B200_CHECK(sb_csr_create_layout(f.G_test_, f.G_trial_[size_t(w)], 1, &f.csr_[size_t(w)]));
+        SERAC_B200_CHECK(sb_csr_create(f.G_test_, f.G_trial_[size_t(w)], &f.csr_[size_t(w)]));
       return f.csr_[size_t(w)];
     }
     /// the values of the assembled matrix into a device array of sb_csr_nnz(pattern) doubles (serac_b200/solvers.hpp)

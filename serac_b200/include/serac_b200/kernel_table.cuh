@@ -12,6 +12,7 @@
 #include <cstring>
 
 #include "serac_b200.h"
+#include "serac_b200/assemble_rows.cuh"
 #include "serac_b200/domain_integral.cuh"
 #include "serac_b200/jvp_stream.cuh"
 #include "serac_b200/simplex_integral.cuh"
@@ -257,6 +258,48 @@ int launch_element_gradient(const sb_elem_grad_args* a, void* stream)
   }
 }
 
+/// the fused assembly exists for hexahedra (sum factorisation in three stages); everything else goes through K_e
+template <typename Sig, int MASK>
+constexpr bool has_assemble_rows()
+{
+  return MASK != 0 && Sig::dim == 3 && !Sig::simplex && !Sig::boundary;
+}
+
+template <typename Sig, int WRT, int MASK>
+int launch_assemble_rows(const sb_assemble_rows_args* a, void* stream)
+{
+  if constexpr (!has_assemble_rows<Sig, MASK>()) {
+    return int(cudaErrorNotSupported);
+  } else {
+    using trial      = typename Sig::template trial_space<WRT>;
+    constexpr int nk = trial::order + 1;
+    constexpr int ck = trial::components;
+    using C = AssembleRowsConfig<Sig::q, nk, ck, Sig::test_n, Sig::test_c, MASK, Sig::EPB>;
+    if (a->num_groups <= 0) return 0;
+    AssembleRowsParams P{};
+    P.trial_basis = make_basis_table(trial::order, Sig::q);
+    P.test_basis  = make_basis_table(Sig::test_space::order, Sig::q);
+    P.dqf         = a->dqf_dev;
+    P.groups      = static_cast<const AsmGroup*>(a->groups_dev);
+    P.units       = static_cast<const AsmUnit*>(a->units_dev);
+    P.nodes       = static_cast<const AsmNode*>(a->nodes_dev);
+    P.pos         = a->pos_dev;
+    P.row_ptr     = a->row_ptr_dev;
+    P.values      = a->values_dev;
+    P.row_ns      = a->row_node_stride;
+    P.row_cs      = a->row_comp_stride;
+    P.col_byvdim  = a->col_byvdim;
+    P.accumulate  = a->accumulate;
+    P.num_groups  = a->num_groups;
+    auto         kernel = &assemble_rows_kernel<Sig::q, nk, ck, Sig::test_n, Sig::test_c, MASK, Sig::EPB>;
+    const size_t smem   = size_t(C::fixed_doubles + a->acc_doubles) * sizeof(double);
+    if (int e = ensure_smem(kernel, smem)) return e;
+    kernel<<<a->num_groups, C::threads, smem, cudaStream_t(stream)>>>(P);
+    sb_count_launch();
+    return int(cudaGetLastError());
+  }
+}
+
 /// 128 registers per thread: 65536 / 128 = 512 threads per SM
 template <typename Sig>
 constexpr int default_min_blocks()
@@ -279,6 +322,13 @@ void fill_wrt(sb_kernel_table& T)
   T.evaluate_ad[WRT]        = &launch_evaluate<Sig, WRT, QF, State, ROWS, MB, FAST>;
   T.jvp[WRT]                = &launch_jvp<Sig, WRT, mask>;
   T.element_gradient[WRT]   = &launch_element_gradient<Sig, WRT, mask>;
+  if constexpr (has_assemble_rows<Sig, mask>()) {
+    using trialW = typename Sig::template trial_space<WRT>;
+    T.assemble_rows[WRT] = &launch_assemble_rows<Sig, WRT, mask>;
+    using AC = AssembleRowsConfig<Sig::q, trialW::order + 1, ck, Sig::test_n, Sig::test_c, mask, Sig::EPB>;
+    T.assemble_rows_fixed_doubles[WRT] = AC::fixed_doubles;
+    T.assemble_rows_trial_blocks[WRT]  = AC::NB;
+  }
   T.derivative_mask[WRT]    = mask;
   T.derivative_entries[WRT] = L.entries;
 }

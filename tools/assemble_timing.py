@@ -32,13 +32,15 @@ def timed(fn, reps=5, warm=2):
     return e0.elapsed_time(e1) / reps
 
 
-e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-e0.record()
-pat, vals = F.assemble(1)  # first call builds the pattern (GradientAssemblyLookupTables::init)
-e1.record()
+import time
+t0 = time.perf_counter()
+pat, vals = F.assemble(1)  # first call builds the pattern (GradientAssemblyLookupTables::init) and the assembly plan
 torch.cuda.synchronize()
-first_ms = e0.elapsed_time(e1)
-assemble_ms = timed(lambda: F.assemble(1))
+first_ms = (time.perf_counter() - t0) * 1e3
+assemble_ms = timed(lambda: F.assemble(1), reps=10)
+if os.environ.get("SB_ASM_QUICK"):
+    print(json.dumps(dict(warps=os.environ.get("SB_ASM_WARPS", "default"), assemble_ms=assemble_ms, first_ms=first_ms)))
+    sys.exit(0)
 npe = 27 * 3
 K_e = torch.zeros((P["ne"], npe, npe), dtype=torch.float64, device=dev)
 
@@ -48,25 +50,36 @@ def elem_grad():
     I.ComputeElementGradients(1, K_e)
 
 
+# the generic route, for comparison: element matrices in HBM (the reference's scheme), then an ordered gather per nonzero
 eg_ms = timed(elem_grad)
 zero_ms = timed(lambda: K_e.zero_())
 elem_grad()
-ref_pat = capi.CsrPattern(G, G)  # gather lists for the reference K_e layout (what the standalone kernel wrote)
-vals_ref = torch.empty(ref_pat.nnz, dtype=torch.float64, device=dev)
-csr_ref_ms = timed(lambda: ref_pat.assemble(K_e, vals_ref))
-assert torch.equal(vals_ref, vals), "node-major and reference-layout assembly must agree bit for bit"
-# SpMV check against the matrix-free action
+vals_ref = torch.empty(pat.nnz, dtype=torch.float64, device=dev)
+csr_ref_ms = timed(lambda: pat.assemble(K_e, vals_ref))
+rel = float((vals_ref - vals).norm() / vals_ref.norm())
+assert rel < 1e-13, rel
 import numpy as np
 import scipy.sparse as sp
 rp, ci = pat.to_host()
 Acsr = sp.csr_matrix((vals.cpu().numpy(), ci, rp), shape=(G.LSize(), G.LSize()))
 jvp = F.GradientMult(1, dU).cpu().numpy()
 err = float(np.linalg.norm(Acsr @ dU.cpu().numpy() - jvp) / np.linalg.norm(jvp))
-flops = P["ne"] * 27 * 81 * (81 * 2 + 4 * 81 * 2)  # per element: 27 trial nodes x (81 FMA products + integrate 9 comps) -- order of magnitude
+# FP64 roofline of the assembly.  Per (element, test node) unit and component pair: 27 points x
+# (9 FMA contraction with the test gradient + 9 FMA stage z), then 9 threads x 27 FMA (stage y) and 9 x 18 (stage x)
+fma_per_unit = 9 * (27 * 18 + 9 * 27 + 9 * 18)
+flops = 2.0 * P["ne"] * 27 * fma_per_unit
+fp64_peak_tflops = 37.1  # profiles/r2a_fp64_peak_b200.json (tools/fp64_peak.cu on this pool's B200)
+hbm_bytes = P["ne"] * 27 * 648.0 + pat.nnz * 8.0 + P["ne"] * 729 * 2.0
+hbm_peak = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"] if os.path.exists(os.path.join(ROOT, "MEASURED_PEAKS.json")) else 6650.0
 out = dict(config="config A: 32768 hexes, H1 p=2, NeoHookean", nnz=int(pat.nnz), rows=int(pat.num_rows),
-           first_assemble_with_pattern_ms=first_ms, assemble_ms=assemble_ms, element_gradient_ms=eg_ms - zero_ms,
-           K_e_GB=K_e.numel() * 8 / 1e9, csr_assemble_reference_layout_ms=csr_ref_ms,
-           csr_assemble_node_major_ms=assemble_ms - (eg_ms - zero_ms), matrix_vs_action_rel=err,
+           first_assemble_with_pattern_and_plan_ms=first_ms, assemble_ms=assemble_ms,
+           generic_route=dict(element_gradient_ms=eg_ms - zero_ms, K_e_GB=K_e.numel() * 8 / 1e9, csr_gather_ms=csr_ref_ms),
+           fused_vs_generic_rel=rel, matrix_vs_action_rel=err,
+           roofline_assemble=dict(kernel="assemble_rows_kernel<3,3,3,3,3,8,4>", bound="fp64", flops=flops,
+                                  achieved_tflops=flops / (assemble_ms * 1e-3) / 1e12, peak_tflops=fp64_peak_tflops,
+                                  frac=flops / (assemble_ms * 1e-3) / 1e12 / fp64_peak_tflops,
+                                  hbm_algorithmic_bytes=hbm_bytes, hbm_achieved_gbs=hbm_bytes / (assemble_ms * 1e-3) / 1e9,
+                                  hbm_frac=hbm_bytes / (assemble_ms * 1e-3) / 1e9 / hbm_peak),
            assembled_rows_per_s=pat.num_rows / (assemble_ms * 1e-3))
 print(json.dumps(out, indent=1))
 if "--json" in sys.argv:
