@@ -33,6 +33,8 @@ CONFIG_A = os.path.join(ROOT, "tests", "golden", "config_a_beam_hex_r4_p2.npz")
 NEOHOOKEAN = [1.0, 100.0, 50.0, 1.0]  # density, K, G, geometric nonlinearity on (BASELINE.md §2 probe values)
 # dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed `ncu --set full` capture of this command
 # (profiles/r1c_summary.md, raw extract profiles/r1e_ncu_full_raw_extract.txt)
+NCU_TRAFFIC_SOURCE = ("ncu --set full capture of this command, one launch, not measured in this run: "
+                      "profiles/r1e_ncu_full_raw_extract.txt (dram__bytes_read.sum + dram__bytes_write.sum)")
 JVP_NCU_TRAFFIC_BYTES = 604.8e6   # 583.7 MB read + 21.1 MB written
 EVAL_NCU_TRAFFIC_BYTES = 638.8e6  # 103.3 MB read + 535.5 MB written (rest of the 573 MB store still in L2)
 
@@ -116,11 +118,114 @@ def build_problem(device):
                 mesh="beam-hex.mesh refined 4x (mfem numbering; fixture tests/golden/config_a_beam_hex_r4_p2.npz)")
 
 
-PER_GPU_BOX = (128, 16, 16)  # hexes per GPU = config A's 32 768 (the beam refined 4x), element size 1/16
-# optional strong-scaling series (SB_BENCH_SCALING=strong, N > 1 only; the default and the driver's series are weak): one
-# fixed 128 x 32 x 32 mesh (131 072 hexes, 3.3 M vdofs) split over the GPUs
+# Workload selection.  Default (what the driver runs, BASELINE.json's metric): config A = configs[1].
+# SB_BENCH_CONFIG=b selects configs[4]: synthetic structured hex cube, H1 p=3, NeoHookean --
+#   weak scaling (default):  one cube of SB_BENCH_B_N^3 hexes per GPU (default 107: ~100 M vdofs and 51 GB of stored
+#                            derivatives per GPU; 135 = ~200 M vdofs per GPU), boxes laid out 2x1x1 / 2x2x1 / 2x2x2
+#   SB_BENCH_SCALING=strong: the fixed 135^3 cube (200.8 M vdofs) split over the GPUs
+BENCH_CONFIG = os.environ.get("SB_BENCH_CONFIG", "a").lower()
 STRONG_SCALING = os.environ.get("SB_BENCH_SCALING", "weak") == "strong"
-STRONG_BOX = (128, 32, 32)
+if BENCH_CONFIG == "b":
+    ORDER = 3
+    _bn = int(os.environ.get("SB_BENCH_B_N", "107"))
+    PER_GPU_BOX, STRONG_BOX, ELEMENT_SIZE = (_bn, _bn, _bn), (135, 135, 135), 1.0 / 128.0
+    WORKLOAD = (f"configs[4]: synthetic structured hex cube, H1 p=3, SolidMechanics NeoHookean, {_bn}^3 hexes "
+                f"(~{3 * (3 * _bn + 1)**3 / 1e6:.0f} M vdofs) per GPU; step = residual with derivative store + one Jacobian action")
+    STRONG_WORKLOAD = ("configs[4] strong scaling: the fixed 135^3-hex cube (200.8 M vdofs), H1 p=3 NeoHookean, split over "
+                       "the GPUs; step = residual with derivative store + one Jacobian action")
+else:
+    ORDER = 2
+    PER_GPU_BOX = (128, 16, 16)  # hexes per GPU = config A's 32 768 (the beam refined 4x), element size 1/16
+    # optional strong-scaling series (N > 1 only; the default and the driver's series are weak): one fixed 128 x 32 x 32
+    # mesh (131 072 hexes, 3.3 M vdofs) split over the GPUs
+    STRONG_BOX, ELEMENT_SIZE = (128, 32, 32), 1.0 / 16.0
+    WORKLOAD = ("configs[1]: SolidMechanics NeoHookean H1 p=2 hex, 32768 hexes / ~840k vdofs / 884736 "
+                "qpts per GPU; step = residual with derivative store + one Jacobian action")
+    STRONG_WORKLOAD = ("strong-scaling variant (SB_BENCH_SCALING=strong): one fixed 128x32x32-hex mesh split over "
+                       "the GPUs; SolidMechanics NeoHookean H1 p=2 hex; step = residual with derivative store + "
+                       "one Jacobian action")
+
+
+def _split_even(n, parts):
+    base, rem = divmod(n, parts)
+    return [base + (1 if i < rem else 0) for i in range(parts)]
+
+
+def build_structured_problem(device):
+    """config B on one GPU: the structured cube, built directly (no partition, P = identity)"""
+    import torch
+    from serac_b200 import capi
+    from serac_b200.structured import StructuredHexMesh
+    p = ORDER
+    n = STRONG_BOX if STRONG_SCALING else PER_GPU_BOX
+    mesh = StructuredHexMesh(*n, *(n[d] * ELEMENT_SIZE for d in range(3)))
+    tab, tab1 = mesh.element_table(p), mesh.element_table(1)
+    G = capi.ElementRestriction(tab, 3, mesh.num_nodes(p))
+    G_shape = capi.ElementRestriction(tab1, 3, mesh.num_nodes(1))
+    nodes = torch.as_tensor(mesh.vertex_coordinates(), dtype=torch.float64, device=device)
+    X_q, J_q = capi.geometric_factors(capi.CUBE, 1, p + 1, G_shape, nodes)
+    integral = capi.Integral(f"solid_neohookean_hex_p{p}", NEOHOOKEAN, X_q, J_q, mesh.ne)
+    F = capi.Functional(G, [G_shape, G, G])
+    F.AddDomainIntegral(integral, [0, 1, 2])
+    vs, ss = G.LSize(), G_shape.LSize()
+    g = np.arange(vs, dtype=np.float64)
+    host = dict(U=synthetic_u(g), A=np.zeros(vs), S=np.zeros(ss), dU=synthetic_du(g))
+    return dict(capi=capi, G=G, G_shape=G_shape, integral=integral, F=F, host=host, ne=mesh.ne,
+                nq=mesh.ne * (p + 1)**3, vdofs=vs, tdofs=vs, tdofs_shape=ss, p=p, keep=(nodes, X_q, J_q),
+                mesh=f"structured {n[0]}x{n[1]}x{n[2]} hexes, one GPU")
+
+
+def synthetic_u(gid):
+    """displacement as a function of the GLOBAL vdof id (shared dofs agree across ranks; small against the element size)"""
+    return 0.016 * ELEMENT_SIZE * np.sin(0.37 * np.asarray(gid, dtype=np.float64) + 1.0)
+
+
+def synthetic_du(gid):
+    return 0.5 + 0.5 * np.sin(0.11 * np.asarray(gid, dtype=np.float64))
+
+
+def global_parity(P, dev, rank, world, r_T, dr_T):
+    """N > 1, untimed: rank 0 evaluates the SAME problem on the whole (unpartitioned) mesh, every rank compares its true
+    dofs of the partitioned residual and Jacobian action with it.  -> dict for the JSON line (relative L2 over all
+    dofs), or a reason when the global problem does not fit beside rank 0's partition."""
+    import torch
+    import torch.distributed as dist
+    from serac_b200 import capi
+    mesh, p = P["global_mesh"], P["p"]
+    n = mesh.num_nodes(p) * 3
+    need = mesh.ne * (p + 1)**3 * 648.0 * 1.35 + 64.0 * n
+    free = torch.cuda.mem_get_info(dev)[0]
+    fits = torch.tensor([1 if (rank != 0 or need < 0.8 * free) else 0], device=dev)
+    dist.broadcast(fits, 0)
+    if int(fits.item()) == 0:
+        return {"skipped": f"the global problem ({mesh.ne} hexes, {need / 1e9:.0f} GB) does not fit beside rank 0's "
+                           "partition; partitioned-vs-global parity at this order: tools/par_check.py"}
+    r_g = torch.empty(n, dtype=torch.float64, device=dev)
+    dr_g = torch.empty(n, dtype=torch.float64, device=dev)
+    if rank == 0:
+        t64 = lambda a: torch.as_tensor(a, dtype=torch.float64, device=dev)
+        tab, tab1 = mesh.element_table(p), mesh.element_table(1)
+        G = capi.ElementRestriction(tab, 3, mesh.num_nodes(p))
+        G1 = capi.ElementRestriction(tab1, 3, mesh.num_nodes(1))
+        nodes = t64(mesh.vertex_coordinates())
+        X_q, J_q = capi.geometric_factors(capi.CUBE, 1, p + 1, G1, nodes)
+        I = capi.Integral(f"solid_neohookean_hex_p{p}", NEOHOOKEAN, X_q, J_q, mesh.ne)
+        F = capi.Functional(G, [G1, G, G])
+        F.AddDomainIntegral(I, [0, 1, 2])
+        gid = np.arange(n)
+        F(0.0, [t64(np.zeros(mesh.num_nodes(1) * 3)), t64(synthetic_u(gid)), t64(np.zeros(n))], wrt=1, out=r_g)
+        F.GradientMult(1, t64(synthetic_du(gid)), out=dr_g)
+        torch.cuda.synchronize()
+        del F, I, X_q, J_q, G, G1
+    dist.broadcast(r_g, 0)
+    dist.broadcast(dr_g, 0)
+    gt = torch.as_tensor(P["part"].global_true_vdofs(), dtype=torch.int64, device=dev)
+    acc = torch.stack([((r_T - r_g[gt])**2).sum(), (r_g[gt]**2).sum(), ((dr_T - dr_g[gt])**2).sum(),
+                       (dr_g[gt]**2).sum()])
+    dist.all_reduce(acc)
+    e_r, e_dr = float((acc[0] / acc[1]).sqrt().item()), float((acc[2] / acc[3]).sqrt().item())
+    return {"residual_rel_l2": e_r, "jvp_rel_l2": e_dr, "tolerance": 1e-12, "ok": bool(e_r < 1e-12 and e_dr < 1e-12),
+            "reference": f"the same Functional on the whole {mesh.n[0]}x{mesh.n[1]}x{mesh.n[2]} mesh, one GPU (rank 0)"}
 
 
 def build_partitioned_problem(device, rank, world):
@@ -130,17 +235,16 @@ def build_partitioned_problem(device, rank, world):
     from serac_b200 import capi
     from serac_b200.parallel import HaloExchange, ParFunctional
     from serac_b200.structured import Partition, StructuredHexMesh, factor_ranks
-    p = 2
+    p = ORDER
     ranks = factor_ranks(world)
     if os.environ.get("SB_BENCH_RANKS"):  # experiments: e.g. "1,2,1" cuts the two boxes across their large face
         ranks = tuple(int(x) for x in os.environ["SB_BENCH_RANKS"].split(","))
         assert int(np.prod(ranks)) == world
     n = tuple(PER_GPU_BOX[d] * ranks[d] for d in range(3))
     per_gpu = PER_GPU_BOX
-    if STRONG_SCALING:  # SURVEY.md section 8d "also report": one fixed mesh split over the GPUs
-        assert all(STRONG_BOX[d] % ranks[d] == 0 for d in range(3)), (STRONG_BOX, ranks)
-        n, per_gpu = STRONG_BOX, tuple(STRONG_BOX[d] // ranks[d] for d in range(3))
-    mesh = StructuredHexMesh(*n, n[0] / 16.0, n[1] / 16.0, n[2] / 16.0)
+    if STRONG_SCALING:  # SURVEY.md section 8d "also report": one fixed mesh split over the GPUs (near-equal boxes)
+        n, per_gpu = STRONG_BOX, tuple(-(-STRONG_BOX[d] // ranks[d]) for d in range(3))
+    mesh = StructuredHexMesh(*n, *(n[d] * ELEMENT_SIZE for d in range(3)))
     # owned-first local numbering: the T-vector is the prefix of the L-vector, so P / P^T run in place
     inplace = (os.environ.get("SB_HALO_TRANSPORT", "peer") == "peer" and os.environ.get("SB_HALO_OVERLAP", "1") != "0"
                and os.environ.get("SB_HALO_INPLACE", "1") != "0")
@@ -155,7 +259,7 @@ def build_partitioned_problem(device, rank, world):
     G_shape = capi.ElementRestriction(tab1, 3, part1.num_local_nodes)
     nodes = torch.as_tensor(part1.vertex_coordinates(), dtype=torch.float64, device=device)
     X_q, J_q = capi.geometric_factors(capi.CUBE, 1, p + 1, G_shape, nodes)
-    integral = capi.Integral("solid_neohookean_hex_p2", NEOHOOKEAN, X_q, J_q, tab.shape[0])
+    integral = capi.Integral(f"solid_neohookean_hex_p{p}", NEOHOOKEAN, X_q, J_q, tab.shape[0])
     F = capi.Functional(G, [G_shape, G, G])
     F.AddDomainIntegral(integral, [0, 1, 2])
     # one halo object per field whose exchange can be in flight at the same time (u, a, the JVP direction, r, dr)
@@ -179,9 +283,9 @@ def build_partitioned_problem(device, rank, world):
         PF = ParFunctional(F, [halo1, halo, halo], halo)
     # globally consistent synthetic inputs: a function of the global vdof id, so shared dofs agree across ranks
     gt, gt1 = part.global_true_vdofs().astype(np.float64), part1.global_true_vdofs().astype(np.float64)
-    host = dict(U=1e-3 * np.sin(0.37 * gt + 1.0), A=np.zeros(len(gt)), S=np.zeros(len(gt1)),
-                dU=0.5 + 0.5 * np.sin(0.11 * gt))
+    host = dict(U=synthetic_u(gt), A=np.zeros(len(gt)), S=np.zeros(len(gt1)), dU=synthetic_du(gt))
     return dict(capi=capi, G=G, G_shape=G_shape, integral=integral, F=F, PF=PF, halo=halo, halo1=halo1, halos=halos,
+                part=part, part1=part1, global_mesh=mesh,
                 overlap=overlap, inplace=inplace, n_independent=n_independent, host=host,
                 ne=tab.shape[0], nq=tab.shape[0] * (p + 1)**3, vdofs=G.LSize(), tdofs=halo.tsize, tdofs_shape=halo1.tsize,
                 global_vdofs=mesh.num_nodes(p) * 3, p=p, transport=transport, ranks=ranks, keep=(nodes, X_q, J_q),
@@ -205,7 +309,7 @@ def run_product(args):
         P = build_partitioned_problem(dev, rank, world)
         call = P["PF"]
     else:
-        P = build_problem(dev)
+        P = build_problem(dev) if BENCH_CONFIG != "b" else build_structured_problem(dev)
         call = P["F"]
     capi, F, G, integral = P["capi"], P["F"], P["G"], P["integral"]
     t64 = lambda a: torch.as_tensor(a, dtype=torch.float64, device=dev)
@@ -298,7 +402,7 @@ def run_product(args):
     rL = torch.empty(P["vdofs"], dtype=torch.float64, device=dev)
     fields = [P["G_shape"].field(SL), G.field(UL), G.field(AL)]
     du_field = G.field(dUL)
-    psteps = min(args.steps, 200)
+    psteps = min(args.steps, 200 if BENCH_CONFIG != "b" else 10)
     ev = [[torch.cuda.Event(enable_timing=True) for _ in range(5)] for _ in range(psteps)]
     for k in range(psteps):
         ev[k][0].record()
@@ -392,7 +496,8 @@ def run_product(args):
     torch.cuda.synchronize()
     if world > 1:
         dist.barrier()
-    e2e_steps = max(3, min(args.steps, 200))  # long enough that one nvidia-smi poll of the clock sampler averages out
+    # long enough that one nvidia-smi poll of the clock sampler averages out (config B: a step moves GBs over PCIe)
+    e2e_steps = max(3, min(args.steps, 200 if BENCH_CONFIG != "b" else 10))
     t0 = time.perf_counter()
     for _ in range(e2e_steps):
         step_host()
@@ -405,15 +510,26 @@ def run_product(args):
     clocks = sampler.stop() if rank == 0 else None
 
     # sanity: host path and device path agree bit for bit (same kernels, same data)
-    assert np.array_equal(hr.numpy(), r.cpu().numpy()) and np.array_equal(hdr.numpy(), dr.cpu().numpy())
+    if world > 1 and P["transport"] == "peer":
+        assert all(h.peer_status() == 0 for h in P["halos"]), "a wait for a neighbour timed out in the host-buffer steps"
+    same_r, same_dr = np.array_equal(hr.numpy(), r.cpu().numpy()), np.array_equal(hdr.numpy(), dr.cpu().numpy())
+    if not (same_r and same_dr):
+        dr_h, r_h = hdr.numpy(), hr.numpy()
+        raise AssertionError(
+            f"rank {rank}: host-buffer path differs from the device path: r equal={same_r} (max |diff| "
+            f"{np.abs(r_h - r.cpu().numpy()).max():.3e}, {int((r_h != r.cpu().numpy()).sum())} entries of {r_h.size}), "
+            f"dr equal={same_dr} (max |diff| {np.abs(dr_h - dr.cpu().numpy()).max():.3e}, "
+            f"{int((dr_h != dr.cpu().numpy()).sum())} entries)")
     assert np.isfinite(hr.numpy()).all() and np.abs(hdr.numpy()).max() > 0
 
     sums = torch.tensor([P["tdofs"], P["tdofs_shape"]], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(sums)
     vdofs_total, shape_total = int(sums[0].item()), int(sums[1].item())
+    parity = None
     if world > 1:
         assert vdofs_total == P["global_vdofs"], "true dofs of the partitions do not add up to the global space"
+        parity = global_parity(P, dev, rank, world, r[:P["tdofs"]], dr[:P["tdofs"]])
         dist.barrier()
         dist.destroy_process_group()
     if rank != 0:
@@ -430,16 +546,13 @@ def run_product(args):
     out = {
         "metric": METRIC, "value": vdofs_total / (ms_per_step * 1e-3) / 1e9, "unit": "GDOF/s", "n_gpus": world,
         "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True,
-        "scaling": "strong" if (STRONG_SCALING and world > 1) else "weak", "vs_baseline": None, "dtype": "f64",
+        "scaling": "strong" if STRONG_SCALING else "weak", "vs_baseline": None, "dtype": "f64",
         "data": "synthetic",
-        "config": {"workload": ("strong-scaling variant (SB_BENCH_SCALING=strong): one fixed 128x32x32-hex mesh split over "
-                                "the GPUs; SolidMechanics NeoHookean H1 p=2 hex; step = residual with derivative store + "
-                                "one Jacobian action") if (STRONG_SCALING and world > 1) else
-                               "configs[1]: SolidMechanics NeoHookean H1 p=2 hex, 32768 hexes / ~840k vdofs / 884736 "
-                               "qpts per GPU; step = residual with derivative store + one Jacobian action",
+        "config": {"workload": STRONG_WORKLOAD if STRONG_SCALING else WORKLOAD,
                    "mesh": P["mesh"], "vdofs_total": vdofs_total, "vdofs_per_gpu": P["vdofs"],
                    "qpts_per_gpu": P["nq"],
-                   "l2_policy": "inputs larger than L2 (573 MB stored derivatives streamed each step)",
+                   "l2_policy": f"inputs larger than L2 ({648.0 * P['nq'] / 1e6:.0f} MB of stored derivatives streamed each "
+                                "step)",
                    "step_launch": "CUDA graph replay" if use_graph else "kernel by kernel",
                    "parallelism": f"1 mesh partition per GPU x{world}"
                                   + (f", shared-dof exchange over {P['transport']}"
@@ -454,17 +567,23 @@ def run_product(args):
         "phases_ms": {"evaluate_with_derivative_store": phase_ms[0], "scatter_r": phase_ms[1], "jvp": phase_ms[2],
                       "scatter_dr": phase_ms[3]},
         "qpts_per_s": P["nq"] * world / (ms_per_step * 1e-3),
-        "roofline": {"kernel": "jvp_stream_kernel<3,3,3,3,3,3,8,*>", "bound": "hbm", "achieved": achieved,
+        "roofline": {"kernel": f"jvp_stream_kernel<3,{p + 1},{p + 1},3,{p + 1},3,8,*>", "bound": "hbm", "achieved": achieved,
                      "peak": peak, "unit": "GB/s", "frac": achieved / peak, "peak_source": peak_src,
-                     "algorithmic_bytes_per_launch": jvp_bytes, "traffic": JVP_NCU_TRAFFIC_BYTES},
+                     "algorithmic_bytes_per_launch": jvp_bytes,
+                     "traffic": JVP_NCU_TRAFFIC_BYTES if BENCH_CONFIG != "b" else None,
+                     "traffic_source": NCU_TRAFFIC_SOURCE if BENCH_CONFIG != "b" else None},
         "roofline_evaluate": {"kernel": "evaluation_kernel<wrt=1>", "bound": "hbm",
                               "achieved": eval_bytes / (phase_ms[0] * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
                               "frac": eval_bytes / (phase_ms[0] * 1e-3) / 1e9 / peak,
-                              "algorithmic_bytes_per_launch": eval_bytes, "traffic": EVAL_NCU_TRAFFIC_BYTES},
+                              "algorithmic_bytes_per_launch": eval_bytes,
+                              "traffic": EVAL_NCU_TRAFFIC_BYTES if BENCH_CONFIG != "b" else None,
+                              "traffic_source": NCU_TRAFFIC_SOURCE if BENCH_CONFIG != "b" else None},
         "clocks": clocks,
     }
     if halo_ms is not None:
         out["phases_ms"]["halo_exchange_3P_1Pt"] = halo_ms
+    if parity is not None:
+        out["parity_vs_global"] = parity
     if args.gpus == 1 and world == 1 and not args.no_solver_layer and not args.no_graph:  # (--no-graph = ncu captures)
         # outside the timed step: the Newton step's linear algebra on the same problem.  Reported
         # beside the headline, never part of it; a failure here is recorded, not raised
@@ -562,17 +681,29 @@ def reference_run(cores, nx_per_core, steps, warmup):
     return vdofs / t / 1e9, t, vdofs
 
 
+def reference_cores():
+    """processes of the reference arm: the largest divisor of the beam's 128 hexes along x that the host cores allow, so
+    that the slabs tile config A's 128 x 16 x 16 beam exactly (one 1/R slab of the mesh per core)"""
+    cores = max(1, min(os.cpu_count() or 1, 128))
+    return max(d for d in (1, 2, 4, 8, 16, 32, 64, 128) if d <= cores)
+
+
+CONFIG_A_VDOFS = 839619  # true dofs of the beam (the slabs' duplicated interface nodes are the same dofs)
+
+
 def cpu_baseline_sample():
+    """bounded sample for the product arm's line: one timed step of the whole config-A beam, one slab per core"""
     from oracle import ref
     if not ref.available():
         return {"value": None, "unit": "GDOF/s", "cores": 0, "kind": "reference",
                 "sample": "oracle/_ref not built on this box"}
-    cores = max(1, min(os.cpu_count() or 1, 128))
-    nx = 2  # 2 x 16 x 16 = 512 hexes per core: ~6 s of reference AD evaluation per step per core
-    value, t, vdofs = reference_run(cores, nx, 1, 1)
-    return {"value": value, "unit": "GDOF/s", "cores": cores, "kind": "reference",
-            "sample": f"{cores} processes x (2x16x16 hexes of the config-A beam, {vdofs // cores} vdofs each), 1 warm-up "
-                      f"+ 1 timed step of the reference's own kernels (oracle/_ref), {t:.2f} s/step; no halo exchange"}
+    cores = reference_cores()
+    nx = 128 // cores
+    _, t, vdofs = reference_run(cores, nx, 1, 1)
+    return {"value": CONFIG_A_VDOFS / t / 1e9, "unit": "GDOF/s", "cores": cores, "kind": "reference",
+            "sample": f"config A itself: {cores} processes x ({nx}x16x16 hexes = 1/{cores} of the 128x16x16 beam, "
+                      f"{vdofs // cores} local vdofs each), 1 warm-up + 1 timed step of the reference's own kernels "
+                      f"(oracle/_ref, -O3), {t:.2f} s/step; gather/scatter included, no halo exchange"}
 
 
 def run_reference(args):
@@ -582,18 +713,21 @@ def run_reference(args):
     if not ref.available():
         print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref/libserac_ref.so not built"}))
         return
-    cores = max(1, min(os.cpu_count() or 1, 128))
-    nx = 1
+    cores = reference_cores()
+    nx = 128 // cores
     steps = max(1, min(args.steps, 3))
-    value, t, vdofs = reference_run(cores, nx, steps, 1)
-    sample = (f"{cores} processes x (1x16x16 hexes of the config-A beam = {vdofs // cores} vdofs each), "
-              f"1 warm-up + {steps} timed steps, {t:.2f} s/step; gather/scatter included, no halo exchange")
+    _, t, vdofs = reference_run(cores, nx, steps, 1)
+    value = CONFIG_A_VDOFS / t / 1e9
+    sample = (f"config A itself: {cores} processes x ({nx}x16x16 hexes = 1/{cores} of the 128x16x16 beam, "
+              f"{vdofs // cores} local vdofs each), 1 warm-up + {steps} timed steps, {t:.2f} s/step; gather/scatter "
+              "included, no halo exchange (flatters the CPU slightly)")
     print(json.dumps({
         "impl": "reference", "metric": METRIC, "value": value, "unit": "GDOF/s", "n_gpus": args.gpus, "steps": steps,
         "warmup": 1, "ms_per_step": t * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f64", "data": "synthetic",
-        "config": {"workload": "configs[1] slabs: SolidMechanics NeoHookean H1 p=2 hex, reference CPU kernels, one "
-                               "mesh slab per host core", "vdofs_total": vdofs},
+        "config": {"workload": WORKLOAD, "mesh": "the 128x16x16-hex beam of config A cut into one slab per host core",
+                   "vdofs_total": CONFIG_A_VDOFS, "vdofs_per_gpu": CONFIG_A_VDOFS, "qpts_per_gpu": 884736,
+                   "parallelism": f"{cores} host processes, one mesh slab each"},
         "cpu_baseline": {"value": value, "unit": "GDOF/s", "cores": cores, "kind": "reference", "sample": sample},
         "e2e": {"value": value, "unit": "GDOF/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }))

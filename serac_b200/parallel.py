@@ -74,7 +74,7 @@ class HaloExchange:
         try:
             grp = self.group if self.group is not None else dist.group.WORLD
             # two slots of (2 * slot + MAXN) 8-byte words: enough for the flag protocol and for the LL one (SB_HALO_LL=1)
-            ring = symm_mem.empty(4 * slot + 2 * MAXN, dtype=torch.float64, device=self.device)
+            ring = symm_mem.empty(self.ring_doubles(slot), dtype=torch.float64, device=self.device)
             ring.zero_()
             hdl = symm_mem.rendezvous(ring, grp.group_name if hasattr(grp, "group_name") else grp)
             ptrs = [int(p) for p in hdl.buffer_ptrs]
@@ -84,18 +84,33 @@ class HaloExchange:
             return False
         torch.cuda.synchronize()
         dist.barrier(group=self.group)  # every ring is zeroed before anyone writes
+        self.attach_rings(ring, slot, rank, ptrs, meta)
+        self._hdl = hdl
+        return True
+
+    @staticmethod
+    def ring_doubles(slot):
+        """8-byte words of a receive ring for slots of `slot` doubles: two slots of (2 * slot + MAXN) words -- enough for
+        the flag protocol and for the LL one"""
+        return 4 * slot + 2 * 32
+
+    def attach_rings(self, ring, slot, rank, ring_ptrs, meta):
+        """ring: this rank's zeroed receive ring (ring_doubles(slot) doubles); ring_ptrs[r]: rank r's ring as addressable
+        from this process (symmetric-memory mapping, CUDA IPC, or simply another tensor of this process when several
+        ranks of a partition live on one device -- the loop-back tests); meta[r]: dict(neighbors, send_off, recv_off) of
+        rank r's halo lists."""
+        lib = capi.lib()
         nn = len(self.neighbors)
         peer_ring = (C.c_void_p * max(nn, 1))()
         P_off, Pt_off = np.zeros(max(nn, 1), dtype=np.int64), np.zeros(max(nn, 1), dtype=np.int64)
         my_idx = np.zeros(max(nn, 1), dtype=np.int32)
         for i, s in enumerate(self.neighbors):
-            j = meta[s]["neighbors"].index(rank)
-            peer_ring[i] = ptrs[s]
+            j = list(meta[s]["neighbors"]).index(rank)
+            peer_ring[i] = int(ring_ptrs[s])
             P_off[i], Pt_off[i], my_idx[i] = meta[s]["recv_off"][j], meta[s]["send_off"][j], j
         capi.check(lib.sb_halo_enable_peer(self.h, capi._dev_ptr(ring), slot, peer_ring, capi._np_ptr(P_off),
                                            capi._np_ptr(Pt_off), capi._np_ptr(my_idx)))
-        self._ring, self._hdl, self.peer = ring, hdl, True
-        return True
+        self._ring, self.peer = ring, True
 
     def peer_status(self):
         st = C.c_int(0)
@@ -226,6 +241,14 @@ class ParFunctional:
         # (Partition.halo_independent_first): they are evaluated while the input exchange is in flight
         self.independent_elements = int(independent_elements)
         self.inplace = bool(inplace)
+        if self.independent_elements > 0:
+            import os
+            # the two halves of the input exchange exist for the flag protocol only (sb_halo_P_peer_put_multi)
+            if os.environ.get("SB_HALO_LL", "1") != "0":
+                raise ValueError("independent_elements > 0 needs the flag protocol: set SB_HALO_LL=0")
+            ids = [id(h) for h in trial_halos]
+            if len(set(ids)) != len(ids) or len(ids) > 4:
+                raise ValueError("independent_elements > 0 needs one halo object per trial field, at most 4 fields")
         if self.inplace:
             hs = list(trial_halos) + [test_halo] + list(self.du_halos.values()) + ([out_halo] if out_halo else [])
             assert all(h.peer and h.owned_first() for h in hs), "in-place exchanges need owned-first peer halos"
@@ -275,10 +298,10 @@ class ParFunctional:
                     return self._finish_output(out)
                 capi.check(lib.sb_halo_P_peer_inplace_multi(n, hs, vs, capi._stream_ptr()))
             else:
-                for h, TL in zip(self.trial_halos, T_inputs):
-                    h.P_put(TL)
+                # fields that share a halo object (or more than 4 of them): one whole exchange per field through the same
+                # entry point as everywhere else -- a halo object serves one field in flight and stays with one protocol
                 for i, (h, TL) in enumerate(zip(self.trial_halos, T_inputs)):
-                    self._L[i] = h.P_finish_inplace(TL)
+                    self._L[i] = h.P_inplace(TL)
         elif self._split:
             for h, T in zip(self.trial_halos, T_inputs):
                 h.P_put(T)
@@ -321,6 +344,16 @@ class ParFunctional:
         """the calling stream waits for the side stream (results of __call__ with out_halo become valid)"""
         if self._side is not None:
             capi_torch().cuda.current_stream().wait_stream(self._side)
+
+    def check_peers(self):
+        """synchronises and raises if a wait for a neighbour gave up (~2 s): the result of that step is not valid.
+        Call it after a step (or every few steps) -- a lost or stalled peer must not turn into silently wrong numbers."""
+        capi_torch().cuda.synchronize()
+        hs = list(self.trial_halos) + [self.test_halo] + list(self.du_halos.values())
+        hs += [self.out_halo] if self.out_halo is not None else []
+        bad = [i for i, h in enumerate(hs) if h.peer and h.peer_status() != 0]
+        if bad:
+            raise RuntimeError(f"shared-dof exchange: wait for a neighbour timed out on halo object(s) {bad}")
 
 
 def capi_torch():
