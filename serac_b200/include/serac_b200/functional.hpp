@@ -50,6 +50,12 @@ namespace serac {
     }                                                                                                         \
   } while (0)
 
+/// The host side with PLAIN structs for the mesh / space layer (FiniteElementSpace, Mesh, Vector below).  It lives in its
+/// own namespace so that serac_b200/functional_mfem.hpp can offer the same class names on mfem's types
+/// (`serac::Functional` over mfem::FiniteElementSpace / mfem::Vector / mfem::Operator); without that header
+/// (SERAC_B200_MFEM_API undefined) the names are visible as serac::Functional, serac::Vector, ... as before.
+namespace core_api {
+
 enum class Ordering : int
 {
   byNODES = SB_ORDERING_BYNODES,
@@ -349,6 +355,18 @@ class Functional<test(trials...)> {
     }
   }
 
+  /// operator() on raw buffers: `mode` = SB_DEVICE / SB_HOST_SYNC for inputs and output alike (what an adapter over
+  /// another library's vector type calls; sizes are the caller's responsibility)
+  void evaluate_raw(double t, int wrt, const double* const* inputs, double* output, int mode)
+  {
+    SERAC_B200_CHECK(sb_functional_evaluate(F_, t, wrt, inputs, mode, output, mode, update_qdata_ ? 1 : 0, nullptr));
+  }
+  void jvp_raw(int wrt, const double* dx, double* df, int mode)
+  {
+    SERAC_B200_CHECK(sb_functional_jvp(F_, wrt, dx, mode, df, mode, nullptr));
+  }
+  Gradient& gradient(int wrt) { return grad_[size_t(wrt)]; }
+
   /// functional.hpp:523: whether the next evaluations commit the quadrature-point state
   void updateQdata(bool update_flag) { update_qdata_ = update_flag; }
 
@@ -588,5 +606,11 @@ std::vector<double> gradient_vector(G& g)
   for (size_t k = 0; k < K->col_ind.size(); k++) v[size_t(K->col_ind[k])] = K->values[k];
   return v;
 }
+
+}  // namespace core_api
+
+#ifndef SERAC_B200_MFEM_API
+using namespace core_api;
+#endif
 
 }  // namespace serac

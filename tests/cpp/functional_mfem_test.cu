@@ -1,0 +1,386 @@
+// Test driver for the mfem-typed boundary (serac_b200/functional_mfem.hpp): the reference's own unit tests of Functional,
+// ported with minimal edits, running through `serac::Functional` on mfem::FiniteElementSpace / mfem::Vector /
+// mfem::Operator, linked against the reference's serial mfem (oracle/_ref/mfem-install, tests only).
+//
+//   comparisons   src/serac/numerics/functional/tests/functional_comparisons.cpp:78-330,431-445: residual, Jacobian action
+//                 and assembled matrix of a toy thermal problem (H1<p>) and a toy elasticity problem (H1<p,dim>) against
+//                 MFEM's own integrators (MassIntegrator + DiffusionIntegrator, VectorMassIntegrator +
+//                 ElasticityIntegrator), tolerance 1e-14 relative as in the reference (:283, :314)
+//   gradients     functional_basic_h1_vector.cpp:60-165 + check_gradient.hpp:16-90: domain + boundary integrals with
+//                 source / flux terms of every shape; JVP against the assembled matrix (5e-6) and finite-difference
+//                 convergence ratios
+//   shape         ShapeAwareFunctional (shape_aware_functional.hpp:292-575): with a shape displacement p the residual
+//                 equals that of the plain Functional on the mesh whose nodes were moved by p
+// Meshes are generated (MakeCartesian3D + a smooth perturbation): the reference's mesh files are not on the GPU box.
+// Exit code 0 = all checks passed; every check prints one line.
+#include <cmath>
+#include <cstdio>
+#include <string>
+
+#include "serac_b200/functional_mfem.hpp"
+
+using namespace serac;
+
+static int g_failures = 0;
+#define EXPECT(cond, ...)                                  \
+  do {                                                     \
+    const bool _ok = (cond);                               \
+    std::printf("%s  ", _ok ? "ok  " : "FAIL");            \
+    std::printf(__VA_ARGS__);                              \
+    std::printf("\n");                                     \
+    if (!_ok) g_failures++;                                \
+  } while (0)
+
+// (literals in device code: a namespace-scope constexpr double that is passed by reference is not usable on the device)
+#define COEF_A 1.7
+#define COEF_B 2.1
+constexpr double a = COEF_A;
+constexpr double b = COEF_B;
+
+// ---- q-functions of the reference tests (functor structs, as in the reference's CUDA-enabled tests) ---------------------
+struct SourceFluxFunctor {  // functional_comparisons.cpp:67-76
+  template <typename Position, typename Temperature>
+  SERAC_HOST_DEVICE auto operator()(double /*t*/, Position position, Temperature temperature) const
+  {
+    auto [X, dX_dxi] = position;
+    auto [u, du_dX]  = temperature;
+    auto source      = COEF_A * u - (100 * X[0] * X[1]);
+    auto flux        = COEF_B * du_dX;
+    return serac::tuple{source, flux};
+  }
+};
+
+template <int dim>
+struct StressFunctor {  // functional_comparisons.cpp:53-65
+  template <typename Position, typename Displacement>
+  SERAC_HOST_DEVICE auto operator()(double /*t*/, Position, Displacement displacement) const
+  {
+    const auto I    = DenseIdentity<dim>();
+    auto [u, du_dx] = displacement;
+    auto body_force = COEF_A * u + I[0];
+    auto strain     = 0.5 * (du_dx + transpose(du_dx));
+    auto stress     = COEF_B * tr(strain) * I + 2.0 * COEF_B * strain;
+    return serac::tuple{body_force, stress};
+  }
+};
+
+template <int dim>
+struct ElasticityTestModelOne {  // functional_basic_h1_vector.cpp:60-75
+  template <typename position_type, typename displacement_type>
+  SERAC_HOST_DEVICE auto operator()(double, position_type, displacement_type displacement) const
+  {
+    const auto d00 = make_tensor<dim, dim>([](int i, int j) { return i + 2 * j + 1; });
+    const auto d01 = make_tensor<dim, dim, dim>([](int i, int j, int k) { return i + 2 * j - k + 1; });
+    const auto d10 = make_tensor<dim, dim, dim>([](int i, int j, int k) { return i + 3 * j - 2 * k; });
+    const auto d11 = make_tensor<dim, dim, dim, dim>([](int i, int j, int k, int l) { return i - j + 2 * k - 3 * l + 1; });
+    auto [u, du_dx] = displacement;
+    auto source     = dot(d00, u) + double_dot(d01, du_dx);
+    auto flux       = dot(d10, u) + double_dot(d11, du_dx);
+    return serac::tuple{source, flux};
+  }
+};
+
+template <int dim>
+struct ElasticityTestModelTwo {  // functional_basic_h1_vector.cpp:77-87 (boundary integrand)
+  template <typename position_type, typename displacement_type>
+  SERAC_HOST_DEVICE auto operator()(double, position_type position, displacement_type displacement) const
+  {
+    auto [X, dX_dxi] = position;
+    auto [u, du_dxi] = displacement;
+    return u * X[0];
+  }
+};
+
+// a nonlinear integrand for the shape-aware check: source and flux depend on position, value and gradient
+struct NonlinearThermal {
+  template <typename Position, typename Temperature>
+  SERAC_HOST_DEVICE auto operator()(double /*t*/, Position position, Temperature temperature) const
+  {
+    auto [X, dX_dxi] = position;
+    auto [u, du_dX]  = temperature;
+    auto source      = u * u + X[0] - 0.3 * X[2];
+    auto flux        = (1.0 + 0.5 * u * u) * du_dX;
+    return serac::tuple{source, flux};
+  }
+};
+
+// ---- helpers ----------------------------------------------------------------------------------------------------------
+mfem::Mesh make_mesh(mfem::Element::Type type, int n = 2)
+{
+  mfem::Mesh mesh = mfem::Mesh::MakeCartesian3D(n, n, n, type, 1.0, 1.2, 0.9);
+  mesh.EnsureNodes();
+  mesh.Transform([](const mfem::Vector& x, mfem::Vector& y) {
+    y    = x;
+    y(0) = x(0) + 0.05 * std::sin(2.0 * x(1)) * x(2);
+    y(1) = x(1) + 0.04 * x(0) * x(2);
+    y(2) = x(2) + 0.03 * std::cos(1.5 * x(0)) * x(1);
+  });
+  return mesh;
+}
+
+double rel(const mfem::Vector& x, const mfem::Vector& y)
+{
+  mfem::Vector d(x);
+  d -= y;
+  return d.Norml2() / (y.Norml2() > 0 ? y.Norml2() : 1.0);
+}
+
+// ---- functional_comparisons.cpp ------------------------------------------------------------------------------------------
+template <int p>
+void thermal_comparison(mfem::Mesh& mesh, const char* tag)
+{
+  constexpr int dim = 3;
+  mfem::H1_FECollection    fec(p, dim);
+  mfem::FiniteElementSpace fes(&mesh, &fec);
+  const mfem::FiniteElement&   el = *fes.GetFE(0);
+  const mfem::IntegrationRule& ir = mfem::IntRules.Get(el.GetGeomType(), el.GetOrder() * 2);
+
+  mfem::BilinearForm        A(&fes);
+  mfem::ConstantCoefficient a_coef(a), b_coef(b);
+  auto* mass = new mfem::MassIntegrator(a_coef);
+  mass->SetIntRule(&ir);
+  A.AddDomainIntegrator(mass);
+  auto* diffusion = new mfem::DiffusionIntegrator(b_coef);
+  diffusion->SetIntRule(&ir);
+  A.AddDomainIntegrator(diffusion);
+  A.Assemble(0);
+  A.Finalize();
+  mfem::LinearForm          f(&fes);
+  mfem::FunctionCoefficient load_func([](const mfem::Vector& c) { return 100 * c(0) * c(1); });
+  auto* load = new mfem::DomainLFIntegrator(load_func);
+  load->SetIntRule(&ir);
+  f.AddDomainIntegrator(load);
+  f.Assemble();
+
+  mfem::Vector U(fes.GetVSize());
+  U.Randomize(1);
+
+  using space = H1<p>;
+  Functional<space(space)> residual(&fes, {&fes});
+  residual.AddDomainIntegral(Dimension<dim>{}, DependsOn<0>{}, SourceFluxFunctor{}, mesh);
+
+  mfem::Vector r1(U.Size());
+  A.Mult(U, r1);
+  r1 -= f;
+  mfem::Vector r2 = residual(0.0, U);
+  EXPECT(rel(r2, r1) < 1e-13, "thermal %s p=%d: ||r_functional - r_mfem|| / ||r|| = %.2e", tag, p, rel(r2, r1));
+
+  auto [r3, drdU] = residual(0.0, differentiate_wrt(U));
+  mfem::Vector dU(U.Size());
+  dU.Randomize(2);
+  mfem::Vector g1(U.Size());
+  A.Mult(dU, g1);
+  mfem::Vector g2 = drdU(dU);
+  EXPECT(rel(g2, g1) < 1e-13, "thermal %s p=%d: gradient action vs A dU %.2e", tag, p, rel(g2, g1));
+  // Gradient is an mfem::Operator
+  const mfem::Operator& op = drdU;
+  mfem::Vector          g3(op.Height());
+  op.Mult(dU, g3);
+  EXPECT(rel(g3, g1) < 1e-13 && op.Height() == fes.GetVSize() && op.Width() == fes.GetVSize(),
+         "thermal %s p=%d: through mfem::Operator::Mult %.2e", tag, p, rel(g3, g1));
+  std::unique_ptr<mfem::SparseMatrix> J = assemble(drdU);
+  mfem::Vector g4(U.Size());
+  J->Mult(dU, g4);
+  EXPECT(rel(g4, g1) < 1e-13, "thermal %s p=%d: assembled matrix action %.2e", tag, p, rel(g4, g1));
+  // entry by entry against mfem's matrix (same sparsity: both come from the element connectivity)
+  const mfem::SparseMatrix& Am = A.SpMat();
+  double                    worst = 0.0, scale = 0.0;
+  for (int i = 0; i < Am.Height(); i++) {
+    for (int k = Am.GetI()[i]; k < Am.GetI()[i + 1]; k++) {
+      worst = std::max(worst, std::abs(Am.GetData()[k] - (*J)(i, Am.GetJ()[k])));
+      scale = std::max(scale, std::abs(Am.GetData()[k]));
+    }
+  }
+  EXPECT(worst < 1e-13 * scale && J->NumNonZeroElems() == Am.NumNonZeroElems(),
+         "thermal %s p=%d: matrix entries max |diff| / max |A| = %.2e, nnz %d vs %d", tag, p, worst / scale,
+         J->NumNonZeroElems(), Am.NumNonZeroElems());
+}
+
+template <int p>
+void elasticity_comparison(mfem::Mesh& mesh, const char* tag)
+{
+  constexpr int dim = 3;
+  mfem::H1_FECollection    fec(p, dim);
+  mfem::FiniteElementSpace fes(&mesh, &fec, dim, mfem::Ordering::byVDIM);
+  const mfem::FiniteElement&   el = *fes.GetFE(0);
+  const mfem::IntegrationRule& ir = mfem::IntRules.Get(el.GetGeomType(), el.GetOrder() * 2);
+
+  mfem::BilinearForm        A(&fes);
+  mfem::ConstantCoefficient a_coef(a), lambda_coef(b), mu_coef(b);
+  auto* mass = new mfem::VectorMassIntegrator(a_coef);
+  mass->SetIntRule(&ir);
+  A.AddDomainIntegrator(mass);
+  auto* elast = new mfem::ElasticityIntegrator(lambda_coef, mu_coef);
+  elast->SetIntRule(&ir);
+  A.AddDomainIntegrator(elast);
+  A.Assemble(0);
+  A.Finalize();
+  mfem::LinearForm               f(&fes);
+  mfem::VectorFunctionCoefficient load_func(dim, [](const mfem::Vector&, mfem::Vector& force) {
+    force    = 0.0;
+    force(0) = -1.0;
+  });
+  auto* load = new mfem::VectorDomainLFIntegrator(load_func);
+  load->SetIntRule(&ir);
+  f.AddDomainIntegrator(load);
+  f.Assemble();
+
+  mfem::Vector U(fes.GetVSize());
+  U.Randomize(3);
+  using space = H1<p, dim>;
+  Functional<space(space)> residual(&fes, {&fes});
+  residual.AddVolumeIntegral(DependsOn<0>{}, StressFunctor<dim>{}, mesh);
+  mfem::Vector r1(U.Size());
+  A.Mult(U, r1);
+  r1 -= f;
+  mfem::Vector r2 = residual(0.0, U);
+  EXPECT(rel(r2, r1) < 1e-13, "elasticity %s p=%d: ||r_functional - r_mfem|| / ||r|| = %.2e", tag, p, rel(r2, r1));
+  auto [r3, drdU] = residual(0.0, differentiate_wrt(U));
+  mfem::Vector dU(U.Size());
+  dU.Randomize(4);
+  mfem::Vector g1(U.Size());
+  A.Mult(dU, g1);
+  mfem::Vector g2 = drdU(dU);
+  EXPECT(rel(g2, g1) < 1e-13, "elasticity %s p=%d: gradient action vs A dU %.2e", tag, p, rel(g2, g1));
+  std::unique_ptr<mfem::SparseMatrix> J = assemble(drdU);
+  mfem::Vector g4(U.Size());
+  J->Mult(dU, g4);
+  EXPECT(rel(g4, g1) < 1e-13, "elasticity %s p=%d: assembled matrix action %.2e", tag, p, rel(g4, g1));
+}
+
+// ---- check_gradient.hpp:16-90 --------------------------------------------------------------------------------------------
+template <typename F>
+void check_gradient(F& f, double t, mfem::Vector& U, const char* what, double epsilon = 1.0e-4)
+{
+  mfem::Vector dU(U.Size());
+  dU.Randomize(42);
+  auto [value, dfdU]                              = f(t, differentiate_wrt(U));
+  std::unique_ptr<mfem::SparseMatrix> dfdU_matrix = assemble(dfdU);
+  mfem::Vector df_jvp1 = dfdU(dU);  // matrix-free
+  mfem::Vector df_jvp2(df_jvp1.Size());
+  dfdU_matrix->Mult(dU, df_jvp2);  // sparse matvec
+  double relative_error = 0.0;
+  if (df_jvp1.Norml2() != 0) relative_error = df_jvp1.DistanceTo(df_jvp2.GetData()) / df_jvp1.Norml2();
+  EXPECT(relative_error < 5.e-6, "%s: JVP vs assembled matrix %.2e", what, relative_error);
+
+  mfem::Vector f_values[5];
+  for (int i = 0; i < 5; i++) {
+    mfem::Vector U_plus_small = U;
+    U_plus_small.Add((i - 2) * epsilon, dU);
+    f_values[i] = f(t, U_plus_small);
+  }
+  mfem::Vector df1_fd[2], df1_cd[2];
+  df1_fd[0] = f_values[4];
+  df1_fd[0] -= f_values[2];
+  df1_fd[0] /= (2.0 * epsilon);
+  df1_fd[1] = f_values[3];
+  df1_fd[1] -= f_values[2];
+  df1_fd[1] /= epsilon;
+  df1_cd[0] = f_values[4];
+  df1_cd[0] -= f_values[0];
+  df1_cd[0] /= (4.0 * epsilon);
+  df1_cd[1] = f_values[3];
+  df1_cd[1] -= f_values[1];
+  df1_cd[1] /= (2.0 * epsilon);
+  double denominator = (df_jvp1.Norml2() < 1.0e-10) ? 1.0 : df_jvp1.Norml2();
+  double e1 = df1_fd[0].DistanceTo(df_jvp1.GetData()) / denominator;
+  double e2 = df1_fd[1].DistanceTo(df_jvp1.GetData()) / denominator;
+  EXPECT(std::fabs(e1 / e2 - 2.0) < 0.1 || std::fmin(e1, e2) < 1.0e-9, "%s: forward differences e1 %.2e e2 %.2e", what, e1, e2);
+  double e3 = df1_cd[0].DistanceTo(df_jvp1.GetData()) / denominator;
+  double e4 = df1_cd[1].DistanceTo(df_jvp1.GetData()) / denominator;
+  EXPECT((std::fabs(e3 / e4 - 4.0) < 0.1) || std::fmin(e3, e4) < 1.0e-9, "%s: centred differences e3 %.2e e4 %.2e", what, e3, e4);
+}
+
+template <int p>
+void elasticity_gradients(mfem::Mesh& mesh, const char* tag)  // functional_basic_h1_vector.cpp:119-141
+{
+  constexpr int dim = 3;
+  using space       = H1<p, dim>;
+  mfem::H1_FECollection    fec(p, dim);
+  mfem::FiniteElementSpace fes(&mesh, &fec, dim, mfem::Ordering::byVDIM);
+  mfem::Vector             U(fes.GetVSize());
+  U.Randomize(5);
+  Functional<space(space)> residual(&fes, {&fes});
+  residual.AddDomainIntegral(Dimension<dim>{}, DependsOn<0>{}, ElasticityTestModelOne<dim>{}, mesh);
+  residual.AddBoundaryIntegral(Dimension<dim - 1>{}, DependsOn<0>{}, ElasticityTestModelTwo<dim>{}, mesh);
+  std::string what = std::string("elasticity_test ") + tag + " p=" + std::to_string(p);
+  check_gradient(residual, 0.0, U, what.c_str());
+}
+
+// ---- ShapeAwareFunctional ------------------------------------------------------------------------------------------------
+template <int p>
+void shape_aware(mfem::Element::Type type, const char* tag)
+{
+  constexpr int dim = 3;
+  using space       = H1<p>;
+  using shape_space = H1<1, dim>;
+  mfem::Mesh               mesh = make_mesh(type);
+  mfem::H1_FECollection    fec(p, dim), shape_fec(1, dim);
+  mfem::FiniteElementSpace fes(&mesh, &fec), shape_fes(&mesh, &shape_fec, dim, mfem::Ordering::byVDIM);
+  mfem::Vector             U(fes.GetVSize()), S(shape_fes.GetVSize());
+  U.Randomize(6);
+  S.Randomize(7);
+  S *= 0.03;
+  ShapeAwareFunctional<shape_space, space(space)> shaped(&shape_fes, &fes, {&fes});
+  shaped.AddDomainIntegral(Dimension<dim>{}, DependsOn<0>{}, NonlinearThermal{}, mesh);
+  mfem::Vector r_shaped = shaped(0.0, S, U);
+  // the same integrand on the mesh whose (order-1, byVDIM) nodes were moved by the shape displacement
+  mfem::Mesh moved = make_mesh(type);
+  {
+    mfem::GridFunction& nodes = *moved.GetNodes();
+    const bool by_vdim = nodes.FESpace()->GetOrdering() == mfem::Ordering::byVDIM;
+    const int  nn      = nodes.FESpace()->GetNDofs();
+    for (int n = 0; n < nn; n++)
+      for (int c = 0; c < dim; c++) nodes(by_vdim ? n * dim + c : c * nn + n) += S(n * dim + c);
+  }
+  mfem::FiniteElementSpace fes_moved(&moved, &fec);
+  Functional<space(space)> plain(&fes_moved, {&fes_moved});
+  plain.AddDomainIntegral(Dimension<dim>{}, DependsOn<0>{}, NonlinearThermal{}, moved);
+  mfem::Vector r_plain = plain(0.0, U);
+  EXPECT(rel(r_shaped, r_plain) < 1e-12, "shape-aware %s p=%d: residual on X + p(X) vs plain Functional on the moved mesh %.2e",
+         tag, p, rel(r_shaped, r_plain));
+  // derivative w.r.t. the field through the shape-aware wrapper: JVP vs central difference
+  auto [r, drdU] = shaped(0.0, S, differentiate_wrt(U));
+  mfem::Vector dU(U.Size());
+  dU.Randomize(8);
+  mfem::Vector jvp = drdU(dU);
+  const double eps = 1e-6;
+  mfem::Vector Up(U), Um(U);
+  Up.Add(eps, dU);
+  Um.Add(-eps, dU);
+  mfem::Vector fd = shaped(0.0, S, Up);
+  mfem::Vector fm = shaped(0.0, S, Um);
+  fd -= fm;
+  fd /= (2.0 * eps);
+  EXPECT(rel(jvp, fd) < 1e-7, "shape-aware %s p=%d: d/dU JVP vs central difference %.2e", tag, p, rel(jvp, fd));
+}
+
+int main(int argc, char** argv)
+{
+  const std::string which = argc > 1 ? argv[1] : "all";
+  mfem::Mesh        hexes = make_mesh(mfem::Element::HEXAHEDRON);
+  mfem::Mesh        tets  = make_mesh(mfem::Element::TETRAHEDRON);
+  if (which == "comparisons" || which == "all") {
+    thermal_comparison<1>(hexes, "hexes");
+    thermal_comparison<2>(hexes, "hexes");
+    thermal_comparison<3>(hexes, "hexes");
+    // (the reference compares against MFEM's integrators on tensor-product meshes only: on simplices of order >= 2 serac's
+    // quadrature rules (polynomials.hpp:57-260) and mfem's IntRules differ; p = 1 integrands are exact under both)
+    thermal_comparison<1>(tets, "tets");
+    elasticity_comparison<1>(hexes, "hexes");
+    elasticity_comparison<2>(hexes, "hexes");
+    elasticity_comparison<1>(tets, "tets");
+  }
+  if (which == "gradients" || which == "all") {
+    elasticity_gradients<1>(hexes, "hexes");
+    elasticity_gradients<2>(hexes, "hexes");
+    elasticity_gradients<1>(tets, "tets");
+    elasticity_gradients<2>(tets, "tets");
+  }
+  if (which == "shape" || which == "all") {
+    shape_aware<2>(mfem::Element::HEXAHEDRON, "hexes");
+    shape_aware<1>(mfem::Element::TETRAHEDRON, "tets");
+  }
+  std::printf("%s: %d failure(s)\n", which.c_str(), g_failures);
+  return g_failures == 0 ? 0 : 1;
+}
