@@ -175,6 +175,30 @@ def build_structured_problem(device):
                 mesh=f"structured {n[0]}x{n[1]}x{n[2]} hexes, one GPU")
 
 
+def bind_to_gpu_numa_node(local_rank):
+    """pin this process (and, by first touch, the host buffers it allocates next) to the NUMA node of its GPU"""
+    try:
+        import torch
+        bus = torch.cuda.get_device_properties(local_rank).pci_bus_id
+        dom = torch.cuda.get_device_properties(local_rank).pci_domain_id
+        dev = torch.cuda.get_device_properties(local_rank).pci_device_id
+        path = f"/sys/bus/pci/devices/{dom:04x}:{bus:02x}:{dev:02x}.0/numa_node"
+        node = int(open(path).read().strip())
+        if node < 0:
+            return None
+        cpus = []
+        for part in open(f"/sys/devices/system/node/node{node}/cpulist").read().strip().split(","):
+            lo, _, hi = part.partition("-")
+            cpus += list(range(int(lo), int(hi or lo) + 1))
+        allowed = sorted(set(cpus) & os.sched_getaffinity(0))
+        if allowed:
+            os.sched_setaffinity(0, allowed)
+            return node
+    except Exception:  # noqa: BLE001  (no sysfs entry, no permission: stay where we are)
+        pass
+    return None
+
+
 def synthetic_u(gid):
     """displacement as a function of the GLOBAL vdof id (shared dofs agree across ranks; small against the element size)"""
     return 0.016 * ELEMENT_SIZE * np.sin(0.37 * np.asarray(gid, dtype=np.float64) + 1.0)
@@ -444,7 +468,10 @@ def run_product(args):
         r, dr = views["r"].clone(), views["dr"].clone()
 
     # --- end to end through the host-buffer API (pinned host memory in, host memory out) ---
-    pin = lambda a: torch.as_tensor(a, dtype=torch.float64).pin_memory()
+    # every rank's host buffers live on the NUMA node its GPU hangs off (first touch after binding the process there):
+    # eight ranks pulling from node 0 share one socket's memory controllers and one inter-socket link
+    numa = bind_to_gpu_numa_node(local) if world > 1 else None
+    pin = lambda a: torch.as_tensor(a, dtype=torch.float64).clone().pin_memory()
     hU, hA, hS, hdU = (pin(P["host"][k]) for k in ("U", "A", "S", "dU"))
     hr = torch.empty(P["tdofs"], dtype=torch.float64).pin_memory()
     hdr = torch.empty(P["tdofs"], dtype=torch.float64).pin_memory()
@@ -462,18 +489,68 @@ def run_product(args):
         if inplace:
             dS, dUd, dA, ddU = (torch.zeros_like(x) for x in (S, U, A, dU))  # L-sized, T-vector in the prefix
             ts, ts1 = P["tdofs"], P["tdofs_shape"]
+            # the copies run on their own streams, as sb_functional_* does with SB_HOST_ASYNC at one rank: the direction
+            # of the Jacobian action goes up during the evaluation, the residual comes down during the Jacobian action
+            up, down = torch.cuda.Stream(), torch.cuda.Stream()
+            ev = {k: torch.cuda.Event() for k in ("in", "du", "r", "dr", "consumed", "copied")}
+
+            # the device work between the copies is two CUDA graphs (evaluation with its exchanges; Jacobian action with
+            # its exchanges), so the host side of a step is a dozen calls -- at one rank the C ABI does the same inside
+            # sb_functional_evaluate / sb_functional_jvp
+            host_graphs = None
+            if use_graph:
+                gA, gB, out_views = torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph(), {}
+                cap = torch.cuda.Stream()
+                with torch.cuda.stream(cap):
+                    for _ in range(2):  # warm-up on the capture stream
+                        call(0.0, [dS, dUd, dA], wrt=1)
+                        call.GradientMult(1, ddU)
+                        call.join()
+                    torch.cuda.synchronize()
+                    dist.barrier()
+                    with torch.cuda.graph(gA, stream=cap):
+                        out_views["r"] = call(0.0, [dS, dUd, dA], wrt=1)
+                        call.join()
+                    with torch.cuda.graph(gB, stream=cap):
+                        out_views["dr"] = call.GradientMult(1, ddU)
+                torch.cuda.synchronize()
+                dist.barrier()
+                host_graphs = (gA, gB)
 
             def step_host():
-                dS[:ts1].copy_(hS, non_blocking=True)
-                dUd[:ts].copy_(hU, non_blocking=True)
-                dA[:ts].copy_(hA, non_blocking=True)
-                rv = call(0.0, [dS, dUd, dA], wrt=1)
-                ddU[:ts].copy_(hdU, non_blocking=True)
-                drv = call.GradientMult(1, ddU)
-                call.join()
-                hr.copy_(rv, non_blocking=True)
-                hdr.copy_(drv, non_blocking=True)
-                torch.cuda.current_stream().synchronize()
+                main = torch.cuda.current_stream()
+                up.wait_event(ev["consumed"])  # the previous step's kernels are done with the staging buffers
+                with torch.cuda.stream(up):
+                    dS[:ts1].copy_(hS, non_blocking=True)
+                    dUd[:ts].copy_(hU, non_blocking=True)
+                    dA[:ts].copy_(hA, non_blocking=True)
+                    ev["in"].record(up)
+                    ddU[:ts].copy_(hdU, non_blocking=True)
+                    ev["du"].record(up)
+                main.wait_event(ev["in"])
+                main.wait_event(ev["copied"])  # the previous step's downloads have left the Functional's L-vectors
+                if host_graphs:
+                    host_graphs[0].replay()
+                    rv = out_views["r"]
+                else:
+                    rv = call(0.0, [dS, dUd, dA], wrt=1)
+                    call.join()  # the residual's P^T ran on the side stream
+                ev["r"].record(main)
+                main.wait_event(ev["du"])
+                if host_graphs:
+                    host_graphs[1].replay()
+                    drv = out_views["dr"]
+                else:
+                    drv = call.GradientMult(1, ddU)
+                ev["dr"].record(main)
+                ev["consumed"].record(main)
+                with torch.cuda.stream(down):
+                    down.wait_event(ev["r"])
+                    hr.copy_(rv, non_blocking=True)
+                    down.wait_event(ev["dr"])
+                    hdr.copy_(drv, non_blocking=True)
+                    ev["copied"].record(down)
+                down.synchronize()
         else:
             dS, dUd, dA, ddU = (torch.empty_like(x, device=dev) for x in (hS, hU, hA, hdU))
             d_r, d_dr = torch.empty_like(r), torch.empty_like(dr)
@@ -562,7 +639,9 @@ def run_product(args):
                                         "input exchange" if P.get("n_independent") else "") if world > 1 else "")},
         "e2e": {"value": vdofs_total / e2e_s / 1e9, "unit": "GDOF/s",
                 "h2d_bytes_per_step": int(8 * (3 * vdofs_total + shape_total)),
-                "d2h_bytes_per_step": int(8 * 2 * vdofs_total), "ms_per_step": e2e_s * 1e3},
+                "d2h_bytes_per_step": int(8 * 2 * vdofs_total), "ms_per_step": e2e_s * 1e3,
+                "host_buffers": "pinned" + (f", bound to the GPU's NUMA node (rank 0: node {numa})" if numa is not None
+                                            else "")},
         "gpu_launches": int(launches_per_step * args.steps),
         "phases_ms": {"evaluate_with_derivative_store": phase_ms[0], "scatter_r": phase_ms[1], "jvp": phase_ms[2],
                       "scatter_dr": phase_ms[3]},

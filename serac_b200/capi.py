@@ -115,6 +115,18 @@ SIGNATURES = {
     "sb_halo_P_finish": (_i, [_vp, _vp, _vp, _vp]),
     "sb_halo_Pt_pack": (_i, [_vp, _vp, _vp]),
     "sb_halo_Pt_finish": (_i, [_vp, _vp, _vp, _vp]),
+    # include/serac_b200_comm.h
+    "sb_comm_unique_id": (_i, [_vp]),
+    "sb_comm_create": (_i, [_vp, _i, _i, _pp]),
+    "sb_comm_destroy": (_i, [_vp]),
+    "sb_comm_rank": (_i, [_vp]),
+    "sb_comm_size": (_i, [_vp]),
+    "sb_comm_allreduce_sum": (_i, [_vp, _vp, _i64, _vp]),
+    "sb_comm_barrier": (_i, [_vp, _vp]),
+    "sb_halo_set_neighbor_ranks": (_i, [_vp, _vp]),
+    "sb_halo_P_nccl": (_i, [_vp, _vp, _vp, _vp, _vp]),
+    "sb_halo_Pt_nccl": (_i, [_vp, _vp, _vp, _vp, _vp]),
+    "sb_halo_enable_peer_ipc": (_i, [_vp, _vp]),
     # include/serac_b200_solvers.h
     "sb_vector_set_subvector": (_i, [_vp, _vp, _i64, _d, _vp]),
     "sb_vector_copy_subvector": (_i, [_vp, _vp, _vp, _i64, _vp]),

@@ -61,6 +61,36 @@ struct sb_integral_s {
   int                        nq = 0;
 };
 
+// ConformingProlongationOperator state of one space on one rank (mfem/fem/pfespace.cpp:3599-3663)
+struct sb_halo_s {
+  int64_t lsize = 0, tsize = 0, nsend = 0, nrecv = 0;
+  int*    ltdof_dev = nullptr;
+  int*    send_idx_dev = nullptr;  // P: true dofs packed for sharers.  P^T: received contributions add into these
+  int*    recv_idx_dev = nullptr;  // P: local dofs filled from owners. P^T: local dofs packed for owners
+  // P^T adds must be ordered: true dof -> ascending list of recv-buffer slots (deterministic, pfespace.cpp:3912-3931)
+  int64_t* add_offsets_dev = nullptr;
+  int*     add_slots_dev   = nullptr;
+  double*  send_buf = nullptr;
+  double*  recv_buf = nullptr;
+  double*  own_send = nullptr;  // allocations of this object (send_buf / recv_buf may point at caller memory)
+  double*  own_recv = nullptr;
+  // peer-memory transport (sb_halo_enable_peer)
+  int                 nn = 0;
+  std::vector<int64_t> send_off, recv_off;
+  struct PeerState*   peer_dev = nullptr;
+  bool                peer_enabled = false;
+  // multi-process setup (comm.cu): the ranks of the neighbours, this rank's own ring and the mapped rings of the others
+  std::vector<int>    neighbor_ranks;
+  double*             ipc_ring = nullptr;              // cudaMalloc'd by sb_halo_enable_peer_ipc (freed with the object)
+  std::vector<void*>  ipc_mapped;                      // cudaIpcOpenMemHandle results (closed with the object)
+  // owned-first local numbering (ltdof[i] == i below tsize, -1 above): the T-vector is the prefix of the L-vector and
+  // P / P^T only touch the shared entries ("in place")
+  bool    owned_first  = false;
+  int*    shared_t_dev = nullptr;  // true dofs that receive contributions in P^T
+  int64_t nshared      = 0;
+};
+
+
 /// map of the element matrices of one pair of restrictions (domain elements or boundary faces) into a pattern
 struct CsrExtraMap {
   int64_t   num_entries = 0, num_unique = 0;
