@@ -542,6 +542,23 @@ class LinearIsotropic:
         return [[lam * t * (1.0 if i == j else 0.0) + 2.0 * self.G * eps[i][j] for j in range(d)] for i in range(d)]
 
 
+class StVenantKirchhoff:
+    """src/serac/physics/materials/solid_material.hpp:61-92"""
+
+    def __init__(self, density, K, G):
+        self.density, self.K, self.G = density, K, G
+
+    def __call__(self, state, grad_u):
+        d = len(grad_u)
+        F = madd(grad_u, eye(d))
+        E = mscale(0.5, madd(madd(grad_u, mT(grad_u)), mdot(mT(grad_u), grad_u)))
+        trE = mtr(E)
+        devE = mdev(E)
+        S = [[2.0 * self.G * devE[i][j] + (self.K * trE if i == j else 0.0) for j in range(d)] for i in range(d)]
+        P = mdot(F, S)
+        return mscale(1.0 / mdet(F), mdot(P, mT(F)))
+
+
 class J2SmallStrainLinear:
     """src/serac/physics/materials/solid_material.hpp:201-259 with LinearHardening (:132-149).  The return map's scalar
     residual is linear in delta_eqps for linear hardening, so the safeguarded Newton solve of
@@ -549,8 +566,10 @@ class J2SmallStrainLinear:
     the implicit-function rule at :664-676.  state = dict(plastic_strain [..][3][3] list of arrays, eqps array)."""
     tol = 1e-10
 
-    def __init__(self, E, nu, sigma_y, Hi, Hk, density):
+    def __init__(self, E, nu, sigma_y, Hi, Hk, density, hardening=None):
         self.E, self.nu, self.sigma_y, self.Hi, self.Hk, self.density = E, nu, sigma_y, Hi, Hk, density
+        # hardening law: (value, derivative) of the flow stress as functions of the accumulated plastic strain
+        self.hardening = hardening or ((lambda e: sigma_y + Hi * e), (lambda e: Hi + 0.0 * e))
 
     def __call__(self, state, du_dX):
         K = self.E / (3.0 * (1.0 - 2.0 * self.nu))
@@ -563,11 +582,21 @@ class J2SmallStrainLinear:
         eta = msub(s, sigma_b)
         q = np.sqrt(1.5) * mnorm(eta)
         qv = value_of(q)
-        resid0 = qv - (self.sigma_y + self.Hi * eqps_old)
+        h, dh = self.hardening
+        resid0 = qv - h(eqps_old)
         yielding = resid0 > self.tol * self.sigma_y
-        denom = 3.0 * G + self.Hk + self.Hi
-        # root of  q - (3G + Hk) d - sigma_y - Hi (eqps_old + d) = 0 ; d(delta)/dq = 1 / denom
-        delta = (q - (self.sigma_y + self.Hi * eqps_old)) / denom
+        # root of  q - (3G + Hk) d - h(eqps_old + d) = 0  (solid_material.hpp:229-247; Newton on the values -- one step for
+        # linear hardening), then d(delta)/dq = 1 / (3G + Hk + h'(eqps_old + d)) by the implicit-function rule
+        # (tuple_tensor_dual_functions.hpp:664-676)
+        dvn = np.zeros_like(qv)
+        for _ in range(60):
+            f = qv - (3.0 * G + self.Hk) * dvn - h(eqps_old + dvn)
+            dvn = np.where(yielding, dvn + f / (3.0 * G + self.Hk + dh(eqps_old + dvn)), 0.0)
+        slope = 3.0 * G + self.Hk + dh(eqps_old + dvn)
+        if isinstance(q, Dual):
+            delta = Dual(dvn, q.g / slope[..., None])
+        else:
+            delta = dvn
         mask = yielding.astype(float)
         qsafe = q if not isinstance(q, Dual) else Dual(np.where(yielding, q.v, 1.0), q.g)
         if not isinstance(q, Dual):
@@ -1031,6 +1060,16 @@ def make_qf(kind, params):
         return shape_aware(material_stress_qf(LinearIsotropic(*params[:3]), params[3] != 0.0))
     if kind == "solid_j2smallstrain_linear":
         return shape_aware(material_stress_qf(J2SmallStrainLinear(*params[:6]), params[6] != 0.0))
+    if kind == "solid_j2smallstrain_powerlaw":  # E nu sigma_y n eps0 Hk density gn (solid_material.hpp:154-173)
+        E, nu, sy, n, e0, Hk, rho = params[:7]
+        law = ((lambda e: sy * (1.0 + e / e0)**(1.0 / n)), (lambda e: sy / (n * e0) * (1.0 + e / e0)**(1.0 / n - 1.0)))
+        return shape_aware(material_stress_qf(J2SmallStrainLinear(E, nu, sy, 0.0, Hk, rho, hardening=law), params[7] != 0.0))
+    if kind == "solid_j2smallstrain_voce":  # E nu sigma_y sigma_sat strain_constant Hk density gn (:180-198)
+        E, nu, sy, ss, c, Hk, rho = params[:7]
+        law = ((lambda e: ss - (ss - sy) * np.exp(-e / c)), (lambda e: (ss - sy) / c * np.exp(-e / c)))
+        return shape_aware(material_stress_qf(J2SmallStrainLinear(E, nu, sy, 0.0, Hk, rho, hardening=law), params[7] != 0.0))
+    if kind == "solid_stvk":
+        return shape_aware(material_stress_qf(StVenantKirchhoff(*params[:3]), params[3] != 0.0))
     if kind == "solid_j2_linear":
         return shape_aware(material_stress_qf(J2FiniteLinear(*params[:5]), params[5] != 0.0))
     if kind == "thermal_linear_conductor":

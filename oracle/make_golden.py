@@ -425,6 +425,17 @@ FIXTURES = [
                                                   p=2, params=[1.0, 1.0, 3.0], vdim=1)),
     # BASELINE.json configs[2] material family: J2 plasticity with QuadratureData state (plastic loading: the return map
     # runs at most points with these parameters), E nu sigma_y Hi Hk density geom_nonlin
+    # the remaining hardening laws of solid_material.hpp (:154-198) and St. Venant-Kirchhoff (:61-92)
+    ("solid_j2smallstrain_powerlaw_hex_p2_cart", dict(mesh_spec=("cart3d", 2, 1, 2, 0.02),
+                                                      kind="solid_j2smallstrain_powerlaw", p=2,
+                                                      params=[100.0, 0.25, 0.5, 3.0, 0.01, 2.0, 1.0, 0.0], vdim=3,
+                                                      u_amp=0.02)),
+    ("solid_j2smallstrain_voce_hex_p2_cart", dict(mesh_spec=("cart3d", 2, 1, 2, 0.02),
+                                                  kind="solid_j2smallstrain_voce", p=2,
+                                                  params=[100.0, 0.25, 0.5, 0.9, 0.02, 2.0, 1.0, 0.0], vdim=3,
+                                                  u_amp=0.02)),
+    ("solid_stvk_hex_p2_cart", dict(mesh_spec=("cart3d", 2, 1, 2, 0.02), kind="solid_stvk", p=2,
+                                    params=[1.0, 100.0, 50.0, 1.0], vdim=3)),
     ("solid_j2smallstrain_linear_hex_p2_cart", dict(mesh_spec=("cart3d", 2, 1, 2, 0.02),
                                                     kind="solid_j2smallstrain_linear", p=2,
                                                     params=[100.0, 0.25, 0.5, 5.0, 2.0, 1.0, 0.0], vdim=3, u_amp=0.02)),

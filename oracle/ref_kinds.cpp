@@ -143,6 +143,36 @@ ref::Registrar r3("solid_j2smallstrain_linear_" TAG, [](mfem::Mesh& mesh, const 
 #endif
 
 #if REF_DIM == 3
+// the other hardening laws of solid_material.hpp (:154-198) under the same small-strain J2 model
+template <typename Hardening>
+ref::IntegralHolder make_j2_small(mfem::Mesh& mesh, Hardening hardening, const double* q)
+{
+  using Material = solid_mechanics::J2SmallStrain<Hardening>;
+  Material m{q[0], q[1], hardening, q[5], q[6]};
+  ref::IntegralHolder h;
+  using QF = ShapeAwareWithState<MaterialStress<Material>, solid_test, H1<p, dim>, H1<p, dim>>;
+  QF     qf{MaterialStress<Material>{m, q[7] != 0.0}};
+  Domain d  = ref::domain_for(mesh);
+  auto   qd = make_qdata<typename Material::State>(mesh, h, typename Material::State{});
+  h.integral   = std::make_unique<Integral>(MakeDomainIntegral<solid_sig, p + 1, dim>(d, qf, qd, {0, 1, 2}));
+  h.num_trials = 3;
+  return h;
+}
+ref::Registrar r3p("solid_j2smallstrain_powerlaw_" TAG, [](mfem::Mesh& mesh, const double* q, int n) {
+  SLIC_ERROR_IF(n != 8, "params: E nu sigma_y n eps0 Hk density geom_nonlin");
+  return make_j2_small(mesh, solid_mechanics::PowerLawHardening{q[2], q[3], q[4]}, q);
+});
+ref::Registrar r3v("solid_j2smallstrain_voce_" TAG, [](mfem::Mesh& mesh, const double* q, int n) {
+  SLIC_ERROR_IF(n != 8, "params: E nu sigma_y sigma_sat strain_constant Hk density geom_nonlin");
+  return make_j2_small(mesh, solid_mechanics::VoceHardening{q[2], q[3], q[4]}, q);
+});
+ref::Registrar r3s("solid_stvk_" TAG, [](mfem::Mesh& mesh, const double* q, int n) {
+  SLIC_ERROR_IF(n != 4, "params: density K G geom_nonlin");
+  return make_solid_stateless(mesh, solid_mechanics::StVenantKirchhoff{q[0], q[1], q[2]}, q[3] != 0.0);
+});
+#endif
+
+#if REF_DIM == 3
 ref::Registrar r3f("solid_j2_linear_" TAG, [](mfem::Mesh& mesh, const double* q, int n) {
   SLIC_ERROR_IF(n != 6, "params: E nu sigma_y Hi density geom_nonlin");
   using Material = solid_mechanics::J2<solid_mechanics::LinearHardening>;

@@ -68,6 +68,34 @@ static Registrar r_j2f({"solid_j2_linear_" SB_STR(SB_REG_TAG),
                         "{E, nu, sigma_y, Hi, density, geometric_nonlinearity(0|1)}"});
 #endif
 
+#ifdef SB_REG_J2
+// the other hardening laws (solid_material.hpp:154-198) and St. Venant-Kirchhoff (:61-92), H1 p <= 2 hexes
+using J2Power = solid_mechanics::J2SmallStrain<solid_mechanics::PowerLawHardening>;
+using J2Voce  = solid_mechanics::J2SmallStrain<solid_mechanics::VoceHardening>;
+template <typename SS, typename Hardening>
+long make_j2_hardening(const double* p, int n, void* out, size_t cap)
+{
+  if (n != 8) return -1;
+  using M = solid_mechanics::J2SmallStrain<Hardening>;
+  M    m{p[0], p[1], Hardening{p[2], p[3], p[4]}, p[5], p[6]};
+  auto gn = (p[7] != 0.0) ? GeometricNonlinearities::On : GeometricNonlinearities::Off;
+  typename SS::template qf<M> qf{MaterialStressFunctor<M>(m, gn)};
+  return store_blob(qf, out, cap);
+}
+static Registrar r_j2p({"solid_j2smallstrain_powerlaw_" SB_STR(SB_REG_TAG),
+                        make_kernel_table<S::type, S::qf<J2Power>, J2Power::State>(),
+                        &make_j2_hardening<S, solid_mechanics::PowerLawHardening>,
+                        "{E, nu, sigma_y, n, eps0, Hk, density, geometric_nonlinearity(0|1)}"});
+static Registrar r_j2v({"solid_j2smallstrain_voce_" SB_STR(SB_REG_TAG),
+                        make_kernel_table<S::type, S::qf<J2Voce>, J2Voce::State>(),
+                        &make_j2_hardening<S, solid_mechanics::VoceHardening>,
+                        "{E, nu, sigma_y, sigma_sat, strain_constant, Hk, density, geometric_nonlinearity(0|1)}"});
+using solid_mechanics::StVenantKirchhoff;
+static Registrar r_stvk({"solid_stvk_" SB_STR(SB_REG_TAG),
+                         make_kernel_table<S::type, S::qf<StVenantKirchhoff>, StVenantKirchhoff::State>(),
+                         &make_solid<S, StVenantKirchhoff>, "{density, K, G, geometric_nonlinearity(0|1)}"});
+#endif
+
 #ifdef SB_REG_AD
 // the same integrand differentiated with dual numbers end to end (the reference's scheme; what an arbitrary user functor
 // gets): kept to cross-check the tangent fast path

@@ -290,7 +290,8 @@ struct J2 {
   double        density;
 
   struct State {
-    tensor<double, dim, dim> Fpinv;                       ///< inverse of the plastic distortion (identity initially)
+    /// inverse of the plastic distortion; State{} is the virgin material, as in the reference (solid_material.hpp:273)
+    tensor<double, dim, dim> Fpinv = DenseIdentity<dim>();
     double                   accumulated_plastic_strain;  ///< uniaxial equivalent plastic strain
   };
 

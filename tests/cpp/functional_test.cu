@@ -6,6 +6,7 @@
 //   functional_test <case> <directory>
 //     solid     H1<2,3>(H1<1,3>, H1<2,3>, H1<2,3>), shape-aware NeoHookean stress integrand (hex or tet mesh)
 //     j2        same signature, J2SmallStrain<LinearHardening> with QuadratureData state, updateQdata(true)
+//     j2_finite finite-deformation J2 with a default-constructed state buffer; checkpoint / restart of the state
 //     pressure  same signature, ONE boundary integral: follower pressure (hex mesh, quadrilateral faces)
 //     user      H1<2>(H1<2>) with a q-function defined in THIS file: checked here against finite differences and the
 //               assembled matrix (check_gradient.hpp:16-90)
@@ -323,6 +324,49 @@ int run_j2(const std::map<std::string, double>& meta)
   return 0;
 }
 
+/// finite-deformation J2 (solid_material.hpp:261-330) with a DEFAULT-constructed state buffer -- State{} must be the
+/// virgin material (Fpinv = I) -- and the checkpoint round trip of the quadrature-point state (to_host / from_host: what a
+/// restart does with the buffer the reference saves through sidre, state_manager.cpp:213-224)
+int run_j2_finite(const std::map<std::string, double>& meta)
+{
+  Problem P = load_problem(meta, false);
+  auto    q = read_bin<double>("params");  // E nu sigma_y Hi density geom_nonlin
+  using Material = solid_mechanics::J2<solid_mechanics::LinearHardening>;
+  Material m{q[0], q[1], solid_mechanics::LinearHardening{q[2], q[3]}, q[4]};
+  auto     gn = q[5] != 0.0 ? GeometricNonlinearities::On : GeometricNonlinearities::Off;
+  const int nq = num_quadrature_points(P.space.geometry, p + 1);
+  Vector S(read_bin<double>("S")), U(read_bin<double>("U")), A(read_bin<double>("A")), dU(read_bin<double>("dU"));
+  std::vector<Material::State> checkpoint;
+  {
+    SolidFunctional residual(&P.space, {&P.shape_space, &P.space, &P.space});
+    auto            qdata = std::make_shared<QuadratureData<Material::State>>(P.mesh.GetNE(), nq);  // State{} everywhere
+    Domain          whole = EntireDomain(P.mesh);
+    residual.AddDomainIntegral(Dimension<dim>{}, DependsOn<0, 1, 2>{},
+                               SolidIntegrand<Material>(MaterialStressFunctor<Material>(m, gn)), whole, qdata);
+    auto [r, drdu] = residual(0.0, S, differentiate_wrt(U), A);
+    write_bin("r", r.to_host());
+    write_bin("dr", drdu(dU).to_host());
+    residual.updateQdata(true);
+    residual(0.0, S, U, A);
+    residual.updateQdata(false);
+    checkpoint = qdata->to_host();
+    std::vector<double> flat(checkpoint.size() * sizeof(Material::State) / sizeof(double));
+    std::memcpy(flat.data(), checkpoint.data(), flat.size() * sizeof(double));
+    write_bin("qdata1", flat);
+    write_bin("r_after_commit", residual(0.0, S, U, A).to_host());
+  }
+  {  // restart: a fresh Functional and state buffer, restored from the checkpoint
+    SolidFunctional residual(&P.space, {&P.shape_space, &P.space, &P.space});
+    auto            qdata = std::make_shared<QuadratureData<Material::State>>(P.mesh.GetNE(), nq);
+    qdata->from_host(checkpoint);
+    Domain whole = EntireDomain(P.mesh);
+    residual.AddDomainIntegral(Dimension<dim>{}, DependsOn<0, 1, 2>{},
+                               SolidIntegrand<Material>(MaterialStressFunctor<Material>(m, gn)), whole, qdata);
+    write_bin("r_after_restart", residual(0.0, S, U, A).to_host());
+  }
+  return 0;
+}
+
 int run_pressure(const std::map<std::string, double>& meta)
 {
   Problem P = load_problem(meta, true);
@@ -582,6 +626,7 @@ int main(int argc, char** argv)
   int rc = 2;
   if (which == "solid") rc = run_solid(meta);
   if (which == "j2") rc = run_j2(meta);
+  if (which == "j2_finite") rc = run_j2_finite(meta);
   if (which == "pressure") rc = run_pressure(meta);
   if (which == "user") rc = run_user(meta);
   if (which == "newton") rc = run_newton(meta, false) || run_newton(meta, true) || run_newton(meta, false, true);

@@ -100,6 +100,23 @@ def test_j2_state_functional(tmp_path, cuda):
     assert rel_l2(out(d, "r_after_commit"), want) < TOL
 
 
+def test_j2_finite_strain_default_state_and_checkpoint_restart(tmp_path, cuda):
+    """J2::State{} is the virgin material (Fpinv = I, solid_material.hpp:273); the state buffer survives a
+    to_host / from_host round trip into a fresh Functional (QuadratureData checkpointing)"""
+    prob = load_golden("solid_j2_linear_hex_p2_cart")
+    q0 = np.asarray(prob["qdata0"]).reshape(-1, 10)
+    assert np.array_equal(q0[:, :9], np.tile(np.eye(3).ravel(), (len(q0), 1))) and not q0[:, 9].any()
+    d = str(tmp_path)
+    export(prob, d)
+    run("j2_finite", d)
+    assert rel_l2(out(d, "r"), prob["r"]) < TOL
+    assert rel_l2(out(d, "dr"), prob["dr"]) < TOL
+    assert rel_l2(out(d, "qdata1"), np.asarray(prob["qdata1"]).ravel()) < TOL
+    want = fo.scatter_add(prob["dof_info"] & MASK, prob["r_E_after_commit"], np.zeros(len(prob["U"])), 3)
+    assert rel_l2(out(d, "r_after_commit"), want) < TOL
+    assert np.array_equal(out(d, "r_after_restart"), out(d, "r_after_commit"))  # same state, same bits
+
+
 def test_boundary_pressure_functional(tmp_path, cuda):
     prob = load_golden("bdr_solid_pressure_hex_p2_cart")
     d = str(tmp_path)

@@ -275,3 +275,27 @@ def test_evaluation_in_two_halves_is_bit_identical(case):
         assert P.torch.equal(P.integral.export_derivatives(1), ref_d)
     dr = P.F.GradientMult(1, P.dU).cpu().numpy()
     assert rel_l2(dr, prob["dr"]) < TOL
+
+
+def test_geometric_factors_refresh_after_node_move():
+    """Shape-optimisation loops move the mesh nodes and re-run GeometricFactors: the integral
+    keeps POINTERS to X_q / J_q, so recomputing them in place on the device updates it -- no rebuild.  Moving the nodes by
+    a field p and evaluating with zero shape displacement must equal evaluating on the original nodes with shape
+    displacement p (the identity ShapeAwareFunctional rests on, shape_aware_functional.hpp:364-438)."""
+    import torch
+    from serac_b200 import capi
+    prob = load_golden("solid_neohookean_hex_p2_patch")
+    dev = torch.device("cuda:0")
+    P = Product(prob, dev)
+    rng = np.random.default_rng(5)
+    shape = P.t(0.02 * rng.uniform(-1, 1, P.G_shape.LSize()))
+    r_shape = P.F(0.0, [shape, P.U, P.A]).clone()
+    # the mesh-nodes space is order 1 with the same numbering as the shape space; both byVDIM in this fixture
+    assert int(prob["mesh_ordering"]) == capi.BYVDIM and int(prob["mesh_order"]) == 1
+    moved = P.nodes + shape
+    check = capi.check
+    check(capi.lib().sb_geometric_factors(P.geom, 1, P.p + 1, P.G_mesh.h, capi._dev_ptr(moved), None, int(prob["ne"]),
+                                          capi._dev_ptr(P.X_q), capi._dev_ptr(P.J_q), capi._stream_ptr()))
+    r_moved = P.F(0.0, [torch.zeros_like(shape), P.U, P.A])
+    assert rel_l2(r_moved.cpu().numpy(), r_shape.cpu().numpy()) < 1e-12
+    assert rel_l2(r_moved.cpu().numpy(), prob["r"]) > 1e-3  # the move really changed the answer
