@@ -274,6 +274,7 @@ int     sb_debug_assembly_plan_host(const int* test_table, int test_npe, int tes
 int     sb_csr_destroy(sb_csr_t A);
 int64_t sb_csr_nnz(sb_csr_t A);
 int64_t sb_csr_num_rows(sb_csr_t A);
+int64_t sb_csr_num_cols(sb_csr_t A);
 int     sb_csr_pattern_dev(sb_csr_t A, const int** row_ptr_dev, const int** col_ind_dev);
 int     sb_csr_pattern_to_host(sb_csr_t A, int* row_ptr_host, int* col_ind_host);
 /* values[nz] = sum over the contributing K_e entries in ascending (element, i, j) order (deterministic gather;

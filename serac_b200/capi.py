@@ -77,6 +77,7 @@ SIGNATURES = {
     "sb_csr_destroy": (_i, [_vp]),
     "sb_csr_nnz": (_i64, [_vp]),
     "sb_csr_num_rows": (_i64, [_vp]),
+    "sb_csr_num_cols": (_i64, [_vp]),
     "sb_csr_pattern_dev": (_i, [_vp, _pp, _pp]),
     "sb_csr_pattern_to_host": (_i, [_vp, _vp, _vp]),
     "sb_csr_assemble": (_i, [_vp, _vp, _vp, _vp]),

@@ -426,6 +426,7 @@ extern "C" int sb_csr_destroy(sb_csr_t A)
 
 extern "C" int64_t sb_csr_nnz(sb_csr_t A) { return A->nnz; }
 extern "C" int64_t sb_csr_num_rows(sb_csr_t A) { return A->num_rows; }
+extern "C" int64_t sb_csr_num_cols(sb_csr_t A) { return A->num_cols; }
 extern "C" int     sb_csr_pattern_dev(sb_csr_t A, const int** rp, const int** ci)
 {
   *rp = A->row_ptr_dev;

@@ -632,17 +632,28 @@ extern "C" int sb_csr_eliminate_rows_cols(sb_csr_t A, double* values_dev, const 
   SB_REQUIRE(num_ess >= 0 && (num_ess == 0 || ess_dofs_dev), "sb_csr_eliminate_rows_cols: bad essential dof list");
   SB_REQUIRE(v.num_rows == 0 || values_dev, "sb_csr_eliminate_rows_cols: null values");
   if (v.num_rows == 0) return SB_OK;
+  // rows AND columns are eliminated, so the matrix must be square -- as for mfem's EliminateRowsCols
+  // (mfem/linalg/hypre_parcsr.cpp:476-489); the marker array is indexed by column as well as by row
+  SB_REQUIRE(sb_csr_num_cols(A) == v.num_rows, "sb_csr_eliminate_rows_cols: the matrix is not square");
   cudaStream_t   s    = as_stream(stream);
+  // scratch of this call from the stream-ordered allocator: no device synchronisation, and the whole Newton step stays
+  // enqueued on the caller's stream
   unsigned char* mark = nullptr;
-  if (int e = build_mark(ess_dofs_dev, num_ess, v.num_rows, s, &mark)) return e;
-  csr_eliminate_kernel<<<reducing_grid(v.num_rows, kWarpsPerCta), kThreads, 0, s>>>(v.row_ptr, v.col_ind, values_dev,
-                                                                                    values_e_dev, mark, v.num_rows);
-  sb_count_launch();
-  const cudaError_t launch = cudaGetLastError();
-  const cudaError_t done   = cudaStreamSynchronize(s);  // the marker array is scratch of this call
-  cudaFree(mark);
-  SB_CHECK_CUDA(launch);
-  SB_CHECK_CUDA(done);
+  SB_CHECK_CUDA(cudaMallocAsync((void**)&mark, size_t(v.num_rows), s));
+  cudaError_t err = cudaMemsetAsync(mark, 0, size_t(v.num_rows), s);
+  if (err == cudaSuccess && num_ess > 0) {
+    mark_kernel<<<reducing_grid(num_ess, kThreads), kThreads, 0, s>>>(mark, ess_dofs_dev, num_ess);
+    sb_count_launch();
+    err = cudaGetLastError();
+  }
+  if (err == cudaSuccess) {
+    csr_eliminate_kernel<<<reducing_grid(v.num_rows, kWarpsPerCta), kThreads, 0, s>>>(v.row_ptr, v.col_ind, values_dev,
+                                                                                      values_e_dev, mark, v.num_rows);
+    sb_count_launch();
+    err = cudaGetLastError();
+  }
+  cudaFreeAsync(mark, s);
+  SB_CHECK_CUDA(err);
   return SB_OK;
 }
 
