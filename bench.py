@@ -591,12 +591,21 @@ def run_product(args):
         assert all(h.peer_status() == 0 for h in P["halos"]), "a wait for a neighbour timed out in the host-buffer steps"
     same_r, same_dr = np.array_equal(hr.numpy(), r.cpu().numpy()), np.array_equal(hdr.numpy(), dr.cpu().numpy())
     if not (same_r and same_dr):
-        dr_h, r_h = hdr.numpy(), hr.numpy()
+        # which path is off?  run each once more and say where the entries are
+        dr_h, r_h = hdr.numpy().copy(), hr.numpy().copy()
+        step_device()
+        torch.cuda.synchronize()
+        dev2_dr = (views["dr"] if inplace else dr).cpu().numpy().copy()
+        step_host()
+        torch.cuda.synchronize()
+        bad = np.nonzero(dr_h != dr.cpu().numpy())[0]
         raise AssertionError(
             f"rank {rank}: host-buffer path differs from the device path: r equal={same_r} (max |diff| "
             f"{np.abs(r_h - r.cpu().numpy()).max():.3e}, {int((r_h != r.cpu().numpy()).sum())} entries of {r_h.size}), "
-            f"dr equal={same_dr} (max |diff| {np.abs(dr_h - dr.cpu().numpy()).max():.3e}, "
-            f"{int((dr_h != dr.cpu().numpy()).sum())} entries)")
+            f"dr equal={same_dr} (max |diff| {np.abs(dr_h - dr.cpu().numpy()).max():.3e}, {len(bad)} entries, "
+            f"indices {bad[:4].tolist()}..{bad[-4:].tolist()}, tsize {r_h.size}); device path repeated == first device "
+            f"result: {np.array_equal(dev2_dr, dr.cpu().numpy())}; host path repeated == first host result: "
+            f"{np.array_equal(hdr.numpy(), dr_h)}; host repeated == device: {np.array_equal(hdr.numpy(), dr.cpu().numpy())}")
     assert np.isfinite(hr.numpy()).all() and np.abs(hdr.numpy()).max() > 0
 
     sums = torch.tensor([P["tdofs"], P["tdofs_shape"]], dtype=torch.float64, device=dev)

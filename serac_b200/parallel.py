@@ -359,3 +359,99 @@ class ParFunctional:
 def capi_torch():
     import torch
     return torch
+
+
+# ---- the Newton step's linear algebra at N ranks ----------------------------------------------------------------------
+class ParCsrOperator:
+    """The assembled Jacobian of a partitioned Functional as an operator on T-vectors.
+
+    The reference turns the rank-local matrix A_L into K = P^T A_L P with hypre's RAP (functional.hpp:654-662) and hands
+    K to hypre's solvers.  Without hypre the product is kept in its factors -- the *sub-assembled* form: every rank holds
+    the CSR matrix of its own elements over its L-dofs (what sb_functional_assemble writes, no communication), and
+
+        y_T = P^T ( A_L ( P x_T ) )
+
+    is the action of the same K: P and P^T are the shared-dof exchanges that already surround every Functional
+    evaluation.  diag(K) = P^T diag(A_L) gives the Jacobi preconditioner.  Essential dofs are eliminated rank-locally
+    (rows and columns of every local copy); the unit diagonal is kept on the owner's copy only, so that P^T adds up to
+    exactly 1 -- K is then [K_ii 0; 0 I] as eliminateAllEssentialDofsFromMatrix leaves it
+    (boundary_condition_manager.hpp:91-94)."""
+
+    def __init__(self, pattern, values, halo, ess_local=None):
+        """pattern / values: the local CSR triple (L x L); halo: HaloExchange of the space (separate T / L vectors);
+        ess_local: local L-dof ids of the essential dofs (every local copy, owned or not)"""
+        import torch
+        self.pat, self.vals, self.halo, self.torch = pattern, values, halo, torch
+        self._xL = self._yL = None
+        if ess_local is not None and len(ess_local):
+            ess_local = np.ascontiguousarray(ess_local, dtype=np.int32)
+            capi.eliminate_rows_cols(pattern, values, ess_local, want_Ae=False)
+            ltdof = np.asarray(halo.lists["ltdof"])
+            ghost = ess_local[ltdof[ess_local] < 0]  # copies owned by another rank: their diagonal must not add up
+            if len(ghost):
+                rp, ci = pattern.to_host()
+                at = np.array([rp[i] + np.searchsorted(ci[rp[i]:rp[i + 1]], i) for i in ghost], dtype=np.int64)
+                values[torch.as_tensor(at, device=values.device)] = 0.0
+
+    def Mult(self, x_T, out=None):
+        self._xL = self.halo.P(x_T, self._xL)
+        self._yL = capi.csr_spmv(self.pat, self.vals, self._xL, out=self._yL)
+        return self.halo.Pt(self._yL, out)
+
+    def diagonal(self):
+        """diag(P^T A_L P) as a T-vector"""
+        return self.halo.Pt(capi.csr_diagonal(self.pat, self.vals))
+
+
+def par_dot(x_T, y_T, group=None):
+    """(x, y) over the true dofs of all ranks: every true dof lives on exactly one rank"""
+    import torch
+    import torch.distributed as dist
+    d = torch.dot(x_T, y_T).reshape(1)
+    dist.all_reduce(d, op=dist.ReduceOp.SUM, group=group)
+    return float(d.item())
+
+
+def par_cg(A, b_T, dinv_T=None, rel_tol=1e-12, abs_tol=0.0, max_iter=1000, group=None):
+    """mfem::CGSolver (mfem/linalg/solvers.cpp:719-897) on T-vectors across the ranks: the same recurrences and stopping
+    test as the rank-local sb_cg_*, with every inner product reduced over the ranks.  A: object with Mult(x_T) -> y_T;
+    dinv_T: inverse diagonal (Jacobi) or None.  -> x_T, info"""
+    torch = capi_torch()
+    x = torch.zeros_like(b_T)
+    r = b_T.clone()
+    z = r * dinv_T if dinv_T is not None else r.clone()
+    d = z.clone()
+    nom0 = nom = par_dot(d, r, group)
+    info = dict(converged=False, final_iter=0, initial_norm=float(np.sqrt(max(nom0, 0.0))))
+    if nom < 0:
+        return x, info
+    r0 = max(nom * rel_tol * rel_tol, abs_tol * abs_tol)
+    if nom <= r0:
+        info.update(converged=True, final_norm=float(np.sqrt(nom)))
+        return x, info
+    z = A.Mult(d)
+    den = par_dot(z, d, group)
+    if den <= 0.0:
+        return x, info
+    i = 1
+    while True:
+        alpha = nom / den
+        x.add_(d, alpha=alpha)
+        r.add_(z, alpha=-alpha)
+        z = r * dinv_T if dinv_T is not None else r.clone()
+        betanom = par_dot(r, z, group)
+        if betanom <= r0:
+            info.update(converged=True, final_iter=i, final_norm=float(np.sqrt(max(betanom, 0.0))))
+            return x, info
+        if i + 1 > max_iter:
+            info.update(final_iter=i, final_norm=float(np.sqrt(max(betanom, 0.0))))
+            return x, info
+        i += 1
+        beta = betanom / nom
+        d.mul_(beta).add_(z)
+        z = A.Mult(d)
+        den = par_dot(d, z, group)
+        if den <= 0.0:
+            info.update(final_iter=i, final_norm=float(np.sqrt(max(betanom, 0.0))))
+            return x, info
+        nom = betanom

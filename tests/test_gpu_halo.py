@@ -176,3 +176,15 @@ def test_partitioned_functional_on_two_gpus_matches_global():
            "127.0.0.1", "--master-port", "29533", os.path.join(ROOT, "tools", "par_check.py")]
     out = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
     assert out.returncode == 0 and "par_check ok" in out.stdout, out.stdout[-2000:] + out.stderr[-2000:]
+
+
+def test_partitioned_newton_solve_on_two_gpus_matches_global():
+    """tools/par_newton_check.py: the Newton step's linear algebra at N ranks (Jacobian in sub-assembled form
+    y = P^T A_L P x, Jacobi from P^T diag(A_L), CG with rank-reduced inner products) against the single-GPU solve"""
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr",
+           "127.0.0.1", "--master-port", "29534", os.path.join(ROOT, "tools", "par_newton_check.py")]
+    out = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0 and "par_newton_check ok" in out.stdout, out.stdout[-2000:] + out.stderr[-2000:]
