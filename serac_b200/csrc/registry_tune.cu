@@ -31,13 +31,12 @@ long make_blob(const double* p, int n, void* out, size_t cap)
 #define TUNE_SET 0
 #endif
 #if TUNE_SET == 0
-TUNE(4, 1, 4)
-TUNE(2, 1, 8)
-TUNE(2, 1, 7)
-#elif TUNE_SET == 1
-TUNE(3, 1, 5)
-TUNE(3, 1, 6)
 TUNE(1, 1, 16)
+TUNE(1, 1, 20)
+TUNE(1, 1, 24)
+#elif TUNE_SET == 1
+TUNE(1, 1, 28)
+TUNE(1, 1, 32)
 #endif
 }  // namespace
 }  // namespace sb

@@ -357,6 +357,84 @@ struct TensorProduct<3, n, q, c> {
     }
     return owner;
   }
+  /// integrate() with the test space's tables behind an accessor (SmemTables / ParamTables), the columns a stage needs
+  /// hoisted into registers; same products in the same order, hence the same bits
+  template <bool HAS_SOURCE, bool HAS_FLUX, typename Tab>
+  static __device__ __forceinline__ bool integrate_t(const Tab& tab, double* s, int qx, int qy, int qz,
+                                                     const double (&src)[c], const double (&flux)[c][3], double (&out)[c])
+  {
+    double* S  = s;                        // [4][c][q][q][q]
+    double* P  = S + 4 * c * q * q * q;    // [3][c][n][q][q]
+    double* Qs = P + 3 * c * n * q * q;    // [2][c][n][n][q]
+    SB_UNROLL
+    for (int a = 0; a < c; a++) {
+      if (HAS_SOURCE) S[(((0 * c + a) * q + qz) * q + qy) * q + qx] = src[a];
+      if (HAS_FLUX) {
+        S[(((1 * c + a) * q + qz) * q + qy) * q + qx] = flux[a][0];
+        S[(((2 * c + a) * q + qz) * q + qy) * q + qx] = flux[a][1];
+        S[(((3 * c + a) * q + qz) * q + qy) * q + qx] = flux[a][2];
+      }
+    }
+    __syncthreads();
+    if (qz < n) {  // dz = qz
+      double bz[q], gz[q];
+      tab.template col<n, q>(qz, bz, gz);
+      SB_UNROLL
+      for (int a = 0; a < c; a++) {
+        double p0 = 0.0, p1 = 0.0, p2 = 0.0;
+        SB_UNROLL
+        for (int k = 0; k < q; k++) {
+          if (HAS_SOURCE) p0 += bz[k] * S[(((0 * c + a) * q + k) * q + qy) * q + qx];
+          if (HAS_FLUX) {
+            p0 += gz[k] * S[(((3 * c + a) * q + k) * q + qy) * q + qx];
+            p1 += bz[k] * S[(((1 * c + a) * q + k) * q + qy) * q + qx];
+            p2 += bz[k] * S[(((2 * c + a) * q + k) * q + qy) * q + qx];
+          }
+        }
+        P[(((0 * c + a) * n + qz) * q + qy) * q + qx] = p0;
+        if (HAS_FLUX) {
+          P[(((1 * c + a) * n + qz) * q + qy) * q + qx] = p1;
+          P[(((2 * c + a) * n + qz) * q + qy) * q + qx] = p2;
+        }
+      }
+    }
+    __syncthreads();
+    if (qz < n && qy < n) {  // dz = qz, dy = qy
+      double by[q], gy[q];
+      tab.template col<n, q>(qy, by, gy);
+      SB_UNROLL
+      for (int a = 0; a < c; a++) {
+        double q0 = 0.0, q1 = 0.0;
+        SB_UNROLL
+        for (int k = 0; k < q; k++) {
+          q0 += by[k] * P[(((0 * c + a) * n + qz) * q + k) * q + qx];
+          if (HAS_FLUX) {
+            q0 += gy[k] * P[(((2 * c + a) * n + qz) * q + k) * q + qx];
+            q1 += by[k] * P[(((1 * c + a) * n + qz) * q + k) * q + qx];
+          }
+        }
+        Qs[(((0 * c + a) * n + qz) * n + qy) * q + qx] = q0;
+        if (HAS_FLUX) Qs[(((1 * c + a) * n + qz) * n + qy) * q + qx] = q1;
+      }
+    }
+    __syncthreads();
+    const bool owner = (qz < n && qy < n && qx < n);
+    if (owner) {
+      double bx[q], gx[q];
+      tab.template col<n, q>(qx, bx, gx);
+      SB_UNROLL
+      for (int a = 0; a < c; a++) {
+        double r = 0.0;
+        SB_UNROLL
+        for (int k = 0; k < q; k++) {
+          r += bx[k] * Qs[(((0 * c + a) * n + qz) * n + qy) * q + k];
+          if (HAS_FLUX) r += gx[k] * Qs[(((1 * c + a) * n + qz) * n + qy) * q + k];
+        }
+        out[a] = r;
+      }
+    }
+    return owner;
+  }
 };
 
 template <int n, int q, int c>
@@ -661,7 +739,10 @@ struct EvalLayout {
     for (int j = 0; j < i; j++) o += simplex_tab_size(j);
     return o;
   }
-  static constexpr int tables = Sig::simplex ? simplex_tab_off(NT + 1) + QPE : (NT + 1) * 2 * MAX_Q * MAX_Q;
+  /// hexahedra: the 1-D tables stay in the kernel's parameter space (ParamTables), no copy in shared memory
+  static constexpr bool param_tables = (dim == 3) && !Sig::simplex;
+  static constexpr int  tables =
+      Sig::simplex ? simplex_tab_off(NT + 1) + QPE : (param_tables ? 0 : (NT + 1) * 2 * MAX_Q * MAX_Q);
   static constexpr int gather_size(int i) { return EPB * Sig::trial_c(i) * ndof(i); }
   static constexpr int gather_off(int i)
   {
@@ -706,18 +787,78 @@ constexpr int eval_smem_doubles()
 template <int dim, int n, int q, int c>
 struct InterpStages;
 
+/// where a kernel finds the 1-D tables: copied into shared memory ...
+struct SmemTables {
+  const double* B;
+  const double* G;
+  /// row r of B and G: the n nodal functions (and derivatives) at quadrature point r
+  template <int n, int q>
+  __device__ __forceinline__ void row(int r, double (&b)[n], double (&g)[n]) const
+  {
+    SB_UNROLL
+    for (int d = 0; d < n; d++) {
+      b[d] = B[r * n + d];
+      g[d] = G[r * n + d];
+    }
+  }
+  /// column d of B and G: nodal function d at the q quadrature points
+  template <int n, int q>
+  __device__ __forceinline__ void col(int d, double (&b)[q], double (&g)[q]) const
+  {
+    SB_UNROLL
+    for (int k = 0; k < q; k++) {
+      b[k] = B[k * n + d];
+      g[k] = G[k * n + d];
+    }
+  }
+};
+/// ... or left in the kernel's parameter space (constant bank): a thread picks its row with a chain of selects over
+/// compile-time offsets.  No shared-memory traffic: in the hexahedron evaluation kernel 28% of all shared-memory loads
+/// were table reads, and the L1 data pipe is that kernel's limiter (profiles/r2q_eval_l1_pipe.txt).
+struct ParamTables {
+  const BasisTable1D& t;
+  template <int n, int q>
+  __device__ __forceinline__ void row(int r, double (&b)[n], double (&g)[n]) const
+  {
+    SB_UNROLL
+    for (int d = 0; d < n; d++) {
+      double vb = t.B[d], vg = t.G[d];
+      SB_UNROLL
+      for (int k = 1; k < q; k++) {
+        vb = (r == k) ? t.B[k * n + d] : vb;
+        vg = (r == k) ? t.G[k * n + d] : vg;
+      }
+      b[d] = vb;
+      g[d] = vg;
+    }
+  }
+  template <int n, int q>
+  __device__ __forceinline__ void col(int d, double (&b)[q], double (&g)[q]) const
+  {
+    SB_UNROLL
+    for (int k = 0; k < q; k++) {
+      double vb = t.B[k * n], vg = t.G[k * n];
+      SB_UNROLL
+      for (int j = 1; j < n; j++) {
+        vb = (d == j) ? t.B[k * n + j] : vb;
+        vg = (d == j) ? t.G[k * n + j] : vg;
+      }
+      b[k] = vb;
+      g[k] = vg;
+    }
+  }
+};
+
+/// NV / NG: does anybody read the interpolated value / gradient?  (qf_usage, physics_functors.hpp)
 template <int n, int q, int c>
 struct InterpStages<3, n, q, c> {
-  static __device__ __forceinline__ void s1(const double* __restrict__ B, const double* __restrict__ G,
-                                            const double* __restrict__ u, double* __restrict__ A1, int qx, int qy, int qz)
+  template <bool NV = true, bool NG = true, typename Tab>
+  static __device__ __forceinline__ void s1(const Tab& tab, const double* __restrict__ u, double* __restrict__ A1, int qx,
+                                            int qy, int qz)
   {
     if (qz < n && qy < n) {
       double b[n], g[n];
-      SB_UNROLL
-      for (int d = 0; d < n; d++) {
-        b[d] = B[qx * n + d];
-        g[d] = G[qx * n + d];
-      }
+      tab.template row<n, q>(qx, b, g);
       SB_UNROLL
       for (int a = 0; a < c; a++) {
         double sB = 0.0, sG = 0.0;
@@ -725,62 +866,61 @@ struct InterpStages<3, n, q, c> {
         for (int dx = 0; dx < n; dx++) {
           const double uu = u[((a * n + qz) * n + qy) * n + dx];
           sB += b[dx] * uu;
-          sG += g[dx] * uu;
+          if constexpr (NG) sG += g[dx] * uu;
         }
         A1[(((0 * c + a) * n + qz) * n + qy) * q + qx] = sB;
-        A1[(((1 * c + a) * n + qz) * n + qy) * q + qx] = sG;
+        if constexpr (NG) A1[(((1 * c + a) * n + qz) * n + qy) * q + qx] = sG;
       }
     }
   }
-  static __device__ __forceinline__ void s2(const double* __restrict__ B, const double* __restrict__ G,
-                                            const double* __restrict__ A1, double* __restrict__ A2, int qx, int qy, int qz)
+  template <bool NV = true, bool NG = true, typename Tab>
+  static __device__ __forceinline__ void s2(const Tab& tab, const double* __restrict__ A1, double* __restrict__ A2, int qx,
+                                            int qy, int qz)
   {
     if (qz < n) {
       double b[n], g[n];
-      SB_UNROLL
-      for (int d = 0; d < n; d++) {
-        b[d] = B[qy * n + d];
-        g[d] = G[qy * n + d];
-      }
+      tab.template row<n, q>(qy, b, g);
       SB_UNROLL
       for (int a = 0; a < c; a++) {
         double sBB = 0.0, sGB = 0.0, sBG = 0.0;
         SB_UNROLL
         for (int dy = 0; dy < n; dy++) {
           const double vb = A1[(((0 * c + a) * n + qz) * n + dy) * q + qx];
-          const double vg = A1[(((1 * c + a) * n + qz) * n + dy) * q + qx];
           sBB += b[dy] * vb;
-          sGB += b[dy] * vg;
-          sBG += g[dy] * vb;
+          if constexpr (NG) {
+            const double vg = A1[(((1 * c + a) * n + qz) * n + dy) * q + qx];
+            sGB += b[dy] * vg;
+            sBG += g[dy] * vb;
+          }
         }
         A2[(((0 * c + a) * n + qz) * q + qy) * q + qx] = sBB;
-        A2[(((1 * c + a) * n + qz) * q + qy) * q + qx] = sGB;
-        A2[(((2 * c + a) * n + qz) * q + qy) * q + qx] = sBG;
+        if constexpr (NG) {
+          A2[(((1 * c + a) * n + qz) * q + qy) * q + qx] = sGB;
+          A2[(((2 * c + a) * n + qz) * q + qy) * q + qx] = sBG;
+        }
       }
     }
   }
-  static __device__ __forceinline__ void s3(const double* __restrict__ B, const double* __restrict__ G,
-                                            const double* __restrict__ A2, int qx, int qy, int qz, double (&val)[c],
-                                            double (&grad)[c][3])
+  template <bool NV = true, bool NG = true, typename Tab>
+  static __device__ __forceinline__ void s3(const Tab& tab, const double* __restrict__ A2, int qx, int qy, int qz,
+                                            double (&val)[c], double (&grad)[c][3])
   {
     double b[n], g[n];
-    SB_UNROLL
-    for (int d = 0; d < n; d++) {
-      b[d] = B[qz * n + d];
-      g[d] = G[qz * n + d];
-    }
+    tab.template row<n, q>(qz, b, g);
     SB_UNROLL
     for (int a = 0; a < c; a++) {
       double v = 0.0, gx = 0.0, gy = 0.0, gz = 0.0;
       SB_UNROLL
       for (int dz = 0; dz < n; dz++) {
         const double bb = A2[(((0 * c + a) * n + dz) * q + qy) * q + qx];
-        const double gb = A2[(((1 * c + a) * n + dz) * q + qy) * q + qx];
-        const double bg = A2[(((2 * c + a) * n + dz) * q + qy) * q + qx];
-        v += b[dz] * bb;
-        gx += b[dz] * gb;
-        gy += b[dz] * bg;
-        gz += g[dz] * bb;
+        if constexpr (NV) v += b[dz] * bb;
+        if constexpr (NG) {
+          const double gb = A2[(((1 * c + a) * n + dz) * q + qy) * q + qx];
+          const double bg = A2[(((2 * c + a) * n + dz) * q + qy) * q + qx];
+          gx += b[dz] * gb;
+          gy += b[dz] * bg;
+          gz += g[dz] * bb;
+        }
       }
       val[a]     = v;
       grad[a][0] = gx;
@@ -1096,7 +1236,7 @@ __global__ void __launch_bounds__(EvalLayout<Sig>::threads, MINB) evaluation_ker
       (copy(std::integral_constant<int, I>{}), ...);
     }
     (std::make_integer_sequence<int, NT + 1>{});
-  } else {
+  } else if constexpr (!LAY::param_tables) {
     for (int i = threadIdx.x; i < LAY::tables; i += LAY::threads) {
       const int           which = i / (2 * MAX_Q * MAX_Q);
       const int           rem   = i - which * (2 * MAX_Q * MAX_Q);
@@ -1245,25 +1385,29 @@ __global__ void __launch_bounds__(EvalLayout<Sig>::threads, MINB) evaluation_ker
       };
       (dense(std::integral_constant<int, I>{}), ...);
     } else if constexpr (dim == 3) {
+      // tables straight from the kernel parameters; values / gradients the q-function never reads are not computed
       auto s1 = [&](auto idx) {
         constexpr int J = decltype(idx)::value;
-        constexpr int n = Sig::trial_n(J), c = Sig::trial_c(J);
+        constexpr int n = Sig::trial_n(J), c = Sig::trial_c(J), use = qf_usage<QF>::argument(J);
         using ST        = InterpStages<3, n, q, c>;
-        ST::s1(B_of(idx), G_of(idx), u_of(idx), w_of(idx), qx, qy, qz);
+        ST::template s1<(use & USES_VALUE) != 0, (use & USES_GRADIENT) != 0>(ParamTables{P.trial_basis[J]}, u_of(idx),
+                                                                             w_of(idx), qx, qy, qz);
       };
       auto s2 = [&](auto idx) {
         constexpr int J = decltype(idx)::value;
-        constexpr int n = Sig::trial_n(J), c = Sig::trial_c(J);
+        constexpr int n = Sig::trial_n(J), c = Sig::trial_c(J), use = qf_usage<QF>::argument(J);
         using ST        = InterpStages<3, n, q, c>;
-        ST::s2(B_of(idx), G_of(idx), w_of(idx), w_of(idx) + 2 * c * n * n * q, qx, qy, qz);
+        ST::template s2<(use & USES_VALUE) != 0, (use & USES_GRADIENT) != 0>(
+            ParamTables{P.trial_basis[J]}, w_of(idx), w_of(idx) + 2 * c * n * n * q, qx, qy, qz);
       };
       auto s3 = [&](auto idx) {
         constexpr int J = decltype(idx)::value;
-        constexpr int n = Sig::trial_n(J), c = Sig::trial_c(J);
+        constexpr int n = Sig::trial_n(J), c = Sig::trial_c(J), use = qf_usage<QF>::argument(J);
         using ST        = InterpStages<3, n, q, c>;
         double val[c];
         double grad[c][3];
-        ST::s3(B_of(idx), G_of(idx), w_of(idx) + 2 * c * n * n * q, qx, qy, qz, val, grad);
+        ST::template s3<(use & USES_VALUE) != 0, (use & USES_GRADIENT) != 0>(
+            ParamTables{P.trial_basis[J]}, w_of(idx) + 2 * c * n * n * q, qx, qy, qz, val, grad);
         finish(idx, val, grad);
       };
       (s1(std::integral_constant<int, I>{}), ...);
@@ -1515,10 +1659,15 @@ __global__ void __launch_bounds__(EvalLayout<Sig>::threads, MINB) evaluation_ker
       owner = SimplexOps<dim, Sig::test_ndof, QPE, ct>::template integrate<has_source, has_flux>(
           tables + LAY::simplex_tab_off(NT), scratch + el * per, ql, src, flux, out);
     } else {
-      using TP        = TensorProduct<dim, Sig::test_n, q, ct>;
-      const double* B = tables + (NT * 2 + 0) * MAX_Q * MAX_Q;
-      const double* G = tables + (NT * 2 + 1) * MAX_Q * MAX_Q;
-      owner = TP::template integrate<has_source, has_flux>(B, G, scratch + el * per, qx, qy, qz, src, flux, out);
+      using TP = TensorProduct<dim, Sig::test_n, q, ct>;
+      if constexpr (LAY::param_tables) {
+        owner = TP::template integrate_t<has_source, has_flux>(ParamTables{P.test_basis}, scratch + el * per, qx, qy, qz,
+                                                               src, flux, out);
+      } else {
+        const double* B = tables + (NT * 2 + 0) * MAX_Q * MAX_Q;
+        const double* G = tables + (NT * 2 + 1) * MAX_Q * MAX_Q;
+        owner = TP::template integrate<has_source, has_flux>(B, G, scratch + el * per, qx, qy, qz, src, flux, out);
+      }
     }
     if (owner && valid) {
       constexpr int n    = Sig::test_n;

@@ -55,6 +55,22 @@ template <typename M>
 struct has_closed_form_tangent<M, std::void_t<decltype(M::closed_form_tangent)>> : std::bool_constant<M::closed_form_tangent> {
 };
 
+/// Which parts of its arguments does a q-function read?  (extension; lets the evaluation kernel skip the interpolation of
+/// values / gradients nobody looks at -- e.g. the gradient of the acceleration in SolidMechanics' integrand.)
+/// A q-function may declare `static constexpr int argument_usage(int i)` (bit 0: value, bit 1: gradient of trial argument
+/// i) and `static constexpr bool uses_position`; anything undeclared counts as used.
+constexpr int USES_VALUE = 1, USES_GRADIENT = 2;
+template <typename QF, typename = void>
+struct qf_usage {
+  static constexpr int  argument(int) { return USES_VALUE | USES_GRADIENT; }
+  static constexpr bool position = true;
+};
+template <typename QF>
+struct qf_usage<QF, std::void_t<decltype(QF::argument_usage(0))>> {
+  static constexpr int  argument(int i) { return QF::argument_usage(i); }
+  static constexpr bool position = QF::uses_position;
+};
+
 /// does q-function QF provide flux_tangent(integral_constant<WRT>, ...) for its argument WRT ?
 template <typename QF, int WRT, typename = void>
 struct provides_flux_tangent : std::false_type {
@@ -500,6 +516,10 @@ struct MaterialStressFunctor {
     return variant<V>(material_, geom_nonlin_);
   }
 
+  /// operator() reads the displacement gradient, the acceleration value and nothing of the position
+  static constexpr int  argument_usage(int i) { return i == 0 ? USES_GRADIENT : i == 1 ? USES_VALUE : (USES_VALUE | USES_GRADIENT); }
+  static constexpr bool uses_position = false;
+
   SERAC_HOST_DEVICE bool nonlinear() const
   {
     if constexpr (MODE == FlagMode::StaticOn) return true;
@@ -731,6 +751,12 @@ template <typename Integrand, int dim, typename test_space, typename... trial_sp
 struct ShapeAwareIntegrandWrapper {
   SERAC_HOST_DEVICE ShapeAwareIntegrandWrapper(Integrand integrand) : integrand_(integrand) {}
   Integrand integrand_;
+  /// the shape displacement's gradient is always read, its value only moves the position handed to the integrand
+  static constexpr int argument_usage(int i)
+  {
+    return i == 0 ? (USES_GRADIENT | (qf_usage<Integrand>::position ? USES_VALUE : 0)) : qf_usage<Integrand>::argument(i - 1);
+  }
+  static constexpr bool uses_position = qf_usage<Integrand>::position;
 
   template <typename PositionType, typename ShapeValueType, typename... QFuncArgs>
   SERAC_HOST_DEVICE auto operator()(double time, PositionType x, ShapeValueType shape_val,
@@ -750,6 +776,11 @@ template <typename Integrand, int dim, typename test_space, typename... trial_sp
 struct ShapeAwareIntegrandWrapperWithState {
   SERAC_HOST_DEVICE ShapeAwareIntegrandWrapperWithState(Integrand integrand) : integrand_(integrand) {}
   Integrand integrand_;
+  static constexpr int argument_usage(int i)
+  {
+    return i == 0 ? (USES_GRADIENT | (qf_usage<Integrand>::position ? USES_VALUE : 0)) : qf_usage<Integrand>::argument(i - 1);
+  }
+  static constexpr bool uses_position = qf_usage<Integrand>::position;
 
   template <typename PositionType, typename StateType, typename ShapeValueType, typename... QFuncArgs>
   SERAC_HOST_DEVICE auto operator()(double time, PositionType x, StateType& state, ShapeValueType shape_val,
