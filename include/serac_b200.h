@@ -187,7 +187,7 @@ typedef struct {
   int    trial_order[SB_MAX_TRIALS], trial_components[SB_MAX_TRIALS];
   size_t qf_bytes;    /* sizeof the q-function functor (copied by value into the kernel parameters) */
   size_t state_bytes; /* sizeof the quadrature-point state; 0 = no state */
-  int    elements_per_block; /* derivative tiles hold this many elements */
+  int    elements_per_block; /* elements per CTA of the streaming kernels; derivative buffers are padded to a multiple */
   sb_eval_launcher      evaluate;                        /* no differentiation */
   sb_eval_launcher      evaluate_ad[SB_MAX_TRIALS];      /* + derivative store w.r.t. trial i */
   sb_jvp_launcher       jvp[SB_MAX_TRIALS];
@@ -200,6 +200,9 @@ typedef struct {
   sb_assemble_rows_launcher assemble_rows[SB_MAX_TRIALS];
   int assemble_rows_fixed_doubles[SB_MAX_TRIALS]; /* shared memory the kernel needs besides the accumulator */
   int assemble_rows_trial_blocks[SB_MAX_TRIALS];  /* blocks the trial components are cut into (one item per block) */
+  /* stored derivatives are laid out [tile][entry][derivative_tile_elements x quadrature points]: 1 for hexahedra with
+   * q >= 3 (every element its own tile), elements_per_block otherwise (sb_integral_export_derivatives converts back) */
+  int derivative_tile_elements;
 } sb_kernel_table;
 
 int         sb_named_integrand_count(void);

@@ -33,7 +33,7 @@ class KernelTable(C.Structure):
         ("element_gradient", _vp * MAX_TRIALS),
         ("derivative_mask", _i * MAX_TRIALS), ("derivative_entries", _i * MAX_TRIALS), ("spatial_dim", _i),
         ("assemble_rows", _vp * MAX_TRIALS), ("assemble_rows_fixed_doubles", _i * MAX_TRIALS),
-        ("assemble_rows_trial_blocks", _i * MAX_TRIALS),
+        ("assemble_rows_trial_blocks", _i * MAX_TRIALS), ("derivative_tile_elements", _i),
     ]
 
 

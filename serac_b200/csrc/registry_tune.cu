@@ -30,13 +30,16 @@ long make_blob(const double* p, int n, void* out, size_t cap)
 #ifndef TUNE_SET
 #define TUNE_SET 0
 #endif
+// EPB >= 1000: experiment switches in the thousands (SignatureT::tune): 1 = streaming stores of the derivatives,
+// 2 = streaming loads of X_q / J_q
 #if TUNE_SET == 0
-TUNE(1, 1, 16)
-TUNE(1, 1, 20)
-TUNE(1, 1, 24)
+TUNE(4, 1, 16)
+TUNE(1004, 1, 16)
+TUNE(2004, 1, 16)
 #elif TUNE_SET == 1
-TUNE(1, 1, 28)
-TUNE(1, 1, 32)
+TUNE(3004, 1, 16)
+TUNE(1, 1, 16)
+TUNE(1001, 1, 16)
 #endif
 }  // namespace
 }  // namespace sb

@@ -73,7 +73,8 @@ template <int q, int nk, int ck, int nt, int ct, int MASK, int EPB>
 struct AssembleRowsConfig {
   static constexpr int  dim = 3;
   static constexpr int  QPE = q * q * q, QQ = q * q;
-  static constexpr int  TILE = EPB * QPE;
+  static constexpr int  TE   = dq_tile_elements(false, QPE, EPB);  ///< elements per stored-derivative tile
+  static constexpr int  TILE = TE * QPE;
   static constexpr int  CPW  = (32 / QQ < ck) ? 32 / QQ : ck;  ///< trial components a warp handles at once
   static constexpr int  NB   = (ck + CPW - 1) / CPW;           ///< trial blocks
   static constexpr int  active  = CPW * QQ;                    ///< working lanes of a warp
@@ -160,8 +161,8 @@ __global__ void __launch_bounds__(AssembleRowsConfig<q, nk, ck, nt, ct, MASK, EP
   auto load_D = [&](double (&dst)[q][C::NE > 0 ? C::NE : 1], int p, int bg) {
     const int b = bg * C::CPW + cl;
     if (cl < C::CPW && b < ck) {
-      const long long tile = p / EPB;
-      const int       ln   = (p - int(tile) * EPB) * C::QPE + qy0 * q + qx0;
+      const long long tile = p / C::TE;
+      const int       ln   = (p - int(tile) * C::TE) * C::QPE + qy0 * q + qx0;
       const double*   dq   = P.dqf + tile * (long long)LY.entries * C::TILE + ln;
       SB_UNROLL
       for (int qz = 0; qz < q; qz++) {
@@ -188,8 +189,8 @@ __global__ void __launch_bounds__(AssembleRowsConfig<q, nk, ck, nt, ct, MASK, EP
   };
   // the rows of test component a of element p's derivative into L2: LY.entries / ct runs of QPE doubles
   auto prefetch_element = [&](int p) {
-    const long long tile = p / EPB;
-    const double*   nq   = P.dqf + tile * (long long)LY.entries * C::TILE + (p - int(tile) * EPB) * C::QPE;
+    const long long tile = p / C::TE;
+    const double*   nq   = P.dqf + tile * (long long)LY.entries * C::TILE + (p - int(tile) * C::TE) * C::QPE;
     constexpr int   per_a = LY.entries / ct;  // entries are a-major inside every block; a few lines too many do no harm
     for (int e = lane; e < LY.entries; e += 32) {
       if (ct > 1 && LY.entries % ct == 0 && !(C::d00 || C::d01 || C::d10) && e / per_a != a) continue;

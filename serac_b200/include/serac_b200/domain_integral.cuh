@@ -47,6 +47,12 @@ SB_HD int elements_per_block(Geometry g, int q)
   return epb > 32 ? 32 : (epb < 1 ? 1 : epb);
 }
 
+/// Stored-derivative layout: [tile][entry][tile elements x QPE lanes].  Elements with a warp's worth of quadrature points
+/// (hexahedra with q >= 3) are their own tile, i.e. [element][entry][QPE]: the evaluation kernel's consecutive stores then
+/// fall on consecutive addresses (config A: 159 -> 150 us), and any kernel may stream any number of elements per CTA.
+/// Smaller elements keep EPB elements per tile so that a warp's access to one entry stays one contiguous run.
+SB_HD int dq_tile_elements(bool simplex, int qpe, int epb) { return (!simplex && qpe >= 27) ? 1 : epb; }
+
 /// one trial / test field as the kernels see it
 struct FieldArg {
   const double* L;            ///< L-vector (device)
@@ -619,8 +625,10 @@ struct SignatureT {
   static constexpr int      NT       = int(sizeof...(trials));
   static constexpr int      QPE      = num_quadrature_points(geom, Q);  ///< quadrature points per element
   static constexpr bool     simplex  = is_simplex(geom);
-  static constexpr int      EPB      = (EPB_ > 0) ? EPB_ : elements_per_block(geom, Q);
+  static constexpr int      EPB      = (EPB_ % 1000 > 0) ? EPB_ % 1000 : elements_per_block(geom, Q);
+  static constexpr int      tune     = EPB_ / 1000;  ///< experiment switches of registry_tune.cu (0 in every product table)
   static constexpr int      threads  = EPB * QPE;
+  static constexpr int      DQ_TE    = dq_tile_elements(simplex, QPE, EPB);  ///< elements per stored-derivative tile
   using test_space                   = test;
   template <int i>
   using trial_space = typename serac::detail::type_at<i, trials...>::type;
@@ -728,7 +736,7 @@ struct EvalLayout {
   static constexpr int dim = Sig::dim, q = Sig::q, NT = Sig::NT, EPB = eval_cta_elements<Sig>();
   static constexpr int CE      = EPB;                ///< elements per CTA
   static constexpr int threads = CE * Sig::QPE;      ///< threads per CTA
-  static constexpr int TILE    = Sig::EPB * Sig::QPE;  ///< lanes of a stored-derivative tile
+  static constexpr int TILE    = Sig::DQ_TE * Sig::QPE;  ///< lanes of a stored-derivative tile
   static constexpr int QPE = Sig::QPE;
   static constexpr int ndof(int i) { return Sig::trial_ndof(i); }
   /// simplex: offset of space i's {phi, dphi} table (i == NT: test space); the nq weights follow the last table
@@ -1276,9 +1284,15 @@ __global__ void __launch_bounds__(EvalLayout<Sig>::threads, MINB) evaluation_ker
   tensor<double, sdim, dim> Jm{};
   SB_UNROLL
   for (int i = 0; i < sdim; i++) {
+    if constexpr (Sig::tune & 2) {
+      x[i] = __ldcs(&P.X_q[((long long)e * sdim + i) * QPE + ql]);
+      SB_UNROLL
+      for (int j = 0; j < dim; j++) Jm(i, j) = __ldcs(&P.J_q[(((long long)e * dim + j) * sdim + i) * QPE + ql]);
+    } else {
     x[i] = P.X_q[((long long)e * sdim + i) * QPE + ql];
     SB_UNROLL
     for (int j = 0; j < dim; j++) Jm(i, j) = P.J_q[(((long long)e * dim + j) * sdim + i) * QPE + ql];
+    }
   }
 
   // --- L -> E gather of every trial field at once (element_restriction.cpp:443-454): all loads are issued before the
@@ -1512,8 +1526,8 @@ __global__ void __launch_bounds__(EvalLayout<Sig>::threads, MINB) evaluation_ker
     constexpr DerivativeLayout LY = DT::layout();
     constexpr int              ck = DT::ck;
     // derivative tile of this element and this quadrature point's lane in it
-    const long long tile = e_raw / Sig::EPB;
-    const int       lane = int(e_raw - tile * Sig::EPB) * QPE + ql;
+    const long long tile = e_raw / Sig::DQ_TE;
+    const int       lane = int(e_raw - tile * Sig::DQ_TE) * QPE + ql;
     double*         dq   = P.dqf + tile * (long long)LY.entries * LAY::TILE + lane;
     bool    first = true;
 
@@ -1524,7 +1538,11 @@ __global__ void __launch_bounds__(EvalLayout<Sig>::threads, MINB) evaluation_ker
       tensor<double, ct>      s_p{};
       tensor<double, ct, dim> f_p{};
       auto sink = [&](int a, int k, int b, int l, double v) {
-        if (valid) dq[(long long)(((a * dim + k) * ck + b) * dim + l) * LAY::TILE] = v;
+        if constexpr (Sig::tune & 1) {
+          if (valid) __stcs(&dq[(long long)(((a * dim + k) * ck + b) * dim + l) * LAY::TILE], v);
+        } else {
+          if (valid) dq[(long long)(((a * dim + k) * ck + b) * dim + l) * LAY::TILE] = v;
+        }
       };
       [&]<int... I>(std::integer_sequence<int, I...>)
       {
@@ -1689,6 +1707,8 @@ struct JvpConfig {
   static constexpr int  QPE     = ipow(q, dim);
   static constexpr int  EPB     = (EPB_ > 0) ? EPB_ : elements_per_block(dim, q);
   static constexpr int  threads = EPB * QPE;
+  static constexpr int  DQ_TE     = dq_tile_elements(false, QPE, EPB);  ///< elements per stored-derivative tile
+  static constexpr int  DQ_STRIDE = DQ_TE * QPE;                          ///< lanes per tile = distance between entries
   static constexpr bool d00 = (MASK & 1) != 0, d01 = (MASK & 2) != 0, d10 = (MASK & 4) != 0, d11 = (MASK & 8) != 0;
   using TPk = TensorProduct<dim, nk, q, ck>;
   using TPt = TensorProduct<dim, nt, q, ct>;
@@ -1725,7 +1745,8 @@ __global__ void __launch_bounds__(JvpConfig<dim, q, nk, ck, nt, ct, MASK, EPB_>:
   const int  elem  = P.elements ? P.elements[e] : e;
 
   // issue the derivative loads early: they are independent of the interpolation
-  const double* dq = P.dqf + (long long)blockIdx.x * LY.entries * C::threads + threadIdx.x;
+  const double* dq = (C::DQ_TE == 1) ? P.dqf + ((long long)blockIdx.x * EPB + el) * LY.entries * QPE + ql
+                                     : P.dqf + (long long)blockIdx.x * LY.entries * C::threads + threadIdx.x;
 
   // gather du
   const FieldArg& f = P.trial;
@@ -1754,7 +1775,7 @@ __global__ void __launch_bounds__(JvpConfig<dim, q, nk, ck, nt, ct, MASK, EPB_>:
   constexpr bool has_flux   = C::d10 || C::d11;
   double         src[ct];
   double         flux[ct][dim];
-  const long long stride = C::threads;
+  const long long stride = C::DQ_STRIDE;
   SB_UNROLL
   for (int a = 0; a < ct; a++) {
     double s = 0.0;
@@ -1810,6 +1831,8 @@ struct ElemGradConfig {
   static constexpr int  QPE     = ipow(q, dim);
   static constexpr int  EPB     = (EPB_ > 0) ? EPB_ : elements_per_block(dim, q);
   static constexpr int  threads = EPB * QPE;
+  static constexpr int  DQ_TE     = dq_tile_elements(false, QPE, EPB);  ///< elements per stored-derivative tile
+  static constexpr int  DQ_STRIDE = DQ_TE * QPE;                          ///< lanes per tile = distance between entries
   static constexpr bool d00 = (MASK & 1) != 0, d01 = (MASK & 2) != 0, d10 = (MASK & 4) != 0, d11 = (MASK & 8) != 0;
   using TPt = TensorProduct<dim, nt, q, ct * ck>;
   static constexpr int ndof_k = ipow(nk, dim);
@@ -1859,8 +1882,9 @@ __global__ void __launch_bounds__(ElemGradConfig<dim, q, nk, ck, nt, ct, MASK, E
   if (dim == 3) w *= tb.w[qz];
 
   // this quadrature point's derivative blocks, pre-multiplied by the quadrature weight
-  const double*   dq     = P.dqf + (long long)blockIdx.x * LY.entries * C::threads + threadIdx.x;
-  const long long stride = C::threads;
+  const double*   dq     = (C::DQ_TE == 1) ? P.dqf + ((long long)blockIdx.x * EPB + el) * LY.entries * QPE + ql
+                                           : P.dqf + (long long)blockIdx.x * LY.entries * C::threads + threadIdx.x;
+  const long long stride = C::DQ_STRIDE;
   double          D[LY.entries > 0 ? LY.entries : 1];
   SB_UNROLL
   for (int i = 0; i < LY.entries; i++) D[i] = dq[i * stride] * w;

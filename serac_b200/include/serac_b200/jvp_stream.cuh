@@ -437,7 +437,9 @@ __global__ void __launch_bounds__(JvpStreamConfig<dim, q, nk, ck, nt, ct, MASK, 
     tma::mbar_wait(bar, parity);
     parity ^= 1u;
 
-    const double* dq = tile_s + tid;
+    // lanes of one entry: the CTA's threads ([entry][threads] tiles) or this element's points ([element][entry][QPE])
+    constexpr int DQS = B::DQ_STRIDE;
+    const double* dq  = (B::DQ_TE == 1) ? tile_s + el * (LY.entries * C::QPE) + ql : tile_s + tid;
     double        src[ct];
     double        flux[ct][dim];
     SB_UNROLL
@@ -445,13 +447,13 @@ __global__ void __launch_bounds__(JvpStreamConfig<dim, q, nk, ck, nt, ct, MASK, 
       double s = 0.0;
       if constexpr (B::d00) {
         SB_UNROLL
-        for (int b = 0; b < ck; b++) s += dq[(LY.offset[0] + a * ck + b) * T] * v[b];
+        for (int b = 0; b < ck; b++) s += dq[(LY.offset[0] + a * ck + b) * DQS] * v[b];
       }
       if constexpr (B::d01) {
         SB_UNROLL
         for (int b = 0; b < ck; b++) {
           SB_UNROLL
-          for (int l = 0; l < dim; l++) s += dq[(LY.offset[1] + (a * ck + b) * dim + l) * T] * g[b][l];
+          for (int l = 0; l < dim; l++) s += dq[(LY.offset[1] + (a * ck + b) * dim + l) * DQS] * g[b][l];
         }
       }
       src[a] = s * w;
@@ -460,13 +462,13 @@ __global__ void __launch_bounds__(JvpStreamConfig<dim, q, nk, ck, nt, ct, MASK, 
         double fl = 0.0;
         if constexpr (B::d10) {
           SB_UNROLL
-          for (int b = 0; b < ck; b++) fl += dq[(LY.offset[2] + (a * dim + k) * ck + b) * T] * v[b];
+          for (int b = 0; b < ck; b++) fl += dq[(LY.offset[2] + (a * dim + k) * ck + b) * DQS] * v[b];
         }
         if constexpr (B::d11) {
           SB_UNROLL
           for (int b = 0; b < ck; b++) {
             SB_UNROLL
-            for (int l = 0; l < dim; l++) fl += dq[(LY.offset[3] + ((a * dim + k) * ck + b) * dim + l) * T] * g[b][l];
+            for (int l = 0; l < dim; l++) fl += dq[(LY.offset[3] + ((a * dim + k) * ck + b) * dim + l) * DQS] * g[b][l];
           }
         }
         flux[a][k] = fl * w;

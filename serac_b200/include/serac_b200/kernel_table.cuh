@@ -360,6 +360,7 @@ sb_kernel_table make_kernel_table()
   T.qf_bytes           = sizeof(QF);
   T.state_bytes        = (std::is_same_v<State, Nothing> || std::is_empty_v<State>) ? 0 : sizeof(State);
   T.elements_per_block = Sig::EPB;
+  T.derivative_tile_elements = Sig::DQ_TE;
   T.evaluate           = &launch_evaluate<Sig, -1, QF, State, 1, (MINB > 0 ? MINB : default_min_blocks<Sig>()), FAST>;
   return T;
 }
