@@ -34,12 +34,10 @@ long make_blob(const double* p, int n, void* out, size_t cap)
 // 2 = streaming loads of X_q / J_q
 #if TUNE_SET == 0
 TUNE(4, 1, 16)
-TUNE(1004, 1, 16)
-TUNE(2004, 1, 16)
+TUNE(4, 1, 18)
 #elif TUNE_SET == 1
-TUNE(3004, 1, 16)
-TUNE(1, 1, 16)
-TUNE(1001, 1, 16)
+TUNE(4, 1, 20)
+TUNE(8, 1, 16)
 #endif
 }  // namespace
 }  // namespace sb

@@ -1270,7 +1270,8 @@ __global__ void __launch_bounds__(EvalLayout<Sig>::threads, MINB) evaluation_ker
     const long long pe = P.first_element + ((long long)blockIdx.x + P.prefetch_distance) * EPB;
     if (pe + EPB <= P.num_elements) {
       prefetch_range_l2<LAY::threads>(P.J_q + pe * (dim * sdim * QPE), (long long)EPB * dim * sdim * QPE * 8);
-      prefetch_range_l2<LAY::threads>(P.X_q + pe * (sdim * QPE), (long long)EPB * sdim * QPE * 8);
+      if constexpr (qf_usage<QF>::position)
+        prefetch_range_l2<LAY::threads>(P.X_q + pe * (sdim * QPE), (long long)EPB * sdim * QPE * 8);
       [&]<int... I>(std::integer_sequence<int, I...>)
       {
         (prefetch_range_l2<LAY::threads>(P.trial[I].table + pe * LAY::ndof(I), (long long)EPB * LAY::ndof(I) * 4), ...);
@@ -1284,15 +1285,9 @@ __global__ void __launch_bounds__(EvalLayout<Sig>::threads, MINB) evaluation_ker
   tensor<double, sdim, dim> Jm{};
   SB_UNROLL
   for (int i = 0; i < sdim; i++) {
-    if constexpr (Sig::tune & 2) {
-      x[i] = __ldcs(&P.X_q[((long long)e * sdim + i) * QPE + ql]);
-      SB_UNROLL
-      for (int j = 0; j < dim; j++) Jm(i, j) = __ldcs(&P.J_q[(((long long)e * dim + j) * sdim + i) * QPE + ql]);
-    } else {
-    x[i] = P.X_q[((long long)e * sdim + i) * QPE + ql];
+    if constexpr (qf_usage<QF>::position) x[i] = P.X_q[((long long)e * sdim + i) * QPE + ql];  // (else: nobody reads it)
     SB_UNROLL
     for (int j = 0; j < dim; j++) Jm(i, j) = P.J_q[(((long long)e * dim + j) * sdim + i) * QPE + ql];
-    }
   }
 
   // --- L -> E gather of every trial field at once (element_restriction.cpp:443-454): all loads are issued before the
@@ -1538,11 +1533,7 @@ __global__ void __launch_bounds__(EvalLayout<Sig>::threads, MINB) evaluation_ker
       tensor<double, ct>      s_p{};
       tensor<double, ct, dim> f_p{};
       auto sink = [&](int a, int k, int b, int l, double v) {
-        if constexpr (Sig::tune & 1) {
-          if (valid) __stcs(&dq[(long long)(((a * dim + k) * ck + b) * dim + l) * LAY::TILE], v);
-        } else {
-          if (valid) dq[(long long)(((a * dim + k) * ck + b) * dim + l) * LAY::TILE] = v;
-        }
+        if (valid) dq[(long long)(((a * dim + k) * ck + b) * dim + l) * LAY::TILE] = v;
       };
       [&]<int... I>(std::integer_sequence<int, I...>)
       {
