@@ -199,6 +199,49 @@ def bind_to_gpu_numa_node(local_rank):
     return None
 
 
+def copies_only_ms(dev, rank, world, ups, downs, reps=20):
+    """the host -> device and device -> host copies of one step, up and down concurrently on two streams, nothing else:
+    max over ranks of the time per step when one rank copies at a time (`one_rank_at_a_time`) and when all do
+    (`all_ranks_at_once`) -- the floor the host links put under the end-to-end step"""
+    import torch
+    import torch.distributed as dist
+    d_up = [torch.empty_like(h, device=dev) for h in ups]
+    d_dn = [torch.zeros_like(h, device=dev) for h in downs]
+    s_up, s_dn = torch.cuda.Stream(), torch.cuda.Stream()
+
+    def once():
+        with torch.cuda.stream(s_up):
+            for d, h in zip(d_up, ups):
+                d.copy_(h, non_blocking=True)
+        with torch.cuda.stream(s_dn):
+            for d, h in zip(d_dn, downs):
+                h.copy_(d, non_blocking=True)
+
+    def timed():
+        for _ in range(2):
+            once()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for _ in range(reps):
+            once()
+        torch.cuda.synchronize()
+        return (time.perf_counter() - t0) / reps * 1e3
+
+    keep = [h.clone() for h in downs]  # the downloads above overwrite the step's results: put them back afterwards
+    solo = 0.0
+    for turn in range(world):
+        dist.barrier()
+        if turn == rank:
+            solo = timed()
+    dist.barrier()
+    together = timed()
+    for h, k in zip(downs, keep):
+        h.copy_(k)
+    t = torch.tensor([solo, together], dtype=torch.float64, device=dev)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return {"one_rank_at_a_time": float(t[0].item()), "all_ranks_at_once": float(t[1].item())}
+
+
 def synthetic_u(gid):
     """displacement as a function of the GLOBAL vdof id (shared dofs agree across ranks; small against the element size)"""
     return 0.016 * ELEMENT_SIZE * np.sin(0.37 * np.asarray(gid, dtype=np.float64) + 1.0)
@@ -586,6 +629,13 @@ def run_product(args):
         e2e_s = float(tt.item())
     clocks = sampler.stop() if rank == 0 else None
 
+    # N > 1: what the host links allow -- the step's copies and nothing else, by this rank alone and by all ranks at once
+    # (untimed part of the run; the box's aggregate host <-> device bandwidth, not the kernels, bounds e2e at 8 GPUs:
+    # profiles/r2x_pcie_probe_n8.json)
+    copy_ceiling = None
+    if world > 1 and BENCH_CONFIG != "b":
+        copy_ceiling = copies_only_ms(dev, rank, world, (hS, hU, hA, hdU), (hr, hdr))
+
     # sanity: host path and device path agree bit for bit (same kernels, same data)
     if world > 1 and P["transport"] == "peer":
         assert all(h.peer_status() == 0 for h in P["halos"]), "a wait for a neighbour timed out in the host-buffer steps"
@@ -650,7 +700,8 @@ def run_product(args):
                 "h2d_bytes_per_step": int(8 * (3 * vdofs_total + shape_total)),
                 "d2h_bytes_per_step": int(8 * 2 * vdofs_total), "ms_per_step": e2e_s * 1e3,
                 "host_buffers": "pinned" + (f", bound to the GPU's NUMA node (rank 0: node {numa})" if numa is not None
-                                            else "")},
+                                            else ""),
+                **({"copies_only_ms": copy_ceiling} if copy_ceiling else {})},
         "gpu_launches": int(launches_per_step * args.steps),
         "phases_ms": {"evaluate_with_derivative_store": phase_ms[0], "scatter_r": phase_ms[1], "jvp": phase_ms[2],
                       "scatter_dr": phase_ms[3]},
