@@ -122,6 +122,7 @@ struct FiniteElementSpace {
   /// fes->GetFaceDofs of the mesh's boundary faces in mfem's native order (only needed by AddBoundaryIntegral)
   int64_t          num_boundary_faces = 0;
   std::vector<int> native_boundary_face_dofs;  ///< [num_boundary_faces][nodes per face]
+  Family           family = Family::H1;  ///< H1, or L2 (discontinuous: mfem hands out its element dofs in lexicographic order)
   int64_t          GetVSize() const { return num_nodes * vdim; }
 };
 
@@ -209,12 +210,13 @@ class Functional<test(trials...)> {
   Functional(const FiniteElementSpace* test_fes, std::array<const FiniteElementSpace*, num_trial_spaces> trial_fes)
       : test_space_(test_fes), trial_space_(trial_fes)
   {
-    constexpr int orders[] = {trials::order..., 0};
-    constexpr int comps[]  = {trials::components..., 0};
-    check_space(*test_fes, test::order, test::components, "test");
+    constexpr int    orders[] = {trials::order..., 0};
+    constexpr int    comps[]  = {trials::components..., 0};
+    constexpr Family fams[]   = {trials::family..., Family::H1};
+    check_space(*test_fes, test::order, test::components, "test", test::family);
     G_test_ = make_restriction(*test_fes);
     for (int i = 0; i < num_trial_spaces; i++) {
-      check_space(*trial_fes[size_t(i)], orders[i], comps[i], "trial");
+      check_space(*trial_fes[size_t(i)], orders[i], comps[i], "trial", fams[i]);
       // spaces that are the same object share one restriction
       G_trial_[size_t(i)] = nullptr;
       if (trial_fes[size_t(i)] == test_fes) G_trial_[size_t(i)] = G_test_;
@@ -488,8 +490,13 @@ class Functional<test(trials...)> {
     std::abort();
   }
 
-  void check_space(const FiniteElementSpace& fes, int order, int components, const char* what) const
+  void check_space(const FiniteElementSpace& fes, int order, int components, const char* what, Family family) const
   {
+    if ((family == Family::L2) != (fes.family == Family::L2)) {
+      std::fprintf(stderr, "serac::Functional: %s space is %s but the template signature says %s\n", what,
+                   fes.family == Family::L2 ? "L2" : "H1", family == Family::L2 ? "L2" : "H1");
+      std::abort();
+    }
     if (fes.order != order || fes.vdim != components) {
       std::fprintf(stderr, "serac::Functional: %s space is H1<%d,%d> but the template signature says H1<%d,%d>\n", what,
                    fes.order, fes.vdim, order, components);
@@ -502,8 +509,13 @@ class Functional<test(trials...)> {
   {
     const int             npe = b200::num_nodes(fes.geometry, fes.order);
     std::vector<uint64_t> dof_info(size_t(fes.num_elements) * size_t(npe));
-    SERAC_B200_CHECK(sb_h1_lexicographic_dof_info(int(fes.geometry), fes.order, fes.native_element_dofs.data(),
-                                                  fes.num_elements, dof_info.data()));
+    if (fes.family == Family::L2) {
+      // "mfem returns DG dofs in lexicographic order already so no permutation is required" (element_restriction.cpp:262-268)
+      for (size_t i = 0; i < dof_info.size(); i++) dof_info[i] = uint64_t(fes.native_element_dofs[i]);
+    } else {
+      SERAC_B200_CHECK(sb_h1_lexicographic_dof_info(int(fes.geometry), fes.order, fes.native_element_dofs.data(),
+                                                    fes.num_elements, dof_info.data()));
+    }
     sb_restriction_t r = nullptr;
     SERAC_B200_CHECK(sb_restriction_create(dof_info.data(), fes.num_elements, npe, fes.vdim, fes.num_nodes,
                                            int(fes.ordering), &r));

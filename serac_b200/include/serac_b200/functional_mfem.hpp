@@ -110,6 +110,7 @@ inline core_api::FiniteElementSpace convert_space(const mfem::FiniteElementSpace
   }
   core_api::FiniteElementSpace out{};
   out.geometry     = geometry_of(g0);
+  out.family       = dynamic_cast<const mfem::L2_FECollection*>(fes.FEColl()) ? Family::L2 : Family::H1;
   out.order        = fes.GetMaxElementOrder();
   out.vdim         = fes.GetVDim();
   out.ordering     = (fes.GetOrdering() == mfem::Ordering::byVDIM) ? core_api::Ordering::byVDIM : core_api::Ordering::byNODES;

@@ -196,6 +196,68 @@ void thermal_comparison(mfem::Mesh& mesh, const char* tag)
          J->NumNonZeroElems(), Am.NumNonZeroElems());
 }
 
+// ---- functional_comparison_L2.cpp:56-160: L2 test and trial spaces against MFEM's mass matrix and load vector -----------
+struct L2SourceFunctor {  // functional_comparison_L2.cpp:40-54 (a = 1.7, b = 0)
+  template <typename Position, typename Temperature>
+  SERAC_HOST_DEVICE auto operator()(double /*t*/, Position position, Temperature temperature) const
+  {
+    auto [X, dX_dxi] = position;
+    auto [u, du_dX]  = temperature;
+    auto source      = COEF_A * u - (100 * X[0] * X[1]);
+    auto flux        = 0.0 * du_dX;
+    return serac::tuple{source, flux};
+  }
+};
+
+template <int p, int dim>
+void l2_comparison(mfem::Mesh& mesh, const char* tag)
+{
+  // serac::generateParFiniteElementSpace<L2<p>>: L2_FECollection on Gauss-Lobatto points (finite_element.hpp / mesh utilities)
+  mfem::L2_FECollection    fec(p, dim, mfem::BasisType::GaussLobatto);
+  mfem::FiniteElementSpace fes(&mesh, &fec);
+  const mfem::FiniteElement&   el = *fes.GetFE(0);
+  const mfem::IntegrationRule& ir = mfem::IntRules.Get(el.GetGeomType(), 2 * p + 1);  // the (p + 1)-point Gauss rule
+
+  mfem::BilinearForm        A(&fes);
+  mfem::ConstantCoefficient a_coef(a);
+  auto* mass = new mfem::MassIntegrator(a_coef);
+  mass->SetIntRule(&ir);
+  A.AddDomainIntegrator(mass);
+  A.Assemble(0);
+  A.Finalize();
+  mfem::LinearForm          f(&fes);
+  mfem::FunctionCoefficient load_func([](const mfem::Vector& c) { return 100 * c(0) * c(1); });
+  auto* load = new mfem::DomainLFIntegrator(load_func);
+  load->SetIntRule(&ir);
+  f.AddDomainIntegrator(load);
+  f.Assemble();
+
+  mfem::Vector U(fes.GetVSize());
+  U.Randomize(3);
+
+  using space = L2<p>;
+  Functional<space(space)> residual(&fes, {&fes});
+  residual.AddDomainIntegral(Dimension<dim>{}, DependsOn<0>{}, L2SourceFunctor{}, mesh);
+
+  mfem::Vector r1(U.Size());
+  A.Mult(U, r1);
+  r1 -= f;
+  mfem::Vector r2 = residual(0.0, U);
+  EXPECT(rel(r2, r1) < 1e-13, "L2 %s p=%d: ||r_functional - r_mfem|| / ||r|| = %.2e", tag, p, rel(r2, r1));
+
+  auto [r3, drdU] = residual(0.0, differentiate_wrt(U));
+  mfem::Vector g1(U.Size());
+  A.Mult(U, g1);
+  mfem::Vector g2 = drdU(U);
+  EXPECT(rel(g2, g1) < 1e-13, "L2 %s p=%d: gradient action vs A U %.2e", tag, p, rel(g2, g1));
+  std::unique_ptr<mfem::SparseMatrix> J = assemble(drdU);
+  mfem::Vector g4(U.Size());
+  J->Mult(U, g4);
+  EXPECT(rel(g4, g1) < 1e-13 && J->NumNonZeroElems() == A.SpMat().NumNonZeroElems(),
+         "L2 %s p=%d: assembled (block-diagonal) matrix action %.2e, nnz %d vs %d", tag, p, rel(g4, g1),
+         J->NumNonZeroElems(), A.SpMat().NumNonZeroElems());
+}
+
 template <int p>
 void elasticity_comparison(mfem::Mesh& mesh, const char* tag)
 {
@@ -370,6 +432,15 @@ int main(int argc, char** argv)
     elasticity_comparison<1>(hexes, "hexes");
     elasticity_comparison<2>(hexes, "hexes");
     elasticity_comparison<1>(tets, "tets");
+  }
+  if (which == "l2" || which == "all") {  // functional_comparison_L2.cpp:162-170
+    mfem::Mesh quads = mfem::Mesh::MakeCartesian2D(3, 2, mfem::Element::QUADRILATERAL, true, 1.0, 1.3);
+    quads.EnsureNodes();
+    l2_comparison<1, 2>(quads, "quads");
+    l2_comparison<2, 2>(quads, "quads");
+    l2_comparison<1, 3>(hexes, "hexes");
+    l2_comparison<2, 3>(hexes, "hexes");
+    l2_comparison<3, 3>(hexes, "hexes");
   }
   if (which == "gradients" || which == "all") {
     elasticity_gradients<1>(hexes, "hexes");
