@@ -320,12 +320,15 @@ def interpolate(u_E, p, q, dim, geom=None):
         gy = np.einsum("wk,vj,ui,eckji->ecwvu", B, G, B, X)
         gz = np.einsum("wk,vj,ui,eckji->ecwvu", G, B, B, X)
         grad = np.stack([gx, gy, gz], axis=2)
-    else:
+    elif dim == 2:
         X = u_E.reshape(ne, c, n, n)
         val = np.einsum("vj,ui,ecji->ecvu", B, B, X)
         gx = np.einsum("vj,ui,ecji->ecvu", B, G, X)
         gy = np.einsum("vj,ui,ecji->ecvu", G, B, X)
         grad = np.stack([gx, gy], axis=2)
+    else:  # segment (F/detail/segment_H1.inl:86-100)
+        val = np.einsum("ui,eci->ecu", B, u_E)
+        grad = np.einsum("ui,eci->ecu", G, u_E)[:, :, None, :]
     nq = q**dim
     return val.reshape(ne, c, nq), grad.reshape(ne, c, dim, nq)
 
@@ -357,13 +360,18 @@ def integrate(source, flux, p, q, dim, geom=None):
             out += np.einsum("wk,vj,ui,ecwvu->eckji", Bw, Bw, Gw, f[:, :, 0])
             out += np.einsum("wk,vj,ui,ecwvu->eckji", Bw, Gw, Bw, f[:, :, 1])
             out += np.einsum("wk,vj,ui,ecwvu->eckji", Gw, Bw, Bw, f[:, :, 2])
-    else:
+    elif dim == 2:
         if source is not None:
             out += np.einsum("vj,ui,ecvu->ecji", Bw, Bw, source.reshape(ne, c, q, q))
         if flux is not None:
             f = flux.reshape(ne, c, 2, q, q)
             out += np.einsum("vj,ui,ecvu->ecji", Bw, Gw, f[:, :, 0])
             out += np.einsum("vj,ui,ecvu->ecji", Gw, Bw, f[:, :, 1])
+    else:  # segment (F/detail/segment_H1.inl:102-118)
+        if source is not None:
+            out += np.einsum("ui,ecu->eci", Bw, source)
+        if flux is not None:
+            out += np.einsum("ui,ecu->eci", Gw, flux[:, :, 0])
     return out.reshape(ne, c, n**dim)
 
 
@@ -866,16 +874,22 @@ def evaluation_kernel(qf, trials_E, orders, X_q, J_q, test_order, q, dim, wrt=-1
 
 
 # ----------------------------------------------------------------------------------------------------------------------
-# boundary integrals (F/boundary_integral_kernels.hpp:111-205): faces of a 3D mesh, trial gradients stay in xi coordinates
+# boundary integrals (F/boundary_integral_kernels.hpp:111-205): faces of a 3D mesh / segments of a 2D mesh, trial gradients stay in xi coordinates
 # ----------------------------------------------------------------------------------------------------------------------
 def vcross(A):
-    """cross product of the two columns of a 3 x 2 matrix given as a list of rows"""
+    """cross product of the two columns of a 3 x 2 matrix given as a list of rows; for a 2 x 1 matrix (the tangent of a
+    segment in the plane) the vector perpendicular to its column, {A10, -A00} (F/tensor.hpp:906-928)"""
+    if len(A) == 2:
+        return [A[1][0], -1.0 * A[0][0]]
     a, b = [A[i][0] for i in range(3)], [A[i][1] for i in range(3)]
     return [a[1] * b[2] - a[2] * b[1], a[2] * b[0] - a[0] * b[2], a[0] * b[1] - a[1] * b[0]]
 
 
 def vnorm(v):
-    return d_sqrt(v[0] * v[0] + v[1] * v[1] + v[2] * v[2])
+    s = v[0] * v[0]
+    for c in v[1:]:
+        s = s + c * c
+    return d_sqrt(s)
 
 
 def shape_aware_boundary(qf):
@@ -884,7 +898,7 @@ def shape_aware_boundary(qf):
 
     def wrapped(t, x, shape, *args):
         X, dX = x
-        xp = ([X[i] + shape[0][i] for i in range(3)], madd(dX, shape[1]))
+        xp = ([X[i] + shape[0][i] for i in range(len(X))], madd(dX, shape[1]))
         corr = vnorm(vcross(xp[1])) / vnorm(vcross(dX))
         return [s * corr for s in qf(t, xp, *args)]
 
@@ -917,7 +931,7 @@ def make_boundary_qf(kind, params):
     if kind == "solid_pressure":
         return shape_aware_boundary(pressure_qf(params[0], params[1] != 0.0))
     if kind == "solid_traction":
-        return shape_aware_boundary(traction_qf(list(params[:3])))
+        return shape_aware_boundary(traction_qf(list(params)))
     raise KeyError(kind)
 
 
@@ -925,7 +939,7 @@ def _face_weights(geom, q):
     if is_simplex(geom):
         return simplex_quadrature(geom, q)[1]
     w = basis_tables(1, q)[2]
-    return np.multiply.outer(w, w).ravel()
+    return w if geom == SEGMENT else np.multiply.outer(w, w).ravel()
 
 
 def boundary_evaluation_kernel(qf, trials_E, orders, X_q, J_q, test_order, q, face_geom, wrt=-1):
@@ -933,46 +947,48 @@ def boundary_evaluation_kernel(qf, trials_E, orders, X_q, J_q, test_order, q, fa
     X_q [nf][3][nq], J_q [nf][j][i][nq] = dX_i/dxi_j.  Returns r_E [nf][ct][ndof] and, when wrt >= 0, the derivative blocks
     d00 [nf][nq][ct][ck] and d01 [nf][nq][ct][ck][2] of the weighted source w.r.t. the value and the xi-gradient."""
     nf, nq = X_q.shape[0], X_q.shape[2]
-    dX = [[J_q[:, j, i, :] for j in range(2)] for i in range(3)]  # 3 x 2
+    sdim, fd = X_q.shape[1], J_q.shape[1]  # space dimension, face dimension (2: faces of 3D meshes, 1: segments)
+    dX = [[J_q[:, j, i, :] for j in range(fd)] for i in range(sdim)]  # sdim x fd
     args = []
     for k, (uE, p) in enumerate(zip(trials_E, orders)):
-        val, grad = interpolate(uE, p, q, 2, face_geom)
+        val, grad = interpolate(uE, p, q, fd, face_geom)
         c = val.shape[1]
         vals, grads = _tensor_lists(val, grad)
         if k == wrt:
-            N = c + c * 2
+            N = c + c * fd
             z = np.zeros((nf, nq, N))
             for a in range(c):
                 g = z.copy()
                 g[..., a] = 1.0
                 vals[a] = Dual(vals[a], g)
-                for j in range(2):
+                for j in range(fd):
                     g = z.copy()
-                    g[..., c + a * 2 + j] = 1.0
+                    g[..., c + a * fd + j] = 1.0
                     grads[a][j] = Dual(grads[a][j], g)
         args.append((vals, grads))
-    x = ([X_q[:, i, :] for i in range(3)], dX)
+    x = ([X_q[:, i, :] for i in range(sdim)], dX)
     source = qf(0.0, x, *args)
     measure = vnorm(vcross(dX))  # |dX/dxi_1 x dX/dxi_2| (:148-152)
     source = [s * measure for s in source]
     ct = len(source)
     src_v = np.stack([np.broadcast_to(value_of(s), (nf, nq)) for s in source], axis=1)
-    r_E = integrate(src_v, None, test_order, q, 2, face_geom)
+    r_E = integrate(src_v, None, test_order, q, fd, face_geom)
     if wrt < 0:
         return r_E, None
     ck = trials_E[wrt].shape[1]
-    ds = np.stack([s.g if isinstance(s, Dual) else np.zeros((nf, nq, ck + ck * 2)) for s in source], axis=2)
-    blocks = dict(d00=ds[..., :ck], d01=ds[..., ck:].reshape(nf, nq, ct, ck, 2))
+    ds = np.stack([s.g if isinstance(s, Dual) else np.zeros((nf, nq, ck + ck * fd)) for s in source], axis=2)
+    blocks = dict(d00=ds[..., :ck], d01=ds[..., ck:].reshape(nf, nq, ct, ck, fd))
     return r_E, blocks
 
 
 def boundary_action_of_gradient_kernel(blocks, du_E, trial_order, test_order, q, face_geom):
     """boundary action_of_gradient_kernel (F/boundary_integral_kernels.hpp:252-277)"""
-    val, grad = interpolate(du_E, trial_order, q, 2, face_geom)
+    fd = blocks["d01"].shape[-1]
+    val, grad = interpolate(du_E, trial_order, q, fd, face_geom)
     v = np.transpose(val, (0, 2, 1))
     g = np.transpose(grad, (0, 3, 1, 2))
     src = np.einsum("eqab,eqb->eqa", blocks["d00"], v) + np.einsum("eqabl,eqbl->eqa", blocks["d01"], g)
-    return integrate(np.transpose(src, (0, 2, 1)), None, test_order, q, 2, face_geom)
+    return integrate(np.transpose(src, (0, 2, 1)), None, test_order, q, fd, face_geom)
 
 
 def action_of_gradient_kernel(blocks, du_E, trial_order, test_order, q, dim, geom=None):

@@ -304,6 +304,11 @@ BOUNDARY_QOI_FIXTURES = [
                                                 params=[0.7, 1.3])),
     ("qoi_boundary_quadratic_tet_p1_beam", dict(mesh_spec=("file", "beam-tet.mesh", 0), kind="qoi_boundary_quadratic",
                                                 p=1, params=[0.7, 1.3])),
+    # segment faces of 2-D meshes (F/detail/segment_H1.inl; F/tests/bug_boundary_qoi.cpp runs on a 2-D mesh)
+    ("qoi_boundary_quadratic_quad_p2_cart", dict(mesh_spec=("cart2d", 3, 2, 0.02), kind="qoi_boundary_quadratic", p=2,
+                                                 params=[0.7, 1.3])),
+    ("qoi_boundary_quadratic_tri_p1_patch", dict(mesh_spec=("file", "patch2D_tris.mesh", 1),
+                                                 kind="qoi_boundary_quadratic", p=1, params=[0.7, 1.3])),
 ]
 
 QOI_FIXTURES = [
@@ -377,6 +382,16 @@ BOUNDARY_FIXTURES = [
     # dead traction: only the shape derivative is non-zero (setTraction)
     ("solid_traction_hex_p2_cart", dict(mesh_spec=("cart3d", 2, 2, 1, 0.02), kind="solid_traction", p=2,
                                         params=[0.3, -1.0, 2.0], shape_amp=0.01)),
+    # segment faces of 2-D meshes (F/detail/segment_H1.inl): quadrilateral and triangular meshes, p = 1 and 2;
+    # star.mesh is the mesh of BASELINE.json configs[0]
+    ("solid_pressure_quad_p2_cart", dict(mesh_spec=("cart2d", 3, 2, 0.02), kind="solid_pressure", p=2,
+                                         params=[3.0, 1.0], shape_amp=0.01)),
+    ("solid_traction_quad_p1_star", dict(mesh_spec=("file", "star.mesh", 0), kind="solid_traction", p=1,
+                                         params=[0.3, -1.0], shape_amp=0.01)),
+    ("solid_pressure_tri_p2_cart", dict(mesh_spec=("cart2d_tri", 3, 2, 0.02), kind="solid_pressure", p=2,
+                                        params=[-1.5, 1.0], shape_amp=0.01)),
+    ("solid_traction_tri_p1_patch", dict(mesh_spec=("file", "patch2D_tris.mesh", 1), kind="solid_traction", p=1,
+                                         params=[0.3, -1.0], shape_amp=0.01)),
 ]
 
 # (file name, kwargs of reference_problem)

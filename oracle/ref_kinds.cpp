@@ -341,7 +341,9 @@ ref::Registrar r8("thermoelastic_thermal_" TAG, [](mfem::Mesh& mesh, const doubl
   return h;
 });
 
-// ---- boundary integrands (faces of the 3D mesh) -------------------------------------------------------------------
+#endif  // REF_DIM == 3
+
+// ---- boundary integrands (quadrilateral / triangular faces of 3D meshes, segment faces of 2D meshes) -------------------------------------------------------------------
 // functor shells restating ShapeAwareFunctional::ShapeAwareBoundaryIntegrandWrapper (shape_aware_functional.hpp:474-499)
 // and the lambdas of SolidMechanics::setTraction / setPressure (solid_mechanics.hpp:1030-1036, 1075-1101) with a
 // constant traction vector / pressure; compute_boundary_area_correction is the reference's.
@@ -414,13 +416,14 @@ ref::Registrar rqb("qoi_boundary_quadratic_" TAG, [](mfem::Mesh& mesh, const dou
 });
 
 ref::Registrar r5("solid_traction_" TAG, [](mfem::Mesh& mesh, const double* q, int n) {
-  SLIC_ERROR_IF(n != 3, "params: tx ty tz");
-  return make_boundary(mesh, ShapeAwareBoundary<UniformTractionIntegrand>{UniformTractionIntegrand{{{q[0], q[1], q[2]}}}});
+  SLIC_ERROR_IF(n != dim, "params: tx ty [tz]");
+  tensor<double, dim> traction{};
+  for (int i = 0; i < dim; i++) traction[i] = q[i];
+  return make_boundary(mesh, ShapeAwareBoundary<UniformTractionIntegrand>{UniformTractionIntegrand{traction}});
 });
 ref::Registrar r6("solid_pressure_" TAG, [](mfem::Mesh& mesh, const double* q, int n) {
   SLIC_ERROR_IF(n != 2, "params: pressure geom_nonlin");
   return make_boundary(mesh, ShapeAwareBoundary<UniformPressureIntegrand>{UniformPressureIntegrand{q[0], q[1] != 0.0}});
 });
-#endif
 
 }  // namespace

@@ -1,6 +1,7 @@
 // serac_b200: named boundary integrands -- what SolidMechanics::setTraction / setPressure register with their Functional
 // (src/serac/physics/solid_mechanics.hpp:1024-1101), wrapped by ShapeAwareFunctional::AddBoundaryIntegral
-// (shape_aware_functional.hpp:474-520), on the boundary faces of H1<p,dim>(H1<1,dim> shape, H1<p,dim> u, H1<p,dim> a).
+// (shape_aware_functional.hpp:474-520), on the boundary faces of H1<p,dim>(H1<1,dim> shape, H1<p,dim> u, H1<p,dim> a):
+// quadrilaterals (hex meshes), triangles (tet meshes) and segments (2-D meshes, F/detail/segment_H1.inl).
 #include "registry.hpp"
 
 namespace sb {
@@ -40,6 +41,12 @@ static Registrar r_traction({"solid_traction_" SB_STR(SB_REG_TAG), make_boundary
                              &make_traction, "{traction_x, traction_y[, traction_z]}"});
 static Registrar r_pressure({"solid_pressure_" SB_STR(SB_REG_TAG), make_boundary_kernel_table<Sig, PressureQF>(),
                              &make_pressure, "{pressure, geometric_nonlinearity(0|1)}"});
+#ifdef SB_REG_TAG2  // segment faces bound quadrilateral and triangular meshes alike: the same tables under both names
+static Registrar r_traction2({"solid_traction_" SB_STR(SB_REG_TAG2), make_boundary_kernel_table<Sig, TractionQF>(),
+                              &make_traction, "{traction_x, traction_y[, traction_z]}"});
+static Registrar r_pressure2({"solid_pressure_" SB_STR(SB_REG_TAG2), make_boundary_kernel_table<Sig, PressureQF>(),
+                              &make_pressure, "{pressure, geometric_nonlinearity(0|1)}"});
+#endif
 
 }  // namespace
 }  // namespace sb

@@ -56,6 +56,10 @@ long make_bqoi(const double* q, int n, void* out, size_t cap)
 }
 static Registrar r_bqoi({"qoi_boundary_quadratic_" SB_STR(SB_REG_TAG), make_boundary_kernel_table<BSig, QuadraticBoundaryQoi>(),
                          &make_bqoi, "{a, b}: boundary integrand a (1 + x_0) u.u + b/2 |du/dxi|^2"});
+#ifdef SB_REG_TAG2
+static Registrar r_bqoi2({"qoi_boundary_quadratic_" SB_STR(SB_REG_TAG2), make_boundary_kernel_table<BSig, QuadraticBoundaryQoi>(),
+                          &make_bqoi, "{a, b}: boundary integrand a (1 + x_0) u.u + b/2 |du/dxi|^2"});
+#endif
 #else
 using Sig = Signature<g, p + 1, QOI, H1<p, dim>>;
 

@@ -44,7 +44,7 @@ SB_HD int elements_per_block(int dim, int q)
 /// geometry-aware version: simplices have no tensor structure, one thread per quadrature point, ~128 threads per CTA
 SB_HD int elements_per_block(Geometry g, int q)
 {
-  if (!is_simplex(g)) return elements_per_block(dimension_of(g), q);
+  if (!uses_dense_table(g)) return elements_per_block(dimension_of(g), q);
   const int nq  = num_quadrature_points(g, q);
   const int epb = 128 / nq;
   return epb > 32 ? 32 : (epb < 1 ? 1 : epb);
@@ -627,7 +627,7 @@ struct SignatureT {
   static constexpr int      q        = Q;
   static constexpr int      NT       = int(sizeof...(trials));
   static constexpr int      QPE      = num_quadrature_points(geom, Q);  ///< quadrature points per element
-  static constexpr bool     simplex  = is_simplex(geom);
+  static constexpr bool     simplex  = uses_dense_table(geom);  ///< dense {phi, dphi} tables (simplices, segments)
   static constexpr int      EPB      = (EPB_ % 1000 > 0) ? EPB_ % 1000 : elements_per_block(geom, Q);
   static constexpr int      tune     = EPB_ / 1000;  ///< experiment switches of registry_tune.cu (0 in every product table)
   static constexpr int      threads  = EPB * QPE;

@@ -212,6 +212,10 @@ inline BasisTable1D make_basis_table(int p, int q)
 // ------------------------------------------------------------------------------------------------
 SB_HD bool is_simplex(Geometry g) { return g == Geometry::TRIANGLE || g == Geometry::TETRAHEDRON; }
 
+/// geometries whose kernels interpolate / integrate by dense sums against a {phi, dphi/dxi} table: the simplices and the
+/// segment (the boundary faces of 2-D meshes, F/detail/segment_H1.inl: with one direction there is nothing to factorise)
+SB_HD bool uses_dense_table(Geometry g) { return is_simplex(g) || g == Geometry::SEGMENT; }
+
 /// H1 nodes per element
 SB_HD int num_nodes(Geometry g, int p)
 {
@@ -419,6 +423,19 @@ inline SimplexTable make_simplex_table(Geometry g, int p, int Q)
 {
   SimplexTable t{};
   t.dim = dimension_of(g);
+  if (g == Geometry::SEGMENT) {  // segment_H1.inl:20-118: Gauss-Lobatto nodes (ascending), Gauss-Legendre rule on [0, 1]
+    const BasisTable1D b = make_basis_table(p, Q);
+    t.nq                 = Q;
+    t.ndof               = p + 1;
+    for (int i = 0; i < Q; i++) {
+      for (int k = 0; k < t.ndof; k++) {
+        t.tab[(i * t.ndof + k) * 2 + 0] = b.B[i * b.n + k];
+        t.tab[(i * t.ndof + k) * 2 + 1] = b.G[i * b.n + k];
+      }
+      t.tab[Q * t.ndof * 2 + i] = b.w[i];
+    }
+    return t;
+  }
   double xi[MAX_SIMPLEX_QPTS * 3], w[MAX_SIMPLEX_QPTS];
   t.nq   = simplex_quadrature(g, Q, xi, w);
   if (p == 0) {  // quantity of interest: one "shape function" = 1 (F/detail/qoi.inl:24)

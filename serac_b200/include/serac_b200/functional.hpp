@@ -299,18 +299,23 @@ class Functional<test(trials...)> {
 
   /// functional.hpp:328-354.  dim = dimension of the boundary faces; integrand: `(t, tuple{x, dx_dxi},
   /// tuple{value, d/dxi}...) -> source` (trial derivatives stay in parent coordinates on a boundary).  Every space and
-  /// the mesh must carry its native boundary-face dofs.  Faces of 3D meshes (quadrilaterals / triangles).
+  /// the mesh must carry its native boundary-face dofs.  Faces of 3D meshes (quadrilaterals / triangles) and of 2D
+  /// meshes (segments, F/detail/segment_H1.inl).
   template <int dim, int... args, typename Integrand>
   void AddBoundaryIntegral(Dimension<dim>, DependsOn<args...>, const Integrand& integrand, const Mesh& mesh)
   {
-    static_assert(dim == 2, "boundary integrals are implemented on the faces of 3D meshes");
+    static_assert(dim == 1 || dim == 2, "boundary integrals live on the faces of 2D or 3D meshes");
     static_assert(((args >= 0 && args < num_trial_spaces) && ...), "DependsOn<> index out of range");
     if (mesh.Dimension() != dim + 1) fail("AddBoundaryIntegral: Dimension<dim> must be the mesh dimension - 1");
     const Geometry g  = mesh.nodes_space.geometry;
-    const Geometry fg = (g == Geometry::CUBE) ? Geometry::SQUARE : Geometry::TRIANGLE;
+    const Geometry fg = (dim == 1) ? Geometry::SEGMENT : (g == Geometry::CUBE) ? Geometry::SQUARE : Geometry::TRIANGLE;
     const sb_kernel_table* table = nullptr;
-    if (fg == Geometry::SQUARE) table = boundary_table_for<Geometry::SQUARE, Integrand, args...>();
-    if (fg == Geometry::TRIANGLE) table = boundary_table_for<Geometry::TRIANGLE, Integrand, args...>();
+    if constexpr (dim == 2) {
+      if (fg == Geometry::SQUARE) table = boundary_table_for<Geometry::SQUARE, Integrand, args...>();
+      if (fg == Geometry::TRIANGLE) table = boundary_table_for<Geometry::TRIANGLE, Integrand, args...>();
+    } else {
+      table = boundary_table_for<Geometry::SEGMENT, Integrand, args...>();
+    }
     const int64_t    nf     = mesh.nodes_space.num_boundary_faces;
     sb_restriction_t G_mesh = make_face_restriction(mesh.nodes_space, fg);
     mesh_restrictions_.push_back(G_mesh);

@@ -14,9 +14,9 @@ namespace b200 {
 inline const double* simplex_table_dev(Geometry g, int p, int Q)
 {
   static std::mutex    mtx;
-  static const double* cache[2][4][MAX_Q + 1] = {};
-  if (!is_simplex(g) || p < 0 || p > 3 || Q < 1 || Q > MAX_Q) return nullptr;
-  const int                   gi = (g == Geometry::TRIANGLE) ? 0 : 1;
+  static const double* cache[3][4][MAX_Q + 1] = {};
+  if (!uses_dense_table(g) || p < 0 || p > 3 || Q < 1 || Q > MAX_Q) return nullptr;
+  const int                   gi = (g == Geometry::TRIANGLE) ? 0 : (g == Geometry::TETRAHEDRON) ? 1 : 2;
   std::lock_guard<std::mutex> lock(mtx);
   if (!cache[gi][p][Q]) {
     SimplexTable t = make_simplex_table(g, p, Q);

@@ -9,6 +9,9 @@
 //   gradients     functional_basic_h1_vector.cpp:60-165 + check_gradient.hpp:16-90: domain + boundary integrals with
 //                 source / flux terms of every shape; JVP against the assembled matrix (5e-6) and finite-difference
 //                 convergence ratios
+//   scalar        functional_basic_h1_scalar.cpp:32-118: H1<ptest>(H1<ptrial>) with a domain and a boundary integral on
+//                 hexahedra, tetrahedra, quadrilaterals and triangles (boundary faces of the 2D meshes: segments),
+//                 equal and mixed orders, through check_gradient
 //   shape         ShapeAwareFunctional (shape_aware_functional.hpp:292-575): with a shape displacement p the residual
 //                 equals that of the plain Functional on the mesh whose nodes were moved by p
 // Meshes are generated (MakeCartesian3D + a smooth perturbation): the reference's mesh files are not on the GPU box.
@@ -91,6 +94,33 @@ struct ElasticityTestModelTwo {  // functional_basic_h1_vector.cpp:77-87 (bounda
   }
 };
 
+template <int dim>
+struct TestThermalModelOne {  // functional_basic_h1_scalar.cpp:32-49
+  template <typename P, typename Temp>
+  SERAC_HOST_DEVICE auto operator()(double, P position, Temp temperature) const
+  {
+    double     d00 = 1.0;
+    const auto d01 = 1.0 * make_tensor<dim>([](int i) { return i; });
+    const auto d10 = 1.0 * make_tensor<dim>([](int i) { return 2 * i * i; });
+    const auto d11 = 1.0 * make_tensor<dim, dim>([](int i, int j) { return i + j * (j + 1) + 1; });
+    auto [X, dX_dxi] = position;
+    auto [u, du_dx]  = temperature;
+    auto source      = d00 * u + dot(d01, du_dx) - 0.0 * (100 * X[0] * X[1]);
+    auto flux        = d10 * u + dot(d11, du_dx);
+    return serac::tuple{source, flux};
+  }
+};
+
+struct TestThermalModelTwo {  // functional_basic_h1_scalar.cpp:51-60 (boundary integrand)
+  template <typename PositionType, typename TempType>
+  SERAC_HOST_DEVICE auto operator()(double, PositionType position, TempType temperature) const
+  {
+    auto [X, dX_dxi] = position;
+    auto [u, du_dxi] = temperature;
+    return X[0] + X[1] - cos(u);
+  }
+};
+
 // a nonlinear integrand for the shape-aware check: source and flux depend on position, value and gradient
 struct NonlinearThermal {
   template <typename Position, typename Temperature>
@@ -114,6 +144,18 @@ mfem::Mesh make_mesh(mfem::Element::Type type, int n = 2)
     y(0) = x(0) + 0.05 * std::sin(2.0 * x(1)) * x(2);
     y(1) = x(1) + 0.04 * x(0) * x(2);
     y(2) = x(2) + 0.03 * std::cos(1.5 * x(0)) * x(1);
+  });
+  return mesh;
+}
+
+mfem::Mesh make_mesh_2d(mfem::Element::Type type, int n = 3)
+{
+  mfem::Mesh mesh = mfem::Mesh::MakeCartesian2D(n, n - 1, type, true, 1.0, 1.3);
+  mesh.EnsureNodes();
+  mesh.Transform([](const mfem::Vector& x, mfem::Vector& y) {
+    y    = x;
+    y(0) = x(0) + 0.05 * std::sin(2.0 * x(1));
+    y(1) = x(1) + 0.04 * x(0) * x(0);
   });
   return mesh;
 }
@@ -369,6 +411,24 @@ void elasticity_gradients(mfem::Mesh& mesh, const char* tag)  // functional_basi
   check_gradient(residual, 0.0, U, what.c_str());
 }
 
+template <int ptest, int ptrial, int dim>
+void thermal_gradients(mfem::Mesh& mesh, const char* tag)  // functional_basic_h1_scalar.cpp:62-91
+{
+  using test_space  = H1<ptest>;
+  using trial_space = H1<ptrial>;
+  mfem::H1_FECollection    test_fec(ptest, dim), trial_fec(ptrial, dim);
+  mfem::FiniteElementSpace test_fes(&mesh, &test_fec), trial_fes(&mesh, &trial_fec);
+  mfem::GridFunction        U_gf(&trial_fes);
+  mfem::FunctionCoefficient x_squared([](const mfem::Vector& x) { return x[0] * x[0]; });
+  U_gf.ProjectCoefficient(x_squared);
+  mfem::Vector U(U_gf);
+  Functional<test_space(trial_space)> residual(&test_fes, {&trial_fes});
+  residual.AddDomainIntegral(Dimension<dim>{}, DependsOn<0>{}, TestThermalModelOne<dim>{}, mesh);
+  residual.AddBoundaryIntegral(Dimension<dim - 1>{}, DependsOn<0>{}, TestThermalModelTwo{}, mesh);
+  std::string what = std::string("thermal_test ") + tag + " <" + std::to_string(ptest) + "," + std::to_string(ptrial) + ">";
+  check_gradient(residual, 0.0, U, what.c_str());
+}
+
 // ---- ShapeAwareFunctional ------------------------------------------------------------------------------------------------
 template <int p>
 void shape_aware(mfem::Element::Type type, const char* tag)
@@ -447,6 +507,19 @@ int main(int argc, char** argv)
     elasticity_gradients<2>(hexes, "hexes");
     elasticity_gradients<1>(tets, "tets");
     elasticity_gradients<2>(tets, "tets");
+  }
+  if (which == "scalar" || which == "all") {  // functional_basic_h1_scalar.cpp:107-118 (2D: boundary integrals on segments)
+    mfem::Mesh quads = make_mesh_2d(mfem::Element::QUADRILATERAL);
+    mfem::Mesh tris  = make_mesh_2d(mfem::Element::TRIANGLE);
+    thermal_gradients<1, 1, 3>(hexes, "hexes");
+    thermal_gradients<1, 1, 2>(tris, "tris");
+    thermal_gradients<1, 1, 3>(tets, "tets");
+    thermal_gradients<1, 1, 2>(quads, "quads");
+    thermal_gradients<2, 1, 2>(quads, "quads");
+    thermal_gradients<2, 1, 2>(tris, "tris");
+    thermal_gradients<2, 1, 3>(hexes, "hexes");
+    thermal_gradients<2, 1, 3>(tets, "tets");
+    thermal_gradients<2, 2, 2>(quads, "quads");
   }
   if (which == "shape" || which == "all") {
     shape_aware<2>(mfem::Element::HEXAHEDRON, "hexes");

@@ -265,7 +265,7 @@ def test_boundary_residual_and_jvps(name):
     mesh_face_table = fo.dof_info(fg, int(prob["mesh_order"]), prob["mesh_face_native_dofs"])
     byvdim = int(prob["mesh_ordering"]) == 1
     nodes_E = fo.gather(mesh_face_table, prob["mesh_nodes"], dim, byvdim)
-    Xv, Xg = fo.interpolate(nodes_E, int(prob["mesh_order"]), q, 2, fg)  # geometric_factors.cpp:140-220
+    Xv, Xg = fo.interpolate(nodes_E, int(prob["mesh_order"]), q, dim - 1, fg)  # geometric_factors.cpp:140-220
     X_q, J_q = Xv, np.transpose(Xg, (0, 2, 1, 3))
     assert rel_l2(X_q, prob["X_q"]) < 1e-14 and rel_l2(J_q, prob["J_q"]) < 1e-14
     qf = fo.make_boundary_qf(str(prob["kind"]), list(prob["params"]))
@@ -303,9 +303,12 @@ def test_boundary_qoi_value(name):
     face_table = fo.dof_info(fg, p, prob["face_native_dofs"])
     mesh_face_table = fo.dof_info(fg, int(prob["mesh_order"]), prob["mesh_face_native_dofs"])
     nodes_E = fo.gather(mesh_face_table, prob["mesh_nodes"], dim, int(prob["mesh_ordering"]) == 1)
-    Xv, Xg = fo.interpolate(nodes_E, int(prob["mesh_order"]), q, 2, fg)
-    val, grad = fo.interpolate(fo.gather(face_table, prob["U"], dim), p, q, 2, fg)
-    n = np.cross(Xg[:, :, 0, :], Xg[:, :, 1, :], axis=1)  # [nf][3][nq]
+    Xv, Xg = fo.interpolate(nodes_E, int(prob["mesh_order"]), q, dim - 1, fg)
+    val, grad = fo.interpolate(fo.gather(face_table, prob["U"], dim), p, q, dim - 1, fg)
+    if dim == 3:
+        n = np.cross(Xg[:, :, 0, :], Xg[:, :, 1, :], axis=1)  # [nf][3][nq]
+    else:  # segment faces: the length of the tangent
+        n = Xg[:, :, 0, :]
     measure = np.linalg.norm(n, axis=1)
     f = a * (1.0 + Xv[:, 0, :]) * np.einsum("ecq,ecq->eq", val, val) + 0.5 * b * np.einsum("ecjq,ecjq->eq", grad, grad)
     q_E = np.einsum("eq,eq,q->e", f, measure, fo._face_weights(fg, q))
