@@ -73,6 +73,7 @@ int sb_restriction_create(const uint64_t* dof_info_host, int64_t num_elements, i
 int sb_restriction_destroy(sb_restriction_t r);
 int64_t sb_restriction_esize(sb_restriction_t r); /* ESize(), F/element_restriction.cpp:421 */
 int64_t sb_restriction_lsize(sb_restriction_t r); /* LSize(), F/element_restriction.cpp:423 */
+int64_t sb_restriction_num_elements(sb_restriction_t r); /* ElementRestriction::num_elements, F/element_restriction.hpp:196 */
 /* device int32 table [num_elements][nodes_per_elem] of scalar node ids (what the fused kernels read) */
 int sb_restriction_table_dev(sb_restriction_t r, const int** table_dev);
 /* Gather L -> E (F/element_restriction.cpp:443-454): E[(e*c + comp)*npe + k] = L[vdof(dof_info(e,k), comp)] */
@@ -255,6 +256,11 @@ int sb_integral_derivative_mask(sb_integral_t I, int wrt);
  * entries, and nothing limits the number of element-matrix entries (the reference hashes every entry,
  * F/dof_numbering.hpp:290-351); nnz < 2^31 as in mfem::SparseMatrix. */
 int     sb_csr_create(sb_restriction_t test, sb_restriction_t trial, sb_csr_t* out);
+/* Meshes of mixed element geometry: BlockElementRestriction keeps one restriction per geometry
+ * (F/element_restriction.cpp:471-536) and lookup_tables.init walks all of them (F/dof_numbering.hpp:290-351): the
+ * pattern is the union over the blocks (tests[b], trials[b]): the restrictions of the two spaces on the elements of
+ * geometry b.  All blocks of a space share its num_nodes, components and ordering. */
+int     sb_csr_create_blocks(int num_blocks, const sb_restriction_t* tests, const sb_restriction_t* trials, sb_csr_t* out);
 /* The same pattern computed on the host from raw restriction tables ([num_elements][npe] node ids): what
  * sb_csr_create runs before uploading, callable without a device (parity tests of the pattern on CPU-only machines).
  * Call with col_ind_host == NULL to get nnz and row_ptr first. */
@@ -307,6 +313,12 @@ int sb_functional_add_integral(sb_functional_t F, sb_integral_t I, const int* tr
  * feeding the integral's i-th trial: dof_info from sb_h1_lexicographic_dof_info(face geometry, p, fes->GetFaceDofs ...). */
 int sb_functional_add_boundary_integral(sb_functional_t F, sb_integral_t I, const int* trial_indices,
                                         sb_restriction_t test_faces, const sb_restriction_t* trial_faces);
+/* An integral on its own block of elements: the elements of ONE geometry of a mixed mesh (the reference keeps a kernel
+ * per geometry, F/integral.hpp:254-257, and a restriction per geometry, F/element_restriction.cpp:471-536).  test_block /
+ * trial_blocks[i]: the restrictions of the test space / of the space feeding the integral's i-th trial on those elements.
+ * sb_functional_assemble then needs a pattern that covers every block (sb_csr_create_blocks). */
+int sb_functional_add_integral_on(sb_functional_t F, sb_integral_t I, const int* trial_indices,
+                                  sb_restriction_t test_block, const sb_restriction_t* trial_blocks);
 /* operator()(t, args...) (F/functional.hpp:446-513).  inputs: one L-vector per trial space.  *_on_host:
  *   SB_DEVICE (0)      device pointers, work is enqueued on `stream`
  *   SB_HOST_SYNC (1)   host buffers, copied to / from the device inside the call; the result is valid on return

@@ -49,6 +49,7 @@ SIGNATURES = {
     "sb_restriction_destroy": (_i, [_vp]),
     "sb_restriction_esize": (_i64, [_vp]),
     "sb_restriction_lsize": (_i64, [_vp]),
+    "sb_restriction_num_elements": (_i64, [_vp]),
     "sb_restriction_table_dev": (_i, [_vp, _pp]),
     "sb_restriction_gather": (_i, [_vp, _vp, _vp, _vp]),
     "sb_restriction_scatter_add": (_i, [_vp, _vp, _vp, _vp]),
@@ -71,6 +72,7 @@ SIGNATURES = {
     "sb_integral_derivative_entries": (_i, [_vp, _i]),
     "sb_integral_derivative_mask": (_i, [_vp, _i]),
     "sb_csr_create": (_i, [_vp, _vp, _pp]),
+    "sb_csr_create_blocks": (_i, [_i, _vp, _vp, _pp]),
     "sb_csr_pattern_host": (_i, [_vp, _i, _i, _i64, _i, _vp, _i, _i, _i64, _i, _i64, _vp, _vp, C.POINTER(_i64)]),
     "sb_debug_assembly_plan_host": (_i, [_vp, _i, _i, _i64, _i, _vp, _i, _i, _i64, _i, _i64, _vp, _i64, _i, _i, _vp, _vp,
                                         _vp, C.POINTER(_i)]),
@@ -84,6 +86,7 @@ SIGNATURES = {
     "sb_csr_accumulate": (_i, [_vp, _vp, _vp, _vp, _vp, _vp]),
     "sb_functional_create": (_i, [_vp, _i, _pp, _pp]),
     "sb_functional_add_boundary_integral": (_i, [_vp, _vp, _vp, _vp, _pp]),
+    "sb_functional_add_integral_on": (_i, [_vp, _vp, _vp, _vp, _pp]),
     "sb_functional_destroy": (_i, [_vp]),
     "sb_functional_add_integral": (_i, [_vp, _vp, _vp]),
     "sb_functional_evaluate": (_i, [_vp, _d, _i, _pp, _i, _vp, _i, _i, _vp]),
@@ -370,9 +373,16 @@ class CsrPattern:
     """Mirror of GradientAssemblyLookupTables (dof_numbering.hpp:253-380)."""
 
     def __init__(self, test, trial, handle=None):
+        """test / trial: one ElementRestriction each, or -- meshes of mixed element geometry -- equally long lists with
+        one restriction per geometry (BlockElementRestriction, element_restriction.cpp:471-536)"""
         if handle is None:
             handle = C.c_void_p()
-            check(lib().sb_csr_create(test.h, trial.h, C.byref(handle)))
+            if isinstance(test, (list, tuple)):
+                ta = (C.c_void_p * len(test))(*[r.h for r in test])
+                ka = (C.c_void_p * len(trial))(*[r.h for r in trial])
+                check(lib().sb_csr_create_blocks(len(test), ta, ka, C.byref(handle)))
+            else:
+                check(lib().sb_csr_create(test.h, trial.h, C.byref(handle)))
         self.h = handle
         self._keep = (test, trial)  # the pattern refers to the restrictions it was built from
         self.nnz = lib().sb_csr_nnz(self.h)
@@ -468,6 +478,16 @@ class Functional:
         self.integrals.append(integral)
         self._keep = getattr(self, "_keep", []) + [test_faces, list(trial_faces)]
 
+    def AddDomainIntegralOn(self, integral, depends_on, test_block, trial_blocks):
+        """an integral on the elements of ONE geometry of a mixed mesh (integral.hpp:254-257): test_block / trial_blocks[i]
+        are the restrictions of the spaces on those elements; assemble() then builds its pattern over every block"""
+        idx = np.ascontiguousarray(depends_on, dtype=np.int32)
+        arr = (C.c_void_p * len(trial_blocks))(*[r.h for r in trial_blocks])
+        check(lib().sb_functional_add_integral_on(self.h, integral.h, _np_ptr(idx), test_block.h, arr))
+        self.integrals.append(integral)
+        self._keep = getattr(self, "_keep", []) + [test_block, list(trial_blocks)]
+        self._blocks = getattr(self, "_blocks", []) + [(test_block, list(depends_on), list(trial_blocks))]
+
     def wait(self):
         """results of asynchronous host-buffer calls are valid after this"""
         check(lib().sb_functional_wait(self.h))
@@ -528,7 +548,14 @@ class Functional:
         """-> (CsrPattern, values): the local CSR triple the reference wraps in mfem::SparseMatrix (functional.hpp:649)."""
         import torch
         if wrt not in self._csr:
-            self._csr[wrt] = CsrPattern(self.test, self.trials[wrt])
+            blocks = [(t, ks[dep.index(wrt)]) for (t, dep, ks) in getattr(self, "_blocks", []) if wrt in dep]
+            if blocks:  # mixed geometries: the pattern is the union over the per-geometry blocks
+                has_plain = len(self.integrals) > len(getattr(self, "_blocks", []))
+                tests = ([self.test] if has_plain else []) + [b[0] for b in blocks]
+                trials = ([self.trials[wrt]] if has_plain else []) + [b[1] for b in blocks]
+                self._csr[wrt] = CsrPattern(tests, trials)
+            else:
+                self._csr[wrt] = CsrPattern(self.test, self.trials[wrt])
         pat = self._csr[wrt]
         hp = C.c_void_p(pat.h.value)
         if on_host:

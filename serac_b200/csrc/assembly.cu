@@ -83,19 +83,34 @@ Incidence build_incidence(const int* table, int npe, int64_t num_nodes, const in
   return inc;
 }
 
+/// one block of a pair of BlockElementRestrictions: the tables of the two spaces on the elements of one geometry
+struct PatternBlock {
+  const int* test_table;
+  int        npe_t;
+  const int* trial_table;
+  int        npe_k;
+  int64_t    ne;
+};
+
 /// F/dof_numbering.hpp:290-351 at node level: row n = sorted unique trial nodes of the elements that contain test node n
-void build_node_pattern(const int* test_table, int npe_t, int64_t num_test_nodes, const int* trial_table, int npe_k,
-                        int64_t ne, std::vector<int64_t>& row_ptr, std::vector<int>& cols)
+/// (over every block: meshes of mixed element geometry have one block per geometry)
+void build_node_pattern(const std::vector<PatternBlock>& blocks, int64_t num_test_nodes, std::vector<int64_t>& row_ptr,
+                        std::vector<int>& cols)
 {
-  const Incidence inc = build_incidence(test_table, npe_t, num_test_nodes, nullptr, ne);
+  std::vector<Incidence> incs;
+  for (const PatternBlock& b : blocks) incs.push_back(build_incidence(b.test_table, b.npe_t, num_test_nodes, nullptr, b.ne));
   row_ptr.assign(size_t(num_test_nodes) + 1, 0);
   // pass 1: row lengths, pass 2: fill (each row sorted + uniqued in a thread-local buffer)
   auto row_of = [&](int64_t n, std::vector<int>& buf) {
     buf.clear();
-    for (int64_t s = inc.off[size_t(n)]; s < inc.off[size_t(n) + 1]; s++) {
-      const int64_t e = inc.pos[size_t(s)];
-      if (s > inc.off[size_t(n)] && inc.pos[size_t(s) - 1] == e) continue;  // node repeated inside one element
-      buf.insert(buf.end(), trial_table + e * npe_k, trial_table + (e + 1) * npe_k);
+    for (size_t b = 0; b < blocks.size(); b++) {
+      const Incidence&    inc = incs[b];
+      const PatternBlock& B   = blocks[b];
+      for (int64_t s = inc.off[size_t(n)]; s < inc.off[size_t(n) + 1]; s++) {
+        const int64_t e = inc.pos[size_t(s)];
+        if (s > inc.off[size_t(n)] && inc.pos[size_t(s) - 1] == e) continue;  // node repeated inside one element
+        buf.insert(buf.end(), B.trial_table + e * B.npe_k, B.trial_table + (e + 1) * B.npe_k);
+      }
     }
     std::sort(buf.begin(), buf.end());
     buf.erase(std::unique(buf.begin(), buf.end()), buf.end());
@@ -116,6 +131,12 @@ void build_node_pattern(const int* test_table, int npe_t, int64_t num_test_nodes
       std::copy(buf.begin(), buf.end(), cols.begin() + row_ptr[size_t(n)]);
     }
   });
+}
+
+void build_node_pattern(const int* test_table, int npe_t, int64_t num_test_nodes, const int* trial_table, int npe_k,
+                        int64_t ne, std::vector<int64_t>& row_ptr, std::vector<int>& cols)
+{
+  build_node_pattern({PatternBlock{test_table, npe_t, trial_table, npe_k, ne}}, num_test_nodes, row_ptr, cols);
 }
 
 /// expansion of the node pattern by components: where each vdof row starts and which column sits at position j of it
@@ -364,10 +385,21 @@ __global__ void expand_pattern_kernel(const long long* __restrict__ nrp, const i
   }
 }
 
-extern "C" int sb_csr_create(sb_restriction_t test, sb_restriction_t trial, sb_csr_t* out)
+extern "C" int sb_csr_create_blocks(int num_blocks, const sb_restriction_t* tests, const sb_restriction_t* trials,
+                                    sb_csr_t* out)
 {
-  SB_REQUIRE(test && trial && out, "sb_csr_create: NULL argument");
-  SB_REQUIRE(test->num_elements == trial->num_elements, "sb_csr_create: element counts differ");
+  SB_REQUIRE(num_blocks >= 1 && tests && trials && out, "sb_csr_create_blocks: bad arguments");
+  sb_restriction_t test = tests[0], trial = trials[0];
+  SB_REQUIRE(test && trial, "sb_csr_create: NULL argument");
+  std::vector<PatternBlock> blocks;
+  for (int b = 0; b < num_blocks; b++) {
+    sb_restriction_t t = tests[b], k = trials[b];
+    SB_REQUIRE(t && k && t->num_elements == k->num_elements, "sb_csr_create: element counts differ");
+    SB_REQUIRE(t->num_nodes == test->num_nodes && t->components == test->components && t->ordering == test->ordering &&
+                   k->num_nodes == trial->num_nodes && k->components == trial->components && k->ordering == trial->ordering,
+               "sb_csr_create_blocks: the blocks must belong to the same pair of spaces");
+    blocks.push_back(PatternBlock{t->table_host.data(), t->npe, k->table_host.data(), k->npe, t->num_elements});
+  }
   auto A      = std::make_unique<sb_csr_s>();
   A->num_rows = sb_restriction_lsize(test);
   A->num_cols = sb_restriction_lsize(trial);
@@ -376,8 +408,7 @@ extern "C" int sb_csr_create(sb_restriction_t test, sb_restriction_t trial, sb_c
   A->test_ordering = test->ordering, A->trial_ordering = trial->ordering;
   A->num_test_nodes = test->num_nodes, A->num_trial_nodes = trial->num_nodes;
   A->test = test, A->trial = trial;
-  build_node_pattern(test->table_host.data(), test->npe, test->num_nodes, trial->table_host.data(), trial->npe,
-                     test->num_elements, A->node_row_ptr, A->node_cols);
+  build_node_pattern(blocks, test->num_nodes, A->node_row_ptr, A->node_cols);
   Expansion X{A->ct, A->ck, test->ordering == SB_ORDERING_BYVDIM, trial->ordering == SB_ORDERING_BYVDIM,
               test->num_nodes, trial->num_nodes, A->node_row_ptr[size_t(test->num_nodes)]};
   A->nnz = X.nnz_nodes * A->ct * A->ck;
@@ -399,6 +430,12 @@ extern "C" int sb_csr_create(sb_restriction_t test, sb_restriction_t trial, sb_c
   }
   *out = A.release();
   return SB_OK;
+}
+
+extern "C" int sb_csr_create(sb_restriction_t test, sb_restriction_t trial, sb_csr_t* out)
+{
+  SB_REQUIRE(test && trial && out, "sb_csr_create: NULL argument");
+  return sb_csr_create_blocks(1, &test, &trial, out);
 }
 
 static void free_plan(AssemblyPlan& P)

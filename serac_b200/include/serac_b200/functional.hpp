@@ -109,8 +109,19 @@ class Vector {
   double* d_ = nullptr;
 };
 
+/// the elements (or boundary faces) of one further geometry of a mesh of mixed element geometry: the reference keeps a
+/// restriction per geometry (BlockElementRestriction, element_restriction.cpp:471-536) and a kernel per geometry
+/// (integral.hpp:254-257)
+struct GeometryBlock {
+  Geometry         geometry;
+  std::vector<int> ids;          ///< mesh element (boundary face) index of every entry, ascending
+  std::vector<int> native_dofs;  ///< [ids.size()][nodes per element], mfem's native order
+};
+
 /// what Functional reads from an mfem::ParFiniteElementSpace: H1 order, vdim, ordering, GetNDofs() and, per element,
-/// fes->GetElementDofs(e) in mfem's native order (single-geometry meshes)
+/// fes->GetElementDofs(e) in mfem's native order.  Single-geometry meshes fill the fields below; on meshes of mixed
+/// element geometry they describe the elements of the FIRST geometry (`element_ids` = their mesh indices) and
+/// `more_elements` the others; likewise for the boundary faces.
 struct FiniteElementSpace {
   Geometry         geometry;
   int              order;
@@ -124,6 +135,17 @@ struct FiniteElementSpace {
   std::vector<int> native_boundary_face_dofs;  ///< [num_boundary_faces][nodes per face]
   Family           family = Family::H1;  ///< H1, or L2 (discontinuous: mfem hands out its element dofs in lexicographic order)
   int64_t          GetVSize() const { return num_nodes * vdim; }
+  /// mixed meshes only
+  std::vector<int>           element_ids;  ///< mesh index of every element of `geometry` (empty: all elements, in order)
+  std::vector<GeometryBlock> more_elements;
+  Geometry                   boundary_face_geometry = Geometry::POINT;  ///< POINT: the face geometry of `geometry`
+  std::vector<GeometryBlock> more_boundary_faces;
+  int64_t                    total_elements() const
+  {
+    int64_t n = num_elements;
+    for (const auto& b : more_elements) n += int64_t(b.ids.size());
+    return n;
+  }
 };
 
 /// what Functional reads from an mfem::Mesh: the nodal grid function (Functional demands nodes, functional.hpp:74-89)
@@ -131,7 +153,7 @@ struct Mesh {
   FiniteElementSpace  nodes_space;  ///< vdim == space dimension
   std::vector<double> nodes;        ///< L-vector of node coordinates in nodes_space's ordering
   int                 Dimension() const { return dimension_of(nodes_space.geometry); }
-  int64_t             GetNE() const { return nodes_space.num_elements; }
+  int64_t             GetNE() const { return nodes_space.total_elements(); }
 };
 
 /// a set of elements of one mesh (domain.hpp); EntireDomain(mesh) = all of them
@@ -224,6 +246,24 @@ class Functional<test(trials...)> {
         if (trial_fes[size_t(j)] == trial_fes[size_t(i)]) G_trial_[size_t(i)] = G_trial_[size_t(j)];
       if (!G_trial_[size_t(i)]) G_trial_[size_t(i)] = make_restriction(*trial_fes[size_t(i)]);
     }
+    // meshes of mixed element geometry: one more restriction per space and further geometry
+    for (size_t b = 0; b < test_fes->more_elements.size(); b++) {
+      G_test_more_.push_back(make_block_restriction(*test_fes, test_fes->more_elements[b]));
+      std::array<sb_restriction_t, num_trial_spaces> row{};
+      for (int i = 0; i < num_trial_spaces; i++) {
+        const FiniteElementSpace& k = *trial_fes[size_t(i)];
+        if (k.more_elements.size() != test_fes->more_elements.size() ||
+            k.more_elements[b].geometry != test_fes->more_elements[b].geometry ||
+            k.more_elements[b].ids.size() != test_fes->more_elements[b].ids.size())
+          fail("Functional: the spaces do not live on the same (mixed) mesh");
+        row[size_t(i)] = nullptr;
+        if (trial_fes[size_t(i)] == test_fes) row[size_t(i)] = G_test_more_.back();
+        for (int j = 0; j < i; j++)
+          if (trial_fes[size_t(j)] == trial_fes[size_t(i)]) row[size_t(i)] = row[size_t(j)];
+        if (!row[size_t(i)]) row[size_t(i)] = make_block_restriction(k, k.more_elements[b]);
+      }
+      G_trial_more_.push_back(row);
+    }
     SERAC_B200_CHECK(sb_functional_create(G_test_, num_trial_spaces, G_trial_.data(), &F_));
     output_L_.SetSize(test_fes->GetVSize());
     grad_.reserve(size_t(num_trial_spaces));
@@ -244,6 +284,9 @@ class Functional<test(trials...)> {
     };
     release(G_test_);
     for (auto r : G_trial_) release(r);
+    for (auto r : G_test_more_) release(r);
+    for (auto& row : G_trial_more_)
+      for (auto r : row) release(r);
     for (auto r : mesh_restrictions_) release(r);
     for (auto p : device_buffers_) cudaFree(p);
   }
@@ -261,6 +304,22 @@ class Functional<test(trials...)> {
     if (mesh.Dimension() != dim) fail("AddDomainIntegral: Dimension<dim> does not match the mesh");
     const Geometry g = mesh.nodes_space.geometry;
     if (g != test_space_->geometry) fail("AddDomainIntegral: mesh and test space geometries differ");
+    if (!mesh.nodes_space.more_elements.empty()) {  // one integral per geometry (integral.hpp:254-257)
+      if constexpr (!std::is_same_v<StateType, Nothing> && !std::is_empty_v<StateType>)
+        fail("AddDomainIntegral: quadrature-point state on meshes of mixed element geometry is not supported");
+      add_domain_integral_block<dim, Integrand, StateType, args...>(integrand, domain, mesh.nodes_space.geometry,
+                                                                    mesh.nodes_space.element_ids, make_restriction(mesh.nodes_space),
+                                                                    G_test_, G_trial_);
+      for (size_t b = 0; b < mesh.nodes_space.more_elements.size(); b++) {
+        const GeometryBlock& blk = mesh.nodes_space.more_elements[b];
+        if (b >= G_test_more_.size() || blk.geometry != test_space_->more_elements[b].geometry)
+          fail("AddDomainIntegral: mesh and test space geometries differ");
+        add_domain_integral_block<dim, Integrand, StateType, args...>(integrand, domain, blk.geometry, blk.ids,
+                                                                      make_block_restriction(mesh.nodes_space, blk),
+                                                                      G_test_more_[b], G_trial_more_[b]);
+      }
+      return;
+    }
     const sb_kernel_table* table = nullptr;
     // the reference instantiates the kernels of every geometry of this dimension (functional.hpp:296-317)
     if constexpr (dim == 3) {
@@ -308,7 +367,14 @@ class Functional<test(trials...)> {
     static_assert(((args >= 0 && args < num_trial_spaces) && ...), "DependsOn<> index out of range");
     if (mesh.Dimension() != dim + 1) fail("AddBoundaryIntegral: Dimension<dim> must be the mesh dimension - 1");
     const Geometry g  = mesh.nodes_space.geometry;
-    const Geometry fg = (dim == 1) ? Geometry::SEGMENT : (g == Geometry::CUBE) ? Geometry::SQUARE : Geometry::TRIANGLE;
+    Geometry fg = (dim == 1) ? Geometry::SEGMENT : (g == Geometry::CUBE) ? Geometry::SQUARE : Geometry::TRIANGLE;
+    if (mesh.nodes_space.boundary_face_geometry != Geometry::POINT) fg = mesh.nodes_space.boundary_face_geometry;
+    if (!mesh.nodes_space.more_boundary_faces.empty()) {  // triangular and quadrilateral faces of a mixed 3D mesh
+      add_boundary_integral_block<dim, Integrand, args...>(integrand, mesh, fg, nullptr);
+      for (size_t b = 0; b < mesh.nodes_space.more_boundary_faces.size(); b++)
+        add_boundary_integral_block<dim, Integrand, args...>(integrand, mesh, mesh.nodes_space.more_boundary_faces[b].geometry, &b);
+      return;
+    }
     const sb_kernel_table* table = nullptr;
     if constexpr (dim == 2) {
       if (fg == Geometry::SQUARE) table = boundary_table_for<Geometry::SQUARE, Integrand, args...>();
@@ -406,8 +472,16 @@ class Functional<test(trials...)> {
       Functional& f = form_;
       const int   w = which_argument_;
       if (f.csr_.size() < size_t(num_trial_spaces)) f.csr_.resize(size_t(num_trial_spaces), nullptr);
-      if (!f.csr_[size_t(w)])
-        SERAC_B200_CHECK(sb_csr_create(f.G_test_, f.G_trial_[size_t(w)], &f.csr_[size_t(w)]));
+      if (!f.csr_[size_t(w)]) {
+        // one block per element geometry of the mesh (BlockElementRestriction, element_restriction.cpp:471-536)
+        std::vector<sb_restriction_t> row_blocks{f.G_test_}, col_blocks{f.G_trial_[size_t(w)]};
+        for (size_t b = 0; b < f.G_test_more_.size(); b++) {
+          row_blocks.push_back(f.G_test_more_[b]);
+          col_blocks.push_back(f.G_trial_more_[b][size_t(w)]);
+        }
+        SERAC_B200_CHECK(sb_csr_create_blocks(int(row_blocks.size()), row_blocks.data(), col_blocks.data(),
+                                              &f.csr_[size_t(w)]));
+      }
       return f.csr_[size_t(w)];
     }
     /// the values of the assembled matrix into a device array of sb_csr_nnz(pattern) doubles (serac_b200/solvers.hpp)
@@ -527,6 +601,116 @@ class Functional<test(trials...)> {
     return r;
   }
 
+  /// the restriction of a space on the elements of one further geometry of a mixed mesh
+  static sb_restriction_t make_block_restriction(const FiniteElementSpace& fes, const GeometryBlock& blk)
+  {
+    FiniteElementSpace view{};
+    view.geometry            = blk.geometry;
+    view.order               = fes.order;
+    view.vdim                = fes.vdim;
+    view.ordering            = fes.ordering;
+    view.num_nodes           = fes.num_nodes;
+    view.num_elements        = int64_t(blk.ids.size());
+    view.native_element_dofs = blk.native_dofs;
+    view.family              = fes.family;
+    return make_restriction(view);
+  }
+
+  /// the domain integral on the elements of ONE geometry of a mixed mesh: `ids` = their mesh indices (empty: identity)
+  template <int dim, typename Integrand, typename StateType, int... args>
+  void add_domain_integral_block(const Integrand& integrand, const Domain& domain, Geometry g, const std::vector<int>& ids,
+                                 sb_restriction_t G_mesh, sb_restriction_t test_block,
+                                 const std::array<sb_restriction_t, num_trial_spaces>& trial_blocks)
+  {
+    mesh_restrictions_.push_back(G_mesh);
+    const Mesh&            mesh  = *domain.mesh;
+    const sb_kernel_table* table = nullptr;
+    if constexpr (dim == 3) {
+      if (g == Geometry::CUBE) table = table_for<Geometry::CUBE, Integrand, StateType, args...>();
+      if (g == Geometry::TETRAHEDRON) table = table_for<Geometry::TETRAHEDRON, Integrand, StateType, args...>();
+    } else if constexpr (dim == 2) {
+      if (g == Geometry::SQUARE) table = table_for<Geometry::SQUARE, Integrand, StateType, args...>();
+      if (g == Geometry::TRIANGLE) table = table_for<Geometry::TRIANGLE, Integrand, StateType, args...>();
+    }
+    if (!table) fail("AddDomainIntegral: unsupported element geometry");
+    // the domain's elements of this geometry, as positions in the block (domain.hpp: one list per geometry)
+    const int64_t    nblock = sb_restriction_num_elements(test_block);
+    std::vector<int> local;
+    if (!domain.entire) {
+      for (int e : domain.elements) {
+        if (ids.empty()) {
+          local.push_back(e);
+        } else {
+          auto it = std::lower_bound(ids.begin(), ids.end(), e);
+          if (it != ids.end() && *it == e) local.push_back(int(it - ids.begin()));
+        }
+      }
+    }
+    const int64_t ne = domain.entire ? nblock : int64_t(local.size());
+    if (ne == 0) return;
+    const int nq        = num_quadrature_points(g, Q);
+    double*   nodes_dev = device_copy(mesh.nodes.data(), mesh.nodes.size());
+    int*      elems_dev = domain.entire ? nullptr : device_copy(local.data(), local.size());
+    double*   X_q       = device_alloc<double>(size_t(ne) * size_t(dim) * size_t(nq));
+    double*   J_q       = device_alloc<double>(size_t(ne) * size_t(dim) * size_t(dim) * size_t(nq));
+    SERAC_B200_CHECK(sb_geometric_factors(int(g), mesh.nodes_space.order, Q, G_mesh, nodes_dev, elems_dev, ne, X_q, J_q,
+                                          nullptr));
+    sb_integral_t I = nullptr;
+    SERAC_B200_CHECK(sb_integral_create(table, &integrand, domain.entire ? nullptr : local.data(), ne, X_q, J_q, &I));
+    const int        which[] = {args..., 0};
+    sb_restriction_t trial_r[sizeof...(args) + 1];
+    for (size_t i = 0; i < sizeof...(args); i++) trial_r[i] = trial_blocks[size_t(which[i])];
+    SERAC_B200_CHECK(sb_functional_add_integral_on(F_, I, which, test_block, trial_r));
+    integrals_.push_back(I);
+  }
+
+  /// the boundary integral on the faces of ONE geometry (which == nullptr: the first, else more_boundary_faces[*which])
+  template <int dim, typename Integrand, int... args>
+  void add_boundary_integral_block(const Integrand& integrand, const Mesh& mesh, Geometry fg, const size_t* which_block)
+  {
+    const sb_kernel_table* table = nullptr;
+    if constexpr (dim == 2) {
+      if (fg == Geometry::SQUARE) table = boundary_table_for<Geometry::SQUARE, Integrand, args...>();
+      if (fg == Geometry::TRIANGLE) table = boundary_table_for<Geometry::TRIANGLE, Integrand, args...>();
+    } else {
+      table = boundary_table_for<Geometry::SEGMENT, Integrand, args...>();
+    }
+    if (!table) fail("AddBoundaryIntegral: unsupported face geometry");
+    auto faces_of = [&](const FiniteElementSpace& fes) {
+      if (!which_block) return make_face_restriction(fes, fg);
+      if (*which_block >= fes.more_boundary_faces.size()) fail("AddBoundaryIntegral: a space lacks a boundary-face block");
+      const GeometryBlock& blk = fes.more_boundary_faces[*which_block];
+      FiniteElementSpace   view{};
+      view.geometry = fes.geometry, view.order = fes.order, view.vdim = fes.vdim, view.ordering = fes.ordering;
+      view.num_nodes = fes.num_nodes, view.family = fes.family;
+      view.num_boundary_faces        = int64_t(blk.ids.size());
+      view.native_boundary_face_dofs = blk.native_dofs;
+      return make_face_restriction(view, fg);
+    };
+    sb_restriction_t G_mesh = faces_of(mesh.nodes_space);
+    mesh_restrictions_.push_back(G_mesh);
+    const int64_t nf = sb_restriction_num_elements(G_mesh);
+    if (nf == 0) return;
+    const int nq        = num_quadrature_points(fg, Q);
+    double*   nodes_dev = device_copy(mesh.nodes.data(), mesh.nodes.size());
+    double*   X_q       = device_alloc<double>(size_t(nf) * size_t(dim + 1) * size_t(nq));
+    double*   J_q       = device_alloc<double>(size_t(nf) * size_t(dim) * size_t(dim + 1) * size_t(nq));
+    SERAC_B200_CHECK(sb_geometric_factors(int(fg), mesh.nodes_space.order, Q, G_mesh, nodes_dev, nullptr, nf, X_q, J_q,
+                                          nullptr));
+    sb_integral_t I = nullptr;
+    SERAC_B200_CHECK(sb_integral_create(table, &integrand, nullptr, nf, X_q, J_q, &I));
+    sb_restriction_t test_faces = faces_of(*test_space_);
+    mesh_restrictions_.push_back(test_faces);
+    const int        which[] = {args..., 0};
+    sb_restriction_t trial_faces[sizeof...(args) + 1];
+    for (size_t i = 0; i < sizeof...(args); i++) {
+      trial_faces[i] = faces_of(*trial_space_[size_t(which[i])]);
+      mesh_restrictions_.push_back(trial_faces[i]);
+    }
+    SERAC_B200_CHECK(sb_functional_add_boundary_integral(F_, I, which, test_faces, trial_faces));
+    integrals_.push_back(I);
+  }
+
   template <typename T>
   T* device_alloc(size_t n)
   {
@@ -547,6 +731,8 @@ class Functional<test(trials...)> {
   std::array<const FiniteElementSpace*, num_trial_spaces> trial_space_;
   sb_restriction_t                                         G_test_ = nullptr;
   std::array<sb_restriction_t, num_trial_spaces>           G_trial_{};
+  std::vector<sb_restriction_t>                            G_test_more_;   ///< mixed meshes: the further geometries
+  std::vector<std::array<sb_restriction_t, num_trial_spaces>> G_trial_more_;
   sb_functional_t                                          F_ = nullptr;
   std::vector<sb_integral_t>                               integrals_;
   std::vector<sb_restriction_t>                            mesh_restrictions_;

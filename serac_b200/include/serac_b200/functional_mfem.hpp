@@ -100,14 +100,15 @@ inline core_api::FiniteElementSpace convert_space(const mfem::FiniteElementSpace
     std::fprintf(stderr, "serac::Functional: empty mesh\n");
     std::abort();
   }
-  const auto g0 = mesh.GetElementGeometry(0);
+  // the geometries of the mesh in mfem::Geometry order, as BlockElementRestriction walks them
+  // (element_restriction.cpp:471-536); the first one fills the space's own fields, the others its `more_elements`
+  std::vector<mfem::Geometry::Type> geoms;
   for (int e = 0; e < mesh.GetNE(); e++) {
-    if (mesh.GetElementGeometry(e) != g0) {
-      // the reference dispatches per geometry (integral.hpp:254-257, element_restriction.cpp:471-536)
-      std::fprintf(stderr, "serac::Functional (serac_b200): meshes of mixed element geometry are not supported\n");
-      std::abort();
-    }
+    const auto g = mesh.GetElementGeometry(e);
+    if (std::find(geoms.begin(), geoms.end(), g) == geoms.end()) geoms.push_back(g);
   }
+  std::sort(geoms.begin(), geoms.end());
+  const auto g0 = geoms[0];
   core_api::FiniteElementSpace out{};
   out.geometry     = geometry_of(g0);
   out.family       = dynamic_cast<const mfem::L2_FECollection*>(fes.FEColl()) ? Family::L2 : Family::H1;
@@ -115,17 +116,42 @@ inline core_api::FiniteElementSpace convert_space(const mfem::FiniteElementSpace
   out.vdim         = fes.GetVDim();
   out.ordering     = (fes.GetOrdering() == mfem::Ordering::byVDIM) ? core_api::Ordering::byVDIM : core_api::Ordering::byNODES;
   out.num_nodes    = fes.GetNDofs();
-  out.num_elements = mesh.GetNE();
+  out.num_elements = 0;
+  for (size_t b = 1; b < geoms.size(); b++) out.more_elements.push_back(core_api::GeometryBlock{geometry_of(geoms[b]), {}, {}});
   mfem::Array<int> dofs;
   for (int e = 0; e < mesh.GetNE(); e++) {
     fes.GetElementDofs(e, dofs);
-    for (int i = 0; i < dofs.Size(); i++) out.native_element_dofs.push_back(dofs[i] >= 0 ? dofs[i] : -1 - dofs[i]);
+    const size_t      b   = size_t(std::find(geoms.begin(), geoms.end(), mesh.GetElementGeometry(e)) - geoms.begin());
+    std::vector<int>& dst = (b == 0) ? out.native_element_dofs : out.more_elements[b - 1].native_dofs;
+    for (int i = 0; i < dofs.Size(); i++) dst.push_back(dofs[i] >= 0 ? dofs[i] : -1 - dofs[i]);
+    if (b == 0) {
+      out.num_elements++;
+      if (geoms.size() > 1) out.element_ids.push_back(e);
+    } else {
+      out.more_elements[b - 1].ids.push_back(e);
+    }
   }
+  // boundary faces, one block per face geometry (FaceType::BOUNDARY restrictions, element_restriction.cpp:279-388)
+  std::vector<mfem::Geometry::Type> fgeoms;
+  for (int f = 0; f < mesh.GetNumFaces(); f++) {
+    if (!mesh.GetFaceInformation(f).IsBoundary()) continue;
+    const auto g = mesh.GetFaceGeometry(f);
+    if (std::find(fgeoms.begin(), fgeoms.end(), g) == fgeoms.end()) fgeoms.push_back(g);
+  }
+  std::sort(fgeoms.begin(), fgeoms.end());
+  if (!fgeoms.empty()) out.boundary_face_geometry = geometry_of(fgeoms[0]);
+  for (size_t b = 1; b < fgeoms.size(); b++)
+    out.more_boundary_faces.push_back(core_api::GeometryBlock{geometry_of(fgeoms[b]), {}, {}});
   for (int f = 0; f < mesh.GetNumFaces(); f++) {
     if (!mesh.GetFaceInformation(f).IsBoundary()) continue;
     fes.GetFaceDofs(f, dofs);
-    for (int i = 0; i < dofs.Size(); i++) out.native_boundary_face_dofs.push_back(dofs[i] >= 0 ? dofs[i] : -1 - dofs[i]);
-    out.num_boundary_faces++;
+    const size_t      b   = size_t(std::find(fgeoms.begin(), fgeoms.end(), mesh.GetFaceGeometry(f)) - fgeoms.begin());
+    std::vector<int>& dst = (b == 0) ? out.native_boundary_face_dofs : out.more_boundary_faces[b - 1].native_dofs;
+    for (int i = 0; i < dofs.Size(); i++) dst.push_back(dofs[i] >= 0 ? dofs[i] : -1 - dofs[i]);
+    if (b == 0)
+      out.num_boundary_faces++;
+    else
+      out.more_boundary_faces[b - 1].ids.push_back(f);
   }
   return out;
 }

@@ -160,6 +160,45 @@ mfem::Mesh make_mesh_2d(mfem::Element::Type type, int n = 3)
   return mesh;
 }
 
+/// quadrilaterals below, triangles above (conforming), like the reference's patch2D_tris_and_quads.mesh
+mfem::Mesh make_mixed_mesh_2d()
+{
+  mfem::Mesh mesh(2, 9, 6, 8);
+  for (int j = 0; j < 3; j++)
+    for (int i = 0; i < 3; i++) {
+      const bool centre = (i == 1 && j == 1);
+      mesh.AddVertex(0.6 * i + (centre ? 0.07 : 0.0) + 0.03 * j * i, 0.5 * j - (centre ? 0.04 : 0.0) + 0.02 * i * i);
+    }
+  mesh.AddQuad(0, 1, 4, 3);
+  mesh.AddQuad(1, 2, 5, 4);
+  mesh.AddTriangle(3, 4, 7);
+  mesh.AddTriangle(3, 7, 6);
+  mesh.AddTriangle(4, 5, 8);
+  mesh.AddTriangle(4, 8, 7);
+  const int bdr[8][2] = {{0, 1}, {1, 2}, {2, 5}, {5, 8}, {8, 7}, {7, 6}, {6, 3}, {3, 0}};
+  for (int b = 0; b < 8; b++) mesh.AddBdrSegment(bdr[b][0], bdr[b][1], 1 + b / 2);
+  mesh.FinalizeMesh();
+  mesh.EnsureNodes();
+  return mesh;
+}
+
+/// a patch of tetrahedra next to a patch of hexahedra (two pieces of one mesh, as in the reference's
+/// patch3D_tets_and_hexes.mesh): triangular and quadrilateral boundary faces
+mfem::Mesh make_mixed_mesh_3d()
+{
+  mfem::Mesh tets  = mfem::Mesh::MakeCartesian3D(1, 1, 1, mfem::Element::TETRAHEDRON, 1.0, 1.1, 0.9);
+  mfem::Mesh hexes = mfem::Mesh::MakeCartesian3D(2, 1, 1, mfem::Element::HEXAHEDRON, 1.0, 1.2, 0.8);
+  hexes.Transform([](const mfem::Vector& x, mfem::Vector& y) {
+    y    = x;
+    y(0) = x(0) + 2.0 + 0.05 * x(1) * x(2);
+    y(2) = x(2) + 0.04 * x(0) * x(1);
+  });
+  mfem::Mesh* pieces[] = {&tets, &hexes};
+  mfem::Mesh  mesh(pieces, 2);
+  mesh.EnsureNodes();
+  return mesh;
+}
+
 double rel(const mfem::Vector& x, const mfem::Vector& y)
 {
   mfem::Vector d(x);
@@ -250,6 +289,70 @@ struct L2SourceFunctor {  // functional_comparison_L2.cpp:40-54 (a = 1.7, b = 0)
     return serac::tuple{source, flux};
   }
 };
+
+// the same comparison on a mesh of mixed element geometry: MFEM's integrators run element by element with the rule of
+// each element's geometry (serac's rules: Q = p + 1 Gauss points per direction / the simplex rule of the same degree)
+template <int p, int dim>
+void thermal_comparison_mixed(mfem::Mesh& mesh, const char* tag)
+{
+  mfem::H1_FECollection    fec(p, dim);
+  mfem::FiniteElementSpace fes(&mesh, &fec);
+  const int                n = fes.GetVSize();
+  mfem::SparseMatrix        A(n, n);
+  mfem::Vector              f(n);
+  f = 0.0;
+  mfem::ConstantCoefficient a_coef(a), b_coef(b);
+  mfem::FunctionCoefficient load_func([](const mfem::Vector& c) { return 100 * c(0) * c(1); });
+  mfem::MassIntegrator      mass(a_coef);
+  mfem::DiffusionIntegrator diffusion(b_coef);
+  mfem::DomainLFIntegrator  load(load_func);
+  mfem::Array<int>          dofs;
+  for (int e = 0; e < mesh.GetNE(); e++) {
+    const mfem::FiniteElement&   el = *fes.GetFE(e);
+    mfem::ElementTransformation& T  = *mesh.GetElementTransformation(e);
+    const mfem::IntegrationRule& ir = mfem::IntRules.Get(el.GetGeomType(), el.GetOrder() * 2);
+    mass.SetIntRule(&ir);
+    diffusion.SetIntRule(&ir);
+    load.SetIntRule(&ir);
+    mfem::DenseMatrix m, d;
+    mfem::Vector      ev;
+    mass.AssembleElementMatrix(el, T, m);
+    diffusion.AssembleElementMatrix(el, T, d);
+    m += d;
+    load.AssembleRHSElementVect(el, T, ev);
+    fes.GetElementDofs(e, dofs);
+    A.AddSubMatrix(dofs, dofs, m);
+    f.AddElementVector(dofs, ev);
+  }
+  A.Finalize();
+  mfem::Vector U(n);
+  U.Randomize(1);
+  using space = H1<p>;
+  Functional<space(space)> residual(&fes, {&fes});
+  residual.AddDomainIntegral(Dimension<dim>{}, DependsOn<0>{}, SourceFluxFunctor{}, mesh);
+  mfem::Vector r1(n);
+  A.Mult(U, r1);
+  r1 -= f;
+  mfem::Vector r2 = residual(0.0, U);
+  EXPECT(rel(r2, r1) < 1e-13, "thermal %s p=%d: ||r_functional - r_mfem|| / ||r|| = %.2e", tag, p, rel(r2, r1));
+  auto [r3, drdU] = residual(0.0, differentiate_wrt(U));
+  mfem::Vector dU(n);
+  dU.Randomize(2);
+  mfem::Vector g1(n);
+  A.Mult(dU, g1);
+  mfem::Vector g2 = drdU(dU);
+  EXPECT(rel(g2, g1) < 1e-13, "thermal %s p=%d: gradient action vs A dU %.2e", tag, p, rel(g2, g1));
+  std::unique_ptr<mfem::SparseMatrix> J = assemble(drdU);
+  mfem::Vector                        g3(n);
+  J->Mult(dU, g3);
+  EXPECT(rel(g3, g1) < 1e-13, "thermal %s p=%d: assembled matrix action vs A dU %.2e", tag, p, rel(g3, g1));
+  bool same_pattern = J->NumNonZeroElems() == A.NumNonZeroElems();
+  for (int i = 0; same_pattern && i <= n; i++) same_pattern = J->GetI()[i] == A.GetI()[i];
+  A.SortColumnIndices();
+  for (int k = 0; same_pattern && k < A.NumNonZeroElems(); k++) same_pattern = J->GetJ()[k] == A.GetJ()[k];
+  EXPECT(same_pattern, "thermal %s p=%d: sparsity pattern over both geometries equals MFEM's (%d nonzeros)", tag, p,
+         J->NumNonZeroElems());
+}
 
 template <int p, int dim>
 void l2_comparison(mfem::Mesh& mesh, const char* tag)
@@ -492,6 +595,11 @@ int main(int argc, char** argv)
     elasticity_comparison<1>(hexes, "hexes");
     elasticity_comparison<2>(hexes, "hexes");
     elasticity_comparison<1>(tets, "tets");
+    // meshes of mixed element geometry against MFEM's integrators (which dispatch per element themselves)
+    mfem::Mesh tris_and_quads = make_mixed_mesh_2d();
+    mfem::Mesh tets_and_hexes = make_mixed_mesh_3d();
+    thermal_comparison_mixed<1, 2>(tris_and_quads, "tris_and_quads");
+    thermal_comparison_mixed<1, 3>(tets_and_hexes, "tets_and_hexes");
   }
   if (which == "l2" || which == "all") {  // functional_comparison_L2.cpp:162-170
     mfem::Mesh quads = mfem::Mesh::MakeCartesian2D(3, 2, mfem::Element::QUADRILATERAL, true, 1.0, 1.3);
@@ -520,6 +628,13 @@ int main(int argc, char** argv)
     thermal_gradients<2, 1, 3>(hexes, "hexes");
     thermal_gradients<2, 1, 3>(tets, "tets");
     thermal_gradients<2, 2, 2>(quads, "quads");
+    // meshes of mixed element geometry (functional_basic_h1_scalar.cpp:112-117): one kernel and one restriction per geometry
+    mfem::Mesh tris_and_quads = make_mixed_mesh_2d();
+    mfem::Mesh tets_and_hexes = make_mixed_mesh_3d();
+    thermal_gradients<1, 1, 2>(tris_and_quads, "tris_and_quads");
+    thermal_gradients<1, 1, 3>(tets_and_hexes, "tets_and_hexes");
+    thermal_gradients<2, 1, 2>(tris_and_quads, "tris_and_quads");
+    thermal_gradients<2, 1, 3>(tets_and_hexes, "tets_and_hexes");
   }
   if (which == "shape" || which == "all") {
     shape_aware<2>(mfem::Element::HEXAHEDRON, "hexes");
