@@ -139,6 +139,7 @@ struct FiniteElementSpace {
   std::vector<int>           element_ids;  ///< mesh index of every element of `geometry` (empty: all elements, in order)
   std::vector<GeometryBlock> more_elements;
   Geometry                   boundary_face_geometry = Geometry::POINT;  ///< POINT: the face geometry of `geometry`
+  std::vector<int>           boundary_face_ids;  ///< mesh face index of every boundary face above (for boundary Domains)
   std::vector<GeometryBlock> more_boundary_faces;
   int64_t                    total_elements() const
   {
@@ -160,7 +161,8 @@ struct Mesh {
 struct Domain {
   const Mesh*      mesh;
   bool             entire;
-  std::vector<int> elements;  ///< element ids when !entire
+  std::vector<int> elements;  ///< element ids when !entire (boundary domains: mesh face ids, ascending)
+  bool             boundary = false;  ///< Domain::Type::BoundaryElements (domain.hpp:27-33)
 };
 inline Domain EntireDomain(const Mesh& mesh) { return Domain{&mesh, true, {}}; }
 
@@ -361,7 +363,8 @@ class Functional<test(trials...)> {
   /// the mesh must carry its native boundary-face dofs.  Faces of 3D meshes (quadrilaterals / triangles) and of 2D
   /// meshes (segments, F/detail/segment_H1.inl).
   template <int dim, int... args, typename Integrand>
-  void AddBoundaryIntegral(Dimension<dim>, DependsOn<args...>, const Integrand& integrand, const Mesh& mesh)
+  void AddBoundaryIntegral(Dimension<dim>, DependsOn<args...>, const Integrand& integrand, const Mesh& mesh,
+                           const std::vector<int>* face_ids = nullptr)
   {
     static_assert(dim == 1 || dim == 2, "boundary integrals live on the faces of 2D or 3D meshes");
     static_assert(((args >= 0 && args < num_trial_spaces) && ...), "DependsOn<> index out of range");
@@ -369,40 +372,18 @@ class Functional<test(trials...)> {
     const Geometry g  = mesh.nodes_space.geometry;
     Geometry fg = (dim == 1) ? Geometry::SEGMENT : (g == Geometry::CUBE) ? Geometry::SQUARE : Geometry::TRIANGLE;
     if (mesh.nodes_space.boundary_face_geometry != Geometry::POINT) fg = mesh.nodes_space.boundary_face_geometry;
-    if (!mesh.nodes_space.more_boundary_faces.empty()) {  // triangular and quadrilateral faces of a mixed 3D mesh
-      add_boundary_integral_block<dim, Integrand, args...>(integrand, mesh, fg, nullptr);
-      for (size_t b = 0; b < mesh.nodes_space.more_boundary_faces.size(); b++)
-        add_boundary_integral_block<dim, Integrand, args...>(integrand, mesh, mesh.nodes_space.more_boundary_faces[b].geometry, &b);
-      return;
-    }
-    const sb_kernel_table* table = nullptr;
-    if constexpr (dim == 2) {
-      if (fg == Geometry::SQUARE) table = boundary_table_for<Geometry::SQUARE, Integrand, args...>();
-      if (fg == Geometry::TRIANGLE) table = boundary_table_for<Geometry::TRIANGLE, Integrand, args...>();
-    } else {
-      table = boundary_table_for<Geometry::SEGMENT, Integrand, args...>();
-    }
-    const int64_t    nf     = mesh.nodes_space.num_boundary_faces;
-    sb_restriction_t G_mesh = make_face_restriction(mesh.nodes_space, fg);
-    mesh_restrictions_.push_back(G_mesh);
-    const int nq        = num_quadrature_points(fg, Q);
-    double*   nodes_dev = device_copy(mesh.nodes.data(), mesh.nodes.size());
-    double*   X_q       = device_alloc<double>(size_t(nf) * size_t(dim + 1) * size_t(nq));
-    double*   J_q       = device_alloc<double>(size_t(nf) * size_t(dim) * size_t(dim + 1) * size_t(nq));
-    SERAC_B200_CHECK(sb_geometric_factors(int(fg), mesh.nodes_space.order, Q, G_mesh, nodes_dev, nullptr, nf, X_q, J_q,
-                                          nullptr));
-    sb_integral_t I = nullptr;
-    SERAC_B200_CHECK(sb_integral_create(table, &integrand, nullptr, nf, X_q, J_q, &I));
-    sb_restriction_t test_faces = make_face_restriction(*test_space_, fg);
-    mesh_restrictions_.push_back(test_faces);
-    const int        which[] = {args..., 0};
-    sb_restriction_t trial_faces[sizeof...(args) + 1];
-    for (size_t i = 0; i < sizeof...(args); i++) {
-      trial_faces[i] = make_face_restriction(*trial_space_[size_t(which[i])], fg);
-      mesh_restrictions_.push_back(trial_faces[i]);
-    }
-    SERAC_B200_CHECK(sb_functional_add_boundary_integral(F_, I, which, test_faces, trial_faces));
-    integrals_.push_back(I);
+    // one integral per face geometry (triangular and quadrilateral faces of a mixed 3D mesh)
+    add_boundary_integral_block<dim, Integrand, args...>(integrand, mesh, fg, nullptr, face_ids);
+    for (size_t b = 0; b < mesh.nodes_space.more_boundary_faces.size(); b++)
+      add_boundary_integral_block<dim, Integrand, args...>(integrand, mesh, mesh.nodes_space.more_boundary_faces[b].geometry,
+                                                           &b, face_ids);
+  }
+  /// ... on part of the boundary (Domain::ofBoundaryElements, domain.hpp:112-127)
+  template <int dim, int... args, typename Integrand>
+  void AddBoundaryIntegral(Dimension<dim> d, DependsOn<args...> a, const Integrand& integrand, const Domain& domain)
+  {
+    if (!domain.boundary) fail("AddBoundaryIntegral: the domain is not a set of boundary elements");
+    AddBoundaryIntegral(d, a, integrand, *domain.mesh, domain.entire ? nullptr : &domain.elements);
   }
 
   /// functional.hpp:446-513: at most one argument may be wrapped in differentiate_wrt(); then the return value is
@@ -666,7 +647,8 @@ class Functional<test(trials...)> {
 
   /// the boundary integral on the faces of ONE geometry (which == nullptr: the first, else more_boundary_faces[*which])
   template <int dim, typename Integrand, int... args>
-  void add_boundary_integral_block(const Integrand& integrand, const Mesh& mesh, Geometry fg, const size_t* which_block)
+  void add_boundary_integral_block(const Integrand& integrand, const Mesh& mesh, Geometry fg, const size_t* which_block,
+                                   const std::vector<int>* face_ids)
   {
     const sb_kernel_table* table = nullptr;
     if constexpr (dim == 2) {
@@ -689,16 +671,29 @@ class Functional<test(trials...)> {
     };
     sb_restriction_t G_mesh = faces_of(mesh.nodes_space);
     mesh_restrictions_.push_back(G_mesh);
-    const int64_t nf = sb_restriction_num_elements(G_mesh);
+    // the domain's faces of this geometry as positions in the block's face list
+    std::vector<int> local;
+    if (face_ids) {
+      const std::vector<int>& ids = which_block ? mesh.nodes_space.more_boundary_faces[*which_block].ids
+                                                : mesh.nodes_space.boundary_face_ids;
+      if (ids.empty() && sb_restriction_num_elements(G_mesh) > 0)
+        fail("AddBoundaryIntegral: the mesh does not carry the face ids of its boundary faces");
+      for (int f : *face_ids) {
+        auto it = std::lower_bound(ids.begin(), ids.end(), f);
+        if (it != ids.end() && *it == f) local.push_back(int(it - ids.begin()));
+      }
+    }
+    const int64_t nf = face_ids ? int64_t(local.size()) : sb_restriction_num_elements(G_mesh);
     if (nf == 0) return;
     const int nq        = num_quadrature_points(fg, Q);
     double*   nodes_dev = device_copy(mesh.nodes.data(), mesh.nodes.size());
+    int*      faces_dev = face_ids ? device_copy(local.data(), local.size()) : nullptr;
     double*   X_q       = device_alloc<double>(size_t(nf) * size_t(dim + 1) * size_t(nq));
     double*   J_q       = device_alloc<double>(size_t(nf) * size_t(dim) * size_t(dim + 1) * size_t(nq));
-    SERAC_B200_CHECK(sb_geometric_factors(int(fg), mesh.nodes_space.order, Q, G_mesh, nodes_dev, nullptr, nf, X_q, J_q,
+    SERAC_B200_CHECK(sb_geometric_factors(int(fg), mesh.nodes_space.order, Q, G_mesh, nodes_dev, faces_dev, nf, X_q, J_q,
                                           nullptr));
     sb_integral_t I = nullptr;
-    SERAC_B200_CHECK(sb_integral_create(table, &integrand, nullptr, nf, X_q, J_q, &I));
+    SERAC_B200_CHECK(sb_integral_create(table, &integrand, face_ids ? local.data() : nullptr, nf, X_q, J_q, &I));
     sb_restriction_t test_faces = faces_of(*test_space_);
     mesh_restrictions_.push_back(test_faces);
     const int        which[] = {args..., 0};
@@ -744,6 +739,24 @@ class Functional<test(trials...)> {
   bool                                                     update_qdata_ = false;
 };
 
+/// the QOI "test space" on the mesh of `first` (F/detail/qoi.inl): order 0, one component, ONE node that every element and
+/// every boundary face refers to, with the same blocks of elements / faces as the space it is modelled on
+inline FiniteElementSpace make_qoi_space(const FiniteElementSpace& first)
+{
+  FiniteElementSpace q{first.geometry, 0, 1, Ordering::byVDIM, 1, first.num_elements,
+                       std::vector<int>(size_t(first.num_elements), 0)};
+  q.num_boundary_faces = first.num_boundary_faces;
+  q.native_boundary_face_dofs.assign(size_t(first.num_boundary_faces), 0);
+  q.element_ids            = first.element_ids;
+  q.boundary_face_geometry = first.boundary_face_geometry;
+  q.boundary_face_ids      = first.boundary_face_ids;
+  for (const auto& b : first.more_elements)
+    q.more_elements.push_back(GeometryBlock{b.geometry, b.ids, std::vector<int>(b.ids.size(), 0)});
+  for (const auto& b : first.more_boundary_faces)
+    q.more_boundary_faces.push_back(GeometryBlock{b.geometry, b.ids, std::vector<int>(b.ids.size(), 0)});
+  return q;
+}
+
 /// Quantity of interest, `Functional<double(trials...)>` (functional_qoi.inl:1-470): the same machinery with the QOI
 /// "test space" (one total per element, summed by the scatter).  operator() returns the scalar (or tuple{scalar,
 /// Gradient&}); Gradient::operator()(dx) is the directional derivative (a length-1 Vector), assemble(Gradient&) the
@@ -759,12 +772,8 @@ class Functional<double(trials...)> {
 
   explicit Functional(std::array<const FiniteElementSpace*, num_trial_spaces> trial_fes)
   {
-    const FiniteElementSpace& first = *trial_fes[0];
-    qoi_space_ = FiniteElementSpace{first.geometry, 0, 1, Ordering::byVDIM, 1, first.num_elements,
-                                    std::vector<int>(size_t(first.num_elements), 0)};
-    qoi_space_.num_boundary_faces = first.num_boundary_faces;
-    qoi_space_.native_boundary_face_dofs.assign(size_t(first.num_boundary_faces), 0);
-    impl_ = std::make_unique<Impl>(&qoi_space_, trial_fes);
+    qoi_space_ = make_qoi_space(*trial_fes[0]);
+    impl_      = std::make_unique<Impl>(&qoi_space_, trial_fes);
   }
 
   template <int dim, int... args, typename Integrand, typename StateType = Nothing>
@@ -779,6 +788,11 @@ class Functional<double(trials...)> {
   void AddBoundaryIntegral(Dimension<dim> d, DependsOn<args...> a, const Integrand& integrand, const Mesh& mesh)
   {
     impl_->AddBoundaryIntegral(d, a, integrand, mesh);
+  }
+  template <int dim, int... args, typename Integrand>
+  void AddBoundaryIntegral(Dimension<dim> d, DependsOn<args...> a, const Integrand& integrand, const Domain& domain)
+  {
+    impl_->AddBoundaryIntegral(d, a, integrand, domain);
   }
 
   template <typename... T>

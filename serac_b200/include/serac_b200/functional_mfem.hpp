@@ -53,26 +53,87 @@ struct differentiate_wrt_this {
 };
 inline differentiate_wrt_this differentiate_wrt(const mfem::Vector& v) { return differentiate_wrt_this{v}; }
 
-/// the subset of serac::Domain (domain.hpp) the element kernels need: a list of elements of one mesh
+/// the subset of serac::Domain (domain.hpp) the element kernels need: a list of elements -- or of boundary elements --
+/// of one mesh.  Predicates take (vertex coordinates, attribute) as in the reference: std::vector<tensor<double, dim>>
+/// (domain.hpp:95-127); std::vector<std::array<double, 3>> is accepted as well.
 struct Domain {
+  enum class Type
+  {
+    Elements,
+    BoundaryElements
+  };
   mfem::Mesh&      mesh_;
-  std::vector<int> elements_;
-  /// Domain::ofElements(mesh, predicate(vertex coordinates, attribute)) (domain.hpp:95-110)
+  std::vector<int> elements_;  ///< mesh element ids, or mesh face ids of boundary elements (ascending)
+  Type             type_ = Type::Elements;
+
+  template <typename Pred>
+  static bool call(Pred& predicate, mfem::Mesh& mesh, const mfem::Array<int>& v, int attr)
+  {
+    const int sdim = mesh.SpaceDimension();
+    if constexpr (std::is_invocable_r_v<bool, Pred, std::vector<tensor<double, 3>>, int>) {
+      if (sdim == 3) {
+        std::vector<tensor<double, 3>> x(static_cast<size_t>(v.Size()));
+        for (int i = 0; i < v.Size(); i++)
+          for (int c = 0; c < 3; c++) x[size_t(i)][c] = mesh.GetVertex(v[i])[c];
+        return predicate(x, attr);
+      }
+    }
+    if constexpr (std::is_invocable_r_v<bool, Pred, std::vector<tensor<double, 2>>, int>) {
+      if (sdim == 2) {
+        std::vector<tensor<double, 2>> x(static_cast<size_t>(v.Size()));
+        for (int i = 0; i < v.Size(); i++)
+          for (int c = 0; c < 2; c++) x[size_t(i)][c] = mesh.GetVertex(v[i])[c];
+        return predicate(x, attr);
+      }
+    }
+    if constexpr (std::is_invocable_r_v<bool, Pred, std::vector<std::array<double, 3>>, int>) {
+      std::vector<std::array<double, 3>> x(static_cast<size_t>(v.Size()), std::array<double, 3>{0.0, 0.0, 0.0});
+      for (int i = 0; i < v.Size(); i++)
+        for (int c = 0; c < sdim; c++) x[size_t(i)][size_t(c)] = mesh.GetVertex(v[i])[c];
+      return predicate(x, attr);
+    }
+    std::fprintf(stderr, "serac::Domain: the predicate does not take the vertex coordinates of a %dD mesh\n", sdim);
+    std::abort();
+  }
+
+  /// Domain::ofElements(mesh, predicate(vertex coordinates, attribute)) (domain.hpp:95-110, domain.cpp:238-300)
   template <typename Pred>
   static Domain ofElements(mfem::Mesh& mesh, Pred&& predicate)
   {
-    Domain d{mesh, {}};
+    Domain d{mesh, {}, Type::Elements};
     for (int e = 0; e < mesh.GetNE(); e++) {
       mfem::Array<int> v;
       mesh.GetElementVertices(e, v);
-      std::vector<std::array<double, 3>> x(static_cast<size_t>(v.Size()), std::array<double, 3>{0.0, 0.0, 0.0});
-      for (int i = 0; i < v.Size(); i++)
-        for (int c = 0; c < mesh.SpaceDimension(); c++) x[size_t(i)][size_t(c)] = mesh.GetVertex(v[i])[c];
-      if (predicate(x, mesh.GetAttribute(e))) d.elements_.push_back(e);
+      if (call(predicate, mesh, v, mesh.GetAttribute(e))) d.elements_.push_back(e);
+    }
+    return d;
+  }
+
+  /// Domain::ofBoundaryElements (domain.hpp:112-127, domain.cpp:311-386): the boundary FACES of the mesh in face order;
+  /// attribute = that of the boundary element on the face, -1 if there is none
+  template <typename Pred>
+  static Domain ofBoundaryElements(mfem::Mesh& mesh, Pred&& predicate)
+  {
+    Domain           d{mesh, {}, Type::BoundaryElements};
+    mfem::Array<int> face_to_bdr = mesh.GetFaceToBdrElMap();
+    for (int f = 0; f < mesh.GetNumFaces(); f++) {
+      if (mesh.GetFaceInformation(f).IsInterior()) continue;
+      mfem::Array<int> v;
+      mesh.GetFaceVertices(f, v);
+      const int bdr_id = face_to_bdr[f];
+      if (call(predicate, mesh, v, bdr_id >= 0 ? mesh.GetBdrAttribute(bdr_id) : -1)) d.elements_.push_back(f);
     }
     return d;
   }
 };
+inline Domain EntireDomain(mfem::Mesh& mesh)
+{
+  return Domain::ofElements(mesh, [](std::vector<std::array<double, 3>>, int) { return true; });
+}
+inline Domain EntireBoundary(mfem::Mesh& mesh)
+{
+  return Domain::ofBoundaryElements(mesh, [](std::vector<std::array<double, 3>>, int) { return true; });
+}
 
 namespace mfem_detail {
 
@@ -148,9 +209,10 @@ inline core_api::FiniteElementSpace convert_space(const mfem::FiniteElementSpace
     const size_t      b   = size_t(std::find(fgeoms.begin(), fgeoms.end(), mesh.GetFaceGeometry(f)) - fgeoms.begin());
     std::vector<int>& dst = (b == 0) ? out.native_boundary_face_dofs : out.more_boundary_faces[b - 1].native_dofs;
     for (int i = 0; i < dofs.Size(); i++) dst.push_back(dofs[i] >= 0 ? dofs[i] : -1 - dofs[i]);
-    if (b == 0)
+    if (b == 0) {
       out.num_boundary_faces++;
-    else
+      out.boundary_face_ids.push_back(f);
+    } else
       out.more_boundary_faces[b - 1].ids.push_back(f);
   }
   return out;
@@ -190,13 +252,27 @@ class Functional<test(trials...), exec> {
 
   /// functional.hpp:219-281
   Functional(const fes_t* test_fes, std::array<const fes_t*, num_trial_spaces> trial_fes)
-      : test_fes_(test_fes), trial_fes_(trial_fes)
+      : test_fes_(test_fes), trial_fes_(trial_fes), test_vsize_(test_fes->GetVSize())
   {
     std::array<const core_api::FiniteElementSpace*, num_trial_spaces> t{};
     const core_api::FiniteElementSpace* ts = space_of(test_fes);
     for (int i = 0; i < num_trial_spaces; i++) t[size_t(i)] = space_of(trial_fes[size_t(i)]);
     impl_ = std::make_unique<Impl>(ts, t);
-    output_T_.SetSize(test_fes->GetVSize());
+    output_T_.SetSize(test_vsize_);
+    grad_.reserve(size_t(num_trial_spaces));
+    for (int i = 0; i < num_trial_spaces; i++) grad_.emplace_back(*this, i);
+  }
+
+  /// quantities of interest (functional_qoi.inl:97-134): no test space; the "test space" has one dof (F/detail/qoi.inl)
+  explicit Functional(std::array<const fes_t*, num_trial_spaces> trial_fes)
+      : test_fes_(nullptr), trial_fes_(trial_fes), test_vsize_(1)
+  {
+    static_assert(test::family == Family::QOI, "only a quantity of interest is built without a test space");
+    std::array<const core_api::FiniteElementSpace*, num_trial_spaces> t{};
+    for (int i = 0; i < num_trial_spaces; i++) t[size_t(i)] = space_of(trial_fes[size_t(i)]);
+    qoi_space_ = std::make_unique<core_api::FiniteElementSpace>(core_api::make_qoi_space(*t[0]));
+    impl_      = std::make_unique<Impl>(qoi_space_.get(), t);
+    output_T_.SetSize(test_vsize_);
     grad_.reserve(size_t(num_trial_spaces));
     for (int i = 0; i < num_trial_spaces; i++) grad_.emplace_back(*this, i);
   }
@@ -215,6 +291,7 @@ class Functional<test(trials...), exec> {
   void AddDomainIntegral(Dimension<dim> d, DependsOn<args...> a, const Integrand& integrand, Domain& domain,
                          std::shared_ptr<QuadratureData<StateType>> qdata = NoQData)
   {
+    if (domain.type_ != Domain::Type::Elements) fail("AddDomainIntegral: the domain is a set of boundary elements");
     core_api::Domain part{mesh_of(domain.mesh_), false, domain.elements_};
     impl_->AddDomainIntegral(d, a, integrand, part, qdata);
   }
@@ -225,6 +302,14 @@ class Functional<test(trials...), exec> {
   {
     if (domain.GetNBE() == 0) return;
     impl_->AddBoundaryIntegral(d, a, integrand, *mesh_of(domain));
+  }
+  /// ... on part of the boundary (Domain::ofBoundaryElements)
+  template <int dim, int... args, typename Integrand>
+  void AddBoundaryIntegral(Dimension<dim> d, DependsOn<args...> a, const Integrand& integrand, Domain& domain)
+  {
+    if (domain.type_ != Domain::Type::BoundaryElements) fail("AddBoundaryIntegral: the domain is not a set of boundary elements");
+    core_api::Domain part{mesh_of(domain.mesh_), false, domain.elements_, true};
+    impl_->AddBoundaryIntegral(d, a, integrand, part);
   }
 
   /// functional.hpp:365-393
@@ -271,14 +356,16 @@ class Functional<test(trials...), exec> {
   /// functional.hpp:523
   void updateQdata(bool update_flag) { impl_->updateQdata(update_flag); }
 
+  Gradient& gradient_of(int which) { return grad_[size_t(which)]; }
+
   /// functional.hpp:532-709
   class Gradient : public mfem::Operator {
    public:
     Gradient(Functional& f, int which)
-        : mfem::Operator(f.test_fes_->GetVSize(), f.trial_fes_[size_t(which)]->GetVSize()),
+        : mfem::Operator(f.test_vsize_, f.trial_fes_[size_t(which)]->GetVSize()),
           form_(f),
           which_argument_(which),
-          df_(f.test_fes_->GetVSize())
+          df_(f.test_vsize_)
     {
     }
     /// functional.hpp:556-559
@@ -373,11 +460,99 @@ class Functional<test(trials...), exec> {
 
   const fes_t*                                                               test_fes_;
   std::array<const fes_t*, num_trial_spaces>                                 trial_fes_;
+  int                                                                        test_vsize_;
+  std::unique_ptr<core_api::FiniteElementSpace>                              qoi_space_;
   std::map<const fes_t*, std::unique_ptr<core_api::FiniteElementSpace>>      spaces_;
   std::map<const mfem::Mesh*, std::unique_ptr<core_api::Mesh>>               meshes_;
   std::unique_ptr<Impl>                                                      impl_;
   mfem::Vector                                                               output_T_;
   std::vector<Gradient>                                                      grad_;
+};
+
+/// Quantity of interest on mfem's types, `Functional<double(trials...)>` (functional_qoi.inl:88-470): operator() returns
+/// the scalar (or tuple{scalar, Gradient&}); Gradient::operator()(dx) is the directional derivative and assemble(Gradient&)
+/// the gradient as a vector (the reference returns a HypreParVector, :411-455; without MPI an mfem::Vector).
+template <typename... trials, ExecutionSpace exec>
+class Functional<double(trials...), exec> {
+  static constexpr int num_trial_spaces = int(sizeof...(trials));
+  using Impl                            = Functional<QOI(trials...), exec>;
+  using fes_t                           = mfem::FiniteElementSpace;
+
+ public:
+  explicit Functional(std::array<const fes_t*, num_trial_spaces> trial_fes) : impl_(trial_fes)
+  {
+    grad_.reserve(size_t(num_trial_spaces));
+    for (int i = 0; i < num_trial_spaces; i++) grad_.emplace_back(*this, i);
+  }
+
+  template <int dim, int... args, typename Integrand, typename DomainType, typename StateType = Nothing>
+  void AddDomainIntegral(Dimension<dim> d, DependsOn<args...> a, const Integrand& integrand, DomainType& domain,
+                         std::shared_ptr<QuadratureData<StateType>> qdata = NoQData)
+  {
+    impl_.AddDomainIntegral(d, a, integrand, domain, qdata);
+  }
+  template <int dim, int... args, typename Integrand, typename DomainType>
+  void AddBoundaryIntegral(Dimension<dim> d, DependsOn<args...> a, const Integrand& integrand, DomainType& domain)
+  {
+    impl_.AddBoundaryIntegral(d, a, integrand, domain);
+  }
+  template <int... args, typename Integrand, typename DomainType, typename StateType = Nothing>
+  void AddAreaIntegral(DependsOn<args...> a, const Integrand& integrand, DomainType& domain,
+                       std::shared_ptr<QuadratureData<StateType>> qdata = NoQData)
+  {
+    impl_.AddDomainIntegral(Dimension<2>{}, a, integrand, domain, qdata);
+  }
+  template <int... args, typename Integrand, typename DomainType, typename StateType = Nothing>
+  void AddVolumeIntegral(DependsOn<args...> a, const Integrand& integrand, DomainType& domain,
+                         std::shared_ptr<QuadratureData<StateType>> qdata = NoQData)
+  {
+    impl_.AddDomainIntegral(Dimension<3>{}, a, integrand, domain, qdata);
+  }
+
+  class Gradient {
+   public:
+    Gradient(Functional& f, int which) : form_(f), which_(which) {}
+    /// functional_qoi.inl:386-390
+    double operator()(const mfem::Vector& dx) { return form_.impl_.gradient_of(which_)(dx)(0); }
+    /// functional_qoi.inl:411-455
+    friend std::unique_ptr<mfem::Vector> assemble(Gradient& g)
+    {
+      auto K = assemble(g.form_.impl_.gradient_of(g.which_));  // 1 x n matrix
+      auto v = std::make_unique<mfem::Vector>(K->Width());
+      *v     = 0.0;
+      const int*    J = K->GetJ();
+      const double* A = K->GetData();
+      for (int k = 0; k < K->NumNonZeroElems(); k++) (*v)(J[k]) = A[k];
+      return v;
+    }
+
+   private:
+    Functional& form_;
+    int         which_;
+  };
+
+  template <typename... T>
+  auto operator()(double t, const T&... args)
+  {
+    constexpr bool differentiated = (std::is_same_v<T, differentiate_wrt_this> || ...);
+    if constexpr (differentiated) {
+      constexpr bool d[]  = {std::is_same_v<T, differentiate_wrt_this>...};
+      int            wrt  = 0;
+      for (int i = 0; i < int(sizeof...(T)); i++)
+        if (d[i]) wrt = i;
+      auto r = impl_(t, args...);
+      return std::tuple<double, Gradient&>(std::get<0>(r)(0), grad_[size_t(wrt)]);
+    } else {
+      const mfem::Vector& r = impl_(t, args...);
+      return r(0);
+    }
+  }
+
+  void updateQdata(bool update_flag) { impl_.updateQdata(update_flag); }
+
+ private:
+  Impl                  impl_;
+  std::vector<Gradient> grad_;
 };
 
 /// shape_aware_functional.hpp:292-575: a Functional whose first argument is a shape displacement field p (H1); the

@@ -12,6 +12,9 @@
 //   scalar        functional_basic_h1_scalar.cpp:32-118: H1<ptest>(H1<ptrial>) with a domain and a boundary integral on
 //                 hexahedra, tetrahedra, quadrilaterals and triangles (boundary faces of the 2D meshes: segments),
 //                 equal and mixed orders, through check_gradient
+//   domains       functional_with_domain.cpp:89-316: Domain::ofElements / ofBoundaryElements with the reference's predicates;
+//                 integrals on complementary parts add up to the whole-mesh Functional (every geometry incl. mixed
+//                 meshes), a domain equals a masked integrand, quantities of interest on part of the mesh / boundary
 //   shape         ShapeAwareFunctional (shape_aware_functional.hpp:292-575): with a shape displacement p the residual
 //                 equals that of the plain Functional on the mesh whose nodes were moved by p
 // Meshes are generated (MakeCartesian3D + a smooth perturbation): the reference's mesh files are not on the GPU box.
@@ -120,6 +123,58 @@ struct TestThermalModelTwo {  // functional_basic_h1_scalar.cpp:51-60 (boundary 
     return X[0] + X[1] - cos(u);
   }
 };
+
+template <int dim, bool apply_mask = false>
+struct TestThermalIntegratorOne {  // functional_with_domain.cpp:26-50
+  template <typename Position, typename Temperature>
+  SERAC_HOST_DEVICE auto operator()(double, Position position, Temperature temperature) const
+  {
+    const double d00 = 1.0;
+    const auto   d01 = 1.0 * make_tensor<dim>([](int i) { return i; });
+    const auto   d10 = 1.0 * make_tensor<dim>([](int i) { return 2 * i * i; });
+    const auto   d11 = 1.0 * make_tensor<dim, dim>([](int i, int j) { return i + j * (j + 1) + 1; });
+    auto [X, dX_dxi] = position;
+    auto [u, du_dx]  = temperature;
+    double mask = 1.0;
+    if constexpr (apply_mask) {
+      mask = (X[0] < 4.0);
+    }
+    auto source = mask * (d00 * u + dot(d01, du_dx) - 0.0 * (100 * X[0] * X[1]));
+    auto flux   = mask * (d10 * u + dot(d11, du_dx));
+    return serac::tuple{source, flux};
+  }
+};
+
+template <bool apply_mask = false>
+struct TestThermalIntegratorTwo {  // functional_with_domain.cpp:52-68
+  template <typename Position, typename Temperature>
+  SERAC_HOST_DEVICE auto operator()(double, Position position, Temperature temperature) const
+  {
+    auto [X, dX_dxi] = position;
+    auto [u, du_dxi] = temperature;
+    double mask = 1.0;
+    if constexpr (apply_mask) {
+      mask = (X[1] >= 0.99);
+    }
+    return mask * (X[0] + X[1] - cos(u));
+  }
+};
+
+struct TrivialIntegrator {  // functional_with_domain.cpp:70-77
+  template <typename UnusedType>
+  SERAC_HOST_DEVICE auto operator()(double /*t*/, UnusedType /*position*/) const
+  {
+    return 1.0;
+  }
+};
+
+template <int dim>
+tensor<double, dim> average(std::vector<tensor<double, dim>>& positions)  // functional_with_domain.cpp:79-87
+{
+  tensor<double, dim> total{};
+  for (auto x : positions) total += x;
+  return total / double(positions.size());
+}
 
 // a nonlinear integrand for the shape-aware check: source and flux depend on position, value and gradient
 struct NonlinearThermal {
@@ -532,6 +587,121 @@ void thermal_gradients(mfem::Mesh& mesh, const char* tag)  // functional_basic_h
   check_gradient(residual, 0.0, U, what.c_str());
 }
 
+// ---- functional_with_domain.cpp --------------------------------------------------------------------------------------------
+template <int ptest, int ptrial, int dim>
+void whole_mesh_comparison(mfem::Mesh& mesh, const char* tag)  // :89-146: integrals on complementary domains add up
+{
+  using test_space  = H1<ptest>;
+  using trial_space = H1<ptrial>;
+  mfem::H1_FECollection    test_fec(ptest, dim), trial_fec(ptrial, dim);
+  mfem::FiniteElementSpace test_fes(&mesh, &test_fec), trial_fes(&mesh, &trial_fec);
+  mfem::GridFunction        U_gf(&trial_fes);
+  mfem::FunctionCoefficient x_squared([](const mfem::Vector& x) { return x[0] * x[0]; });
+  U_gf.ProjectCoefficient(x_squared);
+  mfem::Vector U(U_gf);
+  Functional<test_space(trial_space)> residual(&test_fes, {&trial_fes});
+  Functional<test_space(trial_space)> residual_comparison(&test_fes, {&trial_fes});
+  // (the reference's meshes span [0,1]^d; the generated ones are split at their own mid-planes)
+  mfem::Vector lo, hi;
+  mesh.GetBoundingBox(lo, hi);
+  const double xm = 0.5 * (lo(0) + hi(0)), ym = 0.5 * (lo(1) + hi(1));
+  auto everything = [](std::vector<tensor<double, dim>>, int /* attr */) { return true; };
+  auto on_left    = [xm](std::vector<tensor<double, dim>> X, int /* attr */) { return average(X)[0] < xm; };
+  auto on_right   = [xm](std::vector<tensor<double, dim>> X, int /* attr */) { return average(X)[0] >= xm; };
+  auto on_bottom  = [ym](std::vector<tensor<double, dim>> X, int /* attr */) { return average(X)[1] < ym; };
+  auto on_top     = [ym](std::vector<tensor<double, dim>> X, int /* attr */) { return average(X)[1] >= ym; };
+  Domain whole_mesh      = Domain::ofElements(mesh, everything);
+  Domain left            = Domain::ofElements(mesh, on_left);
+  Domain right           = Domain::ofElements(mesh, on_right);
+  Domain whole_boundary  = Domain::ofBoundaryElements(mesh, everything);
+  Domain bottom_boundary = Domain::ofBoundaryElements(mesh, on_bottom);
+  Domain top_boundary    = Domain::ofBoundaryElements(mesh, on_top);
+  residual.AddDomainIntegral(Dimension<dim>{}, DependsOn<0>{}, TestThermalIntegratorOne<dim>{}, left);
+  residual.AddDomainIntegral(Dimension<dim>{}, DependsOn<0>{}, TestThermalIntegratorOne<dim>{}, right);
+  residual.AddBoundaryIntegral(Dimension<dim - 1>{}, DependsOn<0>{}, TestThermalIntegratorTwo{}, bottom_boundary);
+  residual.AddBoundaryIntegral(Dimension<dim - 1>{}, DependsOn<0>{}, TestThermalIntegratorTwo{}, top_boundary);
+  std::string what = std::string("whole_mesh_comparison ") + tag + " <" + std::to_string(ptest) + "," + std::to_string(ptrial) + ">";
+  check_gradient(residual, 0.0, U, what.c_str());
+  mfem::Vector r0 = residual(0.0, U);
+  residual_comparison.AddDomainIntegral(Dimension<dim>{}, DependsOn<0>{}, TestThermalIntegratorOne<dim>{}, whole_mesh);
+  residual_comparison.AddBoundaryIntegral(Dimension<dim - 1>{}, DependsOn<0>{}, TestThermalIntegratorTwo{}, whole_boundary);
+  mfem::Vector r1 = residual_comparison(0.0, U);
+  const bool split = !left.elements_.empty() && !right.elements_.empty() && !bottom_boundary.elements_.empty() &&
+                     !top_boundary.elements_.empty();
+  EXPECT(split && r0.DistanceTo(r1.GetData()) < 1.0e-14, "%s: left + right + bottom + top vs whole mesh %.2e", what.c_str(),
+         r0.DistanceTo(r1.GetData()));
+}
+
+template <int ptest, int ptrial, int dim>
+void partial_mesh_comparison(mfem::Mesh& mesh, const char* tag)  // :181-226: a domain vs a masked integrand on the whole mesh
+{
+  using test_space  = H1<ptest>;
+  using trial_space = H1<ptrial>;
+  mfem::H1_FECollection    test_fec(ptest, dim), trial_fec(ptrial, dim);
+  mfem::FiniteElementSpace test_fes(&mesh, &test_fec), trial_fes(&mesh, &trial_fec);
+  mfem::GridFunction        U_gf(&trial_fes);
+  mfem::FunctionCoefficient x_squared([](const mfem::Vector& x) { return x[0] * x[0]; });
+  U_gf.ProjectCoefficient(x_squared);
+  mfem::Vector U(U_gf);
+  Functional<test_space(trial_space)> residual(&test_fes, {&trial_fes});
+  Functional<test_space(trial_space)> residual_comparison(&test_fes, {&trial_fes});
+  auto   on_left = [](std::vector<tensor<double, dim>> X, int /* attr */) { return average(X)[0] < 4.0; };
+  Domain left    = Domain::ofElements(mesh, on_left);
+  auto   on_top       = [](std::vector<tensor<double, dim>> X, int /* attr */) { return average(X)[1] >= 0.99; };
+  Domain top_boundary = Domain::ofBoundaryElements(mesh, on_top);
+  residual.AddDomainIntegral(Dimension<dim>{}, DependsOn<0>{}, TestThermalIntegratorOne<dim>{}, left);
+  residual.AddBoundaryIntegral(Dimension<dim - 1>{}, DependsOn<0>{}, TestThermalIntegratorTwo{}, top_boundary);
+  std::string what = std::string("partial_mesh_comparison ") + tag;
+  check_gradient(residual, 0.0, U, what.c_str());
+  mfem::Vector r0 = residual(0.0, U);
+  residual_comparison.AddDomainIntegral(Dimension<dim>{}, DependsOn<0>{}, TestThermalIntegratorOne<dim, true>{}, mesh);
+  residual_comparison.AddBoundaryIntegral(Dimension<dim - 1>{}, DependsOn<0>{}, TestThermalIntegratorTwo<true>{}, mesh);
+  mfem::Vector r1 = residual_comparison(0.0, U);
+  EXPECT(!left.elements_.empty() && int(left.elements_.size()) < mesh.GetNE() && !top_boundary.elements_.empty() &&
+             r0.DistanceTo(r1.GetData()) < 1.0e-14,
+         "%s: %zu of %d elements, %zu boundary faces: domain vs masked integrand %.2e", what.c_str(), left.elements_.size(),
+         mesh.GetNE(), top_boundary.elements_.size(), r0.DistanceTo(r1.GetData()));
+}
+
+/// a beam [0,8] x [0,1] (x [0,1]) like the reference's beam-*.mesh files (straight sides: the masks cut at x = 4, y = 1)
+mfem::Mesh make_beam(mfem::Element::Type type)
+{
+  const bool three_d = (type == mfem::Element::HEXAHEDRON || type == mfem::Element::TETRAHEDRON);
+  mfem::Mesh mesh    = three_d ? mfem::Mesh::MakeCartesian3D(8, 1, 1, type, 8.0, 1.0, 1.0)
+                               : mfem::Mesh::MakeCartesian2D(8, 1, type, true, 8.0, 1.0);
+  mesh.EnsureNodes();
+  return mesh;
+}
+
+void qoi_partial_domains()  // functional_with_domain.cpp:251-316
+{
+  constexpr int dim = 3;
+  mfem::Mesh    mesh = make_beam(mfem::Element::HEXAHEDRON);
+  using trial_space = H1<1>;
+  mfem::H1_FECollection    trial_fec(1, dim);
+  mfem::FiniteElementSpace trial_fes(&mesh, &trial_fec);
+  mfem::GridFunction        U_gf(&trial_fes);
+  mfem::FunctionCoefficient x_squared([](const mfem::Vector& x) { return x[0] * x[0]; });
+  U_gf.ProjectCoefficient(x_squared);
+  mfem::Vector U(U_gf);
+  {
+    Functional<double(trial_space)> qoi({&trial_fes});
+    auto   on_top       = [](std::vector<tensor<double, 3>> X, int /* attr */) { return average(X)[1] >= 0.99; };
+    Domain top_boundary = Domain::ofBoundaryElements(mesh, on_top);
+    qoi.AddBoundaryIntegral(Dimension<dim - 1>{}, DependsOn</*nothing*/>{}, TrivialIntegrator{}, top_boundary);
+    double area = qoi(0.0, U);
+    EXPECT(std::fabs(area - 8.0) < 1.0e-14, "qoi partial_boundary: area of the top of the beam %.16g (8)", area);
+  }
+  {
+    Functional<double(trial_space)> qoi({&trial_fes});
+    auto   on_left = [](std::vector<tensor<double, dim>> X, int /* attr */) { return average(X)[0] < 4.0; };
+    Domain left    = Domain::ofElements(mesh, on_left);
+    qoi.AddDomainIntegral(Dimension<dim>{}, DependsOn</*nothing*/>{}, TrivialIntegrator{}, left);
+    double volume = qoi(0.0, U);
+    EXPECT(std::fabs(volume - 4.0) < 1.0e-14, "qoi partial_domain: volume of the left half of the beam %.16g (4)", volume);
+  }
+}
+
 // ---- ShapeAwareFunctional ------------------------------------------------------------------------------------------------
 template <int p>
 void shape_aware(mfem::Element::Type type, const char* tag)
@@ -635,6 +805,27 @@ int main(int argc, char** argv)
     thermal_gradients<1, 1, 3>(tets_and_hexes, "tets_and_hexes");
     thermal_gradients<2, 1, 2>(tris_and_quads, "tris_and_quads");
     thermal_gradients<2, 1, 3>(tets_and_hexes, "tets_and_hexes");
+  }
+  if (which == "domains" || which == "all") {  // functional_with_domain.cpp:160-249
+    mfem::Mesh quads = make_mesh_2d(mfem::Element::QUADRILATERAL);
+    mfem::Mesh tris  = make_mesh_2d(mfem::Element::TRIANGLE);
+    mfem::Mesh tris_and_quads = make_mixed_mesh_2d();
+    mfem::Mesh tets_and_hexes = make_mixed_mesh_3d();
+    whole_mesh_comparison<1, 1, 2>(tris, "tris");
+    whole_mesh_comparison<1, 1, 2>(quads, "quads");
+    whole_mesh_comparison<1, 1, 2>(tris_and_quads, "tris_and_quads");
+    whole_mesh_comparison<1, 1, 3>(tets, "tets");
+    whole_mesh_comparison<1, 1, 3>(hexes, "hexes");
+    whole_mesh_comparison<1, 1, 3>(tets_and_hexes, "tets_and_hexes");
+    whole_mesh_comparison<2, 1, 2>(tris_and_quads, "tris_and_quads");
+    whole_mesh_comparison<2, 1, 3>(tets_and_hexes, "tets_and_hexes");
+    mfem::Mesh beam_tri = make_beam(mfem::Element::TRIANGLE), beam_quad = make_beam(mfem::Element::QUADRILATERAL);
+    mfem::Mesh beam_tet = make_beam(mfem::Element::TETRAHEDRON), beam_hex = make_beam(mfem::Element::HEXAHEDRON);
+    partial_mesh_comparison<1, 1, 2>(beam_tri, "tris");
+    partial_mesh_comparison<1, 1, 2>(beam_quad, "quads");
+    partial_mesh_comparison<1, 1, 3>(beam_tet, "tets");
+    partial_mesh_comparison<1, 1, 3>(beam_hex, "hexes");
+    qoi_partial_domains();
   }
   if (which == "shape" || which == "all") {
     shape_aware<2>(mfem::Element::HEXAHEDRON, "hexes");
