@@ -515,9 +515,11 @@ class Functional<double(trials...), exec> {
     /// functional_qoi.inl:386-390
     double operator()(const mfem::Vector& dx) { return form_.impl_.gradient_of(which_)(dx)(0); }
     /// functional_qoi.inl:411-455
-    friend std::unique_ptr<mfem::Vector> assemble(Gradient& g)
+    friend std::unique_ptr<mfem::Vector> assemble(Gradient& g) { return g.assemble_vector(); }
+    std::unique_ptr<mfem::Vector>        assemble_vector()
     {
-      auto K = assemble(g.form_.impl_.gradient_of(g.which_));  // 1 x n matrix
+      Gradient& g = *this;
+      auto      K = g.form_.impl_.gradient_of(g.which_).assemble_matrix();  // 1 x n matrix
       auto v = std::make_unique<mfem::Vector>(K->Width());
       *v     = 0.0;
       const int*    J = K->GetJ();

@@ -15,6 +15,10 @@
 //   domains       functional_with_domain.cpp:89-316: Domain::ofElements / ofBoundaryElements with the reference's predicates;
 //                 integrals on complementary parts add up to the whole-mesh Functional (every geometry incl. mixed
 //                 meshes), a domain equals a masked integrand, quantities of interest on part of the mesh / boundary
+//   qoi           functional_qoi.cpp:196-452: Functional<double(...)> -- measures, moments, volume + surface against closed
+//                 forms and MFEM's linear forms, nonlinear and two-argument QOIs through check_gradient's QOI overloads
+//                 (central difference vs assembled gradient vector vs directional derivative), vector-valued and L2
+//                 arguments, AddAreaIntegral / AddVolumeIntegral
 //   shape         ShapeAwareFunctional (shape_aware_functional.hpp:292-575): with a shape displacement p the residual
 //                 equals that of the plain Functional on the mesh whose nodes were moved by p
 // Meshes are generated (MakeCartesian3D + a smooth perturbation): the reference's mesh files are not on the GPU box.
@@ -175,6 +179,76 @@ tensor<double, dim> average(std::vector<tensor<double, dim>>& positions)  // fun
   for (auto x : positions) total += x;
   return total / double(positions.size());
 }
+
+// ---- functional_qoi.cpp:35-128 ------------------------------------------------------------------------------------------
+struct TrivialVariadicIntegrator {
+  template <typename... Args>
+  SERAC_HOST_DEVICE auto operator()(Args...) const
+  {
+    return 1.0;
+  }
+};
+struct ZeroIndexIntegrator {
+  template <typename P>
+  SERAC_HOST_DEVICE auto operator()(double /*t*/, P position) const
+  {
+    return get<VALUE>(position)[0];
+  }
+};
+struct GetZeroIntegrator {
+  template <typename Unused, typename X>
+  SERAC_HOST_DEVICE auto operator()(double /*t*/, Unused, X x) const
+  {
+    return serac::get<0>(x);
+  }
+};
+struct SineIntegrator {
+  template <typename Position, typename Temperature>
+  SERAC_HOST_DEVICE auto operator()(double /*t*/, Position position, Temperature temperature) const
+  {
+    auto X           = get<VALUE>(position);
+    auto [u, grad_u] = temperature;
+    return X[0] * X[0] + sin(X[1]) + X[0] * u * u * u;
+  }
+};
+struct CosineIntegrator {
+  template <typename Position, typename Temperature>
+  SERAC_HOST_DEVICE auto operator()(double /*t*/, Position position, Temperature temperature) const
+  {
+    auto [X, dX_dxi] = position;
+    auto [u, unused] = temperature;
+    return X[0] - X[1] + cos(u * X[1]);
+  }
+};
+struct FourArgSineIntegrator {
+  template <typename Position, typename Temperature, typename TimeDerivativeTemp>
+  SERAC_HOST_DEVICE auto operator()(double /*t*/, Position position, Temperature temperature,
+                                    TimeDerivativeTemp dtemperature_dt) const
+  {
+    auto [X, dX_dxi]     = position;
+    auto [u, grad_u]     = temperature;
+    auto [du_dt, unused] = dtemperature_dt;
+    return X[0] * X[0] + sin(du_dt) + X[0] * u * u * u;
+  }
+};
+struct FourArgCosineIntegrator {
+  template <typename Position, typename Temperature, typename TimeDerivativeTemp>
+  SERAC_HOST_DEVICE auto operator()(double /*t*/, Position position, Temperature temperature,
+                                    TimeDerivativeTemp dtemperature_dt) const
+  {
+    auto [X, dX_dxi]     = position;
+    auto [u, grad_u]     = temperature;
+    auto [du_dt, unused] = dtemperature_dt;
+    return X[0] - X[1] + cos(u * du_dt);
+  }
+};
+struct GetNormZeroIntegrator {
+  template <typename Unused, typename X>
+  SERAC_HOST_DEVICE auto operator()(double /*t*/, Unused, X x) const
+  {
+    return norm(serac::get<0>(x));
+  }
+};
 
 // a nonlinear integrand for the shape-aware check: source and flux depend on position, value and gradient
 struct NonlinearThermal {
@@ -702,6 +776,200 @@ void qoi_partial_domains()  // functional_with_domain.cpp:251-316
   }
 }
 
+// ---- functional_qoi.cpp ------------------------------------------------------------------------------------------------
+// check_gradient.hpp:225-262 (one argument) and :264-330 (two arguments): central difference of the scalar against the
+// assembled gradient vector and against the directional derivative
+template <typename F>
+void check_qoi_gradient(F& f, double t, const mfem::Vector& U, const char* what)
+{
+  mfem::Vector dU(U.Size());
+  dU.Randomize(42);
+  const double epsilon = 1.0e-8;
+  auto [unused, dfdU]  = f(t, differentiate_wrt(U));
+  std::unique_ptr<mfem::Vector> dfdU_vec = assemble(dfdU);
+  mfem::Vector U_plus(U), U_minus(U);
+  U_plus.Add(epsilon, dU);
+  U_minus.Add(-epsilon, dU);
+  double df1 = (f(t, U_plus) - f(t, U_minus)) / (2 * epsilon);
+  double df2 = (*dfdU_vec) * dU;
+  double df3 = dfdU(dU);
+  EXPECT(std::fabs((df1 - df2) / df1) < 2.e-5 && std::fabs((df1 - df3) / df1) < 2.e-5,
+         "%s: central difference %.10e, gradient vector . dU %.10e, directional derivative %.10e", what, df1, df2, df3);
+}
+template <typename F>
+void check_qoi_gradient(F& f, double t, const mfem::Vector& U1, const mfem::Vector& U2, const char* what)
+{
+  // (the reference steps by 1e-8; on the 3D box the scalar is ~2e5 and its derivative w.r.t. the second argument ~1, so a
+  // difference over 2e-8 carries a relative rounding noise of ~1e-3: 1e-5 keeps both noise and truncation below 1e-6)
+  const double epsilon = 1.0e-5;
+  {
+    mfem::Vector dU(U1.Size());
+    dU.Randomize(42);
+    auto [unused, dfdU] = f(t, differentiate_wrt(U1), U2);
+    std::unique_ptr<mfem::Vector> v = assemble(dfdU);
+    mfem::Vector Up(U1), Um(U1);
+    Up.Add(epsilon, dU);
+    Um.Add(-epsilon, dU);
+    double df1 = (f(t, Up, U2) - f(t, Um, U2)) / (2 * epsilon), df2 = (*v) * dU, df3 = dfdU(dU);
+    EXPECT(std::fabs((df1 - df2) / df1) < 2.e-5 && std::fabs((df1 - df3) / df1) < 2.e-5,
+           "%s d/dU1: central difference %.10e, gradient vector . dU %.10e, directional derivative %.10e", what, df1, df2, df3);
+  }
+  {
+    mfem::Vector dU(U2.Size());
+    dU.Randomize(43);
+    auto [unused, dfdU] = f(t, U1, differentiate_wrt(U2));
+    std::unique_ptr<mfem::Vector> v = assemble(dfdU);
+    mfem::Vector Up(U2), Um(U2);
+    Up.Add(epsilon, dU);
+    Um.Add(-epsilon, dU);
+    double df1 = (f(t, U1, Up) - f(t, U1, Um)) / (2 * epsilon), df2 = (*v) * dU, df3 = dfdU(dU);
+    EXPECT(std::fabs((df1 - df2) / df1) < 2.e-5 && std::fabs((df1 - df3) / df1) < 2.e-5,
+           "%s d/dU2: central difference %.10e, gradient vector . dU %.10e, directional derivative %.10e", what, df1, df2, df3);
+  }
+}
+
+// functional_qoi.cpp:129-182: the same quantities through MFEM's linear forms
+double lf_mfem(mfem::Mesh& mesh, bool with_boundary, bool x_moment)
+{
+  mfem::ConstantCoefficient one(1.0);
+  mfem::H1_FECollection     fec(1, mesh.Dimension());
+  mfem::FiniteElementSpace  fes(&mesh, &fec);
+  mfem::LinearForm          lf(&fes);
+  lf.AddDomainIntegrator(new mfem::DomainLFIntegrator(one));
+  if (with_boundary) lf.AddBoundaryIntegrator(new mfem::BoundaryLFIntegrator(one));
+  lf.Assemble();
+  mfem::GridFunction        gf(&fes);
+  mfem::FunctionCoefficient x_coordinate([](const mfem::Vector& x) { return x[0]; });
+  if (x_moment)
+    gf.ProjectCoefficient(x_coordinate);
+  else
+    gf.ProjectCoefficient(one);
+  return lf(gf);
+}
+
+/// functional_qoi.cpp:196-290 on a box (2D: [0,1]^2, 3D: [0,4] x [0,2] x [0,2]) whose measures are known in closed form
+template <int p, int dim>
+void qoi_test(mfem::Mesh& mesh, const char* tag)
+{
+  using trial_space = H1<p>;
+  mfem::H1_FECollection     fec(p, dim);
+  mfem::FiniteElementSpace  fes(&mesh, &fec);
+  mfem::GridFunction        U_gf(&fes), V_gf(&fes);
+  mfem::FunctionCoefficient x_squared([](const mfem::Vector& x) { return x[0] * x[0]; });
+  mfem::FunctionCoefficient x_coord([](const mfem::Vector& x) { return x[0]; });
+  U_gf.ProjectCoefficient(x_squared);
+  V_gf.ProjectCoefficient(x_coord);
+  mfem::Vector U(U_gf), V(V_gf);
+  const double t = 0.0;
+  const double expected_measure[] = {1.0, 16.0}, expected_moment[] = {0.5, 32.0}, expected_sum[] = {5.0, 56.0};
+  {
+    Functional<double(trial_space)> measure({&fes});
+    measure.AddDomainIntegral(Dimension<dim>{}, DependsOn<>{}, TrivialIntegrator{}, mesh);
+    const double m = measure(t, U);
+    EXPECT(std::fabs(m - expected_measure[dim - 2]) / expected_measure[dim - 2] < 1e-10 &&
+               std::fabs(m - lf_mfem(mesh, false, false)) / m < 1e-10,
+           "qoi Measure %s p=%d: %.14g (exact %g, mfem %.14g)", tag, p, m, expected_measure[dim - 2], lf_mfem(mesh, false, false));
+  }
+  {
+    Functional<double(trial_space)> x_moment({&fes});
+    x_moment.AddDomainIntegral(Dimension<dim>{}, DependsOn<>{}, ZeroIndexIntegrator{}, mesh);
+    const double m = x_moment(t, U);
+    Functional<double(trial_space)> x_moment_2({&fes});
+    x_moment_2.AddDomainIntegral(Dimension<dim>{}, DependsOn<0>{}, GetZeroIntegrator{}, mesh);
+    const double m2 = x_moment_2(t, V);
+    EXPECT(std::fabs(m - expected_moment[dim - 2]) / expected_moment[dim - 2] < 1e-10 &&
+               std::fabs(m - lf_mfem(mesh, false, true)) / m < 1e-10 && std::fabs(m2 - m) / m < 1e-10,
+           "qoi Moment %s p=%d: from the position %.14g, from the field x %.14g (exact %g)", tag, p, m, m2, expected_moment[dim - 2]);
+  }
+  {
+    Functional<double(trial_space)> sum_of_measures({&fes});
+    sum_of_measures.AddDomainIntegral(Dimension<dim>{}, DependsOn<>{}, TrivialIntegrator{}, mesh);
+    sum_of_measures.AddBoundaryIntegral(Dimension<dim - 1>{}, DependsOn<>{}, TrivialIntegrator{}, mesh);
+    const double m = sum_of_measures(t, U);
+    EXPECT(std::fabs(m - expected_sum[dim - 2]) / expected_sum[dim - 2] < 1e-10 &&
+               std::fabs(m - lf_mfem(mesh, true, false)) / m < 1e-10,
+           "qoi SumOfMeasures %s p=%d: %.14g (exact %g)", tag, p, m, expected_sum[dim - 2]);
+  }
+  {
+    Functional<double(trial_space)> f({&fes});
+    f.AddDomainIntegral(Dimension<dim>{}, DependsOn<0>{}, SineIntegrator{}, mesh);
+    f.AddBoundaryIntegral(Dimension<dim - 1>{}, DependsOn<0>{}, CosineIntegrator{}, mesh);
+    std::string what = std::string("qoi Nonlinear ") + tag + " p=" + std::to_string(p);
+    check_qoi_gradient(f, t, U, what.c_str());
+  }
+  {  // functional_qoi.cpp:292-335: two arguments
+    mfem::GridFunction        U2_gf(&fes);
+    mfem::FunctionCoefficient y([](const mfem::Vector& x) { return x[1]; });
+    U2_gf.ProjectCoefficient(y);
+    mfem::Vector U2(U2_gf);
+    Functional<double(trial_space, trial_space)> f({&fes, &fes});
+    f.AddDomainIntegral(Dimension<dim>{}, DependsOn<0, 1>{}, FourArgSineIntegrator{}, mesh);
+    f.AddBoundaryIntegral(Dimension<dim - 1>{}, DependsOn<0, 1>{}, FourArgCosineIntegrator{}, mesh);
+    std::string what = std::string("qoi Variadic ") + tag + " p=" + std::to_string(p);
+    check_qoi_gradient(f, t, U, U2, what.c_str());
+  }
+}
+
+void qoi_misc()
+{
+  const double t = 0.0;
+  {  // functional_qoi.cpp:337-368 DependsOnVectorValuedInput: integral of |u| with u = (1, 2, 2)/... -> 3 * volume
+    constexpr int dim = 3;
+    mfem::Mesh    mesh = mfem::Mesh::MakeCartesian3D(2, 2, 2, mfem::Element::HEXAHEDRON, 1.0, 1.0, 1.0);
+    mesh.EnsureNodes();
+    using trial_space = H1<1, dim>;
+    mfem::H1_FECollection    fec(1, dim);
+    mfem::FiniteElementSpace fes(&mesh, &fec, dim, mfem::Ordering::byVDIM);
+    mfem::Vector             U(fes.GetVSize());
+    for (int n = 0; n < fes.GetNDofs(); n++) {
+      U(n * dim + 0) = 1.0;
+      U(n * dim + 1) = 2.0;
+      U(n * dim + 2) = 2.0;
+    }
+    Functional<double(trial_space)> f({&fes});
+    f.AddVolumeIntegral(DependsOn<0>{}, GetNormZeroIntegrator{}, mesh);
+    const double v = f(t, U);
+    EXPECT(std::fabs(v - 3.0) < 1e-12, "qoi DependsOnVectorValuedInput: integral of |u| over the unit cube %.14g (3)", v);
+  }
+  {  // :370-423 AddAreaIntegral / AddVolumeIntegral
+    mfem::Mesh quads = mfem::Mesh::MakeCartesian2D(3, 3, mfem::Element::QUADRILATERAL, true, 1.0, 1.0);
+    quads.EnsureNodes();
+    mfem::H1_FECollection    fec2(1, 2);
+    mfem::FiniteElementSpace fes2(&quads, &fec2);
+    mfem::Vector             U2(fes2.GetVSize());
+    U2 = 0.0;
+    Functional<double(H1<1>)> area({&fes2});
+    area.AddAreaIntegral(DependsOn<>{}, TrivialIntegrator{}, quads);
+    mfem::Mesh hexes = mfem::Mesh::MakeCartesian3D(2, 2, 2, mfem::Element::HEXAHEDRON, 1.0, 2.0, 1.5);
+    hexes.EnsureNodes();
+    mfem::H1_FECollection    fec3(1, 3);
+    mfem::FiniteElementSpace fes3(&hexes, &fec3);
+    mfem::Vector             U3(fes3.GetVSize());
+    U3 = 0.0;
+    Functional<double(H1<1>)> volume({&fes3});
+    volume.AddVolumeIntegral(DependsOn<>{}, TrivialIntegrator{}, hexes);
+    const double a = area(t, U2), v = volume(t, U3);
+    EXPECT(std::fabs(a - 1.0) < 1e-13 && std::fabs(v - 3.0) < 1e-13, "qoi AddAreaIntegral %.14g (1), AddVolumeIntegral %.14g (3)", a, v);
+  }
+  {  // :425-452 UsingL2: an L2 and an H1 argument, volume + surface of a box
+    constexpr int dim = 3;
+    mfem::Mesh    mesh = mfem::Mesh::MakeCartesian3D(2, 1, 1, mfem::Element::HEXAHEDRON, 2.0, 1.0, 1.0);
+    mesh.EnsureNodes();
+    using trial_space_0 = L2<0>;
+    using trial_space_1 = H1<1, dim>;
+    mfem::L2_FECollection    fec0(0, dim, mfem::BasisType::GaussLobatto);
+    mfem::H1_FECollection    fec1(1, dim);
+    mfem::FiniteElementSpace fes0(&mesh, &fec0), fes1(&mesh, &fec1, dim, mfem::Ordering::byVDIM);
+    mfem::Vector             U0(fes0.GetVSize()), U1(fes1.GetVSize());
+    U0 = 0.0;
+    U1 = 0.0;
+    Functional<double(trial_space_0, trial_space_1)> f({&fes0, &fes1});
+    f.AddVolumeIntegral(DependsOn<1>{}, TrivialVariadicIntegrator{}, mesh);
+    const double v = f(t, U0, U1);
+    EXPECT(std::fabs(v - 2.0) < 1e-13, "qoi UsingL2: Functional<double(L2<0>, H1<1,3>)> volume %.14g (2)", v);
+  }
+}
+
 // ---- ShapeAwareFunctional ------------------------------------------------------------------------------------------------
 template <int p>
 void shape_aware(mfem::Element::Type type, const char* tag)
@@ -826,6 +1094,20 @@ int main(int argc, char** argv)
     partial_mesh_comparison<1, 1, 3>(beam_tet, "tets");
     partial_mesh_comparison<1, 1, 3>(beam_hex, "hexes");
     qoi_partial_domains();
+  }
+  if (which == "qoi" || which == "all") {  // functional_qoi.cpp:581-604
+    mfem::Mesh mesh2D = mfem::Mesh::MakeCartesian2D(4, 4, mfem::Element::QUADRILATERAL, true, 1.0, 1.0);
+    mfem::Mesh mesh3D = mfem::Mesh::MakeCartesian3D(4, 2, 2, mfem::Element::HEXAHEDRON, 4.0, 2.0, 2.0);
+    mfem::Mesh tris2D = mfem::Mesh::MakeCartesian2D(3, 3, mfem::Element::TRIANGLE, true, 1.0, 1.0);
+    mfem::Mesh tets3D = mfem::Mesh::MakeCartesian3D(2, 1, 1, mfem::Element::TETRAHEDRON, 4.0, 2.0, 2.0);
+    for (mfem::Mesh* m : {&mesh2D, &mesh3D, &tris2D, &tets3D}) m->EnsureNodes();
+    qoi_test<1, 2>(mesh2D, "quads");
+    qoi_test<2, 2>(mesh2D, "quads");
+    qoi_test<1, 3>(mesh3D, "hexes");
+    qoi_test<2, 3>(mesh3D, "hexes");
+    qoi_test<1, 2>(tris2D, "tris");
+    qoi_test<1, 3>(tets3D, "tets");
+    qoi_misc();
   }
   if (which == "shape" || which == "all") {
     shape_aware<2>(mfem::Element::HEXAHEDRON, "hexes");
