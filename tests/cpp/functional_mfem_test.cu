@@ -15,6 +15,9 @@
 //   domains       functional_with_domain.cpp:89-316: Domain::ofElements / ofBoundaryElements with the reference's predicates;
 //                 integrals on complementary parts add up to the whole-mesh Functional (every geometry incl. mixed
 //                 meshes), a domain equals a masked integrand, quantities of interest on part of the mesh / boundary
+//   nonlinear     functional_nonlinear.cpp:45-153 (thermal and elasticity, p = 1, 2, 3, on the mixed 2D and 3D meshes) and
+//                 functional_multiphysics.cpp:25-83 (two arguments, p = 3, AddVolumeIntegral + AddSurfaceIntegral) through
+//                 check_gradient
 //   qoi           functional_qoi.cpp:196-452: Functional<double(...)> -- measures, moments, volume + surface against closed
 //                 forms and MFEM's linear forms, nonlinear and two-argument QOIs through check_gradient's QOI overloads
 //                 (central difference vs assembled gradient vector vs directional derivative), vector-valued and L2
@@ -247,6 +250,71 @@ struct GetNormZeroIntegrator {
   SERAC_HOST_DEVICE auto operator()(double /*t*/, Unused, X x) const
   {
     return norm(serac::get<0>(x));
+  }
+};
+
+// ---- functional_nonlinear.cpp:57-66,74-79,106-113,121-127 (the reference's lambdas as functors) ---------------------------
+struct NonlinearThermalDomain {
+  template <typename Position, typename Temperature>
+  SERAC_HOST_DEVICE auto operator()(double /*t*/, Position position, Temperature temperature) const
+  {
+    auto [X, dX_dxi] = position;
+    auto [u, du_dX]  = temperature;
+    auto source      = COEF_A * u * u - (100 * X[0] * X[1]);
+    auto flux        = COEF_B * du_dX;
+    return serac::tuple{source, flux};
+  }
+};
+struct NonlinearThermalBoundary {
+  template <typename Position, typename Temperature>
+  SERAC_HOST_DEVICE auto operator()(double /*t*/, Position position, Temperature temperature) const
+  {
+    auto [X, dX_dxi] = position;
+    auto u           = get<0>(temperature);
+    return X[0] + X[1] - cos(u);
+  }
+};
+struct NonlinearElasticDomain {
+  template <typename Position, typename Displacement>
+  SERAC_HOST_DEVICE auto operator()(double /*t*/, Position /*x*/, Displacement displacement) const
+  {
+    auto [u, du_dx] = displacement;
+    auto source     = COEF_A * u * u[0];
+    auto flux       = COEF_B * du_dx;
+    return serac::tuple{source, flux};
+  }
+};
+struct NonlinearElasticBoundary {
+  template <typename Position, typename Displacement>
+  SERAC_HOST_DEVICE auto operator()(double /*t*/, Position position, Displacement displacement) const
+  {
+    auto [X, dX_dxi] = position;
+    auto u           = get<0>(displacement);
+    auto n           = normalize(cross(dX_dxi));
+    return (X[0] + X[1] - cos(u[0])) * n;
+  }
+};
+// ---- functional_multiphysics.cpp:55-76 -------------------------------------------------------------------------------------
+struct MultiphysicsVolume {
+  template <typename Position, typename Temperature, typename Rate>
+  SERAC_HOST_DEVICE auto operator()(double /*t*/, Position position, Temperature temperature, Rate dtemperature_dt) const
+  {
+    auto [X, dX_dxi]     = position;
+    auto [u, du_dX]      = temperature;
+    auto [du_dt, unused] = dtemperature_dt;
+    auto source          = 1.0 * 1.0 * du_dt * du_dt - (100 * X[0] * X[1]);
+    auto flux            = 1.0 * du_dX;
+    return serac::tuple{source, flux};
+  }
+};
+struct MultiphysicsSurface {
+  template <typename Position, typename Temperature, typename Rate>
+  SERAC_HOST_DEVICE auto operator()(double /*t*/, Position position, Temperature temperature, Rate dtemperature_dt) const
+  {
+    auto [X, dX_dxi] = position;
+    auto [u, _0]     = temperature;
+    auto [du_dt, _1] = dtemperature_dt;
+    return X[0] + X[1] - cos(u) * du_dt;
   }
 };
 
@@ -659,6 +727,97 @@ void thermal_gradients(mfem::Mesh& mesh, const char* tag)  // functional_basic_h
   residual.AddBoundaryIntegral(Dimension<dim - 1>{}, DependsOn<0>{}, TestThermalModelTwo{}, mesh);
   std::string what = std::string("thermal_test ") + tag + " <" + std::to_string(ptest) + "," + std::to_string(ptrial) + ">";
   check_gradient(residual, 0.0, U, what.c_str());
+}
+
+// ---- functional_nonlinear.cpp:45-137 ---------------------------------------------------------------------------------------
+template <int p, int dim>
+void nonlinear_thermal(mfem::Mesh& mesh, const char* tag)
+{
+  using space = H1<p>;
+  mfem::H1_FECollection    fec(p, dim);
+  mfem::FiniteElementSpace fes(&mesh, &fec);
+  mfem::Vector             U(fes.GetVSize());
+  U.Randomize(11);
+  Functional<space(space)> residual(&fes, {&fes});
+  residual.AddDomainIntegral(Dimension<dim>{}, DependsOn<0>{}, NonlinearThermalDomain{}, mesh);
+  residual.AddBoundaryIntegral(Dimension<dim - 1>{}, DependsOn<0>{}, NonlinearThermalBoundary{}, mesh);
+  std::string what = std::string("nonlinear Thermal ") + tag + " p=" + std::to_string(p);
+  check_gradient(residual, 0.0, U, what.c_str());
+}
+template <int p, int dim>
+void nonlinear_elasticity(mfem::Mesh& mesh, const char* tag)
+{
+  using space = H1<p, dim>;
+  mfem::H1_FECollection    fec(p, dim);
+  mfem::FiniteElementSpace fes(&mesh, &fec, dim, mfem::Ordering::byVDIM);
+  mfem::Vector             U(fes.GetVSize());
+  U.Randomize(12);
+  Functional<space(space)> residual(&fes, {&fes});
+  residual.AddDomainIntegral(Dimension<dim>{}, DependsOn<0>{}, NonlinearElasticDomain{}, mesh);
+  residual.AddBoundaryIntegral(Dimension<dim - 1>{}, DependsOn<0>{}, NonlinearElasticBoundary{}, mesh);
+  std::string what = std::string("nonlinear Elasticity ") + tag + " p=" + std::to_string(p);
+  check_gradient(residual, 0.0, U, what.c_str());
+}
+
+// ---- functional_multiphysics.cpp:25-83 + check_gradient.hpp:92-222 (two arguments) ----------------------------------------
+template <typename F>
+void check_gradient2(F& f, double t, const mfem::Vector& U, const mfem::Vector& dU_dt, const char* what, double epsilon = 1.0e-4)
+{
+  mfem::Vector dU(U.Size()), ddU_dt(U.Size());
+  dU.Randomize(42);
+  ddU_dt.Randomize(43);
+  auto differences = [&](auto&& eval, const mfem::Vector& jvp, const char* which) {
+    mfem::Vector f_values[5];
+    for (int i = 0; i < 5; i++) f_values[i] = eval((i - 2) * epsilon);
+    mfem::Vector fd0(f_values[4]), fd1(f_values[3]), cd0(f_values[4]), cd1(f_values[3]);
+    fd0 -= f_values[2];
+    fd0 /= (2.0 * epsilon);
+    fd1 -= f_values[2];
+    fd1 /= epsilon;
+    cd0 -= f_values[0];
+    cd0 /= (4.0 * epsilon);
+    cd1 -= f_values[1];
+    cd1 /= (2.0 * epsilon);
+    const double den = (jvp.Norml2() < 1.0e-10) ? 1.0 : jvp.Norml2();
+    const double e1 = fd0.DistanceTo(jvp.GetData()) / den, e2 = fd1.DistanceTo(jvp.GetData()) / den;
+    const double e3 = cd0.DistanceTo(jvp.GetData()) / den, e4 = cd1.DistanceTo(jvp.GetData()) / den;
+    EXPECT((std::fabs(e1 / e2 - 2.0) < 0.1 || std::fmin(e1, e2) < 1.0e-9) && (std::fabs(e3 / e4 - 4.0) < 0.1 || std::fmin(e3, e4) < 1.0e-9),
+           "%s %s: forward e1 %.2e e2 %.2e, centred e3 %.2e e4 %.2e", what, which, e1, e2, e3, e4);
+  };
+  {
+    auto [value, dfdU] = f(t, differentiate_wrt(U), dU_dt);
+    std::unique_ptr<mfem::SparseMatrix> M = assemble(dfdU);
+    mfem::Vector j1 = dfdU(dU), j2(j1.Size());
+    M->Mult(dU, j2);
+    const double re = j1.Norml2() != 0 ? j1.DistanceTo(j2.GetData()) / j1.Norml2() : 0.0;
+    EXPECT(re < 5.e-6, "%s d/dU: JVP vs assembled matrix %.2e", what, re);
+    differences([&](double h) { mfem::Vector Up(U); Up.Add(h, dU); return mfem::Vector(f(t, Up, dU_dt)); }, j1, "d/dU");
+  }
+  {
+    auto [value, dfdV] = f(t, U, differentiate_wrt(dU_dt));
+    std::unique_ptr<mfem::SparseMatrix> M = assemble(dfdV);
+    mfem::Vector j1 = dfdV(ddU_dt), j2(j1.Size());
+    M->Mult(ddU_dt, j2);
+    const double re = j1.DistanceTo(j2.GetData()) / j1.Norml2();
+    EXPECT(re < 5.e-14, "%s d/d(dU_dt): JVP vs assembled matrix %.2e", what, re);
+    differences([&](double h) { mfem::Vector Vp(dU_dt); Vp.Add(h, ddU_dt); return mfem::Vector(f(t, U, Vp)); }, j1, "d/d(dU_dt)");
+  }
+}
+
+void multiphysics(mfem::Mesh& mesh, const char* tag)
+{
+  constexpr int p = 3;
+  using space     = H1<p>;
+  mfem::H1_FECollection    fec(p, 3);
+  mfem::FiniteElementSpace fes(&mesh, &fec);
+  mfem::Vector             U(fes.GetVSize()), dU_dt(fes.GetVSize());
+  U.Randomize(1);
+  dU_dt.Randomize(2);
+  Functional<space(space, space)> residual(&fes, {&fes, &fes});
+  residual.AddVolumeIntegral(DependsOn<0, 1>{}, MultiphysicsVolume{}, mesh);
+  residual.AddSurfaceIntegral(DependsOn<0, 1>{}, MultiphysicsSurface{}, mesh);
+  std::string what = std::string("multiphysics NonlinearThermalTest3D ") + tag;
+  check_gradient2(residual, 0.0, U, dU_dt, what.c_str());
 }
 
 // ---- functional_with_domain.cpp --------------------------------------------------------------------------------------------
@@ -1108,6 +1267,23 @@ int main(int argc, char** argv)
     qoi_test<1, 2>(tris2D, "tris");
     qoi_test<1, 3>(tets3D, "tets");
     qoi_misc();
+  }
+  if (which == "nonlinear" || which == "all") {  // functional_nonlinear.cpp:139-153, functional_multiphysics.cpp:25-83
+    mfem::Mesh mesh2D = make_mixed_mesh_2d();
+    mfem::Mesh mesh3D = make_mixed_mesh_3d();
+    nonlinear_thermal<1, 2>(mesh2D, "2D tris_and_quads");
+    nonlinear_thermal<2, 2>(mesh2D, "2D tris_and_quads");
+    nonlinear_thermal<3, 2>(mesh2D, "2D tris_and_quads");
+    nonlinear_thermal<1, 3>(mesh3D, "3D tets_and_hexes");
+    nonlinear_thermal<2, 3>(mesh3D, "3D tets_and_hexes");
+    nonlinear_thermal<3, 3>(mesh3D, "3D tets_and_hexes");
+    nonlinear_elasticity<1, 2>(mesh2D, "2D tris_and_quads");
+    nonlinear_elasticity<2, 2>(mesh2D, "2D tris_and_quads");
+    nonlinear_elasticity<3, 2>(mesh2D, "2D tris_and_quads");
+    nonlinear_elasticity<1, 3>(mesh3D, "3D tets_and_hexes");
+    nonlinear_elasticity<2, 3>(mesh3D, "3D tets_and_hexes");
+    nonlinear_elasticity<3, 3>(mesh3D, "3D tets_and_hexes");
+    multiphysics(mesh3D, "tets_and_hexes p=3");
   }
   if (which == "shape" || which == "all") {
     shape_aware<2>(mfem::Element::HEXAHEDRON, "hexes");
