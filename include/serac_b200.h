@@ -63,6 +63,17 @@ void      sb_count_launch(void); /* called by kernel-table launchers (serac_b200
  * bits 0-47 index, 60-62 orientation, 63 sign). */
 int sb_h1_lexicographic_dof_info(int geom, int p, const int* native_dofs_host, int64_t num_elements,
                                  uint64_t* dof_info_host);
+/* Face restrictions of DISCONTINUOUS (L2) spaces, FaceType::BOUNDARY and FaceType::INTERIOR
+ * (F/element_restriction.cpp:66-215, 304-355): a DG space has no face dofs of its own -- the dofs "of" a face are those of
+ * an adjacent element that lie on it.  One entry per (face, adjacent element) pair: elem_geom[i] the element's geometry,
+ * elem_dofs_host + elem_dofs_offset[i] its dofs (lexicographic, which is what mfem hands out for L2 spaces), side[i] the
+ * local index of the face among the element's sides (mfem's GetElementFaces / GetElementEdges order) and orientation[i]
+ * of the face relative to the element (mfem's face orientations; for edges 0 = as is, 1 = reversed; the reference passes 0
+ * for the boundary edges of 2D meshes, :340-346).  dof_info_host (out): [num_pairs][nodes per face] DoF words in the
+ * face's lexicographic order.  A boundary restriction has one pair per face; an interior one has two (the two elements of
+ * a face one after the other), i.e. 2 x nodes-per-face columns per face.  Host only: no device is needed. */
+int sb_l2_face_dof_info(int face_geom, int p, int64_t num_pairs, const int* elem_geom, const int* elem_dofs_host,
+                        const int64_t* elem_dofs_offset, const int* side, const int* orientation, uint64_t* dof_info_host);
 /* the permutation itself: lex_perm[k] = native position of lexicographic node k (ndof entries) */
 int sb_h1_lexicographic_permutation(int geom, int p, int* lex_perm_host);
 

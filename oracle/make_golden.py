@@ -457,6 +457,32 @@ FIXTURES = [
 ]
 
 
+def reference_l2_face_tables():
+    """DG face restrictions (element_restriction.cpp:66-215, 304-355): for several meshes and orders the per-(face,
+    element) inputs mfem provides and the reference's FaceType::BOUNDARY / FaceType::INTERIOR dof tables."""
+    out, cases = {}, []
+    specs = [("hex", ("cart3d", 2, 2, 2, 0.02)), ("tet", ("cart3d_tet", 2, 2, 1, 0.02)), ("quad", ("cart2d", 3, 2, 0.02)),
+             ("tri", ("cart2d_tri", 3, 2, 0.02)), ("beamtet", ("file", "beam-tet.mesh", 0)),
+             ("star", ("file", "star.mesh", 0))]
+    for tag, spec in specs:
+        mesh = make_mesh(spec)
+        for p in (0, 1, 2, 3):
+            space = ref.Space(mesh, p, 1, family="L2")
+            for interior in (False, True):
+                info, ins = ref.l2_face_tables(space, mesh.face_geom, interior)
+                if len(ins["side"]) == 0:
+                    continue
+                name = f"{tag}_p{p}_{'interior' if interior else 'boundary'}"
+                cases.append(name)
+                out[name + "_face_geom"] = mesh.face_geom
+                out[name + "_p"] = p
+                out[name + "_dof_info"] = info
+                for k, v in ins.items():
+                    out[f"{name}_{k}"] = v
+    out["cases"] = np.array(cases)
+    return out
+
+
 def config_a_fixture():
     """BASELINE.json configs[1]: beam-hex.mesh refined 4x (32 768 hexes), H1 p=2 vdim 3 (839 619 vdofs).  Stores the
     host-library inputs (native dofs, mesh nodes) and a strided sample + norms of the reference residual / Jacobian
@@ -484,6 +510,11 @@ def main():
         path = os.path.join(GOLDEN_DIR, "config_a_beam_hex_r4_p2.npz")
         np.savez_compressed(path, **data)
         print(f"config A: ne={data['ne']} -> {os.path.getsize(path) / 1024:.0f} KiB")
+    if not only or "l2faces" in only:
+        data = reference_l2_face_tables()
+        path = os.path.join(GOLDEN_DIR, "l2faces_tables.npz")
+        np.savez_compressed(path, **data)
+        print(f"l2faces: {len(data['cases'])} cases -> {os.path.getsize(path) / 1024:.0f} KiB")
     for name, kw in FIXTURES:
         if only and name not in only:
             continue

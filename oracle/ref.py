@@ -55,6 +55,9 @@ def lib():
             "ref_lex_perm": (i, [i, i, vp]),
             "ref_space_face_native_dofs": (l, [vp, i, vp]),
             "ref_space_face_dof_info": (l, [vp, i, vp]),
+            "ref_space_face_dof_info_typed": (l, [vp, i, i, vp]),
+            "ref_space_l2_face_inputs": (l, [vp, i, i, vp, vp, vp, vp, vp]),
+            "ref_space_l2_face_inputs_size": (l, [vp, i, i]),
             "ref_space_face_esize": (l, [vp, i]),
             "ref_space_face_gather": (None, [vp, i, vp, vp]),
             "ref_space_face_scatter_add": (None, [vp, i, vp, vp]),
@@ -212,6 +215,24 @@ class Space:
     def scatter_add(self, E, Lvec):
         lib().ref_space_scatter_add(self.h, self.geom, _p(np.ascontiguousarray(E)), _p(Lvec))
         return Lvec
+
+
+def l2_face_tables(space, face_geom, interior):
+    """DG face restrictions (element_restriction.cpp:304-355): the reference's dof_info [pairs][nodes per face] for
+    FaceType::BOUNDARY (interior=False) or FaceType::INTERIOR, and the per-(face, element) inputs mfem provides:
+    dict(elem_geom, elem_dofs, offsets, side, orientation)"""
+    L, t = lib(), 1 if interior else 0
+    n = L.ref_space_face_dof_info_typed(space.h, face_geom, t, None)
+    info = np.empty(n, dtype=np.uint64)
+    L.ref_space_face_dof_info_typed(space.h, face_geom, t, _p(info))
+    pairs = L.ref_space_l2_face_inputs(space.h, face_geom, t, None, None, None, None, None)
+    nd = L.ref_space_l2_face_inputs_size(space.h, face_geom, t)
+    ins = dict(elem_geom=np.empty(pairs, dtype=np.int32), elem_dofs=np.empty(nd, dtype=np.int32),
+               offsets=np.empty(pairs + 1, dtype=np.int64), side=np.empty(pairs, dtype=np.int32),
+               orientation=np.empty(pairs, dtype=np.int32))
+    L.ref_space_l2_face_inputs(space.h, face_geom, t, _p(ins["elem_geom"]), _p(ins["elem_dofs"]), _p(ins["offsets"]),
+                               _p(ins["side"]), _p(ins["orientation"]))
+    return info.reshape(pairs, -1) if pairs else info.reshape(0, 0), ins
 
 
 class FaceSpace:

@@ -233,6 +233,86 @@ long ref_space_face_dof_info(void* s, int face_geom, uint64_t* out)
   if (out) std::memcpy(out, r.dof_info.data(), sizeof(uint64_t) * size_t(n));
   return n;
 }
+/// serac::GetFaceDofs(fes, face_geom, type) (element_restriction.cpp:279-388) for either face type; type: 0 = BOUNDARY,
+/// 1 = INTERIOR (interior faces of a DG space carry the dofs of both adjacent elements, one after the other)
+long ref_space_face_dof_info_typed(void* s, int face_geom, int type, uint64_t* out)
+{
+  serac::ElementRestriction r(static_cast<Space*>(s)->fes.get(), mfem::Geometry::Type(face_geom),
+                              type == 0 ? FaceType::BOUNDARY : FaceType::INTERIOR);
+  const long n = long(r.num_elements * r.nodes_per_elem);
+  if (out && n) std::memcpy(out, r.dof_info.data(), sizeof(uint64_t) * size_t(n));
+  return n;
+}
+/// what mfem knows about the (face, adjacent element) pairs of a DG space, in the order the reference walks them
+/// (element_restriction.cpp:296-355): the INPUT of the product's sb_l2_face_dof_info.  Returns the number of pairs;
+/// elem_dofs (flat) is indexed through offsets [pairs + 1].  The reference's convention for the orientation of the
+/// boundary edges of 2D meshes (0, :340-346) is applied here, as the adapter of the product does.
+long ref_space_l2_face_inputs(void* s, int face_geom, int type, int* elem_geom, int* elem_dofs, long* offsets, int* side,
+                              int* orientation)
+{
+  auto*        fes          = static_cast<Space*>(s)->fes.get();
+  mfem::Mesh*  mesh         = fes->GetMesh();
+  mfem::Table* face_to_elem = mesh->GetFaceToElementTable();
+  long         n = 0, nd = 0;
+  for (int f = 0; f < fes->GetNF(); f++) {
+    auto faceinfo = mesh->GetFaceInformation(f);
+    if (mesh->GetFaceGeometry(f) != mfem::Geometry::Type(face_geom)) continue;
+    if (faceinfo.IsInterior() && type == 0) continue;
+    if (faceinfo.IsBoundary() && type == 1) continue;
+    mfem::Array<int> elem_ids;
+    face_to_elem->GetRow(f, elem_ids);
+    for (auto elem : elem_ids) {
+      mfem::Array<int> sides, ori;
+      if (mesh->Dimension() == 2) {
+        mesh->GetElementEdges(elem, sides, ori);
+        for (auto& o : ori) o = (o == -1) ? 1 : 0;
+      } else {
+        mesh->GetElementFaces(elem, sides, ori);
+      }
+      int i;
+      for (i = 0; i < sides.Size(); i++)
+        if (sides[i] == f) break;
+      mfem::Array<int> dofs;
+      fes->GetElementDofs(elem, dofs);
+      if (elem_geom) {
+        elem_geom[n]   = int(mesh->GetElementGeometry(elem));
+        side[n]        = i;
+        orientation[n] = (mesh->Dimension() == 2 && type == 0) ? 0 : ori[i];
+        offsets[n]     = nd;
+        for (int k = 0; k < dofs.Size(); k++) elem_dofs[nd + k] = dofs[k];
+      }
+      nd += dofs.Size();
+      n++;
+      if (type == 0) break;
+    }
+  }
+  if (offsets) offsets[n] = nd;
+  delete face_to_elem;
+  return n;
+}
+long ref_space_l2_face_inputs_size(void* s, int face_geom, int type)
+{
+  auto*        fes          = static_cast<Space*>(s)->fes.get();
+  mfem::Mesh*  mesh         = fes->GetMesh();
+  mfem::Table* face_to_elem = mesh->GetFaceToElementTable();
+  long         nd = 0;
+  for (int f = 0; f < fes->GetNF(); f++) {
+    auto faceinfo = mesh->GetFaceInformation(f);
+    if (mesh->GetFaceGeometry(f) != mfem::Geometry::Type(face_geom)) continue;
+    if (faceinfo.IsInterior() && type == 0) continue;
+    if (faceinfo.IsBoundary() && type == 1) continue;
+    mfem::Array<int> elem_ids;
+    face_to_elem->GetRow(f, elem_ids);
+    for (auto elem : elem_ids) {
+      mfem::Array<int> dofs;
+      fes->GetElementDofs(elem, dofs);
+      nd += dofs.Size();
+      if (type == 0) break;
+    }
+  }
+  delete face_to_elem;
+  return nd;
+}
 long ref_space_face_esize(void* s, int face_geom)
 {
   serac::ElementRestriction r(static_cast<Space*>(s)->fes.get(), mfem::Geometry::Type(face_geom),

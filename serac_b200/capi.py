@@ -44,6 +44,7 @@ SIGNATURES = {
     "sb_launch_count_reset": (None, []),
     "sb_count_launch": (None, []),
     "sb_h1_lexicographic_dof_info": (_i, [_i, _i, _vp, _i64, _vp]),
+    "sb_l2_face_dof_info": (_i, [_i, _i, _i64, _vp, _vp, _vp, _vp, _vp, _vp]),
     "sb_h1_lexicographic_permutation": (_i, [_i, _i, _vp]),
     "sb_restriction_create": (_i, [_vp, _i64, _i, _i, _i64, _i, _pp]),
     "sb_restriction_destroy": (_i, [_vp]),
@@ -232,6 +233,19 @@ def h1_dof_info(geom, p, native_dofs):
     native = np.ascontiguousarray(native_dofs, dtype=np.int32)
     out = np.empty(native.shape, dtype=np.uint64)
     check(lib().sb_h1_lexicographic_dof_info(geom, p, _np_ptr(native), native.shape[0], _np_ptr(out)))
+    return out
+
+
+def l2_face_dof_info(face_geom, p, elem_geom, elem_dofs, offsets, side, orientation):
+    """face restriction table of a discontinuous (L2) space, FaceType::BOUNDARY or INTERIOR (element_restriction.cpp:
+    304-355): one row per (face, adjacent element) pair; host only"""
+    eg, ed, so, si, orr = (np.ascontiguousarray(a, dtype=t) for a, t in
+                           ((elem_geom, np.int32), (elem_dofs, np.int32), (offsets, np.int64), (side, np.int32),
+                            (orientation, np.int32)))
+    n = len(si)
+    out = np.empty((n, num_nodes(face_geom, p)), dtype=np.uint64)
+    check(lib().sb_l2_face_dof_info(int(face_geom), int(p), n, _np_ptr(eg), _np_ptr(ed), _np_ptr(so), _np_ptr(si),
+                                    _np_ptr(orr), _np_ptr(out)))
     return out
 
 

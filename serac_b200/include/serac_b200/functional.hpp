@@ -536,8 +536,13 @@ class Functional<test(trials...)> {
     if (fes.native_boundary_face_dofs.size() != size_t(fes.num_boundary_faces) * size_t(npf))
       fail("AddBoundaryIntegral: a space does not carry its native boundary-face dofs");
     std::vector<uint64_t> dof_info(size_t(fes.num_boundary_faces) * size_t(npf));
-    SERAC_B200_CHECK(sb_h1_lexicographic_dof_info(int(fg), fes.order, fes.native_boundary_face_dofs.data(),
-                                                  fes.num_boundary_faces, dof_info.data()));
+    if (fes.family == Family::L2) {
+      // DG spaces: the caller took the face dofs from the adjacent elements (sb_l2_face_dof_info), lexicographic already
+      for (size_t i = 0; i < dof_info.size(); i++) dof_info[i] = uint64_t(fes.native_boundary_face_dofs[i]);
+    } else {
+      SERAC_B200_CHECK(sb_h1_lexicographic_dof_info(int(fg), fes.order, fes.native_boundary_face_dofs.data(),
+                                                    fes.num_boundary_faces, dof_info.data()));
+    }
     sb_restriction_t r = nullptr;
     SERAC_B200_CHECK(sb_restriction_create(dof_info.data(), fes.num_boundary_faces, npf, fes.vdim, fes.num_nodes,
                                            int(fes.ordering), &r));

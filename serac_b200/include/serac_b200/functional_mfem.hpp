@@ -28,6 +28,7 @@
 
 #include <functional>
 #include <map>
+#include <set>
 
 #include "mfem.hpp"
 #include "serac_b200/functional.hpp"
@@ -126,6 +127,17 @@ struct Domain {
     return d;
   }
 };
+/// predicates on the attribute (domain.hpp:190-214)
+template <int dim>
+inline auto by_attr(int value)
+{
+  return [value](std::vector<tensor<double, dim>>, int attr) { return attr == value; };
+}
+template <int dim>
+inline auto by_attr(std::set<int> values)
+{
+  return [values](std::vector<tensor<double, dim>>, int attr) { return values.find(attr) != values.end(); };
+}
 inline Domain EntireDomain(mfem::Mesh& mesh)
 {
   return Domain::ofElements(mesh, [](std::vector<std::array<double, 3>>, int) { return true; });
@@ -205,10 +217,32 @@ inline core_api::FiniteElementSpace convert_space(const mfem::FiniteElementSpace
     out.more_boundary_faces.push_back(core_api::GeometryBlock{geometry_of(fgeoms[b]), {}, {}});
   for (int f = 0; f < mesh.GetNumFaces(); f++) {
     if (!mesh.GetFaceInformation(f).IsBoundary()) continue;
-    fes.GetFaceDofs(f, dofs);
     const size_t      b   = size_t(std::find(fgeoms.begin(), fgeoms.end(), mesh.GetFaceGeometry(f)) - fgeoms.begin());
     std::vector<int>& dst = (b == 0) ? out.native_boundary_face_dofs : out.more_boundary_faces[b - 1].native_dofs;
-    for (int i = 0; i < dofs.Size(); i++) dst.push_back(dofs[i] >= 0 ? dofs[i] : -1 - dofs[i]);
+    if (out.family == Family::L2) {
+      // a DG space has no face dofs: they are those of the adjacent element that lie on the face
+      // (element_restriction.cpp:304-355), already in the face's lexicographic order
+      int e1 = -1, e2 = -1;
+      mesh.GetFaceElements(f, &e1, &e2);
+      mfem::Array<int> sides, ori, edofs;
+      if (mesh.Dimension() == 2) {
+        mesh.GetElementEdges(e1, sides, ori);
+        for (auto& o : ori) o = 0;  // the reference discards mfem's orientation of boundary edges (:340-346)
+      } else {
+        mesh.GetElementFaces(e1, sides, ori);
+      }
+      int side = 0;
+      while (side < sides.Size() && sides[side] != f) side++;
+      fes.GetElementDofs(e1, edofs);
+      const int     eg = int(mesh.GetElementGeometry(e1)), fg = int(mesh.GetFaceGeometry(f)), o = ori[side];
+      const int64_t zero = 0;
+      std::vector<uint64_t> info(size_t(b200::num_nodes(geometry_of(mesh.GetFaceGeometry(f)), out.order)));
+      SERAC_B200_CHECK(sb_l2_face_dof_info(fg, out.order, 1, &eg, edofs.GetData(), &zero, &side, &o, info.data()));
+      for (uint64_t d : info) dst.push_back(int(d));
+    } else {
+      fes.GetFaceDofs(f, dofs);
+      for (int i = 0; i < dofs.Size(); i++) dst.push_back(dofs[i] >= 0 ? dofs[i] : -1 - dofs[i]);
+    }
     if (b == 0) {
       out.num_boundary_faces++;
       out.boundary_face_ids.push_back(f);
@@ -580,11 +614,21 @@ class ShapeAwareFunctional<shape, test(trials...), exec> {
     for (int i = 0; i < num_trial_spaces; i++) prepended[size_t(1 + i)] = trial_fes[size_t(i)];
     functional_ = std::make_unique<functional_t>(test_fes, prepended);
   }
+  /// shape_aware_functional.hpp:333-352: quantities of interest (`test` = double) have no test space
+  ShapeAwareFunctional(const fes_t* shape_fes, std::array<const fes_t*, num_trial_spaces> trial_fes)
+  {
+    static_assert(std::is_same_v<test, double>, "only a quantity of interest is built without a test space");
+    static_assert(shape::family == Family::H1, "Only H1 spaces allowed for shape displacements");
+    std::array<const fes_t*, num_trial_spaces + 1> prepended{};
+    prepended[0] = shape_fes;
+    for (int i = 0; i < num_trial_spaces; i++) prepended[size_t(1 + i)] = trial_fes[size_t(i)];
+    functional_ = std::make_unique<functional_t>(prepended);
+  }
 
   /// shape_aware_functional.hpp:440-470: the integrand sees (t, x, [state,] trial arguments...); the shape displacement
   /// is argument 0 of the underlying Functional
-  template <int dim, int... args, typename Integrand, typename StateType = Nothing>
-  void AddDomainIntegral(Dimension<dim>, DependsOn<args...>, const Integrand& integrand, mfem::Mesh& domain,
+  template <int dim, int... args, typename Integrand, typename DomainType, typename StateType = Nothing>
+  void AddDomainIntegral(Dimension<dim>, DependsOn<args...>, const Integrand& integrand, DomainType& domain,
                          std::shared_ptr<QuadratureData<StateType>> qdata = NoQData)
   {
     if constexpr (std::is_same_v<StateType, Nothing>) {
@@ -597,8 +641,8 @@ class ShapeAwareFunctional<shape, test(trials...), exec> {
   }
 
   /// shape_aware_functional.hpp:474-499
-  template <int dim, int... args, typename Integrand>
-  void AddBoundaryIntegral(Dimension<dim>, DependsOn<args...>, const Integrand& integrand, mfem::Mesh& domain)
+  template <int dim, int... args, typename Integrand, typename DomainType>
+  void AddBoundaryIntegral(Dimension<dim>, DependsOn<args...>, const Integrand& integrand, DomainType& domain)
   {
     using W = ShapeAwareBoundaryIntegrandWrapper<Integrand>;
     functional_->AddBoundaryIntegral(Dimension<dim>{}, DependsOn<0, (args + 1)...>{}, W(integrand), domain);

@@ -15,6 +15,10 @@
 //   domains       functional_with_domain.cpp:89-316: Domain::ofElements / ofBoundaryElements with the reference's predicates;
 //                 integrals on complementary parts add up to the whole-mesh Functional (every geometry incl. mixed
 //                 meshes), a domain equals a masked integrand, quantities of interest on part of the mesh / boundary
+//   boundary      functional_boundary_test.cpp:59-233: boundary integrals of H1 and of discontinuous L2 spaces (face dofs of a
+//                 DG space = those of the adjacent element, element_restriction.cpp:304-355) against MFEM's
+//                 BoundaryLFIntegrator / BoundaryNormalLFIntegrator / BoundaryMassIntegrator on the mixed meshes;
+//                 bug_boundary_qoi.cpp: ShapeAwareFunctional<shape, double()> on the faces of one boundary attribute
 //   nonlinear     functional_nonlinear.cpp:45-153 (thermal and elasticity, p = 1, 2, 3, on the mixed 2D and 3D meshes) and
 //                 functional_multiphysics.cpp:25-83 (two arguments, p = 3, AddVolumeIntegral + AddSurfaceIntegral) through
 //                 check_gradient
@@ -318,6 +322,40 @@ struct MultiphysicsSurface {
   }
 };
 
+// ---- functional_boundary_test.cpp:103-111, 186-194 (the reference's lambdas as functors) ----------------------------------
+template <int dim>
+struct BoundaryTestH1 {
+  double rho;
+  template <typename Position, typename Temperature>
+  SERAC_HOST_DEVICE auto operator()(double /*t*/, Position position, Temperature temperature) const
+  {
+    auto [X, dX_dxi] = position;
+    auto [u, unused] = temperature;
+    auto n           = normalize(cross(dX_dxi));
+    tensor<double, dim> b{};
+    b[0] = sin(X[0]);
+    b[1] = X[0] * X[1];
+    return X[0] * X[1] + dot(b, n) + rho * u;
+  }
+};
+struct BoundaryTestL2 {
+  double rho;
+  template <typename Position, typename Temperature>
+  SERAC_HOST_DEVICE auto operator()(double /*t*/, Position position, Temperature temperature) const
+  {
+    auto [X, dX_dxi] = position;
+    auto [u, unused] = temperature;
+    return X[0] * X[1] + rho * u;
+  }
+};
+struct IdentityFunctor {  // bug_boundary_qoi.cpp:27-33
+  template <typename Arg1, typename Arg2>
+  SERAC_HOST_DEVICE auto operator()(Arg1, Arg2) const
+  {
+    return 1.0;
+  }
+};
+
 // a nonlinear integrand for the shape-aware check: source and flux depend on position, value and gradient
 struct NonlinearThermal {
   template <typename Position, typename Temperature>
@@ -381,15 +419,22 @@ mfem::Mesh make_mixed_mesh_2d()
 
 /// a patch of tetrahedra next to a patch of hexahedra (two pieces of one mesh, as in the reference's
 /// patch3D_tets_and_hexes.mesh): triangular and quadrilateral boundary faces
-mfem::Mesh make_mixed_mesh_3d()
+mfem::Mesh make_mixed_mesh_3d(bool straight = false)
 {
   mfem::Mesh tets  = mfem::Mesh::MakeCartesian3D(1, 1, 1, mfem::Element::TETRAHEDRON, 1.0, 1.1, 0.9);
   mfem::Mesh hexes = mfem::Mesh::MakeCartesian3D(2, 1, 1, mfem::Element::HEXAHEDRON, 1.0, 1.2, 0.8);
-  hexes.Transform([](const mfem::Vector& x, mfem::Vector& y) {
-    y    = x;
-    y(0) = x(0) + 2.0 + 0.05 * x(1) * x(2);
-    y(2) = x(2) + 0.04 * x(0) * x(1);
-  });
+  if (straight) {
+    hexes.Transform([](const mfem::Vector& x, mfem::Vector& y) {
+      y    = x;
+      y(0) = x(0) + 2.0;
+    });
+  } else {
+    hexes.Transform([](const mfem::Vector& x, mfem::Vector& y) {
+      y    = x;
+      y(0) = x(0) + 2.0 + 0.05 * x(1) * x(2);
+      y(2) = x(2) + 0.04 * x(0) * x(1);
+    });
+  }
   mfem::Mesh* pieces[] = {&tets, &hexes};
   mfem::Mesh  mesh(pieces, 2);
   mesh.EnsureNodes();
@@ -818,6 +863,84 @@ void multiphysics(mfem::Mesh& mesh, const char* tag)
   residual.AddSurfaceIntegral(DependsOn<0, 1>{}, MultiphysicsSurface{}, mesh);
   std::string what = std::string("multiphysics NonlinearThermalTest3D ") + tag;
   check_gradient2(residual, 0.0, U, dU_dt, what.c_str());
+}
+
+// ---- functional_boundary_test.cpp:59-233 -------------------------------------------------------------------------------
+template <int p, int dim, bool discontinuous>
+void boundary_test(mfem::Mesh& mesh, const char* tag)
+{
+  const double rho = 1.75;
+  using space      = std::conditional_t<discontinuous, L2<p>, H1<p>>;
+  std::unique_ptr<mfem::FiniteElementCollection> fec;
+  if (discontinuous)
+    fec = std::make_unique<mfem::L2_FECollection>(p, dim, mfem::BasisType::GaussLobatto);
+  else
+    fec = std::make_unique<mfem::H1_FECollection>(p, dim);
+  mfem::FiniteElementSpace fes(&mesh, fec.get());
+  mfem::LinearForm                f(&fes);
+  mfem::FunctionCoefficient       scalar_function([&](const mfem::Vector& coords) { return coords(0) * coords(1); });
+  mfem::VectorFunctionCoefficient vector_function(dim, [&](const mfem::Vector& coords, mfem::Vector& output) {
+    output    = 0.0;
+    output[0] = sin(coords[0]);
+    output[1] = coords[0] * coords[1];
+  });
+  mfem::BilinearForm        B(&fes);
+  mfem::ConstantCoefficient density(rho);
+  if (discontinuous) {
+    f.AddBdrFaceIntegrator(new mfem::BoundaryLFIntegrator(scalar_function, 2, 0));
+    B.AddBdrFaceIntegrator(new mfem::BoundaryMassIntegrator(density));
+  } else {
+    f.AddBoundaryIntegrator(new mfem::BoundaryLFIntegrator(scalar_function, 2, 0));
+    f.AddBoundaryIntegrator(new mfem::BoundaryNormalLFIntegrator(vector_function, 2, 0));
+    B.AddBoundaryIntegrator(new mfem::BoundaryMassIntegrator(density));
+  }
+  f.Assemble();
+  B.Assemble(0);
+  B.Finalize();
+  mfem::Vector U(fes.GetVSize());
+  if (discontinuous) {
+    mfem::GridFunction        u_global(&fes);
+    mfem::FunctionCoefficient xfunc([](const mfem::Vector& x) { return x[0]; });
+    u_global.ProjectCoefficient(xfunc);
+    U = u_global;
+  } else {
+    U.Randomize(3);
+  }
+  Functional<space(space)> residual(&fes, {&fes});
+  if constexpr (discontinuous) {
+    residual.AddBoundaryIntegral(Dimension<dim - 1>{}, DependsOn<0>{}, BoundaryTestL2{rho}, mesh);
+  } else {
+    residual.AddBoundaryIntegral(Dimension<dim - 1>{}, DependsOn<0>{}, BoundaryTestH1<dim>{rho}, mesh);
+  }
+  mfem::Vector r1(U.Size());
+  B.Mult(U, r1);
+  r1 += f;
+  mfem::Vector r2 = residual(0.0, U);
+  std::string what = std::string(discontinuous ? "boundaryL2 " : "FunctionalBoundary ") + tag + " p=" + std::to_string(p);
+  if constexpr (!discontinuous) check_gradient(residual, 0.0, U, what.c_str());
+  EXPECT(rel(r2, r1) < 1e-12, "%s: boundary residual vs MFEM's boundary integrators %.2e", what.c_str(), rel(r2, r1));
+}
+
+// ---- bug_boundary_qoi.cpp:37-64: ShapeAwareFunctional<shape, double()> on a boundary and on the faces of one attribute ------
+void boundary_qoi_by_attribute()
+{
+  constexpr int ORDER = 1;
+  mfem::Mesh    mesh  = mfem::Mesh::MakeCartesian2D(10, 10, mfem::Element::QUADRILATERAL, false, 1.0, 1.0);
+  mesh.EnsureNodes();
+  using shapeFES = H1<ORDER, 2>;
+  mfem::H1_FECollection    shape_fec(ORDER, 2);
+  mfem::FiniteElementSpace shape_fes(&mesh, &shape_fec, 2, mfem::Ordering::byVDIM);
+  mfem::Vector             shape(shape_fes.GetVSize());
+  shape = 0.0;
+  ShapeAwareFunctional<shapeFES, double()> totalSurfArea(&shape_fes, {});
+  totalSurfArea.AddBoundaryIntegral(Dimension<2 - 1>{}, DependsOn<>{}, IdentityFunctor{}, mesh);
+  double totalSurfaceArea = totalSurfArea(0.0, shape);
+  Domain attr1 = Domain::ofBoundaryElements(mesh, by_attr<2>(1));
+  ShapeAwareFunctional<shapeFES, double()> attr1SurfArea(&shape_fes, {});
+  attr1SurfArea.AddBoundaryIntegral(Dimension<2 - 1>{}, DependsOn<>{}, IdentityFunctor{}, attr1);
+  double attr1SurfaceArea = attr1SurfArea(0.0, shape);
+  EXPECT(std::fabs(totalSurfaceArea - 4.0) < 1.0e-14 && std::fabs(attr1SurfaceArea - 1.0) < 1.0e-14,
+         "BoundaryIntegralQOI AttrBug: perimeter %.15g (4), boundary attribute 1 %.15g (1)", totalSurfaceArea, attr1SurfaceArea);
 }
 
 // ---- functional_with_domain.cpp --------------------------------------------------------------------------------------------
@@ -1284,6 +1407,20 @@ int main(int argc, char** argv)
     nonlinear_elasticity<2, 3>(mesh3D, "3D tets_and_hexes");
     nonlinear_elasticity<3, 3>(mesh3D, "3D tets_and_hexes");
     multiphysics(mesh3D, "tets_and_hexes p=3");
+  }
+  if (which == "boundary" || which == "all") {  // functional_boundary_test.cpp:223-232, bug_boundary_qoi.cpp
+    mfem::Mesh mesh2D = make_mixed_mesh_2d();
+    mfem::Mesh mesh3D = make_mixed_mesh_3d(true);
+    boundary_test<1, 2, false>(mesh2D, "2D tris_and_quads");
+    boundary_test<2, 2, false>(mesh2D, "2D tris_and_quads");
+    boundary_test<1, 3, false>(mesh3D, "3D tets_and_hexes");
+    boundary_test<2, 3, false>(mesh3D, "3D tets_and_hexes");
+    boundary_test<1, 2, true>(mesh2D, "2D tris_and_quads");
+    boundary_test<2, 2, true>(mesh2D, "2D tris_and_quads");
+    boundary_test<1, 3, true>(mesh3D, "3D tets_and_hexes");
+    boundary_test<2, 3, true>(mesh3D, "3D tets_and_hexes");
+    boundary_test<3, 3, true>(mesh3D, "3D tets_and_hexes");
+    boundary_qoi_by_attribute();
   }
   if (which == "shape" || which == "all") {
     shape_aware<2>(mfem::Element::HEXAHEDRON, "hexes");

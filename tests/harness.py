@@ -14,7 +14,7 @@ KIND_TO_NAME = {5: "hex", 3: "quad", 4: "tet", 2: "tri"}
 def golden_names():
     """small fixtures with full reference outputs (the config_* files are full-size inputs + sampled outputs)"""
     names = sorted(os.path.splitext(os.path.basename(f))[0] for f in glob.glob(os.path.join(GOLDEN, "*.npz")))
-    return [n for n in names if not n.startswith(("config_", "bdr_", "multi_", "qoi_", "bqoi_", "l2param_", "krylov_", "newton_", "warmstart_"))]
+    return [n for n in names if not n.startswith(("config_", "bdr_", "multi_", "qoi_", "bqoi_", "l2param_", "krylov_", "newton_", "warmstart_", "l2faces_"))]
 
 
 def multifield_golden_names():

@@ -14,7 +14,7 @@ pytestmark = pytest.mark.gpu
 BIN = os.path.join(ROOT, "tests", "cpp", "functional_mfem_test")
 
 
-@pytest.mark.parametrize("suite", ["comparisons", "l2", "gradients", "scalar", "domains", "qoi", "nonlinear", "shape"])
+@pytest.mark.parametrize("suite", ["comparisons", "l2", "gradients", "scalar", "domains", "qoi", "nonlinear", "boundary", "shape"])
 def test_reference_unit_tests_through_the_mfem_typed_functional(suite):
     if not os.path.exists(BIN):
         pytest.skip("tests/cpp/functional_mfem_test not built (needs oracle/_ref/mfem-install: make -C tests/cpp)")
