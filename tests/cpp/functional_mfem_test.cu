@@ -26,7 +26,9 @@
 //                 forms and MFEM's linear forms, nonlinear and two-argument QOIs through check_gradient's QOI overloads
 //                 (central difference vs assembled gradient vector vs directional derivative), vector-valued and L2
 //                 arguments, AddAreaIntegral / AddVolumeIntegral
-//   shape         ShapeAwareFunctional (shape_aware_functional.hpp:292-575): with a shape displacement p the residual
+//   shape         functional_shape_derivatives.cpp: the divergence theorem on the shape-displaced mixed meshes (the residual
+//                 and its derivative w.r.t. the shape field sum to zero);
+//                 ShapeAwareFunctional (shape_aware_functional.hpp:292-575): with a shape displacement p the residual
 //                 equals that of the plain Functional on the mesh whose nodes were moved by p
 // Meshes are generated (MakeCartesian3D + a smooth perturbation): the reference's mesh files are not on the GPU box.
 // Exit code 0 = all checks passed; every check prints one line.
@@ -353,6 +355,74 @@ struct IdentityFunctor {  // bug_boundary_qoi.cpp:27-33
   SERAC_HOST_DEVICE auto operator()(Arg1, Arg2) const
   {
     return 1.0;
+  }
+};
+
+// ---- functional_shape_derivatives.cpp:99-268: a vector field f(x) = C m(x), m = the monomials of degree <= p, C(i, j) =
+// (i + 1) / (j + 1); the domain integrand is div f, the boundary integrand -f . n --------------------------------------------
+template <int dim, int p>
+struct MonomialField {
+  static constexpr int nm = (dim == 2) ? ((p + 1) * (p + 2)) / 2 : ((p + 1) * (p + 2) * (p + 3)) / 6;
+  /// exponents of monomial j in the reference's order: 1, x, y, (z,) x^2, xy, (xz,) y^2, (yz, z^2)
+  static SERAC_HOST_DEVICE void exponents(int j, int (&e)[3])
+  {
+    const int e2[6][3]  = {{0, 0, 0}, {1, 0, 0}, {0, 1, 0}, {2, 0, 0}, {1, 1, 0}, {0, 2, 0}};
+    const int e3[10][3] = {{0, 0, 0}, {1, 0, 0}, {0, 1, 0}, {0, 0, 1}, {2, 0, 0}, {1, 1, 0}, {1, 0, 1}, {0, 2, 0}, {0, 1, 1}, {0, 0, 2}};
+    for (int d = 0; d < 3; d++) e[d] = (dim == 2) ? e2[j][d] : e3[j][d];
+  }
+  template <typename T>
+  static SERAC_HOST_DEVICE T power(T x, int n)
+  {
+    T r = x * 0.0 + 1.0;
+    for (int i = 0; i < n; i++) r = r * x;
+    return r;
+  }
+  template <typename T>
+  static SERAC_HOST_DEVICE tensor<T, dim> value(const tensor<T, dim>& X)
+  {
+    tensor<T, dim> f{};
+    for (int j = 0; j < nm; j++) {
+      int e[3];
+      exponents(j, e);
+      T m = X[0] * 0.0 + 1.0;
+      for (int d = 0; d < dim; d++) m = m * power(X[d], e[d]);
+      for (int i = 0; i < dim; i++) f[i] = f[i] + (double(i + 1) / (j + 1)) * m;
+    }
+    return f;
+  }
+  template <typename T>
+  static SERAC_HOST_DEVICE T divergence(const tensor<T, dim>& X)
+  {
+    T div = X[0] * 0.0;
+    for (int j = 0; j < nm; j++) {
+      int e[3];
+      exponents(j, e);
+      for (int i = 0; i < dim; i++) {  // d m_j / d x_i
+        if (e[i] == 0) continue;
+        T dm = X[0] * 0.0 + double(e[i]);
+        for (int d = 0; d < dim; d++) dm = dm * power(X[d], d == i ? e[d] - 1 : e[d]);
+        div = div + (double(i + 1) / (j + 1)) * dm;
+      }
+    }
+    return div;
+  }
+};
+template <int dim, int p>
+struct DivergenceFunctor {  // TestFunctorOne, :245-252
+  template <typename Position>
+  SERAC_HOST_DEVICE auto operator()(double, Position position) const
+  {
+    return serac::tuple{MonomialField<dim, p>::divergence(get<VALUE>(position)), zero{}};
+  }
+};
+template <int dim, int p>
+struct NormalFluxFunctor {  // TestFunctorTwo, :254-264
+  template <typename Position>
+  SERAC_HOST_DEVICE auto operator()(double, Position position) const
+  {
+    auto [X, dX_dxi] = position;
+    auto n           = normalize(cross(dX_dxi));
+    return -dot(MonomialField<dim, p>::value(X), n);
   }
 };
 
@@ -943,6 +1013,33 @@ void boundary_qoi_by_attribute()
          "BoundaryIntegralQOI AttrBug: perimeter %.15g (4), boundary attribute 1 %.15g (1)", totalSurfaceArea, attr1SurfaceArea);
 }
 
+// ---- functional_shape_derivatives.cpp:266-345: the divergence theorem on the shape-displaced mesh --------------------------
+template <int p, int dim>
+void shape_derivative(mfem::Mesh& mesh, const char* tag, double tolerance)
+{
+  using test_space  = H1<p>;
+  using trial_space = H1<p>;
+  using shape_space = H1<p, dim>;
+  mfem::H1_FECollection    fec(p, dim);
+  mfem::FiniteElementSpace fes1(&mesh, &fec), fes2(&mesh, &fec, dim, mfem::Ordering::byVDIM);
+  mfem::Vector ones(fes1.GetVSize()), U1(fes1.GetVSize()), U2(fes2.GetVSize()), dU2(fes2.GetVSize());
+  ones = 1;
+  U1.Randomize(1);
+  U2.Randomize(2);
+  U2 *= 0.1;
+  dU2.Randomize(3);
+  ShapeAwareFunctional<shape_space, test_space(trial_space)> residual(&fes2, &fes1, {&fes1});
+  residual.AddDomainIntegral(Dimension<dim>{}, DependsOn<>{}, DivergenceFunctor<dim, p>{}, mesh);
+  residual.AddBoundaryIntegral(Dimension<dim - 1>{}, DependsOn<>{}, NormalFluxFunctor<dim, p>{}, mesh);
+  auto [r, drdU2] = residual(0.0, differentiate_wrt(U2), U1);
+  const double sum_r = r * ones;
+  mfem::Vector dr    = drdU2(dU2);
+  const double sum_dr = ones * dr;
+  EXPECT(std::fabs(sum_r) < tolerance && std::fabs(sum_dr) < tolerance,
+         "ShapeDerivative %s p=%d: sum of the residual %.2e, of its shape derivative %.2e (tolerance %.1e)", tag, p, sum_r, sum_dr,
+         tolerance);
+}
+
 // ---- functional_with_domain.cpp --------------------------------------------------------------------------------------------
 template <int ptest, int ptrial, int dim>
 void whole_mesh_comparison(mfem::Mesh& mesh, const char* tag)  // :89-146: integrals on complementary domains add up
@@ -1423,6 +1520,14 @@ int main(int argc, char** argv)
     boundary_qoi_by_attribute();
   }
   if (which == "shape" || which == "all") {
+    {  // functional_shape_derivatives.cpp:347-352 (the reference's tolerances)
+      mfem::Mesh mesh2D = make_mixed_mesh_2d();
+      mfem::Mesh mesh3D = make_mixed_mesh_3d();
+      shape_derivative<1, 2>(mesh2D, "2D tris_and_quads", 3.0e-14);
+      shape_derivative<2, 2>(mesh2D, "2D tris_and_quads", 3.0e-14);
+      shape_derivative<1, 3>(mesh3D, "3D tets_and_hexes", 2.0e-13);
+      shape_derivative<2, 3>(mesh3D, "3D tets_and_hexes", 1.5e-2);
+    }
     shape_aware<2>(mfem::Element::HEXAHEDRON, "hexes");
     shape_aware<1>(mfem::Element::TETRAHEDRON, "tets");
   }
