@@ -399,7 +399,26 @@ def run_product(args):
     r_E = torch.empty(G.ESize(), dtype=torch.float64, device=dev)
     views = {}
 
+    # experiment (off): the residual's scatter does not gate the Jacobian action (which needs the stored derivatives
+    # only), so it can run on a second stream: sb_functional_evaluate_begin (all elements) / _end (the scatter).  Measured:
+    # no gain (0.2796 vs 0.2788 ms, profiles/r3_experiments.md) -- the action kernel is persistent and holds every SM, so
+    # the scatter's CTAs wait for it anyway
+    fork_scatter = world == 1 and os.environ.get("SB_BENCH_FORK_SCATTER", "0") != "0"
+    aux = torch.cuda.Stream() if fork_scatter else None
+    ev_fork, ev_join = torch.cuda.Event(), torch.cuda.Event()
+
     def step_device():
+        if fork_scatter:
+            cur = torch.cuda.current_stream()
+            call.evaluate_begin(0.0, [S, U, A], wrt=1, split_element=P["ne"])
+            ev_fork.record(cur)
+            with torch.cuda.stream(aux):
+                aux.wait_event(ev_fork)
+                call.evaluate_end(out=r)
+                ev_join.record(aux)
+            call.GradientMult(1, dU, out=dr)
+            cur.wait_event(ev_join)
+            return
         if overlap:
             call.prefetch_direction(1, dU)  # side stream: the exchange of the JVP direction runs next to the evaluation
         if inplace:  # results are the prefixes of the Functional's own L-vectors
@@ -702,7 +721,9 @@ def run_product(args):
                    "qpts_per_gpu": P["nq"],
                    "l2_policy": f"inputs larger than L2 ({648.0 * P['nq'] / 1e6:.0f} MB of stored derivatives streamed each "
                                 "step)",
-                   "step_launch": "CUDA graph replay" if use_graph else "kernel by kernel",
+                   "step_launch": ("CUDA graph replay" if use_graph else "kernel by kernel")
+                                  + ("; the residual's scatter runs on a second stream under the Jacobian-action kernel"
+                                     if fork_scatter else ""),
                    "parallelism": f"1 mesh partition per GPU x{world}"
                                   + (f", shared-dof exchange over {P['transport']}"
                                      + (", in place (owned-first numbering), overlapped on a side stream"

@@ -345,7 +345,11 @@ int sb_functional_wait(sb_functional_t F);
 /* operator() in two halves, device buffers only: _begin evaluates, for every domain integral that covers the whole mesh,
  * the elements [0, split_element) -- with partitions whose halo-dependent elements are numbered last these need no data
  * from other ranks, so the caller issues the halo puts, calls _begin, waits for / unpacks the halo, and calls _end, which
- * evaluates the remaining elements (and every other integral) and scatters.  Same result as sb_functional_evaluate. */
+ * evaluates the remaining elements (and every other integral) and scatters.  Same result as sb_functional_evaluate.
+ * With split_element = the number of elements _begin is the evaluation kernel and _end the scatter alone: a caller that
+ * wants the Jacobian action next can issue _end on a second stream (after an event recorded behind _begin) and
+ * sb_functional_jvp on the first -- the action needs the stored derivatives, not the scattered residual, and uses an
+ * E-vector of its own, so the residual's scatter runs under the (HBM-bound) action kernel. */
 int sb_functional_evaluate_begin(sb_functional_t F, double t, int wrt, const double* const* inputs_dev, int update_state,
                                  int64_t split_element, void* stream);
 int sb_functional_evaluate_end(sb_functional_t F, double* output_dev, void* stream);

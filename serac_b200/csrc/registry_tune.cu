@@ -1,5 +1,15 @@
 // serac_b200: tuning variants of the config-A integrand (not part of the default build: make TUNE=1).
 // name: tune_e<EPB>_r<ROWS>_m<MINB>
+#ifndef TUNE_SET
+#define TUNE_SET 0
+#endif
+// sets 2 / 3: several elements per evaluation CTA, (element, point) flattened over the warps (216 threads = 7 warps at
+// 96% lane use instead of one warp at 84%), at the price of block barriers
+#if TUNE_SET == 2
+#define SB_EVAL_CTA_E_HEX_Q3 8
+#elif TUNE_SET == 3
+#define SB_EVAL_CTA_E_HEX_Q3 16
+#endif
 #include "registry.hpp"
 
 namespace sb {
@@ -37,7 +47,10 @@ TUNE(4, 1, 16)
 TUNE(4, 1, 18)
 #elif TUNE_SET == 1
 TUNE(4, 1, 20)
-TUNE(8, 1, 16)
+#elif TUNE_SET == 2
+TUNE(8, 1, 2)
+#elif TUNE_SET == 3
+TUNE(16, 1, 1)
 #endif
 }  // namespace
 }  // namespace sb
