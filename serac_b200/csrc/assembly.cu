@@ -20,6 +20,7 @@
 #include <algorithm>
 #include <cstring>
 #include <numeric>
+#include <cstdlib>
 #include <thread>
 
 #include "internal.hpp"
@@ -500,7 +501,9 @@ int csr_assemble_rows(sb_csr_t A, sb_integral_t I, int local_wrt, sb_restriction
     int64_t   longest = 0;  // a group holds at least one whole row
     for (size_t n = 0; n + 1 < A->node_row_ptr.size(); n++)
       longest = std::max(longest, (A->node_row_ptr[n + 1] - A->node_row_ptr[n]) * A->ck);
-    const int cap = int(std::min<int64_t>(std::max<int64_t>(SB_ASM_ACC_CAP, longest), (220 * 1024) / 8 - fixed));
+    int64_t want = SB_ASM_ACC_CAP;
+    if (const char* env = std::getenv("SB_ASM_ACC_CAP")) want = std::max(64, std::atoi(env));  // tuning experiments
+    const int cap = int(std::min<int64_t>(std::max<int64_t>(want, longest), (220 * 1024) / 8 - fixed));
     const Expansion X{A->ct, A->ck, test->ordering == SB_ORDERING_BYVDIM, trial->ordering == SB_ORDERING_BYVDIM,
                       test->num_nodes, trial->num_nodes, A->node_row_ptr[size_t(test->num_nodes)]};
     HostPlan  H = build_plan(test->table_host.data(), test->npe, A->ct, test->num_nodes, trial->table_host.data(),
