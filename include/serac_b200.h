@@ -272,6 +272,13 @@ int     sb_csr_create(sb_restriction_t test, sb_restriction_t trial, sb_csr_t* o
  * pattern is the union over the blocks (tests[b], trials[b]): the restrictions of the two spaces on the elements of
  * geometry b.  All blocks of a space share its num_nodes, components and ordering. */
 int     sb_csr_create_blocks(int num_blocks, const sb_restriction_t* tests, const sb_restriction_t* trials, sb_csr_t* out);
+/* The pattern of A^T as a pattern object of its own (rows = trial vdofs), and its values from those of A: what
+ * HypreParMatrix::Transpose() gives the adjoint solve and MultTranspose the sensitivities
+ * (src/serac/physics/solid_mechanics.hpp:1362-1371, 1404-1424, 1466-1501).  Everything that takes a (pattern, values)
+ * pair -- sb_csr_spmv, the elimination of essential dofs, the Krylov solvers of serac_b200_solvers.h -- works on the
+ * transposed pair; column indices are ascending within a row, as in every pattern of this library. */
+int     sb_csr_transpose(sb_csr_t A, sb_csr_t* A_transposed_out);
+int     sb_csr_transpose_values(sb_csr_t A_transposed, const double* values_dev, double* values_transposed_dev, void* stream);
 /* The same pattern computed on the host from raw restriction tables ([num_elements][npe] node ids): what
  * sb_csr_create runs before uploading, callable without a device (parity tests of the pattern on CPU-only machines).
  * Call with col_ind_host == NULL to get nnz and row_ptr first. */

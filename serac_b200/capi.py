@@ -74,6 +74,8 @@ SIGNATURES = {
     "sb_integral_derivative_mask": (_i, [_vp, _i]),
     "sb_csr_create": (_i, [_vp, _vp, _pp]),
     "sb_csr_create_blocks": (_i, [_i, _vp, _vp, _pp]),
+    "sb_csr_transpose": (_i, [_vp, _pp]),
+    "sb_csr_transpose_values": (_i, [_vp, _vp, _vp, _vp]),
     "sb_csr_pattern_host": (_i, [_vp, _i, _i, _i64, _i, _vp, _i, _i, _i64, _i, _i64, _vp, _vp, C.POINTER(_i64)]),
     "sb_debug_assembly_plan_host": (_i, [_vp, _i, _i, _i64, _i, _vp, _i, _i, _i64, _i, _i64, _vp, _i64, _i, _i, _vp, _vp,
                                         _vp, C.POINTER(_i)]),
@@ -407,6 +409,22 @@ class CsrPattern:
             lib().sb_csr_destroy(self.h)
         except Exception:
             pass
+
+    def transpose(self):
+        """the pattern of A^T (HypreParMatrix::Transpose, solid_mechanics.hpp:1365): a CsrPattern whose
+        transpose_values(values) reorders the values of A into those of A^T"""
+        h = C.c_void_p()
+        check(lib().sb_csr_transpose(self.h, C.byref(h)))
+        t = CsrPattern(self._keep[1], self._keep[0], handle=h)
+        t._of = self
+        return t
+
+    def transpose_values(self, values, out=None):
+        import torch
+        if out is None:
+            out = torch.empty_like(values)
+        check(lib().sb_csr_transpose_values(self.h, _dev_ptr(values), _dev_ptr(out), _stream_ptr()))
+        return out
 
     def to_host(self):
         rp = np.empty(self.num_rows + 1, dtype=np.int32)

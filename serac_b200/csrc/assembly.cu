@@ -439,6 +439,85 @@ extern "C" int sb_csr_create(sb_restriction_t test, sb_restriction_t trial, sb_c
   return sb_csr_create_blocks(1, &test, &trial, out);
 }
 
+// ---- transposed pattern (adjoint solves and sensitivities: HypreParMatrix::Transpose / MultTranspose,
+//      src/serac/physics/solid_mechanics.hpp:1362-1371, 1404-1424) -------------------------------------------------------
+__global__ void transpose_keys_kernel(const int* __restrict__ row_ptr, const int* __restrict__ col_ind, long long num_rows,
+                                      unsigned long long* __restrict__ keys, int* __restrict__ col_count)
+{
+  // one warp per row: keys[k] = (column << 32) | row; column histogram (integer atomics: order-independent)
+  const long long warp = (blockIdx.x * (long long)blockDim.x + threadIdx.x) / 32;
+  const int       lane = threadIdx.x % 32;
+  const long long nw   = (long long)gridDim.x * blockDim.x / 32;
+  for (long long r = warp; r < num_rows; r += nw) {
+    for (int k = row_ptr[r] + lane; k < row_ptr[r + 1]; k += 32) {
+      const int c = col_ind[k];
+      keys[k]     = ((unsigned long long)(unsigned)c << 32) | (unsigned long long)(unsigned)r;
+      atomicAdd(&col_count[c + 1], 1);
+    }
+  }
+}
+
+__global__ void transpose_cols_kernel(const unsigned long long* __restrict__ keys, long long nnz, int* __restrict__ col_ind_T)
+{
+  for (long long k = blockIdx.x * (long long)blockDim.x + threadIdx.x; k < nnz; k += (long long)gridDim.x * blockDim.x)
+    col_ind_T[k] = int(keys[k] & 0xFFFFFFFFull);
+}
+
+__global__ void transpose_values_kernel(const int* __restrict__ perm, const double* __restrict__ values,
+                                        double* __restrict__ values_T, long long nnz)
+{
+  for (long long k = blockIdx.x * (long long)blockDim.x + threadIdx.x; k < nnz; k += (long long)gridDim.x * blockDim.x)
+    values_T[k] = values[perm[k]];
+}
+
+extern "C" int sb_csr_transpose(sb_csr_t A, sb_csr_t* out)
+{
+  SB_REQUIRE(A && out, "sb_csr_transpose: NULL argument");
+  auto T      = std::make_unique<sb_csr_s>();
+  T->nnz      = A->nnz;
+  T->num_rows = A->num_cols;
+  T->num_cols = A->num_rows;
+  T->ct = A->ck, T->ck = A->ct;
+  T->test_ordering = A->trial_ordering, T->trial_ordering = A->test_ordering;
+  T->num_test_nodes = A->num_trial_nodes, T->num_trial_nodes = A->num_test_nodes;
+  T->test = A->trial, T->trial = A->test;
+  if (int e = dev_alloc(&T->row_ptr_dev, size_t(T->num_rows + 1))) return e;
+  SB_CHECK_CUDA(cudaMemset(T->row_ptr_dev, 0, size_t(T->num_rows + 1) * sizeof(int)));
+  if (int e = dev_alloc(&T->col_ind_dev, size_t(std::max<int64_t>(T->nnz, 1)))) return e;
+  if (int e = dev_alloc(&T->transpose_perm_dev, size_t(std::max<int64_t>(T->nnz, 1)))) return e;
+  if (A->nnz > 0) {
+    unsigned long long* keys = nullptr;
+    if (int e = dev_alloc(&keys, size_t(A->nnz))) return e;
+    transpose_keys_kernel<<<grid_for(A->num_rows * 32, 256), 256>>>(A->row_ptr_dev, A->col_ind_dev, A->num_rows, keys,
+                                                                     T->row_ptr_dev);
+    SB_CHECK_CUDA(cudaGetLastError());
+    thrust::device_ptr<unsigned long long> k(keys);
+    thrust::device_ptr<int>                v(T->transpose_perm_dev);
+    thrust::sequence(thrust::device, v, v + A->nnz);
+    thrust::sort_by_key(thrust::device, k, k + A->nnz, v);  // keys are unique: (column, row) ascending
+    thrust::device_ptr<int> rp(T->row_ptr_dev);
+    thrust::inclusive_scan(thrust::device, rp, rp + T->num_rows + 1, rp);
+    transpose_cols_kernel<<<grid_for(A->nnz, 256), 256>>>(keys, A->nnz, T->col_ind_dev);
+    SB_CHECK_CUDA(cudaGetLastError());
+    SB_CHECK_CUDA(cudaDeviceSynchronize());
+    cudaFree(keys);
+  }
+  *out = T.release();
+  return SB_OK;
+}
+
+extern "C" int sb_csr_transpose_values(sb_csr_t At, const double* values_dev, double* values_T_dev, void* stream)
+{
+  SB_REQUIRE(At && At->transpose_perm_dev, "sb_csr_transpose_values: the pattern was not made by sb_csr_transpose");
+  if (At->nnz == 0) return SB_OK;
+  SB_REQUIRE(values_dev && values_T_dev && values_dev != values_T_dev, "sb_csr_transpose_values: bad value arrays");
+  transpose_values_kernel<<<grid_for(At->nnz, 256), 256, 0, cudaStream_t(stream)>>>(At->transpose_perm_dev, values_dev,
+                                                                                      values_T_dev, At->nnz);
+  sb_count_launch();
+  SB_CHECK_CUDA(cudaGetLastError());
+  return SB_OK;
+}
+
 static void free_plan(AssemblyPlan& P)
 {
   cudaFree(P.groups_dev);
@@ -458,6 +537,7 @@ extern "C" int sb_csr_destroy(sb_csr_t A)
   for (auto& kv : A->plans) free_plan(kv.second);
   cudaFree(A->row_ptr_dev);
   cudaFree(A->col_ind_dev);
+  cudaFree(A->transpose_perm_dev);
   delete A;
   return SB_OK;
 }

@@ -123,4 +123,5 @@ struct sb_csr_s {
   sb_restriction_t     test = nullptr, trial = nullptr;  // the restrictions the pattern was built from (not owned)
   std::map<std::pair<sb_restriction_t, sb_restriction_t>, CsrExtraMap> extra;
   std::map<std::pair<const void*, int>, AssemblyPlan>                  plans;  // keyed by (integral, wrt)
+  int* transpose_perm_dev = nullptr;  // patterns made by sb_csr_transpose: values_T[k] = values[transpose_perm[k]]
 };

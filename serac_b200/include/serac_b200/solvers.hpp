@@ -92,11 +92,33 @@ class DeviceCsrMatrix {
     d.SetSize(Height());
     SERAC_B200_CHECK(sb_csr_diagonal(pattern_, values_.Read(), d.Write(), nullptr));
   }
+  /// HypreParMatrix::Transpose() (the adjoint solve of SolidMechanics::reverseAdjointTimestep, solid_mechanics.hpp:1362-1371):
+  /// a matrix of its own, on the transposed pattern (created on first use and kept with this matrix)
+  std::unique_ptr<DeviceCsrMatrix> Transpose()
+  {
+    if (!transposed_pattern_) SERAC_B200_CHECK(sb_csr_transpose(pattern_, &transposed_pattern_));
+    auto T = std::make_unique<DeviceCsrMatrix>(transposed_pattern_, Height());
+    SERAC_B200_CHECK(sb_csr_transpose_values(transposed_pattern_, values_.Read(), T->values_.Write(), nullptr));
+    return T;
+  }
+  /// mfem::Operator::MultTranspose (sensitivities: drdparam_mat->MultTranspose(adjoint, sensitivity), :1404-1424)
+  void MultTranspose(const Vector& x, Vector& y)
+  {
+    auto T = Transpose();
+    T->Mult(x, y);
+  }
+  ~DeviceCsrMatrix()
+  {
+    if (transposed_pattern_) sb_csr_destroy(transposed_pattern_);
+  }
+  DeviceCsrMatrix(const DeviceCsrMatrix&)            = delete;
+  DeviceCsrMatrix& operator=(const DeviceCsrMatrix&) = delete;
 
  private:
   sb_csr_t pattern_;
   int64_t  width_;
   Vector   values_;
+  sb_csr_t transposed_pattern_ = nullptr;  ///< owned; the transposed matrices made from it must not outlive this one
 };
 
 /// assemble(Gradient&) (functional.hpp:569-667) with the values left on the device
