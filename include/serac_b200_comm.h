@@ -45,6 +45,32 @@ int sb_halo_Pt_nccl(sb_halo_t H, sb_comm_t c, const double* L_dev, double* T_dev
  * Every rank calls it the same number of times, for halo objects built from the same partition. */
 int sb_halo_enable_peer_ipc(sb_halo_t H, sb_comm_t c);
 
+/* ---------------------------------------------------------------------------------------------------------------
+ * The assembled Jacobian of a partitioned Functional as an operator on T-vectors, and mfem::CGSolver on it.
+ *
+ * The reference turns the rank-local matrix A_L into K = P^T A_L P with hypre's RAP (F/functional.hpp:654-662) and hands K
+ * to hypre's solvers.  Without hypre the product stays in its factors (sub-assembled form): every rank keeps the CSR
+ * matrix of its own elements over its L-dofs (what sb_functional_assemble writes, no communication) and
+ * y_T = P^T (A_L (P x_T)), with the exchanges that surround every evaluation.  diag K = P^T diag A_L (Jacobi).
+ * sb_par_csr_create eliminates the essential dofs (local L ids, every local copy, owned or not) from the local values IN
+ * PLACE -- rows and columns zeroed, unit diagonal on the owner's copy only, so that K = [K_ii 0; 0 I] as
+ * eliminateAllEssentialDofsFromMatrix leaves it (boundary_condition_manager.hpp:91-94).  H needs its neighbour ranks
+ * (sb_halo_set_neighbor_ranks); the exchanges run over NCCL point-to-point.
+ * ------------------------------------------------------------------------------------------------------------- */
+typedef struct sb_par_csr_s* sb_par_csr_t;
+int sb_par_csr_create(sb_comm_t c, sb_halo_t H, sb_csr_t A_L, double* values_dev, const int* ess_local_dofs_host,
+                      int64_t num_ess, sb_par_csr_t* out);
+int sb_par_csr_destroy(sb_par_csr_t K);
+int sb_par_csr_mult(sb_par_csr_t K, const double* x_T_dev, double* y_T_dev, void* stream);
+int sb_par_csr_diagonal(sb_par_csr_t K, double* diag_T_dev, void* stream);
+/* (x, y) over the true dofs of all ranks (every true dof lives on exactly one rank); synchronises the stream */
+int sb_par_dot(sb_comm_t c, const double* x_T_dev, const double* y_T_dev, int64_t tsize, double* result_host, void* stream);
+/* mfem::CGSolver (mfem/linalg/solvers.cpp:719-897) on T-vectors across the ranks: the recurrences and the stopping test
+ * of sb_cg_solve_csr with every inner product reduced over the ranks (two reductions per iteration, as hypre's PCG).
+ * x_T_dev is the result (initial guess 0); diag_inv_T_dev = Jacobi scaling or NULL. */
+int sb_par_cg_solve(sb_par_csr_t K, const double* diag_inv_T_dev, const double* b_T_dev, double* x_T_dev, double rel_tol,
+                    double abs_tol, int max_iter, int* converged, int* final_iter, double* final_norm, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

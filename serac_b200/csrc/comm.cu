@@ -266,3 +266,188 @@ extern "C" int sb_halo_enable_peer_ipc(sb_halo_t H, sb_comm_t c)
   // 5. nobody writes into a ring before every rank has zeroed and published its own
   return sb_comm_barrier(c, nullptr);
 }
+
+
+// ===================================================================================================================
+// K = P^T A_L P in sub-assembled form and CG on it (include/serac_b200_comm.h)
+// ===================================================================================================================
+#include "serac_b200_solvers.h"
+
+struct sb_par_csr_s {
+  sb_comm_t     c = nullptr;
+  sb_halo_t     H = nullptr;
+  sb_csr_t      A = nullptr;
+  const double* values = nullptr;
+  double*       xL = nullptr;
+  double*       yL = nullptr;
+  double*       scalar = nullptr;  // device scalar of the all-reduced inner products
+  double*       work[3] = {nullptr, nullptr, nullptr};  // r, z, d of the solver (T-sized)
+};
+
+namespace {
+__global__ void zero_ghost_diagonal_kernel(const int* __restrict__ ess, long long num_ess, const int* __restrict__ ltdof,
+                                           const int* __restrict__ row_ptr, const int* __restrict__ col_ind,
+                                           double* __restrict__ values)
+{
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < num_ess; i += (long long)gridDim.x * blockDim.x) {
+    const int b = ess[i];
+    if (ltdof[b] >= 0) continue;  // the owner's copy keeps the unit diagonal
+    int lo = row_ptr[b], hi = row_ptr[b + 1] - 1;
+    while (lo <= hi) {
+      const int mid = (lo + hi) >> 1, cc = col_ind[mid];
+      if (cc == b) {
+        values[mid] = 0.0;
+        break;
+      }
+      if (cc < b)
+        lo = mid + 1;
+      else
+        hi = mid - 1;
+    }
+  }
+}
+__global__ void scale_kernel(double* __restrict__ z, const double* __restrict__ dinv, const double* __restrict__ r, long long n)
+{
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+    z[i] = dinv ? dinv[i] * r[i] : r[i];
+}
+__global__ void cg_step_kernel(double* __restrict__ x, double* __restrict__ r, const double* __restrict__ d,
+                               const double* __restrict__ z, double alpha, long long n)
+{
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    x[i] += alpha * d[i];
+    r[i] -= alpha * z[i];
+  }
+}
+__global__ void cg_direction_kernel2(double* __restrict__ d, const double* __restrict__ z, double beta, long long n)
+{
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+    d[i] = z[i] + beta * d[i];
+}
+}  // namespace
+
+extern "C" int sb_par_csr_create(sb_comm_t c, sb_halo_t H, sb_csr_t A, double* values, const int* ess_host, int64_t num_ess,
+                                 sb_par_csr_t* out)
+{
+  SB_REQUIRE(c && H && A && values && out && num_ess >= 0, "sb_par_csr_create: bad arguments");
+  SB_REQUIRE(A->num_rows == H->lsize && A->num_cols == H->lsize, "sb_par_csr_create: the matrix must be L x L of the halo's space");
+  auto K    = std::make_unique<sb_par_csr_s>();
+  K->c      = c;
+  K->H      = H;
+  K->A      = A;
+  K->values = values;
+  if (num_ess > 0) {
+    SB_REQUIRE(ess_host != nullptr, "sb_par_csr_create: NULL essential dof list");
+    int* ess_dev = nullptr;
+    if (int e = dev_upload(&ess_dev, ess_host, size_t(num_ess))) return e;
+    if (int e = sb_csr_eliminate_rows_cols(A, values, ess_dev, num_ess, nullptr, nullptr)) return e;
+    zero_ghost_diagonal_kernel<<<grid_for(num_ess, 128), 128>>>(ess_dev, num_ess, H->ltdof_dev, A->row_ptr_dev, A->col_ind_dev,
+                                                                values);
+    SB_CHECK_CUDA(cudaGetLastError());
+    SB_CHECK_CUDA(cudaDeviceSynchronize());
+    cudaFree(ess_dev);
+  }
+  if (int e = dev_alloc(&K->xL, size_t(std::max<int64_t>(H->lsize, 1)))) return e;
+  if (int e = dev_alloc(&K->yL, size_t(std::max<int64_t>(H->lsize, 1)))) return e;
+  if (int e = dev_alloc(&K->scalar, 1)) return e;
+  for (auto& w : K->work)
+    if (int e = dev_alloc(&w, size_t(std::max<int64_t>(H->tsize, 1)))) return e;
+  *out = K.release();
+  return SB_OK;
+}
+
+extern "C" int sb_par_csr_destroy(sb_par_csr_t K)
+{
+  if (!K) return SB_OK;
+  cudaFree(K->xL);
+  cudaFree(K->yL);
+  cudaFree(K->scalar);
+  for (auto w : K->work) cudaFree(w);
+  delete K;
+  return SB_OK;
+}
+
+extern "C" int sb_par_csr_mult(sb_par_csr_t K, const double* x_T, double* y_T, void* stream)
+{
+  SB_REQUIRE(K && x_T && y_T, "sb_par_csr_mult: NULL argument");
+  if (int e = sb_halo_P_nccl(K->H, K->c, x_T, K->xL, stream)) return e;
+  if (int e = sb_csr_spmv(K->A, K->values, K->xL, K->yL, stream)) return e;
+  return sb_halo_Pt_nccl(K->H, K->c, K->yL, y_T, stream);
+}
+
+extern "C" int sb_par_csr_diagonal(sb_par_csr_t K, double* diag_T, void* stream)
+{
+  SB_REQUIRE(K && diag_T, "sb_par_csr_diagonal: NULL argument");
+  if (int e = sb_csr_diagonal(K->A, K->values, K->yL, stream)) return e;
+  return sb_halo_Pt_nccl(K->H, K->c, K->yL, diag_T, stream);
+}
+
+static int par_dot(sb_comm_t c, double* scalar_dev, const double* x, const double* y, int64_t n, double* result, void* stream)
+{
+  double local = 0.0;
+  if (n > 0)
+    if (int e = sb_vector_dot(x, y, n, &local, stream)) return e;
+  cudaStream_t s = cudaStream_t(stream);
+  SB_CHECK_CUDA(cudaMemcpyAsync(scalar_dev, &local, sizeof(double), cudaMemcpyHostToDevice, s));
+  if (int e = sb_comm_allreduce_sum(c, scalar_dev, 1, stream)) return e;
+  SB_CHECK_CUDA(cudaMemcpyAsync(result, scalar_dev, sizeof(double), cudaMemcpyDeviceToHost, s));
+  SB_CHECK_CUDA(cudaStreamSynchronize(s));
+  return SB_OK;
+}
+
+extern "C" int sb_par_dot(sb_comm_t c, const double* x_T, const double* y_T, int64_t tsize, double* result_host, void* stream)
+{
+  SB_REQUIRE(c && result_host && tsize >= 0, "sb_par_dot: bad arguments");
+  double* scalar = nullptr;
+  if (int e = dev_alloc(&scalar, 1)) return e;
+  const int rc = par_dot(c, scalar, x_T, y_T, tsize, result_host, stream);
+  cudaFree(scalar);
+  return rc;
+}
+
+extern "C" int sb_par_cg_solve(sb_par_csr_t K, const double* dinv, const double* b, double* x, double rel_tol, double abs_tol,
+                               int max_iter, int* converged, int* final_iter, double* final_norm, void* stream)
+{
+  SB_REQUIRE(K && b && x && converged && final_iter && final_norm, "sb_par_cg_solve: NULL argument");
+  cudaStream_t  s = cudaStream_t(stream);
+  const int64_t n = K->H->tsize;
+  double *      r = K->work[0], *z = K->work[1], *d = K->work[2];
+  const int     grid = grid_for(std::max<int64_t>(n, 1), 256);
+  *converged = 0, *final_iter = 0, *final_norm = 0.0;
+  // mfem::CGSolver::Mult with iterative_mode = false (solvers.cpp:737-748): x = 0, r = b, z = B r, d = z
+  if (n) SB_CHECK_CUDA(cudaMemsetAsync(x, 0, size_t(n) * sizeof(double), s));
+  if (n) SB_CHECK_CUDA(cudaMemcpyAsync(r, b, size_t(n) * sizeof(double), cudaMemcpyDeviceToDevice, s));
+  scale_kernel<<<grid, 256, 0, s>>>(z, dinv, r, n);
+  if (n) SB_CHECK_CUDA(cudaMemcpyAsync(d, z, size_t(n) * sizeof(double), cudaMemcpyDeviceToDevice, s));
+  double nom = 0.0, den = 0.0, betanom = 0.0;
+  if (int e = par_dot(K->c, K->scalar, d, r, n, &nom, stream)) return e;
+  *final_norm = std::sqrt(std::max(nom, 0.0));
+  if (nom < 0.0) return SB_OK;  // the preconditioner is not positive definite (:765-775)
+  const double r0 = std::max(nom * rel_tol * rel_tol, abs_tol * abs_tol);
+  if (nom <= r0) {
+    *converged = 1;
+    return SB_OK;
+  }
+  if (int e = sb_par_csr_mult(K, d, z, stream)) return e;
+  if (int e = par_dot(K->c, K->scalar, z, d, n, &den, stream)) return e;
+  if (den <= 0.0) return SB_OK;  // the operator is not positive definite (:790-802)
+  for (int i = 1;; i++) {
+    const double alpha = nom / den;
+    cg_step_kernel<<<grid, 256, 0, s>>>(x, r, d, z, alpha, n);
+    scale_kernel<<<grid, 256, 0, s>>>(z, dinv, r, n);
+    if (int e = par_dot(K->c, K->scalar, r, z, n, &betanom, stream)) return e;
+    *final_iter = i;
+    *final_norm = std::sqrt(std::max(betanom, 0.0));
+    if (betanom <= r0) {
+      *converged = 1;
+      return SB_OK;
+    }
+    if (i + 1 > max_iter) return SB_OK;
+    const double beta = betanom / nom;
+    cg_direction_kernel2<<<grid, 256, 0, s>>>(d, z, beta, n);
+    if (int e = sb_par_csr_mult(K, d, z, stream)) return e;
+    if (int e = par_dot(K->c, K->scalar, d, z, n, &den, stream)) return e;
+    if (den <= 0.0) return SB_OK;
+    nom = betanom;
+  }
+}

@@ -23,6 +23,7 @@
 
 #include "serac_b200.h"
 #include "serac_b200_comm.h"
+#include "serac_b200_solvers.h"
 
 #define CHECK(expr)                                                                          \
   do {                                                                                       \
@@ -242,6 +243,49 @@ int run_rank(int rank, int world)
     sb_halo_destroy(Hs);
     sb_halo_destroy(Hu);
     sb_halo_destroy(Ha);
+  }
+  // ===== the Newton step's linear solve across the ranks: K = P^T A_L P in sub-assembled form, Jacobi, CG =====
+  if (access((rd + "/ess_local.bin").c_str(), R_OK) == 0) {
+    sb_halo_t Hs = make_halo(l1), Hu = make_halo(l2);
+    double *  S = to_device(hS), *U = to_device(hU), *A = to_device(hA);
+    double *  SL, *UL, *AL;
+    CUDA(cudaMalloc(&SL, sizeof(double) * size_t(l1.lsize)));
+    CUDA(cudaMalloc(&UL, sizeof(double) * L2));
+    CUDA(cudaMalloc(&AL, sizeof(double) * L2));
+    CHECK(sb_halo_P_nccl(Hs, comm, S, SL, nullptr));
+    CHECK(sb_halo_P_nccl(Hu, comm, U, UL, nullptr));
+    CHECK(sb_halo_P_nccl(Hu, comm, A, AL, nullptr));
+    const double* in[3] = {SL, UL, AL};
+    CHECK(sb_functional_evaluate(F, 0.0, 1, in, SB_DEVICE, r_L, SB_DEVICE, 0, nullptr));
+    sb_csr_t pat = nullptr;
+    CHECK(sb_csr_create(G, G, &pat));
+    double* values = nullptr;
+    CUDA(cudaMalloc(&values, sizeof(double) * size_t(sb_csr_nnz(pat))));
+    CHECK(sb_functional_assemble(F, 1, &pat, values, SB_DEVICE, nullptr));  // rank-local: no communication
+    auto         ess = read_bin<int>(rd + "/ess_local.bin");
+    sb_par_csr_t K   = nullptr;
+    CHECK(sb_par_csr_create(comm, Hu, pat, values, ess.data(), int64_t(ess.size()), &K));
+    double *diag = nullptr, *dinv = nullptr, *x = nullptr;
+    CUDA(cudaMalloc(&diag, sizeof(double) * T2));
+    CUDA(cudaMalloc(&dinv, sizeof(double) * T2));
+    CUDA(cudaMalloc(&x, sizeof(double) * T2));
+    CHECK(sb_par_csr_diagonal(K, diag, nullptr));
+    CHECK(sb_jacobi_setup(diag, dinv, int64_t(T2), nullptr));
+    double* b = to_device(read_bin<double>(rd + "/b_T.bin"));
+    int     converged = 0, iters = 0;
+    double  final_norm = 0.0;
+    CHECK(sb_par_cg_solve(K, dinv, b, x, 1e-12, 0.0, 5000, &converged, &iters, &final_norm, nullptr));
+    CUDA(cudaDeviceSynchronize());
+    write_bin(rd + "/out_cg_x.bin", to_host(x, T2));
+    write_bin(rd + "/out_cg_info.bin", std::vector<double>{double(converged), double(iters), final_norm});
+    // the operator itself on the right-hand side (compared with the global matrix)
+    CHECK(sb_par_csr_mult(K, b, x, nullptr));
+    CUDA(cudaDeviceSynchronize());
+    write_bin(rd + "/out_Kb.bin", to_host(x, T2));
+    sb_par_csr_destroy(K);
+    sb_csr_destroy(pat);
+    sb_halo_destroy(Hs);
+    sb_halo_destroy(Hu);
   }
   // ===== a reduction over the ranks: the true dofs of the partitions add up to the global space =====
   {

@@ -46,6 +46,21 @@ def test_two_ranks_from_cpp_match_the_whole_mesh(tmp_path):
     F.AddDomainIntegral(I, [0, 1, 2])
     r = F(0.0, [t(S), t(U), t(A)], wrt=1).cpu().numpy()
     dr = F.GradientMult(1, t(dU)).cpu().numpy()
+    # the Newton step's linear solve on the whole mesh: Jacobian eliminated at the face x = 0, Jacobi, CG
+    gx = mesh.node_grid(p)[0]
+    fixed = np.nonzero((np.arange(n) // 3) % gx == 0)[0].astype(np.int32)
+    b = rng.uniform(-1, 1, n)
+    b[fixed] = 0.0
+    pat, vals = F.assemble(1)
+    import scipy.sparse as sp
+    capi.eliminate_rows_cols(pat, vals, fixed, want_Ae=False)
+    rp, ci = pat.to_host()
+    K_global = sp.csr_matrix((vals.cpu().numpy(), ci, rp), shape=(n, n))
+    dinv = capi.jacobi_setup(capi.csr_diagonal(pat, vals))
+    cg = capi.CGSolver(n, rel_tol=1e-12, max_iter=5000)
+    x_global, info_global = cg.Mult(pat, t(b), values=vals, dinv=dinv)
+    assert info_global["converged"]
+    x_global = x_global.cpu().numpy()
     # the partition, one directory per rank
     d = str(tmp_path)
     with open(os.path.join(d, "meta.txt"), "w") as f:
@@ -67,6 +82,8 @@ def test_two_ranks_from_cpp_match_the_whole_mesh(tmp_path):
         _export_halo(rd, "p2", l2)
         _export_halo(rd, "p1", l1)
         gt, gt1 = part.global_true_vdofs(), part1.global_true_vdofs()
+        np.nonzero(np.isin(part.global_local_vdofs(), fixed))[0].astype(np.int32).tofile(os.path.join(rd, "ess_local.bin"))
+        b[gt].tofile(os.path.join(rd, "b_T.bin"))
         for name, vals, lsize in (("U", U[gt], l2["lsize"]), ("A", A[gt], l2["lsize"]), ("dU", dU[gt], l2["lsize"]),
                                   ("S", S[gt1], l1["lsize"])):
             buf = np.full(lsize, np.nan)  # L-sized; the prefix is the T-vector, the rest is filled by P
@@ -83,5 +100,10 @@ def test_two_ranks_from_cpp_match_the_whole_mesh(tmp_path):
             r_T = np.fromfile(os.path.join(rd, f"out_{tag}_r.bin"))
             dr_T = np.fromfile(os.path.join(rd, f"out_{tag}_dr.bin"))
             assert rel_l2(r_T, r[gt]) < 1e-13 and rel_l2(dr_T, dr[gt]) < 1e-13, (rk, tag)
+        # K = P^T A_L P (sub-assembled, include/serac_b200_comm.h) acts and solves like the global eliminated matrix
+        assert rel_l2(np.fromfile(os.path.join(rd, "out_Kb.bin")), (K_global @ b)[gt]) < 1e-13, rk
+        conv, iters, _ = np.fromfile(os.path.join(rd, "out_cg_info.bin"))
+        assert conv == 1.0 and abs(int(iters) - info_global["final_iter"]) <= 2, (iters, info_global)
+        assert rel_l2(np.fromfile(os.path.join(rd, "out_cg_x.bin")), x_global[gt]) < 1e-9, rk
         total = float(np.fromfile(os.path.join(rd, "out_sum_tsize.bin"))[0])
         assert total == n  # ncclAllReduce over the ranks: the true dofs add up to the global space
