@@ -260,7 +260,7 @@ def global_parity(P, dev, rank, world, r_T, dr_T):
     from serac_b200 import capi
     mesh, p = P["global_mesh"], P["p"]
     n = mesh.num_nodes(p) * 3
-    need = mesh.ne * (p + 1)**3 * 648.0 * 1.35 + 64.0 * n
+    need = mesh.ne * (p + 1)**3 * 360.0 * 1.6 + 64.0 * n
     free = torch.cuda.mem_get_info(dev)[0]
     fits = torch.tensor([1 if (rank != 0 or need < 0.8 * free) else 0], device=dev)
     dist.broadcast(fits, 0)
@@ -707,10 +707,20 @@ def run_product(args):
     # each), 81 stored derivatives (648 B), int32 restriction table (4 B)  = 666 B/qpt at p=2
     p = P["p"]
     V = 8.0 * 3 * p**3 / (p + 1)**3
-    jvp_bytes = (2 * V + 648.0 + 4.0) * P["nq"]
+    # the stored derivative: 81 doubles per point in the reference's layout (648 B); the NeoHookean tangent is symmetric
+    # and this library stores its upper triangle, 45 doubles (360 B).  The roofline is taken against the
+    # bytes THIS algorithm has to move; the same time against the reference's 648 B is reported beside it.
+    stored = P["integral"].derivative_stored_entries(1)
+    full = P["integral"].derivative_entries(1)
+    D, D_ref = 8.0 * stored, 8.0 * full
+    jvp_bytes = (2 * V + D + 4.0) * P["nq"]
     jvp_ms = phase_ms[2]
     achieved = jvp_bytes / (jvp_ms * 1e-3) / 1e9
-    eval_bytes = (3 * V + 0.9 + 96.0 + 648.0 + 4.0) * P["nq"]  # residual + derivative store, ~770 B/qpt (§8d)
+    eval_bytes = (3 * V + 0.9 + 96.0 + D + 4.0) * P["nq"]  # residual + derivative store, ~770 B/qpt at 81 entries (§8d)
+    ref_layout = {"derivative_doubles_per_qpt": {"stored": stored, "reference_layout": full},
+                  "jvp_GBps_if_reference_layout_bytes": (2 * V + D_ref + 4.0) * P["nq"] / (jvp_ms * 1e-3) / 1e9,
+                  "evaluate_GBps_if_reference_layout_bytes":
+                      (3 * V + 0.9 + 96.0 + D_ref + 4.0) * P["nq"] / (phase_ms[0] * 1e-3) / 1e9}
     out = {
         "metric": METRIC, "value": vdofs_total / (ms_per_step * 1e-3) / 1e9, "unit": "GDOF/s", "n_gpus": world,
         "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True,
@@ -719,7 +729,7 @@ def run_product(args):
         "config": {"workload": STRONG_WORKLOAD if STRONG_SCALING else WORKLOAD,
                    "mesh": P["mesh"], "vdofs_total": vdofs_total, "vdofs_per_gpu": P["vdofs"],
                    "qpts_per_gpu": P["nq"],
-                   "l2_policy": f"inputs larger than L2 ({648.0 * P['nq'] / 1e6:.0f} MB of stored derivatives streamed each "
+                   "l2_policy": f"inputs larger than L2 ({D * P['nq'] / 1e6:.0f} MB of stored derivatives streamed each "
                                 "step)",
                    "step_launch": ("CUDA graph replay" if use_graph else "kernel by kernel")
                                   + ("; the residual's scatter runs on a second stream under the Jacobian-action kernel"
@@ -740,7 +750,8 @@ def run_product(args):
         "phases_ms": {"evaluate_with_derivative_store": phase_ms[0], "scatter_r": phase_ms[1], "jvp": phase_ms[2],
                       "scatter_dr": phase_ms[3]},
         "qpts_per_s": P["nq"] * world / (ms_per_step * 1e-3),
-        "roofline": {"kernel": f"jvp_stream_kernel<3,{p + 1},{p + 1},3,{p + 1},3,8,*>", "bound": "hbm", "achieved": achieved,
+        "roofline": {"kernel": f"jvp_stream_kernel<3,{p + 1},{p + 1},3,{p + 1},3,{P['integral'].derivative_mask(1)},*>",
+                     "bound": "hbm", "achieved": achieved,
                      "peak": peak, "unit": "GB/s", "frac": achieved / peak, "peak_source": peak_src,
                      "algorithmic_bytes_per_launch": jvp_bytes,
                      "traffic": JVP_NCU_TRAFFIC_BYTES if BENCH_CONFIG != "b" else None,
@@ -751,6 +762,7 @@ def run_product(args):
                               "algorithmic_bytes_per_launch": eval_bytes,
                               "traffic": EVAL_NCU_TRAFFIC_BYTES if BENCH_CONFIG != "b" else None,
                               "traffic_source": NCU_TRAFFIC_SOURCE if BENCH_CONFIG != "b" else None},
+        "derivative_storage": ref_layout,
         "clocks": clocks,
         "host_path_equals_device_path": host_check,
     }

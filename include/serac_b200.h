@@ -215,6 +215,12 @@ typedef struct {
   /* stored derivatives are laid out [tile][entry][derivative_tile_elements x quadrature points]: 1 for hexahedra with
    * q >= 3 (every element its own tile), elements_per_block otherwise (sb_integral_export_derivatives converts back) */
   int derivative_tile_elements;
+  /* d flux / d grad stored as the upper triangle of a symmetric matrix (bit 16 of derivative_mask; an extension, see
+   * DESIGN.md 4d): derivative_entries counts what is stored, derivative_full_entries what the reference would store */
+  int derivative_full_entries[SB_MAX_TRIALS];
+  /* q-functions with run-time flags (geometric nonlinearity) may store differently per flag value: sb_integral_create
+   * calls this on its own copy of the table with the functor it was given (NULL = nothing depends on the functor) */
+  void (*specialize)(void* table, const void* qf_blob);
 } sb_kernel_table;
 
 int         sb_named_integrand_count(void);
@@ -254,7 +260,8 @@ int sb_integral_element_gradient(sb_integral_t I, int wrt, double* K_e_dev, void
 /* stored derivative w.r.t. `wrt`, converted to a dense reference-ordered array for parity checks:
  * out_dev[e][q][block entries in d00,d01,d10,d11 order, row-major, absent blocks skipped] */
 int sb_integral_export_derivatives(sb_integral_t I, int wrt, double* out_dev, void* stream);
-int sb_integral_derivative_entries(sb_integral_t I, int wrt);
+int sb_integral_derivative_entries(sb_integral_t I, int wrt);        /* per point, in the reference's (full) layout */
+int sb_integral_derivative_stored_entries(sb_integral_t I, int wrt); /* per point, as stored (symmetric tangents: fewer) */
 int sb_integral_derivative_mask(sb_integral_t I, int wrt);
 
 /* ---------------------------------------------------------------------------------------------------------------

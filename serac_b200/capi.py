@@ -34,6 +34,7 @@ class KernelTable(C.Structure):
         ("derivative_mask", _i * MAX_TRIALS), ("derivative_entries", _i * MAX_TRIALS), ("spatial_dim", _i),
         ("assemble_rows", _vp * MAX_TRIALS), ("assemble_rows_fixed_doubles", _i * MAX_TRIALS),
         ("assemble_rows_trial_blocks", _i * MAX_TRIALS), ("derivative_tile_elements", _i),
+        ("derivative_full_entries", _i * MAX_TRIALS), ("specialize", _vp),
     ]
 
 
@@ -71,6 +72,7 @@ SIGNATURES = {
     "sb_integral_element_gradient": (_i, [_vp, _i, _vp, _vp]),
     "sb_integral_export_derivatives": (_i, [_vp, _i, _vp, _vp]),
     "sb_integral_derivative_entries": (_i, [_vp, _i]),
+    "sb_integral_derivative_stored_entries": (_i, [_vp, _i]),
     "sb_integral_derivative_mask": (_i, [_vp, _i]),
     "sb_csr_create": (_i, [_vp, _vp, _pp]),
     "sb_csr_create_blocks": (_i, [_i, _vp, _vp, _pp]),
@@ -134,6 +136,12 @@ SIGNATURES = {
     "sb_halo_P_nccl": (_i, [_vp, _vp, _vp, _vp, _vp]),
     "sb_halo_Pt_nccl": (_i, [_vp, _vp, _vp, _vp, _vp]),
     "sb_halo_enable_peer_ipc": (_i, [_vp, _vp]),
+    "sb_par_csr_create": (_i, [_vp, _vp, _vp, _vp, _vp, _i64, _pp]),
+    "sb_par_csr_destroy": (_i, [_vp]),
+    "sb_par_csr_mult": (_i, [_vp, _vp, _vp, _vp]),
+    "sb_par_csr_diagonal": (_i, [_vp, _vp, _vp]),
+    "sb_par_dot": (_i, [_vp, _vp, _vp, _i64, C.POINTER(_d), _vp]),
+    "sb_par_cg_solve": (_i, [_vp, _vp, _vp, _vp, _d, _d, _i, C.POINTER(_i), C.POINTER(_i), C.POINTER(_d), _vp]),
     # include/serac_b200_solvers.h
     "sb_vector_set_subvector": (_i, [_vp, _vp, _i64, _d, _vp]),
     "sb_vector_copy_subvector": (_i, [_vp, _vp, _vp, _i64, _vp]),
@@ -374,7 +382,12 @@ class Integral:
     def derivative_entries(self, wrt):
         return lib().sb_integral_derivative_entries(self.h, wrt)
 
+    def derivative_stored_entries(self, wrt):
+        """doubles per quadrature point actually stored (symmetric tangents: the upper triangle only)"""
+        return lib().sb_integral_derivative_stored_entries(self.h, wrt)
+
     def derivative_mask(self, wrt):
+        """bits 0-3: blocks d00, d01, d10, d11 present; bit 4 (16): d11 stored as the upper triangle"""
         return lib().sb_integral_derivative_mask(self.h, wrt)
 
     def export_derivatives(self, wrt):

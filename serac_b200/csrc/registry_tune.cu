@@ -51,6 +51,19 @@ TUNE(4, 1, 20)
 TUNE(8, 1, 2)
 #elif TUNE_SET == 3
 TUNE(16, 1, 1)
+#elif TUNE_SET == 10
+// the streaming Jacobian action under symmetric tangent storage: E = (100 + resident CTAs asked of ptxas) * 1000 + elements
+// per CTA (the evaluation kernel's variant is the default one throughout)
+TUNE(103002, 1, 16)
+TUNE(105002, 1, 16)
+TUNE(106002, 1, 16)
+TUNE(108002, 1, 16)
+TUNE(102004, 1, 16)
+TUNE(103004, 1, 16)
+TUNE(104004, 1, 16)
+TUNE(108001, 1, 16)
+TUNE(112001, 1, 16)
+TUNE(116001, 1, 16)
 #endif
 }  // namespace
 }  // namespace sb

@@ -97,7 +97,7 @@ struct AssembleRowsConfig {
   static constexpr int  QS  = 2 * nk * SQ;   ///< stage-y results  [2][nk (jy)][SQ: (cl, jz, qx)]
   static constexpr int  fixed_doubles = 4 * MAX_Q * MAX_Q + 2 * ASM_MAX_GROUP_NODES + 2 * UCAP + PS + QS;
   static constexpr int  NE  = (d00 ? 1 : 0) + (d01 ? 3 : 0) + (d10 ? 3 : 0) + (d11 ? 9 : 0);  ///< entries per (a,b), point
-  static constexpr DerivativeLayout layout() { return make_layout(ct, ck, dim, d00, d01, d10, d11); }
+  static constexpr DerivativeLayout layout() { return make_layout(ct, ck, dim, d00, d01, d10, d11, (MASK & SB_MASK_SYM) != 0); }
   static_assert(nk <= q && nt <= q, "quadrature rule must have at least p + 1 points per direction");
   static_assert(QQ <= 32, "a column set must fit a warp");
   static_assert(NB <= 255, "item encoding");
@@ -181,7 +181,7 @@ __global__ void __launch_bounds__(AssembleRowsConfig<q, nk, ck, nt, ct, MASK, EP
           for (int k = 0; k < 3; k++) {
             SB_UNROLL
             for (int l = 0; l < 3; l++)
-              dst[qz][i++] = dq[(long long)(LY.offset[3] + ((a * 3 + k) * ck + b) * 3 + l) * C::TILE + qz * QQ];
+              dst[qz][i++] = dq[(long long)(LY.i11(a, k, b, l)) * C::TILE + qz * QQ];
           }
         }
       }
@@ -193,7 +193,7 @@ __global__ void __launch_bounds__(AssembleRowsConfig<q, nk, ck, nt, ct, MASK, EP
     const double*   nq   = P.dqf + tile * (long long)LY.entries * C::TILE + (p - int(tile) * C::TE) * C::QPE;
     constexpr int   per_a = LY.entries / ct;  // entries are a-major inside every block; a few lines too many do no harm
     for (int e = lane; e < LY.entries; e += 32) {
-      if (ct > 1 && LY.entries % ct == 0 && !(C::d00 || C::d01 || C::d10) && e / per_a != a) continue;
+      if (!LY.sym && ct > 1 && LY.entries % ct == 0 && !(C::d00 || C::d01 || C::d10) && e / per_a != a) continue;
       const char* at = reinterpret_cast<const char*>(nq + (long long)e * C::TILE);
       prefetch_l2(at);
       if (C::QPE * 8 > 128) prefetch_l2(at + 128);

@@ -1005,15 +1005,38 @@ struct InterpStages<2, n, q, c> {
 // A block is absent when the q-function's output does not carry derivatives in the pass that seeds it -- the same
 // structural pruning the reference gets from `zero` gradient types.
 // ------------------------------------------------------------------------------------------------
+//
+// Symmetric storage (an extension; the reference stores every block in full): when the q-function declares that its
+// flux tangent has the major symmetry d flux[a][k] / d grad[b][l] = d flux[b][l] / d grad[a][k] (hyperelastic
+// materials: the first Piola tangent is the Hessian of the strain energy, and the congruences of the shape-aware
+// wrapper and of physical_to_parent keep it), d11 is stored as the upper triangle of the (ct dim) x (ck dim) matrix,
+// row-major: N (N + 1) / 2 instead of N^2 doubles per quadrature point (45 instead of 81 for a 3-D vector field).
+// Every reader addresses d11 through i11().
+// ------------------------------------------------------------------------------------------------
 struct DerivativeLayout {
   int  ct, ck, dim;
   bool has[4];
   int  offset[4];
   int  size[4];
   int  entries;
+  bool sym;  ///< d11 stored as its upper triangle
+  /// is (a, k, b, l) an entry the symmetric layout stores itself (the others are read through their transposes) ?
+  SB_HD bool stores11(int a, int k, int b, int l) const { return !sym || (a * dim + k) <= (b * dim + l); }
+  /// position of d flux[a][k] / d grad[b][l] among the entries of one quadrature point
+  SB_HD int i11(int a, int k, int b, int l) const
+  {
+    const int i = a * dim + k, j = b * dim + l, N = ck * dim;
+    if (!sym) return offset[3] + i * N + j;
+    const int lo = i < j ? i : j, hi = i < j ? j : i;
+    return offset[3] + lo * N - (lo * (lo - 1)) / 2 + (hi - lo);
+  }
 };
 
-SB_HD DerivativeLayout make_layout(int ct, int ck, int dim, bool d00, bool d01, bool d10, bool d11)
+/// bit 4 of the kernels' block masks: symmetric d11
+constexpr int SB_MASK_SYM = 16;
+
+SB_HD DerivativeLayout make_layout(int ct, int ck, int dim, bool d00, bool d01, bool d10, bool d11,
+                                             bool sym = false)
 {
   DerivativeLayout L{};
   L.ct      = ct;
@@ -1023,10 +1046,11 @@ SB_HD DerivativeLayout make_layout(int ct, int ck, int dim, bool d00, bool d01, 
   L.has[1]  = d01;
   L.has[2]  = d10;
   L.has[3]  = d11;
+  L.sym     = sym && d11 && ct == ck;
   L.size[0] = ct * ck;
   L.size[1] = ct * ck * dim;
   L.size[2] = ct * dim * ck;
-  L.size[3] = ct * dim * ck * dim;
+  L.size[3] = L.sym ? (ct * dim * (ct * dim + 1)) / 2 : ct * dim * ck * dim;
   int off   = 0;
   for (int b = 0; b < 4; b++) {
     L.offset[b] = off;
@@ -1127,7 +1151,9 @@ struct DerivativeTraits {
                 "a flux tangent provider may only be declared for an argument whose gradient alone enters the flux");
   static constexpr bool value_pass_active = d00 || d10;
   static constexpr bool grad_pass_active  = d01 || d11;
-  static constexpr DerivativeLayout layout() { return make_layout(ct, ck, dim, d00, d01, d10, d11); }
+  /// upper-triangle storage of d11: only on the tangent path, where the q-function itself vouches for the symmetry
+  static constexpr bool sym = tangent && ct == ck && provides_symmetric_flux_tangent<QF, WRT>::value;
+  static constexpr DerivativeLayout layout() { return make_layout(ct, ck, dim, d00, d01, d10, d11, sym); }
 };
 
 // ---- output component extraction ----------------------------------------------------------------
@@ -1536,7 +1562,8 @@ __global__ void __launch_bounds__(EvalLayout<Sig>::threads, MINB) evaluation_ker
       tensor<double, ct>      s_p{};
       tensor<double, ct, dim> f_p{};
       auto sink = [&](int a, int k, int b, int l, double v) {
-        if (valid) dq[(long long)(((a * dim + k) * ck + b) * dim + l) * LAY::TILE] = v;
+        constexpr DerivativeLayout LYs = DT::layout();
+        if (LYs.stores11(a, k, b, l) && valid) dq[(long long)LYs.i11(a, k, b, l) * LAY::TILE] = v;
       };
       [&]<int... I>(std::integer_sequence<int, I...>)
       {
@@ -1627,7 +1654,7 @@ __global__ void __launch_bounds__(EvalLayout<Sig>::threads, MINB) evaluation_ker
                 for (int k = 0; k < dim; k++) {
                   SB_UNROLL
                   for (int l = 0; l < dim; l++)
-                    dq[(long long)(LY.offset[3] + ((a * dim + k) * ck + row) * dim + l) * LAY::TILE] =
+                    dq[(long long)(LY.i11(a, k, row, l)) * LAY::TILE] =
                         partial(f_out[a][k], rl * dim + l);
                 }
               }
@@ -1708,7 +1735,7 @@ struct JvpConfig {
   using TPt = TensorProduct<dim, nt, q, ct>;
   static constexpr int per     = cmax(TPk::interp_scratch, TPt::integ_scratch);
   static constexpr int smem_doubles = 4 * MAX_Q * MAX_Q + EPB * per;
-  static constexpr DerivativeLayout layout() { return make_layout(ct, ck, dim, d00, d01, d10, d11); }
+  static constexpr DerivativeLayout layout() { return make_layout(ct, ck, dim, d00, d01, d10, d11, (MASK & SB_MASK_SYM) != 0); }
 };
 
 template <int dim, int q, int nk, int ck, int nt, int ct, int MASK, int EPB_ = 0>
@@ -1797,7 +1824,7 @@ __global__ void __launch_bounds__(JvpConfig<dim, q, nk, ck, nt, ct, MASK, EPB_>:
         for (int b = 0; b < ck; b++) {
           SB_UNROLL
           for (int l = 0; l < dim; l++)
-            fl += __ldcs(dq + (LY.offset[3] + ((a * dim + k) * ck + b) * dim + l) * stride) * g[b][l];
+            fl += __ldcs(dq + (LY.i11(a, k, b, l)) * stride) * g[b][l];
         }
       }
       flux[a][k] = fl * w;
@@ -1832,7 +1859,7 @@ struct ElemGradConfig {
   static constexpr int ndof_k = ipow(nk, dim);
   static constexpr int per    = TPt::integ_scratch;
   static constexpr int smem_doubles = 4 * MAX_Q * MAX_Q + EPB * per;
-  static constexpr DerivativeLayout layout() { return make_layout(ct, ck, dim, d00, d01, d10, d11); }
+  static constexpr DerivativeLayout layout() { return make_layout(ct, ck, dim, d00, d01, d10, d11, (MASK & SB_MASK_SYM) != 0); }
 };
 
 #ifndef SB_EG_MINB
@@ -1926,7 +1953,7 @@ __global__ void __launch_bounds__(ElemGradConfig<dim, q, nk, ck, nt, ct, MASK, E
           if constexpr (C::d10) fl += D[LY.offset[2] + (a * dim + k) * ck + b] * phi;
           if constexpr (C::d11) {
             SB_UNROLL
-            for (int l = 0; l < dim; l++) fl += D[LY.offset[3] + ((a * dim + k) * ck + b) * dim + l] * dphi[l];
+            for (int l = 0; l < dim; l++) fl += D[LY.i11(a, k, b, l)] * dphi[l];
           }
           flux[a * ck + b][k] = fl;
         }

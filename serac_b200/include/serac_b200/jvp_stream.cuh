@@ -341,8 +341,9 @@ struct JvpStreamConfig {
 #ifndef SB_JVP_MINB
 #define SB_JVP_MINB 2
 #endif
-template <int dim, int q, int nk, int ck, int nt, int ct, int MASK, int EPB_ = 0>
-__global__ void __launch_bounds__(JvpStreamConfig<dim, q, nk, ck, nt, ct, MASK, EPB_>::threads, SB_JVP_MINB)
+/// MINB: resident CTAs per SM asked of ptxas (part of the kernel's name so that tuning variants can live side by side)
+template <int dim, int q, int nk, int ck, int nt, int ct, int MASK, int EPB_ = 0, int MINB = SB_JVP_MINB>
+__global__ void __launch_bounds__(JvpStreamConfig<dim, q, nk, ck, nt, ct, MASK, EPB_>::threads, MINB)
     jvp_stream_kernel(const __grid_constant__ JvpParams P, const int num_tiles)
 {
   using C                       = JvpStreamConfig<dim, q, nk, ck, nt, ct, MASK, EPB_>;
@@ -468,7 +469,7 @@ __global__ void __launch_bounds__(JvpStreamConfig<dim, q, nk, ck, nt, ct, MASK, 
           SB_UNROLL
           for (int b = 0; b < ck; b++) {
             SB_UNROLL
-            for (int l = 0; l < dim; l++) fl += dq[(LY.offset[3] + ((a * dim + k) * ck + b) * dim + l) * DQS] * g[b][l];
+            for (int l = 0; l < dim; l++) fl += dq[(LY.i11(a, k, b, l)) * DQS] * g[b][l];
           }
         }
         flux[a][k] = fl * w;

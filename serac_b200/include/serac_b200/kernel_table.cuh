@@ -145,6 +145,9 @@ int launch_evaluate(const sb_eval_args* a, const void* qf_blob, void* stream)
   }
 }
 
+/// resident CTAs per SM asked of ptxas for the streaming Jacobian action
+constexpr int jvp_min_blocks(int /*dim*/, int /*q*/, int /*mask*/) { return SB_JVP_MINB; }
+
 /// SB_JVP_KERNEL=legacy selects the one-tile-per-CTA kernel (for A/B measurements); default is the TMA-fed stream kernel
 inline bool use_stream_jvp()
 {
@@ -191,7 +194,9 @@ int launch_jvp(const sb_jvp_args* a, void* stream)
     using SC        = JvpStreamConfig<Sig::dim, Sig::q, nk, ck, Sig::test_n, Sig::test_c, MASK, Sig::EPB>;
     if constexpr (SC::supported && SC::smem_bytes <= 227 * 1024) {
       if (use_stream_jvp()) {
-        auto       kernel = &jvp_stream_kernel<Sig::dim, Sig::q, nk, ck, Sig::test_n, Sig::test_c, MASK, Sig::EPB>;
+        // (registry_tune.cu: experiment switches >= 100 name the resident CTAs asked of ptxas)
+        constexpr int JM = (Sig::tune >= 100) ? Sig::tune - 100 : jvp_min_blocks(Sig::dim, Sig::q, MASK);
+        auto       kernel = &jvp_stream_kernel<Sig::dim, Sig::q, nk, ck, Sig::test_n, Sig::test_c, MASK, Sig::EPB, JM>;
         static int resident = 0;  // CTAs per SM for this instantiation
         if (resident == 0) {
           if (int e = ensure_smem(kernel, SC::smem_bytes)) return e;
@@ -308,18 +313,14 @@ constexpr int default_min_blocks()
   return (512 / t32) > 0 ? (512 / t32) : 1;
 }
 
-template <typename Sig, typename QF, typename State, int WRT, int ROWS_REQ, int MINB, bool FAST>
-void fill_wrt(sb_kernel_table& T)
+/// the entries of the table that depend on how the derivative w.r.t. trial WRT is stored (DT = its DerivativeTraits)
+template <typename Sig, int WRT, typename DT>
+void set_derivative_launchers(sb_kernel_table& T)
 {
-  using DT                   = DerivativeTraits<Sig, WRT, QF, State, FAST>;
   constexpr DerivativeLayout L = DT::layout();
-  constexpr int mask = (L.has[0] ? 1 : 0) | (L.has[1] ? 2 : 0) | (L.has[2] ? 4 : 0) | (L.has[3] ? 8 : 0);
+  constexpr int mask = (L.has[0] ? 1 : 0) | (L.has[1] ? 2 : 0) | (L.has[2] ? 4 : 0) | (L.has[3] ? 8 : 0) |
+                       (L.sym ? SB_MASK_SYM : 0);
   constexpr int ck   = Sig::template trial_space<WRT>::components;
-  constexpr int ROWS = (ROWS_REQ > 0 && ck % ROWS_REQ == 0) ? ROWS_REQ : 1;
-  // resident CTAs per SM asked of ptxas: kernels whose q-function differentiates itself fit 128 registers / thread
-  // (measured: 263 -> 178 us on config A); dual-number kernels already spill at 255 and are left alone
-  constexpr int MB = (MINB > 0) ? MINB : (DT::tangent ? default_min_blocks<Sig>() : 1);
-  T.evaluate_ad[WRT]        = &launch_evaluate<Sig, WRT, QF, State, ROWS, MB, FAST>;
   T.jvp[WRT]                = &launch_jvp<Sig, WRT, mask>;
   T.element_gradient[WRT]   = &launch_element_gradient<Sig, WRT, mask>;
   if constexpr (has_assemble_rows<Sig, mask>()) {
@@ -329,8 +330,47 @@ void fill_wrt(sb_kernel_table& T)
     T.assemble_rows_fixed_doubles[WRT] = AC::fixed_doubles;
     T.assemble_rows_trial_blocks[WRT]  = AC::NB;
   }
-  T.derivative_mask[WRT]    = mask;
-  T.derivative_entries[WRT] = L.entries;
+  T.derivative_mask[WRT]         = mask;
+  T.derivative_entries[WRT]      = L.entries;
+  T.derivative_full_entries[WRT] = make_layout(L.ct, L.ck, L.dim, L.has[0], L.has[1], L.has[2], L.has[3]).entries;
+}
+
+template <typename Sig, typename QF, typename State, int WRT, int ROWS_REQ, int MINB, bool FAST>
+void fill_wrt(sb_kernel_table& T)
+{
+  using DT                   = DerivativeTraits<Sig, WRT, QF, State, FAST>;
+  constexpr int ck   = Sig::template trial_space<WRT>::components;
+  constexpr int ROWS = (ROWS_REQ > 0 && ck % ROWS_REQ == 0) ? ROWS_REQ : 1;
+  // resident CTAs per SM asked of ptxas: kernels whose q-function differentiates itself fit 128 registers / thread
+  // (measured: 263 -> 178 us on config A); dual-number kernels already spill at 255 and are left alone
+  constexpr int MB = (MINB > 0) ? MINB : (DT::tangent ? default_min_blocks<Sig>() : 1);
+  T.evaluate_ad[WRT]        = &launch_evaluate<Sig, WRT, QF, State, ROWS, MB, FAST>;
+  set_derivative_launchers<Sig, WRT, DT>(T);
+}
+
+/// sb_kernel_table::specialize: the launchers of the functor's own variant (launch_evaluate dispatches the evaluation
+/// kernel on the same variant_index(), so what it stores is what these read)
+template <typename Sig, typename QF, typename State, bool FAST>
+void specialize_table(void* table, const void* qf_blob)
+{
+  if constexpr (qf_variants<QF>::n > 1) {
+    sb_kernel_table& T = *static_cast<sb_kernel_table*>(table);
+    alignas(16) unsigned char qf_storage[sizeof(QF)];
+    std::memcpy(qf_storage, qf_blob, sizeof(QF));
+    const QF& qf   = *reinterpret_cast<const QF*>(qf_storage);
+    auto per_wrt = [&]<int... I>(std::integer_sequence<int, I...>)
+    {
+      auto per_variant = [&]<int W, int... V>(std::integral_constant<int, W>, std::integer_sequence<int, V...>)
+      {
+        (((qf.variant_index() == V)
+              ? set_derivative_launchers<Sig, W, DerivativeTraits<Sig, W, typename QF::template variant<V>, State, FAST>>(T)
+              : void()),
+         ...);
+      };
+      (per_variant(std::integral_constant<int, I>{}, std::make_integer_sequence<int, qf_variants<QF>::n>{}), ...);
+    };
+    per_wrt(std::make_integer_sequence<int, Sig::NT>{});
+  }
 }
 
 /// State = serac::Nothing: q-function takes no state argument; serac::Empty: takes an Empty& it never touches;
@@ -362,6 +402,7 @@ sb_kernel_table make_kernel_table()
   T.elements_per_block = Sig::EPB;
   T.derivative_tile_elements = Sig::DQ_TE;
   T.evaluate           = &launch_evaluate<Sig, -1, QF, State, 1, (MINB > 0 ? MINB : default_min_blocks<Sig>()), FAST>;
+  T.specialize         = (qf_variants<QF>::n > 1) ? &specialize_table<Sig, QF, State, FAST> : nullptr;
   return T;
 }
 

@@ -80,6 +80,20 @@ struct provides_flux_tangent<QF, WRT, std::void_t<decltype(QF::template has_flux
     : std::bool_constant<QF::template has_flux_tangent<WRT>> {
 };
 
+/// does q-function QF vouch that the flux tangent it provides for argument WRT has the major symmetry
+/// d flux[a][k] / d grad[b][l] = d flux[b][l] / d grad[a][k] ?  Then the kernels store the upper triangle only
+/// (DerivativeLayout::sym, domain_integral.cuh): 45 instead of 81 doubles per quadrature point in 3-D.
+template <typename QF, int WRT, typename = void>
+struct provides_symmetric_flux_tangent : std::false_type {
+};
+#ifndef SB_SYMMETRIC_TANGENT
+#define SB_SYMMETRIC_TANGENT 1  // 0: every tangent is stored in full (for A/B measurements)
+#endif
+template <typename QF, int WRT>
+struct provides_symmetric_flux_tangent<QF, WRT, std::void_t<decltype(QF::template has_symmetric_flux_tangent<WRT>)>>
+    : std::bool_constant<(SB_SYMMETRIC_TANGENT != 0) && QF::template has_symmetric_flux_tangent<WRT>> {
+};
+
 namespace solid_mechanics {
 
 /// linear isotropic elasticity (solid_material.hpp:24-50)
@@ -557,6 +571,12 @@ struct MaterialStressFunctor {
   /// Same mathematics as the reference's dual-number evaluation of operator() above, to rounding.
   template <int WRT>
   static constexpr bool has_flux_tangent = (WRT == 0) && !is_parameterized_material<Material>::value;
+  /// with geometric nonlinearity on, a material that gives its first Piola tangent in the three-coefficient form above
+  /// is hyperelastic and the parent tangent c1 A[k][a] A[l][b] + c2 A[k][b] A[l][a] + c3 d_ab (M M^T)[k][l] is
+  /// symmetric under (a, k) <-> (b, l) term by term; known at compile time only for the static variant of the flag
+  template <int WRT>
+  static constexpr bool has_symmetric_flux_tangent =
+      has_flux_tangent<WRT> && MODE == FlagMode::StaticOn && has_piola_tangent_coefficients<Material>::value;
 
   template <typename X, typename State, int dim, typename Sink, typename Displacement, typename Acceleration>
   SERAC_HOST_DEVICE void flux_tangent(std::integral_constant<int, 0>, double, const X&, State& state,
@@ -818,6 +838,9 @@ struct ShapeAwareIntegrandWrapperWithState {
   /// post-multiplies the linear maps (du/dx' = du/dX inv(J_p), flux -> flux inv(J_p)^T det J_p)
   template <int WRT>
   static constexpr bool has_flux_tangent = (WRT >= 1) && provides_flux_tangent<Integrand, WRT - 1>::value;
+  /// (M -> M inv(J_p) and scale -> scale det J_p are congruences: a symmetric tangent stays symmetric)
+  template <int WRT>
+  static constexpr bool has_symmetric_flux_tangent = (WRT >= 1) && provides_symmetric_flux_tangent<Integrand, WRT - 1>::value;
 
   template <int WRT, typename PositionType, typename StateType, typename Source, typename Flux, typename Sink,
             typename ShapeValueType, typename... QFuncArgs>

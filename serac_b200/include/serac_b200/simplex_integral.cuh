@@ -34,7 +34,7 @@ struct SimplexConfig {
   static constexpr int grad_per = ct * ck * (1 + dim) * nq;
   static constexpr int jvp_smem_doubles  = tables + EPB * jvp_per;
   static constexpr int grad_smem_doubles = tables + EPB * grad_per;
-  static constexpr DerivativeLayout layout() { return make_layout(ct, ck, dim, d00, d01, d10, d11); }
+  static constexpr DerivativeLayout layout() { return make_layout(ct, ck, dim, d00, d01, d10, d11, (MASK & SB_MASK_SYM) != 0); }
 };
 
 template <typename C>
@@ -117,7 +117,7 @@ __global__ void __launch_bounds__(SimplexConfig<geom, Q, pk, ck, pt, ct, MASK, E
         for (int b = 0; b < ck; b++) {
           SB_UNROLL
           for (int l = 0; l < dim; l++)
-            fl += __ldcs(dq + (LY.offset[3] + ((a * dim + k) * ck + b) * dim + l) * stride) * g[b][l];
+            fl += __ldcs(dq + (LY.i11(a, k, b, l)) * stride) * g[b][l];
         }
       }
       flux[a][k] = fl * w;
@@ -191,7 +191,7 @@ __global__ void __launch_bounds__(SimplexConfig<geom, Q, pk, ck, pt, ct, MASK, E
           if constexpr (C::d10) fl += D[LY.offset[2] + (a * dim + k) * ck + b] * phi;
           if constexpr (C::d11) {
             SB_UNROLL
-            for (int l = 0; l < dim; l++) fl += D[LY.offset[3] + ((a * dim + k) * ck + b) * dim + l] * dphi[l];
+            for (int l = 0; l < dim; l++) fl += D[LY.i11(a, k, b, l)] * dphi[l];
           }
           flux[a * ck + b][k] = fl;
         }
