@@ -87,14 +87,21 @@ struct TensorProductR;
 template <int n, int q, int c>
 struct TensorProductR<3, n, q, c> {
   using TP = TensorProduct<3, n, q, c>;
+  // Every intermediate array is a set of blocks of (at most) q^3 doubles, one per (kind, component), each block starting
+  // on a 128-byte line (BLK doubles apart): a warp's access to one block then touches the fewest lines there are.  Inside
+  // a block the index that a stage sums over is the slowest, so that the lanes of one load read one contiguous run
+  // (ncu on the [qz][dy][qx] order: 3 wavefronts per load in the y stages instead of 2; profiles/r4_summary.md).
+  static constexpr int BLK            = ((q * q * q + 15) / 16) * 16;
+  static constexpr int U_SZ           = ((c * n * n * n + 15) / 16) * 16;
+  static constexpr int interp_scratch = U_SZ + (2 + 3) * c * BLK;
+  static constexpr int integ_scratch  = (4 + 3 + 2) * c * BLK;
   template <bool NEED_VALUE, bool NEED_GRAD>
   static __device__ __forceinline__ void interpolate(const ThreadBasis<3, n, q>& tb, double* s, int qx, int qy, int qz,
                                                      double (&val)[c], double (&grad)[c][3])
   {
-    constexpr int ndof = n * n * n;
     const double* u    = s;
-    double*       A1   = s + c * ndof;
-    double*       A2   = A1 + 2 * c * n * n * q;
+    double*       A1   = s + U_SZ;           // blocks (kind < 2, a): [dy][qz][qx]
+    double*       A2   = A1 + 2 * c * BLK;   // blocks (kind < 3, a): [dz][qy][qx]
     if (qz < n && qy < n) {
       SB_UNROLL
       for (int a = 0; a < c; a++) {
@@ -105,8 +112,8 @@ struct TensorProductR<3, n, q, c> {
           sB += tb.Br[0][dx] * uu;
           if (NEED_GRAD) sG += tb.Gr[0][dx] * uu;
         }
-        A1[(((0 * c + a) * n + qz) * n + qy) * q + qx] = sB;
-        if (NEED_GRAD) A1[(((1 * c + a) * n + qz) * n + qy) * q + qx] = sG;
+        A1[(0 * c + a) * BLK + (qy * n + qz) * q + qx] = sB;
+        if (NEED_GRAD) A1[(1 * c + a) * BLK + (qy * n + qz) * q + qx] = sG;
       }
     }
     __syncthreads();
@@ -116,18 +123,18 @@ struct TensorProductR<3, n, q, c> {
         double sBB = 0.0, sGB = 0.0, sBG = 0.0;
         SB_UNROLL
         for (int dy = 0; dy < n; dy++) {
-          const double b = A1[(((0 * c + a) * n + qz) * n + dy) * q + qx];
+          const double b = A1[(0 * c + a) * BLK + (dy * n + qz) * q + qx];
           sBB += tb.Br[1][dy] * b;
           if (NEED_GRAD) {
-            const double g = A1[(((1 * c + a) * n + qz) * n + dy) * q + qx];
+            const double g = A1[(1 * c + a) * BLK + (dy * n + qz) * q + qx];
             sGB += tb.Br[1][dy] * g;
             sBG += tb.Gr[1][dy] * b;
           }
         }
-        A2[(((0 * c + a) * n + qz) * q + qy) * q + qx] = sBB;
+        A2[(0 * c + a) * BLK + (qz * q + qy) * q + qx] = sBB;
         if (NEED_GRAD) {
-          A2[(((1 * c + a) * n + qz) * q + qy) * q + qx] = sGB;
-          A2[(((2 * c + a) * n + qz) * q + qy) * q + qx] = sBG;
+          A2[(1 * c + a) * BLK + (qz * q + qy) * q + qx] = sGB;
+          A2[(2 * c + a) * BLK + (qz * q + qy) * q + qx] = sBG;
         }
       }
     }
@@ -137,11 +144,11 @@ struct TensorProductR<3, n, q, c> {
       double v = 0.0, gx = 0.0, gy = 0.0, gz = 0.0;
       SB_UNROLL
       for (int dz = 0; dz < n; dz++) {
-        const double bb = A2[(((0 * c + a) * n + dz) * q + qy) * q + qx];
+        const double bb = A2[(0 * c + a) * BLK + (dz * q + qy) * q + qx];
         if (NEED_VALUE) v += tb.Br[2][dz] * bb;
         if (NEED_GRAD) {
-          const double gb = A2[(((1 * c + a) * n + dz) * q + qy) * q + qx];
-          const double bg = A2[(((2 * c + a) * n + dz) * q + qy) * q + qx];
+          const double gb = A2[(1 * c + a) * BLK + (dz * q + qy) * q + qx];
+          const double bg = A2[(2 * c + a) * BLK + (dz * q + qy) * q + qx];
           gx += tb.Br[2][dz] * gb;
           gy += tb.Br[2][dz] * bg;
           gz += tb.Gr[2][dz] * bb;
@@ -159,16 +166,16 @@ struct TensorProductR<3, n, q, c> {
                                                    const double (&src)[c], const double (&flux)[c][3],
                                                    double (&out)[c])
   {
-    double* S  = s;
-    double* P  = S + 4 * c * q * q * q;
-    double* Qs = P + 3 * c * n * q * q;
+    double* S  = s;                  // blocks (kind < 4, a): [qz][qy][qx]
+    double* P  = S + 4 * c * BLK;    // blocks (kind < 3, a): [qy][jz][qx]
+    double* Qs = P + 3 * c * BLK;    // blocks (kind < 2, a): [jz][jy][qx]
     SB_UNROLL
     for (int a = 0; a < c; a++) {
-      if (HAS_SOURCE) S[(((0 * c + a) * q + qz) * q + qy) * q + qx] = src[a];
+      if (HAS_SOURCE) S[(0 * c + a) * BLK + (qz * q + qy) * q + qx] = src[a];
       if (HAS_FLUX) {
-        S[(((1 * c + a) * q + qz) * q + qy) * q + qx] = flux[a][0];
-        S[(((2 * c + a) * q + qz) * q + qy) * q + qx] = flux[a][1];
-        S[(((3 * c + a) * q + qz) * q + qy) * q + qx] = flux[a][2];
+        S[(1 * c + a) * BLK + (qz * q + qy) * q + qx] = flux[a][0];
+        S[(2 * c + a) * BLK + (qz * q + qy) * q + qx] = flux[a][1];
+        S[(3 * c + a) * BLK + (qz * q + qy) * q + qx] = flux[a][2];
       }
     }
     __syncthreads();
@@ -178,17 +185,17 @@ struct TensorProductR<3, n, q, c> {
         double p0 = 0.0, p1 = 0.0, p2 = 0.0;
         SB_UNROLL
         for (int k = 0; k < q; k++) {
-          if (HAS_SOURCE) p0 += tb.Bc[2][k] * S[(((0 * c + a) * q + k) * q + qy) * q + qx];
+          if (HAS_SOURCE) p0 += tb.Bc[2][k] * S[(0 * c + a) * BLK + (k * q + qy) * q + qx];
           if (HAS_FLUX) {
-            p0 += tb.Gc[2][k] * S[(((3 * c + a) * q + k) * q + qy) * q + qx];
-            p1 += tb.Bc[2][k] * S[(((1 * c + a) * q + k) * q + qy) * q + qx];
-            p2 += tb.Bc[2][k] * S[(((2 * c + a) * q + k) * q + qy) * q + qx];
+            p0 += tb.Gc[2][k] * S[(3 * c + a) * BLK + (k * q + qy) * q + qx];
+            p1 += tb.Bc[2][k] * S[(1 * c + a) * BLK + (k * q + qy) * q + qx];
+            p2 += tb.Bc[2][k] * S[(2 * c + a) * BLK + (k * q + qy) * q + qx];
           }
         }
-        P[(((0 * c + a) * n + qz) * q + qy) * q + qx] = p0;
+        P[(0 * c + a) * BLK + (qy * n + qz) * q + qx] = p0;
         if (HAS_FLUX) {
-          P[(((1 * c + a) * n + qz) * q + qy) * q + qx] = p1;
-          P[(((2 * c + a) * n + qz) * q + qy) * q + qx] = p2;
+          P[(1 * c + a) * BLK + (qy * n + qz) * q + qx] = p1;
+          P[(2 * c + a) * BLK + (qy * n + qz) * q + qx] = p2;
         }
       }
     }
@@ -199,14 +206,14 @@ struct TensorProductR<3, n, q, c> {
         double q0 = 0.0, q1 = 0.0;
         SB_UNROLL
         for (int k = 0; k < q; k++) {
-          q0 += tb.Bc[1][k] * P[(((0 * c + a) * n + qz) * q + k) * q + qx];
+          q0 += tb.Bc[1][k] * P[(0 * c + a) * BLK + (k * n + qz) * q + qx];
           if (HAS_FLUX) {
-            q0 += tb.Gc[1][k] * P[(((2 * c + a) * n + qz) * q + k) * q + qx];
-            q1 += tb.Bc[1][k] * P[(((1 * c + a) * n + qz) * q + k) * q + qx];
+            q0 += tb.Gc[1][k] * P[(2 * c + a) * BLK + (k * n + qz) * q + qx];
+            q1 += tb.Bc[1][k] * P[(1 * c + a) * BLK + (k * n + qz) * q + qx];
           }
         }
-        Qs[(((0 * c + a) * n + qz) * n + qy) * q + qx] = q0;
-        if (HAS_FLUX) Qs[(((1 * c + a) * n + qz) * n + qy) * q + qx] = q1;
+        Qs[(0 * c + a) * BLK + (qz * n + qy) * q + qx] = q0;
+        if (HAS_FLUX) Qs[(1 * c + a) * BLK + (qz * n + qy) * q + qx] = q1;
       }
     }
     __syncthreads();
@@ -217,8 +224,8 @@ struct TensorProductR<3, n, q, c> {
         double r = 0.0;
         SB_UNROLL
         for (int k = 0; k < q; k++) {
-          r += tb.Bc[0][k] * Qs[(((0 * c + a) * n + qz) * n + qy) * q + k];
-          if (HAS_FLUX) r += tb.Gc[0][k] * Qs[(((1 * c + a) * n + qz) * n + qy) * q + k];
+          r += tb.Bc[0][k] * Qs[(0 * c + a) * BLK + (qz * n + qy) * q + k];
+          if (HAS_FLUX) r += tb.Gc[0][k] * Qs[(1 * c + a) * BLK + (qz * n + qy) * q + k];
         }
         out[a] = r;
       }
@@ -325,7 +332,17 @@ struct JvpStreamConfig {
   static constexpr int QPE       = Base::QPE;
   static constexpr int EPB       = Base::EPB;
   static constexpr int threads   = Base::threads;
-  static constexpr int per       = Base::per;
+  /// scratch doubles per element: the register-basis contraction of hexahedra pads its arrays to 128-byte lines
+  static constexpr int stream_per()
+  {
+    if constexpr (dim == 3) {
+      const int a = TensorProductR<3, nk, q, ck>::interp_scratch, b = TensorProductR<3, nt, q, ct>::integ_scratch;
+      return a > b ? a : b;
+    } else {
+      return Base::per;
+    }
+  }
+  static constexpr int per       = stream_per();
   static constexpr int entries   = Base::layout().entries;
   static constexpr int tile_doubles = entries * threads;
   /// the bulk copy moves whole 16-byte units
@@ -350,7 +367,7 @@ __global__ void __launch_bounds__(JvpStreamConfig<dim, q, nk, ck, nt, ct, MASK, 
   using B                       = typename C::Base;
   constexpr DerivativeLayout LY = B::layout();
   constexpr int QPE = C::QPE, EPB = C::EPB, per = C::per, T = C::threads, NG = C::NG, ndk = C::ndof_k;
-  extern __shared__ __align__(16) double smem[];
+  extern __shared__ __align__(128) double smem[];
   double*   tables  = smem;
   double*   scratch = smem + 4 * MAX_Q * MAX_Q;
   double*   tile_s  = smem + C::scratch_doubles;

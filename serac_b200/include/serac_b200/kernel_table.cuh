@@ -146,7 +146,14 @@ int launch_evaluate(const sb_eval_args* a, const void* qf_blob, void* stream)
 }
 
 /// resident CTAs per SM asked of ptxas for the streaming Jacobian action
-constexpr int jvp_min_blocks(int /*dim*/, int /*q*/, int /*mask*/) { return SB_JVP_MINB; }
+/// (symmetric tangent storage: the tile is 45 instead of 81 entries per point, shared memory admits more CTAs, and
+/// the kernel is bound by the shared-memory pipe and latency rather than by HBM; tools/tune.py on config A: 2 -> 87 us,
+/// 5 / 6 -> 80 us, 8 -> 91 us, profiles/r4b_tune_jvp.txt)
+constexpr int jvp_min_blocks(int dim, int q, int mask)
+{
+  if (dim == 3 && (mask & SB_MASK_SYM) != 0) return q == 3 ? 5 : (q == 4 ? 3 : SB_JVP_MINB);
+  return SB_JVP_MINB;
+}
 
 /// SB_JVP_KERNEL=legacy selects the one-tile-per-CTA kernel (for A/B measurements); default is the TMA-fed stream kernel
 inline bool use_stream_jvp()
