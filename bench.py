@@ -32,11 +32,16 @@ METRIC = "GDOF/s Functional residual + Jacobian action (p=2 hex)"
 CONFIG_A = os.path.join(ROOT, "tests", "golden", "config_a_beam_hex_r4_p2.npz")
 NEOHOOKEAN = [1.0, 100.0, 50.0, 1.0]  # density, K, G, geometric nonlinearity on (BASELINE.md §2 probe values)
 # dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed `ncu --set full` capture of this command
-# (profiles/r1c_summary.md, raw extract profiles/r1e_ncu_full_raw_extract.txt)
+# (profiles/r4_summary.md, raw extract profiles/r4b_ncu_extract.txt; symmetric tangent storage, 45 doubles per point)
 NCU_TRAFFIC_SOURCE = ("ncu --set full capture of this command, one launch, not measured in this run: "
-                      "profiles/r1e_ncu_full_raw_extract.txt (dram__bytes_read.sum + dram__bytes_write.sum)")
-JVP_NCU_TRAFFIC_BYTES = 604.8e6   # 583.7 MB read + 21.1 MB written
-EVAL_NCU_TRAFFIC_BYTES = 638.8e6  # 103.3 MB read + 535.5 MB written (rest of the 573 MB store still in L2)
+                      "profiles/r4b_ncu_extract.txt (dram__bytes_read.sum + dram__bytes_write.sum)")
+JVP_NCU_TRAFFIC_BYTES = 348.7e6   # 328.8 MB read + 19.9 MB written
+EVAL_NCU_TRAFFIC_BYTES = 363.8e6  # 82.9 MB read + 280.9 MB written (rest of the 319 MB store still in L2)
+# what the same capture says limits the two kernels now that they move 44% fewer bytes
+JVP_LIMITER = ("shared-memory data pipe ~70% of cycles (516 wavefronts per element before the scratch re-layout), "
+               "HBM 48%, FP64 16% (profiles/r4b_ncu_extract.txt)")
+EVAL_LIMITER = ("no single pipe: FP64 40%, shared-memory + global wavefronts ~64% of cycles, issue slots 42%, 16 warps/SM "
+                "at 128 registers (profiles/r4b_ncu_extract.txt)")
 
 
 # ---------------------------------------------------------------------------------------------------------------------
@@ -755,13 +760,15 @@ def run_product(args):
                      "peak": peak, "unit": "GB/s", "frac": achieved / peak, "peak_source": peak_src,
                      "algorithmic_bytes_per_launch": jvp_bytes,
                      "traffic": JVP_NCU_TRAFFIC_BYTES if BENCH_CONFIG != "b" else None,
-                     "traffic_source": NCU_TRAFFIC_SOURCE if BENCH_CONFIG != "b" else None},
+                     "traffic_source": NCU_TRAFFIC_SOURCE if BENCH_CONFIG != "b" else None,
+                     "limiter": JVP_LIMITER if BENCH_CONFIG != "b" else None},
         "roofline_evaluate": {"kernel": "evaluation_kernel<wrt=1>", "bound": "hbm",
                               "achieved": eval_bytes / (phase_ms[0] * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
                               "frac": eval_bytes / (phase_ms[0] * 1e-3) / 1e9 / peak,
                               "algorithmic_bytes_per_launch": eval_bytes,
                               "traffic": EVAL_NCU_TRAFFIC_BYTES if BENCH_CONFIG != "b" else None,
-                              "traffic_source": NCU_TRAFFIC_SOURCE if BENCH_CONFIG != "b" else None},
+                              "traffic_source": NCU_TRAFFIC_SOURCE if BENCH_CONFIG != "b" else None,
+                              "limiter": EVAL_LIMITER if BENCH_CONFIG != "b" else None},
         "derivative_storage": ref_layout,
         "clocks": clocks,
         "host_path_equals_device_path": host_check,

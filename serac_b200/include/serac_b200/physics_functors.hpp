@@ -109,6 +109,8 @@ struct LinearIsotropic {
   }
   /// closed-form d sigma / d du_dX, row b: lambda d_aj d_bm + G (d_ab d_jm + d_am d_jb)
   static constexpr bool closed_form_tangent = true;
+  /// ... which is the same under (a, j) <-> (b, m): without geometric nonlinearity the flux tangent is symmetric
+  static constexpr bool symmetric_small_strain_tangent = true;
   template <int dim>
   SERAC_HOST_DEVICE void stress_tangent_row(const State&, const tensor<double, dim, dim>&, const tensor<double, dim, dim>&,
                                             int b, tensor<double, dim, dim, dim>& Cb) const
@@ -480,6 +482,15 @@ struct MechanicalMaterialInterface {
 
 }  // namespace thermomechanics
 
+/// does material M declare that its small-strain moduli d sigma[a][j] / d du_dX[b][m] have the major symmetry ?
+template <typename M, typename = void>
+struct has_symmetric_small_strain_tangent : std::false_type {
+};
+template <typename M>
+struct has_symmetric_small_strain_tangent<M, std::void_t<decltype(M::symmetric_small_strain_tangent)>>
+    : std::bool_constant<M::symmetric_small_strain_tangent> {
+};
+
 /// does material M provide piola_tangent_coefficients(state, du_dX) -> {c1, c2, c3} with
 ///   d P[a][i] / d F[b][m] = c1 Finv[i][a] Finv[m][b] + c2 Finv[i][b] Finv[m][a] + c3 d_ab d_im      (P = J sigma F^-T) ?
 template <typename M, typename = void>
@@ -574,9 +585,13 @@ struct MaterialStressFunctor {
   /// with geometric nonlinearity on, a material that gives its first Piola tangent in the three-coefficient form above
   /// is hyperelastic and the parent tangent c1 A[k][a] A[l][b] + c2 A[k][b] A[l][a] + c3 d_ab (M M^T)[k][l] is
   /// symmetric under (a, k) <-> (b, l) term by term; known at compile time only for the static variant of the flag
+  /// (geometric nonlinearity off: flux = sigma, and the parent tangent scale sum_jm M[k][j] M[l][m] C[a][j][b][m] is
+  /// symmetric whenever the small-strain moduli C are)
   template <int WRT>
   static constexpr bool has_symmetric_flux_tangent =
-      has_flux_tangent<WRT> && MODE == FlagMode::StaticOn && has_piola_tangent_coefficients<Material>::value;
+      has_flux_tangent<WRT> &&
+      ((MODE == FlagMode::StaticOn && has_piola_tangent_coefficients<Material>::value) ||
+       (MODE == FlagMode::StaticOff && has_symmetric_small_strain_tangent<Material>::value));
 
   template <typename X, typename State, int dim, typename Sink, typename Displacement, typename Acceleration>
   SERAC_HOST_DEVICE void flux_tangent(std::integral_constant<int, 0>, double, const X&, State& state,
