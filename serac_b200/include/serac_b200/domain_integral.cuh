@@ -1327,29 +1327,45 @@ __global__ void __launch_bounds__(EvalLayout<Sig>::threads, MINB) evaluation_ker
       for (int i = 0; i < NT; i++) m = cmax(m, (LAY::gather_size(i) + LAY::threads - 1) / LAY::threads);
       return m;
     }();
-    double gv[NT > 0 ? NT : 1][NGMAX];
-    auto   load_field = [&](auto idx) {
-      constexpr int   I    = decltype(idx)::value;
-      constexpr int   c    = Sig::trial_c(I);
-      constexpr int   nd   = LAY::ndof(I);
-      constexpr int   NG   = (LAY::gather_size(I) + LAY::threads - 1) / LAY::threads;
-      const FieldArg& f    = P.trial[I];
+    // Three phases over ALL fields, each free of branches (slots past the end are clamped and only their store is
+    // predicated): every table load is in flight before the first L-vector load needs its index, every L-vector load
+    // before the first store.  Written field by field with `if (i < sz)` around the dependent pair, ptxas kept the pairs
+    // in seven reconvergence regions one after the other -- seven table latencies in series, 26% of the kernel's stall
+    // samples (profiles/r4_summary.md).
+    double    gv[NT > 0 ? NT : 1][NGMAX];
+    long long gi[NT > 0 ? NT : 1][NGMAX];
+    auto      index_field = [&](auto idx) {
+      constexpr int   I  = decltype(idx)::value;
+      constexpr int   c  = Sig::trial_c(I);
+      constexpr int   nd = LAY::ndof(I);
+      constexpr int   NG = (LAY::gather_size(I) + LAY::threads - 1) / LAY::threads;
+      constexpr int   sz = LAY::gather_size(I);
+      const FieldArg& f  = P.trial[I];
       SB_UNROLL
       for (int j = 0; j < NG; j++) {
-        const int i = threadIdx.x + j * LAY::threads;
-        constexpr int sz = LAY::gather_size(I);
-        if (i < sz) {
-          const int le   = i / (c * nd);
-          const int rem  = i - le * (c * nd);
-          const int a    = rem / nd;
-          const int node = rem - a * nd;
-          int       ee   = P.first_element + blockIdx.x * EPB + le;
+        const int i0   = threadIdx.x + j * LAY::threads;
+        const int i    = i0 < sz ? i0 : sz - 1;
+        const int le   = i / (c * nd);
+        const int rem  = i - le * (c * nd);
+        const int a    = rem / nd;
+        const int node = rem - a * nd;
+        int       ge;
+        if constexpr (EPB == 1) {
+          ge = elem;
+        } else {
+          int ee = P.first_element + blockIdx.x * EPB + le;
           if (ee >= P.num_elements) ee = P.num_elements - 1;
-          const int       ge  = P.elements ? P.elements[ee] : ee;
-          const long long idx = (long long)f.table[(long long)ge * nd + node];
-          gv[I][j]            = f.L[idx * f.node_stride + a * f.comp_stride];
+          ge = P.elements ? P.elements[ee] : ee;
         }
+        gi[I][j] = (long long)f.table[(long long)ge * nd + node] * f.node_stride + a * f.comp_stride;
       }
+    };
+    auto load_field = [&](auto idx) {
+      constexpr int   I  = decltype(idx)::value;
+      constexpr int   NG = (LAY::gather_size(I) + LAY::threads - 1) / LAY::threads;
+      const FieldArg& f  = P.trial[I];
+      SB_UNROLL
+      for (int j = 0; j < NG; j++) gv[I][j] = f.L[gi[I][j]];
     };
     auto store_field = [&](auto idx) {
       constexpr int I  = decltype(idx)::value;
@@ -1361,6 +1377,8 @@ __global__ void __launch_bounds__(EvalLayout<Sig>::threads, MINB) evaluation_ker
         if (i < sz) gathered[off + i] = gv[I][j];
       }
     };
+    [&]<int... I>(std::integer_sequence<int, I...>) { (index_field(std::integral_constant<int, I>{}), ...); }
+    (seq{});
     [&]<int... I>(std::integer_sequence<int, I...>) { (load_field(std::integral_constant<int, I>{}), ...); }
     (seq{});
     [&]<int... I>(std::integer_sequence<int, I...>) { (store_field(std::integral_constant<int, I>{}), ...); }
