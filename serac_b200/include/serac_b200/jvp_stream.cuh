@@ -79,6 +79,16 @@ struct ThreadBasis {
   }
 };
 
+/// exchange point between two stages: the CTA's barrier, or the warp's when an element is one warp's own
+template <bool WS>
+__device__ __forceinline__ void jvp_stage_sync()
+{
+  if constexpr (WS)
+    __syncwarp();
+  else
+    __syncthreads();
+}
+
 /// sum-factorised interpolation / integration with the 1-D tables in registers (same staging and summation order as
 /// TensorProduct<> in domain_integral.cuh, hence the same bits)
 template <int dim, int n, int q, int c>
@@ -95,14 +105,15 @@ struct TensorProductR<3, n, q, c> {
   static constexpr int U_SZ           = ((c * n * n * n + 15) / 16) * 16;
   static constexpr int interp_scratch = U_SZ + (2 + 3) * c * BLK;
   static constexpr int integ_scratch  = (4 + 3 + 2) * c * BLK;
-  template <bool NEED_VALUE, bool NEED_GRAD>
+  /// WS: the element is one warp's own (JvpStreamConfig::LPE == 32): the stages exchange through __syncwarp
+  template <bool NEED_VALUE, bool NEED_GRAD, bool WS = false>
   static __device__ __forceinline__ void interpolate(const ThreadBasis<3, n, q>& tb, double* s, int qx, int qy, int qz,
-                                                     double (&val)[c], double (&grad)[c][3])
+                                                     double (&val)[c], double (&grad)[c][3], bool on = true)
   {
     const double* u    = s;
     double*       A1   = s + U_SZ;           // blocks (kind < 2, a): [dy][qz][qx]
     double*       A2   = A1 + 2 * c * BLK;   // blocks (kind < 3, a): [dz][qy][qx]
-    if (qz < n && qy < n) {
+    if (on && qz < n && qy < n) {
       SB_UNROLL
       for (int a = 0; a < c; a++) {
         double sB = 0.0, sG = 0.0;
@@ -116,8 +127,8 @@ struct TensorProductR<3, n, q, c> {
         if (NEED_GRAD) A1[(1 * c + a) * BLK + (qy * n + qz) * q + qx] = sG;
       }
     }
-    __syncthreads();
-    if (qz < n) {
+    jvp_stage_sync<WS>();
+    if (on && qz < n) {
       SB_UNROLL
       for (int a = 0; a < c; a++) {
         double sBB = 0.0, sGB = 0.0, sBG = 0.0;
@@ -138,7 +149,7 @@ struct TensorProductR<3, n, q, c> {
         }
       }
     }
-    __syncthreads();
+    jvp_stage_sync<WS>();
     SB_UNROLL
     for (int a = 0; a < c; a++) {
       double v = 0.0, gx = 0.0, gy = 0.0, gz = 0.0;
@@ -161,25 +172,25 @@ struct TensorProductR<3, n, q, c> {
     }
   }
 
-  template <bool HAS_SOURCE, bool HAS_FLUX>
+  template <bool HAS_SOURCE, bool HAS_FLUX, bool WS = false>
   static __device__ __forceinline__ bool integrate(const ThreadBasis<3, n, q>& tb, double* s, int qx, int qy, int qz,
                                                    const double (&src)[c], const double (&flux)[c][3],
-                                                   double (&out)[c])
+                                                   double (&out)[c], bool on = true)
   {
     double* S  = s;                  // blocks (kind < 4, a): [qz][qy][qx]
     double* P  = S + 4 * c * BLK;    // blocks (kind < 3, a): [qy][jz][qx]
     double* Qs = P + 3 * c * BLK;    // blocks (kind < 2, a): [jz][jy][qx]
     SB_UNROLL
     for (int a = 0; a < c; a++) {
-      if (HAS_SOURCE) S[(0 * c + a) * BLK + (qz * q + qy) * q + qx] = src[a];
-      if (HAS_FLUX) {
+      if (HAS_SOURCE && on) S[(0 * c + a) * BLK + (qz * q + qy) * q + qx] = src[a];
+      if (HAS_FLUX && on) {
         S[(1 * c + a) * BLK + (qz * q + qy) * q + qx] = flux[a][0];
         S[(2 * c + a) * BLK + (qz * q + qy) * q + qx] = flux[a][1];
         S[(3 * c + a) * BLK + (qz * q + qy) * q + qx] = flux[a][2];
       }
     }
-    __syncthreads();
-    if (qz < n) {
+    jvp_stage_sync<WS>();
+    if (on && qz < n) {
       SB_UNROLL
       for (int a = 0; a < c; a++) {
         double p0 = 0.0, p1 = 0.0, p2 = 0.0;
@@ -199,8 +210,8 @@ struct TensorProductR<3, n, q, c> {
         }
       }
     }
-    __syncthreads();
-    if (qz < n && qy < n) {
+    jvp_stage_sync<WS>();
+    if (on && qz < n && qy < n) {
       SB_UNROLL
       for (int a = 0; a < c; a++) {
         double q0 = 0.0, q1 = 0.0;
@@ -216,8 +227,8 @@ struct TensorProductR<3, n, q, c> {
         if (HAS_FLUX) Qs[(1 * c + a) * BLK + (qz * n + qy) * q + qx] = q1;
       }
     }
-    __syncthreads();
-    const bool owner = (qz < n && qy < n && qx < n);
+    jvp_stage_sync<WS>();
+    const bool owner = (on && qz < n && qy < n && qx < n);
     if (owner) {
       SB_UNROLL
       for (int a = 0; a < c; a++) {
@@ -236,9 +247,9 @@ struct TensorProductR<3, n, q, c> {
 
 template <int n, int q, int c>
 struct TensorProductR<2, n, q, c> {
-  template <bool NEED_VALUE, bool NEED_GRAD>
+  template <bool NEED_VALUE, bool NEED_GRAD, bool WS = false>
   static __device__ __forceinline__ void interpolate(const ThreadBasis<2, n, q>& tb, double* s, int qx, int qy, int,
-                                                     double (&val)[c], double (&grad)[c][2])
+                                                     double (&val)[c], double (&grad)[c][2], bool = true)
   {
     constexpr int ndof = n * n;
     const double* u    = s;
@@ -276,10 +287,10 @@ struct TensorProductR<2, n, q, c> {
     }
   }
 
-  template <bool HAS_SOURCE, bool HAS_FLUX>
+  template <bool HAS_SOURCE, bool HAS_FLUX, bool WS = false>
   static __device__ __forceinline__ bool integrate(const ThreadBasis<2, n, q>& tb, double* s, int qx, int qy, int,
                                                    const double (&src)[c], const double (&flux)[c][2],
-                                                   double (&out)[c])
+                                                   double (&out)[c], bool = true)
   {
     double* S = s;
     double* P = S + 3 * c * q * q;
@@ -331,7 +342,11 @@ struct JvpStreamConfig {
   using Base                     = JvpConfig<dim, q, nk, ck, nt, ct, MASK, EPB_>;
   static constexpr int QPE       = Base::QPE;
   static constexpr int EPB       = Base::EPB;
-  static constexpr int threads   = Base::threads;
+  /// lanes per element: a hexahedron with 27 points gets a warp of its own (5 idle lanes).  With 27 lanes per element
+  /// the elements of a CTA straddle its warps, and every shared-memory access of the straddling warp touches two
+  /// elements' blocks: 2.5 wavefronts on average instead of 2 (ncu source page, profiles/r4_summary.md)
+  static constexpr int LPE       = (dim == 3 && Base::DQ_TE == 1 && QPE > 16 && QPE < 32) ? 32 : QPE;
+  static constexpr int threads   = EPB * LPE;
   /// scratch doubles per element: the register-basis contraction of hexahedra pads its arrays to 128-byte lines
   static constexpr int stream_per()
   {
@@ -344,12 +359,14 @@ struct JvpStreamConfig {
   }
   static constexpr int per       = stream_per();
   static constexpr int entries   = Base::layout().entries;
-  static constexpr int tile_doubles = entries * threads;
+  static constexpr int tile_doubles = entries * EPB * QPE;
   /// the bulk copy moves whole 16-byte units
   static constexpr bool supported = (tile_doubles % 2 == 0) && (tile_doubles * 8 < (1 << 20));
   static constexpr int  ndof_k    = ipow(nk, dim);
   static constexpr int  gathers   = EPB * ck * ndof_k;
-  static constexpr int  NG        = (gathers + threads - 1) / threads;  ///< du values each thread prefetches
+  /// an element per warp: the warp gathers its own element's du and nothing but the tile buffer is shared in the CTA
+  static constexpr bool warp_owned = (LPE == 32);
+  static constexpr int  NG = warp_owned ? (ck * ndof_k + 31) / 32 : (gathers + threads - 1) / threads;  ///< du values each thread prefetches
   // smem: [tables 4 x MAX_Q^2][scratch EPB x per (+1 pad to keep the tile 16-byte aligned)][tile][mbarrier]
   static constexpr int scratch_doubles = ((4 * MAX_Q * MAX_Q + EPB * per + 1) / 2) * 2;
   static constexpr size_t smem_bytes   = size_t(scratch_doubles + tile_doubles) * 8 + 16;
@@ -390,8 +407,10 @@ __global__ void __launch_bounds__(JvpStreamConfig<dim, q, nk, ck, nt, ct, MASK, 
     tma::bulk_g2s(tile_s, P.dqf + (long long)tile * C::tile_doubles, tile_bytes, bar);
   }
 
-  const int el    = tid / QPE;
-  const int ql    = tid - el * QPE;
+  const int  el  = tid / C::LPE;
+  const int  ql0 = tid - el * C::LPE;
+  const bool on  = ql0 < QPE;               // (idle lanes shadow the element's last point and store nothing)
+  const int  ql  = on ? ql0 : QPE - 1;
   const int qi[3] = {ql % q, (ql / q) % q, (dim == 3) ? ql / (q * q) : 0};
   const int qx = qi[0], qy = qi[1], qz = qi[2];
 
@@ -407,15 +426,25 @@ __global__ void __launch_bounds__(JvpStreamConfig<dim, q, nk, ck, nt, ct, MASK, 
   const FieldArg& f = P.trial;
   int             g_le[NG], g_node[NG];
   long long       g_comp[NG];
+  int             g_slot[NG];  ///< position in the element's [component][node] block, -1 = none
   SB_UNROLL
   for (int j = 0; j < NG; j++) {
-    const int i   = tid + j * T;
-    const int ii  = (i < C::gathers) ? i : 0;
-    g_le[j]       = ii / (ck * ndk);
-    const int rem = ii - g_le[j] * (ck * ndk);
-    const int a   = rem / ndk;
-    g_node[j]     = rem - a * ndk;
-    g_comp[j]     = a * f.comp_stride;
+    int rem;
+    if constexpr (C::warp_owned) {
+      const int i = ql0 + j * 32;
+      g_le[j]     = el;
+      g_slot[j]   = (i < ck * ndk) ? i : -1;
+      rem         = (i < ck * ndk) ? i : 0;
+    } else {
+      const int i  = tid + j * T;
+      const int ii = (i < C::gathers) ? i : 0;
+      g_le[j]      = ii / (ck * ndk);
+      rem          = ii - g_le[j] * (ck * ndk);
+      g_slot[j]    = (i < C::gathers) ? rem : -1;
+    }
+    const int a = rem / ndk;
+    g_node[j]   = rem - a * ndk;
+    g_comp[j]   = a * f.comp_stride;
   }
   auto gather = [&](int t, double(&v)[NG]) {
     SB_UNROLL
@@ -438,16 +467,15 @@ __global__ void __launch_bounds__(JvpStreamConfig<dim, q, nk, ck, nt, ct, MASK, 
   constexpr bool has_flux   = B::d10 || B::d11;
 
   for (; tile < num_tiles; tile += gridDim.x) {
-    __syncthreads();  // previous tile's integrate has finished reading the scratch
+    constexpr bool WS = C::warp_owned;
+    jvp_stage_sync<WS>();  // previous tile's integrate has finished reading the scratch
     SB_UNROLL
-    for (int j = 0; j < NG; j++) {
-      const int i = tid + j * T;
-      if (i < C::gathers) scratch[g_le[j] * per + (i - g_le[j] * (ck * ndk))] = nxt[j];
-    }
-    __syncthreads();
+    for (int j = 0; j < NG; j++)
+      if (g_slot[j] >= 0) scratch[g_le[j] * per + g_slot[j]] = nxt[j];
+    jvp_stage_sync<WS>();
     double v[ck];
     double g[ck][dim];
-    TPk::template interpolate<(B::d00 || B::d10), (B::d01 || B::d11)>(tbk, scratch + el * per, qx, qy, qz, v, g);
+    TPk::template interpolate<(B::d00 || B::d10), (B::d01 || B::d11), WS>(tbk, scratch + el * per, qx, qy, qz, v, g, on);
 
     const int next = tile + gridDim.x;
     if (next < num_tiles) gather(next, nxt);  // in flight while this tile is contracted and integrated
@@ -498,7 +526,7 @@ __global__ void __launch_bounds__(JvpStreamConfig<dim, q, nk, ck, nt, ct, MASK, 
       tma::bulk_g2s(tile_s, P.dqf + (long long)next * C::tile_doubles, tile_bytes, bar);
     }
     double     out[ct];
-    const bool owner = TPt::template integrate<has_source, has_flux>(tbt, scratch + el * per, qx, qy, qz, src, flux, out);
+    const bool owner = TPt::template integrate<has_source, has_flux, WS>(tbt, scratch + el * per, qx, qy, qz, src, flux, out, on);
     const int  e_raw = tile * EPB + el;
     if (owner && e_raw < P.num_elements) {
       const int elem = P.elements ? P.elements[e_raw] : e_raw;
