@@ -799,10 +799,6 @@ def solver_layer_sample(P, dev, peak):
     n = G.LSize()
     F(0.0, [S, U, A], wrt=1)
     pat, vals = F.assemble(1)
-    ess = np.arange(0, 3 * (n // 3 // 64), dtype=np.int32)
-    capi.eliminate_rows_cols(pat, vals, ess, want_Ae=False)
-    dinv = capi.jacobi_setup(capi.csr_diagonal(pat, vals))
-    y = torch.empty(n, dtype=torch.float64, device=dev)
 
     def timed(fn, reps):
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -814,12 +810,30 @@ def solver_layer_sample(P, dev, peak):
         torch.cuda.synchronize()
         return e0.elapsed_time(e1) / reps
 
+    # assemble(Gradient&) of BASELINE configs[2] (every Newton step pays it): the pattern and the plan exist after the
+    # first call, so this is the fused element-stiffness -> CSR kernel alone (tools/assemble_timing.py
+    # has the comparison with the element-matrix route)
+    timed(lambda: F.assemble(1), 2)
+    assemble_ms = timed(lambda: F.assemble(1), 5)
+    pat, vals = F.assemble(1)
+    ess = np.arange(0, 3 * (n // 3 // 64), dtype=np.int32)
+    capi.eliminate_rows_cols(pat, vals, ess, want_Ae=False)
+    dinv = capi.jacobi_setup(capi.csr_diagonal(pat, vals))
+    y = torch.empty(n, dtype=torch.float64, device=dev)
+
     timed(lambda: capi.csr_spmv(pat, vals, dU, out=y), 3)
     spmv_ms = timed(lambda: capi.csr_spmv(pat, vals, dU, out=y), 10)
     nnz = int(pat.nnz)
     spmv_gbs = (12.0 * nnz + 16.0 * n) / (spmv_ms * 1e-3) / 1e9
     b = y.clone()
     res = {"workload": "eliminated NeoHookean Jacobian of config A", "rows": int(n), "nnz": nnz,
+           "assemble_ms": assemble_ms,
+           "assemble_roofline": {"kernel": "assemble_rows_kernel", "bound": "fp64", "flops": 14189395968.0,
+                                 "achieved_tflops": 14189395968.0 / (assemble_ms * 1e-3) / 1e12, "peak_tflops": 37.1,
+                                 "peak_source": "measured DFMA rate, profiles/r2a_fp64_peak_b200.json",
+                                 "frac": 14189395968.0 / (assemble_ms * 1e-3) / 1e12 / 37.1,
+                                 "limiter": "shared-memory pipe 55%, 15% of it bank conflicts of the row accumulation "
+                                            "(profiles/r4_summary.md)"},
            "spmv_ms": spmv_ms, "spmv_gbs": spmv_gbs, "spmv_frac_of_hbm_peak": spmv_gbs / peak,
            "note": "outside the timed step; 50 iterations each, tolerances 0 so that exactly 50 run"}
     iters = 50

@@ -11,9 +11,9 @@ import sys
 
 HOT = [
     ("evaluation_kernel (config A: SolidMechanics NeoHookean hex p=2, derivative store)", ["evaluation_kernel", "(serac::Geometry)5, 3, 0, serac::H1<2, 3>, serac::H1<1, 3>, serac::H1<2, 3>, serac::H1<2, 3> >, 1, serac::ShapeAwareIntegrandWrapperWithState<serac::MaterialStressFunctor<serac::solid_mechanics::NeoHookean, (serac::FlagMode)2>", "serac::Empty, 1, 16, true>"]),
-    ("jvp_stream_kernel<3,3,3,3,3,3,8> (config A Jacobian action)", ["jvp_stream_kernel<3, 3, 3, 3, 3, 3, 8"]),
+    ("jvp_stream_kernel<3,3,3,3,3,3,24,2,5> (config A Jacobian action, symmetric tangent storage)", ["jvp_stream_kernel<3, 3, 3, 3, 3, 3, 24"]),
     ("scatter_kernel<false, true> (node-major E-vector)", ["scatter_kernel<false, true>"]),
-    ("assemble_rows_kernel (config A fused assembly)", ["assemble_rows_kernel<3, 3, 3, 3, 3, 8"]),
+    ("assemble_rows_kernel (config A fused assembly, symmetric tangent storage)", ["assemble_rows_kernel<3, 3, 3, 3, 3, 24"]),
     ("cg_spmv_dot_kernel", ["cg_spmv_dot_kernel"]),
     ("csr_spmv_kernel", ["csr_spmv_kernel"]),
 ]
