@@ -69,13 +69,13 @@ err = float(np.linalg.norm(Acsr @ dU.cpu().numpy() - jvp) / np.linalg.norm(jvp))
 fma_per_unit = 9 * (27 * 18 + 9 * 27 + 9 * 18)
 flops = 2.0 * P["ne"] * 27 * fma_per_unit
 fp64_peak_tflops = 37.1  # profiles/r2a_fp64_peak_b200.json (tools/fp64_peak.cu on this pool's B200)
-hbm_bytes = P["ne"] * 27 * 648.0 + pat.nnz * 8.0 + P["ne"] * 729 * 2.0
+hbm_bytes = P["ne"] * 27 * 8.0 * I.derivative_stored_entries(1) + pat.nnz * 8.0 + P["ne"] * 729 * 2.0
 hbm_peak = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"] if os.path.exists(os.path.join(ROOT, "MEASURED_PEAKS.json")) else 6650.0
 out = dict(config="config A: 32768 hexes, H1 p=2, NeoHookean", nnz=int(pat.nnz), rows=int(pat.num_rows),
            first_assemble_with_pattern_and_plan_ms=first_ms, assemble_ms=assemble_ms,
            generic_route=dict(element_gradient_ms=eg_ms - zero_ms, K_e_GB=K_e.numel() * 8 / 1e9, csr_gather_ms=csr_ref_ms),
            fused_vs_generic_rel=rel, matrix_vs_action_rel=err,
-           roofline_assemble=dict(kernel="assemble_rows_kernel<3,3,3,3,3,8,4>", bound="fp64", flops=flops,
+           roofline_assemble=dict(kernel=f"assemble_rows_kernel<3,3,3,3,3,{I.derivative_mask(1)},*>", bound="fp64", flops=flops,
                                   achieved_tflops=flops / (assemble_ms * 1e-3) / 1e12, peak_tflops=fp64_peak_tflops,
                                   frac=flops / (assemble_ms * 1e-3) / 1e12 / fp64_peak_tflops,
                                   hbm_algorithmic_bytes=hbm_bytes, hbm_achieved_gbs=hbm_bytes / (assemble_ms * 1e-3) / 1e9,
