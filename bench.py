@@ -837,12 +837,18 @@ def solver_layer_sample(P, dev, peak):
            "spmv_ms": spmv_ms, "spmv_gbs": spmv_gbs, "spmv_frac_of_hbm_peak": spmv_gbs / peak,
            "note": "outside the timed step; 50 iterations each, tolerances 0 so that exactly 50 run"}
     iters = 50
-    for name, solver, kw in (("cg_jacobi", capi.CGSolver(n, rel_tol=0.0, abs_tol=0.0, max_iter=iters, check_every=10), {}),
-                             ("gmres50_jacobi", capi.GMRESSolver(n, kdim=50, rel_tol=0.0, abs_tol=0.0, max_iter=iters), {})):
-        solver.Mult(pat, b, values=vals, dinv=dinv)  # warm-up
+    # the same Jacobi-preconditioned CG matrix-free: [J_ii 0; 0 I] through Gradient::Mult (the streaming Jacobian action
+    # + scatter) instead of the assembled matrix -- what a Newton-Krylov step costs when nothing is assembled
+    op = capi.GradientOperator(F, 1, ess)
+    for name, solver, operator in (
+            ("cg_jacobi", capi.CGSolver(n, rel_tol=0.0, abs_tol=0.0, max_iter=iters, check_every=10), pat),
+            ("cg_jacobi_matrix_free", capi.CGSolver(n, rel_tol=0.0, abs_tol=0.0, max_iter=iters, check_every=10), op),
+            ("gmres50_jacobi", capi.GMRESSolver(n, kdim=50, rel_tol=0.0, abs_tol=0.0, max_iter=iters), pat)):
+        kw = dict(values=vals) if operator is pat else {}
+        solver.Mult(operator, b, dinv=dinv, **kw)  # warm-up
         capi.lib().sb_launch_count_reset()
         box = {}
-        ms = timed(lambda: box.update(info=solver.Mult(pat, b, values=vals, dinv=dinv)[1]), 1)
+        ms = timed(lambda: box.update(info=solver.Mult(operator, b, dinv=dinv, **kw)[1]), 1)
         info = box["info"]
         res[name] = {"iterations": int(info["final_iter"]), "ms_per_iteration": ms / max(int(info["final_iter"]), 1),
                      "launches": int(capi.lib().sb_launch_count()),
