@@ -299,3 +299,33 @@ def test_geometric_factors_refresh_after_node_move():
     r_moved = P.F(0.0, [torch.zeros_like(shape), P.U, P.A])
     assert rel_l2(r_moved.cpu().numpy(), r_shape.cpu().numpy()) < 1e-12
     assert rel_l2(r_moved.cpu().numpy(), prob["r"]) > 1e-3  # the move really changed the answer
+
+
+def test_symmetric_tangent_storage(cuda):
+    """hyperelastic flux tangents are stored as their upper triangle (45 of 81 doubles per point), chosen
+    per integral from the functor's geometric-nonlinearity flag; everything else stays in the reference's full layout.
+    The exported (expanded) derivative is exactly symmetric, and equal to the dual-number derivative to rounding
+    (test_tangent_fast_path_matches_dual_number_path)."""
+    prob = load_golden("solid_neohookean_hex_p2_patch")
+    assert float(prob["params"][3]) == 1.0  # geometric nonlinearity on
+    P = Product(prob, cuda)
+    I, capi = P.integral, P.capi
+    assert (I.derivative_entries(1), I.derivative_stored_entries(1), I.derivative_mask(1)) == (81, 45, 8 | 16)
+    assert I.derivative_stored_entries(0) == I.derivative_entries(0)  # w.r.t. the shape field: not symmetric, full
+    P.F(0.0, [P.S, P.U, P.A], wrt=1)
+    D = I.export_derivatives(1).cpu().numpy().reshape(-1, 9, 9)
+    assert np.abs(D).max() > 0 and np.array_equal(D, D.transpose(0, 2, 1))
+    ne = int(prob["ne"])
+    # NeoHookean without geometric nonlinearity: flux = Cauchy stress of du_dX, whose tangent is not symmetric -> full
+    off = list(np.asarray(prob["params"], dtype=float))
+    off[3] = 0.0
+    I_off = capi.Integral("solid_neohookean_hex_p2", off, P.X_q, P.J_q, ne)
+    assert (I_off.derivative_stored_entries(1), I_off.derivative_mask(1)) == (81, 8)
+    # linear isotropic elasticity: symmetric small-strain moduli -> upper triangle without geometric nonlinearity only
+    I_lin0 = capi.Integral("solid_linear_isotropic_hex_p2", off, P.X_q, P.J_q, ne)
+    I_lin1 = capi.Integral("solid_linear_isotropic_hex_p2", list(prob["params"]), P.X_q, P.J_q, ne)
+    assert (I_lin0.derivative_stored_entries(1), I_lin0.derivative_mask(1)) == (45, 8 | 16)
+    assert (I_lin1.derivative_stored_entries(1), I_lin1.derivative_mask(1)) == (81, 8)
+    # ... and the dual-number twin of the integrand never uses it
+    ad = Product(prob, cuda, name_suffix="_ad")
+    assert ad.integral.derivative_stored_entries(1) == 81
