@@ -1060,6 +1060,32 @@ SB_HD DerivativeLayout make_layout(int ct, int ck, int dim, bool d00, bool d01, 
   return L;
 }
 
+/// compile-time check of the symmetric packing: i11 is symmetric under (a,k) <-> (b,l) and maps the upper triangle one to
+/// one onto [offset[3], offset[3] + N (N + 1) / 2)
+SB_HD bool symmetric_layout_is_consistent(int c, int dim)
+{
+  const DerivativeLayout L = make_layout(c, c, dim, false, false, false, true, true);
+  const int              N = c * dim;
+  if (!L.sym || L.entries != N * (N + 1) / 2) return false;
+  int next = 0;  // the upper triangle in row-major order must come out as 0, 1, 2, ...
+  for (int i = 0; i < N; i++) {
+    for (int j = 0; j < N; j++) {
+      const int ij = L.i11(i / dim, i % dim, j / dim, j % dim), ji = L.i11(j / dim, j % dim, i / dim, i % dim);
+      if (ij != ji || ij < 0 || ij >= L.entries) return false;
+      if (j >= i && ij != next++) return false;
+      if (L.stores11(i / dim, i % dim, j / dim, j % dim) != (i <= j)) return false;
+    }
+  }
+  return next == L.entries;
+}
+static_assert(symmetric_layout_is_consistent(3, 3) && symmetric_layout_is_consistent(2, 2) &&
+                  symmetric_layout_is_consistent(1, 3) && symmetric_layout_is_consistent(3, 2),
+              "DerivativeLayout: symmetric d11 packing");
+static_assert(make_layout(3, 3, 3, false, false, false, true, true).entries == 45 &&
+                  make_layout(3, 3, 3, false, false, false, true, false).entries == 81 &&
+                  !make_layout(3, 1, 3, false, false, false, true, true).sym,
+              "DerivativeLayout: 45 of 81 entries for a 3-D vector field; rectangular blocks stay full");
+
 // ---- calling the q-function -------------------------------------------------------------------
 template <typename QF, typename Pos, typename State, typename... Args>
 SERAC_HOST_DEVICE inline auto call_qf(const QF& qf, double t, const Pos& x, State& state, const Args&... args)
