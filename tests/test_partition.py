@@ -162,3 +162,49 @@ def test_distributed_residual_over_gloo(world, ranks):
     for pr in procs:
         pr.join(timeout=60)
     assert all(msg == "ok" for _, msg in res), res
+
+
+@pytest.mark.parametrize("mesh_n,p", [((7, 7, 7), 3), ((5, 4, 3), 3), ((7, 6, 5), 2)])
+def test_exchange_lists_of_uneven_2x2x2_partitions(mesh_n, p):
+    """The shape of the strong config-B series at 8 GPUs (BASELINE configs[4]: 135 = 68 + 67 hexes per direction, p = 3):
+    boxes of unequal size, seven neighbours per rank incl. edge and corner neighbours.  All eight ranks in one process:
+    P and P^T are played through the exchange lists exactly as the device kernels use them (owner -> sharers by send /
+    recv segments, sharers -> owner in ascending slot order) and compared with the global vectors."""
+    ranks = (2, 2, 2)
+    mesh = StructuredHexMesh(*mesh_n)
+    parts = [Partition(mesh, ranks, r, p, components=3, owned_first=True) for r in range(8)]
+    lists = [pt.halo_lists() for pt in parts]
+    nglob = mesh.num_nodes(p) * 3
+    assert {pt.num_elements for pt in parts} != {mesh.ne // 8}, "the boxes are meant to differ in size"
+    rng = np.random.default_rng(1)
+    g = rng.uniform(-1, 1, nglob)
+
+    def segment(l, key_off, i):
+        return slice(int(l[key_off][i]), int(l[key_off][i + 1]))
+
+    # ---- P: every local copy equals the global value; owned-first numbering: the T-vector is the prefix ----
+    Ls = []
+    for r, (pt, l) in enumerate(zip(parts, lists)):
+        L = np.full(l["lsize"], np.nan)
+        L[:l["tsize"]] = g[pt.global_true_vdofs()]
+        assert np.array_equal(l["ltdof"][:l["tsize"]], np.arange(l["tsize"]))  # in place: T is the prefix of L
+        Ls.append(L)
+    for r, l in enumerate(lists):  # owner r -> sharer s
+        for i, s in enumerate(l["neighbors"]):
+            j = list(lists[s]["neighbors"]).index(r)
+            sent = Ls[r][:l["tsize"]][l["send_idx"][segment(l, "send_off", i)]]
+            Ls[s][lists[s]["recv_idx"][segment(lists[s], "recv_off", j)]] = sent
+    for pt, L in zip(parts, Ls):
+        assert np.array_equal(L, g[pt.global_local_vdofs()])
+    # ---- P^T: the owner adds every sharer's partial sum; the result is the sum over all copies ----
+    parts_L = [rng.uniform(-1, 1, l["lsize"]) for l in lists]
+    tot = np.zeros(nglob)
+    for pt, L in zip(parts, parts_L):
+        np.add.at(tot, pt.global_local_vdofs(), L)
+    for r, (pt, l) in enumerate(zip(parts, lists)):
+        T = parts_L[r][:l["tsize"]].copy()
+        for i, s in enumerate(l["neighbors"]):  # fixed neighbour order
+            j = list(lists[s]["neighbors"]).index(r)
+            theirs = parts_L[s][lists[s]["recv_idx"][segment(lists[s], "recv_off", j)]]
+            np.add.at(T, l["send_idx"][segment(l, "send_off", i)], theirs)
+        assert np.allclose(T, tot[pt.global_true_vdofs()], rtol=0, atol=1e-13)
