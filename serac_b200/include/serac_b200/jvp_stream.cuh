@@ -2,7 +2,9 @@
 //
 // Same arithmetic as jvp_kernel (domain_integral.cuh; reference: action_of_gradient_kernel,
 // src/serac/numerics/functional/domain_integral_kernels.hpp:277-304 with chain_rule :223-237), different data movement.
-// The kernel is HBM-bound on the stored derivatives (648 of 666 B per quadrature point for solids), so:
+// With the reference's full derivative layout the kernel is HBM-bound on the stored derivatives (648 of 666 B per
+// quadrature point for solids); with symmetric tangent storage (DerivativeLayout::sym, 360 B) it runs at the shared-memory
+// pipe (profiles/r4_summary.md).  So:
 //   * CTAs are persistent (grid = resident CTAs x SMs) and walk the derivative tiles round-robin;
 //   * each tile -- [entry][lane] doubles, contiguous in HBM -- is brought into shared memory by ONE bulk async copy
 //     (cp.async.bulk / TMA, completion on an mbarrier), issued a whole tile ahead of its use, so the copy engine keeps
@@ -10,7 +12,9 @@
 //   * the du gather of tile i+1 (table -> L dependent loads) is issued into registers while tile i is contracted and
 //     integrated, so its latency never sits on the critical path;
 //   * the 1-D basis rows / columns every thread needs live in registers for the whole kernel (the sum-factorised
-//     stages then cost one shared-memory load per FMA instead of two).
+//     stages then cost one shared-memory load per FMA instead of two);
+//   * a 27-point hexahedron is one warp's own (JvpStreamConfig::LPE): its scratch blocks start on 128-byte lines, the
+//     stages exchange through __syncwarp, and only the tile buffer is shared by the CTA's warps.
 #pragma once
 
 #include <cstdint>
